@@ -1,0 +1,772 @@
+// libdavo_b200.so -- C ABI (include/davo_b200.h) over the sm_100a kernels.
+// Host side: variant config -> layer plans (K-step tables, TF32 weight packing,
+// TMA tensor maps) -> per-micro-batch launch sequence.
+#include "../../include/davo_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "frontend.cuh"
+
+using namespace davo;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+// TF 'SAME' (asymmetric) padding: out = ceil(in / stride), pad_before = total / 2.
+struct SamePad { int out, before, after; };
+SamePad same_pad(int in, int k, int stride, int dil) {
+  SamePad s;
+  s.out = (in + stride - 1) / stride;
+  int eff = (k - 1) * dil + 1;
+  int total = (s.out - 1) * stride + eff - in;
+  if (total < 0) total = 0;
+  s.before = total / 2;
+  s.after = total - s.before;
+  return s;
+}
+
+float host_round_tf32(float x) {   // cvt.rna.tf32.f32
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+int posmod(int a, int b) { return a - floordiv(a, b) * b; }
+
+struct Layer {
+  const char* name;
+  int k, stride, dil;
+  int Hin, Win, Cin_total;     // input tensor
+  int Cin_g, groups;           // channels reduced per group
+  int BN;                      // output channels per group (= MMA N)
+  int Hout, Wout, out_stride;
+  int pad_t, pad_l;
+  int epi;
+  int tiles_h, tiles_w;
+  // device
+  float* d_in = nullptr;
+  float* d_out = nullptr;
+  float* d_wpack = nullptr;    // [groups][n_ksteps][BN][32]
+  float* d_bias = nullptr;     // [groups*BN]
+  float* d_whwio[2] = {nullptr, nullptr};   // unpacked HWIO per group (direct debug path)
+  int cmap[16];
+  int use_cmap = 0;
+  int Cin_w = 0;               // weight input channels (HWIO 'I')
+  CUtensorMap tmA, tmB;
+  ConvParams prm;
+};
+
+}  // namespace
+
+struct davo_ctx {
+  davo_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  std::map<std::string, HostTensor> weights;
+  bool finalized = false;
+  int mb = 0;                       // frame pairs per micro-batch
+  int conv_impl = 0;                // 0 tcgen05 (product), 1 direct fp32 (debug cross-check)
+  std::vector<Layer> layers;        // cnv1..cnv7
+  // device buffers
+  std::vector<void*> allocs;
+  float *d_pool = nullptr, *d_attw = nullptr, *d_packed = nullptr, *d_sum7 = nullptr;
+  float *d_sew = nullptr, *d_staticw = nullptr, *d_wpred = nullptr, *d_bpred = nullptr;
+  float* d_c7tmp = nullptr;         // direct path only
+  int nparts7 = 0;
+  // host-buffer entry point staging
+  uint8_t* s_img = nullptr; float *s_flow = nullptr, *s_seg = nullptr, *s_pose = nullptr;
+  // last forward
+  int last_launches = 0;
+  int last_npairs_mb = 0;
+  const uint8_t* last_img = nullptr; const float* last_flow = nullptr; const float* last_seg = nullptr;
+  float* last_pose = nullptr; int last_B = 0;
+};
+
+namespace {
+
+int fail(davo_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU_OK(call)                                                                      \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(ctx, DAVO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int dev_alloc(davo_ctx* ctx, void** p, size_t bytes) {
+  CU_OK(cudaMalloc(p, bytes));
+  CU_OK(cudaMemset(*p, 0, bytes));
+  ctx->allocs.push_back(*p);
+  return 0;
+}
+
+const HostTensor* find_w(davo_ctx* ctx, const std::string& name) {
+  auto it = ctx->weights.find(name);
+  return it == ctx->weights.end() ? nullptr : &it->second;
+}
+
+bool shape_is(const HostTensor* t, std::initializer_list<int64_t> s) {
+  if (!t || t->shape.size() != s.size()) return false;
+  size_t i = 0;
+  for (int64_t v : s) if (t->shape[i++] != v) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------- layer plan --
+// Builds the K-step table and packs weights for one conv layer.
+// getw(g, ty, tx, ci, n): HWIO weight of group g (ci = weight input channel).
+template <class GetW>
+int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bias_host) {
+  std::vector<KStep> ks;
+  // For every K-step, its 32 reduction entries as (ty, tx, ci) or invalid (-1).
+  struct Ent { int ty, tx, ci; };
+  std::vector<std::vector<Ent>> ents;
+  const bool strided = L.stride == 2;
+  if (L.stride != 1 && L.stride != 2) return fail(ctx, DAVO_ERR_ARG, "%s: stride %d unsupported", L.name, L.stride);
+  if (strided && (L.dil != 1 || (L.Hin & 1) || (L.Win & 1)))
+    return fail(ctx, DAVO_ERR_ARG, "%s: stride-2 layer needs even input size and dilation 1", L.name);
+  const bool pair_slab = strided && L.Cin_total == 16;
+  if (!pair_slab && (L.Cin_g % 32) != 0)
+    return fail(ctx, DAVO_ERR_ARG, "%s: %d input channels per group is not a multiple of 32", L.name, L.Cin_g);
+  for (int ty = 0; ty < L.k; ++ty) {
+    const int dy = ty * L.dil - L.pad_t;
+    const int dh = strided ? floordiv(dy, 2) : dy;
+    const int par = strided ? posmod(dy, 2) : 0;
+    if (pair_slab) {
+      // one K-step = two horizontally adjacent input pixels x 16 channels
+      const int dx_lo = -L.pad_l, dx_hi = L.k - 1 - L.pad_l;
+      for (int w2 = floordiv(dx_lo, 2); w2 <= floordiv(dx_hi, 2); ++w2) {
+        KStep s{};
+        s.c = 0; s.dw = (int8_t)w2; s.par = (int8_t)par; s.dh = (int8_t)dh;
+        std::vector<Ent> e(32);
+        for (int kk = 0; kk < 32; ++kk) {
+          const int wp = kk / 16, ch = kk % 16;
+          const int tx = 2 * w2 + wp + L.pad_l;
+          int ci = -1;
+          if (tx >= 0 && tx < L.k) {
+            if (L.use_cmap) { for (int i = 0; i < L.Cin_w; ++i) if (L.cmap[i] == ch) ci = i; }
+            else if (ch < L.Cin_w) ci = ch;
+          }
+          e[kk] = Ent{ty, tx, ci};
+        }
+        ks.push_back(s);
+        ents.push_back(e);
+      }
+    } else {
+      for (int tx = 0; tx < L.k; ++tx) {
+        const int dx = tx * L.dil - L.pad_l;
+        const int dw = strided ? floordiv(dx, 2) : dx;
+        const int wp = strided ? posmod(dx, 2) : 0;
+        for (int sl = 0; sl < L.Cin_g / 32; ++sl) {
+          KStep s{};
+          s.c = (int16_t)(wp * L.Cin_total + sl * 32);
+          s.dw = (int8_t)dw; s.par = (int8_t)par; s.dh = (int8_t)dh;
+          std::vector<Ent> e(32);
+          for (int kk = 0; kk < 32; ++kk) e[kk] = Ent{ty, tx, sl * 32 + kk};
+          ks.push_back(s);
+          ents.push_back(e);
+        }
+      }
+    }
+  }
+  const int nk = (int)ks.size();
+  if (nk > kMaxKSteps) return fail(ctx, DAVO_ERR_ARG, "%s: %d K-steps exceed the table (%d)", L.name, nk, kMaxKSteps);
+  // pack B: [g][k][n][32], TF32-rounded
+  std::vector<float> pack((size_t)L.groups * nk * L.BN * 32, 0.f);
+  for (int g = 0; g < L.groups; ++g)
+    for (int k = 0; k < nk; ++k)
+      for (int n = 0; n < L.BN; ++n)
+        for (int kk = 0; kk < 32; ++kk) {
+          const Ent& e = ents[k][kk];
+          float v = 0.f;
+          if (e.ci >= 0) v = getw(g, e.ty, e.tx, e.ci, n);
+          pack[(((size_t)g * nk + k) * L.BN + n) * 32 + kk] = host_round_tf32(v);
+        }
+  if (int rc = dev_alloc(ctx, (void**)&L.d_wpack, pack.size() * 4)) return rc;
+  CU_OK(cudaMemcpy(L.d_wpack, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice));
+  if (int rc = dev_alloc(ctx, (void**)&L.d_bias, bias_host.size() * 4)) return rc;
+  CU_OK(cudaMemcpy(L.d_bias, bias_host.data(), bias_host.size() * 4, cudaMemcpyHostToDevice));
+  // unpacked HWIO copies for the direct cross-check path
+  for (int g = 0; g < L.groups; ++g) {
+    std::vector<float> hw((size_t)L.k * L.k * L.Cin_w * L.BN);
+    for (int ty = 0; ty < L.k; ++ty)
+      for (int tx = 0; tx < L.k; ++tx)
+        for (int ci = 0; ci < L.Cin_w; ++ci)
+          for (int n = 0; n < L.BN; ++n)
+            hw[(((size_t)ty * L.k + tx) * L.Cin_w + ci) * L.BN + n] = host_round_tf32(getw(g, ty, tx, ci, n));
+    if (int rc = dev_alloc(ctx, (void**)&L.d_whwio[g], hw.size() * 4)) return rc;
+    CU_OK(cudaMemcpy(L.d_whwio[g], hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // kernel parameters
+  ConvParams& P = L.prm;
+  memset(&P, 0, sizeof P);
+  P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.groups = L.groups;
+  P.Hout = L.Hout; P.Wout = L.Wout; P.out_stride = L.out_stride;
+  P.cin_group_off = L.Cin_g;
+  P.n_ksteps = nk;
+  P.bias = L.d_bias;
+  for (int k = 0; k < nk; ++k) P.ks[k] = ks[k];
+  // tensor maps
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  {
+    const cuuint64_t C = L.Cin_total, H = L.Hin, W = L.Win, N = ctx->mb;
+    cuuint64_t dims[5], strides[4];
+    if (strided) {
+      dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
+      strides[0] = 2 * C * 4; strides[1] = W * C * 4; strides[2] = 2 * W * C * 4; strides[3] = H * W * C * 4;
+    } else {
+      dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
+      strides[0] = C * 4; strides[1] = W * C * 4; strides[2] = W * C * 4; strides[3] = H * W * C * 4;
+    }
+    const cuuint32_t box[5] = {32, (cuuint32_t)kTileW, 1, (cuuint32_t)kTileH, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&L.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, L.d_in, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) -> %d", L.name, (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {32, (cuuint64_t)L.groups * nk * L.BN};
+    cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)L.BN};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, L.d_wpack, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(B) -> %d", L.name, (int)r);
+  }
+  return 0;
+}
+
+template <int BN, int EPI>
+int launch_conv_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  ConvParams P = L.prm;
+  P.num_tiles = npairs * L.groups * L.tiles_h * L.tiles_w;
+  P.out = L.d_out;
+  P.sum_out = ctx->d_sum7;
+  const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
+  conv_tc_kernel<BN, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(L.tmA, L.tmB, P);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  if (L.epi == EPI_SUM_RELU) {
+    if (L.BN == 256) return launch_conv_t<256, EPI_SUM_RELU>(ctx, L, npairs, st);
+    return fail(ctx, DAVO_ERR_ARG, "%s: sum epilogue built for N=256 only", L.name);
+  }
+  switch (L.BN) {
+    case 16: return launch_conv_t<16, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 32: return launch_conv_t<32, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 64: return launch_conv_t<64, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 128: return launch_conv_t<128, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 256: return launch_conv_t<256, EPI_STORE_RELU>(ctx, L, npairs, st);
+  }
+  return fail(ctx, DAVO_ERR_ARG, "%s: N=%d has no kernel instance", L.name, L.BN);
+}
+
+int launch_conv_direct(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  for (int g = 0; g < L.groups; ++g) {
+    DirectConvParams p;
+    memset(&p, 0, sizeof p);
+    p.npairs = npairs; p.Hin = L.Hin; p.Win = L.Win; p.Cin_total = L.Cin_total;
+    p.cin_off = g * L.Cin_g; p.Cin = L.Cin_w;
+    p.Hout = L.Hout; p.Wout = L.Wout; p.Cout = L.BN;
+    p.kh = p.kw = L.k; p.stride = L.stride; p.dil = L.dil; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
+    p.relu = 1;
+    p.use_cmap = L.use_cmap;
+    for (int i = 0; i < 16; ++i) p.cmap[i] = L.cmap[i];
+    p.in = L.d_in; p.w = L.d_whwio[g]; p.bias = L.d_bias + g * L.BN;
+    if (L.epi == EPI_SUM_RELU) {
+      p.out = ctx->d_c7tmp; p.out_stride = L.groups * L.BN; p.cout_off = g * L.BN; p.round_out = 0;
+    } else {
+      p.out = L.d_out; p.out_stride = L.out_stride; p.cout_off = g * L.BN; p.round_out = 1;
+    }
+    const long long total = (long long)npairs * L.Hout * L.Wout * L.BN;
+    conv_direct_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+    CU_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+__global__ void sum7_direct_kernel(const float* in, int hw, int nparts, float* out) {
+  // in [n][hw][512] -> out [n][2][nparts][256]; row 0 holds the sum, the rest zeros.
+  const int n = blockIdx.x, br = blockIdx.y, c = threadIdx.x;
+  float a = 0.f;
+  for (int i = 0; i < hw; ++i) a += in[((size_t)n * hw + i) * 512 + br * 256 + c];
+  float* o = out + ((size_t)(n * 2 + br) * nparts) * 256 + c;
+  o[0] = a;
+  for (int i = 1; i < nparts; ++i) o[(size_t)i * 256] = 0.f;
+}
+
+int launch_front(davo_ctx* ctx, int pair0, int npairs, const uint8_t* img, const float* flow,
+                 const float* seg, cudaStream_t st, int* launches) {
+  const davo_config& c = ctx->cfg;
+  FrontParams fp;
+  memset(&fp, 0, sizeof fp);
+  fp.H = c.H; fp.W = c.W; fp.pair0 = pair0; fp.npairs = npairs;
+  fp.in_mode = c.in_mode; fp.att_src = c.att_src; fp.att_tgt_ones = c.att_tgt_ones;
+  fp.mask_rgb = c.mask_mode != 0;
+  fp.mask_flow = c.mask_mode == 2;
+  fp.se_act = c.se_act; fp.flow_abs = c.flow_abs; fp.flow_norm = c.flow_norm;
+  fp.img = img; fp.flow = flow; fp.seg = seg;
+  fp.se_w = ctx->d_sew; fp.static_w = ctx->d_staticw;
+  fp.pool_part = ctx->d_pool; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
+  if (c.att_src == 1) {
+    se_pool_kernel<<<dim3(kPoolSplits, npairs), 256, 0, st>>>(fp);
+    CU_OK(cudaGetLastError());
+    ++*launches;
+  }
+  const int hw = c.H * c.W;
+  pack_kernel<<<dim3((hw * 4 + 255) / 256, npairs), 256, 0, st>>>(fp);
+  CU_OK(cudaGetLastError());
+  ++*launches;
+  return 0;
+}
+
+int launch_head(davo_ctx* ctx, int pair0, int npairs, float* pose_out, cudaStream_t st, int* launches) {
+  const Layer& L7 = ctx->layers.back();
+  HeadParams hp;
+  hp.pair0 = pair0; hp.npairs = npairs; hp.nparts = ctx->nparts7;
+  hp.inv_hw = 1.0f / (float)(L7.Hout * L7.Wout);
+  hp.sums = ctx->d_sum7; hp.wpred = ctx->d_wpred; hp.bpred = ctx->d_bpred; hp.pose_out = pose_out;
+  head_kernel<<<npairs, 256, 0, st>>>(hp);
+  CU_OK(cudaGetLastError());
+  ++*launches;
+  return 0;
+}
+
+int run_microbatch(davo_ctx* ctx, int pair0, int npairs, const uint8_t* img, const float* flow,
+                   const float* seg, float* pose_out, cudaStream_t st, int* launches) {
+  if (int rc = launch_front(ctx, pair0, npairs, img, flow, seg, st, launches)) return rc;
+  for (Layer& L : ctx->layers) {
+    int rc = ctx->conv_impl == 0 ? launch_conv(ctx, L, npairs, st) : launch_conv_direct(ctx, L, npairs, st);
+    if (rc) return rc;
+    *launches += (ctx->conv_impl == 0) ? 1 : L.groups;
+  }
+  const Layer& L7 = ctx->layers.back();
+  if (ctx->conv_impl != 0) {
+    sum7_direct_kernel<<<dim3(npairs, 2), 256, 0, st>>>(ctx->d_c7tmp, L7.Hout * L7.Wout, ctx->nparts7, ctx->d_sum7);
+    CU_OK(cudaGetLastError());
+    ++*launches;
+  }
+  return launch_head(ctx, pair0, npairs, pose_out, st, launches);
+}
+
+}  // namespace
+
+// =============================================================== C ABI ========
+
+extern "C" const char* davo_build_info(void) {
+  return "davo_b200 sm_100a tcgen05/TMA, nvcc " __DATE__;
+}
+
+extern "C" const char* davo_last_error(const davo_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
+  davo_ctx* ctx = nullptr;   // errors before allocation go to the thread-local slot
+  if (!cfg || !out) return fail(nullptr, DAVO_ERR_ARG, "davo_create: null argument");
+  *out = nullptr;
+  if (cfg->posenn != 0)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d is not built (only decouple_sharednet_v0_dilation)", cfg->posenn);
+  if (cfg->posenn_se != 0)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built", cfg->posenn_se);
+  if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: H and W must be positive multiples of 8 (got %dx%d)", cfg->H, cfg->W);
+  if (cfg->max_batch <= 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: max_batch must be positive");
+  if (cfg->cnv6_out != 128 && cfg->cnv6_out != 64 && cfg->cnv6_out != 32)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128)", cfg->cnv6_out);
+  if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
+  if (cfg->att_src < 0 || cfg->att_src > 2) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, DAVO_ERR_CUDA, "davo_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, DAVO_ERR_ARG, "davo_create: device %d out of range", device);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, DAVO_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, DAVO_ERR_CUDA, "davo_create: device is sm_%d%d; this library is sm_100a only", prop.major, prop.minor);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, DAVO_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  ctx = new davo_ctx();
+  ctx->cfg = *cfg;
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  int mb = cfg->micro_batch > 0 ? cfg->micro_batch : 34;
+  if (mb > 2 * cfg->max_batch) mb = 2 * cfg->max_batch;
+  ctx->mb = mb;
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void davo_destroy(davo_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->s_img) cudaFree(ctx->s_img);
+  if (ctx->s_flow) cudaFree(ctx->s_flow);
+  if (ctx->s_seg) cudaFree(ctx->s_seg);
+  if (ctx->s_pose) cudaFree(ctx->s_pose);
+  delete ctx;
+}
+
+extern "C" int davo_set_weight(davo_ctx* ctx, const char* name, const float* host,
+                               const int64_t* shape, int rank) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!name || !host || !shape || rank < 1 || rank > 4) return fail(ctx, DAVO_ERR_ARG, "davo_set_weight: bad argument");
+  if (ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_set_weight: weights already finalized");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < rank; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.data.assign(host, host + n);
+  ctx->weights[name] = std::move(t);
+  return 0;
+}
+
+extern "C" int davo_finalize_weights(davo_ctx* ctx) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_finalize_weights: already finalized");
+  CU_OK(cudaSetDevice(ctx->device));
+  const davo_config& c = ctx->cfg;
+  const int mb = ctx->mb;
+  const std::string P = "pose_exp_net/";
+  const int c6 = c.cnv6_out;
+  const int cin1 = c.in_mode == 1 ? 10 : 6;
+
+  // ---- activation geometry (TF SAME) ----
+  struct Geo { int k, stride, dil; };
+  const Geo geo[7] = {{7, 2, 1}, {5, 2, 1}, {3, 1, 2}, {3, 1, 4}, {3, 1, 8}, {3, 1, 2}, {3, 2, 1}};
+  const int cout_total[7] = {16, 32, 64, 128, 256, 2 * c6, 512};
+  const int bn[7] = {16, 32, 64, 128, 256, 2 * c6, 256};
+  const int groups[7] = {1, 1, 1, 1, 1, 1, 2};
+  const int cin_total[7] = {16, 16, 32, 64, 128, 256, 2 * c6};
+  const int cin_g[7] = {16, 16, 32, 64, 128, 256, c6};
+  const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c6};
+  const char* names[7] = {"cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6", "cnv7"};
+  ctx->layers.resize(7);
+  int H = c.H, W = c.W;
+  for (int i = 0; i < 7; ++i) {
+    Layer& L = ctx->layers[i];
+    L.name = names[i];
+    L.k = geo[i].k; L.stride = geo[i].stride; L.dil = geo[i].dil;
+    L.Hin = H; L.Win = W; L.Cin_total = cin_total[i]; L.Cin_g = cin_g[i]; L.groups = groups[i];
+    L.Cin_w = cin_w[i];
+    L.BN = bn[i];
+    SamePad ph = same_pad(H, L.k, L.stride, L.dil), pw = same_pad(W, L.k, L.stride, L.dil);
+    L.Hout = ph.out; L.Wout = pw.out; L.pad_t = ph.before; L.pad_l = pw.before;
+    L.out_stride = cout_total[i];
+    L.epi = (i == 6) ? EPI_SUM_RELU : EPI_STORE_RELU;
+    L.tiles_h = (L.Hout + kTileH - 1) / kTileH;
+    L.tiles_w = (L.Wout + kTileW - 1) / kTileW;
+    for (int j = 0; j < 16; ++j) L.cmap[j] = j;
+    H = L.Hout; W = L.Wout;
+  }
+  // cnv1 reads the 16-channel packed input: [tgt rgb, 0 0, src rgb, src flow, 0 x 6]
+  if (c.in_mode == 0) {
+    Layer& L = ctx->layers[0];
+    L.use_cmap = 1;
+    const int m[6] = {0, 1, 2, 5, 6, 7};
+    for (int j = 0; j < 6; ++j) L.cmap[j] = m[j];
+  }
+
+  // ---- workspace ----
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_pool, (size_t)mb * kPoolSplits * 2 * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * kNumClasses * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_packed, (size_t)mb * c.H * c.W * kPackedC * 4)) return rc;
+  float* prev = ctx->d_packed;
+  for (int i = 0; i < 7; ++i) {
+    Layer& L = ctx->layers[i];
+    L.d_in = prev;
+    if (i < 6) {
+      if (int rc = dev_alloc(ctx, (void**)&L.d_out, (size_t)mb * L.Hout * L.Wout * L.out_stride * 4)) return rc;
+      prev = L.d_out;
+    }
+  }
+  {
+    const Layer& L7 = ctx->layers[6];
+    ctx->nparts7 = L7.tiles_h * L7.tiles_w * 4;
+    if (int rc = dev_alloc(ctx, (void**)&ctx->d_sum7, (size_t)mb * 2 * ctx->nparts7 * 256 * 4)) return rc;
+  }
+
+  // ---- weights ----
+  auto need_conv = [&](const std::string& scope, int k, int ci, int co, const HostTensor** w, const HostTensor** b) -> int {
+    *w = find_w(ctx, P + scope + "/weights");
+    *b = find_w(ctx, P + scope + "/biases");
+    if (!*w || !*b) return fail(ctx, DAVO_ERR_WEIGHT, "missing variable %s%s/{weights,biases}", P.c_str(), scope.c_str());
+    if (!shape_is(*w, {k, k, ci, co}) || !shape_is(*b, {co}))
+      return fail(ctx, DAVO_ERR_WEIGHT, "variable %s%s has the wrong shape (want [%d,%d,%d,%d])", P.c_str(), scope.c_str(), k, k, ci, co);
+    return 0;
+  };
+  for (int i = 0; i < 5; ++i) {
+    Layer& L = ctx->layers[i];
+    const HostTensor *w, *b;
+    if (int rc = need_conv(names[i], L.k, L.Cin_w, L.BN, &w, &b)) return rc;
+    const int Ci = L.Cin_w, Co = L.BN, K = L.k;
+    auto getw = [&](int, int ty, int tx, int ci, int n) { return w->data[(((size_t)ty * K + tx) * Ci + ci) * Co + n]; };
+    if (int rc = plan_layer(ctx, L, getw, b->data)) return rc;
+  }
+  const char* brs[2] = {"rotation", "translation"};
+  {
+    Layer& L = ctx->layers[5];
+    const HostTensor *w[2], *b[2];
+    for (int g = 0; g < 2; ++g)
+      if (int rc = need_conv(std::string("pose/") + brs[g] + "/cnv6", 3, 256, c6, &w[g], &b[g])) return rc;
+    auto getw = [&](int, int ty, int tx, int ci, int n) {
+      const HostTensor* t = w[n / c6];
+      return t->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + (n % c6)];
+    };
+    std::vector<float> bias(2 * c6);
+    for (int n = 0; n < 2 * c6; ++n) bias[n] = b[n / c6]->data[n % c6];
+    if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
+  }
+  {
+    Layer& L = ctx->layers[6];
+    const HostTensor *w[2], *b[2];
+    for (int g = 0; g < 2; ++g)
+      if (int rc = need_conv(std::string("pose/") + brs[g] + "/cnv7", 3, c6, 256, &w[g], &b[g])) return rc;
+    auto getw = [&](int g, int ty, int tx, int ci, int n) {
+      return w[g]->data[(((size_t)ty * 3 + tx) * c6 + ci) * 256 + n];
+    };
+    std::vector<float> bias(512);
+    for (int n = 0; n < 512; ++n) bias[n] = b[n / 256]->data[n % 256];
+    if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
+    if (int rc = dev_alloc(ctx, (void**)&ctx->d_c7tmp, (size_t)mb * L.Hout * L.Wout * 512 * 4)) return rc;
+  }
+  {
+    std::vector<float> wp(2 * 256 * 3), bp(6);
+    for (int g = 0; g < 2; ++g) {
+      const HostTensor *w, *b;
+      if (int rc = need_conv(std::string("pose/") + brs[g] + "/pred", 1, 256, 3, &w, &b)) return rc;
+      for (int i = 0; i < 768; ++i) wp[g * 768 + i] = w->data[i];
+      for (int j = 0; j < 3; ++j) bp[g * 3 + j] = b->data[j];
+    }
+    if (int rc = dev_alloc(ctx, (void**)&ctx->d_wpred, wp.size() * 4)) return rc;
+    if (int rc = dev_alloc(ctx, (void**)&ctx->d_bpred, bp.size() * 4)) return rc;
+    CU_OK(cudaMemcpy(ctx->d_wpred, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpy(ctx->d_bpred, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_sew, 195 * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_staticw, kNumClasses * 4)) return rc;
+  if (c.att_src == 1) {
+    const std::string S = P + "se_flow/";
+    const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
+    const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
+    const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
+    const HostTensor* b2 = find_w(ctx, S + "recover_fc/bias");
+    if (!shape_is(w1, {2, 8}) || !shape_is(b1, {8}) || !shape_is(w2, {8, 19}) || !shape_is(b2, {19}))
+      return fail(ctx, DAVO_ERR_WEIGHT, "missing or mis-shaped %s{bottleneck_fc,recover_fc}/{kernel,bias}", S.c_str());
+    std::vector<float> se;
+    se.insert(se.end(), w1->data.begin(), w1->data.end());
+    se.insert(se.end(), b1->data.begin(), b1->data.end());
+    se.insert(se.end(), w2->data.begin(), w2->data.end());
+    se.insert(se.end(), b2->data.begin(), b2->data.end());
+    CU_OK(cudaMemcpy(ctx->d_sew, se.data(), se.size() * 4, cudaMemcpyHostToDevice));
+  } else if (c.att_src == 2) {
+    // reference posenn.py:380-394 -- variable is double-scoped by davo.py:1392 inside :1114
+    const HostTensor* sw = find_w(ctx, P + "pose_exp_net/seg_channel_weight/weight");
+    if (!shape_is(sw, {19}))
+      return fail(ctx, DAVO_ERR_WEIGHT, "missing or mis-shaped %spose_exp_net/seg_channel_weight/weight", P.c_str());
+    std::vector<float> s(19);
+    for (int i = 0; i < 19; ++i) s[i] = 1.0f / (1.0f + expf(-sw->data[i]));
+    CU_OK(cudaMemcpy(ctx->d_staticw, s.data(), 19 * 4, cudaMemcpyHostToDevice));
+  }
+  CU_OK(cudaDeviceSynchronize());
+  ctx->finalized = true;
+  return 0;
+}
+
+extern "C" int davo_forward(davo_ctx* ctx, int B, const uint8_t* img, const float* flow,
+                            const float* seg, const float* depth, float* pose_out, void* stream) {
+  (void)depth;
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward: weights not finalized");
+  if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward: B=%d outside 1..%d", B, ctx->cfg.max_batch);
+  if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1) && !flow))
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward: null input buffer");
+  CU_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int launches = 0;
+  const int total = 2 * B;
+  int last_n = 0;
+  for (int p0 = 0; p0 < total; p0 += ctx->mb) {
+    const int n = (total - p0) < ctx->mb ? (total - p0) : ctx->mb;
+    if (int rc = run_microbatch(ctx, p0, n, img, flow, seg, pose_out, st, &launches)) return rc;
+    last_n = n;
+  }
+  ctx->last_launches = launches;
+  ctx->last_npairs_mb = last_n;
+  ctx->last_img = img; ctx->last_flow = flow; ctx->last_seg = seg; ctx->last_pose = pose_out; ctx->last_B = B;
+  return 0;
+}
+
+extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const float* flow,
+                                 const float* seg, const float* depth, float* pose_out, void* stream) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: weights not finalized");
+  if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: B=%d outside 1..%d", B, ctx->cfg.max_batch);
+  CU_OK(cudaSetDevice(ctx->device));
+  const davo_config& c = ctx->cfg;
+  const size_t hw = (size_t)c.H * c.W;
+  const size_t n_img = hw * 9, n_flow = hw * 8, n_seg = hw * 3;   // per sample
+  if (!ctx->s_img) {
+    CU_OK(cudaMalloc((void**)&ctx->s_img, n_img * c.max_batch));
+    CU_OK(cudaMalloc((void**)&ctx->s_flow, n_flow * 4 * c.max_batch));
+    CU_OK(cudaMalloc((void**)&ctx->s_seg, n_seg * 4 * c.max_batch));
+    CU_OK(cudaMalloc((void**)&ctx->s_pose, (size_t)12 * 4 * c.max_batch));
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!img || !pose_out) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: null buffer");
+  CU_OK(cudaMemcpyAsync(ctx->s_img, img, n_img * B, cudaMemcpyHostToDevice, st));
+  if (flow) CU_OK(cudaMemcpyAsync(ctx->s_flow, flow, n_flow * 4 * B, cudaMemcpyHostToDevice, st));
+  if (seg) CU_OK(cudaMemcpyAsync(ctx->s_seg, seg, n_seg * 4 * B, cudaMemcpyHostToDevice, st));
+  if (int rc = davo_forward(ctx, B, ctx->s_img, flow ? ctx->s_flow : nullptr, seg ? ctx->s_seg : nullptr,
+                            depth, ctx->s_pose, stream))
+    return rc;
+  CU_OK(cudaMemcpyAsync(pose_out, ctx->s_pose, (size_t)12 * 4 * B, cudaMemcpyDeviceToHost, st));
+  CU_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int davo_last_launch_count(const davo_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, float* out,
+                                     int64_t cap, int64_t* n_out) {
+  if (!ctx || !name || !out || !n_out) return DAVO_ERR_ARG;
+  if (!ctx->finalized || ctx->last_npairs_mb == 0) return fail(ctx, DAVO_ERR_STATE, "davo_get_intermediate: no forward has run");
+  if (pair < 0 || pair >= ctx->last_npairs_mb) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: pair %d not in the last micro-batch (0..%d)", pair, ctx->last_npairs_mb - 1);
+  CU_OK(cudaSetDevice(ctx->device));
+  CU_OK(cudaDeviceSynchronize());
+  const davo_config& c = ctx->cfg;
+  const float* src = nullptr;
+  int64_t n = 0;
+  std::string s(name);
+  if (s == "att_weights") { n = kNumClasses; src = ctx->d_attw + (size_t)pair * n; }
+  else if (s == "packed") { n = (int64_t)c.H * c.W * kPackedC; src = ctx->d_packed + (size_t)pair * n; }
+  else if (s == "cnv7_sum") {
+    // reduce the deterministic partials on the host
+    const int np = ctx->nparts7;
+    std::vector<float> tmp((size_t)2 * np * 256);
+    CU_OK(cudaMemcpy(tmp.data(), ctx->d_sum7 + (size_t)pair * 2 * np * 256, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    if (cap < 512) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: buffer too small");
+    for (int br = 0; br < 2; ++br)
+      for (int ch = 0; ch < 256; ++ch) {
+        float a = 0.f;
+        for (int i = 0; i < np; ++i) a += tmp[((size_t)br * np + i) * 256 + ch];
+        out[br * 256 + ch] = a;
+      }
+    *n_out = 512;
+    return 0;
+  } else {
+    for (int i = 0; i < 6; ++i)
+      if (s == ctx->layers[i].name) {
+        const Layer& L = ctx->layers[i];
+        n = (int64_t)L.Hout * L.Wout * L.out_stride;
+        src = L.d_out + (size_t)pair * n;
+      }
+  }
+  if (!src) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: unknown name '%s'", name);
+  if (cap < n) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: buffer too small (%lld < %lld)", (long long)cap, (long long)n);
+  CU_OK(cudaMemcpy(out, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  *n_out = n;
+  return 0;
+}
+
+extern "C" int davo_debug_set_conv_impl(davo_ctx* ctx, int impl) {
+  if (!ctx || impl < 0 || impl > 1) return DAVO_ERR_ARG;
+  ctx->conv_impl = impl;
+  return 0;
+}
+
+extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int* npairs_out,
+                                   void* stream) {
+  if (!ctx || !ms_out || iters <= 0) return DAVO_ERR_ARG;
+  if (!ctx->finalized || ctx->last_npairs_mb == 0) return fail(ctx, DAVO_ERR_STATE, "davo_profile_layers: run a forward first");
+  CU_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int npairs = ctx->last_B * 2 < ctx->mb ? ctx->last_B * 2 : ctx->mb;
+  if (npairs_out) *npairs_out = npairs;
+  cudaEvent_t e0, e1;
+  CU_OK(cudaEventCreate(&e0));
+  CU_OK(cudaEventCreate(&e1));
+  int dummy = 0;
+  auto timed = [&](auto&& fn, float* ms_dst) -> int {
+    if (int rc = fn()) return rc;   // warm
+    CU_OK(cudaEventRecord(e0, st));
+    for (int it = 0; it < iters; ++it)
+      if (int rc = fn()) return rc;
+    CU_OK(cudaEventRecord(e1, st));
+    CU_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_OK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_dst = ms / iters;
+    return 0;
+  };
+  if (int rc = timed([&] { return launch_front(ctx, 0, npairs, ctx->last_img, ctx->last_flow, ctx->last_seg, st, &dummy); }, &ms_out[0])) return rc;
+  for (int i = 0; i < 7; ++i) {
+    const Layer& L = ctx->layers[i];
+    if (int rc = timed([&] { return launch_conv(ctx, L, npairs, st); }, &ms_out[1 + i])) return rc;
+  }
+  if (int rc = timed([&] { return launch_head(ctx, 0, npairs, ctx->last_pose, st, &dummy); }, &ms_out[8])) return rc;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}

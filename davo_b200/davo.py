@@ -1,0 +1,201 @@
+"""``DAVO`` -- the reference's model wrapper for the pose path, over libdavo_b200.so.
+
+Keeps the calling surface of the reference class (reference ``davo.py:30-33``
+constructor, ``:1533-1551`` ``setup_inference``, ``:1553-1569`` ``inference``)
+and of its use in ``test_kitti_pose.py:126-135``:
+
+    system = DAVO(version=FLAGS.version)
+    system.setup_inference(H, W, "davo", seq_length, batch_size, input_batch,
+                           input_flow=..., input_depth=..., input_seglabel=...)
+    system.load_weights(ckpt)            # stands in for saver.restore(sess, ckpt)
+    pred = system.inference(sess, mode='pose')     # {'pose': ndarray [B,2,6]}
+
+The TensorFlow graph/session is replaced by one C call per ``inference``.
+Inputs bound at ``setup_inference`` may be torch CUDA tensors (used in place),
+numpy arrays (copied host->device inside the call) or callables returning the
+next batch, which plays the role of the reference's ``tf.data`` iterator
+outputs.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _capi
+from . import version as V
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class DAVO(object):
+    def __init__(self, version=None):
+        self.version = version                       # reference davo.py:31-33
+        self._h = None
+        self._lib = None
+        self._weights_loaded = False
+
+    # ------------------------------------------------------------------ setup
+    def setup_inference(self, img_height, img_width, mode, seq_length=3, batch_size=1,
+                        input_img_uint8=None, input_pose=None, input_flow=None,
+                        input_depth=None, input_seglabel=None, device=None, micro_batch=0):
+        """Reference ``davo.py:1533-1551``; only ``mode == 'davo'`` builds anything there."""
+        self.img_height = img_height
+        self.img_width = img_width
+        self.mode = mode
+        self.batch_size = batch_size
+        if self.mode != 'davo':
+            return
+        assert self.version is not None              # reference davo.py:959
+        if seq_length != 3:
+            raise NotImplementedError("davo_b200: only seq_length=3 (two source frames) is built")
+        self.seq_length = seq_length
+        self.num_source = seq_length - 1
+        self.config = V.parse_version(self.version)  # raises NameError like the reference
+        self._inputs = (input_img_uint8, input_flow, input_depth, input_seglabel)
+        self._lib = _capi.load()
+        if device is None:
+            for t in self._inputs:
+                if _is_torch(t) and t.is_cuda:
+                    device = t.device.index
+                    break
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = int(device)
+        cfg = _capi.DavoConfigC(
+            H=img_height, W=img_width, max_batch=batch_size, posenn=self.config.posenn,
+            cnv6_out=self.config.cnv6_out, in_mode=self.config.in_mode,
+            att_src=self.config.att_src, att_tgt_ones=self.config.att_tgt_ones,
+            mask_mode=self.config.mask_mode, se_act=self.config.se_act,
+            flow_abs=self.config.flow_abs, flow_norm=self.config.flow_norm,
+            posenn_se=self.config.posenn_se, micro_batch=micro_batch)
+        h = C.c_void_p()
+        rc = self._lib.davo_create(C.byref(cfg), self.device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("davo_create failed (%d): %s" % (rc, _capi.last_error(self._lib, None)))
+        self._h = h
+        self._pose_dev = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, _capi.last_error(self._lib, self._h)))
+
+    # ---------------------------------------------------------------- weights
+    def load_weights(self, weights):
+        """``{tf variable name: ndarray}`` or a ``.npz`` of that; stands in for
+        ``tf.train.Saver(trainable_variables).restore`` (reference test_kitti_pose.py:129-131)."""
+        if self._h is None:
+            raise RuntimeError("DAVO.load_weights: call setup_inference(mode='davo') first")
+        if isinstance(weights, (str, os.PathLike)):
+            with np.load(weights) as z:
+                weights = {k: z[k] for k in z.files}
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(np.asarray(arr), dtype=np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            self._check(self._lib.davo_set_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p),
+                                                  shape, a.ndim), "davo_set_weight(%s)" % name)
+        self._check(self._lib.davo_finalize_weights(self._h), "davo_finalize_weights")
+        self._weights_loaded = True
+
+    restore = load_weights
+
+    # -------------------------------------------------------------- inference
+    def _resolve(self, x):
+        return x() if callable(x) and not _is_torch(x) and not isinstance(x, np.ndarray) else x
+
+    def inference(self, sess=None, mode='pose', inputs=None, as_torch=False):
+        """Reference ``davo.py:1553-1569``: one run of the pose graph -> ``{'pose': [B,2,6]}``.
+
+        ``sess`` is accepted for signature compatibility and ignored.  ``inputs``
+        may override the bound tensors as ``(img_u8, flow, seg)`` or a dict with
+        keys ``img``, ``flow``, ``seg``.
+        """
+        if mode not in ('pose',):
+            raise NotImplementedError("davo_b200: inference mode %r is not built (only 'pose')" % (mode,))
+        if not self._weights_loaded:
+            raise RuntimeError("DAVO.inference: weights not loaded")
+        if inputs is None:
+            img, flow, _depth, seg = (self._resolve(t) for t in self._inputs)
+        elif isinstance(inputs, dict):
+            img, flow, seg = inputs.get("img"), inputs.get("flow"), inputs.get("seg")
+        else:
+            img, flow, seg = inputs
+        B = int(img.shape[0])
+        H, W = self.img_height, self.img_width
+        want = {"img": (B, H, 3 * W, 3), "flow": (B, 4, H, W, 2), "seg": (B, 3, H, W, 1)}
+        for name, t in (("img", img), ("flow", flow), ("seg", seg)):
+            if t is not None and tuple(t.shape) != want[name]:
+                raise ValueError("DAVO.inference: %s has shape %s, expected %s" % (name, tuple(t.shape), want[name]))
+        if _is_torch(img):
+            return self._run_device(B, img, flow, seg, as_torch)
+        return self._run_host(B, img, flow, seg)
+
+    def _run_device(self, B, img, flow, seg, as_torch):
+        import torch
+        for name, t, dt in (("img", img, torch.uint8), ("flow", flow, torch.float32), ("seg", seg, torch.float32)):
+            if t is None:
+                continue
+            if not (t.is_cuda and t.device.index == self.device and t.dtype == dt and t.is_contiguous()):
+                raise ValueError("DAVO.inference: %s must be a contiguous %s tensor on cuda:%d" % (name, dt, self.device))
+        if self._pose_dev is None or self._pose_dev.shape[0] < B:
+            self._pose_dev = torch.empty((max(B, self.batch_size), 2, 6), dtype=torch.float32,
+                                         device="cuda:%d" % self.device)
+        out = self._pose_dev[:B]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self._check(self._lib.davo_forward(self._h, B, ptr(img), ptr(flow), ptr(seg), None,
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "davo_forward")
+        if as_torch:
+            return {'pose': out}
+        return {'pose': out.cpu().numpy()}
+
+    def _run_host(self, B, img, flow, seg):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        flow = None if flow is None else np.ascontiguousarray(flow, dtype=np.float32)
+        seg = None if seg is None else np.ascontiguousarray(seg, dtype=np.float32)
+        out = np.empty((B, 2, 6), np.float32)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        self._check(self._lib.davo_forward_host(self._h, B, ptr(img), ptr(flow), ptr(seg), None,
+                                                ptr(out), None), "davo_forward_host")
+        return {'pose': out}
+
+    # ------------------------------------------------------ test / debug taps
+    def get_intermediate(self, name: str, pair: int) -> np.ndarray:
+        buf = np.empty((self.img_height * self.img_width * 16,), np.float32)
+        n = C.c_int64(0)
+        self._check(self._lib.davo_get_intermediate(self._h, name.encode(), pair,
+                                                    buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(n)),
+                    "davo_get_intermediate(%s)" % name)
+        return buf[:n.value].copy()
+
+    def last_launch_count(self) -> int:
+        return int(self._lib.davo_last_launch_count(self._h))
+
+    def profile_layers(self, iters: int = 10):
+        """Mean ms per kernel of one micro-batch: front, cnv1..cnv7, head; and pairs per launch."""
+        import torch
+        ms = (C.c_float * 9)()
+        n = C.c_int(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.davo_profile_layers(self._h, iters, ms, C.byref(n), C.c_void_p(stream)),
+                    "davo_profile_layers")
+        names = ["front", "cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6", "cnv7", "head"]
+        return dict(zip(names, [float(v) for v in ms])), int(n.value)
+
+    def _debug_set_conv_impl(self, impl: int):
+        self._check(self._lib.davo_debug_set_conv_impl(self._h, impl), "davo_debug_set_conv_impl")
+
+    def close(self):
+        if self._h is not None and self._lib is not None:
+            self._lib.davo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

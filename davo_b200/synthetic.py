@@ -1,0 +1,117 @@
+"""Synthetic inputs and TF-default random-init weights for the pose path.
+
+There is no dataset or checkpoint offline, so tests, the CLI's ``--synthetic``
+mode and ``bench.py`` use seeded stand-ins with the tensor contract of the
+reference's input pipeline (reference ``test_kitti_pose.py:104-114``):
+
+    img  uint8   [B, H, 3W, 3]   src0 | tgt | src1 stacked along width
+    flow float32 [B, 4, H, W, 2] [src0->tgt, src1->tgt, tgt->src0, tgt->src1]
+    seg  float32 [B, 3, H, W, 1] Cityscapes trainIds 0..18 for [src0, tgt, src1]
+
+Weights follow the initialisers the reference graph would use before a
+checkpoint is restored, keyed by TF variable name (checkpoint surface):
+``slim.conv2d`` -> xavier uniform, zero bias (reference ``nets/posenn.py:205-215``);
+``tf.layers.dense`` with ``variance_scaling_initializer()`` -> truncated normal,
+stddev sqrt(1.3 * 2 / fan_in), zero bias (``nets/attention_module.py:60-61``);
+``seg_channel_weight/weight`` -> N(0, 0.05) (``nets/posenn.py:388-389``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import numpy as np
+
+from . import version as V
+
+FLOW_MEAN, FLOW_STD = 0.32140523, 15.384229   # dataset statistics, reference davo.py:1090
+NUM_CLASSES = 19
+
+
+def make_inputs(batch: int, height: int = 128, width: int = 416, seed: int = 1234,
+                seg_block: int = 16, bad_label_frac: float = 0.0):
+    """Seeded (img, flow, seg) with the reference's shapes and dtypes.
+
+    seg is integer-valued, constant over ``seg_block`` x ``seg_block`` pixel blocks;
+    ``bad_label_frac`` > 0 overwrites that fraction of pixels with label 255
+    (out of range -> attention 0, reference ``davo.py:1115``).
+    """
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(batch, height, 3 * width, 3), dtype=np.uint8)
+    flow = rng.normal(FLOW_MEAN, FLOW_STD, size=(batch, 4, height, width, 2)).astype(np.float32)
+    hb, wb = -(-height // seg_block), -(-width // seg_block)
+    blocks = rng.integers(0, NUM_CLASSES, size=(batch, 3, hb, wb), dtype=np.int64)
+    seg = np.repeat(np.repeat(blocks, seg_block, axis=2), seg_block, axis=3)[:, :, :height, :width]
+    seg = seg.astype(np.float32)
+    if bad_label_frac > 0:
+        bad = rng.random(size=seg.shape) < bad_label_frac
+        seg[bad] = 255.0
+    return img, flow, seg[..., None].copy()
+
+
+def _xavier_uniform(rng, shape):
+    kh, kw, cin, cout = shape
+    lim = math.sqrt(6.0 / (kh * kw * cin + kh * kw * cout))
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def _trunc_normal(rng, shape, std):
+    out = rng.normal(0.0, std, size=shape)
+    bad = np.abs(out) > 2 * std
+    while bad.any():
+        out[bad] = rng.normal(0.0, std, size=int(bad.sum()))
+        bad = np.abs(out) > 2 * std
+    return out.astype(np.float32)
+
+
+def conv_specs(cfg: V.DavoConfig):
+    """[(tf scope under pose_exp_net/, HWIO shape)] of decouple_sharednet_v0_dilation."""
+    cin = 10 if cfg.in_mode == 1 else 6
+    c6 = cfg.cnv6_out
+    specs = [("cnv1", (7, 7, cin, 16)), ("cnv2", (5, 5, 16, 32)), ("cnv3", (3, 3, 32, 64)),
+             ("cnv4", (3, 3, 64, 128)), ("cnv5", (3, 3, 128, 256))]
+    for br in ("rotation", "translation"):
+        specs += [("pose/%s/cnv6" % br, (3, 3, 256, c6)),
+                  ("pose/%s/cnv7" % br, (3, 3, c6, 256)),
+                  ("pose/%s/pred" % br, (1, 1, 256, 3))]
+    return specs
+
+
+def init_weights(version: str, seed: int = 8964, random_bias: bool = False
+                 ) -> Dict[str, np.ndarray]:
+    """{tf variable name: ndarray} for ``version`` (seed 8964 = reference train.py:34).
+
+    ``random_bias`` draws biases from N(0, 0.05) instead of TF's zeros, so that
+    tests exercise the bias path the way a trained checkpoint would.
+    """
+    cfg = V.parse_version(version)
+    if cfg.posenn != V.POSENN_DECOUPLE_SHARED_DIL:
+        raise NotImplementedError("init_weights: only -sharedNN-dilatedPoseNN is built")
+    rng = np.random.default_rng(seed)
+    w: Dict[str, np.ndarray] = {}
+
+    def bias(n):
+        if random_bias:
+            return rng.normal(0.0, 0.05, size=(n,)).astype(np.float32)
+        return np.zeros((n,), np.float32)
+
+    for scope, shape in conv_specs(cfg):
+        w["pose_exp_net/%s/weights" % scope] = _xavier_uniform(rng, shape)
+        w["pose_exp_net/%s/biases" % scope] = bias(shape[3])
+    if cfg.att_src == V.ATT_SE_FLOW:
+        for name, (fi, fo) in (("bottleneck_fc", (2, 8)), ("recover_fc", (8, 19))):
+            std = math.sqrt(1.3 * 2.0 / fi)
+            w["pose_exp_net/se_flow/%s/kernel" % name] = _trunc_normal(rng, (fi, fo), std)
+            w["pose_exp_net/se_flow/%s/bias" % name] = bias(fo)
+    if cfg.att_src == V.ATT_STATIC:
+        # double scope is the reference's: prefix "pose_exp_net/" inside scope pose_exp_net
+        w["pose_exp_net/pose_exp_net/seg_channel_weight/weight"] = \
+            rng.normal(0.0, 0.05, size=(19,)).astype(np.float32)
+    if cfg.posenn_se == V.PSE_INSERT:
+        for br in ("rotation", "translation"):
+            sc = "pose_exp_net/pose/%s/cnv5_se_attention" % br
+            for name, (fi, fo) in (("bottleneck_fc", (256, 32)), ("recover_fc", (32, 256))):
+                std = math.sqrt(1.3 * 2.0 / fi)
+                w["%s/%s/kernel" % (sc, name)] = _trunc_normal(rng, (fi, fo), std)
+                w["%s/%s/bias" % (sc, name)] = bias(fo)
+    return w

@@ -1,0 +1,167 @@
+"""Version-string variant selection for the pose forward path.
+
+Mirrors the ordered substring / regex tests of the reference's inference graph
+builder (reference ``davo.py:1010-1102`` for the option groups, ``:1117-1400``
+for the attention-source chain, ``:1404-1450`` for masking).  First match wins
+inside a group; groups are independent.  The result is the small config struct
+handed to the C ABI (``include/davo_b200.h``: ``davo_config``).
+
+Bad strings raise the same exception types and messages as the reference
+(``NameError`` for PoseNN selection, ``davo.py:1035-1037``).
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, asdict
+
+# posenn kinds (reference nets/posenn.py)
+POSENN_DECOUPLE_SHARED_DIL = 0   # decouple_sharednet_v0_dilation  :189-254  (headline)
+POSENN_COUPLE_SHARED_DIL = 1     # couple_sharednet_v0_dilation    :133-187
+POSENN_DECOUPLE_DIL = 2          # decouple_net_v0_dilation        :69-131
+POSENN_COUPLE_DIL = 3            # couple_net_v0_dilation          :12-66
+POSENN_COUPLE = 4                # couple_net_v0                   :257-311
+POSENN_DECOUPLE = 5              # decouple_net_v0                 :314-378
+
+ATT_NONE, ATT_SE_FLOW, ATT_STATIC = 0, 1, 2
+MASK_OFF, MASK_RGB, MASK_ALL, MASK_ALL_555 = 0, 1, 2, 3
+ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2
+ABS_NONE, ABS_BOTH, ABS_H, ABS_V = 0, 1, 2, 3
+PSE_NONE, PSE_INSERT, PSE_SKIPADD, PSE_REPLACE = 0, 1, 2, 3
+
+# Attention sources of the reference chain that this build does not implement
+# (davo.py:1117-1383), in the reference's evaluation order.
+_UNBUILT_SOURCES = (
+    "-se_flow_on_depthseg_sharedlayers", "-se_flow_on_depthseg_seplayers",
+    "-se_flow_on_depthseg", "-se_mixDepthFlow", "-se_mixDispFlow",
+)
+_UNBUILT_AFTER_SE_FLOW = (
+    "-se_gp2x2_flow_nobottle", "-se_gp2x2_flow", "-se_spp21_flow", "-se_spp2_flow",
+    "-se_spp_flow", "-se_spp864_flow", "-se_depth_wo_tgt_to_seg", "-se_depth_to_seg",
+    "-se_depth_wo_tgt", "-se_depth", "-se_disp_wo_tgt_to_seg", "-se_disp_to_seg",
+    "-se_disp_wo_tgt", "-se_disp", "-se_rgb_wo_tgt_to_seg", "-se_rgb_to_seg",
+    "-se_rgb_wo_tgt", "-se_rgb", "-se_seg_wo_tgt", "-se_seg", "-se_gp2x2_seg",
+    "-se_spp21_seg", "-se_spp_seg_21", "-se_spp2_seg", "-se_spp_seg", "-se_spp864_seg",
+    "-se_SegFlow_to_seg_8_wo_tgt", "-se_SegFlow_to_seg_8", "-se_SegFlow_to_seg_wo_tgt",
+    "-se_SegFlow_to_seg", "-se_mixSegFlow", "-se_spp21_mixSegFlow",
+)
+
+
+@dataclass
+class DavoConfig:
+    """Field-for-field the C struct ``davo_config`` (minus H, W, max_batch)."""
+    posenn: int = POSENN_DECOUPLE_SHARED_DIL
+    cnv6_out: int = 128
+    in_mode: int = 1            # 0 = v0 (RGB only), 1 = v1 (RGB + flow)
+    att_src: int = ATT_NONE
+    att_tgt_ones: int = 1       # target-frame attention map forced to ones
+    mask_mode: int = MASK_OFF
+    se_act: int = ACT_RELU
+    flow_abs: int = ABS_NONE
+    flow_norm: int = 0
+    posenn_se: int = PSE_NONE
+    version_tag: str = "v0"
+
+    def as_dict(self):
+        return asdict(self)
+
+
+def parse_version(version: str) -> DavoConfig:
+    """Resolve a version string exactly as ``build_pose_test_graph_davo`` does."""
+    assert version is not None                                  # davo.py:959
+    if "depth" in version or "disp" in version:                 # davo.py:960
+        raise NotImplementedError(
+            "davo_b200: depth/disp attention inputs are not built (version %r)" % version)
+    cfg = DavoConfig()
+    # G1 PoseNN-internal SE (davo.py:1010-1017)
+    if "-se_insert" in version:
+        cfg.posenn_se = PSE_INSERT
+    elif "-se_skipadd" in version:
+        cfg.posenn_se = PSE_SKIPADD
+    elif "-se_replace" in version:
+        cfg.posenn_se = PSE_REPLACE
+    # G2 PoseNN type (davo.py:1027-1049)
+    if "-sharedNN" in version:
+        if "-dilatedPoseNN" in version:
+            cfg.posenn = POSENN_DECOUPLE_SHARED_DIL
+        elif "-dilatedCouplePoseNN" in version:
+            cfg.posenn = POSENN_COUPLE_SHARED_DIL
+        elif "-couplePoseNN" in version:
+            raise NameError("not support `-sharedNN-couplePoseNN' mode.")
+        else:
+            raise NameError("unknown PoseNN type.")
+    elif "-dilatedPoseNN" in version:
+        cfg.posenn = POSENN_DECOUPLE_DIL
+    elif "-dilatedCouplePoseNN" in version:
+        cfg.posenn = POSENN_COUPLE_DIL
+    elif "-couplePoseNN" in version:
+        cfg.posenn = POSENN_COUPLE
+    else:
+        cfg.posenn = POSENN_DECOUPLE
+    # G3 cnv6 width (davo.py:1052-1053)
+    m = re.search("-cnv6_([0-9]+)", version)
+    cfg.cnv6_out = 128 if m is None else int(m.group(1))
+    # G4 input version (davo.py:1057-1065)
+    m = re.search("^(v[0-9.]+)", version)
+    tag = "v0" if m is None else m.group(1)
+    cfg.version_tag = tag
+    if "v0" in tag:
+        cfg.in_mode = 0
+    elif "v1" in tag:
+        cfg.in_mode = 1
+    else:
+        cfg.in_mode = 0     # pred_info stays None (davo.py:1060)
+    # G5 (davo.py:1066-1073)
+    if "-seglabelid" in version:
+        raise NotImplementedError("davo_b200: -seglabelid input channel is not built")
+    # G6 SE activation (davo.py:1077-1085)
+    if "-fc_tanh" in version:
+        cfg.se_act = ACT_TANH
+    elif "-fc_lrelu" in version:
+        cfg.se_act = ACT_LRELU
+    else:
+        cfg.se_act = ACT_RELU
+    # G7 (davo.py:1088-1091)
+    cfg.flow_norm = 1 if "-norm_flow" in version else 0
+    # G8 (davo.py:1094-1102) -- order matters: _h and _v before the bare token
+    if "-abs_flow_h" in version:
+        cfg.flow_abs = ABS_H
+    elif "-abs_flow_v" in version:
+        cfg.flow_abs = ABS_V
+    elif "-abs_flow" in version:
+        cfg.flow_abs = ABS_BOTH
+    # G10 attention source (davo.py:1117-1400), reference order
+    for tok in _UNBUILT_SOURCES:
+        if tok in version:
+            raise NotImplementedError("davo_b200: attention source %s is not built" % tok)
+    if "-se_flow" in version:                                   # davo.py:1175
+        cfg.att_src = ATT_SE_FLOW
+        cfg.att_tgt_ones = 1                                    # davo.py:1404-1412
+    else:
+        for tok in _UNBUILT_AFTER_SE_FLOW:
+            if tok in version:
+                raise NotImplementedError("davo_b200: attention source %s is not built" % tok)
+        if "-no_segmask" in version:                            # davo.py:1385
+            cfg.att_src = ATT_NONE
+            cfg.att_tgt_ones = 1
+        elif "-segmask_" in version and "-static" in version:   # davo.py:1390
+            cfg.att_src = ATT_STATIC
+            cfg.att_tgt_ones = 1
+        else:                                                   # davo.py:1395
+            cfg.att_src = ATT_STATIC
+            cfg.att_tgt_ones = 0
+    # G12 masking (davo.py:1415-1450)
+    if cfg.in_mode == 1:
+        if "-segmask_" in version:
+            if "-segmask_all" in version and ".555" in tag:
+                cfg.mask_mode = MASK_ALL_555
+            elif "-segmask_all" in version:
+                cfg.mask_mode = MASK_ALL
+            else:
+                cfg.mask_mode = MASK_RGB
+        else:
+            cfg.mask_mode = MASK_OFF
+    else:
+        cfg.mask_mode = MASK_RGB if "-segmask" in version else MASK_OFF
+    if "-batch_norm" in version:                                # davo.py:1453
+        raise NotImplementedError("davo_b200: -batch_norm is not built")
+    return cfg

@@ -1,0 +1,122 @@
+/*
+ * davo_b200.h -- C ABI of libdavo_b200.so: the B200 (sm_100a) implementation of
+ * DAVO's pose-estimation forward path (attention module -> masked frame stack ->
+ * dilated PoseNN -> 6-DoF per frame pair).
+ *
+ * The reference (BassyKuo/DAVO) has no FFI layer: its boundary for this path is
+ * the Python class `DAVO` over a TensorFlow session.  Each entry point below
+ * names the reference interface it stands in for (paths relative to the
+ * reference checkout).  The Python mirror of that class (davo_b200/davo.py)
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: every function returns 0 on success and a negative davo_status
+ * on failure; davo_last_error() then describes it.  A handle is bound to one
+ * CUDA device, is not thread-safe, launches only on the caller's stream and
+ * never synchronises inside davo_forward.  Device buffers passed in are owned
+ * by the caller; weights and activation workspace are owned by the handle.
+ * There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef DAVO_B200_H
+#define DAVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct davo_ctx davo_ctx;
+
+enum davo_status {
+  DAVO_OK = 0,
+  DAVO_ERR_ARG = -1,        /* bad argument / unsupported configuration */
+  DAVO_ERR_CUDA = -2,       /* CUDA runtime or driver error             */
+  DAVO_ERR_WEIGHT = -3,     /* unknown / missing / mis-shaped variable  */
+  DAVO_ERR_STATE = -4       /* call order (e.g. forward before finalize)*/
+};
+
+/* Filled by the version-string parser (davo_b200/version.py), which mirrors
+ * reference davo.py:1010-1102 (option groups) and :1117-1450 (attention source
+ * and masking chain). */
+typedef struct davo_config {
+  int32_t H, W;          /* frame size, reference test_kitti_pose.py:22-23 (128, 416)  */
+  int32_t max_batch;     /* largest B (samples) a forward call may carry               */
+  int32_t posenn;        /* 0 = decouple_sharednet_v0_dilation (nets/posenn.py:189)    */
+  int32_t cnv6_out;      /* "-cnv6_<n>", davo.py:1052-1053                             */
+  int32_t in_mode;       /* 0 = v0 RGB only, 1 = v1 RGB+flow, davo.py:1057-1065        */
+  int32_t att_src;       /* 0 none, 1 se_flow (davo.py:1175), 2 static (:1390)         */
+  int32_t att_tgt_ones;  /* target-frame map forced to 1, davo.py:1404-1412, :1393     */
+  int32_t mask_mode;     /* 0 off, 1 rgb, 2 all, 3 all(.555), davo.py:1415-1450        */
+  int32_t se_act;        /* 0 relu, 1 tanh, 2 leaky_relu(0.2), davo.py:1077-1085       */
+  int32_t flow_abs;      /* 0 none, 1 both, 2 h, 3 v, davo.py:1094-1102                */
+  int32_t flow_norm;     /* "-norm_flow", davo.py:1088-1091                            */
+  int32_t posenn_se;     /* 0 none, 1 insert, 2 skipadd, 3 replace, davo.py:1010-1017  */
+  int32_t micro_batch;   /* frame pairs per pass through the conv stack; 0 = default   */
+} davo_config;
+
+/* Stands in for DAVO.__init__ + DAVO.setup_inference (reference davo.py:31-33,
+ * 1533-1551): fixes the variant, frame size and batch, allocates workspaces. */
+int davo_create(const davo_config* cfg, int device, davo_ctx** out);
+
+/* Stands in for tf.train.Saver(...).restore (reference test_kitti_pose.py:129-131),
+ * one variable at a time, keyed by TF variable name.  Conv kernels are HWIO,
+ * dense kernels [in, out], as TF stores them.  `host` is host memory. */
+int davo_set_weight(davo_ctx*, const char* tf_var_name, const float* host,
+                    const int64_t* shape, int rank);
+
+/* Checks every variable of the variant was supplied, repacks to the kernels'
+ * K-major TF32 layout and uploads. */
+int davo_finalize_weights(davo_ctx*);
+
+/* Stands in for DAVO.inference(sess, mode='pose') = one sess.run of pred_poses
+ * (reference davo.py:1553-1569) on B <= max_batch samples.
+ *   img_u8   device, uint8  [B, H, 3W, 3]   (src0 | tgt | src1 along width)
+ *   flow     device, float  [B, 4, H, W, 2] (only [:,0:2] are read, davo.py:978-982)
+ *   seg      device, float  [B, 3, H, W, 1] ([src0, tgt, src1], davo.py:1000-1004)
+ *   depth    unused by the built variants; pass NULL
+ *   pose_out device, float  [B, 2, 6]: rows [tgt->src0, tgt->src1],
+ *            cols [rz, ry, rx, tx, ty, tz] (nets/posenn.py:193, davo.py:1458)
+ * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream). */
+int davo_forward(davo_ctx*, int B, const uint8_t* img_u8, const float* flow,
+                 const float* seg, const float* depth, float* pose_out,
+                 void* cuda_stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies inputs in, runs the
+ * forward, copies poses out and synchronises the stream -- the end-to-end form
+ * of `sess.run` with fed numpy arrays (reference davo.py:1568). */
+int davo_forward_host(davo_ctx*, int B, const uint8_t* img_u8, const float* flow,
+                      const float* seg, const float* depth, float* pose_out,
+                      void* cuda_stream);
+
+/* Test / mode='feature' access to what the last davo_forward left in the
+ * workspace for frame pair `pair` (= 2*sample + source index) of the LAST
+ * micro-batch: "att_weights" [19], "packed" [H,W,16], "cnv1".."cnv5",
+ * "cnv6" [h,w,2*cnv6_out] (rotation | translation), "cnv7_sum" [2,256].
+ * Copies to HOST memory `out` (capacity `cap` floats); writes the element
+ * count to *n.  Synchronises. */
+int davo_get_intermediate(davo_ctx*, const char* name, int pair, float* out,
+                          int64_t cap, int64_t* n);
+
+/* Number of kernel launches the last davo_forward issued. */
+int davo_last_launch_count(const davo_ctx*);
+
+/* Times each kernel of the last forward's first micro-batch in isolation:
+ * re-launches it `iters` times on `cuda_stream` between CUDA events and returns
+ * mean milliseconds in ms_out[9] = {front end (pool + pack), cnv1..cnv7, head}.
+ * *npairs_out receives the frame pairs per launch.  Synchronises. */
+int davo_profile_layers(davo_ctx*, int iters, float* ms_out, int* npairs_out,
+                        void* cuda_stream);
+
+/* Test hook: 0 = tcgen05 implicit GEMM (the product path), 1 = plain fp32
+ * direct convolution on CUDA cores, used only to cross-check the tensor-core
+ * path on the GPU. */
+int davo_debug_set_conv_impl(davo_ctx*, int impl);
+
+const char* davo_last_error(const davo_ctx*);   /* NULL handle -> last create error */
+void davo_destroy(davo_ctx*);
+const char* davo_build_info(void);              /* arch / compiler string */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAVO_B200_H */

@@ -1,0 +1,407 @@
+"""CPU restatement of DAVO's pose-estimation forward graph (torch-CPU, fp64 or fp32).
+
+TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.  PARITY UNPINNED (the
+reference holds no golden vectors for this path; TF 1.13 is not installable).
+
+Every function cites the reference file:line it follows (paths relative to the
+reference checkout).  Activations are NHWC at the interface (as in TF) and NCHW
+inside the conv helper only because ``torch.nn.functional.conv2d`` wants it.
+
+TF 1.13 op semantics encoded here (they live in TensorFlow, not in the tree):
+  * ``slim.conv2d``: padding='SAME' (asymmetric: pad_before = total // 2), HWIO
+    weights, bias add, then ReLU; ``rate=r`` is a dilated convolution.
+  * ``tf.image.convert_image_dtype(u8 -> f32)`` multiplies by 1/255.
+  * ``tf.cast(f32 -> i32)`` truncates toward zero; ``tf.one_hot`` of an index
+    outside [0, depth) is an all-zero row.
+  * ``tf.layers.dense`` on [B,1,1,C] contracts the last axis with kernel [C,units].
+  * ``tf.nn.leaky_relu`` default alpha = 0.2.
+"""
+from __future__ import annotations
+
+import math
+import re
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+NUM_CLASSES = 19  # Cityscapes trainIds 0..18 (davo.py:1115, one_hot depth=19)
+
+
+# --------------------------------------------------------------------------- #
+# TF 'SAME' padding (tensorflow/core/framework/common_shape_fns.cc semantics)
+# --------------------------------------------------------------------------- #
+def tf_same_pad(in_size: int, k: int, stride: int, dil: int) -> Tuple[int, int, int]:
+    """Returns (out_size, pad_before, pad_after) of TF padding='SAME'."""
+    out = -(-in_size // stride)
+    eff = (k - 1) * dil + 1
+    total = max((out - 1) * stride + eff - in_size, 0)
+    before = total // 2
+    return out, before, total - before
+
+
+def _round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest (ties away) to TF32's 10-bit mantissa, as cvt.rna.tf32.f32.
+
+    Used only to emulate the tensor-core operand format when a test wants to
+    separate indexing errors from TF32 rounding.
+    """
+    xf = x.to(torch.float32).contiguous()
+    bits = xf.view(torch.int32)
+    bits = (bits + 0x1000) & ~0x1FFF
+    return bits.view(torch.float32).to(x.dtype)
+
+
+def conv2d_same(x_nhwc: torch.Tensor, w_hwio: torch.Tensor, b: Optional[torch.Tensor],
+                stride: int = 1, rate: int = 1, relu: bool = True,
+                tf32: bool = False) -> torch.Tensor:
+    """``slim.conv2d(x, Cout, [k,k], stride=, rate=)`` (nets/posenn.py:211-215, 238-240).
+
+    tf32=True rounds both operands to TF32 first (products then accumulate in
+    the working dtype) -- the arithmetic contract of ``tcgen05.mma.kind::tf32``.
+    """
+    kh, kw, cin, cout = w_hwio.shape
+    _, H, W, C = x_nhwc.shape
+    assert C == cin, (C, cin)
+    _, pt, pb = tf_same_pad(H, kh, stride, rate)
+    _, pl, pr = tf_same_pad(W, kw, stride, rate)
+    x = x_nhwc.permute(0, 3, 1, 2)
+    w = w_hwio.permute(3, 2, 0, 1)
+    if tf32:
+        x = _round_tf32(x)
+        w = _round_tf32(w)
+    x = F.pad(x, (pl, pr, pt, pb))
+    y = F.conv2d(x, w.contiguous(), b, stride=stride, padding=0, dilation=rate)
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+# --------------------------------------------------------------------------- #
+# Attention module
+# --------------------------------------------------------------------------- #
+def _act(name: str):
+    if name == "tanh":
+        return torch.tanh
+    if name == "lrelu":
+        return lambda t: F.leaky_relu(t, 0.2)
+    return torch.relu
+
+
+def se_weights(x_nhwc: torch.Tensor, wts: Dict[str, torch.Tensor], scope: str,
+               activation: str) -> torch.Tensor:
+    """``se(input, name, layer_channels, mode='gp', activation)`` -> [B, units2].
+
+    nets/attention_module.py:54-103: global average pool (:66), dense +
+    activation (:89-94), dense + sigmoid (:96-101); returns the excitation
+    vector only.
+    """
+    pool = x_nhwc.mean(dim=(1, 2))                                       # :66
+    fc1 = _act(activation)(pool @ wts[scope + "/bottleneck_fc/kernel"]
+                           + wts[scope + "/bottleneck_fc/bias"])        # :89-94
+    return torch.sigmoid(fc1 @ wts[scope + "/recover_fc/kernel"]
+                         + wts[scope + "/recover_fc/bias"])             # :96-101
+
+
+def se_block(x_nhwc: torch.Tensor, wts: Dict[str, torch.Tensor], scope: str,
+             activation: str = "relu") -> torch.Tensor:
+    """``se_block(input_feature, name, ratio, mode='gp', activation)``.
+
+    nets/attention_module.py:9-52: same two dense layers, returns
+    ``input_feature * excitation`` (:51).
+    """
+    exc = se_weights(x_nhwc, wts, scope, activation)
+    return x_nhwc * exc[:, None, None, :]
+
+
+def class_gather(seg_f32: torch.Tensor, w19: torch.Tensor) -> torch.Tensor:
+    """``reduce_sum(one_hot(int32(seg), 19) * w, -1)`` -> [B,H,W,1].
+
+    davo.py:1115 (cast + one_hot + squeeze) and davo.py:1178 (multiply +
+    reduce_sum + expand_dims): the per-pixel class weight, 0 for a label
+    outside 0..18.  ``w19`` is [B,19] (SE output) or [19] (static weights).
+    """
+    lab = torch.trunc(seg_f32[..., 0]).to(torch.int64)                   # tf.cast truncates
+    valid = (lab >= 0) & (lab < NUM_CLASSES)
+    idx = lab.clamp(0, NUM_CLASSES - 1)
+    if w19.dim() == 1:
+        a = w19[idx]
+    else:
+        B, H, W = idx.shape
+        a = torch.gather(w19, 1, idx.reshape(B, H * W)).reshape(B, H, W)
+    a = torch.where(valid, a, torch.zeros_like(a))
+    return a[..., None]
+
+
+# --------------------------------------------------------------------------- #
+# PoseNN
+# --------------------------------------------------------------------------- #
+def decouple_sharednet_v0_dilation(tgt: torch.Tensor, src: torch.Tensor,
+                                   wts: Dict[str, torch.Tensor], se_attention=False,
+                                   tf32: bool = False,
+                                   taps: Optional[Dict[str, torch.Tensor]] = None
+                                   ) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+    """nets/posenn.py:189-254 (dropout=False, batch_norm=False).
+
+    Returns (pose [B,1,6] = [rz,ry,rx,tx,ty,tz], (cnv6_rot, cnv6_trans)).
+    ``taps`` (optional dict) receives every intermediate activation.
+    """
+    P = "pose_exp_net/"
+
+    def cv(x, name, stride=1, rate=1, relu=True):
+        return conv2d_same(x, wts[P + name + "/weights"], wts[P + name + "/biases"],
+                           stride=stride, rate=rate, relu=relu, tf32=tf32)
+
+    x = torch.cat([tgt, src], dim=3)                                     # :198
+    c1 = cv(x, "cnv1", stride=2)                                         # :211
+    c2 = cv(c1, "cnv2", stride=2)                                        # :212
+    c3 = cv(c2, "cnv3", rate=2)                                          # :213
+    c4 = cv(c3, "cnv4", rate=4)                                          # :214
+    c5 = cv(c4, "cnv5", rate=8)                                          # :215
+    if taps is not None:
+        taps.update(input=x, cnv1=c1, cnv2=c2, cnv3=c3, cnv4=c4, cnv5=c5)
+    avgs, c6s = {}, {}
+    for name in ("rotation", "translation"):                            # :222
+        br = "pose/" + name + "/"
+        if se_attention is True:                                         # :225-228
+            # NB: cnv5 is re-assigned, so translation's SE sits on top of rotation's.
+            c5 = se_block(c5, wts, P + br + "cnv5_se_attention", "relu")
+            c6 = cv(c5, br + "cnv6", rate=2)
+        elif se_attention == "se_skipadd":                               # :229-233
+            c6 = cv(c5, br + "cnv6", rate=2)
+            c6 = torch.relu(c5 + se_block(c6, wts, P + br + "cnv6_se_attention", "relu"))
+        elif se_attention == "se_replace":                               # :234-236
+            c6 = se_block(c5, wts, P + br + "cnv6_se_attention", "relu")
+        else:
+            c6 = cv(c5, br + "cnv6", rate=2)                             # :238
+        c7 = cv(c6, br + "cnv7", stride=2)                               # :239
+        pred = cv(c7, br + "pred", relu=False)                           # :240
+        avgs[name] = pred.mean(dim=(1, 2))                               # :241
+        c6s[name] = c6
+        if taps is not None:
+            taps["cnv6_" + name] = c6
+            taps["cnv7_" + name] = c7
+            taps["pred_" + name] = pred
+    pose = 0.01 * torch.cat([avgs["rotation"].reshape(-1, 1, 3),
+                             avgs["translation"].reshape(-1, 1, 3)], dim=-1)   # :248-250
+    return pose, (c6s["rotation"], c6s["translation"])
+
+
+# --------------------------------------------------------------------------- #
+# Whole inference graph
+# --------------------------------------------------------------------------- #
+def _unsupported(what):
+    raise NotImplementedError("oracle: variant component not restated: " + what)
+
+
+def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.ndarray,
+                 weights: Dict[str, np.ndarray], dtype=torch.float64, tf32: bool = False,
+                 taps: Optional[dict] = None) -> np.ndarray:
+    """``DAVO.build_pose_test_graph_davo`` + one ``sess.run`` (davo.py:955-1494, 1553-1569).
+
+    img_u8 [B,H,3W,3] uint8; flow [B,4,H,W,2] f32; seg [B,3,H,W,1] f32.
+    Returns pred_poses [B,2,6] as float64 numpy.  Restates the
+    ``-sharedNN-dilatedPoseNN`` family with attention sources se_flow /
+    static / none; other sources raise NotImplementedError.
+    """
+    assert version is not None                                           # davo.py:959
+    if "depth" in version or "disp" in version:                          # davo.py:960
+        _unsupported("depth/disp inputs")
+    wts = {k: torch.as_tensor(np.asarray(v), dtype=dtype) for k, v in weights.items()}
+    B, H, W3, _ = img_u8.shape
+    W = W3 // 3
+    scale = torch.tensor(1.0 / 255.0, dtype=dtype)                        # convert_image_dtype
+    x = torch.as_tensor(img_u8).to(dtype) * scale * 2.0 - 1.0             # davo.py:1519-1522
+    # data_loader.py:537-557 -- centre frame is the target
+    tgt = x[:, :, W:2 * W, :]
+    src0 = x[:, :, 0:W, :]
+    src1 = x[:, :, 2 * W:3 * W, :]
+    fl = torch.as_tensor(flow).to(dtype)
+    sg = torch.as_tensor(seg).to(dtype)
+    pred_flows = [torch.zeros_like(fl[:, 0]), fl[:, 0], fl[:, 1]]        # davo.py:978-982
+    pred_segs = [sg[:, 1], sg[:, 0], sg[:, 2]]                           # davo.py:1000-1004
+
+    # 0. PoseNN-internal SE (davo.py:1010-1017)
+    if "-se_insert" in version:
+        se_attention = True
+    elif "-se_skipadd" in version:
+        se_attention = "se_skipadd"
+    elif "-se_replace" in version:
+        se_attention = "se_replace"
+    else:
+        se_attention = False
+    input_images = [tgt, src0, src1, tgt]                                # davo.py:1019-1024
+    # 1. PoseNN type (davo.py:1027-1049)
+    if "-sharedNN" in version:
+        if "-dilatedPoseNN" in version:
+            pass
+        elif "-dilatedCouplePoseNN" in version:
+            _unsupported("couple_sharednet_v0_dilation")
+        elif "-couplePoseNN" in version:
+            raise NameError("not support `-sharedNN-couplePoseNN' mode.")
+        else:
+            raise NameError("unknown PoseNN type.")
+    else:
+        _unsupported("non-shared PoseNN")
+    if re.search("-cnv6_([0-9]+)", version) is not None:                 # davo.py:1052-1053
+        pass  # width is carried by the weight shapes
+    # 2. inputs (davo.py:1057-1073)
+    m = re.search("^(v[0-9.]+)", version)
+    Version = "v0" if m is None else m.group(1)
+    pred_info = None
+    if "v0" in Version:
+        pass
+    elif "v1" in Version:
+        pred_info = pred_flows + [pred_flows[0]]
+    if "-seglabelid" in version:
+        _unsupported("-seglabelid")
+    # 3.1 SE activation (davo.py:1077-1085)
+    if "-fc_tanh" in version:
+        act = "tanh"
+    elif "-fc_lrelu" in version:
+        act = "lrelu"
+    else:
+        act = "relu"
+    # 3.2 / 3.3 SE inputs (davo.py:1087-1102)
+    se_in = list(pred_flows) + [pred_flows[0]]
+    if "-norm_flow" in version:
+        se_in = [(f - 0.32140523) / 15.384229 for f in se_in]
+    if "-abs_flow_h" in version:
+        se_in = [torch.stack([f[..., 0].abs(), f[..., 1]], -1) for f in se_in]
+    elif "-abs_flow_v" in version:
+        se_in = [torch.stack([f[..., 0], f[..., 1].abs()], -1) for f in se_in]
+    elif "-abs_flow" in version:
+        se_in = [f.abs() for f in se_in]
+    # 3.5 attention maps (davo.py:1114-1400)
+    use_se_flow = False
+    att_w = None
+    if "-se_flow_on_depthseg" in version or "-se_mix" in version:
+        _unsupported("depth/mix attention")
+    elif "-se_flow" in version:                                          # davo.py:1175-1180
+        att, att_w = [], []
+        for i in range(3):
+            w19 = se_weights(se_in[i], wts, "pose_exp_net/se_flow", act)
+            att_w.append(w19)
+            att.append(class_gather(pred_segs[i], w19))
+        use_se_flow = True                                               # davo.py:1404
+    elif re.search("-se_(gp2x2|spp|depth|disp|rgb|seg|SegFlow)", version):
+        _unsupported("attention source in " + version)
+    elif "-no_segmask" in version:                                       # davo.py:1385-1389
+        att = [torch.ones_like(s) for s in pred_segs]
+    elif "-segmask_" in version and "-static" in version:                # davo.py:1390-1394
+        w19 = torch.sigmoid(wts["pose_exp_net/pose_exp_net/seg_channel_weight/weight"])
+        att = [class_gather(s, w19) for s in pred_segs]                  # posenn.py:380-394
+        att[0] = torch.ones_like(att[0])
+    else:                                                                # davo.py:1395-1399
+        w19 = torch.sigmoid(wts["pose_exp_net/pose_exp_net/seg_channel_weight/weight"])
+        att = [class_gather(s, w19) for s in pred_segs]
+    # 4.1 masking (davo.py:1404-1450)
+    a_tgt, a_s0, a_s1 = att
+    if use_se_flow:
+        a_tgt = torch.ones_like(a_tgt)
+        a_ts1 = torch.ones_like(a_tgt)
+    else:
+        a_ts1 = a_tgt
+    amaps = [a_tgt, a_s0, a_s1, a_ts1]
+    if pred_info is not None:
+        pred_info = list(pred_info)
+        if "-segmask_" in version:
+            input_images = [im * a for im, a in zip(input_images, amaps)]
+            if "-segmask_all" in version and ".555" in Version:
+                pred_info[0] = pred_info[0] * a_tgt
+                pred_info[3] = pred_info[3] * a_ts1
+            elif "-segmask_all" in version:
+                pred_info = [pi * a for pi, a in zip(pred_info, amaps)]
+            elif "-segmask_rgb" in version:
+                pass
+        input_images = [torch.cat([im, pi], 3) for im, pi in zip(input_images, pred_info)]
+    else:
+        if "-segmask" in version:
+            input_images = [im * a for im, a in zip(input_images, amaps)]
+    # 4.2 PoseNN x2 with shared weights (davo.py:1453-1458)
+    t0 = {} if taps is not None else None
+    t1 = {} if taps is not None else None
+    pose0, _ = decouple_sharednet_v0_dilation(input_images[0], input_images[1], wts,
+                                              se_attention, tf32, t0)
+    pose1, _ = decouple_sharednet_v0_dilation(input_images[3], input_images[2], wts,
+                                              se_attention, tf32, t1)
+    pred_poses = torch.cat([pose0, pose1], dim=-2)                       # davo.py:1458
+    if taps is not None:
+        taps["attention_maps"] = [a.numpy() for a in (a_tgt, a_s0, a_s1)]
+        taps["attention_weights"] = None if att_w is None else [w.numpy() for w in att_w]
+        taps["pair0"] = {k: v.numpy() for k, v in t0.items()}
+        taps["pair1"] = {k: v.numpy() for k, v in t1.items()}
+    return pred_poses.to(torch.float64).numpy()
+
+
+# --------------------------------------------------------------------------- #
+# Host trajectory composition
+# --------------------------------------------------------------------------- #
+def euler2mat(z, y, x, dtype=np.float32):
+    """utils/geo_utils.py:12-63: clip to [-pi, pi] (:29-31), R = Rx @ Ry @ Rz (:62)."""
+    z = np.clip(np.asarray(z, dtype), -np.pi, np.pi).astype(dtype)
+    y = np.clip(np.asarray(y, dtype), -np.pi, np.pi).astype(dtype)
+    x = np.clip(np.asarray(x, dtype), -np.pi, np.pi).astype(dtype)
+    n = z.shape[0]
+    zmat = np.zeros((n, 3, 3), dtype)
+    ymat = np.zeros((n, 3, 3), dtype)
+    xmat = np.zeros((n, 3, 3), dtype)
+    cz, sz = np.cos(z), np.sin(z)
+    zmat[:, 0, 0], zmat[:, 0, 1] = cz, -sz                               # :41-46
+    zmat[:, 1, 0], zmat[:, 1, 1] = sz, cz
+    zmat[:, 2, 2] = 1
+    cy, sy = np.cos(y), np.sin(y)
+    ymat[:, 0, 0], ymat[:, 0, 2] = cy, sy                                # :48-53
+    ymat[:, 1, 1] = 1
+    ymat[:, 2, 0], ymat[:, 2, 2] = -sy, cy
+    cx, sx = np.cos(x), np.sin(x)
+    xmat[:, 0, 0] = 1                                                    # :55-60
+    xmat[:, 1, 1], xmat[:, 1, 2] = cx, -sx
+    xmat[:, 2, 1], xmat[:, 2, 2] = sx, cx
+    return (xmat @ ymat @ zmat).astype(dtype)                            # :62
+
+
+def pose_vec2mat(vec, dtype=np.float32):
+    """utils/geo_utils.py:93-119: [rz,ry,rx,tx,ty,tz] -> 4x4 (fp32 in the TF graph)."""
+    vec = np.asarray(vec, dtype)
+    n = vec.shape[0]
+    out = np.zeros((n, 4, 4), dtype)
+    out[:, :3, :3] = euler2mat(vec[:, 0], vec[:, 1], vec[:, 2], dtype)
+    out[:, :3, 3] = vec[:, 3:6]
+    out[:, 3, 3] = 1
+    return out
+
+
+def compose_trajectory(pred_poses: np.ndarray) -> np.ndarray:
+    """test_kitti_pose.py:133-149 for seq_length 3.
+
+    pred_poses [N,2,6] in sample order -> absolute poses [N+2,4,4] (fp64):
+    identity, then T(tgt->src0) of the first sample, then inv(T(tgt->src1)) of
+    every sample, chained by right-multiplication.
+    """
+    pred_poses = np.asarray(pred_poses, np.float32)
+    rel = []
+    for s in range(pred_poses.shape[0]):
+        v = np.insert(pred_poses[s], 1, np.zeros((1, 6), np.float32), axis=0)   # :141
+        m = pose_vec2mat(v)                                              # :142
+        if s == 0:
+            rel.append(m[0])                                             # :143-144
+        rel.append(np.linalg.inv(m[2]))                                  # :145
+    prev = np.eye(4).astype(float)
+    out = [prev]
+    for p in rel:                                                        # :147-149
+        prev = np.dot(prev, p)
+        out.append(prev)
+    return np.stack(out)
+
+
+def kitti_lines(traj: np.ndarray) -> List[str]:
+    """test_kitti_pose.py:150-153: 12 ``str(float)`` per line."""
+    return [" ".join(str(float(v)) for v in p[:3, :].reshape(12)) for p in traj]
+
+
+def ate(traj_a: np.ndarray, traj_b: np.ndarray) -> float:
+    """RMSE of translation differences, same origin, no alignment."""
+    d = traj_a[:, :3, 3] - traj_b[:, :3, 3]
+    return float(math.sqrt(np.mean(np.sum(d * d, axis=1))))
