@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Benchmark of the DAVO pose forward path (BASELINE.json metric: frame pairs / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one pass of the hot path (attention front end -> dilated PoseNN -> 6-DoF
+head) over one batch of synthetic 128x416 samples: 128 samples = 256 frame pairs
+per GPU (BASELINE.json configs[1]).  Under torchrun every rank runs its own batch
+(weak scaling) and the poses are all-gathered once per step over NCCL.
+
+Prints ONE JSON line (rank 0).  ``value`` is device-resident throughput, ``e2e``
+the same metric through ``DAVO.inference`` with host numpy inputs (host<->device
+copies inside the timed region), ``roofline`` the dominant kernel (cnv6) against
+the measured tensor peak, ``cpu_baseline`` the oracle's fp32 CPU restatement of
+the reference graph timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VERSION = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh"
+H, W = 128, 416
+FLOP_PER_PAIR = 7780171776            # 2 x 3 890 085 888 MACs, all conv layers
+FLOP_PER_PAIR_LAYER = {               # 2 x MACs per frame pair
+    "cnv1": 2 * 104366080, "cnv2": 2 * 42598400, "cnv3": 2 * 61341696, "cnv4": 2 * 245366784,
+    "cnv5": 2 * 981467136, "cnv6": 2 * 1962934272, "cnv7": 2 * 490733568,
+}
+FRONT_BYTES_PER_PAIR = 3008512        # SURVEY.md 8(d) minimum front-end traffic
+METRIC = "PoseNN+attention frame-pairs/sec @128x416"
+UNIT = "frame-pairs/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "of measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "of fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_oracle_rate(batch, iters, threads=None):
+    """Frame pairs / s of the oracle's fp32 torch-CPU restatement on the host cores."""
+    import torch
+    from davo_b200 import synthetic as S
+    from oracle import davo_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    w = S.init_weights(VERSION)
+    img, flow, seg = S.make_inputs(batch, H, W, seed=4321)
+    O.davo_forward(VERSION, img[:1], flow[:1], seg[:1], w, torch.float32)     # warm
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        O.davo_forward(VERSION, img, flow, seg, w, torch.float32)
+    dt = time.perf_counter() - t0
+    return 2 * batch * iters / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference graph's CPU restatement (oracle port) on host cores.
+
+    TensorFlow 1.13 cannot be installed here, so this arm times the oracle, with
+    every host thread torch will use, on a bounded sample of the same workload.
+    """
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 16
+    cores = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_oracle_rate(batch, 1, cores)
+    rate, dt, thr = cpu_oracle_rate(batch, max(args.steps, 1), cores)
+    sample = "%d steps x %d samples (%d frame pairs each) of the 128-sample batch, fp32 torch-CPU" % (
+        max(args.steps, 1), batch, 2 * batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 256 frame pairs (128 samples) @128x416, headline variant; "
+                               "bounded CPU sample", "version": VERSION},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port of the TF 1.13 graph (TF not installable); not TensorFlow itself",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from davo_b200 import synthetic as S
+    from davo_b200.davo import DAVO
+    from davo_b200 import parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the davo_b200 path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B = args.batch
+    peaks, peak_kind = measured_peaks()
+
+    weights = S.init_weights(VERSION)
+    img, flow, seg = S.make_inputs(B, H, W, seed=1234 + rank)
+    d_img, d_flow, d_seg = (torch.as_tensor(x).to(dev) for x in (img, flow, seg))
+    system = DAVO(version=VERSION)
+    system.setup_inference(H, W, "davo", 3, B, d_img, input_flow=d_flow, input_seglabel=d_seg,
+                           device=local, micro_batch=args.micro_batch)
+    system.load_weights(weights)
+
+    def step():
+        out = system.inference(None, "pose", as_torch=True)["pose"]
+        if world > 1:
+            out = parallel.gather_poses(out, world * B)
+        return out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = system.last_launch_count() * args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * 2 * B * args.steps / (ms * 1e-3)
+
+    # end to end: host numpy in, host numpy out, through the public API
+    h_img, h_flow, h_seg = (torch.as_tensor(x).pin_memory().numpy() for x in (img, flow, seg))
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        system.inference(None, "pose", inputs=(h_img, h_flow, h_seg))
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pose_host = system.inference(None, "pose", inputs=(h_img, h_flow, h_seg))["pose"]
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * 2 * B * e2e_steps / float(dt.item())
+    h2d = int(h_img.nbytes + h_flow.nbytes + h_seg.nbytes)
+    d2h = int(pose_host.nbytes)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # dominant kernel (cnv6) timed alone, live, with CUDA events on the launch stream
+    layer_ms, npairs = system.profile_layers(iters=20)
+    dom = max((k for k in layer_ms if k.startswith("cnv")), key=lambda k: layer_ms[k])
+    peak_tf32 = peaks["bf16_tflops"] / 2.0
+    achieved = FLOP_PER_PAIR_LAYER[dom] * npairs / (layer_ms[dom] * 1e-3) / 1e12
+    conv_ms = sum(v for k, v in layer_ms.items() if k.startswith("cnv"))
+    stack_tflops = FLOP_PER_PAIR * npairs / (conv_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "conv_tc_kernel<%s>" % dom, "achieved": achieved,
+        "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": None,
+        "peak_note": "TF32 dense = MEASURED_PEAKS bf16_tflops (burst) / 2, %s" % peak_kind,
+        "pairs_per_launch": npairs, "layer_ms": layer_ms,
+        "conv_stack_tflops": stack_tflops, "conv_stack_frac": stack_tflops / peak_tf32,
+        "front_end_gbs": FRONT_BYTES_PER_PAIR * npairs / (layer_ms["front"] * 1e-3) / 1e9,
+        "front_end_frac_hbm": FRONT_BYTES_PER_PAIR * npairs / (layer_ms["front"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        "whole_step_frac": value / world * FLOP_PER_PAIR / 1e12 / (peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0),
+    }
+    cpu = None
+    if world == 1 or True:
+        rate, cdt, thr = cpu_oracle_rate(8, 2)
+        cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
+               "sample": "2 x 8 samples (16 frame pairs each) of the same workload, fp32 torch-CPU oracle, %.1f s" % cdt}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": "configs[1]: 256 frame pairs (128 samples) per GPU @128x416, headline variant",
+                   "version": VERSION, "samples_per_gpu": B, "frame_pairs_per_step": world * 2 * B,
+                   "micro_batch_pairs": npairs,
+                   "l2": "inputs (361 MB per step) exceed the 126 MB L2; no flush needed",
+                   "parallelism": "sample-sharded x%d, NCCL all-gather of poses" % world},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="samples per GPU per step (2 frame pairs each)")
+    ap.add_argument("--micro-batch", type=int, default=0, help="frame pairs per pass of the conv stack")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

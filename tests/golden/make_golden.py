@@ -1,0 +1,50 @@
+"""Regenerates tests/golden/*.npz from the oracle (fp64) on seeded synthetic inputs.
+
+PARITY UNPINNED: the reference holds no golden vectors for this path and TF 1.13
+is not installable, so these fixtures pin the ORACLE (oracle/davo_oracle.py,
+cross-checked by oracle/posenn_ref.c), not the reference run itself.  Inputs and
+weights are regenerated from seeds (davo_b200/synthetic.py), so only outputs are
+stored.  Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from davo_b200 import synthetic as S          # noqa: E402
+from oracle import davo_oracle as O           # noqa: E402
+
+CASES = {
+    "headline": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh",
+    "no_segmask": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-no_segmask",
+    "static": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-static",
+    "segmask_rgb": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_rgb-se_flow-abs_flow-fc_tanh",
+    "v0_lrelu": "v0-sharedNN-dilatedPoseNN-cnv6_64-segmask_rgb-se_flow-abs_flow_h-norm_flow-fc_lrelu",
+}
+GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)
+
+
+def main():
+    out = {}
+    for key, ver in CASES.items():
+        w = S.init_weights(ver, seed=GOLDEN["weight_seed"], random_bias=True)
+        img, flow, seg = S.make_inputs(GOLDEN["batch"], GOLDEN["height"], GOLDEN["width"],
+                                       seed=GOLDEN["input_seed"], bad_label_frac=GOLDEN["bad_label_frac"])
+        taps = {}
+        pose = O.davo_forward(ver, img, flow, seg, w, torch.float64, taps=taps)
+        out[key + "/pose"] = pose
+        if taps["attention_weights"] is not None:
+            out[key + "/att_w"] = np.stack(taps["attention_weights"][1:], 1)     # [B,2,19] src0, src1
+        # per-layer checksums (mean and mean-abs) of pair 0 / sample 0
+        for name in ("input", "cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6_rotation", "cnv7_translation"):
+            a = taps["pair0"][name][0]
+            out[key + "/stat/" + name] = np.array([a.mean(), np.abs(a).mean(), a.max()])
+        print(key, pose[0, 0])
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "poses.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

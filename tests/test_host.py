@@ -1,0 +1,219 @@
+"""CPU tests of the host side: geometry, sharding, C-ABI exports, DAVO wrapper errors."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from davo_b200 import _capi, geo_utils, parallel
+from davo_b200.davo import DAVO
+from oracle import davo_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADLINE = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh"
+
+
+# ------------------------------------------------------------------ geometry --
+def test_pose_vec2mat_matches_oracle_and_is_rotation():
+    rng = np.random.default_rng(0)
+    v = rng.normal(0, 0.3, size=(50, 6)).astype(np.float32)
+    v[0, :3] = [4.0, -5.0, 3.5]                      # beyond +-pi: clipped (geo_utils.py:29-31)
+    m = geo_utils.pose_vec2mat(v)
+    np.testing.assert_allclose(m, O.pose_vec2mat(v), atol=1e-6)
+    r = m[:, :3, :3].astype(np.float64)
+    np.testing.assert_allclose(r @ r.transpose(0, 2, 1), np.broadcast_to(np.eye(3), r.shape), atol=1e-5)
+    np.testing.assert_allclose(m[:, :3, 3], v[:, 3:])
+    c = np.cos(np.float32(np.pi))
+    assert abs(m[0, 0, 0] - c * c) < 1e-6           # rz, ry clipped to pi: cos(pi)^2
+
+
+def test_euler_order_is_rx_ry_rz():
+    z, y, x = 0.3, -0.2, 0.5
+    m = geo_utils.euler2mat([z], [y], [x])[0].astype(np.float64)
+    rz = np.array([[np.cos(z), -np.sin(z), 0], [np.sin(z), np.cos(z), 0], [0, 0, 1]])
+    ry = np.array([[np.cos(y), 0, np.sin(y)], [0, 1, 0], [-np.sin(y), 0, np.cos(y)]])
+    rx = np.array([[1, 0, 0], [0, np.cos(x), -np.sin(x)], [0, np.sin(x), np.cos(x)]])
+    np.testing.assert_allclose(m, rx @ ry @ rz, atol=1e-6)
+
+
+def test_compose_trajectory_matches_reference_loop():
+    rng = np.random.default_rng(1)
+    poses = rng.normal(0, 0.05, size=(40, 2, 6)).astype(np.float32)
+    traj = geo_utils.compose_trajectory(poses)
+    ref = O.compose_trajectory(poses)
+    assert traj.shape == (42, 4, 4)
+    np.testing.assert_allclose(traj, ref, atol=1e-9)
+    np.testing.assert_array_equal(traj[0], np.eye(4))
+    # the second pose is T(tgt->src0) of the first sample; then inverses of tgt->src1
+    np.testing.assert_allclose(traj[1], geo_utils.pose_vec2mat(poses[:1, 0])[0], atol=1e-7)
+    np.testing.assert_allclose(traj[2], traj[1] @ np.linalg.inv(geo_utils.pose_vec2mat(poses[:1, 1])[0]), atol=1e-7)
+
+
+def test_kitti_text_format(tmp_path):
+    poses = np.zeros((3, 2, 6), np.float32)
+    poses[:, :, 5] = 1.0
+    traj = geo_utils.compose_trajectory(poses)
+    p = tmp_path / "09-pred_kitti_pose.txt"
+    geo_utils.write_kitti_trajectory(str(p), traj)
+    lines = p.read_text().strip().split("\n")
+    assert len(lines) == 5 and all(len(l.split()) == 12 for l in lines)
+    assert lines == O.kitti_lines(traj)
+    assert lines[0].split()[0] == "1.0"              # str(float) formatting
+
+
+def _mat2euler(r):
+    """Inverse of euler2mat for R = Rx Ry Rz (reference utils/geo_utils.py:66-91, branch f1)."""
+    cy = np.sqrt(r[2, 2] ** 2 + r[1, 2] ** 2)
+    return np.arctan2(-r[0, 1], r[0, 0]), np.arctan2(r[0, 2], cy), np.arctan2(-r[1, 2], r[2, 2])
+
+
+def _gt_trajectory():
+    path = "/root/reference/kitti_benchmark/data/odometry/poses/00.txt"
+    if os.path.exists(path):                          # real KITTI motion when the checkout is present
+        rows = np.loadtxt(path)[:300].reshape(-1, 3, 4)
+        gt = np.tile(np.eye(4), (rows.shape[0], 1, 1))
+        gt[:, :3, :] = rows
+        return gt
+    rng = np.random.default_rng(2)
+    gt = [np.eye(4)]
+    for _ in range(299):
+        step = geo_utils.pose_vec2mat(rng.normal(0, [0.005, 0.02, 0.005, 0.03, 0.02, 0.8], size=(1, 6)))[0]
+        gt.append(gt[-1] @ step.astype(np.float64))
+    return np.stack(gt)
+
+
+def test_ground_truth_round_trip_through_pose_vectors():
+    """encode GT steps as the network's [rz,ry,rx,t] vectors -> compose -> the GT trajectory again."""
+    gt = _gt_trajectory()
+    n = gt.shape[0] - 2                               # samples for a stream of n+2 frames
+    poses = np.zeros((n, 2, 6), np.float32)
+    for s in range(n):
+        # pose[s,1] is tgt->src1 with tgt = frame s+1: inv(step s+1 -> s+2) (test_kitti_pose.py:145)
+        t_fwd = np.linalg.inv(gt[s + 1]) @ gt[s + 2]
+        m = np.linalg.inv(t_fwd)
+        poses[s, 1, :3] = _mat2euler(m[:3, :3])
+        poses[s, 1, 3:] = m[:3, 3]
+    first = np.linalg.inv(gt[0]) @ gt[1]              # pose[0,0] = tgt->src0 of the first sample
+    poses[0, 0, :3] = _mat2euler(first[:3, :3])
+    poses[0, 0, 3:] = first[:3, 3]
+    traj = geo_utils.compose_trajectory(poses)
+    assert traj.shape == gt.shape
+    assert O.ate(traj, gt) < 2e-3 * max(1.0, np.abs(gt[:, :3, 3]).max() / 100)
+
+
+# ------------------------------------------------------------------ sharding --
+def test_complete_batch_size_and_valid_sample():
+    assert parallel.complete_batch_size([1, 2, 3], 2) == [1, 2, 3, 3]
+    assert parallel.complete_batch_size([1, 2, 3, 4], 2) == [1, 2, 3, 4]
+    frames = ["09 %06d" % i for i in range(5)] + ["10 000000"]
+    assert [parallel.is_valid_sample(frames, i, 3) for i in range(6)] == [False, True, True, True, False, False]
+
+
+@pytest.mark.parametrize("n,world", [(4539, 8), (4539, 2), (7, 4), (3, 4), (16, 4)])
+def test_shard_ranges_cover_stream_in_order(n, world):
+    seen = []
+    for r in range(world):
+        idx = parallel.padded_indices(n, r, world)
+        assert len(idx) == -(-n // world)
+        seen.extend(idx)
+    assert seen[:n] == list(range(n))
+    assert all(i == n - 1 for i in seen[n:])
+
+
+def test_gloo_world2_gather_matches_single_process():
+    """world_size 2, gloo: the N>1 host path (shard -> local 'forward' -> all-gather -> trim)."""
+    script = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from davo_b200 import parallel
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 11
+full = torch.arange(n * 12, dtype=torch.float32).reshape(n, 2, 6)     # stand-in for per-sample poses
+idx = parallel.padded_indices(n, rank, world)
+local = full[idx] * 2 + 1                                               # the per-rank 'forward'
+out = parallel.gather_poses(local, n)
+assert out.shape == (n, 2, 6) and torch.equal(out, full * 2 + 1), (rank, out)
+dist.destroy_process_group()
+print("OK", rank)
+''' % ROOT
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", "--no-python",
+                          sys.executable, "-c", script],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("OK") == 2
+
+
+# ------------------------------------------------------------------- C ABI ----
+def _declared_functions():
+    hdr = open(os.path.join(ROOT, "include", "davo_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(davo_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.load()                                # builds with nvcc if stale (no GPU needed)
+    names = _declared_functions()
+    assert "davo_forward" in names and "davo_create" in names and len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(_capi.SYMBOLS)
+    assert b"sm_100a" in lib.davo_build_info()
+
+
+def test_library_contains_tcgen05_and_tma_sass():
+    sass = subprocess.run(["cuobjdump", "-sass", _capi.lib_path()], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump not available")
+    assert "UTCHMMA" in sass or "UTCMMA" in sass      # tcgen05.mma
+    assert "UTMALDG" in sass                          # TMA tensor loads
+    assert "LDTM" in sass                             # tcgen05.ld
+
+
+def test_create_without_gpu_fails_loudly_not_silently():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _capi.load()
+    cfg = _capi.DavoConfigC(H=128, W=416, max_batch=1, posenn=0, cnv6_out=128, in_mode=1, att_src=1,
+                            att_tgt_ones=1, mask_mode=2, se_act=1, flow_abs=1)
+    h = ctypes.c_void_p()
+    rc = lib.davo_create(ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b"no CPU fallback" in lib.davo_last_error(None)
+    sysm = DAVO(version=HEADLINE)
+    with pytest.raises(RuntimeError, match="davo_create failed"):
+        sysm.setup_inference(128, 416, "davo", 3, 1)
+
+
+def test_create_rejects_bad_config_before_touching_cuda():
+    lib = _capi.load()
+    h = ctypes.c_void_p()
+    cfg = _capi.DavoConfigC(H=100, W=416, max_batch=1, cnv6_out=128, in_mode=1)
+    assert lib.davo_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
+    assert b"multiples of 8" in lib.davo_last_error(None)
+    cfg = _capi.DavoConfigC(H=128, W=416, max_batch=1, cnv6_out=128, in_mode=1, posenn=3)
+    assert lib.davo_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
+
+
+def test_wrapper_raises_like_the_reference():
+    with pytest.raises(NameError, match="unknown PoseNN type."):
+        DAVO(version="v1-sharedNN").setup_inference(128, 416, "davo", 3, 1)
+    with pytest.raises(AssertionError):
+        DAVO().setup_inference(128, 416, "davo", 3, 1)
+    # any other mode builds nothing, as in the reference (davo.py:1548)
+    DAVO(version=HEADLINE).setup_inference(128, 416, "other", 3, 1)
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "davo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

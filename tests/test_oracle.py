@@ -1,0 +1,123 @@
+"""CPU tests of the oracle itself (it is the checker, so it gets checked first)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from davo_b200 import synthetic as S
+from davo_b200 import version as V
+from oracle import c_ref
+from oracle import davo_oracle as O
+from tests.golden import make_golden as G
+
+HEADLINE = G.CASES["headline"]
+GOLD = np.load(os.path.join(os.path.dirname(G.__file__), "poses.npz"))
+
+
+def test_tf_same_padding_cases():
+    # the three strided layers at 128x416 and the dilated ones
+    assert O.tf_same_pad(128, 7, 2, 1) == (64, 2, 3)
+    assert O.tf_same_pad(416, 7, 2, 1) == (208, 2, 3)
+    assert O.tf_same_pad(64, 5, 2, 1) == (32, 1, 2)
+    assert O.tf_same_pad(32, 3, 2, 1) == (16, 0, 1)
+    assert O.tf_same_pad(104, 3, 2, 1) == (52, 0, 1)
+    assert O.tf_same_pad(32, 3, 1, 8) == (32, 8, 8)
+    assert O.tf_same_pad(33, 3, 2, 1) == (17, 1, 1)     # odd input: symmetric again
+
+
+def test_conv_same_matches_manual_loop():
+    rng = np.random.default_rng(0)
+    x = torch.tensor(rng.normal(size=(1, 7, 9, 3)))
+    w = torch.tensor(rng.normal(size=(3, 3, 3, 4)))
+    b = torch.tensor(rng.normal(size=(4,)))
+    for stride, rate in ((1, 1), (2, 1), (1, 2)):
+        y = O.conv2d_same(x, w, b, stride=stride, rate=rate, relu=False).numpy()
+        Ho, pt, _ = O.tf_same_pad(7, 3, stride, rate)
+        Wo, pl, _ = O.tf_same_pad(9, 3, stride, rate)
+        ref = np.zeros((Ho, Wo, 4))
+        for oh in range(Ho):
+            for ow in range(Wo):
+                acc = b.numpy().copy()
+                for ty in range(3):
+                    for tx in range(3):
+                        ih, iw = oh * stride + ty * rate - pt, ow * stride + tx * rate - pl
+                        if 0 <= ih < 7 and 0 <= iw < 9:
+                            acc += x[0, ih, iw].numpy() @ w[ty, tx].numpy()
+                ref[oh, ow] = acc
+        np.testing.assert_allclose(y[0], ref, rtol=1e-12, atol=1e-12)
+
+
+def test_class_gather_out_of_range_and_truncation():
+    seg = torch.tensor([[[[0.0], [18.0], [19.0], [255.0]], [[-1.0], [3.9], [-0.5], [7.0]]]])
+    w = torch.arange(1, 20, dtype=torch.float64)[None]
+    a = O.class_gather(seg, w)[0, ..., 0].numpy()
+    # 19, 255, -1 -> 0; 3.9 truncates to 3; -0.5 truncates to 0 (class 0)
+    np.testing.assert_array_equal(a, [[1, 19, 0, 0], [0, 4, 1, 8]])
+
+
+def test_round_tf32_emulation():
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -1.0 - 2 ** -11, 3.14159265], dtype=torch.float32)
+    r = O._round_tf32(x).numpy()
+    assert r[0] == 1.0 and r[1] == np.float32(1.0 + 2 ** -10) and r[2] == np.float32(1.0 + 2 ** -10)
+    assert r[3] == np.float32(-1.0 - 2 ** -10)            # ties away from zero
+    assert abs(r[4] - 3.14159265) < 2 ** -10
+
+
+@pytest.mark.parametrize("key", ["headline", "static", "v0_lrelu", "no_segmask"])
+def test_c_restatement_agrees_with_torch_restatement(key):
+    ver = G.CASES[key]
+    w = S.init_weights(ver, random_bias=True)
+    img, flow, seg = S.make_inputs(1, 40, 56, seed=7, seg_block=8, bad_label_frac=0.02)
+    pc, aw = c_ref.forward(V.parse_version(ver).as_dict(), img, flow, seg, w)
+    taps = {}
+    pt = O.davo_forward(ver, img, flow, seg, w, torch.float64, taps=taps)
+    np.testing.assert_allclose(pc, pt, rtol=1e-10, atol=1e-14)
+    if taps["attention_weights"] is not None:
+        np.testing.assert_allclose(aw[0, 0], taps["attention_weights"][1][0], rtol=1e-12)
+        np.testing.assert_allclose(aw[0, 1], taps["attention_weights"][2][0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("key", list(G.CASES))
+def test_oracle_reproduces_committed_golden(key):
+    ver = G.CASES[key]
+    g = G.GOLDEN
+    w = S.init_weights(ver, seed=g["weight_seed"], random_bias=True)
+    img, flow, seg = S.make_inputs(1, g["height"], g["width"], seed=g["input_seed"],
+                                   bad_label_frac=g["bad_label_frac"])
+    # inputs are generated batch-major from one stream: regenerate the full batch, use sample 0
+    img, flow, seg = S.make_inputs(g["batch"], g["height"], g["width"], seed=g["input_seed"],
+                                   bad_label_frac=g["bad_label_frac"])
+    pose = O.davo_forward(ver, img[:1], flow[:1], seg[:1], w, torch.float64)
+    np.testing.assert_allclose(pose[0], GOLD[key + "/pose"][0], rtol=1e-9, atol=1e-13)
+
+
+def test_fp32_oracle_close_to_fp64_oracle():
+    w = S.init_weights(HEADLINE, random_bias=True)
+    img, flow, seg = S.make_inputs(1, 64, 96, seed=3)
+    p64 = O.davo_forward(HEADLINE, img, flow, seg, w, torch.float64)
+    p32 = O.davo_forward(HEADLINE, img, flow, seg, w, torch.float32)
+    assert np.abs(p32 - p64).max() < 1e-6
+
+
+def test_target_attention_is_ones_in_se_flow_mode():
+    # davo.py:1404-1412: the SE result for the (all-zero) target flow is discarded
+    w = S.init_weights(HEADLINE)
+    img, flow, seg = S.make_inputs(1, 32, 48, seed=5)
+    taps = {}
+    O.davo_forward(HEADLINE, img, flow, seg, w, torch.float64, taps=taps)
+    assert np.all(taps["attention_maps"][0] == 1.0)
+    assert taps["attention_maps"][1].min() > 0 and taps["attention_maps"][1].max() < 1
+    # tgt channels of the PoseNN input are the unmasked image; flow slots are zero
+    x = taps["pair0"]["input"][0]
+    assert np.all(x[..., 3:5] == 0)
+    np.testing.assert_allclose(x[..., :3], img[0, :, 48:96].astype(np.float64) / 255 * 2 - 1, atol=1e-12)
+
+
+def test_unsupported_variants_raise():
+    w = S.init_weights(HEADLINE)
+    img, flow, seg = S.make_inputs(1, 32, 48)
+    with pytest.raises(NameError):
+        O.davo_forward("v1-sharedNN-couplePoseNN", img, flow, seg, w)
+    with pytest.raises(NameError):
+        O.davo_forward("v1-sharedNN", img, flow, seg, w)

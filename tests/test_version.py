@@ -1,0 +1,73 @@
+"""Table test of the version-string parser against doc/arch-variants.md and davo.py's chain."""
+import pytest
+
+from davo_b200 import version as V
+
+BASE = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128"
+
+
+def test_headline_variant():
+    c = V.parse_version(BASE + "-segmask_all-se_flow-abs_flow-fc_tanh")
+    assert (c.posenn, c.cnv6_out, c.in_mode) == (V.POSENN_DECOUPLE_SHARED_DIL, 128, 1)
+    assert (c.att_src, c.att_tgt_ones, c.mask_mode) == (V.ATT_SE_FLOW, 1, V.MASK_ALL)
+    assert (c.se_act, c.flow_abs, c.flow_norm, c.posenn_se) == (V.ACT_TANH, V.ABS_BOTH, 0, V.PSE_NONE)
+
+
+@pytest.mark.parametrize("suffix,att,tgt1,mask", [
+    ("-no_segmask", V.ATT_NONE, 1, V.MASK_OFF),
+    ("-segmask_all-static", V.ATT_STATIC, 1, V.MASK_ALL),
+    ("-segmask_rgb-static", V.ATT_STATIC, 1, V.MASK_RGB),
+    ("-segmask_all", V.ATT_STATIC, 0, V.MASK_ALL),           # final else of the chain (davo.py:1395)
+    ("-segmask_rgb-se_flow", V.ATT_SE_FLOW, 1, V.MASK_RGB),
+])
+def test_attention_and_mask_modes(suffix, att, tgt1, mask):
+    c = V.parse_version(BASE + suffix)
+    assert (c.att_src, c.att_tgt_ones, c.mask_mode) == (att, tgt1, mask)
+
+
+def test_order_sensitive_tokens():
+    assert V.parse_version(BASE + "-se_flow-abs_flow_h").flow_abs == V.ABS_H      # _h before bare token
+    assert V.parse_version(BASE + "-se_flow-abs_flow_v").flow_abs == V.ABS_V
+    assert V.parse_version(BASE + "-se_flow-abs_flow").flow_abs == V.ABS_BOTH
+    assert V.parse_version(BASE + "-se_flow-fc_lrelu").se_act == V.ACT_LRELU
+    assert V.parse_version(BASE + "-se_flow-fc_relu").se_act == V.ACT_RELU        # no test for it: default
+    assert V.parse_version(BASE + "-se_flow-norm_flow").flow_norm == 1
+
+
+def test_version_tag_and_cnv6():
+    assert V.parse_version("sharedNN-x-sharedNN-dilatedPoseNN").in_mode == 0      # no ^v tag -> v0
+    assert V.parse_version("v0-sharedNN-dilatedPoseNN").in_mode == 0
+    assert V.parse_version("v1.555-sharedNN-dilatedPoseNN-segmask_all-se_flow").mask_mode == V.MASK_ALL_555
+    assert V.parse_version("v1-sharedNN-dilatedPoseNN-cnv6_64").cnv6_out == 64
+    assert V.parse_version("v1-sharedNN-dilatedPoseNN").cnv6_out == 128
+
+
+def test_posenn_selection_and_errors():
+    assert V.parse_version("v1-dilatedPoseNN").posenn == V.POSENN_DECOUPLE_DIL
+    assert V.parse_version("v1-dilatedCouplePoseNN").posenn == V.POSENN_COUPLE_DIL
+    assert V.parse_version("v1-couplePoseNN").posenn == V.POSENN_COUPLE
+    assert V.parse_version("v1").posenn == V.POSENN_DECOUPLE
+    assert V.parse_version("v1-sharedNN-dilatedCouplePoseNN").posenn == V.POSENN_COUPLE_SHARED_DIL
+    with pytest.raises(NameError, match="not support `-sharedNN-couplePoseNN' mode."):
+        V.parse_version("v1-sharedNN-couplePoseNN")
+    with pytest.raises(NameError, match="unknown PoseNN type."):
+        V.parse_version("v1-sharedNN")
+    with pytest.raises(AssertionError):
+        V.parse_version(None)
+
+
+def test_posenn_internal_se_tokens():
+    assert V.parse_version(BASE + "-no_segmask-se_insert").posenn_se == V.PSE_INSERT
+    assert V.parse_version(BASE + "-se_skipadd").posenn_se == V.PSE_SKIPADD
+    assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
+
+
+@pytest.mark.parametrize("tok", ["-se_seg_wo_tgt", "-se_rgb_wo_tgt_to_seg", "-se_gp2x2_flow", "-se_mixSegFlow"])
+def test_unbuilt_sources_fail_loudly(tok):
+    with pytest.raises(NotImplementedError):
+        V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
+
+
+def test_depth_variants_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-fc_tanh")
