@@ -2,45 +2,58 @@
 // fp32 accumulate in TMEM), operands fed by TMA.  One kernel serves every conv
 // of the PoseNN stack (reference nets/posenn.py:211-215, 238-240):
 //
-//   out[pixel, n] = act( bias[n] + sum_{kstep} A_kstep[pixel, 0:32] . B_kstep[n, 0:32] )
+//   out[pixel, n] = act( bias[n] + sum_{tap} A_tap[pixel, 0:32] . B_tap[n, 0:32] )
 //
-// * M tile = 128 output pixels = a 16 (rows) x 8 (cols) patch of one frame pair.
-// * A K-step is one 32-float (128 B) slab of the reduction axis: a filter tap
-//   (or, for the thin strided layers, two horizontally adjacent taps) x 32
-//   input channels.  Its A operand is ONE 5-D TMA box {32 ch, 8 w, 1, 16 h, 1}
-//   of the NHWC activation, placed by signed coordinates, so TF-'SAME' padding
-//   (asymmetric included) is TMA's out-of-bounds zero fill and dilation is just
-//   the tap offset -- no im2col buffer, no space-to-batch.
-// * Stride-2 layers view the input as [N][H/2][2][W/2][2*C]: a tap becomes a
-//   unit-stride box at one (row parity, column parity) of that view.
-// * The box lands as 128 rows x 128 B with SWIZZLE_128B = the K-major UMMA
-//   operand layout; B (weights, pre-packed [kstep][Cout][32], TF32-rounded) is
-//   a 2-D TMA box of the same form.
+// * M tile = 128 output pixels = a 16 (rows) x 8 (cols) block of one frame pair.
+// * A "tap" is one 32-float (128 B) slab of the reduction axis: a filter tap (or,
+//   for the thin strided layers, two horizontally adjacent taps) x 32 input
+//   channels.
+// * The A operand is never gathered per tap.  A PATCH -- the tile's input halo,
+//   {32 ch, Wp cols, 1, Hp rows, 1} of the NHWC activation -- is loaded ONCE by
+//   a 5-D TMA box placed with signed coordinates, so TF-'SAME' padding (asymmetric
+//   included) is TMA's out-of-bounds zero fill.  The box lands as Hp*Wp rows of
+//   128 B with SWIZZLE_128B.  Every tap of the patch is then just a different
+//   UMMA descriptor: start address = patch + (row*Wp + col)*128 B, 8-row groups
+//   SBO = Wp*128 B apart.  (The hardware swizzle is a function of the absolute
+//   shared-memory address, so a row-shifted window needs no re-layout -- measured,
+//   tools/experiments/desc_shift.cu.)  Dilation is only a tap offset: no im2col
+//   buffer, no space-to-batch, each input byte crosses L2->SM once per tile.
+// * Stride-2 layers view the input as [N][H/2][2][W/2][2*C]: a tap is a unit-stride
+//   window at one (row parity, column parity) of that view; one patch per parity.
+// * B (weights, pre-packed [tap][Cout][32], TF32-rounded) is either streamed
+//   through a ring (one 2-D TMA box per tap) or, for the thin layers, loaded once
+//   and kept resident in shared memory for the CTA's whole life.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA
-// issuer, warps 2-5 epilogue (TMEM -> registers -> bias/ReLU -> global, or the
-// spatial-sum epilogue of cnv7).  Accumulators are double-buffered in TMEM so
-// the epilogue of tile i overlaps the main loop of tile i+1.  Persistent CTAs
-// walk tiles round-robin.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
+// warps 2-5 epilogue (TMEM -> registers -> bias/ReLU -> global, or the spatial-sum
+// epilogue of cnv7).  Accumulators are double-buffered in TMEM so the epilogue of
+// tile i overlaps the main loop of tile i+1.  Persistent CTAs walk tiles round-robin.
 #pragma once
 #include "ptx.cuh"
 
 namespace davo {
 
-constexpr int kMaxKSteps = 72;
+constexpr int kMaxPatches = 16;
+constexpr int kMaxTaps = 144;
 constexpr int kTileM = 128;
 constexpr int kTileH = 16;
 constexpr int kTileW = 8;
 constexpr int kSlabBytes = 128;                     // 32 tf32
-constexpr int kABytes = kTileM * kSlabBytes;        // 16 KB
 constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 226 * 1024;             // of the 227 KB a CTA may own
 
-struct KStep {
-  int16_t c;     // inner (channel-axis) start coordinate, before the group offset
-  int8_t dw;     // column offset added to the tile's first output column
-  int8_t par;    // coordinate on the row-parity axis (0 for stride-1 layers)
-  int8_t dh;     // row offset added to the tile's first output row
-  int8_t pad_[3];
+struct PatchDesc {
+  int16_t c;        // inner (channel-axis) start coordinate, before the group offset
+  int8_t dw;        // patch origin relative to the tile's first output column
+  int8_t par;       // coordinate on the row-parity axis (0 for stride-1 layers)
+  int8_t dh;        // patch origin relative to the tile's first output row
+  uint8_t ntaps;
+  uint16_t tap0;    // first entry in taps[]
+};
+struct TapDesc {
+  uint16_t a_off;   // window origin inside the patch, in 128-B rows: row * Wp + col
+  uint16_t b_idx;   // weight slab index: B rows [b_idx * BN, +BN)
 };
 
 enum { EPI_STORE_RELU = 0, EPI_SUM_RELU = 1 };
@@ -51,40 +64,53 @@ struct ConvParams {
   int Hout, Wout;
   int out_stride;       // floats per output pixel (all groups)
   int cin_group_off;    // inner-coordinate offset of group g = g * cin_group_off
-  int n_ksteps;
+  int n_patches, n_taps;          // per tile
+  int patch_w;                    // Wp
+  int patch_bytes;                // Hp * Wp * 128 (what TMA delivers)
+  int patch_stage_bytes;          // rounded up to 1024
+  int p_stages, b_stages;         // ring depths (b_stages unused when B is resident)
   float* out;           // EPI_STORE: [pairs][Hout][Wout][out_stride]
   const float* bias;    // [groups * BN]
   float* sum_out;       // EPI_SUM:   [pairs][groups][tiles_h*tiles_w][4][BN]
-  KStep ks[kMaxKSteps];
+  PatchDesc patches[kMaxPatches];
+  TapDesc taps[kMaxTaps];
 };
 
 template <int BN>
 struct ConvCfg {
   static constexpr int kBBytes = BN * kSlabBytes;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccStride = BN < 32 ? 32 : BN;             // TMEM columns per accumulator
   static constexpr int kTmemCols = 2 * kAccStride;                 // power of two for BN in {16..256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int EPI>
+// Shared-memory matrix descriptor for a window of a patch (K-major, SWIZZLE_128B):
+// rows 128 B apart, 8-row groups `sbo_bytes` apart.
+__device__ __forceinline__ uint64_t umma_desc_patch(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int EPI, bool B_RESIDENT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
-  constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-B aligned stage bases.
+  // SWIZZLE_128B operands: keep every stage base 1024-B aligned.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
-  uint64_t* full = bars;                 // [S]  TMA -> MMA
-  uint64_t* empty = bars + S;            // [S]  MMA -> TMA
-  uint64_t* acc_full = bars + 2 * S;     // [2]  MMA -> epilogue
-  uint64_t* acc_empty = bars + 2 * S + 2;  // [2]  epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  const int PS = p.p_stages;
+  const int BS = B_RESIDENT ? p.n_taps * p.groups : p.b_stages;   // resident: every slab has a home
+  uint8_t* smem_p = smem;
+  uint8_t* smem_b = smem + PS * p.patch_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + BS * Cfg::kBBytes);
+  uint64_t* p_full = bars;                        // [kMaxStages] TMA -> MMA
+  uint64_t* p_empty = bars + kMaxStages;          // [kMaxStages] MMA -> TMA
+  uint64_t* b_full = bars + 2 * kMaxStages;       // [kMaxStages] (resident: [0] only)
+  uint64_t* b_empty = bars + 3 * kMaxStages;      // [kMaxStages]
+  uint64_t* acc_full = bars + 4 * kMaxStages;     // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,9 +118,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < S; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], 1);
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -114,54 +142,100 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------- TMA producer --
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_pair;
-        int r = tile - n * tiles_per_pair;
+      if constexpr (B_RESIDENT) {
+        // every weight slab of the layer, once, for the life of the CTA
+        const int nb = p.n_taps * p.groups;
+        mbar_expect_tx(&b_full[0], nb * Cfg::kBBytes);
+        for (int i = 0; i < nb; ++i) tma_load_2d(smem_b + i * Cfg::kBBytes, &tmB, &b_full[0], 0, i * BN);
+      }
+      int ps = 0, bs = 0;
+      uint32_t pphase = 0, bphase = 0;
+      // the patch stream runs one patch ahead of the B stream (across tile boundaries)
+      int tile_a = blockIdx.x, pa = 0;          // next patch to load
+      int tile_b = blockIdx.x, pb = 0;          // next patch whose B slabs to load
+      auto issue_patch = [&]() {
+        const int n = tile_a / tiles_per_pair;
+        int r = tile_a - n * tiles_per_pair;
         const int g = r / tiles_per_img;
         r -= g * tiles_per_img;
         const int h0 = (r / p.tiles_w) * kTileH;
         const int w0 = (r % p.tiles_w) * kTileW;
-        const int cg = g * p.cin_group_off;
-        const int brow0 = g * p.n_ksteps * BN;
-        for (int k = 0; k < p.n_ksteps; ++k) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          const KStep s = p.ks[k];
-          tma_load_5d(sa, &tmA, &full[stage], cg + s.c, w0 + s.dw, s.par, h0 + s.dh, n);
-          tma_load_2d(sa + kABytes, &tmB, &full[stage], 0, brow0 + k * BN);
-          if (++stage == S) { stage = 0; phase ^= 1; }
+        const PatchDesc d = p.patches[pa];
+        mbar_wait(&p_empty[ps], pphase ^ 1);
+        mbar_expect_tx(&p_full[ps], p.patch_bytes);
+        tma_load_5d(smem_p + ps * p.patch_stage_bytes, &tmA, &p_full[ps], g * p.cin_group_off + d.c,
+                    w0 + d.dw, d.par, h0 + d.dh, n);
+        if (++ps == PS) { ps = 0; pphase ^= 1; }
+        if (++pa == p.n_patches) { pa = 0; tile_a += gridDim.x; }
+      };
+      if (tile_a < p.num_tiles) issue_patch();
+      while (tile_b < p.num_tiles) {
+        if (tile_a < p.num_tiles) issue_patch();
+        if constexpr (!B_RESIDENT) {
+          const int g = (tile_b % tiles_per_pair) / tiles_per_img;
+          const PatchDesc d = p.patches[pb];
+          for (int t = 0; t < d.ntaps; ++t) {
+            const int bi = g * p.n_taps + p.taps[d.tap0 + t].b_idx;
+            mbar_wait(&b_empty[bs], bphase ^ 1);
+            mbar_expect_tx(&b_full[bs], Cfg::kBBytes);
+            tma_load_2d(smem_b + bs * Cfg::kBBytes, &tmB, &b_full[bs], 0, bi * BN);
+            if (++bs == BS) { bs = 0; bphase ^= 1; }
+          }
         }
+        if (++pb == p.n_patches) { pb = 0; tile_b += gridDim.x; }
       }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer --
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(kTileM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      const uint32_t sbo = (uint32_t)p.patch_w * kSlabBytes;
+      int ps = 0, bs = 0;
+      uint32_t pphase = 0, bphase = 0;
       int it = 0;
+      if constexpr (B_RESIDENT) {
+        mbar_wait(&b_full[0], 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const int g = (tile % tiles_per_pair) / tiles_per_img;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * Cfg::kAccStride;
-        for (int k = 0; k < p.n_ksteps; ++k) {
-          mbar_wait(&full[stage], phase);
+        uint32_t first = 0;
+        for (int pi = 0; pi < p.n_patches; ++pi) {
+          const PatchDesc pd = p.patches[pi];
+          mbar_wait(&p_full[ps], pphase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sa + kABytes);
+          const uint32_t pbase = smem_u32(smem_p + ps * p.patch_stage_bytes);
+          for (int t = 0; t < pd.ntaps; ++t) {
+            const TapDesc td = p.taps[pd.tap0 + t];
+            uint32_t baddr;
+            if constexpr (B_RESIDENT) {
+              baddr = smem_u32(smem_b + (g * p.n_taps + td.b_idx) * Cfg::kBBytes);
+            } else {
+              mbar_wait(&b_full[bs], bphase);
+              tc_fence_after();
+              baddr = smem_u32(smem_b + bs * Cfg::kBBytes);
+            }
+            const uint64_t da = umma_desc_patch(pbase + (uint32_t)td.a_off * kSlabBytes, sbo);
+            const uint64_t db = umma_desc_patch(baddr, 1024);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // 4 x (K = 8 tf32 = 32 B): +2 in the >>4 address field
-            tc_mma_tf32(d, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0);
-          tc_commit(&empty[stage]);         // frees the smem slot when these MMAs retire
-          if (++stage == S) { stage = 0; phase ^= 1; }
+            for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 8 tf32 = 32 B): +2 in the >>4 address field
+              tc_mma_tf32(d, da + 2 * kk, db + 2 * kk, idesc, first);
+              first = 1;
+            }
+            if constexpr (!B_RESIDENT) {
+              tc_commit(&b_empty[bs]);        // frees the weight slot when these MMAs retire
+              if (++bs == BS) { bs = 0; bphase ^= 1; }
+            }
+          }
+          tc_commit(&p_empty[ps]);            // frees the patch slot
+          if (++ps == PS) { ps = 0; pphase ^= 1; }
         }
-        tc_commit(&acc_full[acc]);          // accumulator complete -> epilogue
+        tc_commit(&acc_full[acc]);            // accumulator complete -> epilogue
       }
     }
   } else {

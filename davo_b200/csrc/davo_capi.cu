@@ -6,7 +6,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -72,6 +74,8 @@ struct Layer {
   int cmap[16];
   int use_cmap = 0;
   int Cin_w = 0;               // weight input channels (HWIO 'I')
+  bool b_resident = false;     // all weight slabs stay in shared memory
+  int smem_bytes = 0;
   CUtensorMap tmA, tmB;
   ConvParams prm;
 };
@@ -160,14 +164,14 @@ bool shape_is(const HostTensor* t, std::initializer_list<int64_t> s) {
 }
 
 // ---------------------------------------------------------------- layer plan --
-// Builds the K-step table and packs weights for one conv layer.
+// Builds the patch / tap tables and packs weights for one conv layer.
 // getw(g, ty, tx, ci, n): HWIO weight of group g (ci = weight input channel).
 template <class GetW>
 int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bias_host) {
-  std::vector<KStep> ks;
-  // For every K-step, its 32 reduction entries as (ty, tx, ci) or invalid (-1).
+  // One entry of a tap's 32-wide reduction slab: (ty, tx, ci) or ci = -1 (zero weight).
   struct Ent { int ty, tx, ci; };
-  std::vector<std::vector<Ent>> ents;
+  struct Tap { int par, colkey, slab, dh, dw, c; std::vector<Ent> e; };
+  std::vector<Tap> taps;
   const bool strided = L.stride == 2;
   if (L.stride != 1 && L.stride != 2) return fail(ctx, DAVO_ERR_ARG, "%s: stride %d unsupported", L.name, L.stride);
   if (strided && (L.dil != 1 || (L.Hin & 1) || (L.Win & 1)))
@@ -175,17 +179,19 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
   const bool pair_slab = strided && L.Cin_total == 16;
   if (!pair_slab && (L.Cin_g % 32) != 0)
     return fail(ctx, DAVO_ERR_ARG, "%s: %d input channels per group is not a multiple of 32", L.name, L.Cin_g);
+  // Full 2-D halo patch unless it would not leave room for a 3-deep ring: then one
+  // vertical strip per filter column (cnv5: dilation 8).
+  const int full_hp = kTileH + (L.k - 1) * L.dil, full_wp = kTileW + (L.k - 1) * L.dil;
+  const bool strips = !strided && (size_t)full_hp * full_wp * kSlabBytes > 56 * 1024;
   for (int ty = 0; ty < L.k; ++ty) {
     const int dy = ty * L.dil - L.pad_t;
     const int dh = strided ? floordiv(dy, 2) : dy;
     const int par = strided ? posmod(dy, 2) : 0;
     if (pair_slab) {
-      // one K-step = two horizontally adjacent input pixels x 16 channels
+      // one tap = two horizontally adjacent input pixels x 16 channels
       const int dx_lo = -L.pad_l, dx_hi = L.k - 1 - L.pad_l;
       for (int w2 = floordiv(dx_lo, 2); w2 <= floordiv(dx_hi, 2); ++w2) {
-        KStep s{};
-        s.c = 0; s.dw = (int8_t)w2; s.par = (int8_t)par; s.dh = (int8_t)dh;
-        std::vector<Ent> e(32);
+        Tap t{par, 0, 0, dh, w2, 0, std::vector<Ent>(32)};
         for (int kk = 0; kk < 32; ++kk) {
           const int wp = kk / 16, ch = kk % 16;
           const int tx = 2 * w2 + wp + L.pad_l;
@@ -194,10 +200,9 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
             if (L.use_cmap) { for (int i = 0; i < L.Cin_w; ++i) if (L.cmap[i] == ch) ci = i; }
             else if (ch < L.Cin_w) ci = ch;
           }
-          e[kk] = Ent{ty, tx, ci};
+          t.e[kk] = Ent{ty, tx, ci};
         }
-        ks.push_back(s);
-        ents.push_back(e);
+        taps.push_back(t);
       }
     } else {
       for (int tx = 0; tx < L.k; ++tx) {
@@ -205,29 +210,59 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
         const int dw = strided ? floordiv(dx, 2) : dx;
         const int wp = strided ? posmod(dx, 2) : 0;
         for (int sl = 0; sl < L.Cin_g / 32; ++sl) {
-          KStep s{};
-          s.c = (int16_t)(wp * L.Cin_total + sl * 32);
-          s.dw = (int8_t)dw; s.par = (int8_t)par; s.dh = (int8_t)dh;
-          std::vector<Ent> e(32);
-          for (int kk = 0; kk < 32; ++kk) e[kk] = Ent{ty, tx, sl * 32 + kk};
-          ks.push_back(s);
-          ents.push_back(e);
+          Tap t{par, strided ? wp : (strips ? tx : 0), sl, dh, dw, wp * L.Cin_total + sl * 32, std::vector<Ent>(32)};
+          for (int kk = 0; kk < 32; ++kk) t.e[kk] = Ent{ty, tx, sl * 32 + kk};
+          taps.push_back(t);
         }
       }
     }
   }
-  const int nk = (int)ks.size();
-  if (nk > kMaxKSteps) return fail(ctx, DAVO_ERR_ARG, "%s: %d K-steps exceed the table (%d)", L.name, nk, kMaxKSteps);
-  // pack B: [g][k][n][32], TF32-rounded
-  std::vector<float> pack((size_t)L.groups * nk * L.BN * 32, 0.f);
+  // group taps into patches: key (slab, par, colkey); origin = min offsets over the group
+  struct Patch { int par, colkey, slab, c, dh0, dw0, dh1, dw1; std::vector<int> idx; };
+  std::vector<Patch> patches;
+  for (int i = 0; i < (int)taps.size(); ++i) {
+    const Tap& t = taps[i];
+    Patch* pp = nullptr;
+    for (Patch& q : patches) if (q.par == t.par && q.colkey == t.colkey && q.slab == t.slab) pp = &q;
+    if (!pp) { patches.push_back(Patch{t.par, t.colkey, t.slab, t.c, t.dh, t.dw, t.dh, t.dw, {}}); pp = &patches.back(); }
+    pp->dh0 = std::min(pp->dh0, t.dh); pp->dh1 = std::max(pp->dh1, t.dh);
+    pp->dw0 = std::min(pp->dw0, t.dw); pp->dw1 = std::max(pp->dw1, t.dw);
+    pp->idx.push_back(i);
+  }
+  int Hp = 0, Wp = 0;
+  for (const Patch& q : patches) {
+    Hp = std::max(Hp, kTileH + q.dh1 - q.dh0);
+    Wp = std::max(Wp, kTileW + q.dw1 - q.dw0);
+  }
+  const int nt = (int)taps.size(), np = (int)patches.size();
+  if (nt > kMaxTaps || np > kMaxPatches)
+    return fail(ctx, DAVO_ERR_ARG, "%s: %d taps / %d patches exceed the tables", L.name, nt, np);
+  ConvParams& P = L.prm;
+  memset(&P, 0, sizeof P);
+  // B slabs are packed in patch-major tap order, which is also the issue order.
+  std::vector<int> order;
+  for (int pi = 0; pi < np; ++pi) {
+    const Patch& q = patches[pi];
+    PatchDesc& d = P.patches[pi];
+    d.c = (int16_t)q.c; d.dw = (int8_t)q.dw0; d.par = (int8_t)q.par; d.dh = (int8_t)q.dh0;
+    d.ntaps = (uint8_t)q.idx.size(); d.tap0 = (uint16_t)order.size();
+    for (int i : q.idx) {
+      TapDesc& td = P.taps[order.size()];
+      td.a_off = (uint16_t)((taps[i].dh - q.dh0) * Wp + (taps[i].dw - q.dw0));
+      td.b_idx = (uint16_t)order.size();
+      order.push_back(i);
+    }
+  }
+  // pack B: [g][tap][n][32], TF32-rounded
+  std::vector<float> pack((size_t)L.groups * nt * L.BN * 32, 0.f);
   for (int g = 0; g < L.groups; ++g)
-    for (int k = 0; k < nk; ++k)
+    for (int k = 0; k < nt; ++k)
       for (int n = 0; n < L.BN; ++n)
         for (int kk = 0; kk < 32; ++kk) {
-          const Ent& e = ents[k][kk];
+          const Ent& e = taps[order[k]].e[kk];
           float v = 0.f;
           if (e.ci >= 0) v = getw(g, e.ty, e.tx, e.ci, n);
-          pack[(((size_t)g * nk + k) * L.BN + n) * 32 + kk] = host_round_tf32(v);
+          pack[(((size_t)g * nt + k) * L.BN + n) * 32 + kk] = host_round_tf32(v);
         }
   if (int rc = dev_alloc(ctx, (void**)&L.d_wpack, pack.size() * 4)) return rc;
   CU_OK(cudaMemcpy(L.d_wpack, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice));
@@ -244,15 +279,31 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     if (int rc = dev_alloc(ctx, (void**)&L.d_whwio[g], hw.size() * 4)) return rc;
     CU_OK(cudaMemcpy(L.d_whwio[g], hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
   }
-  // kernel parameters
-  ConvParams& P = L.prm;
-  memset(&P, 0, sizeof P);
+  // kernel parameters and shared-memory plan
   P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.groups = L.groups;
   P.Hout = L.Hout; P.Wout = L.Wout; P.out_stride = L.out_stride;
   P.cin_group_off = L.Cin_g;
-  P.n_ksteps = nk;
+  P.n_patches = np; P.n_taps = nt;
+  P.patch_w = Wp;
+  P.patch_bytes = Hp * Wp * kSlabBytes;
+  P.patch_stage_bytes = (P.patch_bytes + 1023) & ~1023;
   P.bias = L.d_bias;
-  for (int k = 0; k < nk; ++k) P.ks[k] = ks[k];
+  const int bbytes = L.BN * kSlabBytes;
+  const int avail = kSmemBudget - 1024 /*alignment*/ - 512 /*barriers*/;
+  const int resident_bytes = L.groups * nt * bbytes;
+  L.b_resident = resident_bytes + 2 * P.patch_stage_bytes <= avail && resident_bytes <= 100 * 1024;
+  if (L.b_resident) {
+    P.p_stages = std::min(kMaxStages, (avail - resident_bytes) / P.patch_stage_bytes);
+    P.b_stages = 0;
+    L.smem_bytes = 1024 + 512 + resident_bytes + P.p_stages * P.patch_stage_bytes;
+  } else {
+    P.p_stages = 3;
+    while (P.p_stages > 2 && (avail - P.p_stages * P.patch_stage_bytes) / bbytes < 3) --P.p_stages;
+    P.b_stages = std::min(kMaxStages, (avail - P.p_stages * P.patch_stage_bytes) / bbytes);
+    if (P.b_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: shared-memory plan does not fit", L.name);
+    L.smem_bytes = 1024 + 512 + P.b_stages * bbytes + P.p_stages * P.patch_stage_bytes;
+  }
+  if (P.p_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: patch ring does not fit", L.name);
   // tensor maps
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
@@ -266,7 +317,7 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
       dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
       strides[0] = C * 4; strides[1] = W * C * 4; strides[2] = W * C * 4; strides[3] = H * W * C * 4;
     }
-    const cuuint32_t box[5] = {32, (cuuint32_t)kTileW, 1, (cuuint32_t)kTileH, 1};
+    const cuuint32_t box[5] = {32, (cuuint32_t)Wp, 1, (cuuint32_t)Hp, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&L.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, L.d_in, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -274,7 +325,7 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) -> %d", L.name, (int)r);
   }
   {
-    cuuint64_t dims[2] = {32, (cuuint64_t)L.groups * nk * L.BN};
+    cuuint64_t dims[2] = {32, (cuuint64_t)L.groups * nt * L.BN};
     cuuint64_t strides[1] = {128};
     const cuuint32_t box[2] = {32, (cuuint32_t)L.BN};
     const cuuint32_t es[2] = {1, 1};
@@ -283,39 +334,48 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(B) -> %d", L.name, (int)r);
   }
+  if (getenv("DAVO_B200_VERBOSE"))
+    fprintf(stderr, "[davo_b200] %s: patch %dx%d (%d B) x%d patches, %d taps, B %s, rings P%d B%d, smem %d\n",
+            L.name, Hp, Wp, P.patch_bytes, np, nt, L.b_resident ? "resident" : "streamed", P.p_stages,
+            P.b_stages, L.smem_bytes);
   return 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool RES>
 int launch_conv_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
-  using Cfg = ConvCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               Cfg::kSmemBytes));
-    attr_set = true;
+  static int attr_smem = 0;
+  if (attr_smem < L.smem_bytes) {
+    CU_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               L.smem_bytes));
+    attr_smem = L.smem_bytes;
   }
   ConvParams P = L.prm;
   P.num_tiles = npairs * L.groups * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
-  conv_tc_kernel<BN, EPI><<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(L.tmA, L.tmB, P);
+  conv_tc_kernel<BN, EPI, RES><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
   CU_OK(cudaGetLastError());
   return 0;
 }
 
+template <int BN, int EPI>
+int launch_conv_r(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  return L.b_resident ? launch_conv_t<BN, EPI, true>(ctx, L, npairs, st)
+                      : launch_conv_t<BN, EPI, false>(ctx, L, npairs, st);
+}
+
 int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   if (L.epi == EPI_SUM_RELU) {
-    if (L.BN == 256) return launch_conv_t<256, EPI_SUM_RELU>(ctx, L, npairs, st);
+    if (L.BN == 256) return launch_conv_t<256, EPI_SUM_RELU, false>(ctx, L, npairs, st);
     return fail(ctx, DAVO_ERR_ARG, "%s: sum epilogue built for N=256 only", L.name);
   }
   switch (L.BN) {
-    case 16: return launch_conv_t<16, EPI_STORE_RELU>(ctx, L, npairs, st);
-    case 32: return launch_conv_t<32, EPI_STORE_RELU>(ctx, L, npairs, st);
-    case 64: return launch_conv_t<64, EPI_STORE_RELU>(ctx, L, npairs, st);
-    case 128: return launch_conv_t<128, EPI_STORE_RELU>(ctx, L, npairs, st);
-    case 256: return launch_conv_t<256, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 16: return launch_conv_r<16, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 32: return launch_conv_r<32, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 64: return launch_conv_r<64, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 128: return launch_conv_r<128, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 256: return launch_conv_t<256, EPI_STORE_RELU, false>(ctx, L, npairs, st);
   }
   return fail(ctx, DAVO_ERR_ARG, "%s: N=%d has no kernel instance", L.name, L.BN);
 }

@@ -1,0 +1,28 @@
+"""One-off (not in the test suite: ~1-2 min of CPU oracle): ATE of the 4541-frame stream,
+GPU poses vs fp32 oracle poses, random-init weights (BASELINE.json config 3 / north_star)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from davo_b200 import synthetic as S, geo_utils
+from davo_b200.davo import DAVO
+from oracle import davo_oracle as O
+ver = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh"
+n, chunk = 4539, 64
+w = S.init_weights(ver)
+sysm = None
+gpu, ref = [], []
+t0 = time.time()
+for s in range(0, n, chunk):
+    b = min(chunk, n - s)
+    inputs = S.make_inputs(b, 128, 416, seed=1000 + s)
+    if sysm is None:
+        sysm = DAVO(version=ver)
+        sysm.setup_inference(128, 416, "davo", 3, chunk, device=0)
+        sysm.load_weights(w)
+    gpu.append(sysm.inference(None, "pose", inputs=inputs)["pose"])
+    ref.append(O.davo_forward(ver, *inputs, w, torch.float32))
+gpu, ref = np.concatenate(gpu), np.concatenate(ref)
+tg, tr = geo_utils.compose_trajectory(gpu), O.compose_trajectory(ref)
+path = float(np.linalg.norm(np.diff(tr[:, :3, 3], axis=0), axis=1).sum())
+print("samples %d frames %d  max|dpose| %.3e  ATE %.3e m  path %.2f m  end-point error %.3e m  (%.0f s)" % (
+    n, tg.shape[0], np.abs(gpu - ref).max(), O.ate(tg, tr), path, np.linalg.norm(tg[-1, :3, 3] - tr[-1, :3, 3]), time.time() - t0))
