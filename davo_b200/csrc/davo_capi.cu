@@ -75,6 +75,7 @@ struct Layer {
   int use_cmap = 0;
   int Cin_w = 0;               // weight input channels (HWIO 'I')
   bool b_resident = false;     // all weight slabs stay in shared memory
+  bool lo_alias = false;       // cnv1: packed channels 10-15 are TF32 residuals of 0-2, 5-7
   int smem_bytes = 0;
   CUtensorMap tmA, tmB;
   ConvParams prm;
@@ -94,6 +95,7 @@ struct davo_ctx {
   std::vector<Layer> layers;        // cnv1..cnv7
   // device buffers
   std::vector<void*> allocs;
+  unsigned int* d_poolcnt = nullptr;
   float *d_pool = nullptr, *d_attw = nullptr, *d_packed = nullptr, *d_sum7 = nullptr;
   float *d_sew = nullptr, *d_staticw = nullptr, *d_wpred = nullptr, *d_bpred = nullptr;
   float* d_c7tmp = nullptr;         // direct path only
@@ -193,7 +195,12 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
       for (int w2 = floordiv(dx_lo, 2); w2 <= floordiv(dx_hi, 2); ++w2) {
         Tap t{par, 0, 0, dh, w2, 0, std::vector<Ent>(32)};
         for (int kk = 0; kk < 32; ++kk) {
-          const int wp = kk / 16, ch = kk % 16;
+          const int wp = kk / 16;
+          int ch = kk % 16;
+          if (L.lo_alias && ch >= 10) {                 // residual channels reuse the weights
+            const int alias[6] = {0, 1, 2, 5, 6, 7};    // of the channel they refine
+            ch = alias[ch - 10];
+          }
           const int tx = 2 * w2 + wp + L.pad_l;
           int ci = -1;
           if (tx >= 0 && tx < L.k) {
@@ -426,14 +433,13 @@ int launch_front(davo_ctx* ctx, int pair0, int npairs, const uint8_t* img, const
   fp.se_act = c.se_act; fp.flow_abs = c.flow_abs; fp.flow_norm = c.flow_norm;
   fp.img = img; fp.flow = flow; fp.seg = seg;
   fp.se_w = ctx->d_sew; fp.static_w = ctx->d_staticw;
-  fp.pool_part = ctx->d_pool; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
+  fp.pool_part = ctx->d_pool; fp.pool_count = ctx->d_poolcnt; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
   if (c.att_src == 1) {
     se_pool_kernel<<<dim3(kPoolSplits, npairs), 256, 0, st>>>(fp);
     CU_OK(cudaGetLastError());
     ++*launches;
   }
-  const int hw = c.H * c.W;
-  pack_kernel<<<dim3((hw * 4 + 255) / 256, npairs), 256, 0, st>>>(fp);
+  pack_kernel<<<dim3(kPackBlocksPerPair, npairs), 256, 0, st>>>(fp);
   CU_OK(cudaGetLastError());
   ++*launches;
   return 0;
@@ -580,7 +586,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     for (int j = 0; j < 16; ++j) L.cmap[j] = j;
     H = L.Hout; W = L.Wout;
   }
-  // cnv1 reads the 16-channel packed input: [tgt rgb, 0 0, src rgb, src flow, 0 x 6]
+  // cnv1 reads the 16-channel packed input: [tgt rgb, 0 0, src rgb, src flow, residuals x 6]
+  ctx->layers[0].lo_alias = true;
   if (c.in_mode == 0) {
     Layer& L = ctx->layers[0];
     L.use_cmap = 1;
@@ -590,6 +597,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
 
   // ---- workspace ----
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_pool, (size_t)mb * kPoolSplits * 2 * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_poolcnt, (size_t)mb * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * kNumClasses * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_packed, (size_t)mb * c.H * c.W * kPackedC * 4)) return rc;
   float* prev = ctx->d_packed;
@@ -759,7 +767,13 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
   const float* src = nullptr;
   int64_t n = 0;
   std::string s(name);
-  if (s == "att_weights") { n = kNumClasses; src = ctx->d_attw + (size_t)pair * n; }
+  if (s == "att_weights") {
+    n = kNumClasses;
+    if (cap < n) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: buffer too small");
+    if (c.att_src == 1) src = ctx->d_attw + (size_t)pair * n;
+    else if (c.att_src == 2) src = ctx->d_staticw;
+    else { for (int i = 0; i < n; ++i) out[i] = 1.0f; *n_out = n; return 0; }
+  }
   else if (s == "packed") { n = (int64_t)c.H * c.W * kPackedC; src = ctx->d_packed + (size_t)pair * n; }
   else if (s == "cnv7_sum") {
     // reduce the deterministic partials on the host

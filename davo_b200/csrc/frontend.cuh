@@ -15,8 +15,9 @@
 namespace davo {
 
 constexpr int kPoolSplits = 16;
-constexpr int kPackedC = 16;     // packed PoseNN input channels: 10 real + 6 zero
+constexpr int kPackedC = 16;     // packed PoseNN input channels (see pack_kernel)
 constexpr int kNumClasses = 19;
+constexpr int kPackBlocksPerPair = 104;
 
 struct FrontParams {
   int H, W;
@@ -35,6 +36,7 @@ struct FrontParams {
   const float* se_w;     // W1[2][8] b1[8] W2[8][19] b2[19]  (195 floats)
   const float* static_w; // sigmoid(seg_channel_weight)[19]
   float* pool_part;      // [mb][kPoolSplits][2]
+  unsigned int* pool_count;  // [mb], zero between launches
   float* att_w;          // [mb][19]
   float* packed;         // [mb][H][W][16]
 };
@@ -49,8 +51,15 @@ __device__ __forceinline__ float se_in_y(float v, const FrontParams& p) {
   if (p.flow_abs == 1 || p.flow_abs == 3) v = fabsf(v);
   return v;
 }
+__device__ __forceinline__ float se_activation(float v, int act) {
+  if (act == 1) return tanhf(v);
+  if (act == 2) return v > 0.f ? v : 0.2f * v;
+  return fmaxf(v, 0.f);
+}
 
-// grid (kPoolSplits, npairs), 256 threads: deterministic partial sums of the SE input.
+// grid (kPoolSplits, npairs), 256 threads.  Deterministic partial sums of the SE input
+// (attention_module.py:66); the block that finishes a pair last adds the partials in a
+// fixed order and runs the two dense layers (attention_module.py:89-101) -> att_w[pair][19].
 __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   const int pl = blockIdx.y;
   const int pg = p.pair0 + pl;
@@ -73,6 +82,8 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     sy += __shfl_xor_sync(0xffffffffu, sy, o);
   }
   __shared__ float red[8][2];
+  __shared__ float s_fc1[8];
+  __shared__ int s_last;
   if ((threadIdx.x & 31) == 0) {
     red[threadIdx.x >> 5][0] = sx;
     red[threadIdx.x >> 5][1] = sy;
@@ -83,111 +94,130 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     for (int i = 0; i < 8; ++i) { ax += red[i][0]; ay += red[i][1]; }
     p.pool_part[((size_t)pl * kPoolSplits + blockIdx.x) * 2 + 0] = ax;
     p.pool_part[((size_t)pl * kPoolSplits + blockIdx.x) * 2 + 1] = ay;
+    __threadfence();
+    const unsigned int done = atomicAdd(&p.pool_count[pl], 1u);
+    s_last = (done == kPoolSplits - 1);
+    if (s_last) p.pool_count[pl] = 0;              // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 8) {
+    float px = 0.f, py = 0.f;
+    for (int s = 0; s < kPoolSplits; ++s) {
+      px += __ldcg(p.pool_part + ((size_t)pl * kPoolSplits + s) * 2 + 0);
+      py += __ldcg(p.pool_part + ((size_t)pl * kPoolSplits + s) * 2 + 1);
+    }
+    const float inv = 1.0f / (float)hw;
+    px *= inv;
+    py *= inv;
+    const float* W1 = p.se_w;            // [2][8]
+    const float* b1 = p.se_w + 16;       // [8]
+    const int j = threadIdx.x;
+    s_fc1[j] = se_activation(px * W1[j] + py * W1[8 + j] + b1[j], p.se_act);
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumClasses) {
+    const float* W2 = p.se_w + 24;       // [8][19]
+    const float* b2 = p.se_w + 24 + 8 * kNumClasses;
+    const int c = threadIdx.x;
+    float a = b2[c];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
+    p.att_w[(size_t)pl * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
   }
 }
 
-__device__ __forceinline__ float se_activation(float v, int act) {
-  if (act == 1) return tanhf(v);
-  if (act == 2) return v > 0.f ? v : 0.2f * v;
-  return fmaxf(v, 0.f);
+__device__ __forceinline__ float img_norm(uint8_t v) {
+  return (float)v * (1.0f / 255.0f) * 2.0f - 1.0f;     // davo.py:1519-1522
 }
 
-// grid (blocks_per_pair, npairs), 256 threads; 4 threads per pixel, each writes
-// one float4 of the 16-channel packed pixel:
-//   [tgt r g b | 0 0 | src r g b | src flow x y | 0 x 6]      (davo.py:1439-1442, posenn.py:198)
+// grid (kPackBlocksPerPair, npairs), 256 threads, one thread per pixel.  Writes the
+// 16-channel packed pixel (davo.py:1439-1442, posenn.py:198):
+//   ch 0-2  tgt r g b        ch 3-4  tgt flow (zeros)     ch 5-7  src r g b (x A)
+//   ch 8-9  src flow (x A)   ch 10-12 / 13-15: the TF32 rounding residuals of ch 0-2 / 5-7.
+// Every value is stored TF32-rounded (the tensor core drops the low 13 bits).  The image
+// channels take only 256 x |classes| distinct values, so their rounding error would be the
+// same for every pixel and sample; the residual channels (which cnv1 multiplies by the same
+// weights) give them ~21 mantissa bits at no cost: the slab is 16 channels wide anyway.
+// The four float4 of a pixel are transposed across each lane quad with shuffles so that
+// every store instruction writes whole 64-B runs.
+__device__ __forceinline__ float4 shfl_xor4(const float4 v, int m) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                     __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+
 __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
-  __shared__ float s_fc1[8];
   __shared__ float s_w[kNumClasses];
   const int pl = blockIdx.y;
   const int pg = p.pair0 + pl;
   const int b = pg >> 1, k = pg & 1;
-  const size_t hw = (size_t)p.H * p.W;
-
-  if (p.att_src == 1) {
-    // SE excitation (attention_module.py:89-101) from the pooled partials.
-    if (threadIdx.x < 8) {
-      float px = 0.f, py = 0.f;
-      for (int s = 0; s < kPoolSplits; ++s) {
-        px += p.pool_part[((size_t)pl * kPoolSplits + s) * 2 + 0];
-        py += p.pool_part[((size_t)pl * kPoolSplits + s) * 2 + 1];
-      }
-      const float inv = 1.0f / (float)hw;
-      px *= inv;
-      py *= inv;
-      const float* W1 = p.se_w;            // [2][8]
-      const float* b1 = p.se_w + 16;       // [8]
-      const int j = threadIdx.x;
-      s_fc1[j] = se_activation(px * W1[j] + py * W1[8 + j] + b1[j], p.se_act);
-    }
-    __syncthreads();
-    if (threadIdx.x < kNumClasses) {
-      const float* W2 = p.se_w + 24;       // [8][19]
-      const float* b2 = p.se_w + 24 + 8 * kNumClasses;
-      const int c = threadIdx.x;
-      float a = b2[c];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
-      const float wgt = 1.0f / (1.0f + expf(-a));
-      s_w[c] = wgt;
-      if (blockIdx.x == 0) p.att_w[(size_t)pl * kNumClasses + c] = wgt;
-    }
-  } else if (p.att_src == 2) {
-    if (threadIdx.x < kNumClasses) {
-      s_w[threadIdx.x] = p.static_w[threadIdx.x];
-      if (blockIdx.x == 0) p.att_w[(size_t)pl * kNumClasses + threadIdx.x] = s_w[threadIdx.x];
-    }
-  } else {
-    if (threadIdx.x < kNumClasses) {
-      s_w[threadIdx.x] = 1.0f;
-      if (blockIdx.x == 0) p.att_w[(size_t)pl * kNumClasses + threadIdx.x] = 1.0f;
-    }
-  }
+  const int hw = p.H * p.W;
+  if (threadIdx.x < kNumClasses)
+    s_w[threadIdx.x] = p.att_src == 1 ? p.att_w[(size_t)pl * kNumClasses + threadIdx.x]
+                     : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
   __syncthreads();
-
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  const int pix = t >> 2, qtr = t & 3;
-  if (pix >= (int)hw) return;
-  const int h = pix / p.W, w = pix - h * p.W;
-  const int W3 = 3 * p.W;
-
-  // class weight of this pixel in the source frame (davo.py:1115, 1178)
-  float a_src = 1.0f;
-  if (p.att_src != 0) {
-    const float lab_f = __ldg(p.seg + (((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw + pix));
-    const int lab = (int)lab_f;                       // tf.cast truncates toward zero
-    a_src = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;
-  }
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (qtr == 0) {
-    const uint8_t* px = p.img + ((size_t)(b * p.H + h) * W3 + (p.W + w)) * 3;   // tgt = centre frame
-    float a_tgt = 1.0f;
-    if (!p.att_tgt_ones && p.att_src != 0) {
-      const int lab = (int)__ldg(p.seg + (((size_t)b * 3 + 1) * hw + pix));
-      a_tgt = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;
+  const int lane = threadIdx.x & 31, j = lane & 3;
+  const float inv_w = 1.0f / (float)p.W;
+  const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
+  const float* seg_src = p.seg + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw;
+  const float* seg_tgt = p.seg + ((size_t)b * 3 + 1) * hw;
+  const float2* flow_src = reinterpret_cast<const float2*>(p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2);
+  float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * kPackedC);
+  const int src_col0 = (k == 0) ? 0 : 2 * p.W;
+  for (int base = blockIdx.x * 256; base < hw; base += kPackBlocksPerPair * 256) {
+    const int pix_raw = base + threadIdx.x;
+    const int pix = min(pix_raw, hw - 1);                       // keep every lane in the shuffles
+    const int h = (int)(((float)pix + 0.5f) * inv_w);           // exact for these sizes
+    const int row_off = pix + 2 * p.W * h;                      // h * 3W + w
+    float a_src = 1.0f, a_tgt = 1.0f;
+    if (p.att_src != 0) {
+      const int lab = (int)__ldg(seg_src + pix);                // tf.cast truncates toward zero
+      a_src = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;  // one_hot: out of range -> 0
+      if (!p.att_tgt_ones) {
+        const int lt = (int)__ldg(seg_tgt + pix);
+        a_tgt = (lt >= 0 && lt < kNumClasses) ? s_w[lt] : 0.0f;
+      }
     }
-    const float m = p.mask_rgb ? a_tgt : 1.0f;
-    o.x = ((float)px[0] * (1.0f / 255.0f) * 2.0f - 1.0f) * m;
-    o.y = ((float)px[1] * (1.0f / 255.0f) * 2.0f - 1.0f) * m;
-    o.z = ((float)px[2] * (1.0f / 255.0f) * 2.0f - 1.0f) * m;
-  } else if (qtr == 1) {
-    const uint8_t* px = p.img + ((size_t)(b * p.H + h) * W3 + ((k == 0 ? 0 : 2 * p.W) + w)) * 3;
-    const float m = p.mask_rgb ? a_src : 1.0f;
-    o.y = ((float)px[0] * (1.0f / 255.0f) * 2.0f - 1.0f) * m;
-    o.z = ((float)px[1] * (1.0f / 255.0f) * 2.0f - 1.0f) * m;
-    o.w = ((float)px[2] * (1.0f / 255.0f) * 2.0f - 1.0f) * m;
-  } else if (qtr == 2) {
+    const float mt = p.mask_rgb ? a_tgt : 1.0f, ms = p.mask_rgb ? a_src : 1.0f;
+    const uint8_t* pt = img_b + (size_t)(row_off + p.W) * 3;    // tgt = centre frame
+    const uint8_t* ps = img_b + (size_t)(row_off + src_col0) * 3;
+    const float tr = img_norm(pt[0]) * mt, tg = img_norm(pt[1]) * mt, tb = img_norm(pt[2]) * mt;
+    const float sr = img_norm(ps[0]) * ms, sg = img_norm(ps[1]) * ms, sb = img_norm(ps[2]) * ms;
+    float fx = 0.f, fy = 0.f;
     if (p.in_mode == 1) {
-      const float2 f = __ldg(reinterpret_cast<const float2*>(p.flow + ((size_t)b * 4 + k) * hw * 2) + pix);
+      const float2 f = __ldg(flow_src + pix);
       const float m = p.mask_flow ? a_src : 1.0f;
-      o.x = f.x * m;
-      o.y = f.y * m;
+      fx = f.x * m;
+      fy = f.y * m;
+    }
+    const float trh = round_tf32(tr), tgh = round_tf32(tg), tbh = round_tf32(tb);
+    const float srh = round_tf32(sr), sgh = round_tf32(sg), sbh = round_tf32(sb);
+    float4 q0 = make_float4(trh, tgh, tbh, 0.f);
+    float4 q1 = make_float4(0.f, srh, sgh, sbh);
+    float4 q2 = make_float4(round_tf32(fx), round_tf32(fy), round_tf32(tr - trh), round_tf32(tg - tgh));
+    float4 q3 = make_float4(round_tf32(tb - tbh), round_tf32(sr - srh), round_tf32(sg - sgh),
+                            round_tf32(sb - sbh));
+    // 4x4 transpose across the lane quad: afterwards lane j holds quarter j of pixels 4i..4i+3
+    {
+      const bool up = (j & 2) != 0;                              // exchange with lane ^ 2
+      const float4 s0 = shfl_xor4(up ? q0 : q2, 2), s1 = shfl_xor4(up ? q1 : q3, 2);
+      if (up) { q0 = s0; q1 = s1; } else { q2 = s0; q3 = s1; }
+      // now lanes 0,1 hold rows (q0,q1) of pixels {own, own^2}; lanes 2,3 hold rows (q2,q3)
+      float4 a0 = up ? q2 : q0, a1 = up ? q3 : q1;               // own pixel, rows (2j'..)
+      float4 b0 = up ? q0 : q2, b1 = up ? q1 : q3;               // pixel ^2
+      const bool odd = (j & 1) != 0;                             // exchange with lane ^ 1
+      const float4 t0 = shfl_xor4(odd ? a0 : a1, 1), t1 = shfl_xor4(odd ? b0 : b1, 1);
+      if (odd) { a0 = t0; b0 = t1; } else { a1 = t0; b1 = t1; }
+      // lane j now holds quarter j of: (a0: pixel j&~1 | .., a1: .. | 1, b0, b1: the ^2 pair)
+      const int quad = pix_raw & ~3;
+      const int pA = quad + (up ? 2 : 0), pB = quad + (up ? 0 : 2);
+      if (pA + 0 < hw) out[(size_t)(pA + 0) * 4 + j] = a0;
+      if (pA + 1 < hw) out[(size_t)(pA + 1) * 4 + j] = a1;
+      if (pB + 0 < hw) out[(size_t)(pB + 0) * 4 + j] = b0;
+      if (pB + 1 < hw) out[(size_t)(pB + 1) * 4 + j] = b1;
     }
   }
-  o.x = round_tf32(o.x);
-  o.y = round_tf32(o.y);
-  o.z = round_tf32(o.z);
-  o.w = round_tf32(o.w);
-  reinterpret_cast<float4*>(p.packed + ((size_t)pl * hw + pix) * kPackedC)[qtr] = o;
 }
 
 struct HeadParams {

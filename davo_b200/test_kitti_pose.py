@@ -1,0 +1,144 @@
+"""Pose inference CLI with the reference's flags and output file.
+
+Mirrors reference ``test_kitti_pose.py``: same flags (``:20-29``), same loop --
+batches of ``batch_size`` samples through ``DAVO.inference(sess, mode='pose')``
+(``:133-135``), zero target pose inserted / ``pose_vec2mat`` / first sample's
+tgt->src0 then every sample's inv(tgt->src1) (``:136-145``), chained in fp64
+(``:147-149``) and written as ``<output_dir>/<seq>-pred_kitti_pose.txt`` with 12
+floats per line (``:116, 150-153``).
+
+Input sources: ``--synthetic N`` generates an N-frame seeded stream (no dataset is
+available offline); otherwise ``--concat_img_dir`` must hold the reference's dump
+(``<seq>/<id>.jpg`` decoded by PIL if present, ``<id>-flownet2.npy``,
+``<id>-seglabel.npy``; reference ``:45-49``).  ``--ckpt_file`` is an ``.npz`` of
+``{tf variable name: array}``; with ``--synthetic`` and no checkpoint, TF-default
+random init (seed 8964) is used.
+
+Multi-GPU: launch with ``python -m torch.distributed.run --nproc-per-node N``; samples
+are sharded contiguously by rank, poses all-gathered over NCCL, rank 0 composes and writes.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from glob import glob
+
+import numpy as np
+
+from . import geo_utils, parallel, synthetic
+from .davo import DAVO
+
+
+def build_parser():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--batch_size", type=int, default=1, help="The size of of a sample batch")
+    ap.add_argument("--img_height", type=int, default=128, help="Image height")
+    ap.add_argument("--img_width", type=int, default=416, help="Image width")
+    ap.add_argument("--seq_length", type=int, default=3, help="Sequence length for each example")
+    ap.add_argument("--test_seq", type=int, default=9, help="Sequence id to test")
+    ap.add_argument("--concat_img_dir", type=str, default=None, help="Preprocess image dataset directory")
+    ap.add_argument("--output_dir", type=str, default=None, help="Output directory")
+    ap.add_argument("--ckpt_file", type=str, default=None, help="checkpoint file (.npz of TF variables)")
+    ap.add_argument("--version", type=str, default="v1", help="version")
+    ap.add_argument("--synthetic", type=int, default=0, help="use a seeded synthetic stream of this many frames")
+    ap.add_argument("--seed", type=int, default=1234)
+    return ap
+
+
+class SyntheticStream:
+    """Samples of a synthetic N-frame sequence, generated in seeded blocks of 64."""
+
+    def __init__(self, n_frames, h, w, seed):
+        self.n = n_frames - 2
+        self.h, self.w, self.seed = h, w, seed
+        self._blk, self._data = None, None
+
+    def sample(self, i):
+        blk = i // 64
+        if blk != self._blk:
+            self._data = synthetic.make_inputs(64, self.h, self.w, seed=self.seed + blk)
+            self._blk = blk
+        return tuple(a[i % 64] for a in self._data)
+
+
+class DumpStream:
+    """The reference's on-disk dump (reference test_kitti_pose.py:33-72, doc/preprocessing.md)."""
+
+    def __init__(self, root, seq, h, w, seq_length):
+        d = os.path.join(root, '%.2d' % seq)
+        half = int((seq_length - 1) / 2)
+        n_frames = len(glob(d + '/*.jpg')) + 2 * half
+        frames = ['%.2d %.6d' % (seq, n) for n in range(n_frames)]
+        self.ids = [frames[i].split(' ')[1] for i in range(n_frames)
+                    if parallel.is_valid_sample(frames, i, seq_length)]
+        self.dir, self.n, self.h, self.w = d, len(self.ids), h, w
+
+    def sample(self, i):
+        from PIL import Image
+        fid = self.ids[i]
+        img = np.asarray(Image.open(os.path.join(self.dir, fid + '.jpg')).convert('RGB'), np.uint8)
+        flow = np.load(os.path.join(self.dir, fid + '-flownet2.npy')).astype(np.float32)
+        seg = np.load(os.path.join(self.dir, fid + '-seglabel.npy')).astype(np.float32)
+        return img, flow, seg.reshape(3, self.h, self.w, 1)
+
+
+def main(argv=None):
+    FLAGS = build_parser().parse_args(argv)
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("test_kitti_pose: no CUDA device; the davo_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if FLAGS.output_dir and rank == 0 and not os.path.isdir(FLAGS.output_dir):
+        os.makedirs(FLAGS.output_dir)
+    H, W, B = FLAGS.img_height, FLAGS.img_width, FLAGS.batch_size
+    if FLAGS.synthetic:
+        stream = SyntheticStream(FLAGS.synthetic, H, W, FLAGS.seed)
+    else:
+        if not FLAGS.concat_img_dir:
+            raise SystemExit("test_kitti_pose: give --concat_img_dir or --synthetic N")
+        stream = DumpStream(FLAGS.concat_img_dir, FLAGS.test_seq, H, W, FLAGS.seq_length)
+    n = stream.n
+    # shard, then fill the last batch by repeating the last item (reference common_utils.py:8-13)
+    idx = parallel.padded_indices(n, rank, world)
+    n_local = len(idx)
+    idx = parallel.complete_batch_size(list(idx), B)
+
+    system = DAVO(version=FLAGS.version)
+    system.setup_inference(H, W, "davo", FLAGS.seq_length, B, device=local)
+    if FLAGS.ckpt_file:
+        system.load_weights(FLAGS.ckpt_file)
+    elif FLAGS.synthetic:
+        system.load_weights(synthetic.init_weights(FLAGS.version))
+    else:
+        raise SystemExit("test_kitti_pose: --ckpt_file is required with a real dataset")
+
+    poses = torch.empty((len(idx), 2, 6), dtype=torch.float32, device="cuda:%d" % local)
+    for i in range(len(idx) // B):                                     # reference :133
+        batch = [stream.sample(j) for j in idx[i * B:(i + 1) * B]]
+        img, flow, seg = (np.stack([s[k] for s in batch]) for k in range(3))
+        pred = system.inference(None, mode='pose', inputs=(img, flow, seg))     # reference :135
+        poses[i * B:(i + 1) * B] = torch.as_tensor(pred['pose'])
+    all_poses = parallel.gather_poses(poses[:n_local].contiguous(), n).cpu().numpy()
+    if rank == 0:
+        traj = geo_utils.compose_trajectory(all_poses)                 # reference :136-149
+        if FLAGS.output_dir:
+            out = os.path.join(FLAGS.output_dir, '%.2d-pred_kitti_pose.txt' % FLAGS.test_seq)
+            if os.path.isfile(out):
+                os.remove(out)
+            geo_utils.write_kitti_trajectory(out, traj)
+            print("Done. Please check %s" % out)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return all_poses if rank == 0 else None
+
+
+if __name__ == '__main__':
+    main()

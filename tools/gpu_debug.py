@@ -43,7 +43,8 @@ for impl in (1, 0):
         if taps["attention_weights"] is not None:
             print("  pair", p, "att_w", rel(aw, taps["attention_weights"][1 + k][b]), end=" ")
         pk = sysm.get_intermediate("packed", p).reshape(H, W, 16)
-        print("packed", rel(pk[..., :10], tp["input"][b]), "pad", float(np.abs(pk[..., 10:]).max()), end=" ")
+        rc = pk[..., :10].astype(np.float64); rc[..., [0, 1, 2, 5, 6, 7]] += pk[..., 10:16]
+        print("packed %.2e hi+lo %.2e" % (rel(pk[..., :10], tp["input"][b]), rel(rc, tp["input"][b])), end=" ")
         for i, name in enumerate(["cnv1", "cnv2", "cnv3", "cnv4", "cnv5"]):
             g = sysm.get_intermediate(name, p)
             print(name, "%.2e" % rel(g, tp[name][b]), end=" ")
