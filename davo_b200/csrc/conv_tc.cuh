@@ -24,10 +24,12 @@
 //   through a ring (one 2-D TMA box per tap) or, for the thin layers, loaded once
 //   and kept resident in shared memory for the CTA's whole life.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer,
-// warps 2-5 epilogue (TMEM -> registers -> bias/ReLU -> global, or the spatial-sum
-// epilogue of cnv7).  Accumulators are double-buffered in TMEM so the epilogue of
-// tile i overlaps the main loop of tile i+1.  Persistent CTAs walk tiles round-robin.
+// Warp roles (224 threads): warp 0 patch (A) TMA producer, warp 6 weight (B) TMA
+// producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue: TMEM -> registers ->
+// bias/ReLU/round -> a per-warp swizzled smem transpose -> global stores of whole 128-B
+// lines (or the spatial-sum epilogue of cnv7).  Accumulators are double-buffered in TMEM
+// so the epilogue of tile i overlaps the main loop of tile i+1.  Persistent CTAs walk
+// tiles round-robin.
 #pragma once
 #include "ptx.cuh"
 
@@ -39,9 +41,12 @@ constexpr int kTileM = 128;
 constexpr int kTileH = 16;
 constexpr int kTileW = 8;
 constexpr int kSlabBytes = 128;                     // 32 tf32
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 224;                  // 7 warps, see the role list above
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 226 * 1024;             // of the 227 KB a CTA may own
+constexpr int kEpiStageBytes = 4 * 4096;            // 4 epilogue warps x (32 pixels x 128 B)
+constexpr int kBiasSmemBytes = 2048;                // up to 512 bias floats
+constexpr int kBarrierBytes = 512;
 
 struct PatchDesc {
   int16_t c;        // inner (channel-axis) start coordinate, before the group offset
@@ -90,6 +95,17 @@ __device__ __forceinline__ uint64_t umma_desc_patch(uint32_t smem_addr, uint32_t
          (1ull << 46) | (2ull << 61);
 }
 
+// Optional stall accounting (-DDAVO_TIMING, tools/timing_build.py): cycles each role spent
+// waiting, per CTA: [0] producer on p_empty, [1] producer on b_empty, [2] MMA on p_full,
+// [3] MMA on b_full, [4] MMA on acc_empty, [5] epilogue warp 2 on acc_full, [6] epilogue
+// warp 2 busy, [7] CTA total.
+#ifdef DAVO_TIMING
+__device__ long long g_conv_timing[148 * 8];
+#define TWAIT(slot, stmt) do { long long t_ = clock64(); stmt; tacc[slot] += clock64() - t_; } while (0)
+#else
+#define TWAIT(slot, stmt) stmt
+#endif
+
 template <int BN, int EPI, bool B_RESIDENT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -111,9 +127,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = bars + 4 * kMaxStages;     // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarrierBytes);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bias_s) + kBiasSmemBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef DAVO_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_cta0 = clock64();
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -131,6 +153,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  for (int i = threadIdx.x; i < p.groups * BN; i += kConvThreads) bias_s[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -140,49 +163,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_per_pair = tiles_per_img * p.groups;
 
   if (warp == 0) {
-    // ------------------------------------------------------- TMA producer --
+    // ------------------------------------------------- patch (A) producer --
+    if (lane == 0) {
+      int ps = 0;
+      uint32_t pphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_pair;
+        int r = tile - n * tiles_per_pair;
+        const int g = r / tiles_per_img;
+        r -= g * tiles_per_img;
+        const int h0 = (r / p.tiles_w) * kTileH;
+        const int w0 = (r % p.tiles_w) * kTileW;
+        for (int pi = 0; pi < p.n_patches; ++pi) {
+          const PatchDesc d = p.patches[pi];
+          TWAIT(0, mbar_wait(&p_empty[ps], pphase ^ 1));
+          mbar_expect_tx(&p_full[ps], p.patch_bytes);
+          tma_load_5d(smem_p + ps * p.patch_stage_bytes, &tmA, &p_full[ps], g * p.cin_group_off + d.c,
+                      w0 + d.dw, d.par, h0 + d.dh, n);
+          if (++ps == PS) { ps = 0; pphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------ weight (B) producer --
     if (lane == 0) {
       if constexpr (B_RESIDENT) {
         // every weight slab of the layer, once, for the life of the CTA
         const int nb = p.n_taps * p.groups;
         mbar_expect_tx(&b_full[0], nb * Cfg::kBBytes);
         for (int i = 0; i < nb; ++i) tma_load_2d(smem_b + i * Cfg::kBBytes, &tmB, &b_full[0], 0, i * BN);
-      }
-      int ps = 0, bs = 0;
-      uint32_t pphase = 0, bphase = 0;
-      // the patch stream runs one patch ahead of the B stream (across tile boundaries)
-      int tile_a = blockIdx.x, pa = 0;          // next patch to load
-      int tile_b = blockIdx.x, pb = 0;          // next patch whose B slabs to load
-      auto issue_patch = [&]() {
-        const int n = tile_a / tiles_per_pair;
-        int r = tile_a - n * tiles_per_pair;
-        const int g = r / tiles_per_img;
-        r -= g * tiles_per_img;
-        const int h0 = (r / p.tiles_w) * kTileH;
-        const int w0 = (r % p.tiles_w) * kTileW;
-        const PatchDesc d = p.patches[pa];
-        mbar_wait(&p_empty[ps], pphase ^ 1);
-        mbar_expect_tx(&p_full[ps], p.patch_bytes);
-        tma_load_5d(smem_p + ps * p.patch_stage_bytes, &tmA, &p_full[ps], g * p.cin_group_off + d.c,
-                    w0 + d.dw, d.par, h0 + d.dh, n);
-        if (++ps == PS) { ps = 0; pphase ^= 1; }
-        if (++pa == p.n_patches) { pa = 0; tile_a += gridDim.x; }
-      };
-      if (tile_a < p.num_tiles) issue_patch();
-      while (tile_b < p.num_tiles) {
-        if (tile_a < p.num_tiles) issue_patch();
-        if constexpr (!B_RESIDENT) {
-          const int g = (tile_b % tiles_per_pair) / tiles_per_img;
-          const PatchDesc d = p.patches[pb];
-          for (int t = 0; t < d.ntaps; ++t) {
-            const int bi = g * p.n_taps + p.taps[d.tap0 + t].b_idx;
-            mbar_wait(&b_empty[bs], bphase ^ 1);
+      } else {
+        int bs = 0;
+        uint32_t bphase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          const int g = (tile % tiles_per_pair) / tiles_per_img;
+          for (int t = 0; t < p.n_taps; ++t) {          // taps[] is already in issue order
+            const int bi = g * p.n_taps + p.taps[t].b_idx;
+            TWAIT(1, mbar_wait(&b_empty[bs], bphase ^ 1));
             mbar_expect_tx(&b_full[bs], Cfg::kBBytes);
             tma_load_2d(smem_b + bs * Cfg::kBBytes, &tmB, &b_full[bs], 0, bi * BN);
             if (++bs == BS) { bs = 0; bphase ^= 1; }
           }
         }
-        if (++pb == p.n_patches) { pb = 0; tile_b += gridDim.x; }
       }
     }
   } else if (warp == 1) {
@@ -201,13 +223,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const int g = (tile % tiles_per_pair) / tiles_per_img;
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        TWAIT(4, mbar_wait(&acc_empty[acc], acc_phase ^ 1));
         tc_fence_after();
         const uint32_t d = tmem_base + acc * Cfg::kAccStride;
         uint32_t first = 0;
         for (int pi = 0; pi < p.n_patches; ++pi) {
           const PatchDesc pd = p.patches[pi];
-          mbar_wait(&p_full[ps], pphase);
+          TWAIT(2, mbar_wait(&p_full[ps], pphase));
           tc_fence_after();
           const uint32_t pbase = smem_u32(smem_p + ps * p.patch_stage_bytes);
           for (int t = 0; t < pd.ntaps; ++t) {
@@ -216,7 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if constexpr (B_RESIDENT) {
               baddr = smem_u32(smem_b + (g * p.n_taps + td.b_idx) * Cfg::kBBytes);
             } else {
-              mbar_wait(&b_full[bs], bphase);
+              TWAIT(3, mbar_wait(&b_full[bs], bphase));
               tc_fence_after();
               baddr = smem_u32(smem_b + bs * Cfg::kBBytes);
             }
@@ -253,44 +275,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int h = (r / p.tiles_w) * kTileH + (m >> 3);
       const int w = (r % p.tiles_w) * kTileW + (m & 7);
       const bool valid = (h < p.Hout) && (w < p.Wout);
-      const float* bias = p.bias + g * BN;
-      mbar_wait(&acc_full[acc], acc_phase);
+      const float* bias = bias_s + g * BN;
+      TWAIT(5, mbar_wait(&acc_full[acc], acc_phase));
       tc_fence_after();
+#ifdef DAVO_TIMING
+      const long long t_busy0 = clock64();
+#endif
       const uint32_t t0 = tmem_base + acc * Cfg::kAccStride + (uint32_t(q * 32) << 16);
       if constexpr (EPI == EPI_STORE_RELU) {
-        float* dst = p.out + ((size_t)(n * p.Hout + h) * p.Wout + w) * p.out_stride + g * BN;
-        if constexpr (BN >= 32) {
+        // 32 pixels x CH channels per step: registers -> swizzled smem (row = pixel) -> each
+        // global store instruction writes PPS pixels x (CH*4)-byte runs (whole lines at CH=32).
+        constexpr int CH = BN >= 32 ? 32 : 16;
+        constexpr int LPP = CH / 4;                 // lanes (float4) per pixel
+        constexpr int PPS = 32 / LPP;               // pixels per store instruction
+        constexpr int RB = CH * 4;                  // row bytes in the staging buffer
+        uint8_t* stg = epi_stage + q * 4096;
+        const int sub = lane / LPP, cq = lane % LPP;
+        const int th0 = (r / p.tiles_w) * kTileH + q * 4, tw0 = (r % p.tiles_w) * kTileW;
+        float* const obase = p.out + (size_t)n * p.Hout * p.Wout * p.out_stride + g * BN + cq * 4;
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(t0 + c0, v);
-            tmem_ld_wait();
-            if (valid) {
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t v[CH];
+          TWAIT(3, { if constexpr (CH == 32) tmem_ld_32x32(t0 + c0, v); else tmem_ld_32x16(t0 + c0, v);
+                     tmem_ld_wait(); });
+          __syncwarp();                             // the previous step's reads are done
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                o.x = round_tf32(fmaxf(__uint_as_float(v[j + 0]) + __ldg(bias + c0 + j + 0), 0.f));
-                o.y = round_tf32(fmaxf(__uint_as_float(v[j + 1]) + __ldg(bias + c0 + j + 1), 0.f));
-                o.z = round_tf32(fmaxf(__uint_as_float(v[j + 2]) + __ldg(bias + c0 + j + 2), 0.f));
-                o.w = round_tf32(fmaxf(__uint_as_float(v[j + 3]) + __ldg(bias + c0 + j + 3), 0.f));
-                *reinterpret_cast<float4*>(dst + c0 + j) = o;
-              }
-            }
+          for (int j = 0; j < LPP; ++j) {
+            float4 o;
+            o.x = round_tf32(fmaxf(__uint_as_float(v[4 * j + 0]) + bias[c0 + 4 * j + 0], 0.f));
+            o.y = round_tf32(fmaxf(__uint_as_float(v[4 * j + 1]) + bias[c0 + 4 * j + 1], 0.f));
+            o.z = round_tf32(fmaxf(__uint_as_float(v[4 * j + 2]) + bias[c0 + 4 * j + 2], 0.f));
+            o.w = round_tf32(fmaxf(__uint_as_float(v[4 * j + 3]) + bias[c0 + 4 * j + 3], 0.f));
+            *reinterpret_cast<float4*>(stg + lane * RB + ((j ^ (lane & (LPP - 1))) << 4)) = o;
           }
-        } else {
-          uint32_t v[16];
-          tmem_ld_32x16(t0, v);
-          tmem_ld_wait();
-          if (valid) {
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 o;
-              o.x = round_tf32(fmaxf(__uint_as_float(v[j + 0]) + __ldg(bias + j + 0), 0.f));
-              o.y = round_tf32(fmaxf(__uint_as_float(v[j + 1]) + __ldg(bias + j + 1), 0.f));
-              o.z = round_tf32(fmaxf(__uint_as_float(v[j + 2]) + __ldg(bias + j + 2), 0.f));
-              o.w = round_tf32(fmaxf(__uint_as_float(v[j + 3]) + __ldg(bias + j + 3), 0.f));
-              *reinterpret_cast<float4*>(dst + j) = o;
-            }
+          for (int s2 = 0; s2 < 32 / PPS; ++s2) {
+            const int rr = s2 * PPS + sub;          // pixel row within this warp's 32
+            const float4 o = *reinterpret_cast<const float4*>(stg + rr * RB + ((cq ^ (rr & (LPP - 1))) << 4));
+            const int hh = th0 + (rr >> 3), ww = tw0 + (rr & 7);
+            if (hh < p.Hout && ww < p.Wout)
+              *reinterpret_cast<float4*>(obase + ((size_t)hh * p.Wout + ww) * p.out_stride + c0) = o;
           }
         }
       } else {
@@ -308,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            f[j] = valid ? fmaxf(__uint_as_float(v[j]) + __ldg(bias + c0 + j), 0.f) : 0.f;
+            f[j] = valid ? fmaxf(__uint_as_float(v[j]) + bias[c0 + j], 0.f) : 0.f;
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) {
             const bool hi = (lane & off) != 0;
@@ -325,8 +350,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
+#ifdef DAVO_TIMING
+      tacc[6] += clock64() - t_busy0;
+#endif
     }
   }
+#ifdef DAVO_TIMING
+  if (lane == 0 && (warp <= 2 || warp == 6) && blockIdx.x < 148) {
+    long long* o = g_conv_timing + blockIdx.x * 8;
+    if (warp == 6) o[1] = tacc[1];
+    if (warp == 2) { o[7] = clock64() - t_cta0; o[0] = tacc[3]; }   // [0] reused: epilogue LDTM+wait
+    if (warp == 1) { o[2] = tacc[2]; o[3] = tacc[3]; o[4] = tacc[4]; }
+    if (warp == 2) { o[5] = tacc[5]; o[6] = tacc[6]; }
+  }
+#endif
 
   tc_fence_before();
   __syncthreads();

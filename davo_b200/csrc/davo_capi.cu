@@ -296,19 +296,21 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
   P.patch_stage_bytes = (P.patch_bytes + 1023) & ~1023;
   P.bias = L.d_bias;
   const int bbytes = L.BN * kSlabBytes;
-  const int avail = kSmemBudget - 1024 /*alignment*/ - 512 /*barriers*/;
+  const int fixed = 1024 /*alignment*/ + kBarrierBytes + kBiasSmemBytes + kEpiStageBytes;
+  const int avail = kSmemBudget - fixed;
   const int resident_bytes = L.groups * nt * bbytes;
   L.b_resident = resident_bytes + 2 * P.patch_stage_bytes <= avail && resident_bytes <= 100 * 1024;
   if (L.b_resident) {
     P.p_stages = std::min(kMaxStages, (avail - resident_bytes) / P.patch_stage_bytes);
     P.b_stages = 0;
-    L.smem_bytes = 1024 + 512 + resident_bytes + P.p_stages * P.patch_stage_bytes;
+    L.smem_bytes = fixed + resident_bytes + P.p_stages * P.patch_stage_bytes;
   } else {
+    // prefer a 3-deep patch ring if the weight ring can still be >= 4 deep
     P.p_stages = 3;
-    while (P.p_stages > 2 && (avail - P.p_stages * P.patch_stage_bytes) / bbytes < 3) --P.p_stages;
+    if ((avail - 3 * P.patch_stage_bytes) / bbytes < 4) P.p_stages = 2;
     P.b_stages = std::min(kMaxStages, (avail - P.p_stages * P.patch_stage_bytes) / bbytes);
     if (P.b_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: shared-memory plan does not fit", L.name);
-    L.smem_bytes = 1024 + 512 + P.b_stages * bbytes + P.p_stages * P.patch_stage_bytes;
+    L.smem_bytes = fixed + P.b_stages * bbytes + P.p_stages * P.patch_stage_bytes;
   }
   if (P.p_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: patch ring does not fit", L.name);
   // tensor maps
@@ -803,6 +805,20 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
   *n_out = n;
   return 0;
 }
+
+#ifdef DAVO_TIMING
+// Debug build only: run layer `layer` once and return the per-CTA stall counters (8 x 148).
+extern "C" int davo_debug_layer_timing(davo_ctx* ctx, int layer, long long* out, void* stream) {
+  if (!ctx || layer < 0 || layer > 6 || !out) return DAVO_ERR_ARG;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int npairs = ctx->last_B * 2 < ctx->mb ? ctx->last_B * 2 : ctx->mb;
+  if (int rc = launch_conv(ctx, ctx->layers[layer], npairs, st)) return rc;
+  if (int rc = launch_conv(ctx, ctx->layers[layer], npairs, st)) return rc;
+  CU_OK(cudaStreamSynchronize(st));
+  CU_OK(cudaMemcpyFromSymbol(out, davo::g_conv_timing, sizeof(long long) * 148 * 8));
+  return 0;
+}
+#endif
 
 extern "C" int davo_debug_set_conv_impl(davo_ctx* ctx, int impl) {
   if (!ctx || impl < 0 || impl > 1) return DAVO_ERR_ARG;

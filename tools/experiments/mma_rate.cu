@@ -5,7 +5,7 @@
 #include "../../davo_b200/csrc/ptx.cuh"
 using namespace davo;
 
-template <int N>
+template <int N, int M>
 __global__ void __launch_bounds__(128, 1) k(long long* out, int iters, int sbo_bytes, int distinct) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int iters, int sbo_b
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tm = *slot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_tf32(128, N);
+    const uint32_t idesc = umma_idesc_tf32(M, N);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 96 * 1024);
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -40,23 +40,24 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int iters, int sbo_b
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tm, 256); }
 }
 
-template <int N> void run(long long* d, int sbo) {
+template <int N, int M> void run(long long* d, int sbo) {
   const int smem = 162 * 1024 + 1024;
-  cudaFuncSetAttribute(k<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute((k<N, M>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   long long h[2];
-  for (int iters : {64, 1024}) {
-    k<N><<<1, 128, smem>>>(d, iters, sbo, 28);
+  for (int iters : {1024}) {
+    k<N, M><<<1, 128, smem>>>(d, iters, sbo, 28);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("N=%d: %s\n", N, cudaGetErrorString(e)); return; }
     cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-    printf("N=%3d sbo=%4d iters=%4d (x4 MMAs): issue %.1f cyc/MMA, complete %.1f cyc/MMA\n", N, sbo, iters,
+    printf("M=%3d N=%3d sbo=%4d iters=%4d (x4 MMAs): issue %.1f cyc/MMA, complete %.1f cyc/MMA\n", M, N, sbo, iters,
            h[0] / (4.0 * iters), h[1] / (4.0 * iters));
   }
 }
 int main() {
   long long* d; cudaMalloc(&d, 16);
-  for (int sbo : {1024, 1408}) {
-    run<16>(d, sbo); run<32>(d, sbo); run<64>(d, sbo); run<128>(d, sbo); run<256>(d, sbo);
+  for (int sbo : {1024}) {
+    run<16, 128>(d, sbo); run<64, 128>(d, sbo); run<128, 128>(d, sbo); run<192, 128>(d, sbo); run<256, 128>(d, sbo);
+    run<16, 64>(d, sbo); run<64, 64>(d, sbo); run<128, 64>(d, sbo); run<256, 64>(d, sbo);
   }
   return 0;
 }
