@@ -14,7 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdavo_b200.so")
 SOURCES = ["davo_capi.cu"]
-DEPS = ["davo_capi.cu", "conv_tc.cuh", "frontend.cuh", "ptx.cuh", "../../include/davo_b200.h"]
+
+
+def _deps():
+    import glob
+    return (glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+            [os.path.join(HERE, "..", "include", "davo_b200.h")])
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -35,7 +40,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -1,0 +1,292 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, TF32 in / fp32
+// accumulate in TMEM), operands fed by TMA.  One kernel serves every conv of the
+// PoseNN stack (reference nets/posenn.py:211-215, 238-240).
+//
+// Orientation: the GEMM is computed TRANSPOSED, D^T[cout, pixel] = W[cout, k] . X[pixel, k]^T:
+//   * M (TMEM lanes)   = 128 output channels (one "m-block"; layers with fewer are zero-padded,
+//                        layers with 256 have two m-blocks, each its own tile)
+//   * N (TMEM columns) = NPIX output pixels = a (NPIX/8 rows) x 8 (cols) block of one frame pair
+//   * K                = filter taps x 32-channel slabs, 4 MMAs of K=8 per tap
+// Measured on B200 (tools/experiments/mma_rate.cu): one tcgen05.mma M<=128,K=8 costs
+// max(85.4, N/2) cycles whatever M is, so only N=256 runs the tensor pipe at full rate.
+// Putting PIXELS on N makes every layer an N=256 problem, whatever its channel count; and a
+// thread of the epilogue then owns one output CHANNEL, so each store instruction of a warp
+// writes 32 consecutive channels of one pixel (a whole 128-B line of the NHWC tensor) straight
+// from registers -- no shared-memory transpose competing with the tensor core for smem
+// bandwidth (the measured bottleneck of the pixels-on-M version).
+//
+// Pixel operand: never gathered per tap.  A PATCH -- the tile's input halo, {32 ch, Wp cols,
+// 1, Hp rows, 1} of the NHWC activation -- is loaded ONCE by a 5-D TMA box placed with signed
+// coordinates, so TF-'SAME' padding (asymmetric included) is TMA's out-of-bounds zero fill.
+// It lands as Hp*Wp rows of 128 B with SWIZZLE_128B.  Every tap of the patch is then just a
+// different UMMA descriptor: start = patch + (row*Wp + col)*128 B, 8-row groups SBO = Wp*128 B
+// apart.  (The hardware swizzle is a function of the absolute shared-memory address, so a
+// row-shifted window needs no re-layout -- measured, tools/experiments/desc_shift.cu.)
+// Dilation is only a tap offset: no im2col buffer, no space-to-batch, each input byte crosses
+// L2->SM once per tile.  Stride-2 layers view the input as [N][H/2][2][W/2][2*C]: a tap is a
+// unit-stride window at one (row parity, column parity) of that view; one patch per parity.
+//
+// Weight operand: pre-packed [group][m-block][tap][128][32], TF32-rounded, streamed through a
+// ring, one 16-KB 2-D TMA box per tap.
+//
+// Warp roles (224 threads): warp 0 patch producer, warp 6 weight producer, warp 1 TMEM owner +
+// single-thread MMA issuer, warps 2-5 epilogue (TMEM -> registers -> bias/ReLU/round ->
+// coalesced global stores, or the per-channel spatial sum of cnv7).  Accumulators are
+// double-buffered in TMEM (2 x NPIX <= 512 columns) so the epilogue of tile i overlaps the main
+// loop of tile i+1.  Persistent CTAs walk tiles round-robin.
+#pragma once
+#include "conv_common.cuh"
+
+namespace davo {
+namespace cm {
+
+constexpr int kBlockM = 128;                        // output channels per tile
+constexpr int kWBytes = kBlockM * kSlabBytes;       // one weight stage: 16 KB
+
+struct ConvParams {
+  int num_tiles;        // pairs * groups * tiles_h * tiles_w * m_blocks
+  int tiles_w, tiles_h, groups, m_blocks;
+  int Hout, Wout;
+  int out_stride;       // floats per output pixel (all groups)
+  int cout_g;           // real output channels per group
+  int cin_group_off;    // inner-coordinate offset of group g = g * cin_group_off
+  int n_patches, n_taps;          // per tile
+  int patch_w;                    // Wp
+  int patch_bytes;                // Hp * Wp * 128 (what TMA delivers)
+  int patch_stage_bytes;          // rounded up to 1024
+  int p_stages, w_stages;         // ring depths
+  float* out;           // EPI_STORE: [pairs][Hout][Wout][out_stride]
+  const float* bias;    // [groups * cout_g]
+  float* sum_out;       // EPI_SUM:   [pairs][groups][tiles_h*tiles_w][cout_g]
+  PatchDesc patches[kMaxPatches];
+  TapDesc taps[kMaxTaps];
+};
+
+struct TileCoord { int n, g, mb, h0, w0, t; };
+
+template <int NPIX>
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord c;
+  c.mb = tile % p.m_blocks;
+  int r = tile / p.m_blocks;
+  const int tpi = p.tiles_h * p.tiles_w;
+  c.t = r % tpi;
+  r /= tpi;
+  c.g = r % p.groups;
+  c.n = r / p.groups;
+  c.h0 = (c.t / p.tiles_w) * (NPIX / kTileW);
+  c.w0 = (c.t % p.tiles_w) * kTileW;
+  return c;
+}
+
+template <int NPIX, int EPI>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands: keep every stage base 1024-B aligned.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int PS = p.p_stages, WS = p.w_stages;
+  uint8_t* smem_p = smem;
+  uint8_t* smem_w = smem + PS * p.patch_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + WS * kWBytes);
+  uint64_t* p_full = bars;                        // [kMaxStages] TMA -> MMA
+  uint64_t* p_empty = bars + kMaxStages;          // [kMaxStages] MMA -> TMA
+  uint64_t* w_full = bars + 2 * kMaxStages;
+  uint64_t* w_empty = bars + 3 * kMaxStages;
+  uint64_t* acc_full = bars + 4 * kMaxStages;     // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  constexpr int kTmemCols = 2 * NPIX;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+#ifdef DAVO_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_cta0 = clock64();
+#endif
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(&p_full[i], 1);
+      mbar_init(&p_empty[i], 1);
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------- patch producer --
+    if (lane == 0) {
+      int ps = 0;
+      uint32_t pphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile<NPIX>(p, tile);
+        for (int pi = 0; pi < p.n_patches; ++pi) {
+          const PatchDesc d = p.patches[pi];
+          TWAIT(0, mbar_wait(&p_empty[ps], pphase ^ 1));
+          mbar_expect_tx(&p_full[ps], p.patch_bytes);
+          tma_load_5d(smem_p + ps * p.patch_stage_bytes, &tmX, &p_full[ps],
+                      tc.g * p.cin_group_off + d.c, tc.w0 + d.dw, d.par, tc.h0 + d.dh, tc.n);
+          if (++ps == PS) { ps = 0; pphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // --------------------------------------------------- weight producer --
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile<NPIX>(p, tile);
+        const int row0 = (tc.g * p.m_blocks + tc.mb) * p.n_taps;
+        for (int t = 0; t < p.n_taps; ++t) {            // taps[] is in issue order
+          TWAIT(1, mbar_wait(&w_empty[ws], wphase ^ 1));
+          mbar_expect_tx(&w_full[ws], kWBytes);
+          tma_load_2d(smem_w + ws * kWBytes, &tmW, &w_full[ws], 0, (row0 + p.taps[t].b_idx) * kBlockM);
+          if (++ws == WS) { ws = 0; wphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------- MMA issuer --
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kBlockM, NPIX);
+      const uint32_t sbo = (uint32_t)p.patch_w * kSlabBytes;
+      int ps = 0, ws = 0;
+      uint32_t pphase = 0, wphase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        TWAIT(4, mbar_wait(&acc_empty[acc], acc_phase ^ 1));
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * NPIX;
+        uint32_t accumulate = 0;
+        for (int pi = 0; pi < p.n_patches; ++pi) {
+          const PatchDesc pd = p.patches[pi];
+          TWAIT(2, mbar_wait(&p_full[ps], pphase));
+          tc_fence_after();
+          const uint32_t pbase = smem_u32(smem_p + ps * p.patch_stage_bytes);
+          for (int t = 0; t < pd.ntaps; ++t) {
+            const TapDesc td = p.taps[pd.tap0 + t];
+            TWAIT(3, mbar_wait(&w_full[ws], wphase));
+            tc_fence_after();
+            const uint64_t dw = umma_desc(smem_u32(smem_w + ws * kWBytes), 1024);
+            const uint64_t dx = umma_desc(pbase + (uint32_t)td.a_off * kSlabBytes, sbo);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 8 tf32 = 32 B): +2 in the >>4 address field
+              tc_mma_tf32(d, dw + 2 * kk, dx + 2 * kk, idesc, accumulate);
+              accumulate = 1;
+            }
+            tc_commit(&w_empty[ws]);          // frees the weight slot when these MMAs retire
+            if (++ws == WS) { ws = 0; wphase ^= 1; }
+          }
+          tc_commit(&p_empty[ps]);            // frees the patch slot
+          if (++ps == PS) { ps = 0; pphase ^= 1; }
+        }
+        tc_commit(&acc_full[acc]);            // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ----------------------------------------------------------- epilogue --
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const TileCoord tc = decode_tile<NPIX>(p, tile);
+      const int co = tc.mb * kBlockM + q * 32 + lane;          // this thread's output channel
+      const bool co_ok = co < p.cout_g;
+      const float bias = co_ok ? __ldg(p.bias + tc.g * p.cout_g + co) : 0.f;
+      TWAIT(5, mbar_wait(&acc_full[acc], acc_phase));
+      tc_fence_after();
+#ifdef DAVO_TIMING
+      const long long t_busy0 = clock64();
+#endif
+      const uint32_t t0 = tmem_base + acc * NPIX + (uint32_t(q * 32) << 16);
+      const bool warp_has_work = tc.mb * kBlockM + q * 32 < p.cout_g;   // warp-uniform
+      if constexpr (EPI == EPI_STORE_RELU) {
+        // lane = channel: one store instruction writes 32 consecutive channels of one pixel
+        const size_t pix_stride = p.out_stride;
+        float* const obase = p.out + ((size_t)tc.n * p.Hout * p.Wout) * pix_stride + tc.g * p.cout_g + co;
+        if (warp_has_work) {
+#pragma unroll 1
+          for (int n0 = 0; n0 < NPIX; n0 += 32) {             // 4 tile rows x 8 cols per step
+            uint32_t v[32];
+            tmem_ld_32x32(t0 + n0, v);
+            tmem_ld_wait();
+            const int hb = tc.h0 + (n0 >> 3);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int hh = hb + (j >> 3), ww = tc.w0 + (j & 7);
+              if (co_ok && hh < p.Hout && ww < p.Wout)
+                obase[((size_t)hh * p.Wout + ww) * pix_stride] =
+                    round_tf32(fmaxf(__uint_as_float(v[j]) + bias, 0.f));
+            }
+          }
+        }
+      } else {
+        // Spatial-sum epilogue (cnv7 -> pred -> mean, reference nets/posenn.py:239-241: pred
+        // is linear, so only sum_pixels relu(cnv7) is needed).  A thread owns a channel, so
+        // the sum over the tile's pixels is thread-local; one deterministic partial per tile,
+        // added in fixed order by the head kernel.  No atomics.
+        float s = 0.f;
+        if (warp_has_work) {
+#pragma unroll 1
+          for (int n0 = 0; n0 < NPIX; n0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t0 + n0, v);
+            tmem_ld_wait();
+            const int hb = tc.h0 + (n0 >> 3);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int hh = hb + (j >> 3), ww = tc.w0 + (j & 7);
+              if (hh < p.Hout && ww < p.Wout) s += fmaxf(__uint_as_float(v[j]) + bias, 0.f);
+            }
+          }
+        }
+        if (co_ok)
+          p.sum_out[((size_t)(tc.n * p.groups + tc.g) * (p.tiles_h * p.tiles_w) + tc.t) * p.cout_g + co] = s;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+#ifdef DAVO_TIMING
+      tacc[6] += clock64() - t_busy0;
+#endif
+    }
+  }
+#ifdef DAVO_TIMING
+  if (lane == 0 && (warp <= 2 || warp == 6) && blockIdx.x < 148) {
+    long long* o = g_conv_timing + blockIdx.x * 8;
+    if (warp == 0) o[0] = tacc[0];
+    if (warp == 6) o[1] = tacc[1];
+    if (warp == 1) { o[2] = tacc[2]; o[3] = tacc[3]; o[4] = tacc[4]; }
+    if (warp == 2) { o[5] = tacc[5]; o[6] = tacc[6]; o[7] = clock64() - t_cta0; }
+  }
+#endif
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace cm
+}  // namespace davo

@@ -1,0 +1,55 @@
+// Shared definitions of the two implicit-GEMM convolution kernels (conv_pm.cuh: pixels on
+// the MMA M axis; conv_cm.cuh: output channels on the M axis).
+#pragma once
+#include "ptx.cuh"
+
+namespace davo {
+
+constexpr int kMaxPatches = 16;
+constexpr int kMaxTaps = 144;
+constexpr int kTileW = 8;                           // tile columns: one 8-row UMMA group
+constexpr int kSlabBytes = 128;                     // 32 tf32
+constexpr int kConvThreads = 224;                   // 7 warps
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 226 * 1024;             // of the 227 KB a CTA may own
+constexpr int kBarrierBytes = 512;
+
+// A PATCH is the input halo of one tile for one 32-channel slab: one 5-D TMA box
+// {32 ch, Wp, 1, Hp, 1} placed with signed coordinates (out-of-bounds = TF 'SAME' zeros).
+struct PatchDesc {
+  int16_t c;        // inner (channel-axis) start coordinate, before the group offset
+  int8_t dw;        // patch origin relative to the tile's first output column
+  int8_t par;       // coordinate on the row-parity axis (0 for stride-1 layers)
+  int8_t dh;        // patch origin relative to the tile's first output row
+  uint8_t ntaps;
+  uint16_t tap0;    // first entry in taps[]
+};
+// A TAP is one 32-float slab of the reduction: a window of the patch x one weight slab.
+struct TapDesc {
+  uint16_t a_off;   // window origin inside the patch, in 128-B rows: row * Wp + col
+  uint16_t b_idx;   // weight slab index
+};
+
+enum { EPI_STORE_RELU = 0, EPI_SUM_RELU = 1 };
+
+// Shared-memory matrix descriptor (K-major, SWIZZLE_128B): rows 128 B apart, 8-row groups
+// `sbo_bytes` apart.  A window of a patch is start = patch + (row*Wp + col)*128, SBO = Wp*128:
+// the hardware swizzle is a function of the absolute shared-memory address, so a row-shifted
+// window reads back exactly what TMA wrote (measured: tools/experiments/desc_shift.cu).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+// Optional stall accounting (-DDAVO_TIMING, tools/timing_run.py): cycles per CTA:
+// [0] patch producer waiting, [1] weight producer waiting, [2] MMA on patch, [3] MMA on
+// weights, [4] MMA on acc_empty, [5] epilogue warp 2 on acc_full, [6] epilogue warp 2 busy,
+// [7] epilogue warp 2 lifetime.
+#ifdef DAVO_TIMING
+__device__ long long g_conv_timing[148 * 8];
+#define TWAIT(slot, stmt) do { long long t_ = clock64(); stmt; tacc[slot] += clock64() - t_; } while (0)
+#else
+#define TWAIT(slot, stmt) stmt
+#endif
+
+}  // namespace davo

@@ -31,37 +31,15 @@
 // so the epilogue of tile i overlaps the main loop of tile i+1.  Persistent CTAs walk
 // tiles round-robin.
 #pragma once
-#include "ptx.cuh"
+#include "conv_common.cuh"
 
 namespace davo {
+namespace pm {
 
-constexpr int kMaxPatches = 16;
-constexpr int kMaxTaps = 144;
 constexpr int kTileM = 128;
 constexpr int kTileH = 16;
-constexpr int kTileW = 8;
-constexpr int kSlabBytes = 128;                     // 32 tf32
-constexpr int kConvThreads = 224;                  // 7 warps, see the role list above
-constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 226 * 1024;             // of the 227 KB a CTA may own
 constexpr int kEpiStageBytes = 4 * 4096;            // 4 epilogue warps x (32 pixels x 128 B)
 constexpr int kBiasSmemBytes = 2048;                // up to 512 bias floats
-constexpr int kBarrierBytes = 512;
-
-struct PatchDesc {
-  int16_t c;        // inner (channel-axis) start coordinate, before the group offset
-  int8_t dw;        // patch origin relative to the tile's first output column
-  int8_t par;       // coordinate on the row-parity axis (0 for stride-1 layers)
-  int8_t dh;        // patch origin relative to the tile's first output row
-  uint8_t ntaps;
-  uint16_t tap0;    // first entry in taps[]
-};
-struct TapDesc {
-  uint16_t a_off;   // window origin inside the patch, in 128-B rows: row * Wp + col
-  uint16_t b_idx;   // weight slab index: B rows [b_idx * BN, +BN)
-};
-
-enum { EPI_STORE_RELU = 0, EPI_SUM_RELU = 1 };
 
 struct ConvParams {
   int num_tiles;        // pairs * groups * tiles_h * tiles_w
@@ -87,24 +65,6 @@ struct ConvCfg {
   static constexpr int kAccStride = BN < 32 ? 32 : BN;             // TMEM columns per accumulator
   static constexpr int kTmemCols = 2 * kAccStride;                 // power of two for BN in {16..256}
 };
-
-// Shared-memory matrix descriptor for a window of a patch (K-major, SWIZZLE_128B):
-// rows 128 B apart, 8-row groups `sbo_bytes` apart.
-__device__ __forceinline__ uint64_t umma_desc_patch(uint32_t smem_addr, uint32_t sbo_bytes) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         (1ull << 46) | (2ull << 61);
-}
-
-// Optional stall accounting (-DDAVO_TIMING, tools/timing_build.py): cycles each role spent
-// waiting, per CTA: [0] producer on p_empty, [1] producer on b_empty, [2] MMA on p_full,
-// [3] MMA on b_full, [4] MMA on acc_empty, [5] epilogue warp 2 on acc_full, [6] epilogue
-// warp 2 busy, [7] CTA total.
-#ifdef DAVO_TIMING
-__device__ long long g_conv_timing[148 * 8];
-#define TWAIT(slot, stmt) do { long long t_ = clock64(); stmt; tacc[slot] += clock64() - t_; } while (0)
-#else
-#define TWAIT(slot, stmt) stmt
-#endif
 
 template <int BN, int EPI, bool B_RESIDENT>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -242,8 +202,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tc_fence_after();
               baddr = smem_u32(smem_b + bs * Cfg::kBBytes);
             }
-            const uint64_t da = umma_desc_patch(pbase + (uint32_t)td.a_off * kSlabBytes, sbo);
-            const uint64_t db = umma_desc_patch(baddr, 1024);
+            const uint64_t da = umma_desc(pbase + (uint32_t)td.a_off * kSlabBytes, sbo);
+            const uint64_t db = umma_desc(baddr, 1024);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 8 tf32 = 32 B): +2 in the >>4 address field
               tc_mma_tf32(d, da + 2 * kk, db + 2 * kk, idesc, first);
@@ -373,4 +333,5 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+}  // namespace pm
 }  // namespace davo

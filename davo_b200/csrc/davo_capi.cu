@@ -16,7 +16,8 @@
 #include <string>
 #include <vector>
 
-#include "conv_tc.cuh"
+#include "conv_cm.cuh"
+#include "conv_pm.cuh"
 #include "frontend.cuh"
 
 using namespace davo;
@@ -74,11 +75,15 @@ struct Layer {
   int cmap[16];
   int use_cmap = 0;
   int Cin_w = 0;               // weight input channels (HWIO 'I')
-  bool b_resident = false;     // all weight slabs stay in shared memory
+  int orient = 0;              // 0: pixels on the MMA M axis (conv_pm), 1: channels on M (conv_cm)
+  int npix = 128;              // output pixels per tile: 128 = 16x8 (pm, or cm on short maps), 256 = 32x8
+  int m_blocks = 1;            // cm: 128-channel blocks per group
+  bool b_resident = false;     // pm: all weight slabs stay in shared memory
   bool lo_alias = false;       // cnv1: packed channels 10-15 are TF32 residuals of 0-2, 5-7
   int smem_bytes = 0;
-  CUtensorMap tmA, tmB;
-  ConvParams prm;
+  CUtensorMap tmA, tmB;          // activation (patch) map, weight map
+  pm::ConvParams prm_pm;
+  cm::ConvParams prm_cm;
 };
 
 }  // namespace
@@ -183,8 +188,9 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     return fail(ctx, DAVO_ERR_ARG, "%s: %d input channels per group is not a multiple of 32", L.name, L.Cin_g);
   // Full 2-D halo patch unless it would not leave room for a 3-deep ring: then one
   // vertical strip per filter column (cnv5: dilation 8).
-  const int full_hp = kTileH + (L.k - 1) * L.dil, full_wp = kTileW + (L.k - 1) * L.dil;
-  const bool strips = !strided && (size_t)full_hp * full_wp * kSlabBytes > 56 * 1024;
+  const int TR = L.npix / kTileW;                 // tile rows
+  const int full_hp = TR + (L.k - 1) * L.dil, full_wp = kTileW + (L.k - 1) * L.dil;
+  const bool strips = !strided && (size_t)full_hp * full_wp * kSlabBytes > 64 * 1024;
   for (int ty = 0; ty < L.k; ++ty) {
     const int dy = ty * L.dil - L.pad_t;
     const int dh = strided ? floordiv(dy, 2) : dy;
@@ -238,38 +244,52 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
   }
   int Hp = 0, Wp = 0;
   for (const Patch& q : patches) {
-    Hp = std::max(Hp, kTileH + q.dh1 - q.dh0);
+    Hp = std::max(Hp, TR + q.dh1 - q.dh0);
     Wp = std::max(Wp, kTileW + q.dw1 - q.dw0);
   }
   const int nt = (int)taps.size(), np = (int)patches.size();
   if (nt > kMaxTaps || np > kMaxPatches)
     return fail(ctx, DAVO_ERR_ARG, "%s: %d taps / %d patches exceed the tables", L.name, nt, np);
-  ConvParams& P = L.prm;
-  memset(&P, 0, sizeof P);
-  // B slabs are packed in patch-major tap order, which is also the issue order.
+  // Patch / tap tables (same for both orientations).  Weight slabs are packed in patch-major
+  // tap order, which is also the issue order.
+  PatchDesc pdesc[kMaxPatches];
+  TapDesc tdesc[kMaxTaps];
+  memset(pdesc, 0, sizeof pdesc);
+  memset(tdesc, 0, sizeof tdesc);
   std::vector<int> order;
   for (int pi = 0; pi < np; ++pi) {
     const Patch& q = patches[pi];
-    PatchDesc& d = P.patches[pi];
+    PatchDesc& d = pdesc[pi];
     d.c = (int16_t)q.c; d.dw = (int8_t)q.dw0; d.par = (int8_t)q.par; d.dh = (int8_t)q.dh0;
     d.ntaps = (uint8_t)q.idx.size(); d.tap0 = (uint16_t)order.size();
     for (int i : q.idx) {
-      TapDesc& td = P.taps[order.size()];
+      TapDesc& td = tdesc[order.size()];
       td.a_off = (uint16_t)((taps[i].dh - q.dh0) * Wp + (taps[i].dw - q.dw0));
       td.b_idx = (uint16_t)order.size();
       order.push_back(i);
     }
   }
-  // pack B: [g][tap][n][32], TF32-rounded
-  std::vector<float> pack((size_t)L.groups * nt * L.BN * 32, 0.f);
+  const int patch_bytes = Hp * Wp * kSlabBytes;
+  const int patch_stage = (patch_bytes + 1023) & ~1023;
+  // ---- weights: TF32-rounded, K-major 32-float slabs ----
+  //   pm: [g][tap][Cout][32]                      (Cout = MMA N)
+  //   cm: [g][m-block][tap][128][32], zero rows beyond the real channels (128 = MMA M)
+  const int MB = L.m_blocks;
+  const int rows_per_slab = L.orient == 0 ? L.BN : cm::kBlockM;
+  const size_t n_slabs = (size_t)L.groups * (L.orient == 0 ? 1 : MB) * nt;
+  std::vector<float> pack(n_slabs * rows_per_slab * 32, 0.f);
   for (int g = 0; g < L.groups; ++g)
-    for (int k = 0; k < nt; ++k)
-      for (int n = 0; n < L.BN; ++n)
-        for (int kk = 0; kk < 32; ++kk) {
-          const Ent& e = taps[order[k]].e[kk];
-          float v = 0.f;
-          if (e.ci >= 0) v = getw(g, e.ty, e.tx, e.ci, n);
-          pack[(((size_t)g * nt + k) * L.BN + n) * 32 + kk] = host_round_tf32(v);
+    for (int mb = 0; mb < (L.orient == 0 ? 1 : MB); ++mb)
+      for (int k = 0; k < nt; ++k)
+        for (int m = 0; m < rows_per_slab; ++m) {
+          const int n = mb * cm::kBlockM + m;
+          if (n >= L.BN) continue;
+          const size_t slab = L.orient == 0 ? (size_t)g * nt + k : ((size_t)g * MB + mb) * nt + k;
+          for (int kk = 0; kk < 32; ++kk) {
+            const Ent& e = taps[order[k]].e[kk];
+            if (e.ci >= 0)
+              pack[(slab * rows_per_slab + m) * 32 + kk] = host_round_tf32(getw(g, e.ty, e.tx, e.ci, n));
+          }
         }
   if (int rc = dev_alloc(ctx, (void**)&L.d_wpack, pack.size() * 4)) return rc;
   CU_OK(cudaMemcpy(L.d_wpack, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice));
@@ -286,34 +306,58 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     if (int rc = dev_alloc(ctx, (void**)&L.d_whwio[g], hw.size() * 4)) return rc;
     CU_OK(cudaMemcpy(L.d_whwio[g], hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
   }
-  // kernel parameters and shared-memory plan
-  P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.groups = L.groups;
-  P.Hout = L.Hout; P.Wout = L.Wout; P.out_stride = L.out_stride;
-  P.cin_group_off = L.Cin_g;
-  P.n_patches = np; P.n_taps = nt;
-  P.patch_w = Wp;
-  P.patch_bytes = Hp * Wp * kSlabBytes;
-  P.patch_stage_bytes = (P.patch_bytes + 1023) & ~1023;
-  P.bias = L.d_bias;
-  const int bbytes = L.BN * kSlabBytes;
-  const int fixed = 1024 /*alignment*/ + kBarrierBytes + kBiasSmemBytes + kEpiStageBytes;
-  const int avail = kSmemBudget - fixed;
-  const int resident_bytes = L.groups * nt * bbytes;
-  L.b_resident = resident_bytes + 2 * P.patch_stage_bytes <= avail && resident_bytes <= 100 * 1024;
-  if (L.b_resident) {
-    P.p_stages = std::min(kMaxStages, (avail - resident_bytes) / P.patch_stage_bytes);
-    P.b_stages = 0;
-    L.smem_bytes = fixed + resident_bytes + P.p_stages * P.patch_stage_bytes;
+  // ---- kernel parameters and shared-memory plan ----
+  int p_stages = 0, w_stages = 0;
+  if (L.orient == 0) {
+    pm::ConvParams& P = L.prm_pm;
+    memset(&P, 0, sizeof P);
+    P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.groups = L.groups;
+    P.Hout = L.Hout; P.Wout = L.Wout; P.out_stride = L.out_stride;
+    P.cin_group_off = L.Cin_g;
+    P.n_patches = np; P.n_taps = nt; P.patch_w = Wp;
+    P.patch_bytes = patch_bytes; P.patch_stage_bytes = patch_stage;
+    P.bias = L.d_bias;
+    memcpy(P.patches, pdesc, sizeof pdesc);
+    memcpy(P.taps, tdesc, sizeof tdesc);
+    const int bbytes = L.BN * kSlabBytes;
+    const int fixed = 1024 /*alignment*/ + kBarrierBytes + pm::kBiasSmemBytes + pm::kEpiStageBytes;
+    const int avail = kSmemBudget - fixed;
+    const int resident_bytes = L.groups * nt * bbytes;
+    L.b_resident = resident_bytes + 2 * patch_stage <= avail && resident_bytes <= 100 * 1024;
+    if (L.b_resident) {
+      P.p_stages = std::min(kMaxStages, (avail - resident_bytes) / patch_stage);
+      P.b_stages = 0;
+      L.smem_bytes = fixed + resident_bytes + P.p_stages * patch_stage;
+    } else {
+      P.p_stages = 3;
+      if ((avail - 3 * patch_stage) / bbytes < 4) P.p_stages = 2;
+      P.b_stages = std::min(kMaxStages, (avail - P.p_stages * patch_stage) / bbytes);
+      if (P.b_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: shared-memory plan does not fit", L.name);
+      L.smem_bytes = fixed + P.b_stages * bbytes + P.p_stages * patch_stage;
+    }
+    p_stages = P.p_stages; w_stages = P.b_stages;
   } else {
-    // prefer a 3-deep patch ring if the weight ring can still be >= 4 deep
-    P.p_stages = 3;
-    if ((avail - 3 * P.patch_stage_bytes) / bbytes < 4) P.p_stages = 2;
-    P.b_stages = std::min(kMaxStages, (avail - P.p_stages * P.patch_stage_bytes) / bbytes);
-    if (P.b_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: shared-memory plan does not fit", L.name);
-    L.smem_bytes = fixed + P.b_stages * bbytes + P.p_stages * P.patch_stage_bytes;
+    cm::ConvParams& P = L.prm_cm;
+    memset(&P, 0, sizeof P);
+    P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.groups = L.groups; P.m_blocks = MB;
+    P.Hout = L.Hout; P.Wout = L.Wout; P.out_stride = L.out_stride; P.cout_g = L.BN;
+    P.cin_group_off = L.Cin_g;
+    P.n_patches = np; P.n_taps = nt; P.patch_w = Wp;
+    P.patch_bytes = patch_bytes; P.patch_stage_bytes = patch_stage;
+    P.bias = L.d_bias;
+    memcpy(P.patches, pdesc, sizeof pdesc);
+    memcpy(P.taps, tdesc, sizeof tdesc);
+    const int fixed = 1024 /*alignment*/ + kBarrierBytes;
+    const int avail = kSmemBudget - fixed;
+    P.p_stages = patch_stage <= 40 * 1024 ? 3 : 2;
+    if (P.p_stages == 3 && (avail - 3 * patch_stage) / cm::kWBytes < 4) P.p_stages = 2;
+    P.w_stages = std::min(kMaxStages, (avail - P.p_stages * patch_stage) / cm::kWBytes);
+    if (P.w_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: shared-memory plan does not fit", L.name);
+    L.smem_bytes = fixed + P.w_stages * cm::kWBytes + P.p_stages * patch_stage;
+    p_stages = P.p_stages; w_stages = P.w_stages;
   }
-  if (P.p_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: patch ring does not fit", L.name);
-  // tensor maps
+  if (p_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: patch ring does not fit", L.name);
+  // ---- tensor maps ----
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   {
@@ -331,62 +375,87 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     CUresult r = enc(&L.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, L.d_in, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(A) -> %d", L.name, (int)r);
+    if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(activation) -> %d", L.name, (int)r);
   }
   {
-    cuuint64_t dims[2] = {32, (cuuint64_t)L.groups * nt * L.BN};
+    cuuint64_t dims[2] = {32, (cuuint64_t)n_slabs * rows_per_slab};
     cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {32, (cuuint32_t)L.BN};
+    const cuuint32_t box[2] = {32, (cuuint32_t)rows_per_slab};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, L.d_wpack, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(B) -> %d", L.name, (int)r);
+    if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(weights) -> %d", L.name, (int)r);
   }
   if (getenv("DAVO_B200_VERBOSE"))
-    fprintf(stderr, "[davo_b200] %s: patch %dx%d (%d B) x%d patches, %d taps, B %s, rings P%d B%d, smem %d\n",
-            L.name, Hp, Wp, P.patch_bytes, np, nt, L.b_resident ? "resident" : "streamed", P.p_stages,
-            P.b_stages, L.smem_bytes);
+    fprintf(stderr, "[davo_b200] %s: %s, tile %dx8 px, %d m-block(s), patch %dx%d (%d B) x%d, %d taps, weights %s, rings P%d W%d, smem %d\n",
+            L.name, L.orient == 0 ? "pixels-on-M" : "channels-on-M", TR, MB, Hp, Wp, patch_bytes, np, nt,
+            L.b_resident ? "resident" : "streamed", p_stages, w_stages, L.smem_bytes);
   return 0;
 }
 
 template <int BN, int EPI, bool RES>
-int launch_conv_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   static int attr_smem = 0;
   if (attr_smem < L.smem_bytes) {
-    CU_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU_OK(cudaFuncSetAttribute(pm::conv_tc_kernel<BN, EPI, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                L.smem_bytes));
     attr_smem = L.smem_bytes;
   }
-  ConvParams P = L.prm;
+  pm::ConvParams P = L.prm_pm;
   P.num_tiles = npairs * L.groups * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
-  conv_tc_kernel<BN, EPI, RES><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
+  pm::conv_tc_kernel<BN, EPI, RES><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
   CU_OK(cudaGetLastError());
   return 0;
 }
 
 template <int BN, int EPI>
-int launch_conv_r(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
-  return L.b_resident ? launch_conv_t<BN, EPI, true>(ctx, L, npairs, st)
-                      : launch_conv_t<BN, EPI, false>(ctx, L, npairs, st);
+int launch_pm_r(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  return L.b_resident ? launch_pm_t<BN, EPI, true>(ctx, L, npairs, st)
+                      : launch_pm_t<BN, EPI, false>(ctx, L, npairs, st);
+}
+
+template <int NPIX, int EPI>
+int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  static int attr_smem = 0;
+  if (attr_smem < L.smem_bytes) {
+    CU_OK(cudaFuncSetAttribute(cm::conv_tc_kernel<NPIX, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               L.smem_bytes));
+    attr_smem = L.smem_bytes;
+  }
+  cm::ConvParams P = L.prm_cm;
+  P.num_tiles = npairs * L.groups * L.tiles_h * L.tiles_w * L.m_blocks;
+  P.out = L.d_out;
+  P.sum_out = ctx->d_sum7;
+  const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
+  cm::conv_tc_kernel<NPIX, EPI><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
+  CU_OK(cudaGetLastError());
+  return 0;
 }
 
 int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  if (L.orient == 1) {
+    if (L.epi == EPI_SUM_RELU)
+      return L.npix == 256 ? launch_cm_t<256, EPI_SUM_RELU>(ctx, L, npairs, st)
+                           : launch_cm_t<128, EPI_SUM_RELU>(ctx, L, npairs, st);
+    return L.npix == 256 ? launch_cm_t<256, EPI_STORE_RELU>(ctx, L, npairs, st)
+                         : launch_cm_t<128, EPI_STORE_RELU>(ctx, L, npairs, st);
+  }
   if (L.epi == EPI_SUM_RELU) {
-    if (L.BN == 256) return launch_conv_t<256, EPI_SUM_RELU, false>(ctx, L, npairs, st);
-    return fail(ctx, DAVO_ERR_ARG, "%s: sum epilogue built for N=256 only", L.name);
+    if (L.BN == 256) return launch_pm_t<256, EPI_SUM_RELU, false>(ctx, L, npairs, st);
+    return fail(ctx, DAVO_ERR_ARG, "%s: pixels-on-M sum epilogue is built for 256 channels only", L.name);
   }
   switch (L.BN) {
-    case 16: return launch_conv_r<16, EPI_STORE_RELU>(ctx, L, npairs, st);
-    case 32: return launch_conv_r<32, EPI_STORE_RELU>(ctx, L, npairs, st);
-    case 64: return launch_conv_r<64, EPI_STORE_RELU>(ctx, L, npairs, st);
-    case 128: return launch_conv_r<128, EPI_STORE_RELU>(ctx, L, npairs, st);
-    case 256: return launch_conv_t<256, EPI_STORE_RELU, false>(ctx, L, npairs, st);
+    case 16: return launch_pm_r<16, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 32: return launch_pm_r<32, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 64: return launch_pm_r<64, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 128: return launch_pm_r<128, EPI_STORE_RELU>(ctx, L, npairs, st);
+    case 256: return launch_pm_t<256, EPI_STORE_RELU, false>(ctx, L, npairs, st);
   }
-  return fail(ctx, DAVO_ERR_ARG, "%s: N=%d has no kernel instance", L.name, L.BN);
+  return fail(ctx, DAVO_ERR_ARG, "%s: %d output channels have no kernel instance", L.name, L.BN);
 }
 
 int launch_conv_direct(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
@@ -583,7 +652,16 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     L.Hout = ph.out; L.Wout = pw.out; L.pad_t = ph.before; L.pad_l = pw.before;
     L.out_stride = cout_total[i];
     L.epi = (i == 6) ? EPI_SUM_RELU : EPI_STORE_RELU;
-    L.tiles_h = (L.Hout + kTileH - 1) / kTileH;
+    // Orientation (measured): channels-on-M for the wide stride-1 layers whose
+    // maps are tall enough for a 32-row tile; pixels-on-M for thin layers and the summed cnv7.
+    const char* force = getenv("DAVO_B200_ORIENT");          // debug: "pm" or "cm" for every layer
+    L.orient = (L.stride == 1 && L.BN >= 128 && L.Hout >= 32) ? 1 : 0;
+    if (force && !strcmp(force, "pm")) L.orient = 0;
+    if (force && !strcmp(force, "cm")) L.orient = 1;
+    if (L.orient == 0 && L.epi == EPI_SUM_RELU && L.BN != 256) L.orient = 1;
+    L.npix = (L.orient == 1 && L.Hout > 16) ? 256 : 128;
+    L.m_blocks = L.orient == 1 ? (L.BN + cm::kBlockM - 1) / cm::kBlockM : 1;
+    L.tiles_h = (L.Hout + L.npix / kTileW - 1) / (L.npix / kTileW);
     L.tiles_w = (L.Wout + kTileW - 1) / kTileW;
     for (int j = 0; j < 16; ++j) L.cmap[j] = j;
     H = L.Hout; W = L.Wout;
@@ -613,7 +691,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   }
   {
     const Layer& L7 = ctx->layers[6];
-    ctx->nparts7 = L7.tiles_h * L7.tiles_w * 4;
+    ctx->nparts7 = L7.tiles_h * L7.tiles_w * (L7.orient == 0 ? 4 : 1);
     if (int rc = dev_alloc(ctx, (void**)&ctx->d_sum7, (size_t)mb * 2 * ctx->nparts7 * 256 * 4)) return rc;
   }
 
