@@ -17,6 +17,7 @@ _LIB = None
 SYMBOLS = (
     "davo_create", "davo_set_weight", "davo_finalize_weights", "davo_forward",
     "davo_forward_host", "davo_get_intermediate", "davo_last_launch_count",
+    "davo_last_host_copy_bytes",
     "davo_profile_layers", "davo_debug_set_conv_impl", "davo_last_error",
     "davo_destroy", "davo_build_info",
 )
@@ -59,6 +60,7 @@ def load() -> C.CDLL:
     lib.davo_forward_host.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp]
     lib.davo_get_intermediate.argtypes = [vp, C.c_char_p, ip, vp, C.c_int64, C.POINTER(C.c_int64)]
     lib.davo_last_launch_count.argtypes = [vp]
+    lib.davo_last_host_copy_bytes.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.davo_profile_layers.argtypes = [vp, ip, fp, C.POINTER(ip), vp]
     lib.davo_debug_set_conv_impl.argtypes = [vp, ip]
     lib.davo_last_error.argtypes = [vp]
@@ -66,7 +68,7 @@ def load() -> C.CDLL:
     lib.davo_destroy.argtypes = [vp]
     lib.davo_destroy.restype = None
     lib.davo_build_info.restype = C.c_char_p
-    for s in SYMBOLS[:9]:
+    for s in SYMBOLS[:10]:
         getattr(lib, s).restype = ip
     _LIB = lib
     return lib

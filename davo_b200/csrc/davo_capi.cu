@@ -106,7 +106,11 @@ struct davo_ctx {
   float* d_c7tmp = nullptr;         // direct path only
   int nparts7 = 0;
   // host-buffer entry point staging
-  uint8_t* s_img = nullptr; float *s_flow = nullptr, *s_seg = nullptr, *s_pose = nullptr;
+  uint8_t* s_img[2] = {nullptr, nullptr};
+  float *s_flow[2] = {nullptr, nullptr}, *s_seg[2] = {nullptr, nullptr}, *s_pose = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_start = nullptr;
+  long long last_h2d = 0, last_d2h = 0;
   // last forward
   int last_launches = 0;
   int last_npairs_mb = 0;
@@ -599,10 +603,16 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (void* p : ctx->allocs) cudaFree(p);
-  if (ctx->s_img) cudaFree(ctx->s_img);
-  if (ctx->s_flow) cudaFree(ctx->s_flow);
-  if (ctx->s_seg) cudaFree(ctx->s_seg);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->s_img[i]) cudaFree(ctx->s_img[i]);
+    if (ctx->s_flow[i]) cudaFree(ctx->s_flow[i]);
+    if (ctx->s_seg[i]) cudaFree(ctx->s_seg[i]);
+    if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+  }
   if (ctx->s_pose) cudaFree(ctx->s_pose);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
@@ -806,31 +816,92 @@ extern "C" int davo_forward(davo_ctx* ctx, int B, const uint8_t* img, const floa
   return 0;
 }
 
+// Host-buffer entry point: the batch is cut into micro-batch chunks; chunk i+1 is copied
+// host->device on a private copy stream while chunk i computes (two staging buffers), and only
+// the planes the graph reads are copied: flow[:,0:2] (davo.py:978-982) and, when the target
+// map is forced to ones, seg[:,0] and seg[:,2] (davo.py:1000-1004).
 extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const float* flow,
                                  const float* seg, const float* depth, float* pose_out, void* stream) {
+  (void)depth;
   if (!ctx) return DAVO_ERR_ARG;
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: B=%d outside 1..%d", B, ctx->cfg.max_batch);
-  CU_OK(cudaSetDevice(ctx->device));
   const davo_config& c = ctx->cfg;
+  if (!img || !pose_out || (c.att_src != 0 && !seg) || ((c.in_mode == 1 || c.att_src == 1) && !flow))
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: null input buffer");
+  CU_OK(cudaSetDevice(ctx->device));
   const size_t hw = (size_t)c.H * c.W;
-  const size_t n_img = hw * 9, n_flow = hw * 8, n_seg = hw * 3;   // per sample
-  if (!ctx->s_img) {
-    CU_OK(cudaMalloc((void**)&ctx->s_img, n_img * c.max_batch));
-    CU_OK(cudaMalloc((void**)&ctx->s_flow, n_flow * 4 * c.max_batch));
-    CU_OK(cudaMalloc((void**)&ctx->s_seg, n_seg * 4 * c.max_batch));
+  const size_t n_img = hw * 9, n_flow = hw * 8, n_seg = hw * 3;   // elements per sample
+  const int cs = std::max(1, ctx->mb / 2);                         // samples per chunk
+  if (!ctx->s_img[0]) {
+    for (int i = 0; i < 2; ++i) {
+      CU_OK(cudaMalloc((void**)&ctx->s_img[i], n_img * cs));
+      CU_OK(cudaMalloc((void**)&ctx->s_flow[i], n_flow * 4 * cs));
+      CU_OK(cudaMalloc((void**)&ctx->s_seg[i], n_seg * 4 * cs));
+      CU_OK(cudaMemset(ctx->s_flow[i], 0, n_flow * 4 * cs));
+      CU_OK(cudaMemset(ctx->s_seg[i], 0, n_seg * 4 * cs));
+      CU_OK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+      CU_OK(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+    }
     CU_OK(cudaMalloc((void**)&ctx->s_pose, (size_t)12 * 4 * c.max_batch));
+    CU_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU_OK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!img || !pose_out) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: null buffer");
-  CU_OK(cudaMemcpyAsync(ctx->s_img, img, n_img * B, cudaMemcpyHostToDevice, st));
-  if (flow) CU_OK(cudaMemcpyAsync(ctx->s_flow, flow, n_flow * 4 * B, cudaMemcpyHostToDevice, st));
-  if (seg) CU_OK(cudaMemcpyAsync(ctx->s_seg, seg, n_seg * 4 * B, cudaMemcpyHostToDevice, st));
-  if (int rc = davo_forward(ctx, B, ctx->s_img, flow ? ctx->s_flow : nullptr, seg ? ctx->s_seg : nullptr,
-                            depth, ctx->s_pose, stream))
-    return rc;
+  cudaStream_t cp = ctx->copy_stream;
+  // the copy stream must not run ahead of work already queued on the caller's stream
+  CU_OK(cudaEventRecord(ctx->ev_start, st));
+  CU_OK(cudaStreamWaitEvent(cp, ctx->ev_start, 0));
+  const bool need_flow = (c.in_mode == 1 || c.att_src == 1);
+  const bool need_seg = c.att_src != 0;
+  const bool seg_tgt = need_seg && !c.att_tgt_ones;
+  size_t h2d = 0;
+  int launches = 0, last_n = 0, chunk = 0;
+  for (int s0 = 0; s0 < B; s0 += cs, ++chunk) {
+    const int ns = std::min(cs, B - s0);
+    const int buf = chunk & 1;
+    if (chunk >= 2) CU_OK(cudaStreamWaitEvent(cp, ctx->ev_consumed[buf], 0));
+    CU_OK(cudaMemcpyAsync(ctx->s_img[buf], img + n_img * s0, n_img * ns, cudaMemcpyHostToDevice, cp));
+    h2d += n_img * ns;
+    if (need_flow) {
+      CU_OK(cudaMemcpy2DAsync(ctx->s_flow[buf], n_flow * 4, flow + n_flow * s0, n_flow * 4, n_flow * 2, ns,
+                              cudaMemcpyHostToDevice, cp));
+      h2d += n_flow * 2 * ns;
+    }
+    if (need_seg) {
+      if (seg_tgt) {
+        CU_OK(cudaMemcpyAsync(ctx->s_seg[buf], seg + n_seg * s0, n_seg * 4 * ns, cudaMemcpyHostToDevice, cp));
+        h2d += n_seg * 4 * ns;
+      } else {
+        for (int pl = 0; pl < 3; pl += 2)
+          CU_OK(cudaMemcpy2DAsync(ctx->s_seg[buf] + hw * pl, n_seg * 4, seg + n_seg * s0 + hw * pl, n_seg * 4,
+                                  hw * 4, ns, cudaMemcpyHostToDevice, cp));
+        h2d += hw * 4 * 2 * ns;
+      }
+    }
+    CU_OK(cudaEventRecord(ctx->ev_copied[buf], cp));
+    CU_OK(cudaStreamWaitEvent(st, ctx->ev_copied[buf], 0));
+    if (int rc = run_microbatch(ctx, 0, 2 * ns, ctx->s_img[buf], ctx->s_flow[buf], ctx->s_seg[buf],
+                                ctx->s_pose + (size_t)12 * s0, st, &launches))
+      return rc;
+    CU_OK(cudaEventRecord(ctx->ev_consumed[buf], st));
+    last_n = 2 * ns;
+  }
   CU_OK(cudaMemcpyAsync(pose_out, ctx->s_pose, (size_t)12 * 4 * B, cudaMemcpyDeviceToHost, st));
   CU_OK(cudaStreamSynchronize(st));
+  ctx->last_launches = launches;
+  ctx->last_npairs_mb = last_n;
+  ctx->last_h2d = (long long)h2d;
+  ctx->last_d2h = (long long)12 * 4 * B;
+  ctx->last_img = ctx->s_img[(chunk - 1) & 1]; ctx->last_flow = ctx->s_flow[(chunk - 1) & 1];
+  ctx->last_seg = ctx->s_seg[(chunk - 1) & 1]; ctx->last_pose = ctx->s_pose; ctx->last_B = last_n / 2;
+  return 0;
+}
+
+extern "C" int davo_last_host_copy_bytes(const davo_ctx* ctx, long long* h2d, long long* d2h) {
+  if (!ctx || !h2d || !d2h) return DAVO_ERR_ARG;
+  *h2d = ctx->last_h2d;
+  *d2h = ctx->last_d2h;
   return 0;
 }
 

@@ -172,6 +172,13 @@ class DAVO(object):
                     "davo_get_intermediate(%s)" % name)
         return buf[:n.value].copy()
 
+    def last_host_copy_bytes(self):
+        """(host->device, device->host) bytes moved by the last numpy-input inference."""
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._check(self._lib.davo_last_host_copy_bytes(self._h, C.byref(a), C.byref(b)),
+                    "davo_last_host_copy_bytes")
+        return int(a.value), int(b.value)
+
     def last_launch_count(self) -> int:
         return int(self._lib.davo_last_launch_count(self._h))
 

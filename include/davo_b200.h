@@ -81,9 +81,12 @@ int davo_forward(davo_ctx*, int B, const uint8_t* img_u8, const float* flow,
                  const float* seg, const float* depth, float* pose_out,
                  void* cuda_stream);
 
-/* Same call with HOST buffers (pinned or pageable): copies inputs in, runs the
- * forward, copies poses out and synchronises the stream -- the end-to-end form
- * of `sess.run` with fed numpy arrays (reference davo.py:1568). */
+/* Same call with HOST buffers (pinned for overlap; pageable works): the end-to-end
+ * form of `sess.run` with fed numpy arrays (reference davo.py:1568).  The batch is
+ * streamed in micro-batch chunks, the host->device copy of chunk i+1 overlapping
+ * the compute of chunk i; only the planes the graph reads are copied (flow[:,0:2],
+ * and seg[:,{0,2}] when the target map is ones).  Poses are copied back and the
+ * stream synchronised before returning. */
 int davo_forward_host(davo_ctx*, int B, const uint8_t* img_u8, const float* flow,
                       const float* seg, const float* depth, float* pose_out,
                       void* cuda_stream);
@@ -96,6 +99,9 @@ int davo_forward_host(davo_ctx*, int B, const uint8_t* img_u8, const float* flow
  * count to *n.  Synchronises. */
 int davo_get_intermediate(davo_ctx*, const char* name, int pair, float* out,
                           int64_t cap, int64_t* n);
+
+/* Bytes the last davo_forward_host moved host->device and device->host. */
+int davo_last_host_copy_bytes(const davo_ctx*, long long* h2d, long long* d2h);
 
 /* Number of kernel launches the last davo_forward issued. */
 int davo_last_launch_count(const davo_ctx*);

@@ -151,6 +151,31 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     assert sysm.last_launch_count() == 10                                    # pool, pack, 7 convs, head
 
 
+@pytest.mark.parametrize("key", ["headline", "static", "no_segmask"])
+def test_host_entry_point_streams_chunks_and_trims_copies(key):
+    """B=7 through davo_forward_host in 2-sample chunks (copy/compute overlap, two staging
+    buffers): same bits as the device entry point; only the planes the graph reads are copied."""
+    _need_gpu()
+    ver = G.CASES[key]
+    w = S.init_weights(ver, random_bias=True)
+    inputs = S.make_inputs(7, H, W, seed=23, bad_label_frac=0.01)
+    sysm, dev = _system(ver, 7, w, inputs, micro_batch=4)
+    a = sysm.inference(None, "pose")["pose"].copy()
+    b = sysm.inference(None, "pose", inputs=inputs)["pose"]
+    assert np.array_equal(a, b)
+    pinned = tuple(torch.as_tensor(x).pin_memory().numpy() for x in inputs)
+    assert np.array_equal(a, sysm.inference(None, "pose", inputs=pinned)["pose"])
+    h2d, d2h = sysm.last_host_copy_bytes()
+    hw = H * W
+    per_sample = hw * 9 + hw * 2 * 2 * 4 + (hw * 2 * 4 if key != "no_segmask" else 0)
+    assert h2d == 7 * per_sample and d2h == 7 * 48
+    # poisoning the planes the graph does not read changes nothing
+    img, flow, seg = (x.copy() for x in inputs)
+    flow[:, 2:] = np.nan
+    seg[:, 1] = 255.0
+    assert np.array_equal(a, sysm.inference(None, "pose", inputs=(img, flow, seg))["pose"])
+
+
 def test_linearity_of_the_head_in_pred_weights():
     """Size-independent property: poses are linear in the pred layer (posenn.py:240-250)."""
     _need_gpu()
