@@ -53,6 +53,20 @@ float host_round_tf32(float x) {   // cvt.rna.tf32.f32
   return x;
 }
 
+// The TF32 neighbour of x on the other side of the exact value (x_hat = RN result).
+float tf32_other_neighbour(float x, float x_hat) {
+  if (x_hat == x) return x_hat;
+  uint32_t u;
+  memcpy(&u, &x_hat, 4);
+  const bool away = fabsf(x_hat) > fabsf(x);      // RN went away from zero -> step towards zero
+  if (away) u -= 0x2000u;
+  else if ((u & 0x7FFFFFFFu) == 0) { float t = ldexpf(1.0f, -126); u = 0; memcpy(&u, &t, 4); if (x < 0) u |= 0x80000000u; }
+  else u += 0x2000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
 int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 int posmod(int a, int b) { return a - floordiv(a, b) * b; }
 
@@ -97,6 +111,7 @@ struct davo_ctx {
   bool finalized = false;
   int mb = 0;                       // frame pairs per micro-batch
   int conv_impl = 0;                // 0 tcgen05 (product), 1 direct fp32 (debug cross-check)
+  bool compensated_rounding = true; // TF32 weight rounding directions chosen so tap sums cancel
   std::vector<Layer> layers;        // cnv1..cnv7
   // device buffers
   std::vector<void*> allocs;
@@ -172,6 +187,97 @@ bool shape_is(const HostTensor* t, std::initializer_list<int64_t> s) {
   size_t i = 0;
   for (int64_t v : s) if (t->shape[i++] != v) return false;
   return true;
+}
+
+// ------------------------------------------------------------ weight rounding --
+// tcgen05.mma.kind::tf32 multiplies by W_hat = tf32(W).  Round-to-nearest leaves, for every
+// (input channel k, output channel n), a sum over the filter taps S[k][n] = sum_t (W_hat - W)[t]
+// that is a random walk of ~sqrt(taps) half-ulps.  After a ReLU every input channel has a
+// positive spatial mean, so S becomes an offset of the layer's output that is the same for
+// every pixel and every sample: the one rounding error that survives the final spatial mean
+// and then accumulates along a composed trajectory.  Both TF32
+// neighbours of W are within one ulp of it, so the rounding DIRECTION of each weight is chosen
+// to make the tap sums cancel:
+//     minimise  sum_regions frac_r * S_r^2  +  lambda * sum_t e_t^2
+// A region is a set of output pixels that see the same subset of taps (zero padding removes
+// whole tap rows / columns near the border -- with dilation 8 on a 32-row map, for half of the
+// pixels).  Greedy descent over single direction changes, starting from round-to-nearest.
+struct TapRegion { uint64_t mask; double frac; };
+
+std::vector<TapRegion> tap_regions(const Layer& L) {
+  std::map<uint32_t, int> rows, cols;
+  for (int o = 0; o < L.Hout; ++o) {
+    uint32_t m = 0;
+    for (int t = 0; t < L.k; ++t) { const int i = o * L.stride + t * L.dil - L.pad_t; if (i >= 0 && i < L.Hin) m |= 1u << t; }
+    rows[m]++;
+  }
+  for (int o = 0; o < L.Wout; ++o) {
+    uint32_t m = 0;
+    for (int t = 0; t < L.k; ++t) { const int i = o * L.stride + t * L.dil - L.pad_l; if (i >= 0 && i < L.Win) m |= 1u << t; }
+    cols[m]++;
+  }
+  std::vector<TapRegion> out;
+  for (auto& r : rows)
+    for (auto& c : cols) {
+      uint64_t mask = 0;
+      for (int ty = 0; ty < L.k; ++ty)
+        for (int tx = 0; tx < L.k; ++tx)
+          if ((r.first >> ty & 1u) && (c.first >> tx & 1u)) mask |= 1ull << (ty * L.k + tx);
+      if (mask) out.push_back(TapRegion{mask, (double)r.second * c.second / ((double)L.Hout * L.Wout)});
+    }
+  return out;
+}
+
+// Returns the TF32 weights, HWIO per group: [g][ty][tx][ci][n].
+template <class GetW>
+std::vector<float> round_weights_tf32(const Layer& L, GetW getw, bool compensate) {
+  const int T = L.k * L.k;
+  std::vector<float> out((size_t)L.groups * T * L.Cin_w * L.BN);
+  auto at = [&](int g, int t, int ci, int n) -> float& { return out[(((size_t)g * T + t) * L.Cin_w + ci) * L.BN + n]; };
+  const std::vector<TapRegion> regions = tap_regions(L);
+  const int R = (int)regions.size();
+  const double lambda = 0.05;
+  std::vector<double> e0(T), e1(T), S(R);
+  std::vector<float> w0(T), w1(T);
+  std::vector<char> flip(T);
+  for (int g = 0; g < L.groups; ++g)
+    for (int ci = 0; ci < L.Cin_w; ++ci)
+      for (int n = 0; n < L.BN; ++n) {
+        for (int t = 0; t < T; ++t) {
+          const float w = getw(g, t / L.k, t % L.k, ci, n);
+          w0[t] = host_round_tf32(w);
+          w1[t] = tf32_other_neighbour(w, w0[t]);
+          e0[t] = (double)w0[t] - (double)w;
+          e1[t] = (double)w1[t] - (double)w;
+          flip[t] = 0;
+        }
+        if (compensate) {
+          for (int r = 0; r < R; ++r) {
+            double a = 0.0;
+            for (int t = 0; t < T; ++t) if (regions[r].mask >> t & 1ull) a += e0[t];
+            S[r] = a;
+          }
+          for (int iter = 0; iter < 4 * T; ++iter) {
+            int best = -1;
+            double best_dj = -1e-30;
+            for (int t = 0; t < T; ++t) {
+              if (w1[t] == w0[t]) continue;
+              const double cur = flip[t] ? e1[t] : e0[t], alt = flip[t] ? e0[t] : e1[t];
+              const double d = alt - cur;
+              double dj = lambda * (alt * alt - cur * cur);
+              for (int r = 0; r < R; ++r)
+                if (regions[r].mask >> t & 1ull) dj += regions[r].frac * ((S[r] + d) * (S[r] + d) - S[r] * S[r]);
+              if (dj < best_dj) { best_dj = dj; best = t; }
+            }
+            if (best < 0) break;
+            const double d = flip[best] ? e0[best] - e1[best] : e1[best] - e0[best];
+            for (int r = 0; r < R; ++r) if (regions[r].mask >> best & 1ull) S[r] += d;
+            flip[best] ^= 1;
+          }
+        }
+        for (int t = 0; t < T; ++t) at(g, t, ci, n) = flip[t] ? w1[t] : w0[t];
+      }
+  return out;
 }
 
 // ---------------------------------------------------------------- layer plan --
@@ -275,6 +381,10 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
   }
   const int patch_bytes = Hp * Wp * kSlabBytes;
   const int patch_stage = (patch_bytes + 1023) & ~1023;
+  const std::vector<float> wr = round_weights_tf32(L, getw, ctx->compensated_rounding);
+  auto wq = [&](int g, int ty, int tx, int ci, int n) {
+    return wr[((((size_t)g * L.k + ty) * L.k + tx) * L.Cin_w + ci) * L.BN + n];
+  };
   // ---- weights: TF32-rounded, K-major 32-float slabs ----
   //   pm: [g][tap][Cout][32]                      (Cout = MMA N)
   //   cm: [g][m-block][tap][128][32], zero rows beyond the real channels (128 = MMA M)
@@ -292,7 +402,7 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
           for (int kk = 0; kk < 32; ++kk) {
             const Ent& e = taps[order[k]].e[kk];
             if (e.ci >= 0)
-              pack[(slab * rows_per_slab + m) * 32 + kk] = host_round_tf32(getw(g, e.ty, e.tx, e.ci, n));
+              pack[(slab * rows_per_slab + m) * 32 + kk] = wq(g, e.ty, e.tx, e.ci, n);
           }
         }
   if (int rc = dev_alloc(ctx, (void**)&L.d_wpack, pack.size() * 4)) return rc;
@@ -306,7 +416,7 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
       for (int tx = 0; tx < L.k; ++tx)
         for (int ci = 0; ci < L.Cin_w; ++ci)
           for (int n = 0; n < L.BN; ++n)
-            hw[(((size_t)ty * L.k + tx) * L.Cin_w + ci) * L.BN + n] = host_round_tf32(getw(g, ty, tx, ci, n));
+            hw[(((size_t)ty * L.k + tx) * L.Cin_w + ci) * L.BN + n] = wq(g, ty, tx, ci, n);
     if (int rc = dev_alloc(ctx, (void**)&L.d_whwio[g], hw.size() * 4)) return rc;
     CU_OK(cudaMemcpy(L.d_whwio[g], hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
   }
@@ -595,6 +705,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   int mb = cfg->micro_batch > 0 ? cfg->micro_batch : 34;
   if (mb > 2 * cfg->max_batch) mb = 2 * cfg->max_batch;
   ctx->mb = mb;
+  if (const char* cr = getenv("DAVO_B200_WEIGHT_ROUNDING"))     // "nearest": plain round-to-nearest
+    ctx->compensated_rounding = strcmp(cr, "nearest") != 0;
   *out = ctx;
   return 0;
 }

@@ -72,9 +72,11 @@ def test_variants_match_oracle_and_golden(key):
                                        rtol=2e-6, atol=1e-7)
 
 
-def test_every_layer_matches_oracle_per_pixel():
-    """Intermediates of both frame pairs of a sample vs the TF32-operand oracle (indexing check)."""
+def test_every_layer_matches_oracle_per_pixel(monkeypatch):
+    """Intermediates of both frame pairs of a sample vs the TF32-operand oracle (indexing check).
+    The oracle's TF32 emulation rounds weights to nearest, so the library is told to do the same."""
     _need_gpu()
+    monkeypatch.setenv("DAVO_B200_WEIGHT_ROUNDING", "nearest")
     w = S.init_weights(HEADLINE, random_bias=True)
     inputs = S.make_inputs(1, H, W, seed=99, bad_label_frac=0.01)
     taps = {}
@@ -100,6 +102,27 @@ def test_every_layer_matches_oracle_per_pixel():
         s7 = sysm.get_intermediate("cnv7_sum", p).reshape(2, 256)
         assert _rel(s7[0], tp["cnv7_rotation"][0].sum((0, 1))) < 2e-4
         assert _rel(s7[1], tp["cnv7_translation"][0].sum((0, 1))) < 2e-4
+
+
+def test_compensated_weight_rounding_removes_the_systematic_offset(monkeypatch):
+    """Default weight rounding picks, per weight, the TF32 neighbour that makes the rounding errors
+    of a filter's taps cancel (davo_capi.cu: round_weights_tf32).  What it must buy: the
+    sample-independent offset of the pooled cnv7 features and of the poses against the exact
+    (fp64, unrounded) oracle shrinks, while every single pose stays inside the tolerance."""
+    _need_gpu()
+    B = 8
+    w = S.init_weights(HEADLINE, random_bias=True)
+    inputs = S.make_inputs(B, H, W, seed=4242)
+    ref = O.davo_forward(HEADLINE, *inputs, w, torch.float64)
+    bias = {}
+    for mode in ("nearest", "compensated"):
+        monkeypatch.setenv("DAVO_B200_WEIGHT_ROUNDING", mode)
+        sysm, _ = _system(HEADLINE, B, w, inputs)
+        out = sysm.inference(None, "pose")["pose"]
+        _assert_pose(out, ref)
+        bias[mode] = np.abs((out.astype(np.float64) - ref).mean((0, 1)))    # offset common to all pairs
+    assert bias["compensated"].max() < 0.5 * bias["nearest"].max(), bias
+    assert bias["compensated"].max() < 2e-7, bias
 
 
 def test_tensor_core_path_agrees_with_direct_fp32_conv_on_gpu():

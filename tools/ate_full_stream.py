@@ -9,20 +9,27 @@ from oracle import davo_oracle as O
 ver = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh"
 n, chunk = 4539, 64
 w = S.init_weights(ver)
-sysm = None
-gpu, ref = [], []
+modes = sys.argv[1:] or ["compensated"]      # DAVO_B200_WEIGHT_ROUNDING values to compare
+systems = {}
+for m in modes:
+    os.environ["DAVO_B200_WEIGHT_ROUNDING"] = m
+    systems[m] = DAVO(version=ver)
+    systems[m].setup_inference(128, 416, "davo", 3, chunk, device=0)
+    systems[m].load_weights(w)
+gpu, ref = {m: [] for m in modes}, []
 t0 = time.time()
 for s in range(0, n, chunk):
     b = min(chunk, n - s)
     inputs = S.make_inputs(b, 128, 416, seed=1000 + s)
-    if sysm is None:
-        sysm = DAVO(version=ver)
-        sysm.setup_inference(128, 416, "davo", 3, chunk, device=0)
-        sysm.load_weights(w)
-    gpu.append(sysm.inference(None, "pose", inputs=inputs)["pose"])
+    for m in modes:
+        gpu[m].append(systems[m].inference(None, "pose", inputs=inputs)["pose"])
     ref.append(O.davo_forward(ver, *inputs, w, torch.float32))
-gpu, ref = np.concatenate(gpu), np.concatenate(ref)
-tg, tr = geo_utils.compose_trajectory(gpu), O.compose_trajectory(ref)
+ref = np.concatenate(ref)
+tr = O.compose_trajectory(ref)
 path = float(np.linalg.norm(np.diff(tr[:, :3, 3], axis=0), axis=1).sum())
-print("samples %d frames %d  max|dpose| %.3e  ATE %.3e m  path %.2f m  end-point error %.3e m  (%.0f s)" % (
-    n, tg.shape[0], np.abs(gpu - ref).max(), O.ate(tg, tr), path, np.linalg.norm(tg[-1, :3, 3] - tr[-1, :3, 3]), time.time() - t0))
+for m in modes:
+    g = np.concatenate(gpu[m])
+    tg = geo_utils.compose_trajectory(g)
+    print("[%s] samples %d frames %d  max|dpose| %.3e  mean dpose %s  ATE %.3e m  path %.2f m  end-point error %.3e m  (%.0f s)" % (
+        m, n, tg.shape[0], np.abs(g - ref).max(), np.array2string((g - ref).mean((0, 1)), precision=2), O.ate(tg, tr), path,
+        np.linalg.norm(tg[-1, :3, 3] - tr[-1, :3, 3]), time.time() - t0), flush=True)
