@@ -5,7 +5,7 @@
 
 namespace davo {
 
-constexpr int kMaxPatches = 16;
+constexpr int kMaxPatches = 24;
 constexpr int kMaxTaps = 144;
 constexpr int kTileW = 8;                           // tile columns: one 8-row UMMA group
 constexpr int kSlabBytes = 128;                     // 32 tf32
@@ -28,6 +28,11 @@ struct PatchDesc {
 struct TapDesc {
   uint16_t a_off;   // window origin inside the patch, in 128-B rows: row * Wp + col
   uint16_t b_idx;   // weight slab index
+  // Column-widened layers only (conv_pm.cuh, WIDE): the MMA covers a window of the accumulator.
+  uint8_t n16;      // MMA N / 16
+  uint8_t dcol16;   // first accumulator column / 16
+  uint8_t brow8;    // first row of the weight slab / 8
+  uint8_t fresh;    // 1: first MMA to touch its accumulator columns in the tile (overwrite)
 };
 
 enum { EPI_STORE_RELU = 0, EPI_SUM_RELU = 1 };

@@ -24,6 +24,19 @@
 //   through a ring (one 2-D TMA box per tap) or, for the thin layers, loaded once
 //   and kept resident in shared memory for the CTA's whole life.
 //
+// * Column-widened form (WIDE; the thin stride-2 layers cnv1, cnv2).  One tcgen05.mma of
+//   M=128, K=8 costs >= 85 cycles however small N is (tools/experiments/mma_rate.cu), so a
+//   16-channel layer with pixels on M is bound by the NUMBER of MMAs.  Here one M row is a
+//   run of G horizontally adjacent output pixels of one image row and N = G x Cout holds
+//   all of them: the slab "input pixel pair c of the run" feeds output pixel g through
+//   filter column pair d = c - g, so its weight operand is a WINDOW of one resident block
+//   [W[d_max]; ...; W[d_min]] per filter row and its result a window of the accumulator
+//   (per-tap N, first column and first weight row).  Every input pair position c is its own
+//   patch {32 floats at 32*(c mod G), tile_w runs, 1 parity, Hp rows, 1} of the view
+//   [N][H/2][2][W/2G][2G*C]; a tile is tile_h rows x tile_w runs with tile_w == Wp, so its
+//   128 M rows are 128 consecutive 128-B slabs.  cnv1: G = 8 -> 308 MMAs per 1024 pixels
+//   instead of 896.
+//
 // Warp roles (224 threads): warp 0 patch (A) TMA producer, warp 6 weight (B) TMA
 // producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue: TMEM -> registers ->
 // bias/ReLU/round -> a per-warp swizzled smem transpose -> global stores of whole 128-B
@@ -52,6 +65,10 @@ struct ConvParams {
   int patch_bytes;                // Hp * Wp * 128 (what TMA delivers)
   int patch_stage_bytes;          // rounded up to 1024
   int p_stages, b_stages;         // ring depths (b_stages unused when B is resident)
+  // WIDE only
+  int tile_h, tile_w;             // tile = tile_h output rows x tile_w runs (tile_h * tile_w = 128)
+  int run_px;                     // G: output pixels per run (per M row)
+  int b_boxes, b_box_rows;        // resident weights: one TMA box of b_box_rows rows per filter row
   float* out;           // EPI_STORE: [pairs][Hout][Wout][out_stride]
   const float* bias;    // [groups * BN]
   float* sum_out;       // EPI_SUM:   [pairs][groups][tiles_h*tiles_w][4][BN]
@@ -66,7 +83,7 @@ struct ConvCfg {
   static constexpr int kTmemCols = 2 * kAccStride;                 // power of two for BN in {16..256}
 };
 
-template <int BN, int EPI, bool B_RESIDENT>
+template <int BN, int EPI, bool B_RESIDENT, bool WIDE = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvParams p) {
@@ -76,10 +93,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   const int PS = p.p_stages;
+  static_assert(!WIDE || (B_RESIDENT && EPI == EPI_STORE_RELU && BN >= 32), "WIDE: resident weights, store epilogue");
   const int BS = B_RESIDENT ? p.n_taps * p.groups : p.b_stages;   // resident: every slab has a home
+  const int b_bytes = WIDE ? p.b_boxes * p.b_box_rows * kSlabBytes : BS * Cfg::kBBytes;
+  const int TH = WIDE ? p.tile_h : kTileH, TW = WIDE ? p.tile_w : kTileW;
   uint8_t* smem_p = smem;
   uint8_t* smem_b = smem + PS * p.patch_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + BS * Cfg::kBBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + b_bytes);
   uint64_t* p_full = bars;                        // [kMaxStages] TMA -> MMA
   uint64_t* p_empty = bars + kMaxStages;          // [kMaxStages] MMA -> TMA
   uint64_t* b_full = bars + 2 * kMaxStages;       // [kMaxStages] (resident: [0] only)
@@ -132,8 +152,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int r = tile - n * tiles_per_pair;
         const int g = r / tiles_per_img;
         r -= g * tiles_per_img;
-        const int h0 = (r / p.tiles_w) * kTileH;
-        const int w0 = (r % p.tiles_w) * kTileW;
+        const int h0 = (r / p.tiles_w) * TH;
+        const int w0 = (r % p.tiles_w) * TW;
         for (int pi = 0; pi < p.n_patches; ++pi) {
           const PatchDesc d = p.patches[pi];
           TWAIT(0, mbar_wait(&p_empty[ps], pphase ^ 1));
@@ -147,7 +167,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 6) {
     // ------------------------------------------------ weight (B) producer --
     if (lane == 0) {
-      if constexpr (B_RESIDENT) {
+      if constexpr (WIDE) {
+        mbar_expect_tx(&b_full[0], b_bytes);
+        for (int i = 0; i < p.b_boxes; ++i)
+          tma_load_2d(smem_b + i * p.b_box_rows * kSlabBytes, &tmB, &b_full[0], 0, i * p.b_box_rows);
+      } else if constexpr (B_RESIDENT) {
         // every weight slab of the layer, once, for the life of the CTA
         const int nb = p.n_taps * p.groups;
         mbar_expect_tx(&b_full[0], nb * Cfg::kBBytes);
@@ -171,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // --------------------------------------------------------- MMA issuer --
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(kTileM, BN);
-      const uint32_t sbo = (uint32_t)p.patch_w * kSlabBytes;
+      const uint32_t sbo = WIDE ? 1024u : (uint32_t)p.patch_w * kSlabBytes;
       int ps = 0, bs = 0;
       uint32_t pphase = 0, bphase = 0;
       int it = 0;
@@ -194,6 +218,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t pbase = smem_u32(smem_p + ps * p.patch_stage_bytes);
           for (int t = 0; t < pd.ntaps; ++t) {
             const TapDesc td = p.taps[pd.tap0 + t];
+            if constexpr (WIDE) {
+              const uint32_t baddr = smem_u32(smem_b) + ((uint32_t)td.b_idx * p.b_box_rows + td.brow8 * 8u) * kSlabBytes;
+              const uint64_t da = umma_desc(pbase + (uint32_t)td.a_off * kSlabBytes, sbo);
+              const uint64_t db = umma_desc(baddr, 1024);
+              const uint32_t id = umma_idesc_tf32(kTileM, 0) | ((uint32_t)td.n16 << 18);   // N>>3 at bit 17
+              const uint32_t dw = d + td.dcol16 * 16u;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma_tf32(dw, da + 2 * kk, db + 2 * kk, id, (kk == 0 && td.fresh) ? 0u : 1u);
+              continue;
+            }
             uint32_t baddr;
             if constexpr (B_RESIDENT) {
               baddr = smem_u32(smem_b + (g * p.n_taps + td.b_idx) * Cfg::kBBytes);
@@ -234,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       r -= g * tiles_per_img;
       const int h = (r / p.tiles_w) * kTileH + (m >> 3);
       const int w = (r % p.tiles_w) * kTileW + (m & 7);
-      const bool valid = (h < p.Hout) && (w < p.Wout);
+      const bool valid = (h < p.Hout) && (w < p.Wout);     // (unused by the WIDE store epilogue)
       const float* bias = bias_s + g * BN;
       TWAIT(5, mbar_wait(&acc_full[acc], acc_phase));
       tc_fence_after();
@@ -253,6 +288,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int sub = lane / LPP, cq = lane % LPP;
         const int th0 = (r / p.tiles_w) * kTileH + q * 4, tw0 = (r % p.tiles_w) * kTileW;
         float* const obase = p.out + (size_t)n * p.Hout * p.Wout * p.out_stride + g * BN + cq * 4;
+        const int wide_h0 = (r / p.tiles_w) * TH, wide_w0 = (r % p.tiles_w) * TW;
+        const int wide_runs = WIDE ? p.Wout / p.run_px : 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
           uint32_t v[CH];
@@ -273,9 +310,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int s2 = 0; s2 < 32 / PPS; ++s2) {
             const int rr = s2 * PPS + sub;          // pixel row within this warp's 32
             const float4 o = *reinterpret_cast<const float4*>(stg + rr * RB + ((cq ^ (rr & (LPP - 1))) << 4));
-            const int hh = th0 + (rr >> 3), ww = tw0 + (rr & 7);
-            if (hh < p.Hout && ww < p.Wout)
-              *reinterpret_cast<float4*>(obase + ((size_t)hh * p.Wout + ww) * p.out_stride + c0) = o;
+            if constexpr (WIDE) {
+              // M row = run of run_px pixels x Cout channels = BN consecutive floats of the output
+              const int mm = q * 32 + rr;
+              const int hh = wide_h0 + mm / TW, run = wide_w0 + mm % TW;
+              if (hh < p.Hout && run < wide_runs)
+                *reinterpret_cast<float4*>(obase + ((size_t)hh * p.Wout + (size_t)run * p.run_px) * p.out_stride + c0) = o;
+            } else {
+              const int hh = th0 + (rr >> 3), ww = tw0 + (rr & 7);
+              if (hh < p.Hout && ww < p.Wout)
+                *reinterpret_cast<float4*>(obase + ((size_t)hh * p.Wout + ww) * p.out_stride + c0) = o;
+            }
           }
         }
       } else {

@@ -93,6 +93,8 @@ struct Layer {
   int npix = 128;              // output pixels per tile: 128 = 16x8 (pm, or cm on short maps), 256 = 32x8
   int m_blocks = 1;            // cm: 128-channel blocks per group
   bool b_resident = false;     // pm: all weight slabs stay in shared memory
+  int wide_G = 0;              // pm, column-widened: output pixels per M row (0 = off)
+  int wide_tw = 0;             //   runs per tile row (tile = 128/wide_tw rows x wide_tw runs)
   bool lo_alias = false;       // cnv1: packed channels 10-15 are TF32 residuals of 0-2, 5-7
   int smem_bytes = 0;
   CUtensorMap tmA, tmB;          // activation (patch) map, weight map
@@ -508,6 +510,156 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
   return 0;
 }
 
+// ----------------------------------------------------------- widened layer plan --
+// Column-widened plan of a thin stride-2 layer whose input has 16 channels (cnv1, cnv2):
+// one M row = a run of G adjacent output pixels, N = G * Cout (conv_pm.cuh, WIDE).
+//   output pixel g of a run reads input pixel 2g + tx - pad_l (relative to the run's first
+//   input pixel 2G*j); pixel pair c = floor(.. / 2), wp = .. mod 2, and with d = c - g the
+//   filter column is tx = 2d + wp + pad_l.  Weight block of filter row ty:
+//   R[ty] = [W[d_max]; ...; W[d_min]], W[d] = Cout rows x 32 (two pixels x 16 channels).
+//   Pair c feeds g in [c - d_max, c - d_min] (clipped to the run): rows
+//   (d_max - c + g_lo) * Cout.. of R[ty], accumulator columns g_lo * Cout...
+template <class GetW>
+int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bias_host) {
+  const int G = L.wide_G, TWc = L.wide_tw, THr = 128 / TWc, Co = L.BN, NW = G * Co;
+  if (NW != 128) return fail(ctx, DAVO_ERR_ARG, "%s: the widened kernel is built for N = 128 (got %d)", L.name, NW);
+  const int d_min = floordiv(-L.pad_l, 2), d_max = floordiv(L.k - 1 - L.pad_l, 2), nd = d_max - d_min + 1;
+  const int c_min = d_min, c_max = floordiv(2 * (G - 1) + L.k - 1 - L.pad_l, 2);
+  const std::vector<float> wr = round_weights_tf32(L, getw, ctx->compensated_rounding);
+  auto wq = [&](int ty, int tx, int ci, int n) { return wr[(((size_t)ty * L.k + tx) * L.Cin_w + ci) * Co + n]; };
+  auto weight_channel = [&](int ch) {            // packed input channel -> HWIO input channel, -1: none
+    if (L.lo_alias && ch >= 10) { const int alias[6] = {0, 1, 2, 5, 6, 7}; ch = alias[ch - 10]; }
+    if (L.use_cmap) { for (int i = 0; i < L.Cin_w; ++i) if (L.cmap[i] == ch) return i; return -1; }
+    return ch < L.Cin_w ? ch : -1;
+  };
+  // ---- weights: [ty][d_max..d_min][Cout][32] ----
+  const int box_rows = nd * Co;
+  std::vector<float> pack((size_t)L.k * box_rows * 32, 0.f);
+  for (int ty = 0; ty < L.k; ++ty)
+    for (int b = 0; b < nd; ++b)
+      for (int n = 0; n < Co; ++n)
+        for (int kk = 0; kk < 32; ++kk) {
+          const int tx = 2 * (d_max - b) + kk / 16 + L.pad_l, ci = weight_channel(kk % 16);
+          if (tx >= 0 && tx < L.k && ci >= 0) pack[(((size_t)ty * nd + b) * Co + n) * 32 + kk] = wq(ty, tx, ci, n);
+        }
+  if (int rc = dev_alloc(ctx, (void**)&L.d_wpack, pack.size() * 4)) return rc;
+  CU_OK(cudaMemcpy(L.d_wpack, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice));
+  std::vector<float> bias_rep((size_t)NW);
+  for (int i = 0; i < NW; ++i) bias_rep[i] = bias_host[i % Co];
+  if (int rc = dev_alloc(ctx, (void**)&L.d_bias, bias_rep.size() * 4)) return rc;
+  CU_OK(cudaMemcpy(L.d_bias, bias_rep.data(), bias_rep.size() * 4, cudaMemcpyHostToDevice));
+  {
+    std::vector<float> hw((size_t)L.k * L.k * L.Cin_w * Co);
+    for (int ty = 0; ty < L.k; ++ty)
+      for (int tx = 0; tx < L.k; ++tx)
+        for (int ci = 0; ci < L.Cin_w; ++ci)
+          for (int n = 0; n < Co; ++n) hw[(((size_t)ty * L.k + tx) * L.Cin_w + ci) * Co + n] = wq(ty, tx, ci, n);
+    if (int rc = dev_alloc(ctx, (void**)&L.d_whwio[0], hw.size() * 4)) return rc;
+    CU_OK(cudaMemcpy(L.d_whwio[0], hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // ---- patches (one per pair position and row parity) and taps ----
+  // The tile's first MMAs must overwrite the accumulator: start with pair positions whose
+  // column windows partition the run, on the parity of filter row 0.
+  std::vector<int> cover;
+  for (int s0 = 0; s0 < G;) {
+    const int c = s0 + d_max;
+    cover.push_back(c);
+    s0 = std::min(c - d_min, G - 1) + 1;
+  }
+  const int par0 = posmod(-L.pad_t, 2);
+  struct P2 { int c, par; };
+  std::vector<P2> plist;
+  for (int c : cover) plist.push_back(P2{c, par0});
+  for (int par = 0; par < 2; ++par)
+    for (int c = c_min; c <= c_max; ++c) {
+      bool seen = false;
+      for (const P2& q : plist) seen |= (q.c == c && q.par == par);
+      if (!seen) plist.push_back(P2{c, par});
+    }
+  int dh_lo[2] = {1 << 20, 1 << 20}, dh_hi[2] = {-(1 << 20), -(1 << 20)};
+  for (int ty = 0; ty < L.k; ++ty) {
+    const int dy = ty - L.pad_t, par = posmod(dy, 2), dh = floordiv(dy, 2);
+    dh_lo[par] = std::min(dh_lo[par], dh); dh_hi[par] = std::max(dh_hi[par], dh);
+  }
+  const int Hp = THr + std::max(dh_hi[0] - dh_lo[0], dh_hi[1] - dh_lo[1]), Wp = TWc;
+  PatchDesc pdesc[kMaxPatches];
+  TapDesc tdesc[kMaxTaps];
+  memset(pdesc, 0, sizeof pdesc);
+  memset(tdesc, 0, sizeof tdesc);
+  int np = 0, nt = 0;
+  for (const P2& q : plist) {
+    if (np >= kMaxPatches) return fail(ctx, DAVO_ERR_ARG, "%s: too many patches for the widened plan", L.name);
+    PatchDesc& d = pdesc[np];
+    d.c = (int16_t)(32 * posmod(q.c, G)); d.dw = (int8_t)floordiv(q.c, G); d.par = (int8_t)q.par;
+    d.dh = (int8_t)dh_lo[q.par]; d.tap0 = (uint16_t)nt;
+    const int g_lo = std::max(q.c - d_max, 0), g_hi = std::min(q.c - d_min, G - 1);
+    const bool covers = np < (int)cover.size();
+    int n_here = 0;
+    for (int ty = 0; ty < L.k; ++ty) {
+      const int dy = ty - L.pad_t;
+      if (posmod(dy, 2) != q.par) continue;
+      if (nt >= kMaxTaps) return fail(ctx, DAVO_ERR_ARG, "%s: too many taps for the widened plan", L.name);
+      TapDesc& t = tdesc[nt++];
+      t.a_off = (uint16_t)((floordiv(dy, 2) - dh_lo[q.par]) * Wp);
+      t.b_idx = (uint16_t)ty;
+      t.n16 = (uint8_t)((g_hi - g_lo + 1) * Co / 16);
+      t.dcol16 = (uint8_t)(g_lo * Co / 16);
+      t.brow8 = (uint8_t)((d_max - q.c + g_lo) * Co / 8);
+      t.fresh = (covers && n_here == 0) ? 1 : 0;
+      ++n_here;
+    }
+    d.ntaps = (uint8_t)n_here;
+    ++np;
+  }
+  const int patch_bytes = Hp * Wp * kSlabBytes;
+  const int patch_stage = (patch_bytes + 1023) & ~1023;
+  pm::ConvParams& P = L.prm_pm;
+  memset(&P, 0, sizeof P);
+  P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.groups = 1;
+  P.Hout = L.Hout; P.Wout = L.Wout; P.out_stride = L.out_stride;
+  P.cin_group_off = 0;
+  P.n_patches = np; P.n_taps = nt; P.patch_w = Wp;
+  P.patch_bytes = patch_bytes; P.patch_stage_bytes = patch_stage;
+  P.bias = L.d_bias;
+  P.tile_h = THr; P.tile_w = TWc; P.run_px = G; P.b_boxes = L.k; P.b_box_rows = box_rows;
+  memcpy(P.patches, pdesc, sizeof pdesc);
+  memcpy(P.taps, tdesc, sizeof tdesc);
+  const int fixed = 1024 /*alignment*/ + kBarrierBytes + pm::kBiasSmemBytes + pm::kEpiStageBytes;
+  const int resident_bytes = L.k * box_rows * kSlabBytes;
+  L.b_resident = true;
+  P.p_stages = std::min(kMaxStages, (kSmemBudget - fixed - resident_bytes) / patch_stage);
+  P.b_stages = 0;
+  if (P.p_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: widened plan does not fit shared memory", L.name);
+  L.smem_bytes = fixed + resident_bytes + P.p_stages * patch_stage;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  {
+    const cuuint64_t C = L.Cin_total, H = L.Hin, W = L.Win, N = ctx->mb;
+    const cuuint64_t dims[5] = {2 * G * C, W / (2 * G), 2, H / 2, N};
+    const cuuint64_t strides[4] = {2 * G * C * 4, W * C * 4, 2 * W * C * 4, H * W * C * 4};
+    const cuuint32_t box[5] = {32, (cuuint32_t)Wp, 1, (cuuint32_t)Hp, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&L.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, L.d_in, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(activation) -> %d", L.name, (int)r);
+  }
+  {
+    const cuuint64_t dims[2] = {32, (cuuint64_t)L.k * box_rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, L.d_wpack, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(weights) -> %d", L.name, (int)r);
+  }
+  if (getenv("DAVO_B200_VERBOSE"))
+    fprintf(stderr, "[davo_b200] %s: pixels-on-M widened x%d (N=%d), tile %dx%d runs, patch %dx%d (%d B) x%d, %d taps, weights resident %d B, ring P%d, smem %d\n",
+            L.name, G, NW, THr, TWc, Hp, Wp, patch_bytes, np, nt, resident_bytes, P.p_stages, L.smem_bytes);
+  return 0;
+}
+
 template <int BN, int EPI, bool RES>
 int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   static int attr_smem = 0;
@@ -522,6 +674,22 @@ int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   P.sum_out = ctx->d_sum7;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
   pm::conv_tc_kernel<BN, EPI, RES><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_pm_wide(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  static int attr_smem = 0;
+  auto* kern = pm::conv_tc_kernel<128, EPI_STORE_RELU, true, true>;
+  if (attr_smem < L.smem_bytes) {
+    CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    attr_smem = L.smem_bytes;
+  }
+  pm::ConvParams P = L.prm_pm;
+  P.num_tiles = npairs * L.tiles_h * L.tiles_w;
+  P.out = L.d_out;
+  const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
+  kern<<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
   CU_OK(cudaGetLastError());
   return 0;
 }
@@ -558,6 +726,7 @@ int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
     return L.npix == 256 ? launch_cm_t<256, EPI_STORE_RELU>(ctx, L, npairs, st)
                          : launch_cm_t<128, EPI_STORE_RELU>(ctx, L, npairs, st);
   }
+  if (L.wide_G) return launch_pm_wide(ctx, L, npairs, st);
   if (L.epi == EPI_SUM_RELU) {
     if (L.BN == 256) return launch_pm_t<256, EPI_SUM_RELU, false>(ctx, L, npairs, st);
     return fail(ctx, DAVO_ERR_ARG, "%s: pixels-on-M sum epilogue is built for 256 channels only", L.name);
@@ -785,6 +954,21 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     L.m_blocks = L.orient == 1 ? (L.BN + cm::kBlockM - 1) / cm::kBlockM : 1;
     L.tiles_h = (L.Hout + L.npix / kTileW - 1) / (L.npix / kTileW);
     L.tiles_w = (L.Wout + kTileW - 1) / kTileW;
+    // Thin stride-2 layers: runs of G output pixels on one M row, N = G * Cout = 128 (conv_pm.cuh, WIDE).
+    const char* wide_env = getenv("DAVO_B200_WIDE");          // debug: "0" switches the widened plan off
+    const int G = 128 / L.BN;
+    if (L.orient == 0 && L.stride == 2 && L.Cin_total == 16 && L.groups == 1 && L.BN <= 32 && (L.Win % (2 * G)) == 0 &&
+        L.epi == EPI_STORE_RELU && !(wide_env && !strcmp(wide_env, "0"))) {
+      const int runs = L.Wout / G;
+      long best = -1;
+      for (int tw = 2; tw <= 8; tw *= 2) {
+        const long tiles = (long)((L.Hout + 128 / tw - 1) / (128 / tw)) * ((runs + tw - 1) / tw);
+        if (best < 0 || tiles < best) { best = tiles; L.wide_tw = tw; }
+      }
+      L.wide_G = G;
+      L.tiles_h = (L.Hout + 128 / L.wide_tw - 1) / (128 / L.wide_tw);
+      L.tiles_w = (runs + L.wide_tw - 1) / L.wide_tw;
+    }
     for (int j = 0; j < 16; ++j) L.cmap[j] = j;
     H = L.Hout; W = L.Wout;
   }
@@ -832,7 +1016,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     if (int rc = need_conv(names[i], L.k, L.Cin_w, L.BN, &w, &b)) return rc;
     const int Ci = L.Cin_w, Co = L.BN, K = L.k;
     auto getw = [&](int, int ty, int tx, int ci, int n) { return w->data[(((size_t)ty * K + tx) * Ci + ci) * Co + n]; };
-    if (int rc = plan_layer(ctx, L, getw, b->data)) return rc;
+    if (int rc = L.wide_G ? plan_layer_wide(ctx, L, getw, b->data) : plan_layer(ctx, L, getw, b->data)) return rc;
   }
   const char* brs[2] = {"rotation", "translation"};
   {
