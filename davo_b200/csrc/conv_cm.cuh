@@ -7,8 +7,8 @@
 //                        layers with 256 have two m-blocks, each its own tile)
 //   * N (TMEM columns) = NPIX output pixels = a (NPIX/8 rows) x 8 (cols) block of one frame pair
 //   * K                = filter taps x 32-channel slabs, 4 MMAs of K=8 per tap
-// Measured on B200 (tools/experiments/mma_rate.cu): one tcgen05.mma M<=128,K=8 costs
-// max(85.4, N/2) cycles whatever M is, so only N=256 runs the tensor pipe at full rate.
+// Measured on B200 (tools/experiments/mma_floor.cu): one tcgen05.mma M=128,K=8 costs
+// max(53.8, N/2) cycles, so N >= 128 runs the tensor pipe at full rate.
 // Putting PIXELS on N makes every layer an N=256 problem, whatever its channel count; and a
 // thread of the epilogue then owns one output CHANNEL, so each store instruction of a warp
 // writes 32 consecutive channels of one pixel (a whole 128-B line of the NHWC tensor) straight
@@ -100,7 +100,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   constexpr int kTmemCols = 2 * NPIX;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // known warp-uniform to the compiler
   const int lane = threadIdx.x & 31;
 #ifdef DAVO_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -163,9 +163,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer --
-    if (lane == 0) {
+    // All 32 lanes run the loops (operands stay on the uniform datapath); one elected lane issues.
+    {
       constexpr uint32_t idesc = umma_idesc_tf32(kBlockM, NPIX);
-      const uint32_t sbo = (uint32_t)p.patch_w * kSlabBytes;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t w_hi = umma_desc_hi(1024), x_hi = umma_desc_hi((uint32_t)p.patch_w * kSlabBytes);
+      const uint32_t p_lo0 = umma_desc_lo(smem_u32(smem_p)), p_lo_step = (uint32_t)p.patch_stage_bytes >> 4;
+      const uint32_t w_lo0 = umma_desc_lo(smem_u32(smem_w));
       int ps = 0, ws = 0;
       uint32_t pphase = 0, wphase = 0;
       int it = 0;
@@ -174,31 +178,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const uint32_t acc_phase = (it >> 1) & 1;
         TWAIT(4, mbar_wait(&acc_empty[acc], acc_phase ^ 1));
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * NPIX;
-        uint32_t accumulate = 0;
+        const uint32_t d = tmem_u + acc * NPIX;
+        int ti = 0;
         for (int pi = 0; pi < p.n_patches; ++pi) {
-          const PatchDesc pd = p.patches[pi];
+          const int nt = p.patches[pi].ntaps;
           TWAIT(2, mbar_wait(&p_full[ps], pphase));
-          tc_fence_after();
-          const uint32_t pbase = smem_u32(smem_p + ps * p.patch_stage_bytes);
-          for (int t = 0; t < pd.ntaps; ++t) {
-            const TapDesc td = p.taps[pd.tap0 + t];
+          DAVO_MMA_FENCE();
+          const uint32_t pa = p_lo0 + (uint32_t)ps * p_lo_step;
+          for (int t = 0; t < nt; ++t, ++ti) {
+            const uint32_t x_lo = pa + (uint32_t)p.taps[ti].a_off * (kSlabBytes / 16);
             TWAIT(3, mbar_wait(&w_full[ws], wphase));
-            tc_fence_after();
-            const uint64_t dw = umma_desc(smem_u32(smem_w + ws * kWBytes), 1024);
-            const uint64_t dx = umma_desc(pbase + (uint32_t)td.a_off * kSlabBytes, sbo);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 8 tf32 = 32 B): +2 in the >>4 address field
-              tc_mma_tf32(d, dw + 2 * kk, dx + 2 * kk, idesc, accumulate);
-              accumulate = 1;
+            DAVO_MMA_FENCE();
+            if (elect_one()) {
+              tc_mma_tf32_slab(d, w_lo0 + (uint32_t)ws * (kWBytes / 16), w_hi, x_lo, x_hi, idesc, ti != 0);
+              tc_commit(&w_empty[ws]);        // frees the weight slot when these MMAs retire
             }
-            tc_commit(&w_empty[ws]);          // frees the weight slot when these MMAs retire
             if (++ws == WS) { ws = 0; wphase ^= 1; }
           }
-          tc_commit(&p_empty[ps]);            // frees the patch slot
+          if (elect_one()) tc_commit(&p_empty[ps]);       // frees the patch slot
           if (++ps == PS) { ps = 0; pphase ^= 1; }
         }
-        tc_commit(&acc_full[acc]);            // accumulator complete -> epilogue
+        if (elect_one()) tc_commit(&acc_full[acc]);       // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {

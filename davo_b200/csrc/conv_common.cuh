@@ -37,6 +37,15 @@ struct TapDesc {
 
 enum { EPI_STORE_RELU = 0, EPI_SUM_RELU = 1 };
 
+// Ordering of the tensor-core reads after a TMA-fed mbarrier wait.  The wait itself orders the
+// async-proxy writes of TMA before what the waiting thread issues next; -DDAVO_MMA_FENCES=1
+// adds the explicit tcgen05.fence for A/B comparison.
+#if defined(DAVO_MMA_FENCES) && DAVO_MMA_FENCES
+#define DAVO_MMA_FENCE() tc_fence_after()
+#else
+#define DAVO_MMA_FENCE() do { } while (0)
+#endif
+
 // Shared-memory matrix descriptor (K-major, SWIZZLE_128B): rows 128 B apart, 8-row groups
 // `sbo_bytes` apart.  A window of a patch is start = patch + (row*Wp + col)*128, SBO = Wp*128:
 // the hardware swizzle is a function of the absolute shared-memory address, so a row-shifted

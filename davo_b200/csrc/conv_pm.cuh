@@ -110,7 +110,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarrierBytes);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bias_s) + kBiasSmemBytes;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // known warp-uniform to the compiler
   const int lane = threadIdx.x & 31;
 #ifdef DAVO_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -193,9 +193,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer --
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(kTileM, BN);
-      const uint32_t sbo = WIDE ? 1024u : (uint32_t)p.patch_w * kSlabBytes;
+    // All 32 lanes run the loops (operands stay on the uniform datapath); one elected lane issues.
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a_hi = umma_desc_hi(WIDE ? 1024u : (uint32_t)p.patch_w * kSlabBytes);
+      const uint32_t b_hi = umma_desc_hi(1024);
+      const uint32_t p_lo0 = umma_desc_lo(smem_u32(smem_p)), p_lo_step = (uint32_t)p.patch_stage_bytes >> 4;
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(smem_b));
       int ps = 0, bs = 0;
       uint32_t pphase = 0, bphase = 0;
       int it = 0;
@@ -206,53 +210,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const int g = (tile % tiles_per_pair) / tiles_per_img;
         TWAIT(4, mbar_wait(&acc_empty[acc], acc_phase ^ 1));
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * Cfg::kAccStride;
-        uint32_t first = 0;
+        const uint32_t d = tmem_u + acc * Cfg::kAccStride;
+        int ti = 0;
         for (int pi = 0; pi < p.n_patches; ++pi) {
-          const PatchDesc pd = p.patches[pi];
+          const int nt = p.patches[pi].ntaps;
           TWAIT(2, mbar_wait(&p_full[ps], pphase));
-          tc_fence_after();
-          const uint32_t pbase = smem_u32(smem_p + ps * p.patch_stage_bytes);
-          for (int t = 0; t < pd.ntaps; ++t) {
-            const TapDesc td = p.taps[pd.tap0 + t];
+          DAVO_MMA_FENCE();
+          const uint32_t pa = p_lo0 + (uint32_t)ps * p_lo_step;
+          for (int t = 0; t < nt; ++t, ++ti) {
+            const TapDesc td = p.taps[ti];
+            const uint32_t a_lo = pa + (uint32_t)td.a_off * (kSlabBytes / 16);
+            uint32_t b_lo, dd = d, id = umma_idesc_tf32(kTileM, BN), acc_first = ti != 0;
             if constexpr (WIDE) {
-              const uint32_t baddr = smem_u32(smem_b) + ((uint32_t)td.b_idx * p.b_box_rows + td.brow8 * 8u) * kSlabBytes;
-              const uint64_t da = umma_desc(pbase + (uint32_t)td.a_off * kSlabBytes, sbo);
-              const uint64_t db = umma_desc(baddr, 1024);
-              const uint32_t id = umma_idesc_tf32(kTileM, 0) | ((uint32_t)td.n16 << 18);   // N>>3 at bit 17
-              const uint32_t dw = d + td.dcol16 * 16u;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                tc_mma_tf32(dw, da + 2 * kk, db + 2 * kk, id, (kk == 0 && td.fresh) ? 0u : 1u);
-              continue;
-            }
-            uint32_t baddr;
-            if constexpr (B_RESIDENT) {
-              baddr = smem_u32(smem_b + (g * p.n_taps + td.b_idx) * Cfg::kBBytes);
+              b_lo = b_lo0 + ((uint32_t)td.b_idx * p.b_box_rows + td.brow8 * 8u) * (kSlabBytes / 16);
+              dd = d + td.dcol16 * 16u;
+              id = umma_idesc_tf32(kTileM, 0) | ((uint32_t)td.n16 << 18);     // N >> 3 sits at bit 17
+              acc_first = td.fresh ^ 1u;
+            } else if constexpr (B_RESIDENT) {
+              b_lo = b_lo0 + (uint32_t)td.b_idx * (Cfg::kBBytes / 16);        // resident: groups == 1
             } else {
               TWAIT(3, mbar_wait(&b_full[bs], bphase));
-              tc_fence_after();
-              baddr = smem_u32(smem_b + bs * Cfg::kBBytes);
+              DAVO_MMA_FENCE();
+              b_lo = b_lo0 + (uint32_t)bs * (Cfg::kBBytes / 16);
             }
-            const uint64_t da = umma_desc(pbase + (uint32_t)td.a_off * kSlabBytes, sbo);
-            const uint64_t db = umma_desc(baddr, 1024);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {   // 4 x (K = 8 tf32 = 32 B): +2 in the >>4 address field
-              tc_mma_tf32(d, da + 2 * kk, db + 2 * kk, idesc, first);
-              first = 1;
-            }
+            if (elect_one()) tc_mma_tf32_slab(dd, a_lo, a_hi, b_lo, b_hi, id, acc_first);
             if constexpr (!B_RESIDENT) {
-              tc_commit(&b_empty[bs]);        // frees the weight slot when these MMAs retire
+              if (elect_one()) tc_commit(&b_empty[bs]);   // frees the weight slot when these MMAs retire
               if (++bs == BS) { bs = 0; bphase ^= 1; }
             }
           }
-          tc_commit(&p_empty[ps]);            // frees the patch slot
+          if (elect_one()) tc_commit(&p_empty[ps]);       // frees the patch slot
           if (++ps == PS) { ps = 0; pphase ^= 1; }
         }
-        tc_commit(&acc_full[acc]);            // accumulator complete -> epilogue
+        if (elect_one()) tc_commit(&acc_full[acc]);       // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {

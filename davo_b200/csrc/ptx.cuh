@@ -102,6 +102,46 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One 128-B K slab = four K=8 steps.  The issuing thread's own instruction stream is what
+// bounds small-N layers (tools/experiments/mma_floor.cu: 53.8 cycles per MMA at N <= 64, 64 at
+// N = 128 when the thread does nothing else), so descriptors arrive as precomputed 32-bit
+// halves: lo = (smem address >> 4) | LBO, hi = SBO | version | swizzle mode; a K step adds 2 to lo.
+__device__ __forceinline__ void tc_mma_tf32_slab(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                                 uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                 uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 a1, b1;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "add.u32 a1, %1, 2;\n\tadd.u32 b1, %3, 2;\n\t"
+      "mov.b64 da, {a1, %2};\n\tmov.b64 db, {b1, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t"
+      "add.u32 a1, %1, 4;\n\tadd.u32 b1, %3, 4;\n\t"
+      "mov.b64 da, {a1, %2};\n\tmov.b64 db, {b1, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t"
+      "add.u32 a1, %1, 6;\n\tadd.u32 b1, %3, 6;\n\t"
+      "mov.b64 da, {a1, %2};\n\tmov.b64 db, {b1, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, 1;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+// One lane of a converged warp.  The MMA warp runs its loops with all 32 lanes so that every
+// operand of tcgen05.mma / tcgen05.commit is computed on the uniform datapath; issuing from
+// inside `if (lane == 0)` makes the compiler move each operand into uniform registers with an
+// ELECT + R2UR sequence per instruction (seen in SASS: ~17 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// Halves of a K-major SWIZZLE_128B shared-memory descriptor (see umma_desc_sw128 below).
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+  return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

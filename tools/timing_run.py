@@ -19,7 +19,7 @@ from davo_b200 import _capi, synthetic as S
 _capi.SYMBOLS = _capi.SYMBOLS
 from davo_b200.davo import DAVO
 ver = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh"
-Bn = 17
+Bn = int(sys.argv[-1]) if sys.argv[-1].isdigit() else 17
 inputs = [torch.as_tensor(x).cuda() for x in S.make_inputs(Bn, 128, 416)]
 system = DAVO(version=ver)
 system.setup_inference(128, 416, "davo", 3, Bn, inputs[0], input_flow=inputs[1], input_seglabel=inputs[2], device=0)
