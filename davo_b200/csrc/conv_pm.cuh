@@ -51,7 +51,7 @@ namespace pm {
 
 constexpr int kTileM = 128;
 constexpr int kTileH = 16;
-constexpr int kEpiStageBytes = 4 * 4096;            // 4 epilogue warps x (32 pixels x 128 B)
+constexpr int kEpiStageBytes = 4 * 2 * 4096;        // 4 epilogue warps x 2 buffers x (32 pixels x 128 B)
 constexpr int kBiasSmemBytes = 2048;                // up to 512 bias floats
 
 struct ConvParams {
@@ -86,7 +86,7 @@ struct ConvCfg {
 template <int BN, int EPI, bool B_RESIDENT, bool WIDE = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ ConvParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands: keep every stage base 1024-B aligned.
@@ -99,7 +99,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int TH = WIDE ? p.tile_h : kTileH, TW = WIDE ? p.tile_w : kTileW;
   uint8_t* smem_p = smem;
   uint8_t* smem_b = smem + PS * p.patch_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + b_bytes);
+  uint8_t* epi_stage = smem_b + b_bytes;                           // 1024-B aligned (TMA store, 128-B swizzle)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageBytes);
   uint64_t* p_full = bars;                        // [kMaxStages] TMA -> MMA
   uint64_t* p_empty = bars + kMaxStages;          // [kMaxStages] MMA -> TMA
   uint64_t* b_full = bars + 2 * kMaxStages;       // [kMaxStages] (resident: [0] only)
@@ -108,7 +109,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_empty = acc_full + 2;             // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarrierBytes);
-  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bias_s) + kBiasSmemBytes;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // known warp-uniform to the compiler
   const int lane = threadIdx.x & 31;
@@ -120,6 +120,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (EPI == EPI_STORE_RELU) tma_prefetch_desc(&tmO);
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&p_full[i], 1);
       mbar_init(&p_empty[i], 1);
@@ -253,6 +254,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;            // accumulator row = pixel within the tile
     int it = 0;
+    uint32_t epi_step = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -270,24 +272,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long t_busy0 = clock64();
 #endif
       const uint32_t t0 = tmem_base + acc * Cfg::kAccStride + (uint32_t(q * 32) << 16);
-      if constexpr (EPI == EPI_STORE_RELU) {
-        // 32 pixels x CH channels per step: registers -> swizzled smem (row = pixel) -> each
-        // global store instruction writes PPS pixels x (CH*4)-byte runs (whole lines at CH=32).
-        constexpr int CH = BN >= 32 ? 32 : 16;
+      if constexpr (EPI == EPI_STORE_RELU && BN >= 32) {
+        // 32 M rows x 32 accumulator columns per step: registers -> bias/ReLU/round -> this warp's
+        // staging buffer (row = M row, 128 B, 16-B chunks XOR-swizzled by row & 7 = the tensor
+        // map's 128-B swizzle) -> one TMA store of the box {32 floats, tile_w, 32/tile_w rows}.
+        // TMA clips what lies outside the image.  Two buffers per warp: the store of step i
+        // drains while step i+1 is computed.
+        const uint32_t stg0 = smem_u32(epi_stage) + q * 8192;
+        const uint32_t bias_a = smem_u32(bias_s) + g * BN * 4;
+        const int c_w = (r % p.tiles_w) * TW;
+        const int c_h = (r / p.tiles_w) * TH + q * (32 / TW);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          TWAIT(3, { tmem_ld_32x32(t0 + c0, v); tmem_ld_wait(); });
+          const uint32_t stg = stg0 + ((epi_step & 1) << 12);
+          if (lane == 0) tma_store_wait_read<1>();      // the store that last read this buffer is done
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = lds_v4(bias_a + (c0 + 4 * j) * 4);
+            float4 o;
+            o.x = round_tf32_finite(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f));
+            o.y = round_tf32_finite(fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f));
+            o.z = round_tf32_finite(fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f));
+            o.w = round_tf32_finite(fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f));
+            sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), o);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmO, reinterpret_cast<const void*>(epi_stage + q * 8192 + ((epi_step & 1) << 12)),
+                         (WIDE ? 0 : g * BN) + c0, c_w, c_h, n);
+            tma_store_commit();
+          }
+          ++epi_step;
+        }
+      } else if constexpr (EPI == EPI_STORE_RELU) {
+        // BN = 16 (cnv1 when the widened plan does not apply): 32 pixels x 16 channels per step
+        // through a swizzled staging buffer, then stores of whole 64-B runs.
+        constexpr int CH = 16;
         constexpr int LPP = CH / 4;                 // lanes (float4) per pixel
         constexpr int PPS = 32 / LPP;               // pixels per store instruction
         constexpr int RB = CH * 4;                  // row bytes in the staging buffer
-        uint8_t* stg = epi_stage + q * 4096;
+        uint8_t* stg = epi_stage + q * 8192;
         const int sub = lane / LPP, cq = lane % LPP;
         const int th0 = (r / p.tiles_w) * kTileH + q * 4, tw0 = (r % p.tiles_w) * kTileW;
         float* const obase = p.out + (size_t)n * p.Hout * p.Wout * p.out_stride + g * BN + cq * 4;
-        const int wide_h0 = (r / p.tiles_w) * TH, wide_w0 = (r % p.tiles_w) * TW;
-        const int wide_runs = WIDE ? p.Wout / p.run_px : 0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
           uint32_t v[CH];
-          TWAIT(3, { if constexpr (CH == 32) tmem_ld_32x32(t0 + c0, v); else tmem_ld_32x16(t0 + c0, v);
-                     tmem_ld_wait(); });
+          TWAIT(3, { tmem_ld_32x16(t0 + c0, v); tmem_ld_wait(); });
           __syncwarp();                             // the previous step's reads are done
 #pragma unroll
           for (int j = 0; j < LPP; ++j) {
@@ -303,17 +338,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int s2 = 0; s2 < 32 / PPS; ++s2) {
             const int rr = s2 * PPS + sub;          // pixel row within this warp's 32
             const float4 o = *reinterpret_cast<const float4*>(stg + rr * RB + ((cq ^ (rr & (LPP - 1))) << 4));
-            if constexpr (WIDE) {
-              // M row = run of run_px pixels x Cout channels = BN consecutive floats of the output
-              const int mm = q * 32 + rr;
-              const int hh = wide_h0 + mm / TW, run = wide_w0 + mm % TW;
-              if (hh < p.Hout && run < wide_runs)
-                *reinterpret_cast<float4*>(obase + ((size_t)hh * p.Wout + (size_t)run * p.run_px) * p.out_stride + c0) = o;
-            } else {
-              const int hh = th0 + (rr >> 3), ww = tw0 + (rr & 7);
-              if (hh < p.Hout && ww < p.Wout)
-                *reinterpret_cast<float4*>(obase + ((size_t)hh * p.Wout + ww) * p.out_stride + c0) = o;
-            }
+            const int hh = th0 + (rr >> 3), ww = tw0 + (rr & 7);
+            if (hh < p.Hout && ww < p.Wout)
+              *reinterpret_cast<float4*>(obase + ((size_t)hh * p.Wout + ww) * p.out_stride + c0) = o;
           }
         }
       } else {
@@ -351,6 +378,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef DAVO_TIMING
       tacc[6] += clock64() - t_busy0;
 #endif
+    }
+    if constexpr (EPI == EPI_STORE_RELU && BN >= 32) {
+      if (lane == 0) tma_store_wait_read<0>();          // shared memory must outlive the last stores
     }
   }
 #ifdef DAVO_TIMING

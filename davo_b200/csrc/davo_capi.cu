@@ -98,6 +98,7 @@ struct Layer {
   bool lo_alias = false;       // cnv1: packed channels 10-15 are TF32 residuals of 0-2, 5-7
   int smem_bytes = 0;
   CUtensorMap tmA, tmB;          // activation (patch) map, weight map
+  CUtensorMap tmO;               // pm store epilogue: output tiles (TMA store)
   pm::ConvParams prm_pm;
   cm::ConvParams prm_cm;
 };
@@ -280,6 +281,24 @@ std::vector<float> round_weights_tf32(const Layer& L, GetW getw, bool compensate
         for (int t = 0; t < T; ++t) at(g, t, ci, n) = flip[t] ? w1[t] : w0[t];
       }
   return out;
+}
+
+// Output map of the pixels-on-M store epilogue: one box = 32 floats x tile_w units x (32 / tile_w)
+// rows, where a unit is an output pixel (inner = all its channels) or, for the column-widened
+// layers, a run of G pixels (inner = G * Cout floats).
+int encode_output_map(davo_ctx* ctx, Layer& L, int inner, int units_w, int tile_w) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)units_w, (cuuint64_t)L.Hout, (cuuint64_t)ctx->mb};
+  const cuuint64_t strides[3] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * units_w * 4,
+                                 (cuuint64_t)inner * units_w * L.Hout * 4};
+  const cuuint32_t box[4] = {32, (cuuint32_t)tile_w, (cuuint32_t)(32 / tile_w), 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(&L.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, L.d_out, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(output) -> %d", L.name, (int)r);
+  return 0;
 }
 
 // ---------------------------------------------------------------- layer plan --
@@ -503,6 +522,9 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(weights) -> %d", L.name, (int)r);
   }
+  L.tmO = L.tmA;
+  if (L.orient == 0 && L.epi == EPI_STORE_RELU && L.BN >= 32)
+    if (int rc = encode_output_map(ctx, L, L.out_stride, L.Wout, kTileW)) return rc;
   if (getenv("DAVO_B200_VERBOSE"))
     fprintf(stderr, "[davo_b200] %s: %s, tile %dx8 px, %d m-block(s), patch %dx%d (%d B) x%d, %d taps, weights %s, rings P%d W%d, smem %d\n",
             L.name, L.orient == 0 ? "pixels-on-M" : "channels-on-M", TR, MB, Hp, Wp, patch_bytes, np, nt,
@@ -654,6 +676,7 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(weights) -> %d", L.name, (int)r);
   }
+  if (int rc = encode_output_map(ctx, L, NW, L.Wout / G, TWc)) return rc;
   if (getenv("DAVO_B200_VERBOSE"))
     fprintf(stderr, "[davo_b200] %s: pixels-on-M widened x%d (N=%d), tile %dx%d runs, patch %dx%d (%d B) x%d, %d taps, weights resident %d B, ring P%d, smem %d\n",
             L.name, G, NW, THr, TWc, Hp, Wp, patch_bytes, np, nt, resident_bytes, P.p_stages, L.smem_bytes);
@@ -673,7 +696,7 @@ int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
-  pm::conv_tc_kernel<BN, EPI, RES><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
+  pm::conv_tc_kernel<BN, EPI, RES><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, L.tmO, P);
   CU_OK(cudaGetLastError());
   return 0;
 }
@@ -689,7 +712,7 @@ int launch_pm_wide(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   P.num_tiles = npairs * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
-  kern<<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
+  kern<<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, L.tmO, P);
   CU_OK(cudaGetLastError());
   return 0;
 }
