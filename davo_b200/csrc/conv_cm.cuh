@@ -41,6 +41,12 @@ namespace davo {
 namespace cm {
 
 constexpr int kBlockM = 128;                        // output channels per tile
+// 11 warps: 0 patch producer, 1 MMA, 6 weight producer, 2-5 and 7-10 epilogue.  A warp may only
+// read the TMEM lane quadrant (warp % 4), so the two warps of a quadrant take alternate 32-pixel
+// column blocks: the epilogue is bound by one warp's instruction issue, and cnv4's main loop
+// (18 taps) is no longer than its epilogue.
+constexpr int kThreads = 352;
+constexpr int kEpiWarps = 8;
 constexpr int kWBytes = kBlockM * kSlabBytes;       // one weight stage: 16 KB
 
 struct ConvParams {
@@ -79,10 +85,12 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
   return c;
 }
 
-template <int NPIX, int EPI>
-__global__ void __launch_bounds__(kConvThreads, 1)
+// STAGED: the store epilogue goes through shared memory and TMA tile stores (one 4-KB buffer per
+// epilogue warp behind the barriers) instead of 32 scalar stores per 32x32 block.
+template <int NPIX, int EPI, bool STAGED = false>
+__global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-               const __grid_constant__ ConvParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands: keep every stage base 1024-B aligned.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -90,7 +98,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int PS = p.p_stages, WS = p.w_stages;
   uint8_t* smem_p = smem;
   uint8_t* smem_w = smem + PS * p.patch_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + WS * kWBytes);
+  uint8_t* epi_stage = smem_w + WS * kWBytes;                      // 1024-B aligned; STAGED only
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + (STAGED ? kEpiWarps * 4096 : 0));
   uint64_t* p_full = bars;                        // [kMaxStages] TMA -> MMA
   uint64_t* p_empty = bars + kMaxStages;          // [kMaxStages] MMA -> TMA
   uint64_t* w_full = bars + 2 * kMaxStages;
@@ -110,6 +119,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
+    if constexpr (STAGED) tma_prefetch_desc(&tmO);
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&p_full[i], 1);
       mbar_init(&p_empty[i], 1);
@@ -118,7 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], EPI == EPI_STORE_RELU ? kEpiWarps : 4);
     }
     fence_mbar_init();
   }
@@ -202,9 +212,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         __syncwarp();
       }
     }
-  } else {
+  } else if (EPI == EPI_STORE_RELU || warp < 6) {
     // ----------------------------------------------------------- epilogue --
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = warp > 6 ? 1 : 0;      // which of the quadrant's two warps (store epilogue)
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -224,9 +235,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         // lane = channel: one store instruction writes 32 consecutive channels of one pixel
         const size_t pix_stride = p.out_stride;
         float* const obase = p.out + ((size_t)tc.n * p.Hout * p.Wout) * pix_stride + tc.g * p.cout_g + co;
-        if (warp_has_work) {
+        if constexpr (STAGED) {
+          // lane = channel, registers = 32 pixels (4 tile rows x 8 cols): transposed into this
+          // warp's buffer as [pixel][32 channels] (128-B rows, 16-B chunks XOR-swizzled by
+          // pixel & 7 = the tensor map's swizzle; a warp's 32 scalar stores hit 32 banks), then
+          // one TMA store of the box {32 channels, 8 cols, 4 rows}; TMA clips outside the image.
+          const uint32_t stg = smem_u32(epi_stage) + (half * 4 + q) * 4096;
+          uint32_t lane_off[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) lane_off[k] = ((((uint32_t)lane >> 2) ^ k) << 4) | ((lane & 3) << 2);
+          if (warp_has_work) {
 #pragma unroll 1
-          for (int n0 = 0; n0 < NPIX; n0 += 32) {             // 4 tile rows x 8 cols per step
+            for (int n0 = half * 32; n0 < NPIX; n0 += 64) {
+              uint32_t v[32];
+              tmem_ld_32x32(t0 + n0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                v[j] = __float_as_uint(round_tf32_finite(fmaxf(__uint_as_float(v[j]) + bias, 0.f)));
+              if (lane == 0) tma_store_wait_read<0>();    // the previous store has read the buffer
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + j * 128 + lane_off[j & 7]), "r"(v[j]) : "memory");
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmO, reinterpret_cast<const void*>(epi_stage + (half * 4 + q) * 4096),
+                             tc.g * p.cout_g + tc.mb * kBlockM + q * 32, tc.w0, tc.h0 + (n0 >> 3), tc.n);
+                tma_store_commit();
+              }
+            }
+          }
+        } else if (warp_has_work) {
+#pragma unroll 1
+          for (int n0 = half * 32; n0 < NPIX; n0 += 64) {     // 4 tile rows x 8 cols per step
             uint32_t v[32];
             tmem_ld_32x32(t0 + n0, v);
             tmem_ld_wait();
@@ -269,6 +312,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #ifdef DAVO_TIMING
       tacc[6] += clock64() - t_busy0;
 #endif
+    }
+    if constexpr (STAGED) {
+      if (lane == 0) tma_store_wait_read<0>();            // shared memory must outlive the last stores
     }
   }
 #ifdef DAVO_TIMING

@@ -92,6 +92,7 @@ struct Layer {
   int orient = 0;              // 0: pixels on the MMA M axis (conv_pm), 1: channels on M (conv_cm)
   int npix = 128;              // output pixels per tile: 128 = 16x8 (pm, or cm on short maps), 256 = 32x8
   int m_blocks = 1;            // cm: 128-channel blocks per group
+  bool cm_staged = false;      // cm: store epilogue through shared memory + TMA tile stores
   bool b_resident = false;     // pm: all weight slabs stay in shared memory
   int wide_G = 0;              // pm, column-widened: output pixels per M row (0 = off)
   int wide_tw = 0;             //   runs per tile row (tile = 128/wide_tw rows x wide_tw runs)
@@ -482,7 +483,10 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     P.bias = L.d_bias;
     memcpy(P.patches, pdesc, sizeof pdesc);
     memcpy(P.taps, tdesc, sizeof tdesc);
-    const int fixed = 1024 /*alignment*/ + kBarrierBytes;
+    // Short main loops (cnv4: 18 taps) are epilogue-bound with direct stores: stage them.
+    const char* stg_env = getenv("DAVO_B200_CM_STAGED");     // debug: "0" / "1" for every cm layer
+    L.cm_staged = L.epi == EPI_STORE_RELU && (stg_env ? !strcmp(stg_env, "1") : nt <= 18);
+    const int fixed = 1024 /*alignment*/ + kBarrierBytes + (L.cm_staged ? cm::kEpiWarps * 4096 : 0);
     const int avail = kSmemBudget - fixed;
     P.p_stages = patch_stage <= 40 * 1024 ? 3 : 2;
     if (P.p_stages == 3 && (avail - 3 * patch_stage) / cm::kWBytes < 4) P.p_stages = 2;
@@ -523,7 +527,7 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(weights) -> %d", L.name, (int)r);
   }
   L.tmO = L.tmA;
-  if (L.orient == 0 && L.epi == EPI_STORE_RELU && L.BN >= 32)
+  if ((L.orient == 1 && L.cm_staged) || (L.orient == 0 && L.epi == EPI_STORE_RELU && L.BN >= 32))
     if (int rc = encode_output_map(ctx, L, L.out_stride, L.Wout, kTileW)) return rc;
   if (getenv("DAVO_B200_VERBOSE"))
     fprintf(stderr, "[davo_b200] %s: %s, tile %dx8 px, %d m-block(s), patch %dx%d (%d B) x%d, %d taps, weights %s, rings P%d W%d, smem %d\n",
@@ -723,11 +727,11 @@ int launch_pm_r(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
                       : launch_pm_t<BN, EPI, false>(ctx, L, npairs, st);
 }
 
-template <int NPIX, int EPI>
+template <int NPIX, int EPI, bool STAGED = false>
 int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   static int attr_smem = 0;
   if (attr_smem < L.smem_bytes) {
-    CU_OK(cudaFuncSetAttribute(cm::conv_tc_kernel<NPIX, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU_OK(cudaFuncSetAttribute(cm::conv_tc_kernel<NPIX, EPI, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                L.smem_bytes));
     attr_smem = L.smem_bytes;
   }
@@ -736,7 +740,7 @@ int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
-  cm::conv_tc_kernel<NPIX, EPI><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, P);
+  cm::conv_tc_kernel<NPIX, EPI, STAGED><<<grid, cm::kThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, L.tmO, P);
   CU_OK(cudaGetLastError());
   return 0;
 }
@@ -746,6 +750,9 @@ int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
     if (L.epi == EPI_SUM_RELU)
       return L.npix == 256 ? launch_cm_t<256, EPI_SUM_RELU>(ctx, L, npairs, st)
                            : launch_cm_t<128, EPI_SUM_RELU>(ctx, L, npairs, st);
+    if (L.cm_staged)
+      return L.npix == 256 ? launch_cm_t<256, EPI_STORE_RELU, true>(ctx, L, npairs, st)
+                           : launch_cm_t<128, EPI_STORE_RELU, true>(ctx, L, npairs, st);
     return L.npix == 256 ? launch_cm_t<256, EPI_STORE_RELU>(ctx, L, npairs, st)
                          : launch_cm_t<128, EPI_STORE_RELU>(ctx, L, npairs, st);
   }
