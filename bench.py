@@ -47,6 +47,23 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "of fallback"
 
 
+def ncu_traffic(layer):
+    """DRAM bytes (read + write) per launch of `layer`'s kernel from the newest committed
+    `ncu --set full` capture (profiles/r*_ncu_traffic.json), or None.  Not measured by this run."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    e = d.get("layers", {}).get(layer)
+    if not e:
+        return None, None
+    return e["dram_bytes_read"] + e["dram_bytes_write"], {
+        "file": os.path.relpath(files[-1], ROOT), "pairs_per_launch": e.get("pairs_per_launch"),
+        "tensor_pipe_pct": e.get("tensor_pipe_pct")}
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
@@ -247,9 +264,19 @@ def run_ours(args):
     achieved = FLOP_PER_PAIR_LAYER[dom] * npairs / (layer_ms[dom] * 1e-3) / 1e12
     conv_ms = sum(v for k, v in layer_ms.items() if k.startswith("cnv"))
     stack_tflops = FLOP_PER_PAIR * npairs / (conv_ms * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic(dom)
+    if traffic is not None and traffic_src["pairs_per_launch"] not in (None, npairs):
+        traffic = traffic * npairs / traffic_src["pairs_per_launch"]      # same kernel, other pass size
     roofline = {
         "bound": "tensor", "kernel": "conv_tc_kernel<%s>" % dom, "achieved": achieved,
-        "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": None,
+        "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": traffic,
+        "traffic_note": None if traffic is None else
+        "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture %s "
+        "(tensor pipe active %.1f %%); algorithmic in+out bytes of this launch: %d" % (
+            traffic_src["file"], traffic_src["tensor_pipe_pct"] or 0.0,
+            npairs * {"cnv4": 851968 + 1703936, "cnv5": 1703936 + 3407872, "cnv6": 2 * 3407872,
+                      "cnv7": 3407872}.get(dom, 0)),
+        "flop_per_launch": FLOP_PER_PAIR_LAYER[dom] * npairs, "launch_ms": layer_ms[dom],
         "peak_note": "TF32 dense = max(MEASURED_PEAKS bf16_tflops (burst) / 2 = %.1f %s, live cuBLAS TF32 8192^3 GEMM = %.1f)"
                      % (peaks["bf16_tflops"] / 2.0, peak_kind, live_tf32),
         "pairs_per_launch": npairs, "layer_ms": layer_ms,
