@@ -125,6 +125,21 @@ def test_compensated_weight_rounding_removes_the_systematic_offset(monkeypatch):
     assert bias["compensated"].max() < 2e-7, bias
 
 
+@pytest.mark.parametrize("size", [(256, 832, 2), (64, 208, 3), (128, 400, 2), (136, 424, 1)])
+def test_other_input_sizes(size):
+    """BASELINE configs[4] runs 256x832; 128x400 leaves a partial run of the widened cnv1 plan at the
+    right border; 136x424 is not a multiple of 16, so cnv1/cnv2 fall back to the plain plan."""
+    _need_gpu()
+    h, w_, b = size
+    w = S.init_weights(HEADLINE, random_bias=True)
+    inputs = S.make_inputs(b, h, w_, seed=11, bad_label_frac=0.01)
+    sysm = DAVO(version=HEADLINE)
+    d = [torch.as_tensor(x).cuda() for x in inputs]
+    sysm.setup_inference(h, w_, "davo", 3, b, d[0], input_flow=d[1], input_seglabel=d[2], device=0)
+    sysm.load_weights(w)
+    _assert_pose(sysm.inference(None, "pose")["pose"], O.davo_forward(HEADLINE, *inputs, w, torch.float64))
+
+
 def test_tensor_core_path_agrees_with_direct_fp32_conv_on_gpu():
     _need_gpu()
     w = S.init_weights(HEADLINE, random_bias=True)
