@@ -253,7 +253,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     # dominant kernel (cnv6) timed alone, live, with CUDA events on the launch stream
-    step()                                    # profile the device-resident configuration
+    system.inference(None, "pose", as_torch=True)   # rank-local (no collective): rebinds the device-resident inputs
     torch.cuda.synchronize()
     layer_ms, npairs = system.profile_layers(iters=20)
     dom = max((k for k in layer_ms if k.startswith("cnv")), key=lambda k: layer_ms[k])

@@ -18,7 +18,8 @@ SYMBOLS = (
     "davo_create", "davo_set_weight", "davo_finalize_weights", "davo_forward",
     "davo_forward_host", "davo_get_intermediate", "davo_last_launch_count",
     "davo_last_host_copy_bytes",
-    "davo_profile_layers", "davo_debug_set_conv_impl", "davo_last_error",
+    "davo_profile_layers", "davo_debug_set_conv_impl", "davo_forward_pairs", "davo_forward_host_pairs",
+    "davo_last_error",
     "davo_destroy", "davo_build_info",
 )
 
@@ -58,6 +59,8 @@ def load() -> C.CDLL:
     lib.davo_finalize_weights.argtypes = [vp]
     lib.davo_forward.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp]
     lib.davo_forward_host.argtypes = [vp, ip, vp, vp, vp, vp, vp, vp]
+    lib.davo_forward_pairs.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp]
+    lib.davo_forward_host_pairs.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp]
     lib.davo_get_intermediate.argtypes = [vp, C.c_char_p, ip, vp, C.c_int64, C.POINTER(C.c_int64)]
     lib.davo_last_launch_count.argtypes = [vp]
     lib.davo_last_host_copy_bytes.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
@@ -68,10 +71,13 @@ def load() -> C.CDLL:
     lib.davo_destroy.argtypes = [vp]
     lib.davo_destroy.restype = None
     lib.davo_build_info.restype = C.c_char_p
-    for s in SYMBOLS[:10]:
+    for s in SYMBOLS[:12]:
         getattr(lib, s).restype = ip
     _LIB = lib
     return lib
+
+
+PAIRS = {"all": 0, "trajectory": 1, "trajectory_first": 2}     # include/davo_b200.h DAVO_PAIRS_*
 
 
 def last_error(lib, handle) -> str:

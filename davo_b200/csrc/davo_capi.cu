@@ -134,7 +134,7 @@ struct davo_ctx {
   int last_launches = 0;
   int last_npairs_mb = 0;
   const uint8_t* last_img = nullptr; const float* last_flow = nullptr; const float* last_seg = nullptr;
-  float* last_pose = nullptr; int last_B = 0;
+  float* last_pose = nullptr; int last_B = 0; int last_pairs = 0;
 };
 
 namespace {
@@ -805,12 +805,12 @@ __global__ void sum7_direct_kernel(const float* in, int hw, int nparts, float* o
   for (int i = 1; i < nparts; ++i) o[(size_t)i * 256] = 0.f;
 }
 
-int launch_front(davo_ctx* ctx, int pair0, int npairs, const uint8_t* img, const float* flow,
+int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint8_t* img, const float* flow,
                  const float* seg, cudaStream_t st, int* launches) {
   const davo_config& c = ctx->cfg;
   FrontParams fp;
   memset(&fp, 0, sizeof fp);
-  fp.H = c.H; fp.W = c.W; fp.pair0 = pair0; fp.npairs = npairs;
+  fp.H = c.H; fp.W = c.W; fp.pair0 = pair0; fp.npairs = npairs; fp.pair_mode = pair_mode;
   fp.in_mode = c.in_mode; fp.att_src = c.att_src; fp.att_tgt_ones = c.att_tgt_ones;
   fp.mask_rgb = c.mask_mode != 0;
   fp.mask_flow = c.mask_mode == 2;
@@ -829,10 +829,10 @@ int launch_front(davo_ctx* ctx, int pair0, int npairs, const uint8_t* img, const
   return 0;
 }
 
-int launch_head(davo_ctx* ctx, int pair0, int npairs, float* pose_out, cudaStream_t st, int* launches) {
+int launch_head(davo_ctx* ctx, int pair_mode, int pair0, int npairs, float* pose_out, cudaStream_t st, int* launches) {
   const Layer& L7 = ctx->layers.back();
   HeadParams hp;
-  hp.pair0 = pair0; hp.npairs = npairs; hp.nparts = ctx->nparts7;
+  hp.pair0 = pair0; hp.npairs = npairs; hp.pair_mode = pair_mode; hp.nparts = ctx->nparts7;
   hp.inv_hw = 1.0f / (float)(L7.Hout * L7.Wout);
   hp.sums = ctx->d_sum7; hp.wpred = ctx->d_wpred; hp.bpred = ctx->d_bpred; hp.pose_out = pose_out;
   head_kernel<<<npairs, 256, 0, st>>>(hp);
@@ -841,9 +841,9 @@ int launch_head(davo_ctx* ctx, int pair0, int npairs, float* pose_out, cudaStrea
   return 0;
 }
 
-int run_microbatch(davo_ctx* ctx, int pair0, int npairs, const uint8_t* img, const float* flow,
+int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint8_t* img, const float* flow,
                    const float* seg, float* pose_out, cudaStream_t st, int* launches) {
-  if (int rc = launch_front(ctx, pair0, npairs, img, flow, seg, st, launches)) return rc;
+  if (int rc = launch_front(ctx, pair_mode, pair0, npairs, img, flow, seg, st, launches)) return rc;
   for (Layer& L : ctx->layers) {
     int rc = ctx->conv_impl == 0 ? launch_conv(ctx, L, npairs, st) : launch_conv_direct(ctx, L, npairs, st);
     if (rc) return rc;
@@ -855,7 +855,11 @@ int run_microbatch(davo_ctx* ctx, int pair0, int npairs, const uint8_t* img, con
     CU_OK(cudaGetLastError());
     ++*launches;
   }
-  return launch_head(ctx, pair0, npairs, pose_out, st, launches);
+  return launch_head(ctx, pair_mode, pair0, npairs, pose_out, st, launches);
+}
+
+int pairs_selected(int pairs, int B) {
+  return pairs == DAVO_PAIRS_ALL ? 2 * B : pairs == DAVO_PAIRS_TRAJECTORY ? B : B + 1;
 }
 
 }  // namespace
@@ -1123,8 +1127,15 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
 
 extern "C" int davo_forward(davo_ctx* ctx, int B, const uint8_t* img, const float* flow,
                             const float* seg, const float* depth, float* pose_out, void* stream) {
+  return davo_forward_pairs(ctx, B, DAVO_PAIRS_ALL, img, flow, seg, depth, pose_out, stream);
+}
+
+extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
+                                  const float* seg, const float* depth, float* pose_out, void* stream) {
   (void)depth;
   if (!ctx) return DAVO_ERR_ARG;
+  if (pairs < DAVO_PAIRS_ALL || pairs > DAVO_PAIRS_TRAJECTORY_FIRST)
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward: pair selection %d unknown", pairs);
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1) && !flow))
@@ -1132,16 +1143,18 @@ extern "C" int davo_forward(davo_ctx* ctx, int B, const uint8_t* img, const floa
   CU_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int launches = 0;
-  const int total = 2 * B;
+  const int total = pairs_selected(pairs, B);
   int last_n = 0;
+  if (pairs != DAVO_PAIRS_ALL) CU_OK(cudaMemsetAsync(pose_out, 0, (size_t)B * 12 * sizeof(float), st));
   for (int p0 = 0; p0 < total; p0 += ctx->mb) {
     const int n = (total - p0) < ctx->mb ? (total - p0) : ctx->mb;
-    if (int rc = run_microbatch(ctx, p0, n, img, flow, seg, pose_out, st, &launches)) return rc;
+    if (int rc = run_microbatch(ctx, pairs, p0, n, img, flow, seg, pose_out, st, &launches)) return rc;
     last_n = n;
   }
   ctx->last_launches = launches;
   ctx->last_npairs_mb = last_n;
   ctx->last_img = img; ctx->last_flow = flow; ctx->last_seg = seg; ctx->last_pose = pose_out; ctx->last_B = B;
+  ctx->last_pairs = pairs;
   return 0;
 }
 
@@ -1151,8 +1164,15 @@ extern "C" int davo_forward(davo_ctx* ctx, int B, const uint8_t* img, const floa
 // map is forced to ones, seg[:,0] and seg[:,2] (davo.py:1000-1004).
 extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const float* flow,
                                  const float* seg, const float* depth, float* pose_out, void* stream) {
+  return davo_forward_host_pairs(ctx, B, DAVO_PAIRS_ALL, img, flow, seg, depth, pose_out, stream);
+}
+
+extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
+                                       const float* seg, const float* depth, float* pose_out, void* stream) {
   (void)depth;
   if (!ctx) return DAVO_ERR_ARG;
+  if (pairs < DAVO_PAIRS_ALL || pairs > DAVO_PAIRS_TRAJECTORY_FIRST)
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: pair selection %d unknown", pairs);
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   const davo_config& c = ctx->cfg;
@@ -1188,6 +1208,7 @@ extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const
   const bool seg_tgt = need_seg && !c.att_tgt_ones;
   size_t h2d = 0;
   int launches = 0, last_n = 0, chunk = 0;
+  if (pairs != DAVO_PAIRS_ALL) CU_OK(cudaMemsetAsync(ctx->s_pose, 0, (size_t)B * 12 * sizeof(float), st));
   for (int s0 = 0; s0 < B; s0 += cs, ++chunk) {
     const int ns = std::min(cs, B - s0);
     const int buf = chunk & 1;
@@ -1212,11 +1233,15 @@ extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const
     }
     CU_OK(cudaEventRecord(ctx->ev_copied[buf], cp));
     CU_OK(cudaStreamWaitEvent(st, ctx->ev_copied[buf], 0));
-    if (int rc = run_microbatch(ctx, 0, 2 * ns, ctx->s_img[buf], ctx->s_flow[buf], ctx->s_seg[buf],
-                                ctx->s_pose + (size_t)12 * s0, st, &launches))
-      return rc;
+    // a chunk is a batch of its own: only the first one may hold the first sample's tgt->src0
+    const int chunk_pairs = (pairs == DAVO_PAIRS_TRAJECTORY_FIRST && s0 > 0) ? DAVO_PAIRS_TRAJECTORY : pairs;
+    const int np_chunk = pairs_selected(chunk_pairs, ns);
+    for (int q0 = 0; q0 < np_chunk; q0 += ctx->mb)
+      if (int rc = run_microbatch(ctx, chunk_pairs, q0, std::min(ctx->mb, np_chunk - q0), ctx->s_img[buf],
+                                  ctx->s_flow[buf], ctx->s_seg[buf], ctx->s_pose + (size_t)12 * s0, st, &launches))
+        return rc;
     CU_OK(cudaEventRecord(ctx->ev_consumed[buf], st));
-    last_n = 2 * ns;
+    last_n = np_chunk;
   }
   CU_OK(cudaMemcpyAsync(pose_out, ctx->s_pose, (size_t)12 * 4 * B, cudaMemcpyDeviceToHost, st));
   CU_OK(cudaStreamSynchronize(st));
@@ -1225,7 +1250,8 @@ extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const
   ctx->last_h2d = (long long)h2d;
   ctx->last_d2h = (long long)12 * 4 * B;
   ctx->last_img = ctx->s_img[(chunk - 1) & 1]; ctx->last_flow = ctx->s_flow[(chunk - 1) & 1];
-  ctx->last_seg = ctx->s_seg[(chunk - 1) & 1]; ctx->last_pose = ctx->s_pose; ctx->last_B = last_n / 2;
+  ctx->last_seg = ctx->s_seg[(chunk - 1) & 1]; ctx->last_pose = ctx->s_pose; ctx->last_B = std::min(cs, B - (chunk - 1) * cs);
+  ctx->last_pairs = (pairs == DAVO_PAIRS_TRAJECTORY_FIRST && chunk > 1) ? DAVO_PAIRS_TRAJECTORY : pairs;
   return 0;
 }
 
@@ -1330,12 +1356,12 @@ extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int*
     *ms_dst = ms / iters;
     return 0;
   };
-  if (int rc = timed([&] { return launch_front(ctx, 0, npairs, ctx->last_img, ctx->last_flow, ctx->last_seg, st, &dummy); }, &ms_out[0])) return rc;
+  if (int rc = timed([&] { return launch_front(ctx, 0, 0, npairs, ctx->last_img, ctx->last_flow, ctx->last_seg, st, &dummy); }, &ms_out[0])) return rc;
   for (int i = 0; i < 7; ++i) {
     const Layer& L = ctx->layers[i];
     if (int rc = timed([&] { return launch_conv(ctx, L, npairs, st); }, &ms_out[1 + i])) return rc;
   }
-  if (int rc = timed([&] { return launch_head(ctx, 0, npairs, ctx->last_pose, st, &dummy); }, &ms_out[8])) return rc;
+  if (int rc = timed([&] { return launch_head(ctx, 0, 0, npairs, ctx->last_pose, st, &dummy); }, &ms_out[8])) return rc;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return 0;

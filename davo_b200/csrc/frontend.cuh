@@ -19,9 +19,22 @@ constexpr int kPackedC = 16;     // packed PoseNN input channels (see pack_kerne
 constexpr int kNumClasses = 19;
 constexpr int kPackBlocksPerPair = 104;
 
+// Which frame pairs of a batch are computed (include/davo_b200.h: DAVO_PAIRS_*).  Slot s of the
+// selection maps to (sample b, source k); the pose lands at pose_out[b][k][:].
+//   0 all:              s -> (s >> 1, s & 1)
+//   1 trajectory:       s -> (s, 1)            tgt->src1 only: what test_kitti_pose.py:143-145 composes
+//   2 trajectory+first: 0 -> (0, 0), s -> (s - 1, 1)   plus the first sample's tgt->src0
+__device__ __forceinline__ void pair_of_slot(int mode, int s, int* b, int* k) {
+  if (mode == 0) { *b = s >> 1; *k = s & 1; }
+  else if (mode == 1) { *b = s; *k = 1; }
+  else if (s == 0) { *b = 0; *k = 0; }
+  else { *b = s - 1; *k = 1; }
+}
+
 struct FrontParams {
   int H, W;
-  int pair0;             // first global frame pair of this micro-batch
+  int pair0;             // first selection slot of this pass
+  int pair_mode;         // see pair_of_slot
   int npairs;
   int in_mode;           // 1: flows are concatenated (v1)
   int att_src;           // 0 none, 1 se_flow, 2 static
@@ -62,8 +75,8 @@ __device__ __forceinline__ float se_activation(float v, int act) {
 // fixed order and runs the two dense layers (attention_module.py:89-101) -> att_w[pair][19].
 __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   const int pl = blockIdx.y;
-  const int pg = p.pair0 + pl;
-  const int b = pg >> 1, k = pg & 1;
+  int b, k;
+  pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const size_t hw = (size_t)p.H * p.W;
   const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + k) * hw * 2);
   const int n4 = (int)(hw / 2);                      // float4 = 2 pixels
@@ -150,8 +163,8 @@ __device__ __forceinline__ float4 shfl_xor4(const float4 v, int m) {
 __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
   __shared__ float s_w[kNumClasses];
   const int pl = blockIdx.y;
-  const int pg = p.pair0 + pl;
-  const int b = pg >> 1, k = pg & 1;
+  int b, k;
+  pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
   if (threadIdx.x < kNumClasses)
     s_w[threadIdx.x] = p.att_src == 1 ? p.att_w[(size_t)pl * kNumClasses + threadIdx.x]
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
 }
 
 struct HeadParams {
-  int pair0, npairs;
+  int pair0, npairs, pair_mode;
   int nparts;             // partial rows per (pair, branch) = tiles * 4
   float inv_hw;           // 1 / (H7 * W7)
   const float* sums;      // [mb][2][nparts][256]
@@ -250,8 +263,11 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
     for (int i = lane; i < 256; i += 32) a += s_mean[br][i] * p.wpred[(br * 256 + i) * 3 + j];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0)
-      p.pose_out[(size_t)(p.pair0 + pl) * 6 + br * 3 + j] = 0.01f * (a + p.bpred[br * 3 + j]);
+    if (lane == 0) {
+      int b, k;
+      pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
+      p.pose_out[(size_t)(b * 2 + k) * 6 + br * 3 + j] = 0.01f * (a + p.bpred[br * 3 + j]);
+    }
   }
 }
 

@@ -107,13 +107,19 @@ class DAVO(object):
     def _resolve(self, x):
         return x() if callable(x) and not _is_torch(x) and not isinstance(x, np.ndarray) else x
 
-    def inference(self, sess=None, mode='pose', inputs=None, as_torch=False):
+    def inference(self, sess=None, mode='pose', inputs=None, as_torch=False, pairs='all'):
         """Reference ``davo.py:1553-1569``: one run of the pose graph -> ``{'pose': [B,2,6]}``.
 
         ``sess`` is accepted for signature compatibility and ignored.  ``inputs``
         may override the bound tensors as ``(img_u8, flow, seg)`` or a dict with
-        keys ``img``, ``flow``, ``seg``.
+        keys ``img``, ``flow``, ``seg``.  ``pairs``: ``'all'`` (the graph's output),
+        ``'trajectory'`` (only ``pose[:,1]``, what reference test_kitti_pose.py:143-145
+        composes) or ``'trajectory_first'`` (plus ``pose[0,0]``, for the batch that opens a
+        sequence); rows that are not computed are zero.
         """
+        if pairs not in _capi.PAIRS:
+            raise ValueError("DAVO.inference: pairs must be one of %s" % sorted(_capi.PAIRS))
+        sel = _capi.PAIRS[pairs]
         if mode not in ('pose',):
             raise NotImplementedError("davo_b200: inference mode %r is not built (only 'pose')" % (mode,))
         if not self._weights_loaded:
@@ -131,10 +137,10 @@ class DAVO(object):
             if t is not None and tuple(t.shape) != want[name]:
                 raise ValueError("DAVO.inference: %s has shape %s, expected %s" % (name, tuple(t.shape), want[name]))
         if _is_torch(img):
-            return self._run_device(B, img, flow, seg, as_torch)
-        return self._run_host(B, img, flow, seg)
+            return self._run_device(B, img, flow, seg, as_torch, sel)
+        return self._run_host(B, img, flow, seg, sel)
 
-    def _run_device(self, B, img, flow, seg, as_torch):
+    def _run_device(self, B, img, flow, seg, as_torch, sel=0):
         import torch
         for name, t, dt in (("img", img, torch.uint8), ("flow", flow, torch.float32), ("seg", seg, torch.float32)):
             if t is None:
@@ -147,20 +153,20 @@ class DAVO(object):
         out = self._pose_dev[:B]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        self._check(self._lib.davo_forward(self._h, B, ptr(img), ptr(flow), ptr(seg), None,
-                                           C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "davo_forward")
+        self._check(self._lib.davo_forward_pairs(self._h, B, sel, ptr(img), ptr(flow), ptr(seg), None,
+                                                 C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "davo_forward")
         if as_torch:
             return {'pose': out}
         return {'pose': out.cpu().numpy()}
 
-    def _run_host(self, B, img, flow, seg):
+    def _run_host(self, B, img, flow, seg, sel=0):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         flow = None if flow is None else np.ascontiguousarray(flow, dtype=np.float32)
         seg = None if seg is None else np.ascontiguousarray(seg, dtype=np.float32)
         out = np.empty((B, 2, 6), np.float32)
         ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-        self._check(self._lib.davo_forward_host(self._h, B, ptr(img), ptr(flow), ptr(seg), None,
-                                                ptr(out), None), "davo_forward_host")
+        self._check(self._lib.davo_forward_host_pairs(self._h, B, sel, ptr(img), ptr(flow), ptr(seg), None,
+                                                      ptr(out), None), "davo_forward_host")
         return {'pose': out}
 
     # ------------------------------------------------------ test / debug taps

@@ -43,6 +43,10 @@ def build_parser():
     ap.add_argument("--version", type=str, default="v1", help="version")
     ap.add_argument("--synthetic", type=int, default=0, help="use a seeded synthetic stream of this many frames")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--all_pairs", action="store_true",
+                    help="compute both poses of every sample as the reference graph does; by default only "
+                         "the poses the trajectory is composed from are computed (reference :143-145), "
+                         "which writes the same file with half the work")
     return ap
 
 
@@ -123,7 +127,9 @@ def main(argv=None):
     for i in range(len(idx) // B):                                     # reference :133
         batch = [stream.sample(j) for j in idx[i * B:(i + 1) * B]]
         img, flow, seg = (np.stack([s[k] for s in batch]) for k in range(3))
-        pred = system.inference(None, mode='pose', inputs=(img, flow, seg))     # reference :135
+        # reference :143-145 reads pose[s,1] of every sample and pose[0,0] of the sequence's first
+        sel = 'all' if FLAGS.all_pairs else ('trajectory_first' if (i == 0 and idx[0] == 0) else 'trajectory')
+        pred = system.inference(None, mode='pose', inputs=(img, flow, seg), pairs=sel)   # reference :135
         poses[i * B:(i + 1) * B] = torch.as_tensor(pred['pose'])
     all_poses = parallel.gather_poses(poses[:n_local].contiguous(), n).cpu().numpy()
     if rank == 0:

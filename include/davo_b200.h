@@ -81,6 +81,23 @@ int davo_forward(davo_ctx*, int B, const uint8_t* img_u8, const float* flow,
                  const float* seg, const float* depth, float* pose_out,
                  void* cuda_stream);
 
+/* Which frame pairs of the batch are computed.  The reference's consumer of pred_poses,
+ * test_kitti_pose.py:136-153, composes only pose[s][1] (tgt->src1) of every sample plus
+ * pose[0][0] (tgt->src0) of the first sample of a sequence (:143-145): the other half of the
+ * graph's work is discarded.  The TRAJECTORY selections compute exactly what that loop reads;
+ * the rows of pose_out that are not computed are set to zero.  The output file is identical. */
+enum {
+  DAVO_PAIRS_ALL = 0,               /* [B,2,6], as sess.run(pred_poses)            */
+  DAVO_PAIRS_TRAJECTORY = 1,        /* pose[s][1] for every s                      */
+  DAVO_PAIRS_TRAJECTORY_FIRST = 2   /* ... and pose[0][0]: the chunk that opens a sequence */
+};
+int davo_forward_pairs(davo_ctx*, int B, int pairs, const uint8_t* img_u8, const float* flow,
+                       const float* seg, const float* depth, float* pose_out,
+                       void* cuda_stream);
+int davo_forward_host_pairs(davo_ctx*, int B, int pairs, const uint8_t* img_u8, const float* flow,
+                            const float* seg, const float* depth, float* pose_out,
+                            void* cuda_stream);
+
 /* Same call with HOST buffers (pinned for overlap; pageable works): the end-to-end
  * form of `sess.run` with fed numpy arrays (reference davo.py:1568).  The batch is
  * streamed in micro-batch chunks, the host->device copy of chunk i+1 overlapping

@@ -289,16 +289,44 @@ def test_full_length_stream_is_batch_split_invariant():
     assert traj.shape == (4541, 4, 4) and np.all(np.isfinite(traj))
 
 
+@pytest.mark.parametrize("host", [False, True])
+def test_pair_selection_computes_what_the_trajectory_reads(host):
+    """DAVO_PAIRS_TRAJECTORY[_FIRST]: the selected poses carry the same bits as the full run, the
+    rest is zero; B = 19 samples crosses the host entry point's 16-sample chunk boundary."""
+    _need_gpu()
+    B = 19
+    w = S.init_weights(HEADLINE, random_bias=True)
+    inputs = S.make_inputs(B, H, W, seed=31)
+    sysm, dev = _system(HEADLINE, B, w, inputs)
+    feed = inputs if host else dev
+    full = sysm.inference(None, "pose", inputs=feed)["pose"].copy()
+    traj = sysm.inference(None, "pose", inputs=feed, pairs="trajectory")["pose"].copy()
+    first = sysm.inference(None, "pose", inputs=feed, pairs="trajectory_first")["pose"].copy()
+    assert np.array_equal(traj[:, 1], full[:, 1]) and not traj[:, 0].any()
+    assert np.array_equal(first[:, 1], full[:, 1]) and np.array_equal(first[0, 0], full[0, 0])
+    assert not first[1:, 0].any()
+    assert np.array_equal(geo_utils.compose_trajectory(first), geo_utils.compose_trajectory(full))
+    with pytest.raises(ValueError):
+        sysm.inference(None, "pose", inputs=feed, pairs="some")
+
+
 def test_cli_writes_reference_format_trajectory(tmp_path):
     """test_kitti_pose-shaped CLI on a synthetic 41-frame stream (ragged last batch of 4)."""
     _need_gpu()
     from davo_b200 import test_kitti_pose as cli
-    poses = cli.main(["--synthetic", "41", "--batch_size", "4", "--version", HEADLINE,
+    poses = cli.main(["--synthetic", "41", "--batch_size", "4", "--version", HEADLINE, "--all_pairs",
                       "--output_dir", str(tmp_path), "--test_seq", "9", "--seed", "77"])
     assert poses.shape == (39, 2, 6)
-    lines = (tmp_path / "09-pred_kitti_pose.txt").read_text().strip().split("\n")
+    text_all = (tmp_path / "09-pred_kitti_pose.txt").read_text()
+    lines = text_all.strip().split("\n")
     assert len(lines) == 41 and all(len(l.split()) == 12 for l in lines)
     assert lines == O.kitti_lines(O.compose_trajectory(poses))
+    # default: only the poses the composition reads are computed -- the file is the same, byte for byte
+    half = cli.main(["--synthetic", "41", "--batch_size", "4", "--version", HEADLINE,
+                     "--output_dir", str(tmp_path), "--test_seq", "9", "--seed", "77"])
+    assert (tmp_path / "09-pred_kitti_pose.txt").read_text() == text_all
+    assert np.array_equal(half[:, 1], poses[:, 1]) and np.array_equal(half[0, 0], poses[0, 0])
+    assert not half[1:, 0].any()
     # the same samples through the oracle
     stream = cli.SyntheticStream(41, H, W, 77)
     inputs = tuple(np.stack([stream.sample(i)[k] for i in range(6)]) for k in range(3))
