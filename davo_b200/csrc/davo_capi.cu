@@ -818,8 +818,10 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   fp.img = img; fp.flow = flow; fp.seg = seg;
   fp.se_w = ctx->d_sew; fp.static_w = ctx->d_staticw;
   fp.pool_part = ctx->d_pool; fp.pool_count = ctx->d_poolcnt; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
-  if (c.att_src == 1) {
-    se_pool_kernel<<<dim3(kPoolSplits, npairs), 256, 0, st>>>(fp);
+  if (c.att_src == 1 || c.att_src >= 3) {
+    static const int se_dims[5][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}};
+    fp.se_in = se_dims[c.att_src][0]; fp.se_hid = se_dims[c.att_src][1];
+    se_pool_kernel<<<dim3(kPoolSplits, npairs, c.att_tgt_ones ? 1 : 2), 256, 0, st>>>(fp);
     CU_OK(cudaGetLastError());
     ++*launches;
   }
@@ -888,7 +890,7 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (cfg->cnv6_out != 128 && cfg->cnv6_out != 64 && cfg->cnv6_out != 32)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128)", cfg->cnv6_out);
   if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
-  if (cfg->att_src < 0 || cfg->att_src > 2) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
+  if (cfg->att_src < 0 || cfg->att_src > 4) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -1019,9 +1021,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   }
 
   // ---- workspace ----
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_pool, (size_t)mb * kPoolSplits * 2 * 4)) return rc;
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_poolcnt, (size_t)mb * 4)) return rc;
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * kNumClasses * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_pool, (size_t)mb * 2 * kPoolSplits * kPoolDim * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_poolcnt, (size_t)mb * 2 * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * 2 * kNumClasses * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_packed, (size_t)mb * c.H * c.W * kPackedC * 4)) return rc;
   float* prev = ctx->d_packed;
   for (int i = 0; i < 7; ++i) {
@@ -1095,15 +1097,17 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     CU_OK(cudaMemcpy(ctx->d_wpred, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemcpy(ctx->d_bpred, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
   }
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_sew, 195 * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_sew, (19 * 19 + 19 + 19 * 19 + 19) * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_staticw, kNumClasses * 4)) return rc;
-  if (c.att_src == 1) {
-    const std::string S = P + "se_flow/";
+  if (c.att_src == 1 || c.att_src >= 3) {
+    // se(flow|rgb, [8,19]) (attention_module.py:54-103) or se_block(seg_19, ratio=1) (:9-52)
+    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? "se_seg/" : "se_rgb/");
+    const int din = c.att_src == 1 ? 2 : c.att_src == 3 ? 19 : 3, dh = c.att_src == 3 ? 19 : 8;
     const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
     const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
     const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
     const HostTensor* b2 = find_w(ctx, S + "recover_fc/bias");
-    if (!shape_is(w1, {2, 8}) || !shape_is(b1, {8}) || !shape_is(w2, {8, 19}) || !shape_is(b2, {19}))
+    if (!shape_is(w1, {din, dh}) || !shape_is(b1, {dh}) || !shape_is(w2, {dh, 19}) || !shape_is(b2, {19}))
       return fail(ctx, DAVO_ERR_WEIGHT, "missing or mis-shaped %s{bottleneck_fc,recover_fc}/{kernel,bias}", S.c_str());
     std::vector<float> se;
     se.insert(se.end(), w1->data.begin(), w1->data.end());
@@ -1278,7 +1282,7 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
   if (s == "att_weights") {
     n = kNumClasses;
     if (cap < n) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: buffer too small");
-    if (c.att_src == 1) src = ctx->d_attw + (size_t)pair * n;
+    if (c.att_src == 1 || c.att_src >= 3) src = ctx->d_attw + (size_t)pair * 2 * n;
     else if (c.att_src == 2) src = ctx->d_staticw;
     else { for (int i = 0; i < n; ++i) out[i] = 1.0f; *n_out = n; return 0; }
   }

@@ -15,6 +15,7 @@
 namespace davo {
 
 constexpr int kPoolSplits = 16;
+constexpr int kPoolDim = 20;     // >= the widest pooled vector (19 class frequencies)
 constexpr int kPackedC = 16;     // packed PoseNN input channels (see pack_kernel)
 constexpr int kNumClasses = 19;
 constexpr int kPackBlocksPerPair = 104;
@@ -37,7 +38,8 @@ struct FrontParams {
   int pair_mode;         // see pair_of_slot
   int npairs;
   int in_mode;           // 1: flows are concatenated (v1)
-  int att_src;           // 0 none, 1 se_flow, 2 static
+  int att_src;           // 0 none, 1 se_flow, 2 static, 3 se_seg, 4 se_rgb (-> seg): davo.py:1117-1400
+  int se_in, se_hid;     // SE dense sizes: in -> hid -> 19 (flow 2,8; seg 19,19; rgb 3,8)
   int att_tgt_ones;
   int mask_rgb, mask_flow;
   int se_act;            // 0 relu, 1 tanh, 2 lrelu
@@ -46,11 +48,11 @@ struct FrontParams {
   const uint8_t* img;    // [B][H][3W][3]
   const float* flow;     // [B][4][H][W][2]
   const float* seg;      // [B][3][H][W][1]
-  const float* se_w;     // W1[2][8] b1[8] W2[8][19] b2[19]  (195 floats)
+  const float* se_w;     // W1[in][hid] b1[hid] W2[hid][19] b2[19]
   const float* static_w; // sigmoid(seg_channel_weight)[19]
-  float* pool_part;      // [mb][kPoolSplits][2]
-  unsigned int* pool_count;  // [mb], zero between launches
-  float* att_w;          // [mb][19]
+  float* pool_part;      // [mb][2 frames][kPoolSplits][kPoolDim]
+  unsigned int* pool_count;  // [mb][2], zero between launches
+  float* att_w;          // [mb][2 frames][19]: frame 0 = the pair's source frame, 1 = the target
   float* packed;         // [mb][H][W][16]
 };
 
@@ -70,74 +72,119 @@ __device__ __forceinline__ float se_activation(float v, int act) {
   return fmaxf(v, 0.f);
 }
 
-// grid (kPoolSplits, npairs), 256 threads.  Deterministic partial sums of the SE input
-// (attention_module.py:66); the block that finishes a pair last adds the partials in a
-// fixed order and runs the two dense layers (attention_module.py:89-101) -> att_w[pair][19].
+// grid (kPoolSplits, npairs, frames), 256 threads.  Global average pool of the SE input in
+// deterministic partial sums (attention_module.py:66 / :22); the block that finishes a
+// (pair, frame) last adds the partials in a fixed order and runs the two dense layers
+// (attention_module.py:89-101 / :37-50) -> att_w[pair][frame][19].
+//   se_flow (davo.py:1176):      pool = mean of the (abs / normalised) flow, 2 -> 8 -> 19
+//   se_seg (davo.py:1306, 1313): pool = class frequencies of one_hot(label) (out-of-range labels
+//                                 are all-zero rows), 19 -> 19 -> 19; excitation * one_hot summed
+//                                 over classes = excitation[label]
+//   se_rgb*_to_seg (davo.py:1277, 1287): pool = mean r, g, b of the frame, 3 -> 8 -> 19
+// blockIdx.z = 0: the pair's source frame; 1: the target frame (variants that do not force the
+// target map to ones).
 __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
-  const int pl = blockIdx.y;
+  const int pl = blockIdx.y, fr = blockIdx.z;
   int b, k;
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
-  const size_t hw = (size_t)p.H * p.W;
-  const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + k) * hw * 2);
-  const int n4 = (int)(hw / 2);                      // float4 = 2 pixels
-  const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
-  const int beg = blockIdx.x * per;
-  const int end = min(beg + per, n4);
-  float sx = 0.f, sy = 0.f;
-  for (int i = beg + threadIdx.x; i < end; i += 256) {
-    const float4 v = __ldg(src + i);
-    sx += se_in_x(v.x, p) + se_in_x(v.z, p);
-    sy += se_in_y(v.y, p) + se_in_y(v.w, p);
-  }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    sx += __shfl_xor_sync(0xffffffffu, sx, o);
-    sy += __shfl_xor_sync(0xffffffffu, sy, o);
-  }
-  __shared__ float red[8][2];
-  __shared__ float s_fc1[8];
+  const int hw = p.H * p.W;
+  const int D = p.se_in;
+  __shared__ float red[8][4];
+  __shared__ int s_hist[kNumClasses];
+  __shared__ float s_pool[kPoolDim];
+  __shared__ float s_fc1[kPoolDim];
   __shared__ int s_last;
-  if ((threadIdx.x & 31) == 0) {
-    red[threadIdx.x >> 5][0] = sx;
-    red[threadIdx.x >> 5][1] = sy;
+  float* part = p.pool_part + (((size_t)pl * 2 + fr) * kPoolSplits + blockIdx.x) * kPoolDim;
+  if (p.att_src == 3) {
+    if (threadIdx.x < kNumClasses) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const float* seg = p.seg + ((size_t)b * 3 + (fr ? 1 : (k == 0 ? 0 : 2))) * hw;
+    const int per = (hw + kPoolSplits - 1) / kPoolSplits;
+    const int beg = blockIdx.x * per, end = min(beg + per, hw);
+    for (int i = beg + threadIdx.x; i < end; i += 256) {
+      const int lab = (int)__ldg(seg + i);                      // tf.cast truncates toward zero
+      if (lab >= 0 && lab < kNumClasses) atomicAdd(&s_hist[lab], 1);   // integer counts: exact, order-free
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumClasses) part[threadIdx.x] = (float)s_hist[threadIdx.x];
+  } else {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (p.att_src == 1) {
+      const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2);
+      const int n4 = hw / 2;                          // float4 = 2 pixels
+      const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
+      const int beg = blockIdx.x * per, end = min(beg + per, n4);
+      if (fr == 0)                                    // the target's flow is all zeros (davo.py:979)
+        for (int i = beg + threadIdx.x; i < end; i += 256) {
+          const float4 v = __ldg(src + i);
+          s0 += se_in_x(v.x, p) + se_in_x(v.z, p);
+          s1 += se_in_y(v.y, p) + se_in_y(v.w, p);
+        }
+    } else {
+      // byte sums are exact; the affine map to [-1, 1] (davo.py:1519-1522) is applied to the mean
+      const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
+      const int col0 = fr ? p.W : (k == 0 ? 0 : 2 * p.W);
+      const int per = (hw + kPoolSplits - 1) / kPoolSplits;
+      const int beg = blockIdx.x * per, end = min(beg + per, hw);
+      unsigned int u0 = 0, u1 = 0, u2 = 0;
+      for (int i = beg + threadIdx.x; i < end; i += 256) {
+        const int h = i / p.W, w = i - h * p.W;
+        const uint8_t* px = img_b + ((size_t)h * 3 * p.W + col0 + w) * 3;
+        u0 += px[0]; u1 += px[1]; u2 += px[2];
+      }
+      s0 = (float)u0; s1 = (float)u1; s2 = (float)u2;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red[threadIdx.x >> 5][0] = s0; red[threadIdx.x >> 5][1] = s1; red[threadIdx.x >> 5][2] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float a = 0.f;
+      for (int i = 0; i < 8; ++i) a += red[i][threadIdx.x];
+      part[threadIdx.x] = a;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float ax = 0.f, ay = 0.f;
-    for (int i = 0; i < 8; ++i) { ax += red[i][0]; ay += red[i][1]; }
-    p.pool_part[((size_t)pl * kPoolSplits + blockIdx.x) * 2 + 0] = ax;
-    p.pool_part[((size_t)pl * kPoolSplits + blockIdx.x) * 2 + 1] = ay;
     __threadfence();
-    const unsigned int done = atomicAdd(&p.pool_count[pl], 1u);
+    const unsigned int done = atomicAdd(&p.pool_count[pl * 2 + fr], 1u);
     s_last = (done == kPoolSplits - 1);
-    if (s_last) p.pool_count[pl] = 0;              // ready for the next launch
+    if (s_last) p.pool_count[pl * 2 + fr] = 0;       // ready for the next launch
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x < 8) {
-    float px = 0.f, py = 0.f;
-    for (int s = 0; s < kPoolSplits; ++s) {
-      px += __ldcg(p.pool_part + ((size_t)pl * kPoolSplits + s) * 2 + 0);
-      py += __ldcg(p.pool_part + ((size_t)pl * kPoolSplits + s) * 2 + 1);
-    }
-    const float inv = 1.0f / (float)hw;
-    px *= inv;
-    py *= inv;
-    const float* W1 = p.se_w;            // [2][8]
-    const float* b1 = p.se_w + 16;       // [8]
-    const int j = threadIdx.x;
-    s_fc1[j] = se_activation(px * W1[j] + py * W1[8 + j] + b1[j], p.se_act);
+  if (threadIdx.x < D) {
+    const float* pp = p.pool_part + ((size_t)pl * 2 + fr) * kPoolSplits * kPoolDim + threadIdx.x;
+    float a = 0.f;
+    for (int sp = 0; sp < kPoolSplits; ++sp) a += __ldcg(pp + sp * kPoolDim);
+    a *= 1.0f / (float)hw;
+    if (p.att_src == 4) a = a * (1.0f / 255.0f) * 2.0f - 1.0f;
+    s_pool[threadIdx.x] = a;
+  }
+  __syncthreads();
+  const int Hd = p.se_hid;
+  const float* W1 = p.se_w;                    // [D][Hd]
+  const float* b1 = W1 + D * Hd;               // [Hd]
+  const float* W2 = b1 + Hd;                   // [Hd][19]
+  const float* b2 = W2 + Hd * kNumClasses;     // [19]
+  if (threadIdx.x < Hd) {
+    float a = b1[threadIdx.x];
+    for (int i = 0; i < D; ++i) a += s_pool[i] * W1[i * Hd + threadIdx.x];
+    s_fc1[threadIdx.x] = se_activation(a, p.se_act);
   }
   __syncthreads();
   if (threadIdx.x < kNumClasses) {
-    const float* W2 = p.se_w + 24;       // [8][19]
-    const float* b2 = p.se_w + 24 + 8 * kNumClasses;
     const int c = threadIdx.x;
     float a = b2[c];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
-    p.att_w[(size_t)pl * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
+    for (int j = 0; j < Hd; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
+    p.att_w[((size_t)pl * 2 + fr) * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
   }
 }
 
@@ -161,14 +208,18 @@ __device__ __forceinline__ float4 shfl_xor4(const float4 v, int m) {
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
-  __shared__ float s_w[kNumClasses];
+  __shared__ float s_w[kNumClasses], s_wt[kNumClasses];    // class weights: source frame, target frame
   const int pl = blockIdx.y;
   int b, k;
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
-  if (threadIdx.x < kNumClasses)
-    s_w[threadIdx.x] = p.att_src == 1 ? p.att_w[(size_t)pl * kNumClasses + threadIdx.x]
+  if (threadIdx.x < kNumClasses) {
+    const bool se = p.att_src == 1 || p.att_src >= 3;
+    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * 2 + 0) * kNumClasses + threadIdx.x]
                      : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
+    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * 2 + 1) * kNumClasses + threadIdx.x]
+                      : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, j = lane & 3;
   const float inv_w = 1.0f / (float)p.W;
@@ -189,7 +240,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
       a_src = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;  // one_hot: out of range -> 0
       if (!p.att_tgt_ones) {
         const int lt = (int)__ldg(seg_tgt + pix);
-        a_tgt = (lt >= 0 && lt < kNumClasses) ? s_w[lt] : 0.0f;
+        a_tgt = (lt >= 0 && lt < kNumClasses) ? s_wt[lt] : 0.0f;
       }
     }
     const float mt = p.mask_rgb ? a_tgt : 1.0f, ms = p.mask_rgb ? a_src : 1.0f;

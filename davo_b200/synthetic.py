@@ -98,11 +98,14 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
     for scope, shape in conv_specs(cfg):
         w["pose_exp_net/%s/weights" % scope] = _xavier_uniform(rng, shape)
         w["pose_exp_net/%s/biases" % scope] = bias(shape[3])
-    if cfg.att_src == V.ATT_SE_FLOW:
-        for name, (fi, fo) in (("bottleneck_fc", (2, 8)), ("recover_fc", (8, 19))):
+    se_scopes = {V.ATT_SE_FLOW: ("se_flow", 2, 8), V.ATT_SE_SEG: ("se_seg", 19, 19),
+                 V.ATT_SE_RGB_SEG: ("se_rgb", 3, 8)}
+    if cfg.att_src in se_scopes:
+        scope, din, dh = se_scopes[cfg.att_src]
+        for name, (fi, fo) in (("bottleneck_fc", (din, dh)), ("recover_fc", (dh, 19))):
             std = math.sqrt(1.3 * 2.0 / fi)
-            w["pose_exp_net/se_flow/%s/kernel" % name] = _trunc_normal(rng, (fi, fo), std)
-            w["pose_exp_net/se_flow/%s/bias" % name] = bias(fo)
+            w["pose_exp_net/%s/%s/kernel" % (scope, name)] = _trunc_normal(rng, (fi, fo), std)
+            w["pose_exp_net/%s/%s/bias" % (scope, name)] = bias(fo)
     if cfg.att_src == V.ATT_STATIC:
         # double scope is the reference's: prefix "pose_exp_net/" inside scope pose_exp_net
         w["pose_exp_net/pose_exp_net/seg_channel_weight/weight"] = \

@@ -22,7 +22,7 @@ POSENN_COUPLE_DIL = 3            # couple_net_v0_dilation          :12-66
 POSENN_COUPLE = 4                # couple_net_v0                   :257-311
 POSENN_DECOUPLE = 5              # decouple_net_v0                 :314-378
 
-ATT_NONE, ATT_SE_FLOW, ATT_STATIC = 0, 1, 2
+ATT_NONE, ATT_SE_FLOW, ATT_STATIC, ATT_SE_SEG, ATT_SE_RGB_SEG = 0, 1, 2, 3, 4
 MASK_OFF, MASK_RGB, MASK_ALL, MASK_ALL_555 = 0, 1, 2, 3
 ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2
 ABS_NONE, ABS_BOTH, ABS_H, ABS_V = 0, 1, 2, 3
@@ -44,6 +44,18 @@ _UNBUILT_AFTER_SE_FLOW = (
     "-se_SegFlow_to_seg_8_wo_tgt", "-se_SegFlow_to_seg_8", "-se_SegFlow_to_seg_wo_tgt",
     "-se_SegFlow_to_seg", "-se_mixSegFlow", "-se_spp21_mixSegFlow",
 )
+
+
+# Sources of that chain that ARE built: token -> (att_src, att_tgt_ones).  `_wo_tgt` forces the
+# target map to ones (davo.py:1283, 1310); without it the target frame gets its own SE map, and
+# since no variable lives under 'pose_exp_net/se_flow' the G11 override does not fire
+# (davo.py:1404-1414).
+_BUILT_AFTER_SE_FLOW = {
+    "-se_rgb_wo_tgt_to_seg": (ATT_SE_RGB_SEG, 1),     # davo.py:1274-1283
+    "-se_rgb_to_seg": (ATT_SE_RGB_SEG, 0),            # davo.py:1284-1292
+    "-se_seg_wo_tgt": (ATT_SE_SEG, 1),                # davo.py:1304-1310
+    "-se_seg": (ATT_SE_SEG, 0),                       # davo.py:1311-1316
+}
 
 
 @dataclass
@@ -137,10 +149,16 @@ def parse_version(version: str) -> DavoConfig:
         cfg.att_src = ATT_SE_FLOW
         cfg.att_tgt_ones = 1                                    # davo.py:1404-1412
     else:
-        for tok in _UNBUILT_AFTER_SE_FLOW:
+        chain_hit = None
+        for tok in _UNBUILT_AFTER_SE_FLOW:                      # reference order: first match wins
             if tok in version:
-                raise NotImplementedError("davo_b200: attention source %s is not built" % tok)
-        if "-no_segmask" in version:                            # davo.py:1385
+                if tok not in _BUILT_AFTER_SE_FLOW:
+                    raise NotImplementedError("davo_b200: attention source %s is not built" % tok)
+                chain_hit = tok
+                break
+        if chain_hit is not None:
+            cfg.att_src, cfg.att_tgt_ones = _BUILT_AFTER_SE_FLOW[chain_hit]
+        elif "-no_segmask" in version:                          # davo.py:1385
             cfg.att_src = ATT_NONE
             cfg.att_tgt_ones = 1
         elif "-segmask_" in version and "-static" in version:   # davo.py:1390

@@ -285,8 +285,29 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att_w.append(w19)
             att.append(class_gather(pred_segs[i], w19))
         use_se_flow = True                                               # davo.py:1404
-    elif re.search("-se_(gp2x2|spp|depth|disp|rgb|seg|SegFlow)", version):
+    elif re.search("-se_(gp2x2|spp|depth|disp|SegFlow)", version):
         _unsupported("attention source in " + version)
+    elif "-se_rgb_wo_tgt_to_seg" in version or "-se_rgb_to_seg" in version:   # davo.py:1274-1292
+        att, att_w = [], []
+        for i in range(3):
+            w19 = se_weights(input_images[i], wts, "pose_exp_net/se_rgb", act)
+            att_w.append(w19)
+            att.append(class_gather(pred_segs[i], w19))
+        if "-se_rgb_wo_tgt_to_seg" in version:
+            att[0] = torch.ones_like(att[0])                             # davo.py:1283
+    elif "-se_rgb" in version:
+        _unsupported("-se_rgb without _to_seg")
+    elif "-se_seg_wo_tgt" in version or "-se_seg" in version:            # davo.py:1304-1316
+        att, att_w = [], []
+        for i in range(3):
+            lab = torch.trunc(pred_segs[i][..., 0]).to(torch.int64)      # davo.py:1115
+            onehot = torch.nn.functional.one_hot(lab.clamp(0, NUM_CLASSES - 1), NUM_CLASSES).to(dtype)
+            onehot = onehot * ((lab >= 0) & (lab < NUM_CLASSES)).to(dtype)[..., None]
+            exc = se_weights(onehot, wts, "pose_exp_net/se_seg", act)    # se_block, ratio=1: 19 -> 19 -> 19
+            att_w.append(exc)
+            att.append((onehot * exc[:, None, None, :]).sum(-1, keepdim=True))   # attention_module.py:51, davo.py:1306
+        if "-se_seg_wo_tgt" in version:
+            att[0] = torch.ones_like(att[0])                             # davo.py:1310
     elif "-no_segmask" in version:                                       # davo.py:1385-1389
         att = [torch.ones_like(s) for s in pred_segs]
     elif "-segmask_" in version and "-static" in version:                # davo.py:1390-1394

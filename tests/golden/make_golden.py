@@ -23,6 +23,9 @@ CASES = {
     "static": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-static",
     "segmask_rgb": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_rgb-se_flow-abs_flow-fc_tanh",
     "v0_lrelu": "v0-sharedNN-dilatedPoseNN-cnv6_64-segmask_rgb-se_flow-abs_flow_h-norm_flow-fc_lrelu",
+    "se_seg_wo_tgt": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_seg_wo_tgt-fc_tanh",
+    "se_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_seg-fc_tanh",
+    "se_rgb_to_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_rgb_wo_tgt_to_seg-fc_tanh",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)
 

@@ -19,6 +19,10 @@ def test_headline_variant():
     ("-segmask_rgb-static", V.ATT_STATIC, 1, V.MASK_RGB),
     ("-segmask_all", V.ATT_STATIC, 0, V.MASK_ALL),           # final else of the chain (davo.py:1395)
     ("-segmask_rgb-se_flow", V.ATT_SE_FLOW, 1, V.MASK_RGB),
+    ("-segmask_all-se_seg_wo_tgt-fc_tanh", V.ATT_SE_SEG, 1, V.MASK_ALL),       # davo.py:1304-1310
+    ("-segmask_all-se_seg-fc_tanh", V.ATT_SE_SEG, 0, V.MASK_ALL),              # davo.py:1311-1316
+    ("-segmask_all-se_rgb_wo_tgt_to_seg", V.ATT_SE_RGB_SEG, 1, V.MASK_ALL),    # davo.py:1274-1283
+    ("-segmask_rgb-se_rgb_to_seg", V.ATT_SE_RGB_SEG, 0, V.MASK_RGB),           # davo.py:1284-1292
 ])
 def test_attention_and_mask_modes(suffix, att, tgt1, mask):
     c = V.parse_version(BASE + suffix)
@@ -62,7 +66,7 @@ def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_seg_wo_tgt", "-se_rgb_wo_tgt_to_seg", "-se_gp2x2_flow", "-se_mixSegFlow"])
+@pytest.mark.parametrize("tok", ["-se_rgb_wo_tgt", "-se_gp2x2_seg", "-se_gp2x2_flow", "-se_mixSegFlow"])
 def test_unbuilt_sources_fail_loudly(tok):
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
