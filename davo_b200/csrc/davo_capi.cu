@@ -123,6 +123,9 @@ struct davo_ctx {
   float *d_pool = nullptr, *d_attw = nullptr, *d_packed = nullptr, *d_sum7 = nullptr;
   float *d_sew = nullptr, *d_staticw = nullptr, *d_wpred = nullptr, *d_bpred = nullptr;
   float* d_c7tmp = nullptr;         // direct path only
+  // -se_insert: excitation of cnv5 per branch (frontend.cuh: se5_*)
+  float *d_se5w = nullptr, *d_se5part = nullptr, *d_se5scale = nullptr, *d_se5out = nullptr;
+  unsigned int* d_se5cnt = nullptr;
   int nparts7 = 0;
   // host-buffer entry point staging
   uint8_t* s_img[2] = {nullptr, nullptr};
@@ -846,7 +849,20 @@ int launch_head(davo_ctx* ctx, int pair_mode, int pair0, int npairs, float* pose
 int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint8_t* img, const float* flow,
                    const float* seg, float* pose_out, cudaStream_t st, int* launches) {
   if (int rc = launch_front(ctx, pair_mode, pair0, npairs, img, flow, seg, st, launches)) return rc;
-  for (Layer& L : ctx->layers) {
+  for (size_t li = 0; li < ctx->layers.size(); ++li) {
+    Layer& L = ctx->layers[li];
+    if (li == 5 && ctx->cfg.posenn_se == 1) {      // -se_insert: excite cnv5 per branch in front of cnv6
+      Se5Params sp;
+      sp.npairs = npairs; sp.hw = L.Hin * L.Win;
+      sp.cnv5 = ctx->layers[4].d_out; sp.w = ctx->d_se5w; sp.part = ctx->d_se5part; sp.count = ctx->d_se5cnt;
+      sp.scale = ctx->d_se5scale; sp.out = ctx->d_se5out;
+      se5_excite_kernel<<<dim3(kSe5Splits, npairs), 256, 0, st>>>(sp);
+      CU_OK(cudaGetLastError());
+      const long long total = (long long)npairs * sp.hw * 64;
+      se5_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sp);
+      CU_OK(cudaGetLastError());
+      *launches += 2;
+    }
     int rc = ctx->conv_impl == 0 ? launch_conv(ctx, L, npairs, st) : launch_conv_direct(ctx, L, npairs, st);
     if (rc) return rc;
     *launches += (ctx->conv_impl == 0) ? 1 : L.groups;
@@ -882,8 +898,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   *out = nullptr;
   if (cfg->posenn != 0)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d is not built (only decouple_sharednet_v0_dilation)", cfg->posenn);
-  if (cfg->posenn_se != 0)
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built", cfg->posenn_se);
+  if (cfg->posenn_se != 0 && cfg->posenn_se != 1)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built (only -se_insert)", cfg->posenn_se);
   if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: H and W must be positive multiples of 8 (got %dx%d)", cfg->H, cfg->W);
   if (cfg->max_batch <= 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: max_batch must be positive");
@@ -963,9 +979,11 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   struct Geo { int k, stride, dil; };
   const Geo geo[7] = {{7, 2, 1}, {5, 2, 1}, {3, 1, 2}, {3, 1, 4}, {3, 1, 8}, {3, 1, 2}, {3, 2, 1}};
   const int cout_total[7] = {16, 32, 64, 128, 256, 2 * c6, 512};
-  const int bn[7] = {16, 32, 64, 128, 256, 2 * c6, 256};
-  const int groups[7] = {1, 1, 1, 1, 1, 1, 2};
-  const int cin_total[7] = {16, 16, 32, 64, 128, 256, 2 * c6};
+  const int bn[7] = {16, 32, 64, 128, 256, (c.posenn_se == 1 ? 1 : 2) * c6, 256};
+  const int groups[7] = {1, 1, 1, 1, 1, c.posenn_se == 1 ? 2 : 1, 2};
+  // -se_insert: cnv6 reads two differently scaled copies of cnv5 (one per branch): a grouped layer
+  const bool se5 = c.posenn_se == 1;
+  const int cin_total[7] = {16, 16, 32, 64, 128, se5 ? 512 : 256, 2 * c6};
   const int cin_g[7] = {16, 16, 32, 64, 128, 256, c6};
   const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c6};
   const char* names[7] = {"cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6", "cnv7"};
@@ -1028,6 +1046,14 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   float* prev = ctx->d_packed;
   for (int i = 0; i < 7; ++i) {
     Layer& L = ctx->layers[i];
+    if (i == 5 && se5) {
+      const size_t hw5 = (size_t)L.Hin * L.Win;
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5part, (size_t)mb * kSe5Splits * 256 * 4)) return rc;
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5cnt, (size_t)mb * 4)) return rc;
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5scale, (size_t)mb * 2 * 256 * 4)) return rc;
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5out, (size_t)mb * hw5 * 512 * 4)) return rc;
+      prev = ctx->d_se5out;
+    }
     L.d_in = prev;
     if (i < 6) {
       if (int rc = dev_alloc(ctx, (void**)&L.d_out, (size_t)mb * L.Hout * L.Wout * L.out_stride * 4)) return rc;
@@ -1063,13 +1089,39 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     const HostTensor *w[2], *b[2];
     for (int g = 0; g < 2; ++g)
       if (int rc = need_conv(std::string("pose/") + brs[g] + "/cnv6", 3, 256, c6, &w[g], &b[g])) return rc;
-    auto getw = [&](int, int ty, int tx, int ci, int n) {
-      const HostTensor* t = w[n / c6];
-      return t->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + (n % c6)];
-    };
     std::vector<float> bias(2 * c6);
     for (int n = 0; n < 2 * c6; ++n) bias[n] = b[n / c6]->data[n % c6];
-    if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
+    if (se5) {      // two groups: branch g convolves its own scaled copy of cnv5
+      auto getw = [&](int g, int ty, int tx, int ci, int n) {
+        return w[g]->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + n];
+      };
+      if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
+    } else {        // one N = 2*c6 GEMM: rotation | translation
+      auto getw = [&](int, int ty, int tx, int ci, int n) {
+        const HostTensor* t = w[n / c6];
+        return t->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + (n % c6)];
+      };
+      if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
+    }
+  }
+  if (se5) {
+    // reference nets/posenn.py:227: variables pose/<branch>/cnv5_se_attention/{bottleneck_fc,recover_fc}
+    std::vector<float> sw;
+    for (int g = 0; g < 2; ++g) {
+      const std::string S = P + "pose/" + brs[g] + "/cnv5_se_attention/";
+      const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
+      const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
+      const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
+      const HostTensor* b2 = find_w(ctx, S + "recover_fc/bias");
+      if (!shape_is(w1, {256, 32}) || !shape_is(b1, {32}) || !shape_is(w2, {32, 256}) || !shape_is(b2, {256}))
+        return fail(ctx, DAVO_ERR_WEIGHT, "missing or mis-shaped %s{bottleneck_fc,recover_fc}/{kernel,bias}", S.c_str());
+      sw.insert(sw.end(), w1->data.begin(), w1->data.end());
+      sw.insert(sw.end(), b1->data.begin(), b1->data.end());
+      sw.insert(sw.end(), w2->data.begin(), w2->data.end());
+      sw.insert(sw.end(), b2->data.begin(), b2->data.end());
+    }
+    if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5w, sw.size() * 4)) return rc;
+    CU_OK(cudaMemcpy(ctx->d_se5w, sw.data(), sw.size() * 4, cudaMemcpyHostToDevice));
   }
   {
     Layer& L = ctx->layers[6];

@@ -323,6 +323,89 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
 }
 
 // ------------------------------------------------------------------------------
+// `-se_insert` (reference nets/posenn.py:225-228): se_block(cnv5, 'cnv5_se_attention', ratio=8)
+// in front of cnv6 of each branch.  cnv5 is RE-ASSIGNED inside the branch loop, so the
+// translation branch's block sits on top of the rotation branch's output:
+//     exc_r = SE_r(mean cnv5),  cnv6_rot   = conv(cnv5 * exc_r)
+//     exc_t = SE_t(mean(cnv5 * exc_r)) = SE_t(mean(cnv5) * exc_r),  cnv6_trans = conv(cnv5 * exc_r * exc_t)
+// The excitation is per channel, so the second block needs no second pass over the map.
+constexpr int kSe5Splits = 32;
+struct Se5Params {
+  int npairs, hw;               // pixels of the cnv5 map
+  const float* cnv5;            // [mb][hw][256]
+  const float* w;               // per branch: W1[256][32] b1[32] W2[32][256] b2[256]
+  float* part;                  // [mb][kSe5Splits][256]
+  unsigned int* count;          // [mb]
+  float* scale;                 // [mb][2][256]: exc_r, exc_r * exc_t
+  float* out;                   // [mb][hw][512]: cnv5 * scale[0] | cnv5 * scale[1], TF32-rounded
+};
+constexpr int kSe5BranchFloats = 256 * 32 + 32 + 32 * 256 + 256;
+
+// grid (kSe5Splits, npairs), 256 threads (thread = channel).
+__global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
+  const int pl = blockIdx.y, c = threadIdx.x;
+  const int per = (p.hw + kSe5Splits - 1) / kSe5Splits;
+  const int beg = blockIdx.x * per, end = min(beg + per, p.hw);
+  const float* src = p.cnv5 + (size_t)pl * p.hw * 256 + c;
+  float a = 0.f;
+  for (int i = beg; i < end; ++i) a += src[(size_t)i * 256];
+  p.part[((size_t)pl * kSe5Splits + blockIdx.x) * 256 + c] = a;
+  __shared__ int s_last;
+  __shared__ float s_mean[256], s_hid[32];
+  __syncthreads();
+  if (c == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(&p.count[pl], 1u);
+    s_last = (done == kSe5Splits - 1);
+    if (s_last) p.count[pl] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float m = 0.f;
+  for (int sp = 0; sp < kSe5Splits; ++sp) m += __ldcg(p.part + ((size_t)pl * kSe5Splits + sp) * 256 + c);
+  m *= 1.0f / (float)p.hw;
+  float scale = 1.0f;
+  for (int br = 0; br < 2; ++br) {
+    const float* W1 = p.w + br * kSe5BranchFloats;       // [256][32]
+    const float* b1 = W1 + 256 * 32;
+    const float* W2 = b1 + 32;                           // [32][256]
+    const float* b2 = W2 + 32 * 256;
+    s_mean[c] = m * scale;                               // mean of what this branch's block sees
+    __syncthreads();
+    if (c < 32) {
+      float h = b1[c];
+      for (int i = 0; i < 256; ++i) h += s_mean[i] * W1[i * 32 + c];
+      s_hid[c] = fmaxf(h, 0.f);                          // se_block's default activation: relu
+    }
+    __syncthreads();
+    float e = b2[c];
+    for (int j = 0; j < 32; ++j) e += s_hid[j] * W2[j * 256 + c];
+    scale *= 1.0f / (1.0f + expf(-e));
+    p.scale[((size_t)pl * 2 + br) * 256 + c] = scale;
+    __syncthreads();
+  }
+}
+
+// one thread per (pixel, 4 channels): out[pixel][br*256 + c] = tf32(cnv5[pixel][c] * scale[br][c])
+__global__ void __launch_bounds__(256) se5_scale_kernel(const Se5Params p) {
+  const long long total = (long long)p.npairs * p.hw * 64;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx & 63);
+  const long long pix = idx >> 6;                         // global pixel index over the pass
+  const int pl = (int)(pix / p.hw);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p.cnv5) + pix * 64 + c4);
+  float4* o = reinterpret_cast<float4*>(p.out) + pix * 128 + c4;
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + ((size_t)pl * 2 + br) * 256 + c4 * 4);
+    o[br * 64] = make_float4(round_tf32(v.x * sc.x), round_tf32(v.y * sc.y), round_tf32(v.z * sc.z),
+                             round_tf32(v.w * sc.w));
+  }
+}
+
+// ------------------------------------------------------------------------------
 // Plain fp32 direct convolution (CUDA cores).  NOT on the product path: it is the
 // on-GPU cross-check the tests use to tell a tcgen05/TMA descriptor error from a
 // host-side packing error (davo_debug_set_conv_impl).

@@ -26,6 +26,7 @@ CASES = {
     "se_seg_wo_tgt": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_seg_wo_tgt-fc_tanh",
     "se_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_seg-fc_tanh",
     "se_rgb_to_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_rgb_wo_tgt_to_seg-fc_tanh",
+    "se_insert": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-no_segmask-se_insert",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)
 
