@@ -96,7 +96,7 @@ struct Layer {
   bool b_resident = false;     // pm: all weight slabs stay in shared memory
   int wide_G = 0;              // pm, column-widened: output pixels per M row (0 = off)
   int wide_tw = 0;             //   runs per tile row (tile = 128/wide_tw rows x wide_tw runs)
-  bool lo_alias = false;       // cnv1: packed channels 10-15 are TF32 residuals of 0-2, 5-7
+  int pc2w[16];                // input tensor channel -> HWIO input channel of the weights, -1: none (cnv1: packed input)
   int smem_bytes = 0;
   CUtensorMap tmA, tmB;          // activation (patch) map, weight map
   CUtensorMap tmO;               // pm store epilogue: output tiles (TMA store)
@@ -114,6 +114,7 @@ struct davo_ctx {
   std::map<std::string, HostTensor> weights;
   bool finalized = false;
   int mb = 0;                       // frame pairs per micro-batch
+  int packed_c = 16;                // channels per pixel of the packed PoseNN input (8 or 16)
   int conv_impl = 0;                // 0 tcgen05 (product), 1 direct fp32 (debug cross-check)
   bool compensated_rounding = true; // TF32 weight rounding directions chosen so tap sums cancel
   std::vector<Layer> layers;        // cnv1..cnv7
@@ -337,17 +338,9 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
         Tap t{par, 0, 0, dh, w2, 0, std::vector<Ent>(32)};
         for (int kk = 0; kk < 32; ++kk) {
           const int wp = kk / 16;
-          int ch = kk % 16;
-          if (L.lo_alias && ch >= 10) {                 // residual channels reuse the weights
-            const int alias[6] = {0, 1, 2, 5, 6, 7};    // of the channel they refine
-            ch = alias[ch - 10];
-          }
+          const int ch = kk % 16;
           const int tx = 2 * w2 + wp + L.pad_l;
-          int ci = -1;
-          if (tx >= 0 && tx < L.k) {
-            if (L.use_cmap) { for (int i = 0; i < L.Cin_w; ++i) if (L.cmap[i] == ch) ci = i; }
-            else if (ch < L.Cin_w) ci = ch;
-          }
+          const int ci = (tx >= 0 && tx < L.k) ? L.pc2w[ch] : -1;
           t.e[kk] = Ent{ty, tx, ci};
         }
         taps.push_back(t);
@@ -552,15 +545,15 @@ template <class GetW>
 int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bias_host) {
   const int G = L.wide_G, TWc = L.wide_tw, THr = 128 / TWc, Co = L.BN, NW = G * Co;
   if (NW != 128) return fail(ctx, DAVO_ERR_ARG, "%s: the widened kernel is built for N = 128 (got %d)", L.name, NW);
-  const int d_min = floordiv(-L.pad_l, 2), d_max = floordiv(L.k - 1 - L.pad_l, 2), nd = d_max - d_min + 1;
-  const int c_min = d_min, c_max = floordiv(2 * (G - 1) + L.k - 1 - L.pad_l, 2);
+  // S input pixels x C channels make one 32-float slab (C = 16: S = 2; cnv1's 8-channel input: S = 4).
+  // Output pixel g of a run reads input pixel u = 2g + tx - pad_l (relative to the run's first
+  // input pixel); slab c = floor(u / S), wp = u mod S.  With d = (S/2) c - g the filter column is
+  // tx = 2d + wp + pad_l, so the weights of (c, g) depend on d only.
+  const int C = L.Cin_total, S = 32 / C, half = S / 2, slabs_per_run = 2 * G / S;
+  const int d_min = -floordiv(L.pad_l + S - 1, 2), d_max = floordiv(L.k - 1 - L.pad_l, 2), nd = d_max - d_min + 1;
+  const int c_min = floordiv(-L.pad_l, S), c_max = floordiv(2 * (G - 1) + L.k - 1 - L.pad_l, S);
   const std::vector<float> wr = round_weights_tf32(L, getw, ctx->compensated_rounding);
   auto wq = [&](int ty, int tx, int ci, int n) { return wr[(((size_t)ty * L.k + tx) * L.Cin_w + ci) * Co + n]; };
-  auto weight_channel = [&](int ch) {            // packed input channel -> HWIO input channel, -1: none
-    if (L.lo_alias && ch >= 10) { const int alias[6] = {0, 1, 2, 5, 6, 7}; ch = alias[ch - 10]; }
-    if (L.use_cmap) { for (int i = 0; i < L.Cin_w; ++i) if (L.cmap[i] == ch) return i; return -1; }
-    return ch < L.Cin_w ? ch : -1;
-  };
   // ---- weights: [ty][d_max..d_min][Cout][32] ----
   const int box_rows = nd * Co;
   std::vector<float> pack((size_t)L.k * box_rows * 32, 0.f);
@@ -568,7 +561,7 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
     for (int b = 0; b < nd; ++b)
       for (int n = 0; n < Co; ++n)
         for (int kk = 0; kk < 32; ++kk) {
-          const int tx = 2 * (d_max - b) + kk / 16 + L.pad_l, ci = weight_channel(kk % 16);
+          const int tx = 2 * (d_max - b) + kk / C + L.pad_l, ci = L.pc2w[kk % C];
           if (tx >= 0 && tx < L.k && ci >= 0) pack[(((size_t)ty * nd + b) * Co + n) * 32 + kk] = wq(ty, tx, ci, n);
         }
   if (int rc = dev_alloc(ctx, (void**)&L.d_wpack, pack.size() * 4)) return rc;
@@ -586,24 +579,31 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
     if (int rc = dev_alloc(ctx, (void**)&L.d_whwio[0], hw.size() * 4)) return rc;
     CU_OK(cudaMemcpy(L.d_whwio[0], hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
   }
-  // ---- patches (one per pair position and row parity) and taps ----
-  // The tile's first MMAs must overwrite the accumulator: start with pair positions whose
-  // column windows partition the run, on the parity of filter row 0.
-  std::vector<int> cover;
+  // ---- patches (one per slab position and row parity) and taps ----
+  auto g_lo_of = [&](int c) { return std::max(half * c - d_max, 0); };
+  auto g_hi_of = [&](int c) { return std::min(half * c - d_min, G - 1); };
+  // The tile's first MMAs must OVERWRITE the accumulator.  Cover the run with column windows
+  // that do not overlap: slab positions whose windows reach furthest, each cut to start where
+  // the previous one ended; what is cut off is issued as an extra accumulating tap.
+  struct Cover { int c, from; };
+  std::vector<Cover> cover;
   for (int s0 = 0; s0 < G;) {
-    const int c = s0 + d_max;
-    cover.push_back(c);
-    s0 = std::min(c - d_min, G - 1) + 1;
+    int best = c_min - 1;
+    for (int c = c_min; c <= c_max; ++c)
+      if (g_lo_of(c) <= s0 && s0 <= g_hi_of(c) && (best < c_min || g_hi_of(c) > g_hi_of(best))) best = c;
+    if (best < c_min) return fail(ctx, DAVO_ERR_ARG, "%s: widened plan cannot cover the run", L.name);
+    cover.push_back(Cover{best, s0});
+    s0 = g_hi_of(best) + 1;
   }
   const int par0 = posmod(-L.pad_t, 2);
-  struct P2 { int c, par; };
+  struct P2 { int c, par, from; };                 // from >= 0: cover patch, fresh columns start there
   std::vector<P2> plist;
-  for (int c : cover) plist.push_back(P2{c, par0});
+  for (const Cover& cv : cover) plist.push_back(P2{cv.c, par0, cv.from});
   for (int par = 0; par < 2; ++par)
     for (int c = c_min; c <= c_max; ++c) {
       bool seen = false;
       for (const P2& q : plist) seen |= (q.c == c && q.par == par);
-      if (!seen) plist.push_back(P2{c, par});
+      if (!seen) plist.push_back(P2{c, par, -1});
     }
   int dh_lo[2] = {1 << 20, 1 << 20}, dh_hi[2] = {-(1 << 20), -(1 << 20)};
   for (int ty = 0; ty < L.k; ++ty) {
@@ -619,23 +619,29 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
   for (const P2& q : plist) {
     if (np >= kMaxPatches) return fail(ctx, DAVO_ERR_ARG, "%s: too many patches for the widened plan", L.name);
     PatchDesc& d = pdesc[np];
-    d.c = (int16_t)(32 * posmod(q.c, G)); d.dw = (int8_t)floordiv(q.c, G); d.par = (int8_t)q.par;
+    d.c = (int16_t)(32 * posmod(q.c, slabs_per_run)); d.dw = (int8_t)floordiv(q.c, slabs_per_run); d.par = (int8_t)q.par;
     d.dh = (int8_t)dh_lo[q.par]; d.tap0 = (uint16_t)nt;
-    const int g_lo = std::max(q.c - d_max, 0), g_hi = std::min(q.c - d_min, G - 1);
-    const bool covers = np < (int)cover.size();
+    const int g_lo = g_lo_of(q.c), g_hi = g_hi_of(q.c);
     int n_here = 0;
-    for (int ty = 0; ty < L.k; ++ty) {
-      const int dy = ty - L.pad_t;
-      if (posmod(dy, 2) != q.par) continue;
-      if (nt >= kMaxTaps) return fail(ctx, DAVO_ERR_ARG, "%s: too many taps for the widened plan", L.name);
+    auto emit = [&](int ty, int ga, int gb, int fresh) {
       TapDesc& t = tdesc[nt++];
-      t.a_off = (uint16_t)((floordiv(dy, 2) - dh_lo[q.par]) * Wp);
+      t.a_off = (uint16_t)((floordiv(ty - L.pad_t, 2) - dh_lo[q.par]) * Wp);
       t.b_idx = (uint16_t)ty;
-      t.n16 = (uint8_t)((g_hi - g_lo + 1) * Co / 16);
-      t.dcol16 = (uint8_t)(g_lo * Co / 16);
-      t.brow8 = (uint8_t)((d_max - q.c + g_lo) * Co / 8);
-      t.fresh = (covers && n_here == 0) ? 1 : 0;
+      t.n16 = (uint8_t)((gb - ga + 1) * Co / 16);
+      t.dcol16 = (uint8_t)(ga * Co / 16);
+      t.brow8 = (uint8_t)((d_max - half * q.c + ga) * Co / 8);
+      t.fresh = (uint8_t)fresh;
       ++n_here;
+    };
+    for (int ty = 0; ty < L.k; ++ty) {
+      if (posmod(ty - L.pad_t, 2) != q.par) continue;
+      if (nt + 2 > kMaxTaps) return fail(ctx, DAVO_ERR_ARG, "%s: too many taps for the widened plan", L.name);
+      if (q.from >= 0 && n_here == 0) {
+        emit(ty, q.from, g_hi, 1);
+        if (g_lo < q.from) emit(ty, g_lo, q.from - 1, 0);
+      } else {
+        emit(ty, g_lo, g_hi, 0);
+      }
     }
     d.ntaps = (uint8_t)n_here;
     ++np;
@@ -663,9 +669,9 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   {
-    const cuuint64_t C = L.Cin_total, H = L.Hin, W = L.Win, N = ctx->mb;
-    const cuuint64_t dims[5] = {2 * G * C, W / (2 * G), 2, H / 2, N};
-    const cuuint64_t strides[4] = {2 * G * C * 4, W * C * 4, 2 * W * C * 4, H * W * C * 4};
+    const cuuint64_t H = L.Hin, W = L.Win, N = ctx->mb;
+    const cuuint64_t dims[5] = {(cuuint64_t)2 * G * C, W / (2 * G), 2, H / 2, N};
+    const cuuint64_t strides[4] = {(cuuint64_t)2 * G * C * 4, W * C * 4, 2 * W * C * 4, H * W * C * 4};
     const cuuint32_t box[5] = {32, (cuuint32_t)Wp, 1, (cuuint32_t)Hp, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&L.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, L.d_in, dims, strides, box, es,
@@ -685,8 +691,8 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
   }
   if (int rc = encode_output_map(ctx, L, NW, L.Wout / G, TWc)) return rc;
   if (getenv("DAVO_B200_VERBOSE"))
-    fprintf(stderr, "[davo_b200] %s: pixels-on-M widened x%d (N=%d), tile %dx%d runs, patch %dx%d (%d B) x%d, %d taps, weights resident %d B, ring P%d, smem %d\n",
-            L.name, G, NW, THr, TWc, Hp, Wp, patch_bytes, np, nt, resident_bytes, P.p_stages, L.smem_bytes);
+    fprintf(stderr, "[davo_b200] %s: pixels-on-M widened x%d (N=%d, %d-pixel slabs), tile %dx%d runs, patch %dx%d (%d B) x%d, %d taps, weights resident %d B, ring P%d, smem %d\n",
+            L.name, G, NW, S, THr, TWc, Hp, Wp, patch_bytes, np, nt, resident_bytes, P.p_stages, L.smem_bytes);
   return 0;
 }
 
@@ -814,6 +820,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   FrontParams fp;
   memset(&fp, 0, sizeof fp);
   fp.H = c.H; fp.W = c.W; fp.pair0 = pair0; fp.npairs = npairs; fp.pair_mode = pair_mode;
+  fp.packed_c = ctx->packed_c;
   fp.in_mode = c.in_mode; fp.att_src = c.att_src; fp.att_tgt_ones = c.att_tgt_ones;
   fp.mask_rgb = c.mask_mode != 0;
   fp.mask_flow = c.mask_mode == 2;
@@ -983,8 +990,12 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   const int groups[7] = {1, 1, 1, 1, 1, c.posenn_se == 1 ? 2 : 1, 2};
   // -se_insert: cnv6 reads two differently scaled copies of cnv5 (one per branch): a grouped layer
   const bool se5 = c.posenn_se == 1;
-  const int cin_total[7] = {16, 16, 32, 64, 128, se5 ? 512 : 256, 2 * c6};
-  const int cin_g[7] = {16, 16, 32, 64, 128, 256, c6};
+  // Packed PoseNN input (frontend.cuh: pack_kernel): 8 channels per pixel when the width allows the
+  // column-widened cnv1 plan (runs of 16 input pixels), else the 16-channel layout of the plain plan.
+  const char* wide_env0 = getenv("DAVO_B200_WIDE");
+  ctx->packed_c = ((c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
+  const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? 512 : 256, 2 * c6};
+  const int cin_g[7] = {ctx->packed_c, 16, 32, 64, 128, 256, c6};
   const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c6};
   const char* names[7] = {"cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6", "cnv7"};
   ctx->layers.resize(7);
@@ -1014,7 +1025,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     // Thin stride-2 layers: runs of G output pixels on one M row, N = G * Cout = 128 (conv_pm.cuh, WIDE).
     const char* wide_env = getenv("DAVO_B200_WIDE");          // debug: "0" switches the widened plan off
     const int G = 128 / L.BN;
-    if (L.orient == 0 && L.stride == 2 && L.Cin_total == 16 && L.groups == 1 && L.BN <= 32 && (L.Win % (2 * G)) == 0 &&
+    if (L.orient == 0 && L.stride == 2 && (L.Cin_total == 16 || L.Cin_total == 8) && L.groups == 1 && L.BN <= 32 &&
+        (L.Win % (2 * G)) == 0 &&
         L.epi == EPI_STORE_RELU && !(wide_env && !strcmp(wide_env, "0"))) {
       const int runs = L.Wout / G;
       long best = -1;
@@ -1026,23 +1038,39 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
       L.tiles_h = (L.Hout + 128 / L.wide_tw - 1) / (128 / L.wide_tw);
       L.tiles_w = (runs + L.wide_tw - 1) / L.wide_tw;
     }
-    for (int j = 0; j < 16; ++j) L.cmap[j] = j;
+    for (int j = 0; j < 16; ++j) { L.cmap[j] = j; L.pc2w[j] = j < L.Cin_w ? j : -1; }
     H = L.Hout; W = L.Wout;
   }
-  // cnv1 reads the 16-channel packed input: [tgt rgb, 0 0, src rgb, src flow, residuals x 6]
-  ctx->layers[0].lo_alias = true;
-  if (c.in_mode == 0) {
+  {
+    // cnv1 reads the packed input.  The reference's cnv1 sees [tgt rgb, tgt flow (zeros), src rgb,
+    // src flow] (v1: 10 channels) or [tgt rgb, src rgb] (v0: 6).  Packed layouts:
+    //   8 channels:  tgt rgb, src rgb, src flow            (the all-zero target flow is not stored)
+    //   16 channels: tgt rgb, 0 0, src rgb, src flow, 6 x TF32 residuals (ignored: measured to
+    //                make no difference once the weights are rounded with compensation)
     Layer& L = ctx->layers[0];
-    L.use_cmap = 1;
-    const int m[6] = {0, 1, 2, 5, 6, 7};
-    for (int j = 0; j < 6; ++j) L.cmap[j] = m[j];
+    if (L.wide_G == 0 && ctx->packed_c == 8)
+      return fail(ctx, DAVO_ERR_ARG, "cnv1: 8-channel packed input needs the widened plan");
+    for (int j = 0; j < 16; ++j) L.pc2w[j] = -1;
+    const int rgb_src = ctx->packed_c == 8 ? 3 : 5, flow_src = ctx->packed_c == 8 ? 6 : 8;
+    for (int j = 0; j < 3; ++j) {
+      L.pc2w[j] = j;                                        // tgt rgb
+      L.pc2w[rgb_src + j] = (c.in_mode == 1 ? 5 : 3) + j;   // src rgb
+    }
+    if (c.in_mode == 1) { L.pc2w[flow_src] = 8; L.pc2w[flow_src + 1] = 9; }
+    L.use_cmap = 1;                                         // direct cross-check path: weight channel -> packed channel
+    for (int ci = 0; ci < L.Cin_w; ++ci) {
+      L.cmap[ci] = 0;
+      bool found = false;
+      for (int j = 0; j < 16; ++j) if (L.pc2w[j] == ci) { L.cmap[ci] = j; found = true; }
+      if (!found) L.cmap[ci] = -1;                          // the target's zero flow: no packed channel
+    }
   }
 
   // ---- workspace ----
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_pool, (size_t)mb * 2 * kPoolSplits * kPoolDim * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_poolcnt, (size_t)mb * 2 * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * 2 * kNumClasses * 4)) return rc;
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_packed, (size_t)mb * c.H * c.W * kPackedC * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_packed, (size_t)mb * c.H * c.W * ctx->packed_c * 4)) return rc;
   float* prev = ctx->d_packed;
   for (int i = 0; i < 7; ++i) {
     Layer& L = ctx->layers[i];
@@ -1338,7 +1366,7 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
     else if (c.att_src == 2) src = ctx->d_staticw;
     else { for (int i = 0; i < n; ++i) out[i] = 1.0f; *n_out = n; return 0; }
   }
-  else if (s == "packed") { n = (int64_t)c.H * c.W * kPackedC; src = ctx->d_packed + (size_t)pair * n; }
+  else if (s == "packed") { n = (int64_t)c.H * c.W * ctx->packed_c; src = ctx->d_packed + (size_t)pair * n; }
   else if (s == "cnv7_sum") {
     // reduce the deterministic partials on the host
     const int np = ctx->nparts7;

@@ -16,7 +16,7 @@ namespace davo {
 
 constexpr int kPoolSplits = 16;
 constexpr int kPoolDim = 20;     // >= the widest pooled vector (19 class frequencies)
-constexpr int kPackedC = 16;     // packed PoseNN input channels (see pack_kernel)
+constexpr int kPackedC = 16;     // widest packed PoseNN input (see pack_kernel; FrontParams::packed_c = 8 or 16)
 constexpr int kNumClasses = 19;
 constexpr int kPackBlocksPerPair = 104;
 
@@ -36,6 +36,7 @@ struct FrontParams {
   int H, W;
   int pair0;             // first selection slot of this pass
   int pair_mode;         // see pair_of_slot
+  int packed_c;          // 8: [tgt rgb, src rgb, src flow]; 16: the legacy layout of pack_kernel
   int npairs;
   int in_mode;           // 1: flows are concatenated (v1)
   int att_src;           // 0 none, 1 se_flow, 2 static, 3 se_seg, 4 se_rgb (-> seg): davo.py:1117-1400
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
   const float* seg_src = p.seg + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw;
   const float* seg_tgt = p.seg + ((size_t)b * 3 + 1) * hw;
   const float2* flow_src = reinterpret_cast<const float2*>(p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2);
-  float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * kPackedC);
+  float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * p.packed_c);
   const int src_col0 = (k == 0) ? 0 : 2 * p.W;
   for (int base = blockIdx.x * 256; base < hw; base += kPackBlocksPerPair * 256) {
     const int pix_raw = base + threadIdx.x;
@@ -257,6 +258,14 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
     }
     const float trh = round_tf32(tr), tgh = round_tf32(tg), tbh = round_tf32(tb);
     const float srh = round_tf32(sr), sgh = round_tf32(sg), sbh = round_tf32(sb);
+    if (p.packed_c == 8) {
+      // 32 B per pixel, consecutive lanes = consecutive pixels: a warp writes 1 KB contiguous.
+      if (pix_raw < hw) {
+        out[(size_t)pix_raw * 2 + 0] = make_float4(trh, tgh, tbh, srh);
+        out[(size_t)pix_raw * 2 + 1] = make_float4(sgh, sbh, round_tf32(fx), round_tf32(fy));
+      }
+      continue;
+    }
     float4 q0 = make_float4(trh, tgh, tbh, 0.f);
     float4 q1 = make_float4(0.f, srh, sgh, sbh);
     float4 q2 = make_float4(round_tf32(fx), round_tf32(fy), round_tf32(tr - trh), round_tf32(tg - tgh));
@@ -443,6 +452,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const DirectConvParams
       const float* wp = p.w + ((size_t)(ty * p.kw + tx) * p.Cin) * p.Cout + co;
       for (int ci = 0; ci < p.Cin; ++ci) {
         const int ic = p.use_cmap ? p.cmap[ci] : ci;
+        if (ic < 0) continue;                    // a weight channel whose input is identically zero
         acc = fmaf(ip[ic], wp[(size_t)ci * p.Cout], acc);
       }
     }

@@ -85,15 +85,12 @@ def test_every_layer_matches_oracle_per_pixel(monkeypatch):
     sysm.inference(None, "pose")
     for p in range(2):
         tp = taps["pair%d" % p]
-        packed = sysm.get_intermediate("packed", p).reshape(H, W, 16)
-        assert np.all(packed[..., 3:5] == 0)                                # tgt flow slots (zeros)
-        assert _rel(packed[..., :10], tp["input"][0]) < 6e-4               # stored TF32-rounded
-        recon = packed[..., :10].astype(np.float64)                         # + residual channels 10-15
-        recon[..., [0, 1, 2, 5, 6, 7]] += packed[..., 10:16]
-        assert _rel(recon[..., [0, 1, 2, 5, 6, 7]], tp["input"][0][..., [0, 1, 2, 5, 6, 7]]) < 2e-6
+        # packed PoseNN input, 8 channels: tgt rgb, src rgb x A, src flow x A (the zero tgt flow is dropped)
+        packed = sysm.get_intermediate("packed", p).reshape(H, W, 8)
+        assert _rel(packed, tp["input"][0][..., [0, 1, 2, 5, 6, 7, 8, 9]]) < 6e-4     # stored TF32-rounded
         # out-of-range labels zero the source pixel (davo.py:1115)
         bad = inputs[2][0, 0 if p == 0 else 2, ..., 0] == 255
-        assert bad.any() and np.all(packed[bad][:, 5:10] == 0)
+        assert bad.any() and np.all(packed[bad][:, 3:8] == 0)
         for name in ("cnv1", "cnv2", "cnv3", "cnv4", "cnv5"):
             assert _rel(sysm.get_intermediate(name, p), tp[name][0]) < 1.5e-3, name
         c6 = sysm.get_intermediate("cnv6", p).reshape(32, 104, 256)

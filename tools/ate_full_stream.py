@@ -9,10 +9,13 @@ from oracle import davo_oracle as O
 ver = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh"
 n, chunk = 4539, 64
 w = S.init_weights(ver)
-modes = sys.argv[1:] or ["compensated"]      # DAVO_B200_WEIGHT_ROUNDING values to compare
+modes = sys.argv[1:] or ["compensated"]      # DAVO_B200_WEIGHT_ROUNDING values to compare; "noresidual" = compensated without residual channels
 systems = {}
 for m in modes:
-    os.environ["DAVO_B200_WEIGHT_ROUNDING"] = m
+    os.environ["DAVO_B200_WEIGHT_ROUNDING"] = "compensated" if m == "noresidual" else m
+    os.environ.pop("DAVO_B200_NO_RESIDUAL", None)
+    if m == "noresidual":
+        os.environ["DAVO_B200_NO_RESIDUAL"] = "1"
     systems[m] = DAVO(version=ver)
     systems[m].setup_inference(128, 416, "davo", 3, chunk, device=0)
     systems[m].load_weights(w)

@@ -42,9 +42,11 @@ for impl in (1, 0):
         aw = sysm.get_intermediate("att_weights", p)
         if taps["attention_weights"] is not None:
             print("  pair", p, "att_w", rel(aw, taps["attention_weights"][1 + k][b]), end=" ")
-        pk = sysm.get_intermediate("packed", p).reshape(H, W, 16)
-        rc = pk[..., :10].astype(np.float64); rc[..., [0, 1, 2, 5, 6, 7]] += pk[..., 10:16]
-        print("packed %.2e hi+lo %.2e" % (rel(pk[..., :10], tp["input"][b]), rel(rc, tp["input"][b])), end=" ")
+        pk = sysm.get_intermediate("packed", p)
+        if pk.size == H * W * 8:
+            print("packed8 %.2e" % rel(pk.reshape(H, W, 8), tp["input"][b][..., [0, 1, 2, 5, 6, 7, 8, 9]]), end=" ")
+        else:
+            print("packed16 %.2e" % rel(pk.reshape(H, W, 16)[..., :10], tp["input"][b]), end=" ")
         for i, name in enumerate(["cnv1", "cnv2", "cnv3", "cnv4", "cnv5"]):
             g = sysm.get_intermediate(name, p)
             print(name, "%.2e" % rel(g, tp[name][b]), end=" ")
