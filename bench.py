@@ -234,7 +234,7 @@ def run_ours(args):
 
     # end to end: host numpy in, host numpy out, through the public API
     h_img, h_flow, h_seg = (torch.as_tensor(x).pin_memory().numpy() for x in (img, flow, seg))
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 50))
     for _ in range(2):
         system.inference(None, "pose", inputs=(h_img, h_flow, h_seg))
     sync_all()
@@ -247,6 +247,19 @@ def run_ours(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * 2 * B * e2e_steps / float(dt.item())
     h2d, d2h = system.last_host_copy_bytes()      # counted by the library from the copies it issues
+    # what the link itself gives: one plain pinned host->device copy of the same number of bytes
+    pin = torch.empty(h2d, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(h2d, dtype=torch.uint8, device=dev)
+    dst.copy_(pin, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        dst.copy_(pin, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    pcie_gbs = 5 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del pin, dst
 
     if rank != 0:
         if world > 1:
@@ -303,7 +316,10 @@ def run_ours(args):
                    "parallelism": "sample-sharded x%d, NCCL all-gather of poses" % world},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
+                "steps": e2e_steps, "pcie_h2d_gbs": pcie_gbs,
+                "pcie_bound": 2 * B / (h2d / (pcie_gbs * 1e9)),
+                "note": "host inputs cross PCIe inside the timed region: pcie_bound = frame pairs / (h2d bytes / "
+                        "measured pinned copy rate) is the ceiling of this number on this box"},
         "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -835,7 +835,8 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     CU_OK(cudaGetLastError());
     ++*launches;
   }
-  pack_kernel<<<dim3(kPackBlocksPerPair, npairs), 256, 0, st>>>(fp);
+  if (ctx->packed_c == 8) pack8_kernel<<<dim3(kPack8Blocks, npairs), 256, 0, st>>>(fp);
+  else pack_kernel<<<dim3(kPackBlocksPerPair, npairs), 256, 0, st>>>(fp);
   CU_OK(cudaGetLastError());
   ++*launches;
   return 0;
@@ -1293,8 +1294,14 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   size_t h2d = 0;
   int launches = 0, last_n = 0, chunk = 0;
   if (pairs != DAVO_PAIRS_ALL) CU_OK(cudaMemsetAsync(ctx->s_pose, 0, (size_t)B * 12 * sizeof(float), st));
-  for (int s0 = 0; s0 < B; s0 += cs, ++chunk) {
-    const int ns = std::min(cs, B - s0);
+  // The copy is the bound, so the time after the LAST copy is what compute adds: the final chunks
+  // taper (.., cs, cs/2, cs/4, cs/4) so that only a quarter chunk is computed after the copies end.
+  int ns = 0, last_ns = 0;
+  for (int s0 = 0; s0 < B; s0 += ns, ++chunk) {
+    const int left = B - s0;
+    const int minc = std::max(1, cs / 4);
+    ns = left > cs + cs / 2 ? cs : left > 2 * minc ? std::min(cs, (left + 1) / 2) : std::min(left, minc);
+    last_ns = ns;
     const int buf = chunk & 1;
     if (chunk >= 2) CU_OK(cudaStreamWaitEvent(cp, ctx->ev_consumed[buf], 0));
     CU_OK(cudaMemcpyAsync(ctx->s_img[buf], img + n_img * s0, n_img * ns, cudaMemcpyHostToDevice, cp));
@@ -1334,7 +1341,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   ctx->last_h2d = (long long)h2d;
   ctx->last_d2h = (long long)12 * 4 * B;
   ctx->last_img = ctx->s_img[(chunk - 1) & 1]; ctx->last_flow = ctx->s_flow[(chunk - 1) & 1];
-  ctx->last_seg = ctx->s_seg[(chunk - 1) & 1]; ctx->last_pose = ctx->s_pose; ctx->last_B = std::min(cs, B - (chunk - 1) * cs);
+  ctx->last_seg = ctx->s_seg[(chunk - 1) & 1]; ctx->last_pose = ctx->s_pose; ctx->last_B = last_ns;
   ctx->last_pairs = (pairs == DAVO_PAIRS_TRAJECTORY_FIRST && chunk > 1) ? DAVO_PAIRS_TRAJECTORY : pairs;
   return 0;
 }

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
   const float* seg_src = p.seg + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw;
   const float* seg_tgt = p.seg + ((size_t)b * 3 + 1) * hw;
   const float2* flow_src = reinterpret_cast<const float2*>(p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2);
-  float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * p.packed_c);
+  float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * kPackedC);
   const int src_col0 = (k == 0) ? 0 : 2 * p.W;
   for (int base = blockIdx.x * 256; base < hw; base += kPackBlocksPerPair * 256) {
     const int pix_raw = base + threadIdx.x;
@@ -258,14 +258,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
     }
     const float trh = round_tf32(tr), tgh = round_tf32(tg), tbh = round_tf32(tb);
     const float srh = round_tf32(sr), sgh = round_tf32(sg), sbh = round_tf32(sb);
-    if (p.packed_c == 8) {
-      // 32 B per pixel, consecutive lanes = consecutive pixels: a warp writes 1 KB contiguous.
-      if (pix_raw < hw) {
-        out[(size_t)pix_raw * 2 + 0] = make_float4(trh, tgh, tbh, srh);
-        out[(size_t)pix_raw * 2 + 1] = make_float4(sgh, sbh, round_tf32(fx), round_tf32(fy));
-      }
-      continue;
-    }
+
     float4 q0 = make_float4(trh, tgh, tbh, 0.f);
     float4 q1 = make_float4(0.f, srh, sgh, sbh);
     float4 q2 = make_float4(round_tf32(fx), round_tf32(fy), round_tf32(tr - trh), round_tf32(tg - tgh));
@@ -290,6 +283,104 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
       if (pB + 0 < hw) out[(size_t)(pB + 0) * 4 + j] = b0;
       if (pB + 1 < hw) out[(size_t)(pB + 1) * 4 + j] = b1;
     }
+  }
+}
+
+// 8-channel packed layout (FrontParams::packed_c == 8; W % 16 == 0): [tgt r g b, src r g b (x A),
+// src flow x y (x A)], every value TF32-rounded.  grid (kPack8Blocks, npairs), 256 threads, one
+// thread per 4 consecutive pixels of a row: the 12 image bytes of a frame are three 32-bit
+// loads, labels and flow are float4 loads.  A thread's 8 float4 (128 B) go through a per-warp
+// XOR-swizzled staging buffer so that every store instruction of the warp writes 512
+// consecutive bytes.
+constexpr int kPack8Blocks = 52;
+__device__ __forceinline__ void unpack_rgb4(uint32_t t0, uint32_t t1, uint32_t t2, float (&r)[4], float (&g)[4],
+                                            float (&b)[4]) {
+  r[0] = img_norm(t0 & 255u); g[0] = img_norm((t0 >> 8) & 255u); b[0] = img_norm((t0 >> 16) & 255u);
+  r[1] = img_norm(t0 >> 24); g[1] = img_norm(t1 & 255u); b[1] = img_norm((t1 >> 8) & 255u);
+  r[2] = img_norm((t1 >> 16) & 255u); g[2] = img_norm(t1 >> 24); b[2] = img_norm(t2 & 255u);
+  r[3] = img_norm((t2 >> 8) & 255u); g[3] = img_norm((t2 >> 16) & 255u); b[3] = img_norm(t2 >> 24);
+}
+
+__global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
+  __shared__ float s_w[kNumClasses], s_wt[kNumClasses];    // class weights: source frame, target frame
+  __shared__ float4 s_stage[8][256];
+  const int pl = blockIdx.y;
+  int b, k;
+  pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
+  const int hw = p.H * p.W, groups = hw / 4;
+  if (threadIdx.x < kNumClasses) {
+    const bool se = p.att_src == 1 || p.att_src >= 3;
+    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * 2 + 0) * kNumClasses + threadIdx.x]
+                     : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
+    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * 2 + 1) * kNumClasses + threadIdx.x]
+                      : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
+  const float* seg_src = p.seg + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw;
+  const float* seg_tgt = p.seg + ((size_t)b * 3 + 1) * hw;
+  const float* flow_src = p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2;
+  float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 8);
+  const int src_col0 = (k == 0) ? 0 : 2 * p.W;
+  float4* st = s_stage[warp];
+  for (int base = blockIdx.x * 256; base < groups; base += kPack8Blocks * 256) {
+    const int gi = base + threadIdx.x;
+    float4 q[8];
+    if (gi < groups) {
+      const int p0 = gi * 4, h = p0 / p.W, w = p0 - h * p.W;
+      const size_t row = (size_t)h * 3 * p.W;
+      const uint32_t* pt = reinterpret_cast<const uint32_t*>(img_b + (row + p.W + w) * 3);
+      const uint32_t* ps = reinterpret_cast<const uint32_t*>(img_b + (row + src_col0 + w) * 3);
+      float tr[4], tg[4], tb[4], sr[4], sg[4], sb[4], a_src[4] = {1.f, 1.f, 1.f, 1.f}, a_tgt[4] = {1.f, 1.f, 1.f, 1.f};
+      unpack_rgb4(__ldg(pt), __ldg(pt + 1), __ldg(pt + 2), tr, tg, tb);
+      unpack_rgb4(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2), sr, sg, sb);
+      if (p.att_src != 0) {
+        const float4 ls = __ldg(reinterpret_cast<const float4*>(seg_src + p0));
+        const float lsv[4] = {ls.x, ls.y, ls.z, ls.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int lab = (int)lsv[i];                              // tf.cast truncates toward zero
+          a_src[i] = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;   // one_hot: out of range -> 0
+        }
+        if (!p.att_tgt_ones) {
+          const float4 lt = __ldg(reinterpret_cast<const float4*>(seg_tgt + p0));
+          const float ltv[4] = {lt.x, lt.y, lt.z, lt.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int lab = (int)ltv[i];
+            a_tgt[i] = (lab >= 0 && lab < kNumClasses) ? s_wt[lab] : 0.0f;
+          }
+        }
+      }
+      float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.in_mode == 1) {
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(flow_src + (size_t)p0 * 2));
+        const float4 f1 = __ldg(reinterpret_cast<const float4*>(flow_src + (size_t)p0 * 2 + 4));
+        fx[0] = f0.x; fy[0] = f0.y; fx[1] = f0.z; fy[1] = f0.w;
+        fx[2] = f1.x; fy[2] = f1.y; fx[3] = f1.z; fy[3] = f1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float mt = p.mask_rgb ? a_tgt[i] : 1.0f, ms = p.mask_rgb ? a_src[i] : 1.0f;
+        const float mf = p.mask_flow ? a_src[i] : 1.0f;
+        q[2 * i + 0] = make_float4(round_tf32(tr[i] * mt), round_tf32(tg[i] * mt), round_tf32(tb[i] * mt),
+                                   round_tf32(sr[i] * ms));
+        q[2 * i + 1] = make_float4(round_tf32(sg[i] * ms), round_tf32(sb[i] * ms), round_tf32(fx[i] * mf),
+                                   round_tf32(fy[i] * mf));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st[8 * lane + (j ^ (lane & 7))] = q[j];
+    __syncwarp();
+    const size_t f4_0 = (size_t)(base + warp * 32) * 8;          // first float4 of this warp's 32 groups
+#pragma unroll
+    for (int J = 0; J < 8; ++J) {
+      const int i = J * 32 + lane, Lp = i >> 3, jp = i & 7;
+      const float4 v = st[8 * Lp + (jp ^ (Lp & 7))];
+      if (f4_0 + i < (size_t)hw * 2) out[f4_0 + i] = v;
+    }
+    __syncwarp();
   }
 }
 
