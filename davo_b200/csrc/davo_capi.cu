@@ -129,10 +129,12 @@ struct davo_ctx {
   unsigned int* d_se5cnt = nullptr;
   int nparts7 = 0;
   // host-buffer entry point staging
-  uint8_t* s_img[2] = {nullptr, nullptr};
-  float *s_flow[2] = {nullptr, nullptr}, *s_seg[2] = {nullptr, nullptr}, *s_pose = nullptr;
+  static constexpr int kStage = 3;  // staging buffers: copy of chunk i+2 never waits for compute of chunk i
+  uint8_t* s_img[kStage] = {};
+  float *s_flow[kStage] = {}, *s_seg[kStage] = {}, *s_pose = nullptr;
+  int s_chunk = 0;                  // samples per staging buffer
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_start = nullptr;
+  cudaEvent_t ev_copied[kStage] = {}, ev_consumed[kStage] = {}, ev_start = nullptr;
   long long last_h2d = 0, last_d2h = 0;
   // last forward
   int last_launches = 0;
@@ -947,7 +949,7 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (void* p : ctx->allocs) cudaFree(p);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < davo_ctx::kStage; ++i) {
     if (ctx->s_img[i]) cudaFree(ctx->s_img[i]);
     if (ctx->s_flow[i]) cudaFree(ctx->s_flow[i]);
     if (ctx->s_seg[i]) cudaFree(ctx->s_seg[i]);
@@ -1268,9 +1270,13 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   const size_t n_img = hw * 9, n_flow = hw * 8, n_seg = hw * 3;   // elements per sample
   // Host inputs arrive over PCIe more slowly than the stack computes, so what matters is how soon
   // compute can start behind the copy: chunks of 16 samples (8 chunks per 128-sample batch).
-  const int cs = std::max(1, std::min(ctx->mb, 32) / 2);           // samples per chunk
+  int cs = std::max(1, std::min(ctx->mb, 32) / 2);                 // samples per chunk
+  if (const char* e = getenv("DAVO_B200_HOST_CHUNK"))              // experiment knob
+    cs = std::max(1, std::min(atoi(e), std::max(1, ctx->mb / 2)));
+  if (ctx->s_img[0] && ctx->s_chunk != cs) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: chunk size changed");
   if (!ctx->s_img[0]) {
-    for (int i = 0; i < 2; ++i) {
+    ctx->s_chunk = cs;
+    for (int i = 0; i < davo_ctx::kStage; ++i) {
       CU_OK(cudaMalloc((void**)&ctx->s_img[i], n_img * cs));
       CU_OK(cudaMalloc((void**)&ctx->s_flow[i], n_flow * 4 * cs));
       CU_OK(cudaMalloc((void**)&ctx->s_seg[i], n_seg * 4 * cs));
@@ -1302,8 +1308,8 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
     const int minc = std::max(1, cs / 4);
     ns = left > cs + cs / 2 ? cs : left > 2 * minc ? std::min(cs, (left + 1) / 2) : std::min(left, minc);
     last_ns = ns;
-    const int buf = chunk & 1;
-    if (chunk >= 2) CU_OK(cudaStreamWaitEvent(cp, ctx->ev_consumed[buf], 0));
+    const int buf = chunk % davo_ctx::kStage;
+    if (chunk >= davo_ctx::kStage) CU_OK(cudaStreamWaitEvent(cp, ctx->ev_consumed[buf], 0));
     CU_OK(cudaMemcpyAsync(ctx->s_img[buf], img + n_img * s0, n_img * ns, cudaMemcpyHostToDevice, cp));
     h2d += n_img * ns;
     if (need_flow) {
@@ -1340,8 +1346,9 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   ctx->last_npairs_mb = last_n;
   ctx->last_h2d = (long long)h2d;
   ctx->last_d2h = (long long)12 * 4 * B;
-  ctx->last_img = ctx->s_img[(chunk - 1) & 1]; ctx->last_flow = ctx->s_flow[(chunk - 1) & 1];
-  ctx->last_seg = ctx->s_seg[(chunk - 1) & 1]; ctx->last_pose = ctx->s_pose; ctx->last_B = last_ns;
+  const int lastbuf = (chunk - 1) % davo_ctx::kStage;
+  ctx->last_img = ctx->s_img[lastbuf]; ctx->last_flow = ctx->s_flow[lastbuf];
+  ctx->last_seg = ctx->s_seg[lastbuf]; ctx->last_pose = ctx->s_pose; ctx->last_B = last_ns;
   ctx->last_pairs = (pairs == DAVO_PAIRS_TRAJECTORY_FIRST && chunk > 1) ? DAVO_PAIRS_TRAJECTORY : pairs;
   return 0;
 }
