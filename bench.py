@@ -317,7 +317,7 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "pcie_h2d_gbs": pcie_gbs,
-                "pcie_bound": 2 * B / (h2d / (pcie_gbs * 1e9)),
+                "pcie_bound": world * 2 * B / (h2d / (pcie_gbs * 1e9)),
                 "note": "host inputs cross PCIe inside the timed region: pcie_bound = frame pairs / (h2d bytes / "
                         "measured pinned copy rate) is the ceiling of this number on this box"},
         "roofline": roofline, "cpu_baseline": cpu,
