@@ -50,7 +50,8 @@ constexpr int kEpiWarps = 8;
 constexpr int kWBytes = kBlockM * kSlabBytes;       // one weight stage: 16 KB
 
 struct ConvParams {
-  int num_tiles;        // pairs * groups * tiles_h * tiles_w * m_blocks
+  int num_tiles;        // pairs * groups * tiles_h * tiles_w * m_blocks; CLUSTER: work items (see decode_item_cluster)
+  int num_pixel_tiles;  // CLUSTER: pairs * tiles_h * tiles_w
   int tiles_w, tiles_h, groups, m_blocks;
   int Hout, Wout;
   int out_stride;       // floats per output pixel (all groups)
@@ -70,6 +71,28 @@ struct ConvParams {
 
 struct TileCoord { int n, g, mb, h0, w0, t; };
 
+// CLUSTER (2 CTAs): the two CTAs of a cluster walk the same (group, m-block) sequence on two
+// different pixel tiles, so each weight slab is fetched from L2 once: CTA r loads rows
+// [64r, 64r+64) of the slab and multicasts them into both CTAs' rings.  A stage is refilled only
+// after BOTH MMA warps released it (w_empty counts 2; the commit is multicast).  Work item `item`
+// = (pixel-tile pair, group, m-block); with an odd number of pixel tiles the last pair's second
+// CTA repeats the last tile (identical stores).
+template <int NPIX>
+__device__ __forceinline__ TileCoord decode_item_cluster(const ConvParams& p, int item, int rank) {
+  TileCoord c;
+  c.mb = item % p.m_blocks;
+  int r = item / p.m_blocks;
+  c.g = r % p.groups;
+  const int pp = r / p.groups;
+  const int tpi = p.tiles_h * p.tiles_w;
+  const int pix = min(2 * pp + rank, p.num_pixel_tiles - 1);
+  c.t = pix % tpi;
+  c.n = pix / tpi;
+  c.h0 = (c.t / p.tiles_w) * (NPIX / kTileW);
+  c.w0 = (c.t % p.tiles_w) * kTileW;
+  return c;
+}
+
 template <int NPIX>
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
   TileCoord c;
@@ -87,7 +110,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
 
 // STAGED: the store epilogue goes through shared memory and TMA tile stores (one 4-KB buffer per
 // epilogue warp behind the barriers) instead of 32 scalar stores per 32x32 block.
-template <int NPIX, int EPI, bool STAGED = false>
+template <int NPIX, int EPI, bool STAGED = false, bool CLUSTER = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvParams p) {
@@ -111,6 +134,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // known warp-uniform to the compiler
   const int lane = threadIdx.x & 31;
+  const int rank = CLUSTER ? (int)cluster_ctarank() : 0;
+  const int first = CLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int step = CLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto decode = [&](int tile) { return CLUSTER ? decode_item_cluster<NPIX>(p, tile, rank) : decode_tile<NPIX>(p, tile); };
 #ifdef DAVO_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_cta0 = clock64();
@@ -124,7 +151,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_init(&p_full[i], 1);
       mbar_init(&p_empty[i], 1);
       mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
+      mbar_init(&w_empty[i], CLUSTER ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -135,6 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CLUSTER) cluster_sync();          // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -143,8 +171,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       int ps = 0;
       uint32_t pphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile<NPIX>(p, tile);
+      for (int tile = first; tile < p.num_tiles; tile += step) {
+        const TileCoord tc = decode(tile);
         for (int pi = 0; pi < p.n_patches; ++pi) {
           const PatchDesc d = p.patches[pi];
           TWAIT(0, mbar_wait(&p_empty[ps], pphase ^ 1));
@@ -160,13 +188,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       int ws = 0;
       uint32_t wphase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile<NPIX>(p, tile);
+      for (int tile = first; tile < p.num_tiles; tile += step) {
+        const TileCoord tc = decode(tile);
         const int row0 = (tc.g * p.m_blocks + tc.mb) * p.n_taps;
         for (int t = 0; t < p.n_taps; ++t) {            // taps[] is in issue order
           TWAIT(1, mbar_wait(&w_empty[ws], wphase ^ 1));
           mbar_expect_tx(&w_full[ws], kWBytes);
-          tma_load_2d(smem_w + ws * kWBytes, &tmW, &w_full[ws], 0, (row0 + p.taps[t].b_idx) * kBlockM);
+          if constexpr (CLUSTER)      // my half of the slab, into both CTAs (tmW's box is 64 rows here)
+            tma_load_2d_multicast(smem_w + ws * kWBytes + rank * (kWBytes / 2), &tmW, &w_full[ws], 0,
+                                  (row0 + p.taps[t].b_idx) * kBlockM + rank * (kBlockM / 2), (uint16_t)3);
+          else
+            tma_load_2d(smem_w + ws * kWBytes, &tmW, &w_full[ws], 0, (row0 + p.taps[t].b_idx) * kBlockM);
           if (++ws == WS) { ws = 0; wphase ^= 1; }
         }
       }
@@ -183,7 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       int ps = 0, ws = 0;
       uint32_t pphase = 0, wphase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         TWAIT(4, mbar_wait(&acc_empty[acc], acc_phase ^ 1));
@@ -201,7 +233,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             DAVO_MMA_FENCE();
             if (elect_one()) {
               tc_mma_tf32_slab(d, w_lo0 + (uint32_t)ws * (kWBytes / 16), w_hi, x_lo, x_hi, idesc, ti != 0);
-              tc_commit(&w_empty[ws]);        // frees the weight slot when these MMAs retire
+              if constexpr (CLUSTER) tc_commit_multicast(&w_empty[ws], (uint16_t)3);   // both producers wait for both MMA warps
+              else tc_commit(&w_empty[ws]);   // frees the weight slot when these MMAs retire
             }
             if (++ws == WS) { ws = 0; wphase ^= 1; }
           }
@@ -217,10 +250,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = warp > 6 ? 1 : 0;      // which of the quadrant's two warps (store epilogue)
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first; tile < p.num_tiles; tile += step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const TileCoord tc = decode_tile<NPIX>(p, tile);
+      const TileCoord tc = decode(tile);
       const int co = tc.mb * kBlockM + q * 32 + lane;          // this thread's output channel
       const bool co_ok = co < p.cout_g;
       const float bias = co_ok ? __ldg(p.bias + tc.g * p.cout_g + co) : 0.f;
@@ -329,6 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CLUSTER) cluster_sync();          // the peer may still be writing my ring / arriving on my barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

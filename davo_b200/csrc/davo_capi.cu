@@ -93,6 +93,7 @@ struct Layer {
   int npix = 128;              // output pixels per tile: 128 = 16x8 (pm, or cm on short maps), 256 = 32x8
   int m_blocks = 1;            // cm: 128-channel blocks per group
   bool cm_staged = false;      // cm: store epilogue through shared memory + TMA tile stores
+  bool cm_cluster = false;     // cm: 2-CTA clusters, each weight slab fetched once and multicast
   bool b_resident = false;     // pm: all weight slabs stay in shared memory
   int wide_G = 0;              // pm, column-widened: output pixels per M row (0 = off)
   int wide_tw = 0;             //   runs per tile row (tile = 128/wide_tw rows x wide_tw runs)
@@ -100,6 +101,7 @@ struct Layer {
   int smem_bytes = 0;
   CUtensorMap tmA, tmB;          // activation (patch) map, weight map
   CUtensorMap tmO;               // pm store epilogue: output tiles (TMA store)
+  CUtensorMap tmB64;             // cm clusters: weight map with a 64-row box (half a slab per CTA)
   pm::ConvParams prm_pm;
   cm::ConvParams prm_cm;
 };
@@ -523,6 +525,16 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(weights) -> %d", L.name, (int)r);
+    L.tmB64 = L.tmB;
+    const char* cl_env = getenv("DAVO_B200_CLUSTER");            // debug: "0" switches the clusters off
+    L.cm_cluster = L.orient == 1 && L.epi == EPI_STORE_RELU && !(cl_env && !strcmp(cl_env, "0"));
+    if (L.cm_cluster) {
+      const cuuint32_t box64[2] = {32, (cuuint32_t)(rows_per_slab / 2)};
+      r = enc(&L.tmB64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, L.d_wpack, dims, strides, box64, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(weights, half slab) -> %d", L.name, (int)r);
+    }
   }
   L.tmO = L.tmA;
   if ((L.orient == 1 && L.cm_staged) || (L.orient == 0 && L.epi == EPI_STORE_RELU && L.BN >= 32))
@@ -756,7 +768,46 @@ int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   return 0;
 }
 
+// 2-CTA clusters, weights multicast (conv_cm.cuh: CLUSTER).
+template <int NPIX, bool STAGED>
+int launch_cm_cluster(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  auto* kern = cm::conv_tc_kernel<NPIX, EPI_STORE_RELU, STAGED, true>;
+  static int attr_smem = 0, max_clusters = 0;
+  if (attr_smem < L.smem_bytes) {
+    CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
+    attr_smem = L.smem_bytes;
+    max_clusters = 0;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.blockDim = dim3(cm::kThreads); cfg.dynamicSmemBytes = L.smem_bytes; cfg.stream = st;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3(ctx->num_sms & ~1);
+    CU_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    if (max_clusters <= 0) return fail(ctx, DAVO_ERR_CUDA, "%s: no 2-CTA cluster fits", L.name);
+    if (getenv("DAVO_B200_VERBOSE")) fprintf(stderr, "[davo_b200] %s: %d active 2-CTA clusters\n", L.name, max_clusters);
+  }
+  cm::ConvParams P = L.prm_cm;
+  P.num_pixel_tiles = npairs * L.tiles_h * L.tiles_w;
+  P.num_tiles = ((P.num_pixel_tiles + 1) / 2) * L.groups * L.m_blocks;
+  P.out = L.d_out;
+  P.sum_out = ctx->d_sum7;
+  const int clusters = P.num_tiles < max_clusters ? P.num_tiles : max_clusters;
+  cfg.gridDim = dim3(2 * clusters);
+  CU_OK(cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB64, L.tmO, P));
+  return 0;
+}
+
 int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  if (L.orient == 1 && L.cm_cluster) {
+    if (L.cm_staged)
+      return L.npix == 256 ? launch_cm_cluster<256, true>(ctx, L, npairs, st) : launch_cm_cluster<128, true>(ctx, L, npairs, st);
+    return L.npix == 256 ? launch_cm_cluster<256, false>(ctx, L, npairs, st) : launch_cm_cluster<128, false>(ctx, L, npairs, st);
+  }
   if (L.orient == 1) {
     if (L.epi == EPI_SUM_RELU)
       return L.npix == 256 ? launch_cm_t<256, EPI_SUM_RELU>(ctx, L, npairs, st)

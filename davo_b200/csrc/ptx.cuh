@@ -68,6 +68,26 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// ---- 2-CTA clusters: one weight slab fetched from L2 once and written into both CTAs ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// The box lands at the same shared-memory offset in every CTA of `cta_mask`, and each of those
+// CTAs' mbarrier at the offset of `bar` receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* m, uint64_t* bar,
+                                                      int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
 // Tile store shared -> global (bulk async group); out-of-bounds parts of the box are clipped.
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1,
                                              int c2, int c3) {
@@ -170,6 +190,14 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
 }
 __device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) {
   return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+}
+// Same, arriving on the mbarrier at that offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
