@@ -130,6 +130,7 @@ struct davo_ctx {
   float *d_se5w = nullptr, *d_se5part = nullptr, *d_se5scale = nullptr, *d_se5out = nullptr;
   unsigned int* d_se5cnt = nullptr;
   int nparts7 = 0;
+  int nbr = 2;                      // pose branches: 2 (rotation, translation: decouple nets) or 1 (couple nets)
   // host-buffer entry point staging
   static constexpr int kStage = 3;  // staging buffers: copy of chunk i+2 never waits for compute of chunk i
   uint8_t* s_img[kStage] = {};
@@ -489,7 +490,10 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     const int fixed = 1024 /*alignment*/ + kBarrierBytes + (L.cm_staged ? cm::kEpiWarps * 4096 : 0);
     const int avail = kSmemBudget - fixed;
     P.p_stages = patch_stage <= 40 * 1024 ? 3 : 2;
-    if (P.p_stages == 3 && (avail - 3 * patch_stage) / cm::kWBytes < 4) P.p_stages = 2;
+    if (const char* e = getenv("DAVO_B200_CM_PSTAGES")) P.p_stages = std::max(2, atoi(e));   // experiment knob
+    // A third patch stage pays when at least five weight stages remain (cnv5: P3 W5, 0.610 -> 0.589 ms).
+    if (!getenv("DAVO_B200_CM_PSTAGES") && P.p_stages == 2 && (avail - 3 * patch_stage) / cm::kWBytes >= 5) P.p_stages = 3;
+    if (P.p_stages >= 3 && (avail - P.p_stages * patch_stage) / cm::kWBytes < 4) P.p_stages = 2;
     P.w_stages = std::min(kMaxStages, (avail - P.p_stages * patch_stage) / cm::kWBytes);
     if (P.w_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: shared-memory plan does not fit", L.name);
     L.smem_bytes = fixed + P.w_stages * cm::kWBytes + P.p_stages * patch_stage;
@@ -858,11 +862,11 @@ int launch_conv_direct(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t s
 }
 
 __global__ void sum7_direct_kernel(const float* in, int hw, int nparts, float* out) {
-  // in [n][hw][512] -> out [n][2][nparts][256]; row 0 holds the sum, the rest zeros.
-  const int n = blockIdx.x, br = blockIdx.y, c = threadIdx.x;
+  // in [n][hw][nbr*256] -> out [n][nbr][nparts][256]; row 0 holds the sum, the rest zeros.
+  const int n = blockIdx.x, br = blockIdx.y, nbr = gridDim.y, c = threadIdx.x;
   float a = 0.f;
-  for (int i = 0; i < hw; ++i) a += in[((size_t)n * hw + i) * 512 + br * 256 + c];
-  float* o = out + ((size_t)(n * 2 + br) * nparts) * 256 + c;
+  for (int i = 0; i < hw; ++i) a += in[((size_t)n * hw + i) * nbr * 256 + br * 256 + c];
+  float* o = out + ((size_t)(n * nbr + br) * nparts) * 256 + c;
   o[0] = a;
   for (int i = 1; i < nparts; ++i) o[(size_t)i * 256] = 0.f;
 }
@@ -898,7 +902,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
 int launch_head(davo_ctx* ctx, int pair_mode, int pair0, int npairs, float* pose_out, cudaStream_t st, int* launches) {
   const Layer& L7 = ctx->layers.back();
   HeadParams hp;
-  hp.pair0 = pair0; hp.npairs = npairs; hp.pair_mode = pair_mode; hp.nparts = ctx->nparts7;
+  hp.pair0 = pair0; hp.npairs = npairs; hp.pair_mode = pair_mode; hp.nparts = ctx->nparts7; hp.nbr = ctx->nbr;
   hp.inv_hw = 1.0f / (float)(L7.Hout * L7.Wout);
   hp.sums = ctx->d_sum7; hp.wpred = ctx->d_wpred; hp.bpred = ctx->d_bpred; hp.pose_out = pose_out;
   head_kernel<<<npairs, 256, 0, st>>>(hp);
@@ -914,7 +918,7 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
     Layer& L = ctx->layers[li];
     if (li == 5 && ctx->cfg.posenn_se == 1) {      // -se_insert: excite cnv5 per branch in front of cnv6
       Se5Params sp;
-      sp.npairs = npairs; sp.hw = L.Hin * L.Win;
+      sp.npairs = npairs; sp.hw = L.Hin * L.Win; sp.nbr = ctx->nbr;
       sp.cnv5 = ctx->layers[4].d_out; sp.w = ctx->d_se5w; sp.part = ctx->d_se5part; sp.count = ctx->d_se5cnt;
       sp.scale = ctx->d_se5scale; sp.out = ctx->d_se5out;
       se5_excite_kernel<<<dim3(kSe5Splits, npairs), 256, 0, st>>>(sp);
@@ -930,7 +934,7 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
   }
   const Layer& L7 = ctx->layers.back();
   if (ctx->conv_impl != 0) {
-    sum7_direct_kernel<<<dim3(npairs, 2), 256, 0, st>>>(ctx->d_c7tmp, L7.Hout * L7.Wout, ctx->nparts7, ctx->d_sum7);
+    sum7_direct_kernel<<<dim3(npairs, ctx->nbr), 256, 0, st>>>(ctx->d_c7tmp, L7.Hout * L7.Wout, ctx->nparts7, ctx->d_sum7);
     CU_OK(cudaGetLastError());
     ++*launches;
   }
@@ -957,8 +961,9 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   davo_ctx* ctx = nullptr;   // errors before allocation go to the thread-local slot
   if (!cfg || !out) return fail(nullptr, DAVO_ERR_ARG, "davo_create: null argument");
   *out = nullptr;
-  if (cfg->posenn != 0)
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d is not built (only decouple_sharednet_v0_dilation)", cfg->posenn);
+  if (cfg->posenn != 0 && cfg->posenn != 1)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d is not built (only the shared dilated nets: "
+                "decouple_sharednet_v0_dilation, couple_sharednet_v0_dilation)", cfg->posenn);
   if (cfg->posenn_se != 0 && cfg->posenn_se != 1)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built (only -se_insert)", cfg->posenn_se);
   if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
@@ -1039,16 +1044,19 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   // ---- activation geometry (TF SAME) ----
   struct Geo { int k, stride, dil; };
   const Geo geo[7] = {{7, 2, 1}, {5, 2, 1}, {3, 1, 2}, {3, 1, 4}, {3, 1, 8}, {3, 1, 2}, {3, 2, 1}};
-  const int cout_total[7] = {16, 32, 64, 128, 256, 2 * c6, 512};
-  const int bn[7] = {16, 32, 64, 128, 256, (c.posenn_se == 1 ? 1 : 2) * c6, 256};
-  const int groups[7] = {1, 1, 1, 1, 1, c.posenn_se == 1 ? 2 : 1, 2};
+  // couple nets (posenn.py:133-187): one branch, pred 256 -> 6; decouple nets: rotation | translation
+  const int nbr = c.posenn == 1 ? 1 : 2;
+  ctx->nbr = nbr;
+  const int cout_total[7] = {16, 32, 64, 128, 256, nbr * c6, nbr * 256};
+  const int bn[7] = {16, 32, 64, 128, 256, (c.posenn_se == 1 ? 1 : nbr) * c6, 256};
+  const int groups[7] = {1, 1, 1, 1, 1, c.posenn_se == 1 ? nbr : 1, nbr};
   // -se_insert: cnv6 reads two differently scaled copies of cnv5 (one per branch): a grouped layer
   const bool se5 = c.posenn_se == 1;
   // Packed PoseNN input (frontend.cuh: pack_kernel): 8 channels per pixel when the width allows the
   // column-widened cnv1 plan (runs of 16 input pixels), else the 16-channel layout of the plain plan.
   const char* wide_env0 = getenv("DAVO_B200_WIDE");
   ctx->packed_c = ((c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
-  const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? 512 : 256, 2 * c6};
+  const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? nbr * 256 : 256, nbr * c6};
   const int cin_g[7] = {ctx->packed_c, 16, 32, 64, 128, 256, c6};
   const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c6};
   const char* names[7] = {"cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6", "cnv7"};
@@ -1133,7 +1141,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5part, (size_t)mb * kSe5Splits * 256 * 4)) return rc;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5cnt, (size_t)mb * 4)) return rc;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5scale, (size_t)mb * 2 * 256 * 4)) return rc;
-      if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5out, (size_t)mb * hw5 * 512 * 4)) return rc;
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5out, (size_t)mb * hw5 * nbr * 256 * 4)) return rc;
       prev = ctx->d_se5out;
     }
     L.d_in = prev;
@@ -1145,7 +1153,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   {
     const Layer& L7 = ctx->layers[6];
     ctx->nparts7 = L7.tiles_h * L7.tiles_w * (L7.orient == 0 ? 4 : 1);
-    if (int rc = dev_alloc(ctx, (void**)&ctx->d_sum7, (size_t)mb * 2 * ctx->nparts7 * 256 * 4)) return rc;
+    if (int rc = dev_alloc(ctx, (void**)&ctx->d_sum7, (size_t)mb * nbr * ctx->nparts7 * 256 * 4)) return rc;
   }
 
   // ---- weights ----
@@ -1166,13 +1174,15 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     if (int rc = L.wide_G ? plan_layer_wide(ctx, L, getw, b->data) : plan_layer(ctx, L, getw, b->data)) return rc;
   }
   const char* brs[2] = {"rotation", "translation"};
+  // variable scope of branch g under pose_exp_net/: pose/rotation/, pose/translation/ (decouple) or pose/ (couple)
+  auto branch_scope = [&](int g) { return nbr == 2 ? std::string("pose/") + brs[g] + "/" : std::string("pose/"); };
   {
     Layer& L = ctx->layers[5];
     const HostTensor *w[2], *b[2];
-    for (int g = 0; g < 2; ++g)
-      if (int rc = need_conv(std::string("pose/") + brs[g] + "/cnv6", 3, 256, c6, &w[g], &b[g])) return rc;
-    std::vector<float> bias(2 * c6);
-    for (int n = 0; n < 2 * c6; ++n) bias[n] = b[n / c6]->data[n % c6];
+    for (int g = 0; g < nbr; ++g)
+      if (int rc = need_conv(branch_scope(g) + "cnv6", 3, 256, c6, &w[g], &b[g])) return rc;
+    std::vector<float> bias(nbr * c6);
+    for (int n = 0; n < nbr * c6; ++n) bias[n] = b[n / c6]->data[n % c6];
     if (se5) {      // two groups: branch g convolves its own scaled copy of cnv5
       auto getw = [&](int g, int ty, int tx, int ci, int n) {
         return w[g]->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + n];
@@ -1189,8 +1199,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   if (se5) {
     // reference nets/posenn.py:227: variables pose/<branch>/cnv5_se_attention/{bottleneck_fc,recover_fc}
     std::vector<float> sw;
-    for (int g = 0; g < 2; ++g) {
-      const std::string S = P + "pose/" + brs[g] + "/cnv5_se_attention/";
+    for (int g = 0; g < nbr; ++g) {
+      const std::string S = P + branch_scope(g) + "cnv5_se_attention/";
       const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
       const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
       const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
@@ -1208,23 +1218,25 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   {
     Layer& L = ctx->layers[6];
     const HostTensor *w[2], *b[2];
-    for (int g = 0; g < 2; ++g)
-      if (int rc = need_conv(std::string("pose/") + brs[g] + "/cnv7", 3, c6, 256, &w[g], &b[g])) return rc;
+    for (int g = 0; g < nbr; ++g)
+      if (int rc = need_conv(branch_scope(g) + "cnv7", 3, c6, 256, &w[g], &b[g])) return rc;
     auto getw = [&](int g, int ty, int tx, int ci, int n) {
       return w[g]->data[(((size_t)ty * 3 + tx) * c6 + ci) * 256 + n];
     };
-    std::vector<float> bias(512);
-    for (int n = 0; n < 512; ++n) bias[n] = b[n / 256]->data[n % 256];
+    std::vector<float> bias(nbr * 256);
+    for (int n = 0; n < nbr * 256; ++n) bias[n] = b[n / 256]->data[n % 256];
     if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
-    if (int rc = dev_alloc(ctx, (void**)&ctx->d_c7tmp, (size_t)mb * L.Hout * L.Wout * 512 * 4)) return rc;
+    if (int rc = dev_alloc(ctx, (void**)&ctx->d_c7tmp, (size_t)mb * L.Hout * L.Wout * nbr * 256 * 4)) return rc;
   }
   {
-    std::vector<float> wp(2 * 256 * 3), bp(6);
-    for (int g = 0; g < 2; ++g) {
+    // pred: [256, 3] per branch (decouple, posenn.py:240) or [256, 6] (couple, :181); stored [br][256][6/nbr]
+    const int per = 6 / nbr;
+    std::vector<float> wp(256 * 6), bp(6);
+    for (int g = 0; g < nbr; ++g) {
       const HostTensor *w, *b;
-      if (int rc = need_conv(std::string("pose/") + brs[g] + "/pred", 1, 256, 3, &w, &b)) return rc;
-      for (int i = 0; i < 768; ++i) wp[g * 768 + i] = w->data[i];
-      for (int j = 0; j < 3; ++j) bp[g * 3 + j] = b->data[j];
+      if (int rc = need_conv(branch_scope(g) + "pred", 1, 256, per, &w, &b)) return rc;
+      for (int i = 0; i < 256 * per; ++i) wp[g * 256 * per + i] = w->data[i];
+      for (int j = 0; j < per; ++j) bp[g * per + j] = b->data[j];
     }
     if (int rc = dev_alloc(ctx, (void**)&ctx->d_wpred, wp.size() * 4)) return rc;
     if (int rc = dev_alloc(ctx, (void**)&ctx->d_bpred, bp.size() * 4)) return rc;
@@ -1435,16 +1447,17 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
   else if (s == "cnv7_sum") {
     // reduce the deterministic partials on the host
     const int np = ctx->nparts7;
-    std::vector<float> tmp((size_t)2 * np * 256);
-    CU_OK(cudaMemcpy(tmp.data(), ctx->d_sum7 + (size_t)pair * 2 * np * 256, tmp.size() * 4, cudaMemcpyDeviceToHost));
-    if (cap < 512) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: buffer too small");
-    for (int br = 0; br < 2; ++br)
+    const int nbr = ctx->nbr;
+    std::vector<float> tmp((size_t)nbr * np * 256);
+    CU_OK(cudaMemcpy(tmp.data(), ctx->d_sum7 + (size_t)pair * nbr * np * 256, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    if (cap < nbr * 256) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: buffer too small");
+    for (int br = 0; br < nbr; ++br)
       for (int ch = 0; ch < 256; ++ch) {
         float a = 0.f;
         for (int i = 0; i < np; ++i) a += tmp[((size_t)br * np + i) * 256 + ch];
         out[br * 256 + ch] = a;
       }
-    *n_out = 512;
+    *n_out = nbr * 256;
     return 0;
   } else {
     for (int i = 0; i < 6; ++i)

@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
 
 struct HeadParams {
   int pair0, npairs, pair_mode;
+  int nbr;                // branches: 2 (rotation, translation; pred 256 -> 3 each) or 1 (couple nets; pred 256 -> 6)
   int nparts;             // partial rows per (pair, branch) = tiles * 4
   float inv_hw;           // 1 / (H7 * W7)
   const float* sums;      // [mb][2][nparts][256]
@@ -400,8 +401,8 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __shared__ float s_mean[2][256];
   const int pl = blockIdx.x;
   const int c = threadIdx.x;
-  for (int br = 0; br < 2; ++br) {
-    const float* src = p.sums + ((size_t)(pl * 2 + br) * p.nparts) * 256 + c;
+  for (int br = 0; br < p.nbr; ++br) {
+    const float* src = p.sums + ((size_t)(pl * p.nbr + br) * p.nparts) * 256 + c;
     float a = 0.f;
     for (int i = 0; i < p.nparts; ++i) a += src[(size_t)i * 256];
     s_mean[br][c] = a * p.inv_hw;
@@ -409,15 +410,16 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < 6) {
-    const int br = warp / 3, j = warp % 3;
+    const int per = 6 / p.nbr;                   // outputs per branch
+    const int br = warp / per, j = warp % per;   // output warp = [rz ry rx | tx ty tz] either way (posenn.py:248-250, :183)
     float a = 0.f;
-    for (int i = lane; i < 256; i += 32) a += s_mean[br][i] * p.wpred[(br * 256 + i) * 3 + j];
+    for (int i = lane; i < 256; i += 32) a += s_mean[br][i] * p.wpred[(br * 256 + i) * per + j];
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) {
       int b, k;
       pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
-      p.pose_out[(size_t)(b * 2 + k) * 6 + br * 3 + j] = 0.01f * (a + p.bpred[br * 3 + j]);
+      p.pose_out[(size_t)(b * 2 + k) * 6 + warp] = 0.01f * (a + p.bpred[br * per + j]);
     }
   }
 }
@@ -432,12 +434,13 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
 constexpr int kSe5Splits = 32;
 struct Se5Params {
   int npairs, hw;               // pixels of the cnv5 map
+  int nbr;                      // branches (2: rotation then translation; 1: couple nets)
   const float* cnv5;            // [mb][hw][256]
   const float* w;               // per branch: W1[256][32] b1[32] W2[32][256] b2[256]
   float* part;                  // [mb][kSe5Splits][256]
   unsigned int* count;          // [mb]
-  float* scale;                 // [mb][2][256]: exc_r, exc_r * exc_t
-  float* out;                   // [mb][hw][512]: cnv5 * scale[0] | cnv5 * scale[1], TF32-rounded
+  float* scale;                 // [mb][nbr][256]: exc_r, exc_r * exc_t
+  float* out;                   // [mb][hw][nbr*256]: cnv5 * scale[0] | cnv5 * scale[1], TF32-rounded
 };
 constexpr int kSe5BranchFloats = 256 * 32 + 32 + 32 * 256 + 256;
 
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
   for (int sp = 0; sp < kSe5Splits; ++sp) m += __ldcg(p.part + ((size_t)pl * kSe5Splits + sp) * 256 + c);
   m *= 1.0f / (float)p.hw;
   float scale = 1.0f;
-  for (int br = 0; br < 2; ++br) {
+  for (int br = 0; br < p.nbr; ++br) {
     const float* W1 = p.w + br * kSe5BranchFloats;       // [256][32]
     const float* b1 = W1 + 256 * 32;
     const float* W2 = b1 + 32;                           // [32][256]
@@ -482,7 +485,7 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
     float e = b2[c];
     for (int j = 0; j < 32; ++j) e += s_hid[j] * W2[j * 256 + c];
     scale *= 1.0f / (1.0f + expf(-e));
-    p.scale[((size_t)pl * 2 + br) * 256 + c] = scale;
+    p.scale[((size_t)pl * p.nbr + br) * 256 + c] = scale;
     __syncthreads();
   }
 }
@@ -496,10 +499,9 @@ __global__ void __launch_bounds__(256) se5_scale_kernel(const Se5Params p) {
   const long long pix = idx >> 6;                         // global pixel index over the pass
   const int pl = (int)(pix / p.hw);
   const float4 v = __ldg(reinterpret_cast<const float4*>(p.cnv5) + pix * 64 + c4);
-  float4* o = reinterpret_cast<float4*>(p.out) + pix * 128 + c4;
-#pragma unroll
-  for (int br = 0; br < 2; ++br) {
-    const float4 sc = *reinterpret_cast<const float4*>(p.scale + ((size_t)pl * 2 + br) * 256 + c4 * 4);
+  float4* o = reinterpret_cast<float4*>(p.out) + pix * 64 * p.nbr + c4;
+  for (int br = 0; br < p.nbr; ++br) {
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + ((size_t)pl * p.nbr + br) * 256 + c4 * 4);
     o[br * 64] = make_float4(round_tf32(v.x * sc.x), round_tf32(v.y * sc.y), round_tf32(v.z * sc.z),
                              round_tf32(v.w * sc.w));
   }

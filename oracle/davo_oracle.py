@@ -188,6 +188,48 @@ def decouple_sharednet_v0_dilation(tgt: torch.Tensor, src: torch.Tensor,
     return pose, (c6s["rotation"], c6s["translation"])
 
 
+def couple_sharednet_v0_dilation(tgt: torch.Tensor, src: torch.Tensor,
+                                 wts: Dict[str, torch.Tensor], se_attention=False,
+                                 tf32: bool = False,
+                                 taps: Optional[Dict[str, torch.Tensor]] = None
+                                 ) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+    """nets/posenn.py:133-187 (dropout=False, batch_norm=False): the same shared trunk, ONE pose
+    branch under scope ``pose/``: cnv6, cnv7, pred 256 -> 6; pose = 0.01 * mean (:181-184).
+
+    Returns (pose [B,1,6], (cnv6, cnv6)).
+    """
+    P = "pose_exp_net/"
+
+    def cv(x, name, stride=1, rate=1, relu=True):
+        return conv2d_same(x, wts[P + name + "/weights"], wts[P + name + "/biases"],
+                           stride=stride, rate=rate, relu=relu, tf32=tf32)
+
+    x = torch.cat([tgt, src], dim=3)                                     # :142
+    c1 = cv(x, "cnv1", stride=2)                                         # :153
+    c2 = cv(c1, "cnv2", stride=2)
+    c3 = cv(c2, "cnv3", rate=2)
+    c4 = cv(c3, "cnv4", rate=4)
+    c5 = cv(c4, "cnv5", rate=8)                                          # :157
+    if taps is not None:
+        taps.update(input=x, cnv1=c1, cnv2=c2, cnv3=c3, cnv4=c4, cnv5=c5)
+    if se_attention is True:                                             # :163-166
+        c5 = se_block(c5, wts, P + "pose/cnv5_se_attention", "relu")
+        c6 = cv(c5, "pose/cnv6", rate=2)
+    elif se_attention == "se_skipadd":                                   # :167-171
+        c6 = cv(c5, "pose/cnv6", rate=2)
+        c6 = torch.relu(c5 + se_block(c6, wts, P + "pose/cnv6_se_attention", "relu"))
+    elif se_attention == "se_replace":                                   # :172-174
+        c6 = se_block(c5, wts, P + "pose/cnv6_se_attention", "relu")
+    else:
+        c6 = cv(c5, "pose/cnv6", rate=2)                                 # :176
+    c7 = cv(c6, "pose/cnv7", stride=2)                                   # :177
+    pred = cv(c7, "pose/pred", relu=False)                               # :178
+    if taps is not None:
+        taps.update(cnv6_rotation=c6, cnv7_rotation=c7, pred_rotation=pred)
+    pose = 0.01 * pred.mean(dim=(1, 2)).reshape(-1, 1, 6)                # :179-181
+    return pose, (c6, c6)
+
+
 # --------------------------------------------------------------------------- #
 # Whole inference graph
 # --------------------------------------------------------------------------- #
@@ -233,11 +275,12 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
         se_attention = False
     input_images = [tgt, src0, src1, tgt]                                # davo.py:1019-1024
     # 1. PoseNN type (davo.py:1027-1049)
+    pose_net = decouple_sharednet_v0_dilation
     if "-sharedNN" in version:
         if "-dilatedPoseNN" in version:
             pass
         elif "-dilatedCouplePoseNN" in version:
-            _unsupported("couple_sharednet_v0_dilation")
+            pose_net = couple_sharednet_v0_dilation
         elif "-couplePoseNN" in version:
             raise NameError("not support `-sharedNN-couplePoseNN' mode.")
         else:
@@ -343,10 +386,8 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
     # 4.2 PoseNN x2 with shared weights (davo.py:1453-1458)
     t0 = {} if taps is not None else None
     t1 = {} if taps is not None else None
-    pose0, _ = decouple_sharednet_v0_dilation(input_images[0], input_images[1], wts,
-                                              se_attention, tf32, t0)
-    pose1, _ = decouple_sharednet_v0_dilation(input_images[3], input_images[2], wts,
-                                              se_attention, tf32, t1)
+    pose0, _ = pose_net(input_images[0], input_images[1], wts, se_attention, tf32, t0)
+    pose1, _ = pose_net(input_images[3], input_images[2], wts, se_attention, tf32, t1)
     pred_poses = torch.cat([pose0, pose1], dim=-2)                       # davo.py:1458
     if taps is not None:
         taps["attention_maps"] = [a.numpy() for a in (a_tgt, a_s0, a_s1)]

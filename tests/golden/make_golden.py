@@ -27,6 +27,8 @@ CASES = {
     "se_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_seg-fc_tanh",
     "se_rgb_to_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_rgb_wo_tgt_to_seg-fc_tanh",
     "se_insert": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-no_segmask-se_insert",
+    "couple_shared": "v1-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh",
+    "couple_shared_se_insert": "v1-sharedNN-dilatedCouplePoseNN-cnv6_64-no_segmask-se_insert",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)
 
@@ -44,6 +46,8 @@ def main():
             out[key + "/att_w"] = np.stack(taps["attention_weights"][1:], 1)     # [B,2,19] src0, src1
         # per-layer checksums (mean and mean-abs) of pair 0 / sample 0
         for name in ("input", "cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6_rotation", "cnv7_translation"):
+            if name not in taps["pair0"]:
+                continue                         # couple nets have a single branch
             a = taps["pair0"][name][0]
             out[key + "/stat/" + name] = np.array([a.mean(), np.abs(a).mean(), a.max()])
         print(key, pose[0, 0])
