@@ -131,6 +131,8 @@ struct davo_ctx {
   unsigned int* d_se5cnt = nullptr;
   int nparts7 = 0;
   int nbr = 2;                      // pose branches: 2 (rotation, translation: decouple nets) or 1 (couple nets)
+  bool unit_sample = false;         // non-shared nets: one evaluation per sample on (tgt, src0, src1)
+  int max_units() const { return unit_sample ? cfg.max_batch : 2 * cfg.max_batch; }
   // host-buffer entry point staging
   static constexpr int kStage = 3;  // staging buffers: copy of chunk i+2 never waits for compute of chunk i
   uint8_t* s_img[kStage] = {};
@@ -877,6 +879,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   FrontParams fp;
   memset(&fp, 0, sizeof fp);
   fp.H = c.H; fp.W = c.W; fp.pair0 = pair0; fp.npairs = npairs; fp.pair_mode = pair_mode;
+  fp.unit_sample = ctx->unit_sample ? 1 : 0;
   fp.packed_c = ctx->packed_c;
   fp.in_mode = c.in_mode; fp.att_src = c.att_src; fp.att_tgt_ones = c.att_tgt_ones;
   fp.mask_rgb = c.mask_mode != 0;
@@ -888,11 +891,13 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   if (c.att_src == 1 || c.att_src >= 3) {
     static const int se_dims[5][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}};
     fp.se_in = se_dims[c.att_src][0]; fp.se_hid = se_dims[c.att_src][1];
-    se_pool_kernel<<<dim3(kPoolSplits, npairs, c.att_tgt_ones ? 1 : 2), 256, 0, st>>>(fp);
+    const int src_frames = ctx->unit_sample ? 2 : 1;
+    se_pool_kernel<<<dim3(kPoolSplits, npairs, src_frames + (c.att_tgt_ones ? 0 : 1)), 256, 0, st>>>(fp);
     CU_OK(cudaGetLastError());
     ++*launches;
   }
-  if (ctx->packed_c == 8) pack8_kernel<<<dim3(kPack8Blocks, npairs), 256, 0, st>>>(fp);
+  if (ctx->unit_sample) pack_sample_kernel<<<dim3(kPackBlocksPerPair, npairs), 256, 0, st>>>(fp);
+  else if (ctx->packed_c == 8) pack8_kernel<<<dim3(kPack8Blocks, npairs), 256, 0, st>>>(fp);
   else pack_kernel<<<dim3(kPackBlocksPerPair, npairs), 256, 0, st>>>(fp);
   CU_OK(cudaGetLastError());
   ++*launches;
@@ -903,6 +908,7 @@ int launch_head(davo_ctx* ctx, int pair_mode, int pair0, int npairs, float* pose
   const Layer& L7 = ctx->layers.back();
   HeadParams hp;
   hp.pair0 = pair0; hp.npairs = npairs; hp.pair_mode = pair_mode; hp.nparts = ctx->nparts7; hp.nbr = ctx->nbr;
+  hp.nsrc = ctx->unit_sample ? 2 : 1;
   hp.inv_hw = 1.0f / (float)(L7.Hout * L7.Wout);
   hp.sums = ctx->d_sum7; hp.wpred = ctx->d_wpred; hp.bpred = ctx->d_bpred; hp.pose_out = pose_out;
   head_kernel<<<npairs, 256, 0, st>>>(hp);
@@ -941,8 +947,9 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
   return launch_head(ctx, pair_mode, pair0, npairs, pose_out, st, launches);
 }
 
+constexpr int kUnitsAreSamples = 3;     // pair_of_slot mode of the non-shared nets
 int pairs_selected(int pairs, int B) {
-  return pairs == DAVO_PAIRS_ALL ? 2 * B : pairs == DAVO_PAIRS_TRAJECTORY ? B : B + 1;
+  return pairs == DAVO_PAIRS_ALL ? 2 * B : (pairs == DAVO_PAIRS_TRAJECTORY || pairs == kUnitsAreSamples) ? B : B + 1;
 }
 
 }  // namespace
@@ -961,9 +968,9 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   davo_ctx* ctx = nullptr;   // errors before allocation go to the thread-local slot
   if (!cfg || !out) return fail(nullptr, DAVO_ERR_ARG, "davo_create: null argument");
   *out = nullptr;
-  if (cfg->posenn != 0 && cfg->posenn != 1)
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d is not built (only the shared dilated nets: "
-                "decouple_sharednet_v0_dilation, couple_sharednet_v0_dilation)", cfg->posenn);
+  if (cfg->posenn < 0 || cfg->posenn > 3)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d is not built (only the four dilated nets, "
+                "posenn.py:12-254)", cfg->posenn);
   if (cfg->posenn_se != 0 && cfg->posenn_se != 1)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built (only -se_insert)", cfg->posenn_se);
   if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
@@ -993,7 +1000,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   // partial wave of every layer (measured: 62 k pairs/s at 34, 73 k at 256); 256 pairs keep the
   // workspace at 3.6 GB.
   int mb = cfg->micro_batch > 0 ? cfg->micro_batch : 256;
-  if (mb > 2 * cfg->max_batch) mb = 2 * cfg->max_batch;
+  ctx->unit_sample = cfg->posenn >= 2;
+  if (mb > ctx->max_units()) mb = ctx->max_units();
   ctx->mb = mb;
   if (const char* cr = getenv("DAVO_B200_WEIGHT_ROUNDING"))     // "nearest": plain round-to-nearest
     ctx->compensated_rounding = strcmp(cr, "nearest") != 0;
@@ -1039,13 +1047,15 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   const int mb = ctx->mb;
   const std::string P = "pose_exp_net/";
   const int c6 = c.cnv6_out;
-  const int cin1 = c.in_mode == 1 ? 10 : 6;
+  // cnv1 input channels of the reference: (rgb [+ flow]) x (tgt + sources), posenn.py:21, 198
+  const int cin1 = (c.in_mode == 1 ? 5 : 3) * (1 + (c.posenn >= 2 ? 2 : 1));
 
   // ---- activation geometry (TF SAME) ----
   struct Geo { int k, stride, dil; };
   const Geo geo[7] = {{7, 2, 1}, {5, 2, 1}, {3, 1, 2}, {3, 1, 4}, {3, 1, 8}, {3, 1, 2}, {3, 2, 1}};
   // couple nets (posenn.py:133-187): one branch, pred 256 -> 6; decouple nets: rotation | translation
-  const int nbr = c.posenn == 1 ? 1 : 2;
+  const int nbr = (c.posenn == 1 || c.posenn == 3) ? 1 : 2;
+  const int nsrc = ctx->unit_sample ? 2 : 1;      // poses per evaluation (num_source, posenn.py:19, 76, 140, 196)
   ctx->nbr = nbr;
   const int cout_total[7] = {16, 32, 64, 128, 256, nbr * c6, nbr * 256};
   const int bn[7] = {16, 32, 64, 128, 256, (c.posenn_se == 1 ? 1 : nbr) * c6, 256};
@@ -1055,7 +1065,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   // Packed PoseNN input (frontend.cuh: pack_kernel): 8 channels per pixel when the width allows the
   // column-widened cnv1 plan (runs of 16 input pixels), else the 16-channel layout of the plain plan.
   const char* wide_env0 = getenv("DAVO_B200_WIDE");
-  ctx->packed_c = ((c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
+  ctx->packed_c = (!ctx->unit_sample && (c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
   const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? nbr * 256 : 256, nbr * c6};
   const int cin_g[7] = {ctx->packed_c, 16, 32, 64, 128, 256, c6};
   const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c6};
@@ -1113,12 +1123,24 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     if (L.wide_G == 0 && ctx->packed_c == 8)
       return fail(ctx, DAVO_ERR_ARG, "cnv1: 8-channel packed input needs the widened plan");
     for (int j = 0; j < 16; ++j) L.pc2w[j] = -1;
-    const int rgb_src = ctx->packed_c == 8 ? 3 : 5, flow_src = ctx->packed_c == 8 ? 6 : 8;
-    for (int j = 0; j < 3; ++j) {
-      L.pc2w[j] = j;                                        // tgt rgb
-      L.pc2w[rgb_src + j] = (c.in_mode == 1 ? 5 : 3) + j;   // src rgb
+    const int per_frame = c.in_mode == 1 ? 5 : 3;           // reference channels per frame: rgb [+ flow]
+    if (ctx->unit_sample) {
+      // pack_sample_kernel: 0-2 tgt rgb, 3-5 src0 rgb, 6-7 src0 flow, 8-10 src1 rgb, 11-12 src1 flow
+      for (int j = 0; j < 3; ++j) {
+        L.pc2w[j] = j;
+        L.pc2w[3 + j] = per_frame + j;
+        L.pc2w[8 + j] = 2 * per_frame + j;
+      }
+      if (c.in_mode == 1)
+        for (int j = 0; j < 2; ++j) { L.pc2w[6 + j] = per_frame + 3 + j; L.pc2w[11 + j] = 2 * per_frame + 3 + j; }
+    } else {
+      const int rgb_src = ctx->packed_c == 8 ? 3 : 5, flow_src = ctx->packed_c == 8 ? 6 : 8;
+      for (int j = 0; j < 3; ++j) {
+        L.pc2w[j] = j;                                        // tgt rgb
+        L.pc2w[rgb_src + j] = per_frame + j;                  // src rgb
+      }
+      if (c.in_mode == 1) { L.pc2w[flow_src] = 8; L.pc2w[flow_src + 1] = 9; }
     }
-    if (c.in_mode == 1) { L.pc2w[flow_src] = 8; L.pc2w[flow_src + 1] = 9; }
     L.use_cmap = 1;                                         // direct cross-check path: weight channel -> packed channel
     for (int ci = 0; ci < L.Cin_w; ++ci) {
       L.cmap[ci] = 0;
@@ -1129,9 +1151,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   }
 
   // ---- workspace ----
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_pool, (size_t)mb * 2 * kPoolSplits * kPoolDim * 4)) return rc;
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_poolcnt, (size_t)mb * 2 * 4)) return rc;
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * 2 * kNumClasses * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_pool, (size_t)mb * kAttFrames * kPoolSplits * kPoolDim * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_poolcnt, (size_t)mb * kAttFrames * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * kAttFrames * kNumClasses * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_packed, (size_t)mb * c.H * c.W * ctx->packed_c * 4)) return rc;
   float* prev = ctx->d_packed;
   for (int i = 0; i < 7; ++i) {
@@ -1229,9 +1251,10 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     if (int rc = dev_alloc(ctx, (void**)&ctx->d_c7tmp, (size_t)mb * L.Hout * L.Wout * nbr * 256 * 4)) return rc;
   }
   {
-    // pred: [256, 3] per branch (decouple, posenn.py:240) or [256, 6] (couple, :181); stored [br][256][6/nbr]
-    const int per = 6 / nbr;
-    std::vector<float> wp(256 * 6), bp(6);
+    // pred: [256, 3*num_source] per branch (decouple, posenn.py:117, 240) or [256, 6*num_source]
+    // (couple, :58, 181); stored [br][256][per]
+    const int per = 6 * nsrc / nbr;
+    std::vector<float> wp(256 * 6 * nsrc), bp(6 * nsrc);
     for (int g = 0; g < nbr; ++g) {
       const HostTensor *w, *b;
       if (int rc = need_conv(branch_scope(g) + "pred", 1, 256, per, &w, &b)) return rc;
@@ -1292,10 +1315,12 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
     return fail(ctx, DAVO_ERR_ARG, "davo_forward: null input buffer");
   CU_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ctx->unit_sample) pairs = kUnitsAreSamples;        // both poses come out of one evaluation
   int launches = 0;
   const int total = pairs_selected(pairs, B);
   int last_n = 0;
-  if (pairs != DAVO_PAIRS_ALL) CU_OK(cudaMemsetAsync(pose_out, 0, (size_t)B * 12 * sizeof(float), st));
+  if (pairs == DAVO_PAIRS_TRAJECTORY || pairs == DAVO_PAIRS_TRAJECTORY_FIRST)
+    CU_OK(cudaMemsetAsync(pose_out, 0, (size_t)B * 12 * sizeof(float), st));
   for (int p0 = 0; p0 < total; p0 += ctx->mb) {
     const int n = (total - p0) < ctx->mb ? (total - p0) : ctx->mb;
     if (int rc = run_microbatch(ctx, pairs, p0, n, img, flow, seg, pose_out, st, &launches)) return rc;
@@ -1333,9 +1358,10 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   const size_t n_img = hw * 9, n_flow = hw * 8, n_seg = hw * 3;   // elements per sample
   // Host inputs arrive over PCIe more slowly than the stack computes, so what matters is how soon
   // compute can start behind the copy: chunks of 16 samples (8 chunks per 128-sample batch).
-  int cs = std::max(1, std::min(ctx->mb, 32) / 2);                 // samples per chunk
+  const int ups = ctx->unit_sample ? 1 : 2;                        // units of a pass per sample
+  int cs = std::max(1, std::min(ctx->mb / ups, 16));               // samples per chunk
   if (const char* e = getenv("DAVO_B200_HOST_CHUNK"))              // experiment knob
-    cs = std::max(1, std::min(atoi(e), std::max(1, ctx->mb / 2)));
+    cs = std::max(1, std::min(atoi(e), std::max(1, ctx->mb / ups)));
   if (ctx->s_img[0] && ctx->s_chunk != cs) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: chunk size changed");
   if (!ctx->s_img[0]) {
     ctx->s_chunk = cs;
@@ -1362,7 +1388,9 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   const bool seg_tgt = need_seg && !c.att_tgt_ones;
   size_t h2d = 0;
   int launches = 0, last_n = 0, chunk = 0;
-  if (pairs != DAVO_PAIRS_ALL) CU_OK(cudaMemsetAsync(ctx->s_pose, 0, (size_t)B * 12 * sizeof(float), st));
+  if (ctx->unit_sample) pairs = kUnitsAreSamples;
+  if (pairs == DAVO_PAIRS_TRAJECTORY || pairs == DAVO_PAIRS_TRAJECTORY_FIRST)
+    CU_OK(cudaMemsetAsync(ctx->s_pose, 0, (size_t)B * 12 * sizeof(float), st));
   // The copy is the bound, so the time after the LAST copy is what compute adds: the final chunks
   // taper (.., cs, cs/2, cs/4, cs/4) so that only a quarter chunk is computed after the copies end.
   int ns = 0, last_ns = 0;
@@ -1439,7 +1467,7 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
   if (s == "att_weights") {
     n = kNumClasses;
     if (cap < n) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: buffer too small");
-    if (c.att_src == 1 || c.att_src >= 3) src = ctx->d_attw + (size_t)pair * 2 * n;
+    if (c.att_src == 1 || c.att_src >= 3) src = ctx->d_attw + (size_t)pair * kAttFrames * n;
     else if (c.att_src == 2) src = ctx->d_staticw;
     else { for (int i = 0; i < n; ++i) out[i] = 1.0f; *n_out = n; return 0; }
   }
@@ -1479,7 +1507,7 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
 extern "C" int davo_debug_layer_timing(davo_ctx* ctx, int layer, long long* out, void* stream) {
   if (!ctx || layer < 0 || layer > 6 || !out) return DAVO_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int npairs = ctx->last_B * 2 < ctx->mb ? ctx->last_B * 2 : ctx->mb;
+  const int npairs = std::min(ctx->last_B * (ctx->unit_sample ? 1 : 2), ctx->mb);
   if (int rc = launch_conv(ctx, ctx->layers[layer], npairs, st)) return rc;
   if (int rc = launch_conv(ctx, ctx->layers[layer], npairs, st)) return rc;
   CU_OK(cudaStreamSynchronize(st));
@@ -1500,7 +1528,7 @@ extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int*
   if (!ctx->finalized || ctx->last_npairs_mb == 0) return fail(ctx, DAVO_ERR_STATE, "davo_profile_layers: run a forward first");
   CU_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int npairs = ctx->last_B * 2 < ctx->mb ? ctx->last_B * 2 : ctx->mb;
+  const int npairs = std::min(ctx->last_B * (ctx->unit_sample ? 1 : 2), ctx->mb);
   if (npairs_out) *npairs_out = npairs;
   cudaEvent_t e0, e1;
   CU_OK(cudaEventCreate(&e0));
@@ -1518,12 +1546,12 @@ extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int*
     *ms_dst = ms / iters;
     return 0;
   };
-  if (int rc = timed([&] { return launch_front(ctx, 0, 0, npairs, ctx->last_img, ctx->last_flow, ctx->last_seg, st, &dummy); }, &ms_out[0])) return rc;
+  if (int rc = timed([&] { return launch_front(ctx, ctx->unit_sample ? kUnitsAreSamples : 0, 0, npairs, ctx->last_img, ctx->last_flow, ctx->last_seg, st, &dummy); }, &ms_out[0])) return rc;
   for (int i = 0; i < 7; ++i) {
     const Layer& L = ctx->layers[i];
     if (int rc = timed([&] { return launch_conv(ctx, L, npairs, st); }, &ms_out[1 + i])) return rc;
   }
-  if (int rc = timed([&] { return launch_head(ctx, 0, 0, npairs, ctx->last_pose, st, &dummy); }, &ms_out[8])) return rc;
+  if (int rc = timed([&] { return launch_head(ctx, ctx->unit_sample ? kUnitsAreSamples : 0, 0, npairs, ctx->last_pose, st, &dummy); }, &ms_out[8])) return rc;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return 0;

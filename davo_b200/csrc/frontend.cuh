@@ -16,6 +16,7 @@ namespace davo {
 
 constexpr int kPoolSplits = 16;
 constexpr int kPoolDim = 20;     // >= the widest pooled vector (19 class frequencies)
+constexpr int kAttFrames = 3;    // attention-weight slots per unit (see unit_frame)
 constexpr int kPackedC = 16;     // widest packed PoseNN input (see pack_kernel; FrontParams::packed_c = 8 or 16)
 constexpr int kNumClasses = 19;
 constexpr int kPackBlocksPerPair = 104;
@@ -25,15 +26,27 @@ constexpr int kPackBlocksPerPair = 104;
 //   0 all:              s -> (s >> 1, s & 1)
 //   1 trajectory:       s -> (s, 1)            tgt->src1 only: what test_kitti_pose.py:143-145 composes
 //   2 trajectory+first: 0 -> (0, 0), s -> (s - 1, 1)   plus the first sample's tgt->src0
+//   3 sample units:     s -> (s, 0)            the non-shared nets take (tgt, src0, src1) at once
 __device__ __forceinline__ void pair_of_slot(int mode, int s, int* b, int* k) {
   if (mode == 0) { *b = s >> 1; *k = s & 1; }
-  else if (mode == 1) { *b = s; *k = 1; }
+  else if (mode == 1 || mode == 3) { *b = s; *k = mode == 1 ? 1 : 0; }
   else if (s == 0) { *b = 0; *k = 0; }
   else { *b = s - 1; *k = 1; }
 }
 
+// Attention-weight slot `fr` of a unit -> frame of the sample, coded as its plane in the inputs
+// (0 = src0, 1 = tgt, 2 = src1: seg[:, f], image columns [f*W, (f+1)*W); flow[:, 0] belongs to
+// src0, flow[:, 1] to src1, the target's flow is zeros, davo.py:978-982).
+//   frame-pair units (shared nets):  slot 0 = the pair's source frame, slot 1 = the target
+//   sample units (non-shared nets):  slot 0 = src0, slot 1 = src1, slot 2 = the target
+__device__ __forceinline__ int unit_frame(int unit_sample, int k, int fr) {
+  if (unit_sample) return fr == 0 ? 0 : fr == 1 ? 2 : 1;
+  return fr == 0 ? (k == 0 ? 0 : 2) : 1;
+}
+
 struct FrontParams {
   int H, W;
+  int unit_sample;       // 1: a unit is a whole sample (tgt, src0, src1), posenn.py:12-131
   int pair0;             // first selection slot of this pass
   int pair_mode;         // see pair_of_slot
   int packed_c;          // 8: [tgt rgb, src rgb, src flow]; 16: the legacy layout of pack_kernel
@@ -51,9 +64,9 @@ struct FrontParams {
   const float* seg;      // [B][3][H][W][1]
   const float* se_w;     // W1[in][hid] b1[hid] W2[hid][19] b2[19]
   const float* static_w; // sigmoid(seg_channel_weight)[19]
-  float* pool_part;      // [mb][2 frames][kPoolSplits][kPoolDim]
-  unsigned int* pool_count;  // [mb][2], zero between launches
-  float* att_w;          // [mb][2 frames][19]: frame 0 = the pair's source frame, 1 = the target
+  float* pool_part;      // [mb][kAttFrames][kPoolSplits][kPoolDim]
+  unsigned int* pool_count;  // [mb][kAttFrames], zero between launches
+  float* att_w;          // [mb][kAttFrames][19], slots as in unit_frame
   float* packed;         // [mb][H][W][16]
 };
 
@@ -90,16 +103,17 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
   const int D = p.se_in;
+  const int f = unit_frame(p.unit_sample, k, fr);
   __shared__ float red[8][4];
   __shared__ int s_hist[kNumClasses];
   __shared__ float s_pool[kPoolDim];
   __shared__ float s_fc1[kPoolDim];
   __shared__ int s_last;
-  float* part = p.pool_part + (((size_t)pl * 2 + fr) * kPoolSplits + blockIdx.x) * kPoolDim;
+  float* part = p.pool_part + (((size_t)pl * kAttFrames + fr) * kPoolSplits + blockIdx.x) * kPoolDim;
   if (p.att_src == 3) {
     if (threadIdx.x < kNumClasses) s_hist[threadIdx.x] = 0;
     __syncthreads();
-    const float* seg = p.seg + ((size_t)b * 3 + (fr ? 1 : (k == 0 ? 0 : 2))) * hw;
+    const float* seg = p.seg + ((size_t)b * 3 + f) * hw;
     const int per = (hw + kPoolSplits - 1) / kPoolSplits;
     const int beg = blockIdx.x * per, end = min(beg + per, hw);
     for (int i = beg + threadIdx.x; i < end; i += 256) {
@@ -111,11 +125,11 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   } else {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if (p.att_src == 1) {
-      const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2);
+      const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + (f == 2 ? 1 : 0)) * (size_t)hw * 2);
       const int n4 = hw / 2;                          // float4 = 2 pixels
       const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
       const int beg = blockIdx.x * per, end = min(beg + per, n4);
-      if (fr == 0)                                    // the target's flow is all zeros (davo.py:979)
+      if (f != 1)                                     // the target's flow is all zeros (davo.py:979)
         for (int i = beg + threadIdx.x; i < end; i += 256) {
           const float4 v = __ldg(src + i);
           s0 += se_in_x(v.x, p) + se_in_x(v.z, p);
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     } else {
       // byte sums are exact; the affine map to [-1, 1] (davo.py:1519-1522) is applied to the mean
       const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
-      const int col0 = fr ? p.W : (k == 0 ? 0 : 2 * p.W);
+      const int col0 = f * p.W;
       const int per = (hw + kPoolSplits - 1) / kPoolSplits;
       const int beg = blockIdx.x * per, end = min(beg + per, hw);
       unsigned int u0 = 0, u1 = 0, u2 = 0;
@@ -154,15 +168,15 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned int done = atomicAdd(&p.pool_count[pl * 2 + fr], 1u);
+    const unsigned int done = atomicAdd(&p.pool_count[pl * kAttFrames + fr], 1u);
     s_last = (done == kPoolSplits - 1);
-    if (s_last) p.pool_count[pl * 2 + fr] = 0;       // ready for the next launch
+    if (s_last) p.pool_count[pl * kAttFrames + fr] = 0;       // ready for the next launch
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x < D) {
-    const float* pp = p.pool_part + ((size_t)pl * 2 + fr) * kPoolSplits * kPoolDim + threadIdx.x;
+    const float* pp = p.pool_part + ((size_t)pl * kAttFrames + fr) * kPoolSplits * kPoolDim + threadIdx.x;
     float a = 0.f;
     for (int sp = 0; sp < kPoolSplits; ++sp) a += __ldcg(pp + sp * kPoolDim);
     a *= 1.0f / (float)hw;
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     const int c = threadIdx.x;
     float a = b2[c];
     for (int j = 0; j < Hd; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
-    p.att_w[((size_t)pl * 2 + fr) * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
+    p.att_w[((size_t)pl * kAttFrames + fr) * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
   }
 }
 
@@ -216,9 +230,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
   const int hw = p.H * p.W;
   if (threadIdx.x < kNumClasses) {
     const bool se = p.att_src == 1 || p.att_src >= 3;
-    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * 2 + 0) * kNumClasses + threadIdx.x]
+    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * kAttFrames + 0) * kNumClasses + threadIdx.x]
                      : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
-    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * 2 + 1) * kNumClasses + threadIdx.x]
+    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * kAttFrames + 1) * kNumClasses + threadIdx.x]
                       : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
   }
   __syncthreads();
@@ -310,9 +324,9 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
   const int hw = p.H * p.W, groups = hw / 4;
   if (threadIdx.x < kNumClasses) {
     const bool se = p.att_src == 1 || p.att_src >= 3;
-    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * 2 + 0) * kNumClasses + threadIdx.x]
+    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * kAttFrames + 0) * kNumClasses + threadIdx.x]
                      : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
-    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * 2 + 1) * kNumClasses + threadIdx.x]
+    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * kAttFrames + 1) * kNumClasses + threadIdx.x]
                       : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
   }
   __syncthreads();
@@ -384,19 +398,83 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
   }
 }
 
+// Sample units (non-shared nets, posenn.py:12-131: inputs = concat(tgt, src0, src1)): 16 packed
+// channels per pixel:  0-2 tgt rgb (x A_tgt), 3-5 src0 rgb, 6-7 src0 flow (x A_0),
+// 8-10 src1 rgb, 11-12 src1 flow (x A_1), 13-15 zero.  grid (kPackBlocksPerPair, units), one
+// thread per pixel.
+__global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
+  __shared__ float s_w[3][kNumClasses];                     // class weights of slots src0, src1, tgt
+  const int pl = blockIdx.y;
+  int b, k;
+  pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
+  const int hw = p.H * p.W;
+  if (threadIdx.x < 3 * kNumClasses) {
+    const int fr = threadIdx.x / kNumClasses, c = threadIdx.x % kNumClasses;
+    const bool se = p.att_src == 1 || p.att_src >= 3;
+    float v = 1.0f;
+    if (p.att_src == 2) v = p.static_w[c];
+    else if (se && !(fr == 2 && p.att_tgt_ones)) v = p.att_w[((size_t)pl * kAttFrames + fr) * kNumClasses + c];
+    s_w[fr][c] = v;
+  }
+  __syncthreads();
+  const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
+  const float* seg_b = p.seg + (size_t)b * 3 * hw;
+  const float2* flow_b = reinterpret_cast<const float2*>(p.flow + (size_t)b * 4 * (size_t)hw * 2);
+  float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 16);
+  for (int pix = blockIdx.x * 256 + threadIdx.x; pix < hw; pix += kPackBlocksPerPair * 256) {
+    const int h = pix / p.W, w = pix - h * p.W;
+    const uint8_t* row = img_b + ((size_t)h * 3 * p.W + w) * 3;
+    float a[3] = {1.f, 1.f, 1.f};                            // A_src0, A_src1, A_tgt
+    if (p.att_src != 0) {
+#pragma unroll
+      for (int fr = 0; fr < 3; ++fr) {
+        if (fr == 2 && p.att_tgt_ones) continue;
+        const int lab = (int)__ldg(seg_b + (size_t)unit_frame(1, 0, fr) * hw + pix);   // tf.cast truncates
+        a[fr] = (lab >= 0 && lab < kNumClasses) ? s_w[fr][lab] : 0.0f;                 // one_hot: out of range -> 0
+      }
+    }
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    const float mt = p.mask_rgb ? a[2] : 1.0f;
+    const uint8_t* pt = row + (size_t)p.W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = img_norm(pt[c]) * mt;
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      const float ms = p.mask_rgb ? a[sidx] : 1.0f, mf = p.mask_flow ? a[sidx] : 1.0f;
+      const uint8_t* ps = row + (size_t)(sidx == 0 ? 0 : 2 * p.W) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[3 + 5 * sidx + c] = img_norm(ps[c]) * ms;
+      if (p.in_mode == 1) {
+        const float2 f = __ldg(flow_b + (size_t)sidx * hw + pix);
+        v[6 + 5 * sidx] = f.x * mf;
+        v[7 + 5 * sidx] = f.y * mf;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      out[(size_t)pix * 4 + q] = make_float4(round_tf32(v[4 * q]), round_tf32(v[4 * q + 1]), round_tf32(v[4 * q + 2]),
+                                             round_tf32(v[4 * q + 3]));
+  }
+}
+
 struct HeadParams {
   int pair0, npairs, pair_mode;
-  int nbr;                // branches: 2 (rotation, translation; pred 256 -> 3 each) or 1 (couple nets; pred 256 -> 6)
+  int nbr;                // branches: 2 (rotation, translation) or 1 (couple nets)
+  int nsrc;               // source frames per unit: 1 (shared nets: a frame pair) or 2 (a whole sample)
   int nparts;             // partial rows per (pair, branch) = tiles * 4
   float inv_hw;           // 1 / (H7 * W7)
-  const float* sums;      // [mb][2][nparts][256]
-  const float* wpred;     // [2][256][3]
-  const float* bpred;     // [2][3]
-  float* pose_out;        // [B][2][6] -> pair-major [2B][6]
+  const float* sums;      // [mb][nbr][nparts][256]
+  const float* wpred;     // [nbr][256][per], per = 6 * nsrc / nbr outputs of a branch's pred conv
+  const float* bpred;     // [nbr][per]
+  float* pose_out;        // [B][2][6]
 };
 
-// grid npairs, 256 threads.  mean_{h,w} pred(cnv7) == pred(mean_{h,w} cnv7): pred is linear
-// (posenn.py:240-241); pose = 0.01 * [rot(3), trans(3)] (posenn.py:248-250).
+// grid units, 256 threads.  mean_{h,w} pred(cnv7) == pred(mean_{h,w} cnv7): pred is linear
+// (posenn.py:240-241); pose = 0.01 * [rot(3), trans(3)] per source frame:
+//   decouple nets: branch avg [3*nsrc] -> [nsrc, 3], rot | trans concatenated (posenn.py:121-123, 248-250)
+//   couple nets:   avg [6*nsrc] -> [nsrc, 6]                                     (posenn.py:62, 183)
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   __shared__ float s_mean[2][256];
   const int pl = blockIdx.x;
@@ -409,17 +487,20 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < 6) {
-    const int per = 6 / p.nbr;                   // outputs per branch
-    const int br = warp / per, j = warp % per;   // output warp = [rz ry rx | tx ty tz] either way (posenn.py:248-250, :183)
+  const int per = 6 * p.nsrc / p.nbr;            // outputs per branch
+  int b, k;
+  pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
+  for (int o = warp; o < 6 * p.nsrc; o += 8) {
+    const int br = o / per, j = o % per;
     float a = 0.f;
     for (int i = lane; i < 256; i += 32) a += s_mean[br][i] * p.wpred[(br * 256 + i) * per + j];
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
     if (lane == 0) {
-      int b, k;
-      pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
-      p.pose_out[(size_t)(b * 2 + k) * 6 + warp] = 0.01f * (a + p.bpred[br * per + j]);
+      // where output j of branch br lands in pose[b][source][6]
+      const int comps = 6 / p.nbr;               // components a branch contributes per source: 3 or 6
+      const int src = p.nsrc == 1 ? k : j / comps, comp = br * comps + j % comps;
+      p.pose_out[(size_t)(b * 2 + src) * 6 + comp] = 0.01f * (a + p.bpred[br * per + j]);
     }
   }
 }

@@ -67,17 +67,19 @@ def _trunc_normal(rng, shape, std):
 def conv_specs(cfg: V.DavoConfig):
     """[(tf scope under pose_exp_net/, HWIO shape)] of decouple_sharednet_v0_dilation
     (posenn.py:189-254) or couple_sharednet_v0_dilation (:133-187)."""
-    cin = 10 if cfg.in_mode == 1 else 6
+    shared = cfg.posenn in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_COUPLE_SHARED_DIL)
+    nsrc = 1 if shared else 2                            # num_source of one evaluation
+    cin = (5 if cfg.in_mode == 1 else 3) * (1 + nsrc)    # (rgb [+ flow]) x (tgt + sources)
     c6 = cfg.cnv6_out
     specs = [("cnv1", (7, 7, cin, 16)), ("cnv2", (5, 5, 16, 32)), ("cnv3", (3, 3, 32, 64)),
              ("cnv4", (3, 3, 64, 128)), ("cnv5", (3, 3, 128, 256))]
-    if cfg.posenn == V.POSENN_COUPLE_SHARED_DIL:
+    if cfg.posenn in (V.POSENN_COUPLE_SHARED_DIL, V.POSENN_COUPLE_DIL):
         return specs + [("pose/cnv6", (3, 3, 256, c6)), ("pose/cnv7", (3, 3, c6, 256)),
-                        ("pose/pred", (1, 1, 256, 6))]
+                        ("pose/pred", (1, 1, 256, 6 * nsrc))]
     for br in ("rotation", "translation"):
         specs += [("pose/%s/cnv6" % br, (3, 3, 256, c6)),
                   ("pose/%s/cnv7" % br, (3, 3, c6, 256)),
-                  ("pose/%s/pred" % br, (1, 1, 256, 3))]
+                  ("pose/%s/pred" % br, (1, 1, 256, 3 * nsrc))]
     return specs
 
 
@@ -89,8 +91,9 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
     tests exercise the bias path the way a trained checkpoint would.
     """
     cfg = V.parse_version(version)
-    if cfg.posenn not in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_COUPLE_SHARED_DIL):
-        raise NotImplementedError("init_weights: only the -sharedNN dilated nets are built")
+    if cfg.posenn not in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_COUPLE_SHARED_DIL,
+                          V.POSENN_DECOUPLE_DIL, V.POSENN_COUPLE_DIL):
+        raise NotImplementedError("init_weights: only the four dilated nets are built")
     rng = np.random.default_rng(seed)
     w: Dict[str, np.ndarray] = {}
 
@@ -115,7 +118,8 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         w["pose_exp_net/pose_exp_net/seg_channel_weight/weight"] = \
             rng.normal(0.0, 0.05, size=(19,)).astype(np.float32)
     if cfg.posenn_se == V.PSE_INSERT:
-        for br in (("rotation/", "translation/") if cfg.posenn == V.POSENN_DECOUPLE_SHARED_DIL else ("",)):
+        for br in (("rotation/", "translation/") if cfg.posenn in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_DECOUPLE_DIL)
+                   else ("",)):
             sc = "pose_exp_net/pose/%scnv5_se_attention" % br
             for name, (fi, fo) in (("bottleneck_fc", (256, 32)), ("recover_fc", (32, 256))):
                 std = math.sqrt(1.3 * 2.0 / fi)

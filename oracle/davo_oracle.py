@@ -230,6 +230,55 @@ def couple_sharednet_v0_dilation(tgt: torch.Tensor, src: torch.Tensor,
     return pose, (c6, c6)
 
 
+def net_v0_dilation(tgt: torch.Tensor, src0: torch.Tensor, src1: torch.Tensor,
+                    wts: Dict[str, torch.Tensor], decouple: bool, se_attention=False, tf32: bool = False,
+                    taps: Optional[Dict[str, torch.Tensor]] = None):
+    """``decouple_net_v0_dilation`` (nets/posenn.py:69-131) / ``couple_net_v0_dilation`` (:12-66),
+    dropout=False, batch_norm=False: ONE evaluation per sample on concat(tgt, src0, src1) (:21, :78),
+    num_source = 2.  Decouple: rotation / translation branches, pred 256 -> 3*2 each, reshaped
+    [-1, 2, 3] and concatenated (:117-123).  Couple: one branch, pred 256 -> 12 -> [-1, 2, 6] (:58-62).
+
+    Returns (pose [B,2,6], (cnv6_rot, cnv6_trans)).
+    """
+    P = "pose_exp_net/"
+
+    def cv(x, name, stride=1, rate=1, relu=True):
+        return conv2d_same(x, wts[P + name + "/weights"], wts[P + name + "/biases"],
+                           stride=stride, rate=rate, relu=relu, tf32=tf32)
+
+    x = torch.cat([tgt, src0, src1], dim=3)
+    c1 = cv(x, "cnv1", stride=2)
+    c2 = cv(c1, "cnv2", stride=2)
+    c3 = cv(c2, "cnv3", rate=2)
+    c4 = cv(c3, "cnv4", rate=4)
+    c5 = cv(c4, "cnv5", rate=8)
+    if taps is not None:
+        taps.update(input=x, cnv1=c1, cnv2=c2, cnv3=c3, cnv4=c4, cnv5=c5)
+    avgs, c6s = [], []
+    for br in (("pose/rotation/", "pose/translation/") if decouple else ("pose/",)):
+        if se_attention is True:             # cnv5 is re-assigned: the second branch sees the first's output
+            c5 = se_block(c5, wts, P + br + "cnv5_se_attention", "relu")
+            c6 = cv(c5, br + "cnv6", rate=2)
+        elif se_attention == "se_skipadd":
+            c6 = cv(c5, br + "cnv6", rate=2)
+            c6 = torch.relu(c5 + se_block(c6, wts, P + br + "cnv6_se_attention", "relu"))
+        elif se_attention == "se_replace":
+            c6 = se_block(c5, wts, P + br + "cnv6_se_attention", "relu")
+        else:
+            c6 = cv(c5, br + "cnv6", rate=2)
+        c7 = cv(c6, br + "cnv7", stride=2)
+        pred = cv(c7, br + "pred", relu=False)
+        avgs.append(pred.mean(dim=(1, 2)))
+        c6s.append(c6)
+    if taps is not None:
+        taps.update(cnv6_rotation=c6s[0], cnv6_translation=c6s[-1])
+    if decouple:
+        pose = 0.01 * torch.cat([avgs[0].reshape(-1, 2, 3), avgs[1].reshape(-1, 2, 3)], dim=-1)
+    else:
+        pose = 0.01 * avgs[0].reshape(-1, 2, 6)
+    return pose, (c6s[0], c6s[-1])
+
+
 # --------------------------------------------------------------------------- #
 # Whole inference graph
 # --------------------------------------------------------------------------- #
@@ -285,8 +334,12 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             raise NameError("not support `-sharedNN-couplePoseNN' mode.")
         else:
             raise NameError("unknown PoseNN type.")
+    elif "-dilatedPoseNN" in version:                                    # davo.py:1040-1041
+        pose_net = "decouple_net_v0_dilation"
+    elif "-dilatedCouplePoseNN" in version:                              # davo.py:1042-1043
+        pose_net = "couple_net_v0_dilation"
     else:
-        _unsupported("non-shared PoseNN")
+        _unsupported("non-dilated PoseNN (couple_net_v0 / decouple_net_v0)")
     if re.search("-cnv6_([0-9]+)", version) is not None:                 # davo.py:1052-1053
         pass  # width is carried by the weight shapes
     # 2. inputs (davo.py:1057-1073)
@@ -386,9 +439,14 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
     # 4.2 PoseNN x2 with shared weights (davo.py:1453-1458)
     t0 = {} if taps is not None else None
     t1 = {} if taps is not None else None
-    pose0, _ = pose_net(input_images[0], input_images[1], wts, se_attention, tf32, t0)
-    pose1, _ = pose_net(input_images[3], input_images[2], wts, se_attention, tf32, t1)
-    pred_poses = torch.cat([pose0, pose1], dim=-2)                       # davo.py:1458
+    if isinstance(pose_net, str):                                        # davo.py:1459-1460: one evaluation per sample
+        pred_poses, _ = net_v0_dilation(input_images[0], input_images[1], input_images[2], wts,
+                                        pose_net.startswith("decouple"), se_attention, tf32, t0)
+        t1 = t0
+    else:
+        pose0, _ = pose_net(input_images[0], input_images[1], wts, se_attention, tf32, t0)
+        pose1, _ = pose_net(input_images[3], input_images[2], wts, se_attention, tf32, t1)
+        pred_poses = torch.cat([pose0, pose1], dim=-2)                   # davo.py:1458
     if taps is not None:
         taps["attention_maps"] = [a.numpy() for a in (a_tgt, a_s0, a_s1)]
         taps["attention_weights"] = None if att_w is None else [w.numpy() for w in att_w]
