@@ -6,8 +6,8 @@
 //
 // * M tile = 128 output pixels = a 16 (rows) x 8 (cols) block of one frame pair.
 // * A "tap" is one 32-float (128 B) slab of the reduction axis: a filter tap (or,
-//   for the thin strided layers, two horizontally adjacent taps) x 32 input
-//   channels.
+//   for the thin strided layers, 2 or 4 horizontally adjacent taps) x 32 / 16 / 8
+//   input channels.
 // * The A operand is never gathered per tap.  A PATCH -- the tile's input halo,
 //   {32 ch, Wp cols, 1, Hp rows, 1} of the NHWC activation -- is loaded ONCE by
 //   a 5-D TMA box placed with signed coordinates, so TF-'SAME' padding (asymmetric
@@ -25,24 +25,27 @@
 //   and kept resident in shared memory for the CTA's whole life.
 //
 // * Column-widened form (WIDE; the thin stride-2 layers cnv1, cnv2).  One tcgen05.mma of
-//   M=128, K=8 costs >= 85 cycles however small N is (tools/experiments/mma_rate.cu), so a
-//   16-channel layer with pixels on M is bound by the NUMBER of MMAs.  Here one M row is a
-//   run of G horizontally adjacent output pixels of one image row and N = G x Cout holds
-//   all of them: the slab "input pixel pair c of the run" feeds output pixel g through
-//   filter column pair d = c - g, so its weight operand is a WINDOW of one resident block
+//   M=128, K=8 costs 53.8 cycles however small N is (64 at N=128;
+//   tools/experiments/mma_floor.cu), so a 16-channel layer with pixels on M is bound by the
+//   NUMBER of MMAs.  Here one M row is a run of G horizontally adjacent output pixels of one
+//   image row and N = G x Cout = 128 holds all of them.  A slab is S input pixels x C channels
+//   (32 floats: C = 16, S = 2 for cnv2; the 8-channel packed input gives cnv1 S = 4).  Slab c
+//   of a run feeds output pixel g through the filter columns tx = 2d + wp + pad_l with
+//   d = (S/2)c - g, so its weight operand is a WINDOW of one resident block
 //   [W[d_max]; ...; W[d_min]] per filter row and its result a window of the accumulator
-//   (per-tap N, first column and first weight row).  Every input pair position c is its own
-//   patch {32 floats at 32*(c mod G), tile_w runs, 1 parity, Hp rows, 1} of the view
-//   [N][H/2][2][W/2G][2G*C]; a tile is tile_h rows x tile_w runs with tile_w == Wp, so its
-//   128 M rows are 128 consecutive 128-B slabs.  cnv1: G = 8 -> 308 MMAs per 1024 pixels
-//   instead of 896.
+//   (per-tap N, first column and first weight row: davo_capi.cu, plan_layer_wide).  Every slab
+//   position c is its own patch {32 floats at 32*(c mod slabs_per_run), tile_w runs, 1 parity,
+//   Hp rows, 1} of the view [N][H/2][2][W/2G][2G*C]; a tile is tile_h rows x tile_w runs with
+//   tile_w == Wp, so its 128 M rows are 128 consecutive 128-B slabs.  cnv1: 172 MMAs per 1024
+//   pixels instead of 896.
 //
-// Warp roles (224 threads): warp 0 patch (A) TMA producer, warp 6 weight (B) TMA
-// producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue: TMEM -> registers ->
-// bias/ReLU/round -> a per-warp swizzled smem transpose -> global stores of whole 128-B
-// lines (or the spatial-sum epilogue of cnv7).  Accumulators are double-buffered in TMEM
-// so the epilogue of tile i overlaps the main loop of tile i+1.  Persistent CTAs walk
-// tiles round-robin.
+// Warp roles (224 threads): warp 0 patch (A) TMA producer, warp 6 weight (B) TMA producer,
+// warp 1 TMEM owner + MMA issue (all 32 lanes run the loop so that every operand lives on the
+// uniform datapath; elect.sync picks the issuing lane), warps 2-5 epilogue: TMEM -> registers ->
+// bias/ReLU/round -> a per-warp swizzled staging buffer -> one TMA tile store per 32x32 block
+// (or the spatial-sum epilogue of cnv7).  Accumulators are double-buffered in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1.  Persistent CTAs walk tiles
+// round-robin.
 #pragma once
 #include "conv_common.cuh"
 

@@ -332,6 +332,25 @@ def test_cli_writes_reference_format_trajectory(tmp_path):
     _assert_pose(poses[:6], ref)
 
 
+def test_cli_on_a_reference_layout_dump(tmp_path):
+    """CLI over an on-disk dump in the reference's layout (jpg triples + flownet2 / seglabel npy,
+    reference test_kitti_pose.py:33-72) with an .npz checkpoint: poses equal the oracle's on the
+    decoded frames."""
+    _need_gpu()
+    from davo_b200 import test_kitti_pose as cli
+    from tests.test_host import _write_dump
+    _write_dump(str(tmp_path / "dump"), 9, 7, H, W)
+    w = S.init_weights(HEADLINE, random_bias=True)
+    np.savez(str(tmp_path / "model.npz"), **w)
+    poses = cli.main(["--concat_img_dir", str(tmp_path / "dump"), "--test_seq", "9", "--batch_size", "2", "--all_pairs",
+                      "--version", HEADLINE, "--ckpt_file", str(tmp_path / "model.npz"), "--output_dir", str(tmp_path / "out")])
+    assert poses.shape == (5, 2, 6)
+    stream = cli.DumpStream(str(tmp_path / "dump"), 9, H, W, 3)
+    inputs = tuple(np.stack([stream.sample(i)[k] for i in range(5)]) for k in range(3))
+    _assert_pose(poses, O.davo_forward(HEADLINE, *inputs, w, torch.float64))
+    assert len((tmp_path / "out" / "09-pred_kitti_pose.txt").read_text().strip().split("\n")) == 7
+
+
 def test_two_rank_sharded_stream_matches_single_gpu(tmp_path):
     """N>1 path on real GPUs (NCCL all-gather): identical bits to the 1-GPU run."""
     _need_gpu()

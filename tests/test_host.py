@@ -217,3 +217,40 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def _write_dump(root, seq, n_frames, h, w, seed=3):
+    """A dump in the reference's layout (doc/preprocessing.md:50-113, test_kitti_pose.py:45-49):
+    <root>/<seq>/<id>.jpg (src0|tgt|src1 side by side), <id>-flownet2.npy (4,H,W,2),
+    <id>-seglabel.npy (3,H,W,1), one triple per valid target frame."""
+    from PIL import Image
+    d = os.path.join(root, "%.2d" % seq)
+    os.makedirs(d)
+    rng = np.random.default_rng(seed)
+    out = []
+    for t in range(1, n_frames - 1):
+        fid = "%.6d" % t
+        img = rng.integers(0, 256, size=(h, 3 * w, 3), dtype=np.uint8)
+        Image.fromarray(img).save(os.path.join(d, fid + ".jpg"), quality=95)
+        flow = rng.normal(0.3, 15.0, size=(4, h, w, 2)).astype(np.float32)
+        seg = rng.integers(0, 19, size=(3, h, w, 1)).astype(np.uint8)
+        np.save(os.path.join(d, fid + "-flownet2.npy"), flow)
+        np.save(os.path.join(d, fid + "-seglabel.npy"), seg)
+        out.append((flow, seg))
+    return out
+
+
+def test_dump_stream_reads_the_reference_layout(tmp_path):
+    from PIL import Image
+    from davo_b200.test_kitti_pose import DumpStream
+    h, w, n = 16, 32, 6
+    ref = _write_dump(str(tmp_path), 9, n, h, w)
+    stream = DumpStream(str(tmp_path), 9, h, w, 3)
+    assert stream.n == n - 2 and stream.ids[0] == "000001" and stream.ids[-1] == "%.6d" % (n - 2)
+    for i in range(stream.n):
+        img, flow, seg = stream.sample(i)
+        assert img.shape == (h, 3 * w, 3) and img.dtype == np.uint8
+        assert flow.shape == (4, h, w, 2) and flow.dtype == np.float32
+        assert seg.shape == (3, h, w, 1) and seg.dtype == np.float32
+        assert np.array_equal(flow, ref[i][0]) and np.array_equal(seg, ref[i][1].astype(np.float32))
+        assert np.array_equal(img, np.asarray(Image.open(str(tmp_path / "09" / (stream.ids[i] + ".jpg"))).convert("RGB")))
