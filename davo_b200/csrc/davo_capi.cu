@@ -1424,7 +1424,8 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
     // a chunk is a batch of its own: only the first one may hold the first sample's tgt->src0
     const int chunk_pairs = (pairs == DAVO_PAIRS_TRAJECTORY_FIRST && s0 > 0) ? DAVO_PAIRS_TRAJECTORY : pairs;
     const int np_chunk = pairs_selected(chunk_pairs, ns);
-    for (int q0 = 0; q0 < np_chunk; q0 += ctx->mb)
+    static const bool copy_only = getenv("DAVO_B200_HOST_COPY_ONLY") != nullptr;   // experiment: time the copies alone
+    for (int q0 = 0; q0 < np_chunk && !copy_only; q0 += ctx->mb)
       if (int rc = run_microbatch(ctx, chunk_pairs, q0, std::min(ctx->mb, np_chunk - q0), ctx->s_img[buf],
                                   ctx->s_flow[buf], ctx->s_seg[buf], ctx->s_pose + (size_t)12 * s0, st, &launches))
         return rc;
