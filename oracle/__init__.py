@@ -13,4 +13,11 @@ therefore a line-by-line restatement of the reference files (cited per
 function) plus the documented TF 1.13 op semantics; it is cross-checked by a
 second, independent plain-C restatement (``oracle/posenn_ref.c``), not by the
 reference itself.
+
+What IS pinned against the reference's own code (the TF-free pieces next to the path):
+``tests/golden/reference_pins.json`` holds outputs of ``utils/common_utils.py``
+(complete_batch_size, is_valid_sample) and ``data/kitti/pose_evaluation_utils.py``
+(compute_ate) imported from /root/reference (``tests/golden/make_reference_pins.py``),
+and ``oracle/ref_build.py`` compiles the reference's KITTI devkit from its sources into
+``oracle/_ref/``, which the tests run on the trajectory file this repo writes.
 """

@@ -521,6 +521,19 @@ def kitti_lines(traj: np.ndarray) -> List[str]:
     return [" ".join(str(float(v)) for v in p[:3, :].reshape(12)) for p in traj]
 
 
+def snippet_ate(gtruth_xyz: np.ndarray, pred_xyz: np.ndarray) -> float:
+    """``compute_ate`` of data/kitti/pose_evaluation_utils.py:7-27 on already associated positions:
+    align the first frames (:20-21), fit one scale factor (:24), RMSE divided by the number of
+    matches -- the reference divides sqrt(sum) by N, not by sqrt(N) (:26).  Pinned against the
+    reference's own function in tests/golden/reference_pins.json."""
+    g = np.asarray(gtruth_xyz, np.float64)
+    p = np.asarray(pred_xyz, np.float64).copy()
+    p += (g[0] - p[0])[None, :]
+    scale = np.sum(g * p) / np.sum(p ** 2)
+    err = p * scale - g
+    return float(np.sqrt(np.sum(err ** 2)) / g.shape[0])
+
+
 def ate(traj_a: np.ndarray, traj_b: np.ndarray) -> float:
     """RMSE of translation differences, same origin, no alignment."""
     d = traj_a[:, :3, 3] - traj_b[:, :3, 3]

@@ -121,3 +121,80 @@ def test_unsupported_variants_raise():
         O.davo_forward("v1-sharedNN-couplePoseNN", img, flow, seg, w)
     with pytest.raises(NameError):
         O.davo_forward("v1-sharedNN", img, flow, seg, w)
+
+
+# ---- pins taken from the reference's own TF-free code (tests/golden/make_reference_pins.py) ----
+def _pins():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_pins.json")) as f:
+        return json.load(f)
+
+
+def test_batch_padding_and_sample_validity_match_the_reference_functions():
+    """parallel.complete_batch_size / is_valid_sample against outputs of the reference's
+    utils/common_utils.py:8-28 (imported from /root/reference when the fixture was made)."""
+    from davo_b200 import parallel
+    pins = _pins()
+    for c in pins["complete_batch_size"]:
+        out = parallel.complete_batch_size(list(range(c["n"])), c["batch"]) if c["n"] else []
+        assert (len(out), out[-8:], int(sum(out))) == (c["len"], c["tail"], c["sum"]), c
+    for case in pins["is_valid_sample"].values():
+        fr = case["frames"]
+        assert [parallel.is_valid_sample(fr, i, 3) for i in range(len(fr))] == case["seq3"]
+        assert [parallel.is_valid_sample(fr, i, 5) for i in range(len(fr))] == case["seq5"]
+
+
+def test_snippet_ate_matches_the_reference_compute_ate():
+    """O.snippet_ate against data/kitti/pose_evaluation_utils.py:compute_ate run on TUM files."""
+    for c in _pins()["compute_ate"]:
+        assert abs(O.snippet_ate(np.array(c["gt"]), np.array(c["pred"])) - c["ate"]) <= 1e-6 * max(1.0, c["ate"])
+
+
+def test_reference_pins_are_current_when_the_reference_is_here():
+    """In the build container the reference tree exists: the committed pins equal a fresh run."""
+    ref = os.environ.get("DAVO_REFERENCE_DIR", "/root/reference")
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not on this box")
+    import subprocess, sys, json, tempfile, shutil
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as d:
+        shutil.copy(os.path.join(here, "golden", "make_reference_pins.py"), d)
+        subprocess.run([sys.executable, os.path.join(d, "make_reference_pins.py")], check=True, capture_output=True)
+        with open(os.path.join(d, "reference_pins.json")) as f:
+            fresh = json.load(f)
+    assert fresh == _pins()
+
+
+def test_trajectory_file_is_read_by_the_reference_devkit(tmp_path):
+    """The reference's own KITTI evaluator (kitti_benchmark/cpp, built by oracle/ref_build.py into
+    oracle/_ref/) reads the file geo_utils.write_kitti_trajectory writes: every pose is parsed, a
+    result identical to the ground truth scores zero, and a 2 % translation scale error scores 2 %."""
+    import subprocess
+    from oracle import ref_build
+    from davo_b200 import geo_utils
+    devkit = ref_build.build()
+    if devkit is None:
+        pytest.skip("reference devkit not built and reference tree not on this box")
+    rng = np.random.default_rng(5)
+    gt_dir, res_dir = tmp_path / "data" / "odometry" / "poses", tmp_path / "results" / "x" / "data"
+    gt_dir.mkdir(parents=True)
+    res_dir.mkdir(parents=True)
+    n = 900
+    for seq in range(11):
+        poses = np.zeros((n, 2, 6), np.float32)
+        poses[:, 1, :3] = rng.normal(0, 2e-3, size=(n, 3))          # small rotations
+        poses[:, 1, 3:] = [0.0, 0.0, -1.0]                           # tgt -> src1: one metre per frame
+        poses[:, 1, 3:] += rng.normal(0, 0.02, size=(n, 3))
+        traj = geo_utils.compose_trajectory(poses)
+        geo_utils.write_kitti_trajectory(str(gt_dir / ("%02d.txt" % seq)), traj)
+        scaled = traj.copy()
+        scaled[:, :3, 3] *= 1.02 if seq == 10 else 1.0
+        geo_utils.write_kitti_trajectory(str(res_dir / ("%02d.txt" % seq)), scaled)
+    out = subprocess.run([devkit, "x"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300).stdout
+    for seq in range(11):
+        assert "Processing: %02d.txt, poses: %d/%d" % (seq, n + 2, n + 2) in out, out[-2000:]
+    assert "Done." in out
+    stats = {seq: [float(v) for v in (tmp_path / "results" / "x" / ("%02d-stats.txt" % seq)).read_text().split()]
+             for seq in (0, 10)}
+    assert stats[0][0] < 1e-5 and stats[0][1] < 1e-7           # identical files: zero translation / rotation error
+    assert abs(stats[10][0] - 0.02) < 2e-3                      # 2 % scale error reads as 2 % translation error
