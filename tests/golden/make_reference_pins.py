@@ -5,6 +5,9 @@ from /root/reference in this container and their outputs on fixed inputs are com
   utils/common_utils.py: complete_batch_size, is_valid_sample   (sample list of test_kitti_pose.py:83-101,
                                                                  the padding rule of the rank shards)
   data/kitti/pose_evaluation_utils.py: compute_ate              (the snippet ATE of SURVEY 8c)
+                                       pose_vec2mat(vec, False)   (numpy statement of the same
+                                                                  [rz,ry,rx,tx,ty,tz] -> 4x4 convention as the
+                                                                  TF utils/geo_utils.py:93-119 used on the path)
 
 Run:  python tests/golden/make_reference_pins.py
 """
@@ -57,7 +60,12 @@ def write_tum(path, t, xyz):
 def main():
     cu = _load("utils/common_utils.py", "ref_common_utils")
     pe = _load("data/kitti/pose_evaluation_utils.py", "ref_pose_eval")
-    pins = {"complete_batch_size": [], "is_valid_sample": {}, "compute_ate": []}
+    pins = {"complete_batch_size": [], "is_valid_sample": {}, "compute_ate": [], "pose_vec2mat": []}
+    rng = np.random.default_rng(23)
+    vecs = np.concatenate([rng.normal(0, 0.02, size=(6, 6)), rng.uniform(-3.0, 3.0, size=(6, 6)),
+                           np.array([[0, 0, 0, 1, 2, 3], [0.5, 0, 0, 0, 0, 0], [0, 0.5, 0, 0, 0, 0], [0, 0, 0.5, 0, 0, 0]], float)])
+    for v in vecs:
+        pins["pose_vec2mat"].append({"vec": v.tolist(), "mat": np.asarray(pe.pose_vec2mat(v, False), float).tolist()})
     for n, b in batch_cases():
         out = cu.complete_batch_size(list(range(n)), b) if n else []
         pins["complete_batch_size"].append({"n": n, "batch": b, "len": len(out), "tail": out[-8:], "sum": int(sum(out))})

@@ -150,6 +150,17 @@ def test_snippet_ate_matches_the_reference_compute_ate():
         assert abs(O.snippet_ate(np.array(c["gt"]), np.array(c["pred"])) - c["ate"]) <= 1e-6 * max(1.0, c["ate"])
 
 
+def test_pose_vec2mat_convention_matches_the_reference_numpy_statement():
+    """Host geo_utils.pose_vec2mat and the oracle's against data/kitti/pose_evaluation_utils.py:
+    pose_vec2mat(vec, is_kitti_format=False): R = Rx.Ry.Rz of [rz, ry, rx], t = [tx, ty, tz]."""
+    from davo_b200 import geo_utils
+    for c in _pins()["pose_vec2mat"]:
+        v = np.array([c["vec"]], np.float32)
+        want = np.array(c["mat"])
+        assert np.abs(geo_utils.pose_vec2mat(v)[0] - want).max() < 2e-6
+        assert np.abs(O.pose_vec2mat(v)[0] - want).max() < 2e-6
+
+
 def test_reference_pins_are_current_when_the_reference_is_here():
     """In the build container the reference tree exists: the committed pins equal a fresh run."""
     ref = os.environ.get("DAVO_REFERENCE_DIR", "/root/reference")
