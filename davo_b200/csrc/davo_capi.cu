@@ -136,7 +136,7 @@ struct davo_ctx {
   // host-buffer entry point staging
   static constexpr int kStage = 3;  // staging buffers: copy of chunk i+2 never waits for compute of chunk i
   uint8_t* s_img[kStage] = {};
-  float *s_flow[kStage] = {}, *s_seg[kStage] = {}, *s_pose = nullptr;
+  float *s_flow[kStage] = {}, *s_seg[kStage] = {}, *s_depth[kStage] = {}, *s_pose = nullptr;
   int s_chunk = 0;                  // samples per staging buffer
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[kStage] = {}, ev_consumed[kStage] = {}, ev_start = nullptr;
@@ -146,6 +146,7 @@ struct davo_ctx {
   int last_npairs_mb = 0;
   const uint8_t* last_img = nullptr; const float* last_flow = nullptr; const float* last_seg = nullptr;
   float* last_pose = nullptr; int last_B = 0; int last_pairs = 0;
+  const float* cur_depth = nullptr; // depth planes of the batch (chunk) being enqueued; se_depth sources only
 };
 
 namespace {
@@ -885,11 +886,11 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   fp.mask_rgb = c.mask_mode != 0;
   fp.mask_flow = c.mask_mode == 2;
   fp.se_act = c.se_act; fp.flow_abs = c.flow_abs; fp.flow_norm = c.flow_norm;
-  fp.img = img; fp.flow = flow; fp.seg = seg;
+  fp.img = img; fp.flow = flow; fp.seg = seg; fp.depth = ctx->cur_depth; fp.depth_norm = c.depth_norm;
   fp.se_w = ctx->d_sew; fp.static_w = ctx->d_staticw;
   fp.pool_part = ctx->d_pool; fp.pool_count = ctx->d_poolcnt; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
   if (c.att_src == 1 || c.att_src >= 3) {
-    static const int se_dims[5][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}};
+    static const int se_dims[6][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}, {1, 8}};
     fp.se_in = se_dims[c.att_src][0]; fp.se_hid = se_dims[c.att_src][1];
     const int src_frames = ctx->unit_sample ? 2 : 1;
     se_pool_kernel<<<dim3(kPoolSplits, npairs, src_frames + (c.att_tgt_ones ? 0 : 1)), 256, 0, st>>>(fp);
@@ -979,7 +980,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (cfg->cnv6_out != 128 && cfg->cnv6_out != 64 && cfg->cnv6_out != 32)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128)", cfg->cnv6_out);
   if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
-  if (cfg->att_src < 0 || cfg->att_src > 4) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
+  if (cfg->att_src < 0 || cfg->att_src > 5) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
+  if (cfg->att_src == 5 && ((cfg->H * cfg->W) % 4) != 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: se_depth needs H*W % 4 == 0");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -1017,6 +1019,7 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
     if (ctx->s_img[i]) cudaFree(ctx->s_img[i]);
     if (ctx->s_flow[i]) cudaFree(ctx->s_flow[i]);
     if (ctx->s_seg[i]) cudaFree(ctx->s_seg[i]);
+    if (ctx->s_depth[i]) cudaFree(ctx->s_depth[i]);
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
   }
@@ -1270,8 +1273,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_staticw, kNumClasses * 4)) return rc;
   if (c.att_src == 1 || c.att_src >= 3) {
     // se(flow|rgb, [8,19]) (attention_module.py:54-103) or se_block(seg_19, ratio=1) (:9-52)
-    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? "se_seg/" : "se_rgb/");
-    const int din = c.att_src == 1 ? 2 : c.att_src == 3 ? 19 : 3, dh = c.att_src == 3 ? 19 : 8;
+    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? "se_seg/" : c.att_src == 4 ? "se_rgb/" : "se_depth/");
+    const int din = c.att_src == 1 ? 2 : c.att_src == 3 ? 19 : c.att_src == 4 ? 3 : 1, dh = c.att_src == 3 ? 19 : 8;
     const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
     const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
     const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
@@ -1305,10 +1308,11 @@ extern "C" int davo_forward(davo_ctx* ctx, int B, const uint8_t* img, const floa
 
 extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
                                   const float* seg, const float* depth, float* pose_out, void* stream) {
-  (void)depth;
   if (!ctx) return DAVO_ERR_ARG;
   if (pairs < DAVO_PAIRS_ALL || pairs > DAVO_PAIRS_TRAJECTORY_FIRST)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward: pair selection %d unknown", pairs);
+  if (ctx->cfg.att_src == 5 && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward: this variant reads input_depth; got NULL");
+  ctx->cur_depth = depth;
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1) && !flow))
@@ -1344,10 +1348,10 @@ extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const
 
 extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
                                        const float* seg, const float* depth, float* pose_out, void* stream) {
-  (void)depth;
   if (!ctx) return DAVO_ERR_ARG;
   if (pairs < DAVO_PAIRS_ALL || pairs > DAVO_PAIRS_TRAJECTORY_FIRST)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: pair selection %d unknown", pairs);
+  if (ctx->cfg.att_src == 5 && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: this variant reads input_depth; got NULL");
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   const davo_config& c = ctx->cfg;
@@ -1371,6 +1375,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
       CU_OK(cudaMalloc((void**)&ctx->s_seg[i], n_seg * 4 * cs));
       CU_OK(cudaMemset(ctx->s_flow[i], 0, n_flow * 4 * cs));
       CU_OK(cudaMemset(ctx->s_seg[i], 0, n_seg * 4 * cs));
+      if (c.att_src == 5) CU_OK(cudaMalloc((void**)&ctx->s_depth[i], n_seg * 4 * cs));
       CU_OK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
       CU_OK(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
     }
@@ -1419,6 +1424,11 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
         h2d += hw * 4 * 2 * ns;
       }
     }
+    if (c.att_src == 5) {       // se_depth: all three planes (the frame's and the target's are pooled)
+      CU_OK(cudaMemcpyAsync(ctx->s_depth[buf], depth + n_seg * s0, n_seg * 4 * ns, cudaMemcpyHostToDevice, cp));
+      h2d += n_seg * 4 * ns;
+    }
+    ctx->cur_depth = ctx->s_depth[buf];
     CU_OK(cudaEventRecord(ctx->ev_copied[buf], cp));
     CU_OK(cudaStreamWaitEvent(st, ctx->ev_copied[buf], 0));
     // a chunk is a batch of its own: only the first one may hold the first sample's tgt->src0

@@ -52,7 +52,8 @@ struct FrontParams {
   int packed_c;          // 8: [tgt rgb, src rgb, src flow]; 16: the legacy layout of pack_kernel
   int npairs;
   int in_mode;           // 1: flows are concatenated (v1)
-  int att_src;           // 0 none, 1 se_flow, 2 static, 3 se_seg, 4 se_rgb (-> seg): davo.py:1117-1400
+  int att_src;           // 0 none, 1 se_flow, 2 static, 3 se_seg, 4 se_rgb (-> seg), 5 se_depth (-> seg): davo.py:1117-1400
+  int depth_norm;        // "-norm_depth": SE depth input / 80
   int se_in, se_hid;     // SE dense sizes: in -> hid -> 19 (flow 2,8; seg 19,19; rgb 3,8)
   int att_tgt_ones;
   int mask_rgb, mask_flow;
@@ -62,6 +63,7 @@ struct FrontParams {
   const uint8_t* img;    // [B][H][3W][3]
   const float* flow;     // [B][4][H][W][2]
   const float* seg;      // [B][3][H][W][1]
+  const float* depth;    // [B][3][H][W][1] ([src0, tgt, src1]); se_depth sources only
   const float* se_w;     // W1[in][hid] b1[hid] W2[hid][19] b2[19]
   const float* static_w; // sigmoid(seg_channel_weight)[19]
   float* pool_part;      // [mb][kAttFrames][kPoolSplits][kPoolDim]
@@ -95,6 +97,9 @@ __device__ __forceinline__ float se_activation(float v, int act) {
 //                                 are all-zero rows), 19 -> 19 -> 19; excitation * one_hot summed
 //                                 over classes = excitation[label]
 //   se_rgb*_to_seg (davo.py:1277, 1287): pool = mean r, g, b of the frame, 3 -> 8 -> 19
+//   se_depth*_to_seg (davo.py:1214, 1223): pool = mean(depth of the frame + depth of the TARGET):
+//                                 davo.py:1109 adds a Tensor to a Python list, which TensorFlow
+//                                 broadcasts ([d_tgt, d_src0, d_src1] + d_tgt); 1 -> 8 -> 19
 // blockIdx.z = 0: the pair's source frame; 1: the target frame (variants that do not force the
 // target map to ones).
 __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
@@ -124,7 +129,17 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     if (threadIdx.x < kNumClasses) part[threadIdx.x] = (float)s_hist[threadIdx.x];
   } else {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    if (p.att_src == 1) {
+    if (p.att_src == 5) {
+      const float4* df = reinterpret_cast<const float4*>(p.depth + ((size_t)b * 3 + f) * hw);
+      const float4* dt = reinterpret_cast<const float4*>(p.depth + ((size_t)b * 3 + 1) * hw);
+      const int n4 = hw / 4;
+      const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
+      const int beg = blockIdx.x * per, end = min(beg + per, n4);
+      for (int i = beg + threadIdx.x; i < end; i += 256) {
+        const float4 a = __ldg(df + i), c = __ldg(dt + i);
+        s0 += (a.x + c.x) + (a.y + c.y) + (a.z + c.z) + (a.w + c.w);
+      }
+    } else if (p.att_src == 1) {
       const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + (f == 2 ? 1 : 0)) * (size_t)hw * 2);
       const int n4 = hw / 2;                          // float4 = 2 pixels
       const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
@@ -181,6 +196,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     for (int sp = 0; sp < kPoolSplits; ++sp) a += __ldcg(pp + sp * kPoolDim);
     a *= 1.0f / (float)hw;
     if (p.att_src == 4) a = a * (1.0f / 255.0f) * 2.0f - 1.0f;
+    if (p.att_src == 5 && p.depth_norm) a = a / 80.0f;
     s_pool[threadIdx.x] = a;
   }
   __syncthreads();

@@ -72,7 +72,7 @@ class DAVO(object):
             att_src=self.config.att_src, att_tgt_ones=self.config.att_tgt_ones,
             mask_mode=self.config.mask_mode, se_act=self.config.se_act,
             flow_abs=self.config.flow_abs, flow_norm=self.config.flow_norm,
-            posenn_se=self.config.posenn_se, micro_batch=micro_batch)
+            posenn_se=self.config.posenn_se, micro_batch=micro_batch, depth_norm=self.config.depth_norm)
         h = C.c_void_p()
         rc = self._lib.davo_create(C.byref(cfg), self.device, C.byref(h))
         if rc != 0:
@@ -126,25 +126,33 @@ class DAVO(object):
             raise NotImplementedError("davo_b200: inference mode %r is not built (only 'pose')" % (mode,))
         if not self._weights_loaded:
             raise RuntimeError("DAVO.inference: weights not loaded")
+        depth = None
         if inputs is None:
-            img, flow, _depth, seg = (self._resolve(t) for t in self._inputs)
+            img, flow, depth, seg = (self._resolve(t) for t in self._inputs)
         elif isinstance(inputs, dict):
-            img, flow, seg = inputs.get("img"), inputs.get("flow"), inputs.get("seg")
+            img, flow, seg, depth = inputs.get("img"), inputs.get("flow"), inputs.get("seg"), inputs.get("depth")
+        elif len(inputs) == 4:
+            img, flow, seg, depth = inputs
         else:
             img, flow, seg = inputs
+        if self.config.att_src != V.ATT_SE_DEPTH_SEG:
+            depth = None                                  # only the se_depth sources read it
+        elif depth is None:
+            raise ValueError("DAVO.inference: version %r reads input_depth [B,3,H,W,1]" % (self.version,))
         B = int(img.shape[0])
         H, W = self.img_height, self.img_width
-        want = {"img": (B, H, 3 * W, 3), "flow": (B, 4, H, W, 2), "seg": (B, 3, H, W, 1)}
-        for name, t in (("img", img), ("flow", flow), ("seg", seg)):
+        want = {"img": (B, H, 3 * W, 3), "flow": (B, 4, H, W, 2), "seg": (B, 3, H, W, 1), "depth": (B, 3, H, W, 1)}
+        for name, t in (("img", img), ("flow", flow), ("seg", seg), ("depth", depth)):
             if t is not None and tuple(t.shape) != want[name]:
                 raise ValueError("DAVO.inference: %s has shape %s, expected %s" % (name, tuple(t.shape), want[name]))
         if _is_torch(img):
-            return self._run_device(B, img, flow, seg, as_torch, sel)
-        return self._run_host(B, img, flow, seg, sel)
+            return self._run_device(B, img, flow, seg, as_torch, sel, depth)
+        return self._run_host(B, img, flow, seg, sel, depth)
 
-    def _run_device(self, B, img, flow, seg, as_torch, sel=0):
+    def _run_device(self, B, img, flow, seg, as_torch, sel=0, depth=None):
         import torch
-        for name, t, dt in (("img", img, torch.uint8), ("flow", flow, torch.float32), ("seg", seg, torch.float32)):
+        for name, t, dt in (("img", img, torch.uint8), ("flow", flow, torch.float32), ("seg", seg, torch.float32),
+                            ("depth", depth, torch.float32)):
             if t is None:
                 continue
             if not (t.is_cuda and t.device.index == self.device and t.dtype == dt and t.is_contiguous()):
@@ -157,14 +165,14 @@ class DAVO(object):
 
         def launch():
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            self._check(self._lib.davo_forward_pairs(self._h, B, sel, ptr(img), ptr(flow), ptr(seg), None,
+            self._check(self._lib.davo_forward_pairs(self._h, B, sel, ptr(img), ptr(flow), ptr(seg), ptr(depth),
                                                      C.c_void_p(out.data_ptr()), C.c_void_p(stream)), "davo_forward")
 
         # The same buffers called again and again (the bound-inputs form of the reference's
         # sess.run loop): davo_forward only enqueues work, so the third identical call is captured
         # into a CUDA graph and later ones replay it (launch gaps: -13 % latency at B=1, -1.4 % at
         # B=128).  DAVO_B200_GRAPH=0 switches this off; any capture failure does too.
-        key = (B, sel, out.data_ptr()) + tuple(t.data_ptr() if t is not None else 0 for t in (img, flow, seg))
+        key = (B, sel, out.data_ptr()) + tuple(t.data_ptr() if t is not None else 0 for t in (img, flow, seg, depth))
         if self._graph_ok and key == self._graph_key:
             self._graph_hits += 1
         else:
@@ -188,13 +196,14 @@ class DAVO(object):
             return {'pose': out}
         return {'pose': out.cpu().numpy()}
 
-    def _run_host(self, B, img, flow, seg, sel=0):
+    def _run_host(self, B, img, flow, seg, sel=0, depth=None):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         flow = None if flow is None else np.ascontiguousarray(flow, dtype=np.float32)
         seg = None if seg is None else np.ascontiguousarray(seg, dtype=np.float32)
+        depth = None if depth is None else np.ascontiguousarray(depth, dtype=np.float32)
         out = np.empty((B, 2, 6), np.float32)
         ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-        self._check(self._lib.davo_forward_host_pairs(self._h, B, sel, ptr(img), ptr(flow), ptr(seg), None,
+        self._check(self._lib.davo_forward_host_pairs(self._h, B, sel, ptr(img), ptr(flow), ptr(seg), ptr(depth),
                                                       ptr(out), None), "davo_forward_host")
         return {'pose': out}
 

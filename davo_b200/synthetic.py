@@ -49,6 +49,16 @@ def make_inputs(batch: int, height: int = 128, width: int = 416, seed: int = 123
     return img, flow, seg[..., None].copy()
 
 
+def make_depth(batch: int, height: int = 128, width: int = 416, seed: int = 4321) -> np.ndarray:
+    """Seeded input_depth [B,3,H,W,1] (metres, 1..80, smooth over 8x8 blocks): [src0, tgt, src1]
+    (reference davo.py:991-996); read only by the se_depth attention sources."""
+    rng = np.random.default_rng(seed)
+    hb, wb = -(-height // 8), -(-width // 8)
+    blocks = rng.uniform(1.0, 80.0, size=(batch, 3, hb, wb))
+    d = np.repeat(np.repeat(blocks, 8, axis=2), 8, axis=3)[:, :, :height, :width]
+    return d.astype(np.float32)[..., None].copy()
+
+
 def _xavier_uniform(rng, shape):
     kh, kw, cin, cout = shape
     lim = math.sqrt(6.0 / (kh * kw * cin + kh * kw * cout))
@@ -106,7 +116,7 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         w["pose_exp_net/%s/weights" % scope] = _xavier_uniform(rng, shape)
         w["pose_exp_net/%s/biases" % scope] = bias(shape[3])
     se_scopes = {V.ATT_SE_FLOW: ("se_flow", 2, 8), V.ATT_SE_SEG: ("se_seg", 19, 19),
-                 V.ATT_SE_RGB_SEG: ("se_rgb", 3, 8)}
+                 V.ATT_SE_RGB_SEG: ("se_rgb", 3, 8), V.ATT_SE_DEPTH_SEG: ("se_depth", 1, 8)}
     if cfg.att_src in se_scopes:
         scope, din, dh = se_scopes[cfg.att_src]
         for name, (fi, fo) in (("bottleneck_fc", (din, dh)), ("recover_fc", (dh, 19))):

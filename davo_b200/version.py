@@ -22,7 +22,7 @@ POSENN_COUPLE_DIL = 3            # couple_net_v0_dilation          :12-66
 POSENN_COUPLE = 4                # couple_net_v0                   :257-311
 POSENN_DECOUPLE = 5              # decouple_net_v0                 :314-378
 
-ATT_NONE, ATT_SE_FLOW, ATT_STATIC, ATT_SE_SEG, ATT_SE_RGB_SEG = 0, 1, 2, 3, 4
+ATT_NONE, ATT_SE_FLOW, ATT_STATIC, ATT_SE_SEG, ATT_SE_RGB_SEG, ATT_SE_DEPTH_SEG = 0, 1, 2, 3, 4, 5
 MASK_OFF, MASK_RGB, MASK_ALL, MASK_ALL_555 = 0, 1, 2, 3
 ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2
 ABS_NONE, ABS_BOTH, ABS_H, ABS_V = 0, 1, 2, 3
@@ -51,6 +51,8 @@ _UNBUILT_AFTER_SE_FLOW = (
 # since no variable lives under 'pose_exp_net/se_flow' the G11 override does not fire
 # (davo.py:1404-1414).
 _BUILT_AFTER_SE_FLOW = {
+    "-se_depth_wo_tgt_to_seg": (ATT_SE_DEPTH_SEG, 1), # davo.py:1211-1219
+    "-se_depth_to_seg": (ATT_SE_DEPTH_SEG, 0),        # davo.py:1220-1227
     "-se_rgb_wo_tgt_to_seg": (ATT_SE_RGB_SEG, 1),     # davo.py:1274-1283
     "-se_rgb_to_seg": (ATT_SE_RGB_SEG, 0),            # davo.py:1284-1292
     "-se_seg_wo_tgt": (ATT_SE_SEG, 1),                # davo.py:1304-1310
@@ -71,6 +73,8 @@ class DavoConfig:
     flow_abs: int = ABS_NONE
     flow_norm: int = 0
     posenn_se: int = PSE_NONE
+    depth_norm: int = 0         # "-norm_depth" (davo.py:1108-1111); only read by the se_depth sources
+    needs_depth: int = 0        # "depth"/"disp" in the version: the graph reads input_depth (davo.py:960)
     version_tag: str = "v0"
 
     def as_dict(self):
@@ -80,10 +84,9 @@ class DavoConfig:
 def parse_version(version: str) -> DavoConfig:
     """Resolve a version string exactly as ``build_pose_test_graph_davo`` does."""
     assert version is not None                                  # davo.py:959
-    if "depth" in version or "disp" in version:                 # davo.py:960
-        raise NotImplementedError(
-            "davo_b200: depth/disp attention inputs are not built (version %r)" % version)
     cfg = DavoConfig()
+    cfg.needs_depth = 1 if ("depth" in version or "disp" in version) else 0     # davo.py:960
+    cfg.depth_norm = 1 if "-norm_depth" in version else 0                       # davo.py:1108-1111
     # G1 PoseNN-internal SE (davo.py:1010-1017)
     if "-se_insert" in version:
         cfg.posenn_se = PSE_INSERT
@@ -180,6 +183,10 @@ def parse_version(version: str) -> DavoConfig:
             cfg.mask_mode = MASK_OFF
     else:
         cfg.mask_mode = MASK_RGB if "-segmask" in version else MASK_OFF
+    if cfg.needs_depth and cfg.att_src != ATT_SE_DEPTH_SEG and cfg.att_src != ATT_SE_FLOW:
+        # depth/disp is only read by sources of the chain; the ones built are the se_depth*_to_seg pair
+        raise NotImplementedError(
+            "davo_b200: depth/disp attention inputs are not built (version %r)" % version)
     if "-batch_norm" in version:                                # davo.py:1453
         raise NotImplementedError("davo_b200: -batch_norm is not built")
     return cfg

@@ -44,7 +44,8 @@ typedef struct davo_config {
   int32_t posenn;        /* 0 = decouple_sharednet_v0_dilation (nets/posenn.py:189)    */
   int32_t cnv6_out;      /* "-cnv6_<n>", davo.py:1052-1053                             */
   int32_t in_mode;       /* 0 = v0 RGB only, 1 = v1 RGB+flow, davo.py:1057-1065        */
-  int32_t att_src;       /* 0 none, 1 se_flow (davo.py:1175), 2 static (:1390)         */
+  int32_t att_src;       /* 0 none, 1 se_flow (davo.py:1175), 2 static (:1390), 3 se_seg (:1304),
+                            4 se_rgb -> seg (:1274), 5 se_depth -> seg (:1211)          */
   int32_t att_tgt_ones;  /* target-frame map forced to 1, davo.py:1404-1412, :1393     */
   int32_t mask_mode;     /* 0 off, 1 rgb, 2 all, 3 all(.555), davo.py:1415-1450        */
   int32_t se_act;        /* 0 relu, 1 tanh, 2 leaky_relu(0.2), davo.py:1077-1085       */
@@ -52,6 +53,7 @@ typedef struct davo_config {
   int32_t flow_norm;     /* "-norm_flow", davo.py:1088-1091                            */
   int32_t posenn_se;     /* 0 none, 1 insert, 2 skipadd, 3 replace, davo.py:1010-1017  */
   int32_t micro_batch;   /* frame pairs per pass through the conv stack; 0 = default   */
+  int32_t depth_norm;    /* "-norm_depth": SE depth input / 80, davo.py:1108-1111       */
 } davo_config;
 
 /* Stands in for DAVO.__init__ + DAVO.setup_inference (reference davo.py:31-33,
@@ -73,7 +75,8 @@ int davo_finalize_weights(davo_ctx*);
  *   img_u8   device, uint8  [B, H, 3W, 3]   (src0 | tgt | src1 along width)
  *   flow     device, float  [B, 4, H, W, 2] (only [:,0:2] are read, davo.py:978-982)
  *   seg      device, float  [B, 3, H, W, 1] ([src0, tgt, src1], davo.py:1000-1004)
- *   depth    unused by the built variants; pass NULL
+ *   depth    device, float  [B, 3, H, W, 1] ([src0, tgt, src1], davo.py:991-996): read by the
+ *            se_depth variants only (att_src 5); NULL otherwise
  *   pose_out device, float  [B, 2, 6]: rows [tgt->src0, tgt->src1],
  *            cols [rz, ry, rx, tx, ty, tz] (nets/posenn.py:193, davo.py:1458)
  * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream). */

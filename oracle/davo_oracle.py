@@ -288,7 +288,7 @@ def _unsupported(what):
 
 def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.ndarray,
                  weights: Dict[str, np.ndarray], dtype=torch.float64, tf32: bool = False,
-                 taps: Optional[dict] = None) -> np.ndarray:
+                 taps: Optional[dict] = None, depth: Optional[np.ndarray] = None) -> np.ndarray:
     """``DAVO.build_pose_test_graph_davo`` + one ``sess.run`` (davo.py:955-1494, 1553-1569).
 
     img_u8 [B,H,3W,3] uint8; flow [B,4,H,W,2] f32; seg [B,3,H,W,1] f32.
@@ -297,8 +297,7 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
     static / none; other sources raise NotImplementedError.
     """
     assert version is not None                                           # davo.py:959
-    if "depth" in version or "disp" in version:                          # davo.py:960
-        _unsupported("depth/disp inputs")
+    is_read_depth = "depth" in version or "disp" in version            # davo.py:960
     wts = {k: torch.as_tensor(np.asarray(v), dtype=dtype) for k, v in weights.items()}
     B, H, W3, _ = img_u8.shape
     W = W3 // 3
@@ -381,7 +380,25 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att_w.append(w19)
             att.append(class_gather(pred_segs[i], w19))
         use_se_flow = True                                               # davo.py:1404
-    elif re.search("-se_(gp2x2|spp|depth|disp|SegFlow)", version):
+    elif re.search("-se_(gp2x2|spp)", version):
+        _unsupported("attention source in " + version)
+    elif "-se_depth_wo_tgt_to_seg" in version or "-se_depth_to_seg" in version:     # davo.py:1211-1227
+        dp = torch.as_tensor(depth).to(dtype)
+        pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]                     # davo.py:991-996: tgt, src0, src1
+        # davo.py:1109: `[d for d in pred_depths] + pred_depths[0]` is list + Tensor: TensorFlow
+        # converts the list to a [3,B,H,W,1] tensor and BROADCASTS the add, so every SE input is
+        # depth_i + depth_tgt.
+        se_in_d = [d + pred_depths[0] for d in pred_depths]
+        if "-norm_depth" in version:                                     # davo.py:1110-1111
+            se_in_d = [d / 80.0 for d in se_in_d]
+        att, att_w = [], []
+        for i in range(3):
+            w19 = se_weights(se_in_d[i], wts, "pose_exp_net/se_depth", act)
+            att_w.append(w19)
+            att.append(class_gather(pred_segs[i], w19))
+        if "-se_depth_wo_tgt_to_seg" in version:
+            att[0] = torch.ones_like(att[0])                             # davo.py:1218
+    elif re.search("-se_(depth|disp|SegFlow)", version):
         _unsupported("attention source in " + version)
     elif "-se_rgb_wo_tgt_to_seg" in version or "-se_rgb_to_seg" in version:   # davo.py:1274-1292
         att, att_w = [], []

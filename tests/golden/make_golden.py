@@ -29,6 +29,8 @@ CASES = {
     "se_insert": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-no_segmask-se_insert",
     "couple_shared": "v1-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh",
     "couple_shared_se_insert": "v1-sharedNN-dilatedCouplePoseNN-cnv6_64-no_segmask-se_insert",
+    "se_depth": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_depth_wo_tgt_to_seg-fc_tanh",
+    "se_depth_norm_tgt": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_rgb-se_depth_to_seg-norm_depth-fc_lrelu",
     "decouple_net": "v1-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh",
     "couple_net_v0": "v0-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_seg-fc_tanh",
 }
@@ -42,7 +44,8 @@ def main():
         img, flow, seg = S.make_inputs(GOLDEN["batch"], GOLDEN["height"], GOLDEN["width"],
                                        seed=GOLDEN["input_seed"], bad_label_frac=GOLDEN["bad_label_frac"])
         taps = {}
-        pose = O.davo_forward(ver, img, flow, seg, w, torch.float64, taps=taps)
+        depth = S.make_depth(GOLDEN["batch"], GOLDEN["height"], GOLDEN["width"])
+        pose = O.davo_forward(ver, img, flow, seg, w, torch.float64, taps=taps, depth=depth)
         out[key + "/pose"] = pose
         if taps["attention_weights"] is not None:
             out[key + "/att_w"] = np.stack(taps["attention_weights"][1:], 1)     # [B,2,19] src0, src1

@@ -32,11 +32,12 @@ def _need_gpu():
 
 
 def _system(ver, B, weights, inputs, micro_batch=0, device_inputs=True):
+    """inputs = (img, flow, seg[, depth])"""
     sysm = DAVO(version=ver)
     if device_inputs:
         inputs = tuple(torch.as_tensor(x).cuda() for x in inputs)
     sysm.setup_inference(H, W, "davo", 3, B, inputs[0], input_flow=inputs[1], input_seglabel=inputs[2],
-                         device=0, micro_batch=micro_batch)
+                         input_depth=inputs[3] if len(inputs) > 3 else None, device=0, micro_batch=micro_batch)
     sysm.load_weights(weights)
     return sysm, inputs
 
@@ -61,16 +62,21 @@ def test_variants_match_oracle_and_golden(key):
     ver, g = G.CASES[key], G.GOLDEN
     w = S.init_weights(ver, seed=g["weight_seed"], random_bias=True)
     inputs = S.make_inputs(g["batch"], H, W, seed=g["input_seed"], bad_label_frac=g["bad_label_frac"])
-    sysm, _ = _system(ver, g["batch"], w, inputs)
+    depth = S.make_depth(g["batch"], H, W)                                   # read by the se_depth sources only
+    sysm, _ = _system(ver, g["batch"], w, inputs + (depth,))
     out = sysm.inference(None, "pose")["pose"]
     assert out.shape == (2, 2, 6) and out.dtype == np.float32
     _assert_pose(out, GOLD[key + "/pose"])                                  # committed fixture
-    _assert_pose(out, O.davo_forward(ver, *inputs, w, torch.float64))       # live oracle
+    _assert_pose(out, O.davo_forward(ver, *inputs, w, torch.float64, depth=depth))       # live oracle
     if key + "/att_w" in GOLD.files:
         sample_units = sysm.config.posenn >= 2          # non-shared nets: one evaluation (unit) per sample
         for p in range(2 if sample_units else 4):
             want = GOLD[key + "/att_w"][p, 0] if sample_units else GOLD[key + "/att_w"][p // 2, p % 2]
             np.testing.assert_allclose(sysm.get_intermediate("att_weights", p), want, rtol=2e-6, atol=1e-7)
+    if sysm.config.att_src == 5:                                             # host-buffer entry point with depth
+        assert np.array_equal(out, sysm.inference(None, "pose", inputs=inputs + (depth,))["pose"])
+        with pytest.raises(ValueError):
+            sysm.inference(None, "pose", inputs=inputs)
 
 
 def test_every_layer_matches_oracle_per_pixel(monkeypatch):

@@ -88,7 +88,8 @@ def test_oracle_reproduces_committed_golden(key):
     # inputs are generated batch-major from one stream: regenerate the full batch, use sample 0
     img, flow, seg = S.make_inputs(g["batch"], g["height"], g["width"], seed=g["input_seed"],
                                    bad_label_frac=g["bad_label_frac"])
-    pose = O.davo_forward(ver, img[:1], flow[:1], seg[:1], w, torch.float64)
+    depth = S.make_depth(g["batch"], g["height"], g["width"])
+    pose = O.davo_forward(ver, img[:1], flow[:1], seg[:1], w, torch.float64, depth=depth[:1])
     np.testing.assert_allclose(pose[0], GOLD[key + "/pose"][0], rtol=1e-9, atol=1e-13)
 
 

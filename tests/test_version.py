@@ -74,4 +74,9 @@ def test_unbuilt_sources_fail_loudly(tok):
 
 def test_depth_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-fc_tanh")
+        V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt-fc_tanh")
+    with pytest.raises(NotImplementedError):
+        V.parse_version(BASE + "-segmask_all-se_disp_wo_tgt_to_seg-fc_tanh")
+    c = V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-norm_depth-fc_tanh")     # davo.py:1211-1219
+    assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 1, 1, 1)
+    assert V.parse_version(BASE + "-segmask_all-se_depth_to_seg").att_tgt_ones == 0
