@@ -891,7 +891,9 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   fp.pool_part = ctx->d_pool; fp.pool_count = ctx->d_poolcnt; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
   if (c.att_src == 1 || c.att_src >= 3) {
     static const int se_dims[6][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}, {1, 8}};
-    fp.se_in = se_dims[c.att_src][0]; fp.se_hid = se_dims[c.att_src][1];
+    fp.se_in = se_dims[c.att_src][0]; fp.se_hid = c.se_hidden > 0 ? c.se_hidden : se_dims[c.att_src][1];
+    fp.pool_2x2 = (c.att_src == 1 && c.se_pool == 1) ? 1 : 0;
+    if (fp.pool_2x2) fp.se_in = 8;
     const int src_frames = ctx->unit_sample ? 2 : 1;
     se_pool_kernel<<<dim3(kPoolSplits, npairs, src_frames + (c.att_tgt_ones ? 0 : 1)), 256, 0, st>>>(fp);
     CU_OK(cudaGetLastError());
@@ -981,6 +983,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128)", cfg->cnv6_out);
   if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
   if (cfg->att_src < 0 || cfg->att_src > 5) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
+  if (cfg->se_pool < 0 || cfg->se_pool > 1 || cfg->se_hidden < 0 || cfg->se_hidden > 19 || (cfg->se_pool == 1 && cfg->att_src != 1))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad se_pool / se_hidden");
   if (cfg->att_src == 5 && ((cfg->H * cfg->W) % 4) != 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: se_depth needs H*W % 4 == 0");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1274,7 +1278,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   if (c.att_src == 1 || c.att_src >= 3) {
     // se(flow|rgb, [8,19]) (attention_module.py:54-103) or se_block(seg_19, ratio=1) (:9-52)
     const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? "se_seg/" : c.att_src == 4 ? "se_rgb/" : "se_depth/");
-    const int din = c.att_src == 1 ? 2 : c.att_src == 3 ? 19 : c.att_src == 4 ? 3 : 1, dh = c.att_src == 3 ? 19 : 8;
+    const int din = c.att_src == 1 ? (c.se_pool == 1 ? 8 : 2) : c.att_src == 3 ? 19 : c.att_src == 4 ? 3 : 1;
+    const int dh = c.se_hidden > 0 ? c.se_hidden : (c.att_src == 3 ? 19 : 8);
     const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
     const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
     const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");

@@ -54,6 +54,8 @@ struct FrontParams {
   int in_mode;           // 1: flows are concatenated (v1)
   int att_src;           // 0 none, 1 se_flow, 2 static, 3 se_seg, 4 se_rgb (-> seg), 5 se_depth (-> seg): davo.py:1117-1400
   int depth_norm;        // "-norm_depth": SE depth input / 80
+  int pool_2x2;          // se_flow only: mode='gp2x2' (attention_module.py:68-78): the means of the four
+                         // quadrants [:h/2,:w/2], [:h/2,w/2:], [h/2:,:w/2], [h/2:,w/2:] concatenated -> 8 inputs
   int se_in, se_hid;     // SE dense sizes: in -> hid -> 19 (flow 2,8; seg 19,19; rgb 3,8)
   int att_tgt_ones;
   int mask_rgb, mask_flow;
@@ -144,12 +146,41 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
       const int n4 = hw / 2;                          // float4 = 2 pixels
       const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
       const int beg = blockIdx.x * per, end = min(beg + per, n4);
-      if (f != 1)                                     // the target's flow is all zeros (davo.py:979)
+      if (f != 1 && !p.pool_2x2)                      // the target's flow is all zeros (davo.py:979)
         for (int i = beg + threadIdx.x; i < end; i += 256) {
           const float4 v = __ldg(src + i);
           s0 += se_in_x(v.x, p) + se_in_x(v.z, p);
           s1 += se_in_y(v.y, p) + se_in_y(v.w, p);
         }
+      if (f != 1 && p.pool_2x2) {
+        // per-quadrant sums: this thread's 8 accumulators, reduced over the block into part[0..7]
+        float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int hh = p.H / 2, hw2 = p.W / 2;
+        for (int i = beg + threadIdx.x; i < end; i += 256) {
+          const float4 v = __ldg(src + i);
+          const int pix = 2 * i, h = pix / p.W, w = pix - h * p.W;       // W is even: both pixels in one row
+          const int qa = (h >= hh ? 2 : 0) + (w >= hw2 ? 1 : 0), qb = (h >= hh ? 2 : 0) + (w + 1 >= hw2 ? 1 : 0);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            if (qa == k2) { q[2 * k2] += se_in_x(v.x, p); q[2 * k2 + 1] += se_in_y(v.y, p); }
+            if (qb == k2) { q[2 * k2] += se_in_x(v.z, p); q[2 * k2 + 1] += se_in_y(v.w, p); }
+          }
+        }
+        __shared__ float red8[8][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+          if ((threadIdx.x & 31) == 0) red8[threadIdx.x >> 5][j] = q[j];
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) {
+          float a = 0.f;
+          for (int i = 0; i < 8; ++i) a += red8[i][threadIdx.x];
+          part[threadIdx.x] = a;
+        }
+        __syncthreads();
+      }
     } else {
       // byte sums are exact; the affine map to [-1, 1] (davo.py:1519-1522) is applied to the mean
       const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
@@ -174,11 +205,12 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
       red[threadIdx.x >> 5][0] = s0; red[threadIdx.x >> 5][1] = s1; red[threadIdx.x >> 5][2] = s2;
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 3 && !(p.att_src == 1 && p.pool_2x2 && f != 1)) {
       float a = 0.f;
       for (int i = 0; i < 8; ++i) a += red[i][threadIdx.x];
       part[threadIdx.x] = a;
     }
+    if (p.att_src == 1 && p.pool_2x2 && f == 1 && threadIdx.x >= 3 && threadIdx.x < 8) part[threadIdx.x] = 0.f;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -194,7 +226,13 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     const float* pp = p.pool_part + ((size_t)pl * kAttFrames + fr) * kPoolSplits * kPoolDim + threadIdx.x;
     float a = 0.f;
     for (int sp = 0; sp < kPoolSplits; ++sp) a += __ldcg(pp + sp * kPoolDim);
-    a *= 1.0f / (float)hw;
+    if (p.att_src == 1 && p.pool_2x2) {            // quadrant pixel counts (attention_module.py:70-71: h//2, w//2)
+      const int qd = threadIdx.x >> 1;
+      const int rows = (qd & 2) ? p.H - p.H / 2 : p.H / 2, cols = (qd & 1) ? p.W - p.W / 2 : p.W / 2;
+      a *= 1.0f / (float)(rows * cols);
+    } else {
+      a *= 1.0f / (float)hw;
+    }
     if (p.att_src == 4) a = a * (1.0f / 255.0f) * 2.0f - 1.0f;
     if (p.att_src == 5 && p.depth_norm) a = a / 80.0f;
     s_pool[threadIdx.x] = a;

@@ -119,6 +119,10 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
                  V.ATT_SE_RGB_SEG: ("se_rgb", 3, 8), V.ATT_SE_DEPTH_SEG: ("se_depth", 1, 8)}
     if cfg.att_src in se_scopes:
         scope, din, dh = se_scopes[cfg.att_src]
+        if cfg.se_pool == 1:
+            din *= 4                                     # gp2x2: four quadrant means concatenated
+        if cfg.se_hidden:
+            dh = cfg.se_hidden
         for name, (fi, fo) in (("bottleneck_fc", (din, dh)), ("recover_fc", (dh, 19))):
             std = math.sqrt(1.3 * 2.0 / fi)
             w["pose_exp_net/%s/%s/kernel" % (scope, name)] = _trunc_normal(rng, (fi, fo), std)

@@ -35,7 +35,7 @@ _UNBUILT_SOURCES = (
     "-se_flow_on_depthseg", "-se_mixDepthFlow", "-se_mixDispFlow",
 )
 _UNBUILT_AFTER_SE_FLOW = (
-    "-se_gp2x2_flow_nobottle", "-se_gp2x2_flow", "-se_spp21_flow", "-se_spp2_flow",
+    "-se_spp21_flow", "-se_spp2_flow",
     "-se_spp_flow", "-se_spp864_flow", "-se_depth_wo_tgt_to_seg", "-se_depth_to_seg",
     "-se_depth_wo_tgt", "-se_depth", "-se_disp_wo_tgt_to_seg", "-se_disp_to_seg",
     "-se_disp_wo_tgt", "-se_disp", "-se_rgb_wo_tgt_to_seg", "-se_rgb_to_seg",
@@ -74,6 +74,8 @@ class DavoConfig:
     flow_norm: int = 0
     posenn_se: int = PSE_NONE
     depth_norm: int = 0         # "-norm_depth" (davo.py:1108-1111); only read by the se_depth sources
+    se_pool: int = 0            # se_flow: 0 = global mean, 1 = gp2x2 (davo.py:1181-1192)
+    se_hidden: int = 0          # SE bottleneck width, 0 = default (8; se_seg 19); gp2x2_flow_nobottle: 19
     needs_depth: int = 0        # "depth"/"disp" in the version: the graph reads input_depth (davo.py:960)
     version_tag: str = "v0"
 
@@ -151,6 +153,13 @@ def parse_version(version: str) -> DavoConfig:
     if "-se_flow" in version:                                   # davo.py:1175
         cfg.att_src = ATT_SE_FLOW
         cfg.att_tgt_ones = 1                                    # davo.py:1404-1412
+    elif "-se_gp2x2_flow_nobottle" in version or "-se_gp2x2_flow" in version:     # davo.py:1181-1192
+        # se(flow, "se_flow", [19,19] | [8,19], mode='gp2x2'): the variables live under
+        # pose_exp_net/se_flow, so the G11 override (target map := 1) fires as for -se_flow
+        cfg.att_src = ATT_SE_FLOW
+        cfg.att_tgt_ones = 1
+        cfg.se_pool = 1
+        cfg.se_hidden = 19 if "-se_gp2x2_flow_nobottle" in version else 8
     else:
         chain_hit = None
         for tok in _UNBUILT_AFTER_SE_FLOW:                      # reference order: first match wins

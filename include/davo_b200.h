@@ -54,6 +54,8 @@ typedef struct davo_config {
   int32_t posenn_se;     /* 0 none, 1 insert, 2 skipadd, 3 replace, davo.py:1010-1017  */
   int32_t micro_batch;   /* frame pairs per pass through the conv stack; 0 = default   */
   int32_t depth_norm;    /* "-norm_depth": SE depth input / 80, davo.py:1108-1111       */
+  int32_t se_pool;       /* se_flow only: 0 global mean, 1 gp2x2 (four quadrant means), davo.py:1181-1192 */
+  int32_t se_hidden;     /* width of the SE bottleneck; 0 = the source's default (8; se_seg 19)  */
 } davo_config;
 
 /* Stands in for DAVO.__init__ + DAVO.setup_inference (reference davo.py:31-33,

@@ -90,14 +90,19 @@ def _act(name: str):
 
 
 def se_weights(x_nhwc: torch.Tensor, wts: Dict[str, torch.Tensor], scope: str,
-               activation: str) -> torch.Tensor:
+               activation: str, mode: str = "gp") -> torch.Tensor:
     """``se(input, name, layer_channels, mode='gp', activation)`` -> [B, units2].
 
     nets/attention_module.py:54-103: global average pool (:66), dense +
     activation (:89-94), dense + sigmoid (:96-101); returns the excitation
     vector only.
     """
-    pool = x_nhwc.mean(dim=(1, 2))                                       # :66
+    if mode == "gp2x2":                                                  # :68-78
+        h, w = x_nhwc.shape[1] // 2, x_nhwc.shape[2] // 2
+        pool = torch.cat([x_nhwc[:, :h, :w].mean(dim=(1, 2)), x_nhwc[:, :h, w:].mean(dim=(1, 2)),
+                          x_nhwc[:, h:, :w].mean(dim=(1, 2)), x_nhwc[:, h:, w:].mean(dim=(1, 2))], dim=-1)
+    else:
+        pool = x_nhwc.mean(dim=(1, 2))                                   # :66
     fc1 = _act(activation)(pool @ wts[scope + "/bottleneck_fc/kernel"]
                            + wts[scope + "/bottleneck_fc/bias"])        # :89-94
     return torch.sigmoid(fc1 @ wts[scope + "/recover_fc/kernel"]
@@ -380,6 +385,13 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att_w.append(w19)
             att.append(class_gather(pred_segs[i], w19))
         use_se_flow = True                                               # davo.py:1404
+    elif "-se_gp2x2_flow_nobottle" in version or "-se_gp2x2_flow" in version:   # davo.py:1181-1192
+        att, att_w = [], []
+        for i in range(3):
+            w19 = se_weights(se_in[i], wts, "pose_exp_net/se_flow", act, mode="gp2x2")
+            att_w.append(w19)
+            att.append(class_gather(pred_segs[i], w19))
+        use_se_flow = True                               # variables under pose_exp_net/se_flow (davo.py:1404)
     elif re.search("-se_(gp2x2|spp)", version):
         _unsupported("attention source in " + version)
     elif "-se_depth_wo_tgt_to_seg" in version or "-se_depth_to_seg" in version:     # davo.py:1211-1227

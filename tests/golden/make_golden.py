@@ -31,6 +31,8 @@ CASES = {
     "couple_shared_se_insert": "v1-sharedNN-dilatedCouplePoseNN-cnv6_64-no_segmask-se_insert",
     "se_depth": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_depth_wo_tgt_to_seg-fc_tanh",
     "se_depth_norm_tgt": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_rgb-se_depth_to_seg-norm_depth-fc_lrelu",
+    "gp2x2_flow": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_gp2x2_flow-abs_flow-fc_tanh",
+    "gp2x2_flow_nobottle": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_gp2x2_flow_nobottle-norm_flow-fc_tanh",
     "decouple_net": "v1-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh",
     "couple_net_v0": "v0-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_seg-fc_tanh",
 }

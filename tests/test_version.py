@@ -66,7 +66,7 @@ def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_rgb_wo_tgt", "-se_gp2x2_seg", "-se_gp2x2_flow", "-se_mixSegFlow"])
+@pytest.mark.parametrize("tok", ["-se_rgb_wo_tgt", "-se_gp2x2_seg", "-se_spp21_flow", "-se_mixSegFlow"])
 def test_unbuilt_sources_fail_loudly(tok):
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
