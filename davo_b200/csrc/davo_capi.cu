@@ -12,8 +12,16 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "conv_cm.cuh"
@@ -25,6 +33,83 @@ using namespace davo;
 namespace {
 
 thread_local std::string g_create_error;
+
+// A few host threads for the one CPU pass of the host-buffer entry point (label floats -> bytes).
+class HostPool {
+ public:
+  explicit HostPool(int n) {
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i); });
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> g(m_); stop_ = true; ++epoch_; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size() + 1; }
+  // fn(part, parts) on every worker and on the calling thread; returns when all are done
+  void run(const std::function<void(int, int)>& fn) {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      fn_ = &fn; pending_ = (int)workers_.size(); ++epoch_;
+    }
+    cv_.notify_all();
+    fn((int)workers_.size(), size());
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+  }
+ private:
+  void loop(int id) {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void(int, int)>* fn;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+        fn = fn_;
+      }
+      (*fn)(id, size());
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int, int)>* fn_ = nullptr;
+  int pending_ = 0;
+  unsigned long epoch_ = 0;
+  bool stop_ = false;
+};
+
+// tf.cast(label, int32) (truncation toward zero, davo.py:1115) -> byte; anything outside 0..18
+// becomes 255 (an all-zero one_hot row).  NaN maps to 0 as the device conversion does.
+inline void labels_to_bytes(const float* src, uint8_t* dst, size_t n) {
+  size_t i = 0;
+#if defined(__SSE2__)
+  const __m128 lo = _mm_set1_ps(-1.0f), hi = _mm_set1_ps(19.0f);
+  const __m128i inval = _mm_set1_epi32(255);
+  for (; i + 16 <= n; i += 16) {
+    __m128i r[4];
+    for (int k = 0; k < 4; ++k) {
+      const __m128 v = _mm_loadu_ps(src + i + 4 * k);
+      const __m128i ok = _mm_castps_si128(_mm_and_ps(_mm_cmpgt_ps(v, lo), _mm_cmplt_ps(v, hi)));
+      const __m128i nan = _mm_castps_si128(_mm_cmpunord_ps(v, v));
+      const __m128i iv = _mm_cvttps_epi32(v);
+      r[k] = _mm_or_si128(_mm_and_si128(ok, iv), _mm_andnot_si128(ok, _mm_andnot_si128(nan, inval)));
+    }
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i),
+                     _mm_packus_epi16(_mm_packs_epi32(r[0], r[1]), _mm_packs_epi32(r[2], r[3])));
+  }
+#endif
+  for (; i < n; ++i) {
+    const float v = src[i];
+    dst[i] = (v > -1.0f && v < 19.0f) ? (uint8_t)(int)v : (v != v ? (uint8_t)0 : (uint8_t)255);
+  }
+}
 
 struct HostTensor {
   std::vector<int64_t> shape;
@@ -137,6 +222,13 @@ struct davo_ctx {
   static constexpr int kStage = 3;  // staging buffers: copy of chunk i+2 never waits for compute of chunk i
   uint8_t* s_img[kStage] = {};
   float *s_flow[kStage] = {}, *s_seg[kStage] = {}, *s_depth[kStage] = {}, *s_pose = nullptr;
+  // Labels cross PCIe as bytes: converted on the CPU into pinned staging (h_seg8), copied to s_seg8.
+  uint8_t *h_seg8[kStage] = {}, *s_seg8[kStage] = {};
+  cudaEvent_t ev_seg8[kStage] = {};  // h_seg8[i] has been read by its copy
+  HostPool* pool = nullptr;
+  bool host_seg8 = true;
+  const uint8_t* cur_seg8 = nullptr; // byte labels of the chunk being enqueued (NULL: float labels)
+  const uint8_t* last_seg8 = nullptr;
   int s_chunk = 0;                  // samples per staging buffer
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[kStage] = {}, ev_consumed[kStage] = {}, ev_start = nullptr;
@@ -887,6 +979,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   fp.mask_flow = c.mask_mode == 2;
   fp.se_act = c.se_act; fp.flow_abs = c.flow_abs; fp.flow_norm = c.flow_norm;
   fp.img = img; fp.flow = flow; fp.seg = seg; fp.depth = ctx->cur_depth; fp.depth_norm = c.depth_norm;
+  fp.seg8 = seg ? nullptr : ctx->cur_seg8;       // the host entry point passes seg = NULL with byte labels
   fp.se_w = ctx->d_sew; fp.static_w = ctx->d_staticw;
   fp.pool_part = ctx->d_pool; fp.pool_count = ctx->d_poolcnt; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
   if (c.att_src == 1 || c.att_src >= 3) {
@@ -1009,6 +1102,7 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   ctx->unit_sample = cfg->posenn >= 2;
   if (mb > ctx->max_units()) mb = ctx->max_units();
   ctx->mb = mb;
+  if (const char* e = getenv("DAVO_B200_HOST_SEG8")) ctx->host_seg8 = strcmp(e, "0") != 0;   // "0": labels cross PCIe as floats
   if (const char* cr = getenv("DAVO_B200_WEIGHT_ROUNDING"))     // "nearest": plain round-to-nearest
     ctx->compensated_rounding = strcmp(cr, "nearest") != 0;
   *out = ctx;
@@ -1024,9 +1118,13 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
     if (ctx->s_flow[i]) cudaFree(ctx->s_flow[i]);
     if (ctx->s_seg[i]) cudaFree(ctx->s_seg[i]);
     if (ctx->s_depth[i]) cudaFree(ctx->s_depth[i]);
+    if (ctx->s_seg8[i]) cudaFree(ctx->s_seg8[i]);
+    if (ctx->h_seg8[i]) cudaFreeHost(ctx->h_seg8[i]);
+    if (ctx->ev_seg8[i]) cudaEventDestroy(ctx->ev_seg8[i]);
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
   }
+  delete ctx->pool;
   if (ctx->s_pose) cudaFree(ctx->s_pose);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1318,6 +1416,7 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
     return fail(ctx, DAVO_ERR_ARG, "davo_forward: pair selection %d unknown", pairs);
   if (ctx->cfg.att_src == 5 && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward: this variant reads input_depth; got NULL");
   ctx->cur_depth = depth;
+  ctx->cur_seg8 = nullptr;
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1) && !flow))
@@ -1338,6 +1437,7 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
   ctx->last_launches = launches;
   ctx->last_npairs_mb = last_n;
   ctx->last_img = img; ctx->last_flow = flow; ctx->last_seg = seg; ctx->last_pose = pose_out; ctx->last_B = B;
+  ctx->last_seg8 = nullptr;
   ctx->last_pairs = pairs;
   return 0;
 }
@@ -1381,10 +1481,20 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
       CU_OK(cudaMemset(ctx->s_flow[i], 0, n_flow * 4 * cs));
       CU_OK(cudaMemset(ctx->s_seg[i], 0, n_seg * 4 * cs));
       if (c.att_src == 5) CU_OK(cudaMalloc((void**)&ctx->s_depth[i], n_seg * 4 * cs));
+      if (ctx->host_seg8 && c.att_src != 0) {
+        CU_OK(cudaMalloc((void**)&ctx->s_seg8[i], n_seg * cs));
+        CU_OK(cudaHostAlloc((void**)&ctx->h_seg8[i], n_seg * cs, cudaHostAllocDefault));
+        CU_OK(cudaEventCreateWithFlags(&ctx->ev_seg8[i], cudaEventDisableTiming));
+      }
       CU_OK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
       CU_OK(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
     }
     CU_OK(cudaMalloc((void**)&ctx->s_pose, (size_t)12 * 4 * c.max_batch));
+    if (ctx->host_seg8 && c.att_src != 0) {
+      int nthreads = std::max(2, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+      if (const char* e = getenv("DAVO_B200_HOST_THREADS")) nthreads = std::max(1, std::min(atoi(e), 32));
+      ctx->pool = new HostPool(nthreads - 1);
+    }
     CU_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CU_OK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
   }
@@ -1401,13 +1511,12 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   if (ctx->unit_sample) pairs = kUnitsAreSamples;
   if (pairs == DAVO_PAIRS_TRAJECTORY || pairs == DAVO_PAIRS_TRAJECTORY_FIRST)
     CU_OK(cudaMemsetAsync(ctx->s_pose, 0, (size_t)B * 12 * sizeof(float), st));
-  // The copy is the bound, so the time after the LAST copy is what compute adds: the final chunks
-  // taper (.., cs, cs/2, cs/4, cs/4) so that only a quarter chunk is computed after the copies end.
+  // With byte labels the copy of a chunk (0.36 ms per 16 samples) and its compute (0.43 ms per 32
+  // pairs) are nearly balanced, so equal chunks are best: tapering the last ones (tried) only adds
+  // passes that are too small to fill the GPU.
   int ns = 0, last_ns = 0;
   for (int s0 = 0; s0 < B; s0 += ns, ++chunk) {
-    const int left = B - s0;
-    const int minc = std::max(1, cs / 4);
-    ns = left > cs + cs / 2 ? cs : left > 2 * minc ? std::min(cs, (left + 1) / 2) : std::min(left, minc);
+    ns = std::min(cs, B - s0);
     last_ns = ns;
     const int buf = chunk % davo_ctx::kStage;
     if (chunk >= davo_ctx::kStage) CU_OK(cudaStreamWaitEvent(cp, ctx->ev_consumed[buf], 0));
@@ -1418,7 +1527,36 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
                               cudaMemcpyHostToDevice, cp));
       h2d += n_flow * 2 * ns;
     }
-    if (need_seg) {
+    ctx->cur_seg8 = nullptr;
+    if (need_seg && ctx->host_seg8) {
+      // Labels are small integers held in floats: convert the planes the graph reads to bytes on
+      // the CPU (a few threads, while the DMA engine moves this chunk's image and flow) and send a
+      // quarter of the bytes.  The pinned buffer is reused every kStage chunks: wait for its copy.
+      if (chunk >= davo_ctx::kStage) CU_OK(cudaEventSynchronize(ctx->ev_seg8[buf]));
+      const float* src = seg + n_seg * s0;
+      uint8_t* dst = ctx->h_seg8[buf];
+      const int planes[3] = {0, 2, 1};
+      const int npl = seg_tgt ? 3 : 2;
+      const size_t jobs = (size_t)ns * npl;
+      ctx->pool->run([&](int part, int parts) {
+        // split every plane into `parts` pieces so that few-sample chunks still use all threads
+        for (size_t j = 0; j < jobs; ++j) {
+          const size_t off = ((j / npl) * 3 + planes[j % npl]) * hw;
+          const size_t beg = hw * part / parts, end = hw * (part + 1) / parts;
+          labels_to_bytes(src + off + beg, dst + off + beg, end - beg);
+        }
+      });
+      if (seg_tgt) {
+        CU_OK(cudaMemcpyAsync(ctx->s_seg8[buf], dst, n_seg * ns, cudaMemcpyHostToDevice, cp));
+        h2d += n_seg * ns;
+      } else {
+        for (int pl = 0; pl < 3; pl += 2)
+          CU_OK(cudaMemcpy2DAsync(ctx->s_seg8[buf] + hw * pl, n_seg, dst + hw * pl, n_seg, hw, ns, cudaMemcpyHostToDevice, cp));
+        h2d += hw * 2 * ns;
+      }
+      CU_OK(cudaEventRecord(ctx->ev_seg8[buf], cp));
+      ctx->cur_seg8 = ctx->s_seg8[buf];
+    } else if (need_seg) {
       if (seg_tgt) {
         CU_OK(cudaMemcpyAsync(ctx->s_seg[buf], seg + n_seg * s0, n_seg * 4 * ns, cudaMemcpyHostToDevice, cp));
         h2d += n_seg * 4 * ns;
@@ -1442,7 +1580,8 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
     static const bool copy_only = getenv("DAVO_B200_HOST_COPY_ONLY") != nullptr;   // experiment: time the copies alone
     for (int q0 = 0; q0 < np_chunk && !copy_only; q0 += ctx->mb)
       if (int rc = run_microbatch(ctx, chunk_pairs, q0, std::min(ctx->mb, np_chunk - q0), ctx->s_img[buf],
-                                  ctx->s_flow[buf], ctx->s_seg[buf], ctx->s_pose + (size_t)12 * s0, st, &launches))
+                                  ctx->s_flow[buf], ctx->cur_seg8 ? nullptr : ctx->s_seg[buf],
+                                  ctx->s_pose + (size_t)12 * s0, st, &launches))
         return rc;
     CU_OK(cudaEventRecord(ctx->ev_consumed[buf], st));
     last_n = np_chunk;
@@ -1455,7 +1594,8 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   ctx->last_d2h = (long long)12 * 4 * B;
   const int lastbuf = (chunk - 1) % davo_ctx::kStage;
   ctx->last_img = ctx->s_img[lastbuf]; ctx->last_flow = ctx->s_flow[lastbuf];
-  ctx->last_seg = ctx->s_seg[lastbuf]; ctx->last_pose = ctx->s_pose; ctx->last_B = last_ns;
+  ctx->last_seg = ctx->cur_seg8 ? nullptr : ctx->s_seg[lastbuf]; ctx->last_seg8 = ctx->cur_seg8;
+  ctx->last_pose = ctx->s_pose; ctx->last_B = last_ns;
   ctx->last_pairs = (pairs == DAVO_PAIRS_TRAJECTORY_FIRST && chunk > 1) ? DAVO_PAIRS_TRAJECTORY : pairs;
   return 0;
 }
@@ -1524,6 +1664,7 @@ extern "C" int davo_debug_layer_timing(davo_ctx* ctx, int layer, long long* out,
   if (!ctx || layer < 0 || layer > 6 || !out) return DAVO_ERR_ARG;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int npairs = std::min(ctx->last_B * (ctx->unit_sample ? 1 : 2), ctx->mb);
+  ctx->cur_seg8 = ctx->last_seg8;
   if (int rc = launch_conv(ctx, ctx->layers[layer], npairs, st)) return rc;
   if (int rc = launch_conv(ctx, ctx->layers[layer], npairs, st)) return rc;
   CU_OK(cudaStreamSynchronize(st));
@@ -1545,6 +1686,7 @@ extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int*
   CU_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int npairs = std::min(ctx->last_B * (ctx->unit_sample ? 1 : 2), ctx->mb);
+  ctx->cur_seg8 = ctx->last_seg8;
   if (npairs_out) *npairs_out = npairs;
   cudaEvent_t e0, e1;
   CU_OK(cudaEventCreate(&e0));

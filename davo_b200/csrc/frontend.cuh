@@ -65,6 +65,8 @@ struct FrontParams {
   const uint8_t* img;    // [B][H][3W][3]
   const float* flow;     // [B][4][H][W][2]
   const float* seg;      // [B][3][H][W][1]
+  const uint8_t* seg8;   // the same labels as bytes (255 = outside 0..18), or NULL: the host entry point
+                         // converts the float labels on the CPU so that a quarter of their bytes crosses PCIe
   const float* depth;    // [B][3][H][W][1] ([src0, tgt, src1]); se_depth sources only
   const float* se_w;     // W1[in][hid] b1[hid] W2[hid][19] b2[19]
   const float* static_w; // sigmoid(seg_channel_weight)[19]
@@ -73,6 +75,23 @@ struct FrontParams {
   float* att_w;          // [mb][kAttFrames][19], slots as in unit_frame
   float* packed;         // [mb][H][W][16]
 };
+
+// Label of pixel `pix` of plane `plane` (element offset of the plane = plane index * H*W) as the
+// reference's tf.cast(seg, int32) (davo.py:1115: truncation toward zero); bytes are already ints.
+__device__ __forceinline__ int label_at(const FrontParams& p, size_t plane_off, int pix) {
+  if (p.seg8) return p.seg8[plane_off + pix];
+  return (int)__ldg(p.seg + plane_off + pix);
+}
+// four consecutive labels (pix % 4 == 0)
+__device__ __forceinline__ void labels4_at(const FrontParams& p, size_t plane_off, int pix, int (&lab)[4]) {
+  if (p.seg8) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p.seg8 + plane_off + pix));
+    lab[0] = w & 255u; lab[1] = (w >> 8) & 255u; lab[2] = (w >> 16) & 255u; lab[3] = w >> 24;
+  } else {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p.seg + plane_off + pix));
+    lab[0] = (int)v.x; lab[1] = (int)v.y; lab[2] = (int)v.z; lab[3] = (int)v.w;
+  }
+}
 
 __device__ __forceinline__ float se_in_x(float v, const FrontParams& p) {
   if (p.flow_norm) v = (v - 0.32140523f) / 15.384229f;
@@ -120,11 +139,11 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   if (p.att_src == 3) {
     if (threadIdx.x < kNumClasses) s_hist[threadIdx.x] = 0;
     __syncthreads();
-    const float* seg = p.seg + ((size_t)b * 3 + f) * hw;
+    const size_t seg_off = ((size_t)b * 3 + f) * hw;
     const int per = (hw + kPoolSplits - 1) / kPoolSplits;
     const int beg = blockIdx.x * per, end = min(beg + per, hw);
     for (int i = beg + threadIdx.x; i < end; i += 256) {
-      const int lab = (int)__ldg(seg + i);                      // tf.cast truncates toward zero
+      const int lab = label_at(p, seg_off, i);                   // tf.cast truncates toward zero
       if (lab >= 0 && lab < kNumClasses) atomicAdd(&s_hist[lab], 1);   // integer counts: exact, order-free
     }
     __syncthreads();
@@ -293,8 +312,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
   const int lane = threadIdx.x & 31, j = lane & 3;
   const float inv_w = 1.0f / (float)p.W;
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
-  const float* seg_src = p.seg + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw;
-  const float* seg_tgt = p.seg + ((size_t)b * 3 + 1) * hw;
+  const size_t seg_src = ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw, seg_tgt = ((size_t)b * 3 + 1) * hw;
   const float2* flow_src = reinterpret_cast<const float2*>(p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2);
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * kPackedC);
   const int src_col0 = (k == 0) ? 0 : 2 * p.W;
@@ -305,10 +323,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
     const int row_off = pix + 2 * p.W * h;                      // h * 3W + w
     float a_src = 1.0f, a_tgt = 1.0f;
     if (p.att_src != 0) {
-      const int lab = (int)__ldg(seg_src + pix);                // tf.cast truncates toward zero
+      const int lab = label_at(p, seg_src, pix);                 // tf.cast truncates toward zero
       a_src = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;  // one_hot: out of range -> 0
       if (!p.att_tgt_ones) {
-        const int lt = (int)__ldg(seg_tgt + pix);
+        const int lt = label_at(p, seg_tgt, pix);
         a_tgt = (lt >= 0 && lt < kNumClasses) ? s_wt[lt] : 0.0f;
       }
     }
@@ -386,8 +404,7 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
-  const float* seg_src = p.seg + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw;
-  const float* seg_tgt = p.seg + ((size_t)b * 3 + 1) * hw;
+  const size_t seg_src = ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw, seg_tgt = ((size_t)b * 3 + 1) * hw;
   const float* flow_src = p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2;
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 8);
   const int src_col0 = (k == 0) ? 0 : 2 * p.W;
@@ -404,21 +421,17 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
       unpack_rgb4(__ldg(pt), __ldg(pt + 1), __ldg(pt + 2), tr, tg, tb);
       unpack_rgb4(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2), sr, sg, sb);
       if (p.att_src != 0) {
-        const float4 ls = __ldg(reinterpret_cast<const float4*>(seg_src + p0));
-        const float lsv[4] = {ls.x, ls.y, ls.z, ls.w};
+        int lsv[4];
+        labels4_at(p, seg_src, p0, lsv);                            // tf.cast truncates toward zero
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int lab = (int)lsv[i];                              // tf.cast truncates toward zero
-          a_src[i] = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;   // one_hot: out of range -> 0
-        }
+        for (int i = 0; i < 4; ++i)
+          a_src[i] = (lsv[i] >= 0 && lsv[i] < kNumClasses) ? s_w[lsv[i]] : 0.0f;   // one_hot: out of range -> 0
         if (!p.att_tgt_ones) {
-          const float4 lt = __ldg(reinterpret_cast<const float4*>(seg_tgt + p0));
-          const float ltv[4] = {lt.x, lt.y, lt.z, lt.w};
+          int ltv[4];
+          labels4_at(p, seg_tgt, p0, ltv);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int lab = (int)ltv[i];
-            a_tgt[i] = (lab >= 0 && lab < kNumClasses) ? s_wt[lab] : 0.0f;
-          }
+          for (int i = 0; i < 4; ++i)
+            a_tgt[i] = (ltv[i] >= 0 && ltv[i] < kNumClasses) ? s_wt[ltv[i]] : 0.0f;
         }
       }
       float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f};
@@ -472,7 +485,7 @@ __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
   }
   __syncthreads();
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
-  const float* seg_b = p.seg + (size_t)b * 3 * hw;
+  const size_t seg_b = (size_t)b * 3 * hw;
   const float2* flow_b = reinterpret_cast<const float2*>(p.flow + (size_t)b * 4 * (size_t)hw * 2);
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 16);
   for (int pix = blockIdx.x * 256 + threadIdx.x; pix < hw; pix += kPackBlocksPerPair * 256) {
@@ -483,7 +496,7 @@ __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
 #pragma unroll
       for (int fr = 0; fr < 3; ++fr) {
         if (fr == 2 && p.att_tgt_ones) continue;
-        const int lab = (int)__ldg(seg_b + (size_t)unit_frame(1, 0, fr) * hw + pix);   // tf.cast truncates
+        const int lab = label_at(p, seg_b + (size_t)unit_frame(1, 0, fr) * hw, pix);    // tf.cast truncates
         a[fr] = (lab >= 0 && lab < kNumClasses) ? s_w[fr][lab] : 0.0f;                 // one_hot: out of range -> 0
       }
     }

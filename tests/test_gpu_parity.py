@@ -209,7 +209,8 @@ def test_host_entry_point_streams_chunks_and_trims_copies(key):
     assert np.array_equal(a, sysm.inference(None, "pose", inputs=pinned)["pose"])
     h2d, d2h = sysm.last_host_copy_bytes()
     hw = H * W
-    per_sample = hw * 9 + hw * 2 * 2 * 4 + (hw * 2 * 4 if key != "no_segmask" else 0)
+    # image bytes, two float flow planes, and the two label planes as BYTES (converted on the host)
+    per_sample = hw * 9 + hw * 2 * 2 * 4 + (hw * 2 if key != "no_segmask" else 0)
     assert h2d == 7 * per_sample and d2h == 7 * 48
     # poisoning the planes the graph does not read changes nothing
     img, flow, seg = (x.copy() for x in inputs)

@@ -16,4 +16,5 @@ t0 = time.perf_counter()
 for _ in range(30):
     sysm.inference(None, "pose", inputs=pinned)
 dt = (time.perf_counter() - t0) / 30
-print("copy_only=%s: %.3f ms per 128 samples (%.1f GB/s)" % (os.environ.get("DAVO_B200_HOST_COPY_ONLY"), dt * 1e3, 224919552 / dt / 1e9))
+h2d, _ = sysm.last_host_copy_bytes()
+print("copy_only=%s: %.3f ms per 128 samples, %d bytes host->device (%.1f GB/s)" % (os.environ.get("DAVO_B200_HOST_COPY_ONLY"), dt * 1e3, h2d, h2d / dt / 1e9))
