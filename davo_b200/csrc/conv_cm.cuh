@@ -132,6 +132,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   constexpr int kTmemCols = 2 * NPIX;
 
+  pdl_launch_dependents();
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // known warp-uniform to the compiler
   const int lane = threadIdx.x & 31;
   const int rank = CLUSTER ? (int)cluster_ctarank() : 0;
@@ -169,6 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 0) {
     // ---------------------------------------------------- patch producer --
     if (lane == 0) {
+      pdl_wait();                 // the activations this layer reads are the previous kernel's output
       int ps = 0;
       uint32_t pphase = 0;
       for (int tile = first; tile < p.num_tiles; tile += step) {

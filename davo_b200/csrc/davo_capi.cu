@@ -204,6 +204,7 @@ struct davo_ctx {
   int packed_c = 16;                // channels per pixel of the packed PoseNN input (8 or 16)
   int conv_impl = 0;                // 0 tcgen05 (product), 1 direct fp32 (debug cross-check)
   bool compensated_rounding = true; // TF32 weight rounding directions chosen so tap sums cancel
+  bool pdl = true;                  // programmatic dependent launch of every kernel of a pass
   std::vector<Layer> layers;        // cnv1..cnv7
   // device buffers
   std::vector<void*> allocs;
@@ -276,6 +277,31 @@ EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+// Every kernel of a pass goes through here: programmatic dependent launch (ptx.cuh: pdl_wait), and
+// a 2-CTA cluster where the kernel wants one.
+template <class... KArgs, class... Args>
+int launch_k(davo_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+             bool cluster2, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (ctx->pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = na;
+  CU_OK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+  return 0;
 }
 
 int dev_alloc(davo_ctx* ctx, void** p, size_t bytes) {
@@ -822,9 +848,8 @@ int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
-  pm::conv_tc_kernel<BN, EPI, RES><<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, L.tmO, P);
-  CU_OK(cudaGetLastError());
-  return 0;
+  return launch_k(ctx, pm::conv_tc_kernel<BN, EPI, RES>, dim3(grid), dim3(kConvThreads), L.smem_bytes, st, false,
+                  L.tmA, L.tmB, L.tmO, P);
 }
 
 int launch_pm_wide(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
@@ -838,9 +863,7 @@ int launch_pm_wide(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   P.num_tiles = npairs * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
-  kern<<<grid, kConvThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, L.tmO, P);
-  CU_OK(cudaGetLastError());
-  return 0;
+  return launch_k(ctx, kern, dim3(grid), dim3(kConvThreads), L.smem_bytes, st, false, L.tmA, L.tmB, L.tmO, P);
 }
 
 template <int BN, int EPI>
@@ -862,9 +885,8 @@ int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
-  cm::conv_tc_kernel<NPIX, EPI, STAGED><<<grid, cm::kThreads, L.smem_bytes, st>>>(L.tmA, L.tmB, L.tmO, P);
-  CU_OK(cudaGetLastError());
-  return 0;
+  return launch_k(ctx, cm::conv_tc_kernel<NPIX, EPI, STAGED>, dim3(grid), dim3(cm::kThreads), L.smem_bytes, st, false,
+                  L.tmA, L.tmB, L.tmO, P);
 }
 
 // 2-CTA clusters, weights multicast (conv_cm.cuh: CLUSTER).
@@ -896,9 +918,7 @@ int launch_cm_cluster(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
   const int clusters = P.num_tiles < max_clusters ? P.num_tiles : max_clusters;
-  cfg.gridDim = dim3(2 * clusters);
-  CU_OK(cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB64, L.tmO, P));
-  return 0;
+  return launch_k(ctx, kern, dim3(2 * clusters), dim3(cm::kThreads), L.smem_bytes, st, true, L.tmA, L.tmB64, L.tmO, P);
 }
 
 int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
@@ -988,14 +1008,15 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     fp.pool_2x2 = (c.att_src == 1 && c.se_pool == 1) ? 1 : 0;
     if (fp.pool_2x2) fp.se_in = 8;
     const int src_frames = ctx->unit_sample ? 2 : 1;
-    se_pool_kernel<<<dim3(kPoolSplits, npairs, src_frames + (c.att_tgt_ones ? 0 : 1)), 256, 0, st>>>(fp);
-    CU_OK(cudaGetLastError());
+    if (int rc = launch_k(ctx, se_pool_kernel, dim3(kPoolSplits, npairs, src_frames + (c.att_tgt_ones ? 0 : 1)),
+                          dim3(256), 0, st, false, fp))
+      return rc;
     ++*launches;
   }
-  if (ctx->unit_sample) pack_sample_kernel<<<dim3(kPackBlocksPerPair, npairs), 256, 0, st>>>(fp);
-  else if (ctx->packed_c == 8) pack8_kernel<<<dim3(kPack8Blocks, npairs), 256, 0, st>>>(fp);
-  else pack_kernel<<<dim3(kPackBlocksPerPair, npairs), 256, 0, st>>>(fp);
-  CU_OK(cudaGetLastError());
+  if (int rc = ctx->unit_sample ? launch_k(ctx, pack_sample_kernel, dim3(kPackBlocksPerPair, npairs), dim3(256), 0, st, false, fp)
+             : ctx->packed_c == 8 ? launch_k(ctx, pack8_kernel, dim3(kPack8Blocks, npairs), dim3(256), 0, st, false, fp)
+                                  : launch_k(ctx, pack_kernel, dim3(kPackBlocksPerPair, npairs), dim3(256), 0, st, false, fp))
+    return rc;
   ++*launches;
   return 0;
 }
@@ -1007,8 +1028,7 @@ int launch_head(davo_ctx* ctx, int pair_mode, int pair0, int npairs, float* pose
   hp.nsrc = ctx->unit_sample ? 2 : 1;
   hp.inv_hw = 1.0f / (float)(L7.Hout * L7.Wout);
   hp.sums = ctx->d_sum7; hp.wpred = ctx->d_wpred; hp.bpred = ctx->d_bpred; hp.pose_out = pose_out;
-  head_kernel<<<npairs, 256, 0, st>>>(hp);
-  CU_OK(cudaGetLastError());
+  if (int rc = launch_k(ctx, head_kernel, dim3(npairs), dim3(256), 0, st, false, hp)) return rc;
   ++*launches;
   return 0;
 }
@@ -1023,11 +1043,9 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
       sp.npairs = npairs; sp.hw = L.Hin * L.Win; sp.nbr = ctx->nbr;
       sp.cnv5 = ctx->layers[4].d_out; sp.w = ctx->d_se5w; sp.part = ctx->d_se5part; sp.count = ctx->d_se5cnt;
       sp.scale = ctx->d_se5scale; sp.out = ctx->d_se5out;
-      se5_excite_kernel<<<dim3(kSe5Splits, npairs), 256, 0, st>>>(sp);
-      CU_OK(cudaGetLastError());
+      if (int rc = launch_k(ctx, se5_excite_kernel, dim3(kSe5Splits, npairs), dim3(256), 0, st, false, sp)) return rc;
       const long long total = (long long)npairs * sp.hw * 64;
-      se5_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sp);
-      CU_OK(cudaGetLastError());
+      if (int rc = launch_k(ctx, se5_scale_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, false, sp)) return rc;
       *launches += 2;
     }
     int rc = ctx->conv_impl == 0 ? launch_conv(ctx, L, npairs, st) : launch_conv_direct(ctx, L, npairs, st);
@@ -1103,6 +1121,7 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (mb > ctx->max_units()) mb = ctx->max_units();
   ctx->mb = mb;
   if (const char* e = getenv("DAVO_B200_HOST_SEG8")) ctx->host_seg8 = strcmp(e, "0") != 0;   // "0": labels cross PCIe as floats
+  if (const char* e = getenv("DAVO_B200_PDL")) ctx->pdl = strcmp(e, "0") != 0;               // "0": plain stream order
   if (const char* cr = getenv("DAVO_B200_WEIGHT_ROUNDING"))     // "nearest": plain round-to-nearest
     ctx->compensated_rounding = strcmp(cr, "nearest") != 0;
   *out = ctx;

@@ -124,6 +124,8 @@ __device__ __forceinline__ float se_activation(float v, int act) {
 // blockIdx.z = 0: the pair's source frame; 1: the target frame (variants that do not force the
 // target map to ones).
 __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
   const int pl = blockIdx.y, fr = blockIdx.z;
   int b, k;
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
@@ -296,6 +298,8 @@ __device__ __forceinline__ float4 shfl_xor4(const float4 v, int m) {
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
   __shared__ float s_w[kNumClasses], s_wt[kNumClasses];    // class weights: source frame, target frame
   const int pl = blockIdx.y;
   int b, k;
@@ -388,6 +392,8 @@ __device__ __forceinline__ void unpack_rgb4(uint32_t t0, uint32_t t1, uint32_t t
 }
 
 __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
   __shared__ float s_w[kNumClasses], s_wt[kNumClasses];    // class weights: source frame, target frame
   __shared__ float4 s_stage[8][256];
   const int pl = blockIdx.y;
@@ -470,6 +476,8 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
 // 8-10 src1 rgb, 11-12 src1 flow (x A_1), 13-15 zero.  grid (kPackBlocksPerPair, units), one
 // thread per pixel.
 __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
   __shared__ float s_w[3][kNumClasses];                     // class weights of slots src0, src1, tgt
   const int pl = blockIdx.y;
   int b, k;
@@ -543,6 +551,8 @@ struct HeadParams {
 //   decouple nets: branch avg [3*nsrc] -> [nsrc, 3], rot | trans concatenated (posenn.py:121-123, 248-250)
 //   couple nets:   avg [6*nsrc] -> [nsrc, 6]                                     (posenn.py:62, 183)
 __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
   __shared__ float s_mean[2][256];
   const int pl = blockIdx.x;
   const int c = threadIdx.x;
@@ -594,6 +604,8 @@ constexpr int kSe5BranchFloats = 256 * 32 + 32 + 32 * 256 + 256;
 
 // grid (kSe5Splits, npairs), 256 threads (thread = channel).
 __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
   const int pl = blockIdx.y, c = threadIdx.x;
   const int per = (p.hw + kSe5Splits - 1) / kSe5Splits;
   const int beg = blockIdx.x * per, end = min(beg + per, p.hw);
@@ -640,6 +652,8 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
 
 // one thread per (pixel, 4 channels): out[pixel][br*256 + c] = tf32(cnv5[pixel][c] * scale[br][c])
 __global__ void __launch_bounds__(256) se5_scale_kernel(const Se5Params p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
   const long long total = (long long)p.npairs * p.hw * 64;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;

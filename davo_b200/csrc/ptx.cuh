@@ -68,6 +68,15 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// ---- programmatic dependent launch ----
+// Every kernel of a pass is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its
+// CTAs may become resident while the previous kernel of the stream drains, run their prologue
+// (barrier init, TMEM allocation, tensor-map prefetch, weight loads: nothing the previous kernel
+// writes) and then block in pdl_wait() until the previous grid has completed and its writes
+// are visible.  pdl_launch_dependents() at kernel entry lets the next kernel do the same.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- 2-CTA clusters: one weight slab fetched from L2 once and written into both CTAs ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -174,6 +174,9 @@ class DAVO(object):
         # into a CUDA graph and later ones replay it (launch gaps: -13 % latency at B=1, -1.4 % at
         # B=128).  DAVO_B200_GRAPH=0 switches this off; any capture failure does too.
         key = (B, sel, out.data_ptr()) + tuple(t.data_ptr() if t is not None else 0 for t in (img, flow, seg, depth))
+        if torch.cuda.is_current_stream_capturing():     # the caller is building a graph of their own
+            launch()
+            return {'pose': out}
         if self._graph_ok and key == self._graph_key:
             self._graph_hits += 1
         else:

@@ -1,6 +1,8 @@
-"""Experiment: how much of a step is launch gaps?  The same step as stream launches and as one CUDA graph."""
+"""Experiment: how much of a step is launch gaps?  The same step as stream launches (DAVO_B200_GRAPH=0 keeps
+the host wrapper from replaying a graph of its own) and captured by the caller into one CUDA graph."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["DAVO_B200_GRAPH"] = "0"
 import torch
 from davo_b200 import synthetic as S
 from davo_b200.davo import DAVO
