@@ -315,6 +315,33 @@ def test_pair_selection_computes_what_the_trajectory_reads(host):
         sysm.inference(None, "pose", inputs=feed, pairs="some")
 
 
+@pytest.mark.parametrize("case", [
+    ("decouple_net", 136, 424, 3, 0),        # sample units on a width that is not a multiple of 16: plain cnv1 plan
+    ("se_insert", 128, 416, 3, 2),           # passes of 2 pairs: the excitation buffers across ragged passes
+    ("se_seg", 128, 416, 5, 4),              # target map computed: all three label planes cross as bytes on the host path
+    ("couple_net_v0", 128, 416, 3, 2),       # sample units, passes of 2 samples
+])
+def test_variant_corner_cases_device_and_host_entry(case):
+    """Variants x sizes x pass sizes the other tests do not combine; device and host entry points agree
+    bit for bit and match the oracle; the pair selection is accepted (and ignored by sample-unit nets)."""
+    _need_gpu()
+    key, h, w_, B, mb = case
+    ver = G.CASES[key]
+    w = S.init_weights(ver, random_bias=True)
+    inputs = S.make_inputs(B, h, w_, seed=3, bad_label_frac=0.01)
+    sysm = DAVO(version=ver)
+    d = [torch.as_tensor(x).cuda() for x in inputs]
+    sysm.setup_inference(h, w_, "davo", 3, B, d[0], input_flow=d[1], input_seglabel=d[2], device=0, micro_batch=mb)
+    sysm.load_weights(w)
+    out = sysm.inference(None, "pose")["pose"].copy()
+    _assert_pose(out, O.davo_forward(ver, *inputs, w, torch.float64))
+    assert np.array_equal(out, sysm.inference(None, "pose", inputs=inputs)["pose"])
+    traj = sysm.inference(None, "pose", inputs=inputs, pairs="trajectory_first")["pose"]
+    assert np.array_equal(traj[:, 1], out[:, 1]) and np.array_equal(traj[0, 0], out[0, 0])
+    if sysm.config.posenn >= 2:
+        assert np.array_equal(traj, out)                  # both poses come out of one evaluation
+
+
 def test_cli_writes_reference_format_trajectory(tmp_path):
     """test_kitti_pose-shaped CLI on a synthetic 41-frame stream (ragged last batch of 4)."""
     _need_gpu()
