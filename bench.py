@@ -303,6 +303,7 @@ def run_ours(args):
             npairs * {"cnv4": 851968 + 1703936, "cnv5": 1703936 + 3407872, "cnv6": 2 * 3407872,
                       "cnv7": 3407872}.get(dom, 0)),
         "flop_per_launch": FLOP_PER_PAIR_LAYER[dom] * npairs, "launch_ms": layer_ms[dom],
+        "nominal_peak": 1100.0, "frac_nominal": achieved / 1100.0,     # B200 TF32 dense, for context only
         "peak_note": "TF32 dense = max(MEASURED_PEAKS bf16_tflops (burst) / 2 = %.1f %s, live cuBLAS TF32 8192^3 GEMM = %.1f)"
                      % (peaks["bf16_tflops"] / 2.0, peak_kind, live_tf32),
         "pairs_per_launch": npairs, "layer_ms": layer_ms,
