@@ -5,7 +5,7 @@
 
 namespace davo {
 
-constexpr int kMaxPatches = 24;
+constexpr int kMaxPatches = 32;
 constexpr int kMaxTaps = 144;
 constexpr int kTileW = 8;                           // tile columns: one 8-row UMMA group
 constexpr int kSlabBytes = 128;                     // 32 tf32

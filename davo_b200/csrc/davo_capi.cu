@@ -162,6 +162,11 @@ struct Layer {
   int Cin_g, groups;           // channels reduced per group
   int BN;                      // output channels per group (= MMA N)
   int Hout, Wout, out_stride;
+  // Buffer pitches (rows x columns actually allocated): odd maps are padded to even with a zero
+  // row / column that is never written, so that the stride-2 view [H/2][2][W/2][2C] exists (the
+  // non-dilated nets go down to 4x13, 2x7, 1x4 maps).  Equal to the map size everywhere else.
+  int Hin_p = 0, Win_p = 0, Hout_p = 0, Wout_p = 0;
+  bool pitched_out() const { return Hout_p != Hout || Wout_p != Wout; }
   int pad_t, pad_l;
   int epi;
   int tiles_h, tiles_w;
@@ -420,9 +425,11 @@ std::vector<float> round_weights_tf32(const Layer& L, GetW getw, bool compensate
 int encode_output_map(davo_ctx* ctx, Layer& L, int inner, int units_w, int tile_w) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  // units per allocated row: the pitch, in the same units (pixels, or runs of Wout / units_w pixels)
+  const cuuint64_t units_p = (cuuint64_t)units_w * L.Wout_p / L.Wout;
   const cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)units_w, (cuuint64_t)L.Hout, (cuuint64_t)ctx->mb};
-  const cuuint64_t strides[3] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * units_w * 4,
-                                 (cuuint64_t)inner * units_w * L.Hout * 4};
+  const cuuint64_t strides[3] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * units_p * 4,
+                                 (cuuint64_t)inner * units_p * L.Hout_p * 4};
   const cuuint32_t box[4] = {32, (cuuint32_t)tile_w, (cuuint32_t)(32 / tile_w), 1};
   const cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(&L.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, L.d_out, dims, strides, box, es,
@@ -443,8 +450,8 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
   std::vector<Tap> taps;
   const bool strided = L.stride == 2;
   if (L.stride != 1 && L.stride != 2) return fail(ctx, DAVO_ERR_ARG, "%s: stride %d unsupported", L.name, L.stride);
-  if (strided && (L.dil != 1 || (L.Hin & 1) || (L.Win & 1)))
-    return fail(ctx, DAVO_ERR_ARG, "%s: stride-2 layer needs even input size and dilation 1", L.name);
+  if (strided && (L.dil != 1 || (L.Hin_p & 1) || (L.Win_p & 1)))
+    return fail(ctx, DAVO_ERR_ARG, "%s: stride-2 layer needs dilation 1 and an even input pitch", L.name);
   const bool pair_slab = strided && L.Cin_total == 16;
   if (!pair_slab && (L.Cin_g % 32) != 0)
     return fail(ctx, DAVO_ERR_ARG, "%s: %d input channels per group is not a multiple of 32", L.name, L.Cin_g);
@@ -625,14 +632,16 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   {
-    const cuuint64_t C = L.Cin_total, H = L.Hin, W = L.Win, N = ctx->mb;
+    // extents: the real map (out-of-bounds = 'SAME' zeros); the strided view takes the even pitch,
+    // whose extra row / column is zero memory.  Strides: the pitch.
+    const cuuint64_t C = L.Cin_total, H = L.Hin, W = L.Win, Hq = L.Hin_p, Wq = L.Win_p, N = ctx->mb;
     cuuint64_t dims[5], strides[4];
     if (strided) {
-      dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
-      strides[0] = 2 * C * 4; strides[1] = W * C * 4; strides[2] = 2 * W * C * 4; strides[3] = H * W * C * 4;
+      dims[0] = 2 * C; dims[1] = Wq / 2; dims[2] = 2; dims[3] = Hq / 2; dims[4] = N;
+      strides[0] = 2 * C * 4; strides[1] = Wq * C * 4; strides[2] = 2 * Wq * C * 4; strides[3] = Hq * Wq * C * 4;
     } else {
       dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
-      strides[0] = C * 4; strides[1] = W * C * 4; strides[2] = W * C * 4; strides[3] = H * W * C * 4;
+      strides[0] = C * 4; strides[1] = Wq * C * 4; strides[2] = Wq * C * 4; strides[3] = Hq * Wq * C * 4;
     }
     const cuuint32_t box[5] = {32, (cuuint32_t)Wp, 1, (cuuint32_t)Hp, 1};
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
@@ -662,6 +671,8 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     }
   }
   L.tmO = L.tmA;
+  if (L.pitched_out() && L.epi == EPI_STORE_RELU && !(L.orient == 0 && L.BN >= 32))
+    return fail(ctx, DAVO_ERR_ARG, "%s: an odd-sized output map needs the TMA-store epilogue (pixels-on-M, >= 32 channels)", L.name);
   if ((L.orient == 1 && L.cm_staged) || (L.orient == 0 && L.epi == EPI_STORE_RELU && L.BN >= 32))
     if (int rc = encode_output_map(ctx, L, L.out_stride, L.Wout, kTileW)) return rc;
   if (getenv("DAVO_B200_VERBOSE"))
@@ -953,6 +964,8 @@ int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
 }
 
 int launch_conv_direct(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
+  if (L.pitched_out() || L.Hin_p != L.Hin || L.Win_p != L.Win)
+    return fail(ctx, DAVO_ERR_ARG, "%s: the direct cross-check path does not handle padded pitches", L.name);
   for (int g = 0; g < L.groups; ++g) {
     DirectConvParams p;
     memset(&p, 0, sizeof p);
@@ -1082,9 +1095,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   davo_ctx* ctx = nullptr;   // errors before allocation go to the thread-local slot
   if (!cfg || !out) return fail(nullptr, DAVO_ERR_ARG, "davo_create: null argument");
   *out = nullptr;
-  if (cfg->posenn < 0 || cfg->posenn > 3)
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d is not built (only the four dilated nets, "
-                "posenn.py:12-254)", cfg->posenn);
+  if (cfg->posenn < 0 || cfg->posenn > 5)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d unknown (0..5, posenn.py:12-378)", cfg->posenn);
   if (cfg->posenn_se != 0 && cfg->posenn_se != 1)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built (only -se_insert)", cfg->posenn_se);
   if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
@@ -1173,12 +1185,20 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   const int c6 = c.cnv6_out;
   // cnv1 input channels of the reference: (rgb [+ flow]) x (tgt + sources), posenn.py:21, 198
   const int cin1 = (c.in_mode == 1 ? 5 : 3) * (1 + (c.posenn >= 2 ? 2 : 1));
+  int Hq = c.H, Wq = c.W;                          // pitch of the running activation
 
   // ---- activation geometry (TF SAME) ----
   struct Geo { int k, stride, dil; };
-  const Geo geo[7] = {{7, 2, 1}, {5, 2, 1}, {3, 1, 2}, {3, 1, 4}, {3, 1, 8}, {3, 1, 2}, {3, 2, 1}};
+  // dilated nets (posenn.py:12-254): cnv3-5 dilated 2/4/8, cnv6 dilated 2; the original nets
+  // (couple_net_v0 / decouple_net_v0, posenn.py:257-378): stride 2 all the way down
+  const bool dilated = c.posenn <= 3;
+  const Geo geo_dil[7] = {{7, 2, 1}, {5, 2, 1}, {3, 1, 2}, {3, 1, 4}, {3, 1, 8}, {3, 1, 2}, {3, 2, 1}};
+  const Geo geo_v0[7] = {{7, 2, 1}, {5, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}};
+  const Geo* geo = dilated ? geo_dil : geo_v0;
+  if (!dilated && c.posenn_se != 0)
+    return fail(ctx, DAVO_ERR_ARG, "PoseNN-internal SE is built for the dilated nets only");
   // couple nets (posenn.py:133-187): one branch, pred 256 -> 6; decouple nets: rotation | translation
-  const int nbr = (c.posenn == 1 || c.posenn == 3) ? 1 : 2;
+  const int nbr = (c.posenn == 1 || c.posenn == 3 || c.posenn == 4) ? 1 : 2;
   const int nsrc = ctx->unit_sample ? 2 : 1;      // poses per evaluation (num_source, posenn.py:19, 76, 140, 196)
   ctx->nbr = nbr;
   const int cout_total[7] = {16, 32, 64, 128, 256, nbr * c6, nbr * 256};
@@ -1200,11 +1220,14 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     Layer& L = ctx->layers[i];
     L.name = names[i];
     L.k = geo[i].k; L.stride = geo[i].stride; L.dil = geo[i].dil;
-    L.Hin = H; L.Win = W; L.Cin_total = cin_total[i]; L.Cin_g = cin_g[i]; L.groups = groups[i];
+    L.Hin = H; L.Win = W; L.Hin_p = Hq; L.Win_p = Wq;
+    L.Cin_total = cin_total[i]; L.Cin_g = cin_g[i]; L.groups = groups[i];
     L.Cin_w = cin_w[i];
     L.BN = bn[i];
     SamePad ph = same_pad(H, L.k, L.stride, L.dil), pw = same_pad(W, L.k, L.stride, L.dil);
     L.Hout = ph.out; L.Wout = pw.out; L.pad_t = ph.before; L.pad_l = pw.before;
+    L.Hout_p = L.Hout + (L.Hout & 1 && L.Hout > 1 ? 1 : 0); L.Wout_p = L.Wout + (L.Wout & 1 ? 1 : 0);
+    if (i == 6) { L.Hout_p = L.Hout; L.Wout_p = L.Wout; }      // cnv7 is never stored
     L.out_stride = cout_total[i];
     L.epi = (i == 6) ? EPI_SUM_RELU : EPI_STORE_RELU;
     // Orientation (measured): channels-on-M for the wide stride-1 layers whose
@@ -1235,7 +1258,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
       L.tiles_w = (runs + L.wide_tw - 1) / L.wide_tw;
     }
     for (int j = 0; j < 16; ++j) { L.cmap[j] = j; L.pc2w[j] = j < L.Cin_w ? j : -1; }
-    H = L.Hout; W = L.Wout;
+    H = L.Hout; W = L.Wout; Hq = L.Hout_p; Wq = L.Wout_p;
   }
   {
     // cnv1 reads the packed input.  The reference's cnv1 sees [tgt rgb, tgt flow (zeros), src rgb,
@@ -1292,7 +1315,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     }
     L.d_in = prev;
     if (i < 6) {
-      if (int rc = dev_alloc(ctx, (void**)&L.d_out, (size_t)mb * L.Hout * L.Wout * L.out_stride * 4)) return rc;
+      if (int rc = dev_alloc(ctx, (void**)&L.d_out, (size_t)mb * L.Hout_p * L.Wout_p * L.out_stride * 4)) return rc;
       prev = L.d_out;
     }
   }
@@ -1666,6 +1689,7 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
     for (int i = 0; i < 6; ++i)
       if (s == ctx->layers[i].name) {
         const Layer& L = ctx->layers[i];
+        if (L.pitched_out()) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: %s is stored with a padded pitch", L.name);
         n = (int64_t)L.Hout * L.Wout * L.out_stride;
         src = L.d_out + (size_t)pair * n;
       }

@@ -83,7 +83,7 @@ def conv_specs(cfg: V.DavoConfig):
     c6 = cfg.cnv6_out
     specs = [("cnv1", (7, 7, cin, 16)), ("cnv2", (5, 5, 16, 32)), ("cnv3", (3, 3, 32, 64)),
              ("cnv4", (3, 3, 64, 128)), ("cnv5", (3, 3, 128, 256))]
-    if cfg.posenn in (V.POSENN_COUPLE_SHARED_DIL, V.POSENN_COUPLE_DIL):
+    if cfg.posenn in (V.POSENN_COUPLE_SHARED_DIL, V.POSENN_COUPLE_DIL, V.POSENN_COUPLE):
         return specs + [("pose/cnv6", (3, 3, 256, c6)), ("pose/cnv7", (3, 3, c6, 256)),
                         ("pose/pred", (1, 1, 256, 6 * nsrc))]
     for br in ("rotation", "translation"):
@@ -101,9 +101,9 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
     tests exercise the bias path the way a trained checkpoint would.
     """
     cfg = V.parse_version(version)
-    if cfg.posenn not in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_COUPLE_SHARED_DIL,
-                          V.POSENN_DECOUPLE_DIL, V.POSENN_COUPLE_DIL):
-        raise NotImplementedError("init_weights: only the four dilated nets are built")
+    if cfg.posenn not in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_COUPLE_SHARED_DIL, V.POSENN_DECOUPLE_DIL,
+                          V.POSENN_COUPLE_DIL, V.POSENN_COUPLE, V.POSENN_DECOUPLE):
+        raise NotImplementedError("init_weights: unknown PoseNN kind")
     rng = np.random.default_rng(seed)
     w: Dict[str, np.ndarray] = {}
 
@@ -132,7 +132,8 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         w["pose_exp_net/pose_exp_net/seg_channel_weight/weight"] = \
             rng.normal(0.0, 0.05, size=(19,)).astype(np.float32)
     if cfg.posenn_se == V.PSE_INSERT:
-        for br in (("rotation/", "translation/") if cfg.posenn in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_DECOUPLE_DIL)
+        for br in (("rotation/", "translation/") if cfg.posenn in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_DECOUPLE_DIL,
+                                                               V.POSENN_DECOUPLE)
                    else ("",)):
             sc = "pose_exp_net/pose/%scnv5_se_attention" % br
             for name, (fi, fo) in (("bottleneck_fc", (256, 32)), ("recover_fc", (32, 256))):

@@ -237,11 +237,14 @@ def couple_sharednet_v0_dilation(tgt: torch.Tensor, src: torch.Tensor,
 
 def net_v0_dilation(tgt: torch.Tensor, src0: torch.Tensor, src1: torch.Tensor,
                     wts: Dict[str, torch.Tensor], decouple: bool, se_attention=False, tf32: bool = False,
-                    taps: Optional[Dict[str, torch.Tensor]] = None):
+                    taps: Optional[Dict[str, torch.Tensor]] = None, dilated: bool = True):
     """``decouple_net_v0_dilation`` (nets/posenn.py:69-131) / ``couple_net_v0_dilation`` (:12-66),
     dropout=False, batch_norm=False: ONE evaluation per sample on concat(tgt, src0, src1) (:21, :78),
     num_source = 2.  Decouple: rotation / translation branches, pred 256 -> 3*2 each, reshaped
     [-1, 2, 3] and concatenated (:117-123).  Couple: one branch, pred 256 -> 12 -> [-1, 2, 6] (:58-62).
+
+    ``dilated=False``: ``decouple_net_v0`` (:314-378) / ``couple_net_v0`` (:257-311), the same
+    graphs with cnv3..cnv6 at stride 2 instead of dilation (:280-282, :300).
 
     Returns (pose [B,2,6], (cnv6_rot, cnv6_trans)).
     """
@@ -251,12 +254,17 @@ def net_v0_dilation(tgt: torch.Tensor, src0: torch.Tensor, src1: torch.Tensor,
         return conv2d_same(x, wts[P + name + "/weights"], wts[P + name + "/biases"],
                            stride=stride, rate=rate, relu=relu, tf32=tf32)
 
+    def mid(x, name, rate):          # cnv3..cnv6: dilated, or stride 2 in the original nets
+        return cv(x, name, rate=rate) if dilated else cv(x, name, stride=2)
+
+    if not dilated and se_attention is not False:
+        _unsupported("PoseNN-internal SE in the non-dilated nets")
     x = torch.cat([tgt, src0, src1], dim=3)
     c1 = cv(x, "cnv1", stride=2)
     c2 = cv(c1, "cnv2", stride=2)
-    c3 = cv(c2, "cnv3", rate=2)
-    c4 = cv(c3, "cnv4", rate=4)
-    c5 = cv(c4, "cnv5", rate=8)
+    c3 = mid(c2, "cnv3", 2)
+    c4 = mid(c3, "cnv4", 4)
+    c5 = mid(c4, "cnv5", 8)
     if taps is not None:
         taps.update(input=x, cnv1=c1, cnv2=c2, cnv3=c3, cnv4=c4, cnv5=c5)
     avgs, c6s = [], []
@@ -270,7 +278,7 @@ def net_v0_dilation(tgt: torch.Tensor, src0: torch.Tensor, src1: torch.Tensor,
         elif se_attention == "se_replace":
             c6 = se_block(c5, wts, P + br + "cnv6_se_attention", "relu")
         else:
-            c6 = cv(c5, br + "cnv6", rate=2)
+            c6 = mid(c5, br + "cnv6", 2)
         c7 = cv(c6, br + "cnv7", stride=2)
         pred = cv(c7, br + "pred", relu=False)
         avgs.append(pred.mean(dim=(1, 2)))
@@ -342,8 +350,10 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
         pose_net = "decouple_net_v0_dilation"
     elif "-dilatedCouplePoseNN" in version:                              # davo.py:1042-1043
         pose_net = "couple_net_v0_dilation"
-    else:
-        _unsupported("non-dilated PoseNN (couple_net_v0 / decouple_net_v0)")
+    elif "-couplePoseNN" in version:                                     # davo.py:1044-1045
+        pose_net = "couple_net_v0"
+    else:                                                                # davo.py:1046-1047
+        pose_net = "decouple_net_v0"
     if re.search("-cnv6_([0-9]+)", version) is not None:                 # davo.py:1052-1053
         pass  # width is carried by the weight shapes
     # 2. inputs (davo.py:1057-1073)
@@ -470,7 +480,8 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
     t1 = {} if taps is not None else None
     if isinstance(pose_net, str):                                        # davo.py:1459-1460: one evaluation per sample
         pred_poses, _ = net_v0_dilation(input_images[0], input_images[1], input_images[2], wts,
-                                        pose_net.startswith("decouple"), se_attention, tf32, t0)
+                                        pose_net.startswith("decouple"), se_attention, tf32, t0,
+                                        dilated=pose_net.endswith("_dilation"))
         t1 = t0
     else:
         pose0, _ = pose_net(input_images[0], input_images[1], wts, se_attention, tf32, t0)

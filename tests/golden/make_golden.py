@@ -35,6 +35,8 @@ CASES = {
     "gp2x2_flow_nobottle": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_gp2x2_flow_nobottle-norm_flow-fc_tanh",
     "decouple_net": "v1-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh",
     "couple_net_v0": "v0-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_seg-fc_tanh",
+    "plain_decouple_net": "v1-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh",
+    "plain_couple_net": "v1-couplePoseNN-cnv6_64-segmask_all-static",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)
 

@@ -197,7 +197,7 @@ def test_create_rejects_bad_config_before_touching_cuda():
     cfg = _capi.DavoConfigC(H=100, W=416, max_batch=1, cnv6_out=128, in_mode=1)
     assert lib.davo_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
     assert b"multiples of 8" in lib.davo_last_error(None)
-    cfg = _capi.DavoConfigC(H=128, W=416, max_batch=1, cnv6_out=128, in_mode=1, posenn=4)     # couple_net_v0: not built
+    cfg = _capi.DavoConfigC(H=128, W=416, max_batch=1, cnv6_out=128, in_mode=1, posenn=6)     # no such PoseNN
     assert lib.davo_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1
 
 

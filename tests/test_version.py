@@ -60,6 +60,17 @@ def test_posenn_selection_and_errors():
         V.parse_version(None)
 
 
+def test_all_six_posenn_kinds_resolve_as_in_the_reference():
+    """davo.py:1027-1049: -sharedNN {-dilatedPoseNN | -dilatedCouplePoseNN}, else -dilatedPoseNN,
+    -dilatedCouplePoseNN, -couplePoseNN, default decouple_net_v0."""
+    assert V.parse_version("v1-sharedNN-dilatedPoseNN").posenn == V.POSENN_DECOUPLE_SHARED_DIL
+    assert V.parse_version("v1-sharedNN-dilatedCouplePoseNN").posenn == V.POSENN_COUPLE_SHARED_DIL
+    assert V.parse_version("v1-dilatedPoseNN").posenn == V.POSENN_DECOUPLE_DIL
+    assert V.parse_version("v1-dilatedCouplePoseNN").posenn == V.POSENN_COUPLE_DIL
+    assert V.parse_version("v1-couplePoseNN").posenn == V.POSENN_COUPLE
+    assert V.parse_version("v1-cnv6_128").posenn == V.POSENN_DECOUPLE
+
+
 def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-no_segmask-se_insert").posenn_se == V.PSE_INSERT
     assert V.parse_version(BASE + "-se_skipadd").posenn_se == V.PSE_SKIPADD
