@@ -8,9 +8,10 @@ from davo_b200.davo import DAVO
 from tests.golden import make_golden as G
 H, W, B = 128, 416, 128
 inputs = [torch.as_tensor(x).cuda() for x in S.make_inputs(B, H, W, seed=5)]
+depth = torch.as_tensor(S.make_depth(B, H, W)).cuda()           # read by the se_depth sources only
 for key, ver in G.CASES.items():
     sysm = DAVO(version=ver)
-    sysm.setup_inference(H, W, "davo", 3, B, inputs[0], input_flow=inputs[1], input_seglabel=inputs[2], device=0)
+    sysm.setup_inference(H, W, "davo", 3, B, inputs[0], input_flow=inputs[1], input_seglabel=inputs[2], input_depth=depth, device=0)
     sysm.load_weights(S.init_weights(ver))
     for _ in range(3):
         sysm.inference(None, "pose", as_torch=True)
