@@ -48,19 +48,20 @@ def relative_pose_list(pred_poses):
     t_src0 = pose_vec2mat(pred_poses[:1, 0])           # first sample, tgt->src0
     t_src1 = pose_vec2mat(pred_poses[:, 1])            # every sample, tgt->src1
     rel = [t_src0[0]]
-    rel.extend(np.linalg.inv(m) for m in t_src1)
+    rel.extend(np.linalg.inv(t_src1))                  # one batched LAPACK call: the same bits as one call per matrix
     return rel
 
 
 def compose_trajectory(pred_poses):
     """Absolute poses [N+2,4,4] fp64, chained by right multiplication
     (reference test_kitti_pose.py:118-119, 147-149)."""
-    prev = np.eye(4).astype(float)
-    out = [prev]
-    for p in relative_pose_list(pred_poses):
-        prev = np.dot(prev, p)
-        out.append(prev)
-    return np.stack(out)
+    rel = relative_pose_list(pred_poses)
+    out = np.empty((len(rel) + 1, 4, 4), np.float64)
+    out[0] = np.eye(4)
+    rel64 = np.asarray(rel, np.float64)                # np.dot(float64, float32) promotes the same way
+    for i in range(len(rel)):
+        np.dot(out[i], rel64[i], out=out[i + 1])
+    return out
 
 
 def write_kitti_trajectory(path, traj):
