@@ -25,6 +25,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from . import _capi
+from . import tf_checkpoint
 from . import version as V
 
 
@@ -89,13 +90,18 @@ class DAVO(object):
 
     # ---------------------------------------------------------------- weights
     def load_weights(self, weights):
-        """``{tf variable name: ndarray}`` or a ``.npz`` of that; stands in for
+        """``{tf variable name: ndarray}``, a ``.npz`` of that, or the prefix of a TensorFlow checkpoint
+        (``model-<step>``: ``.index`` + ``.data-*``, read by ``tf_checkpoint.py``); stands in for
         ``tf.train.Saver(trainable_variables).restore`` (reference test_kitti_pose.py:129-131)."""
         if self._h is None:
             raise RuntimeError("DAVO.load_weights: call setup_inference(mode='davo') first")
         if isinstance(weights, (str, os.PathLike)):
-            with np.load(weights) as z:
-                weights = {k: z[k] for k in z.files}
+            path = os.fspath(weights)
+            if tf_checkpoint.is_checkpoint_prefix(path):      # a TF checkpoint prefix, as given to saver.restore
+                weights = tf_checkpoint.read_checkpoint(path, tf_checkpoint.pose_variables)
+            else:
+                with np.load(path) as z:
+                    weights = {k: z[k] for k in z.files}
         for name, arr in weights.items():
             a = np.ascontiguousarray(np.asarray(arr), dtype=np.float32)
             shape = (C.c_int64 * a.ndim)(*a.shape)

@@ -39,7 +39,8 @@ def build_parser():
     ap.add_argument("--test_seq", type=int, default=9, help="Sequence id to test")
     ap.add_argument("--concat_img_dir", type=str, default=None, help="Preprocess image dataset directory")
     ap.add_argument("--output_dir", type=str, default=None, help="Output directory")
-    ap.add_argument("--ckpt_file", type=str, default=None, help="checkpoint file (.npz of TF variables)")
+    ap.add_argument("--ckpt_file", type=str, default=None,
+                    help="checkpoint: the prefix of a TensorFlow checkpoint (model-<step>) or an .npz of TF variables")
     ap.add_argument("--version", type=str, default="v1", help="version")
     ap.add_argument("--synthetic", type=int, default=0, help="use a seeded synthetic stream of this many frames")
     ap.add_argument("--seed", type=int, default=1234)

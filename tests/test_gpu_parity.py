@@ -379,6 +379,14 @@ def test_cli_on_a_reference_layout_dump(tmp_path):
     poses = cli.main(["--concat_img_dir", str(tmp_path / "dump"), "--test_seq", "9", "--batch_size", "2", "--all_pairs",
                       "--version", HEADLINE, "--ckpt_file", str(tmp_path / "model.npz"), "--output_dir", str(tmp_path / "out")])
     assert poses.shape == (5, 2, 6)
+    # the same weights as a TensorFlow checkpoint (tensor bundle) with optimizer slots beside them
+    from tests.test_host import _write_bundle
+    _write_bundle(str(tmp_path / "model-1600000"), {**w, "global_step": np.array([1600000], np.int64),
+                                                    "pose_exp_net/cnv1/weights/Adam": np.zeros((7, 7, 10, 16), np.float32)})
+    poses_tf = cli.main(["--concat_img_dir", str(tmp_path / "dump"), "--test_seq", "9", "--batch_size", "2", "--all_pairs",
+                         "--version", HEADLINE, "--ckpt_file", str(tmp_path / "model-1600000"),
+                         "--output_dir", str(tmp_path / "out_tf")])
+    assert np.array_equal(poses, poses_tf)
     stream = cli.DumpStream(str(tmp_path / "dump"), 9, H, W, 3)
     inputs = tuple(np.stack([stream.sample(i)[k] for i in range(5)]) for k in range(3))
     _assert_pose(poses, O.davo_forward(HEADLINE, *inputs, w, torch.float64))

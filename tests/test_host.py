@@ -254,3 +254,116 @@ def test_dump_stream_reads_the_reference_layout(tmp_path):
         assert seg.shape == (3, h, w, 1) and seg.dtype == np.float32
         assert np.array_equal(flow, ref[i][0]) and np.array_equal(seg, ref[i][1].astype(np.float32))
         assert np.array_equal(img, np.asarray(Image.open(str(tmp_path / "09" / (stream.ids[i] + ".jpg"))).convert("RGB")))
+
+
+# ---- TensorFlow checkpoint (tensor bundle) reader ----
+def _pb_varint(v):
+    out = bytearray()
+    v &= (1 << 64) - 1
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def _pb(field, wt, payload):
+    return _pb_varint((field << 3) | wt) + payload
+
+
+def _write_bundle(prefix, tensors, extra_entries=(), block_bytes=300):
+    """A writer of the tensor-bundle format independent of the reader: LevelDB-style table with
+    prefix-compressed keys, restart points every 4 entries, several data blocks, masked crc32c."""
+    import struct
+    from davo_b200 import tf_checkpoint as T
+    data = bytearray()
+    entries = {b"": _pb(1, 0, _pb_varint(1)) + _pb(3, 2, _pb_varint(2) + _pb(1, 0, _pb_varint(1)))}   # header
+    for name in sorted(tensors):
+        a = np.ascontiguousarray(tensors[name])
+        raw = a.astype("<f4").tobytes() if a.dtype != np.int64 else a.astype("<i8").tobytes()
+        shape = b"".join(_pb(2, 2, _pb_varint(len(_pb(1, 0, _pb_varint(d)))) + _pb(1, 0, _pb_varint(d))) for d in a.shape)
+        e = _pb(1, 0, _pb_varint(1 if a.dtype != np.int64 else 9)) + _pb(2, 2, _pb_varint(len(shape)) + shape)
+        e += _pb(4, 0, _pb_varint(len(data))) + _pb(5, 0, _pb_varint(len(raw))) + _pb(6, 5, struct.pack("<I", T.masked_crc32c(raw)))
+        entries[name.encode()] = e
+        data += raw
+    for k, v in extra_entries:
+        entries[k] = v
+    with open(prefix + ".data-00000-of-00001", "wb") as f:
+        f.write(bytes(data))
+
+    def build_block(kvs, interval=4):
+        out, restarts, prev = bytearray(), [], b""
+        for i, (k, v) in enumerate(kvs):
+            shared = 0
+            if i % interval == 0:
+                restarts.append(len(out))
+            else:
+                while shared < min(len(prev), len(k)) and prev[shared] == k[shared]:
+                    shared += 1
+            out += _pb_varint(shared) + _pb_varint(len(k) - shared) + _pb_varint(len(v)) + k[shared:] + v
+            prev = k
+        for r in restarts or [0]:
+            out += struct.pack("<I", r)
+        out += struct.pack("<I", len(restarts) or 1)
+        return bytes(out)
+
+    table, handles = bytearray(), []
+
+    def emit(block):
+        off = len(table)
+        table.extend(block + b"\x00" + struct.pack("<I", T.masked_crc32c(block + b"\x00")))
+        return _pb_varint(off) + _pb_varint(len(block))
+
+    cur, size = [], 0
+    for k in sorted(entries):
+        cur.append((k, entries[k]))
+        size += len(k) + len(entries[k])
+        if size >= block_bytes:
+            handles.append((cur[-1][0], emit(build_block(cur))))
+            cur, size = [], 0
+    if cur:
+        handles.append((cur[-1][0], emit(build_block(cur))))
+    meta = emit(build_block([]))
+    index = emit(build_block(handles, interval=1))
+    footer = meta + index
+    footer += b"\x00" * (40 - len(footer)) + struct.pack("<Q", T.TABLE_MAGIC)
+    with open(prefix + ".index", "wb") as f:
+        f.write(bytes(table) + footer)
+
+
+def test_tf_checkpoint_reader_round_trip(tmp_path):
+    """tf_checkpoint.read_checkpoint on a bundle written by an independent writer of the same format:
+    all pose variables come back bit for bit, optimizer slots / non-float variables are skipped,
+    crc32c is checked, damage is reported."""
+    from davo_b200 import tf_checkpoint as T
+    from davo_b200 import synthetic as S
+    assert T.crc32c(b"123456789") == 0xE3069283                      # the Castagnoli check value
+    w = S.init_weights("v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh", random_bias=True)
+    extra = {"global_step": np.array([1600000], np.int64),
+             "pose_exp_net/cnv1/weights/Adam": np.zeros((7, 7, 10, 16), np.float32),
+             "depth_net/cnv1/weights": np.ones((3, 3, 3, 8), np.float32)}
+    prefix = str(tmp_path / "model-1600000")
+    _write_bundle(prefix, {**w, **extra})
+    assert T.is_checkpoint_prefix(prefix) and not T.is_checkpoint_prefix(str(tmp_path / "nothing"))
+    header, entries = T.read_index(prefix + ".index")
+    assert header["num_shards"] == 1 and set(entries) == set(w) | set(extra)
+    got = T.read_checkpoint(prefix, T.pose_variables, verify_data_crc=True)
+    assert set(got) == set(w)
+    for k in w:
+        assert got[k].dtype == np.float32 and got[k].shape == w[k].shape and np.array_equal(got[k], w[k])
+    assert "depth_net/cnv1/weights" in T.read_checkpoint(prefix) and "global_step" not in T.read_checkpoint(prefix)
+    # damage: a flipped byte in the index fails the block crc; a flipped tensor byte fails the data crc
+    raw = bytearray(open(prefix + ".index", "rb").read())
+    raw[10] ^= 0xFF
+    open(str(tmp_path / "bad.index"), "wb").write(bytes(raw))
+    with pytest.raises(ValueError, match="crc32c"):
+        T.read_index(str(tmp_path / "bad.index"))
+    d = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    d[entries["pose_exp_net/cnv1/biases"]["offset"] + 5] ^= 0x01
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(d))
+    with pytest.raises(ValueError, match="crc32c"):
+        T.read_checkpoint(prefix, T.pose_variables, verify_data_crc=True)
+    with pytest.raises(ValueError, match="magic"):
+        open(str(tmp_path / "junk.index"), "wb").write(b"x" * 100)
+        T.read_index(str(tmp_path / "junk.index"))
