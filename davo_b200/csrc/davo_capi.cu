@@ -245,6 +245,9 @@ struct davo_ctx {
   const uint8_t* last_img = nullptr; const float* last_flow = nullptr; const float* last_seg = nullptr;
   float* last_pose = nullptr; int last_B = 0; int last_pairs = 0;
   const float* cur_depth = nullptr; // depth planes of the batch (chunk) being enqueued; se_depth sources only
+  // Function attributes are per device: what this context has already raised, by kernel.
+  std::map<const void*, int> smem_attr;
+  std::map<std::pair<const void*, int>, int> max_clusters;   // by (kernel, dynamic shared memory)
 };
 
 namespace {
@@ -306,6 +309,17 @@ int launch_k(davo_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = na;
   CU_OK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+  return 0;
+}
+
+// Opt the kernel in to `bytes` of dynamic shared memory on this context's device (once per size).
+template <class K>
+int ensure_smem(davo_ctx* ctx, K kern, int bytes) {
+  int& have = ctx->smem_attr[reinterpret_cast<const void*>(kern)];
+  if (have < bytes) {
+    CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    have = bytes;
+  }
   return 0;
 }
 
@@ -848,12 +862,7 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
 
 template <int BN, int EPI, bool RES>
 int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
-  static int attr_smem = 0;
-  if (attr_smem < L.smem_bytes) {
-    CU_OK(cudaFuncSetAttribute(pm::conv_tc_kernel<BN, EPI, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               L.smem_bytes));
-    attr_smem = L.smem_bytes;
-  }
+  if (int rc = ensure_smem(ctx, pm::conv_tc_kernel<BN, EPI, RES>, L.smem_bytes)) return rc;
   pm::ConvParams P = L.prm_pm;
   P.num_tiles = npairs * L.groups * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
@@ -864,12 +873,8 @@ int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
 }
 
 int launch_pm_wide(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
-  static int attr_smem = 0;
   auto* kern = pm::conv_tc_kernel<128, EPI_STORE_RELU, true, true>;
-  if (attr_smem < L.smem_bytes) {
-    CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
-    attr_smem = L.smem_bytes;
-  }
+  if (int rc = ensure_smem(ctx, kern, L.smem_bytes)) return rc;
   pm::ConvParams P = L.prm_pm;
   P.num_tiles = npairs * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
@@ -885,12 +890,7 @@ int launch_pm_r(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
 
 template <int NPIX, int EPI, bool STAGED = false>
 int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
-  static int attr_smem = 0;
-  if (attr_smem < L.smem_bytes) {
-    CU_OK(cudaFuncSetAttribute(cm::conv_tc_kernel<NPIX, EPI, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               L.smem_bytes));
-    attr_smem = L.smem_bytes;
-  }
+  if (int rc = ensure_smem(ctx, cm::conv_tc_kernel<NPIX, EPI, STAGED>, L.smem_bytes)) return rc;
   cm::ConvParams P = L.prm_cm;
   P.num_tiles = npairs * L.groups * L.tiles_h * L.tiles_w * L.m_blocks;
   P.out = L.d_out;
@@ -904,12 +904,8 @@ int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
 template <int NPIX, bool STAGED>
 int launch_cm_cluster(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   auto* kern = cm::conv_tc_kernel<NPIX, EPI_STORE_RELU, STAGED, true>;
-  static int attr_smem = 0, max_clusters = 0;
-  if (attr_smem < L.smem_bytes) {
-    CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_bytes));
-    attr_smem = L.smem_bytes;
-    max_clusters = 0;
-  }
+  if (int rc = ensure_smem(ctx, kern, L.smem_bytes)) return rc;
+  int& max_clusters = ctx->max_clusters[std::make_pair(reinterpret_cast<const void*>(kern), L.smem_bytes)];
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cudaLaunchAttribute attr;
