@@ -41,7 +41,10 @@ enum davo_status {
 typedef struct davo_config {
   int32_t H, W;          /* frame size, reference test_kitti_pose.py:22-23 (128, 416)  */
   int32_t max_batch;     /* largest B (samples) a forward call may carry               */
-  int32_t posenn;        /* 0 = decouple_sharednet_v0_dilation (nets/posenn.py:189)    */
+  int32_t posenn;        /* nets/posenn.py, selected at davo.py:1027-1049:
+                            0 decouple_sharednet_v0_dilation (:189, headline), 1 couple_sharednet_v0_dilation (:133),
+                            2 decouple_net_v0_dilation (:69), 3 couple_net_v0_dilation (:12),
+                            4 couple_net_v0 (:257), 5 decouple_net_v0 (:314); 2-5 evaluate a whole sample at once */
   int32_t cnv6_out;      /* "-cnv6_<n>", davo.py:1052-1053                             */
   int32_t in_mode;       /* 0 = v0 RGB only, 1 = v1 RGB+flow, davo.py:1057-1065        */
   int32_t att_src;       /* 0 none, 1 se_flow (davo.py:1175), 2 static (:1390), 3 se_seg (:1304),
@@ -52,7 +55,7 @@ typedef struct davo_config {
   int32_t flow_abs;      /* 0 none, 1 both, 2 h, 3 v, davo.py:1094-1102                */
   int32_t flow_norm;     /* "-norm_flow", davo.py:1088-1091                            */
   int32_t posenn_se;     /* 0 none, 1 insert, 2 skipadd, 3 replace, davo.py:1010-1017  */
-  int32_t micro_batch;   /* frame pairs per pass through the conv stack; 0 = default   */
+  int32_t micro_batch;   /* units (frame pairs; samples for posenn 2-5) per pass of the conv stack; 0 = 256 */
   int32_t depth_norm;    /* "-norm_depth": SE depth input / 80, davo.py:1108-1111       */
   int32_t se_pool;       /* se_flow only: 0 global mean, 1 gp2x2 (four quadrant means), davo.py:1181-1192 */
   int32_t se_hidden;     /* width of the SE bottleneck; 0 = the source's default (8; se_seg 19)  */
