@@ -24,7 +24,7 @@ def _deps():
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "-ldl",
     "-Xptxas", "-v",
 ]
 

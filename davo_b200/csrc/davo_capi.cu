@@ -27,6 +27,7 @@
 #include "conv_cm.cuh"
 #include "conv_pm.cuh"
 #include "frontend.cuh"
+#include "comm.cuh"
 
 using namespace davo;
 
@@ -248,6 +249,9 @@ struct davo_ctx {
   // Function attributes are per device: what this context has already raised, by kernel.
   std::map<const void*, int> smem_attr;
   std::map<std::pair<const void*, int>, int> max_clusters;   // by (kernel, dynamic shared memory)
+  // pose all-gather (comm.cuh): the handle's own communicator, if davo_comm_create made one
+  davo_comm::Comm comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
 };
 
 namespace {
@@ -1152,6 +1156,7 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
     if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
   }
   delete ctx->pool;
+  if (ctx->comm) davo_comm::api().CommDestroy(ctx->comm);
   if (ctx->s_pose) cudaFree(ctx->s_pose);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -1751,5 +1756,67 @@ extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int*
   if (int rc = timed([&] { return launch_head(ctx, ctx->unit_sample ? kUnitsAreSamples : 0, 0, npairs, ctx->last_pose, st, &dummy); }, &ms_out[8])) return rc;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pose all-gather over NCCL.  Ranks hold equal, padded blocks of [n_local, 2, 6]
+// poses (davo_b200/parallel.py: padded_indices); rank r's block lands at all[r * n_local].
+// ---------------------------------------------------------------------------------------------
+extern "C" int davo_comm_unique_id(void* id128) {
+  if (!id128) return fail(nullptr, DAVO_ERR_ARG, "davo_comm_unique_id: null argument");
+  const davo_comm::Api& n = davo_comm::api();
+  if (!n.why.empty()) return fail(nullptr, DAVO_ERR_STATE, "davo_comm_unique_id: %s", n.why.c_str());
+  davo_comm::UniqueId id;
+  const int r = n.GetUniqueId(&id);
+  if (r != davo_comm::kNcclSuccess) return fail(nullptr, DAVO_ERR_CUDA, "ncclGetUniqueId: %s", n.GetErrorString(r));
+  std::memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+extern "C" int davo_comm_create(davo_ctx* ctx, const void* id128, int rank, int world) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, DAVO_ERR_ARG, "davo_comm_create: bad argument (rank %d of %d)", rank, world);
+  if (ctx->comm) return fail(ctx, DAVO_ERR_STATE, "davo_comm_create: the handle already has a communicator");
+  const davo_comm::Api& n = davo_comm::api();
+  if (!n.why.empty()) return fail(ctx, DAVO_ERR_STATE, "davo_comm_create: %s", n.why.c_str());
+  CU_OK(cudaSetDevice(ctx->device));
+  davo_comm::UniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  const int r = n.CommInitRank(&ctx->comm, world, id, rank);
+  if (r != davo_comm::kNcclSuccess) {
+    ctx->comm = nullptr;
+    return fail(ctx, DAVO_ERR_CUDA, "ncclCommInitRank(rank %d of %d): %s", rank, world, n.GetErrorString(r));
+  }
+  ctx->comm_rank = rank;
+  ctx->comm_world = world;
+  return 0;
+}
+
+extern "C" int davo_comm_world(const davo_ctx* ctx, int* rank, int* world) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (rank) *rank = ctx->comm_rank;
+  if (world) *world = ctx->comm ? ctx->comm_world : 1;
+  return 0;
+}
+
+extern "C" int davo_allgather_poses(davo_ctx* ctx, void* nccl_comm, const float* local, int n_local,
+                                    float* all, void* stream) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!local || !all || n_local < 0) return fail(ctx, DAVO_ERR_ARG, "davo_allgather_poses: bad argument");
+  davo_comm::Comm comm = nccl_comm ? nccl_comm : ctx->comm;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t count = static_cast<size_t>(n_local) * 2 * 6;
+  if (!comm) {
+    // no communicator: a world of one, the gather is a copy
+    CU_OK(cudaSetDevice(ctx->device));
+    if (all != local && count) CU_OK(cudaMemcpyAsync(all, local, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  const davo_comm::Api& n = davo_comm::api();
+  if (!n.why.empty()) return fail(ctx, DAVO_ERR_STATE, "davo_allgather_poses: %s", n.why.c_str());
+  CU_OK(cudaSetDevice(ctx->device));
+  const int r = n.AllGather(local, all, count, davo_comm::kNcclFloat, comm, st);
+  if (r != davo_comm::kNcclSuccess) return fail(ctx, DAVO_ERR_CUDA, "ncclAllGather: %s", n.GetErrorString(r));
   return 0;
 }

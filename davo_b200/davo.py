@@ -251,6 +251,50 @@ class DAVO(object):
         self._graph, self._graph_key, self._graph_hits = None, None, 0      # a captured graph holds the old path
         self._check(self._lib.davo_debug_set_conv_impl(self._h, impl), "davo_debug_set_conv_impl")
 
+    # ------------------------------------------------------------------ multi-GPU
+    def init_comm(self, rank=None, world=None):
+        """Build the handle's NCCL communicator (``davo_comm_create``).  Collective: every rank
+        calls it.  The 128-byte id made on rank 0 travels over the already initialised
+        ``torch.distributed`` group (plumbing only; the gather itself is the library's)."""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            if world in (None, 1):
+                return 1
+            raise RuntimeError("DAVO.init_comm: torch.distributed is not initialised")
+        rank = dist.get_rank() if rank is None else rank
+        world = dist.get_world_size() if world is None else world
+        if world == 1:
+            return 1
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            rc = self._lib.davo_comm_unique_id(ident)
+            if rc != 0:
+                raise RuntimeError("davo_comm_unique_id failed (%d): %s" % (rc, _capi.last_error(self._lib, None)))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)
+        ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        self._check(self._lib.davo_comm_create(self._h, ident, rank, world), "davo_comm_create")
+        self._comm_world = world
+        return world
+
+    def comm_world(self) -> int:
+        return getattr(self, "_comm_world", 1)
+
+    def allgather_poses(self, local_poses):
+        """``[n_local,2,6]`` CUDA tensor of this rank -> ``[world*n_local,2,6]`` in rank order,
+        enqueued on the current stream (``davo_allgather_poses``)."""
+        import torch
+        assert local_poses.is_cuda and local_poses.dtype == torch.float32 and tuple(local_poses.shape[1:]) == (2, 6)
+        local_poses = local_poses.contiguous()
+        n_local = int(local_poses.shape[0])
+        out = torch.empty((self.comm_world() * n_local, 2, 6), dtype=torch.float32, device=local_poses.device)
+        stream = torch.cuda.current_stream(local_poses.device).cuda_stream
+        self._check(self._lib.davo_allgather_poses(self._h, None, C.c_void_p(local_poses.data_ptr()), n_local,
+                                                   C.c_void_p(out.data_ptr()), C.c_void_p(stream)),
+                    "davo_allgather_poses")
+        return out
+
     def close(self):
         self._graph = None
         if self._h is not None and self._lib is not None:

@@ -2,9 +2,10 @@
 
 The reference is single-process; every sample (frame triple) is independent, so
 the stream is cut into contiguous blocks by rank, each rank runs the forward on
-its block, and the ``[n_local, 2, 6]`` poses are gathered once
-(``torch.distributed.all_gather_into_tensor``: NCCL over NVLink on GPUs, gloo on
-CPU for tests).  Shards are padded to equal length by repeating the last sample
+its block, and the ``[n_local, 2, 6]`` poses are gathered once: on GPUs by the
+library's own ``davo_allgather_poses`` (ncclAllGather over NVLink on the compute
+stream, include/davo_b200.h) when the ``DAVO`` object carries a communicator,
+else by ``torch.distributed.all_gather_into_tensor`` (gloo on CPU for tests).  Shards are padded to equal length by repeating the last sample
 -- the rule the reference uses to fill its final batch (reference
 ``utils/common_utils.py:8-13``) -- and the padding is trimmed after the gather.
 Trajectory composition stays sequential on the host.
@@ -52,14 +53,17 @@ def padded_indices(n_samples: int, rank: int, world: int):
     return idx
 
 
-def gather_poses(local_poses, n_samples: int):
+def gather_poses(local_poses, n_samples: int, system=None):
     """All-gather ``[n_local, 2, 6]`` from every rank and trim to ``[n_samples, 2, 6]``.
 
     ``local_poses`` is a torch tensor (CUDA with NCCL, CPU with gloo).  Without an
-    initialised process group (single GPU) it is returned trimmed.
+    initialised process group (single GPU) it is returned trimmed.  ``system`` is the
+    rank's ``DAVO`` object: after ``system.init_comm()`` the gather is the C library's.
     """
     import torch
     import torch.distributed as dist
+    if system is not None and system.comm_world() > 1 and local_poses.is_cuda:
+        return system.allgather_poses(local_poses)[:n_samples]
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return local_poses[:n_samples]
     world = dist.get_world_size()

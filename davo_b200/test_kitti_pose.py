@@ -124,6 +124,8 @@ def main(argv=None):
     else:
         raise SystemExit("test_kitti_pose: --ckpt_file is required with a real dataset")
 
+    if world > 1:
+        system.init_comm(rank, world)                                  # the library's own NCCL communicator
     poses = torch.empty((len(idx), 2, 6), dtype=torch.float32, device="cuda:%d" % local)
     for i in range(len(idx) // B):                                     # reference :133
         batch = [stream.sample(j) for j in idx[i * B:(i + 1) * B]]
@@ -132,7 +134,7 @@ def main(argv=None):
         sel = 'all' if FLAGS.all_pairs else ('trajectory_first' if (i == 0 and idx[0] == 0) else 'trajectory')
         pred = system.inference(None, mode='pose', inputs=(img, flow, seg), pairs=sel)   # reference :135
         poses[i * B:(i + 1) * B] = torch.as_tensor(pred['pose'])
-    all_poses = parallel.gather_poses(poses[:n_local].contiguous(), n).cpu().numpy()
+    all_poses = parallel.gather_poses(poses[:n_local].contiguous(), n, system).cpu().numpy()
     if rank == 0:
         traj = geo_utils.compose_trajectory(all_poses)                 # reference :136-149
         if FLAGS.output_dir:

@@ -143,6 +143,26 @@ int davo_profile_layers(davo_ctx*, int iters, float* ms_out, int* npairs_out,
  * path on the GPU. */
 int davo_debug_set_conv_impl(davo_ctx*, int impl);
 
+/* --- multi-GPU: one process and one handle per GPU, samples sharded by rank, one collective ---
+ * The reference is single-process (test_kitti_pose.py:133-153); sharding its sample list by rank
+ * needs one exchange, the all-gather of the [n_local,2,6] pose blocks before the sequential
+ * composition on the host.  NCCL is bound at run time (libnccl.so.2; DAVO_B200_NCCL_LIB overrides).
+ *
+ * davo_comm_unique_id: rank 0 fills 128 bytes (an ncclUniqueId) and hands them to the other ranks
+ *   by whatever side channel the host has (torch.distributed store, MPI, a file).
+ * davo_comm_create: collective over all ranks; builds the handle's own communicator on its device.
+ * davo_allgather_poses: enqueues on `cuda_stream` the gather of `n_local` samples (n_local*12
+ *   floats, the same on every rank -- pad the last shard as utils/common_utils.py:8-13 pads a
+ *   batch); rank r's block lands at all + r*n_local*12.  `nccl_comm` is an ncclComm_t the host
+ *   already owns, or NULL for the handle's communicator; with neither, the world is one rank and
+ *   the call is a device copy.  No host synchronisation. */
+#define DAVO_COMM_ID_BYTES 128
+int davo_comm_unique_id(void* id128);
+int davo_comm_create(davo_ctx*, const void* id128, int rank, int world);
+int davo_comm_world(const davo_ctx*, int* rank, int* world);
+int davo_allgather_poses(davo_ctx*, void* nccl_comm, const float* local_dev, int n_local,
+                         float* all_dev, void* cuda_stream);
+
 const char* davo_last_error(const davo_ctx*);   /* NULL handle -> last create error */
 void davo_destroy(davo_ctx*);
 const char* davo_build_info(void);              /* arch / compiler string */

@@ -410,3 +410,65 @@ def test_two_rank_sharded_stream_matches_single_gpu(tmp_path):
         assert res.returncode == 0, res.stdout + res.stderr
         outs.append((d / "09-pred_kitti_pose.txt").read_text())
     assert outs[0] == outs[1] and len(outs[0].strip().split("\n")) == 45
+
+
+_GATHER_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from davo_b200 import synthetic as S, parallel
+from davo_b200.davo import DAVO
+rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ver = sys.argv[2]
+s = DAVO(version=ver); s.setup_inference(64, 96, "davo", 3, 4, device=local); s.load_weights(S.init_weights(ver))
+assert s.comm_world() == 1
+n = 7                                                     # samples in the stream; 4 per rank, one padded
+idx = parallel.padded_indices(n, rank, world)
+full = torch.arange(n * 12, dtype=torch.float32, device="cuda").reshape(n, 2, 6)
+local_p = full[idx] * 3 - 1
+alone = s.allgather_poses(local_p)                        # no communicator yet: a world of one, a copy
+assert torch.equal(alone, local_p)
+assert s.init_comm() == world and s.comm_world() == world
+for _ in range(3):                                        # same communicator, several gathers in stream order
+    out = parallel.gather_poses(local_p, n, s)
+    ref = torch.empty((world * len(idx), 2, 6), device="cuda"); dist.all_gather_into_tensor(ref, local_p)
+    assert out.shape == (n, 2, 6) and torch.equal(out, full * 3 - 1) and torch.equal(out, ref[:n]), rank
+try:
+    s.init_comm()
+    raise SystemExit("second init_comm did not fail")
+except RuntimeError as e:
+    assert "already has a communicator" in str(e)
+torch.cuda.synchronize(); dist.barrier(); s.close(); dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_library_allgather_matches_torch_distributed(tmp_path):
+    """davo_comm_create + davo_allgather_poses (include/davo_b200.h) against torch.distributed on 2 GPUs."""
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "gather_worker.py"
+    script.write_text(_GATHER_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", str(script), root, HEADLINE]
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("OK") == 2
+
+
+def test_allgather_without_communicator_is_a_copy():
+    """One rank, no communicator: davo_allgather_poses degenerates to a device copy; bad arguments fail."""
+    _need_gpu()
+    s = DAVO(version=HEADLINE)
+    s.setup_inference(64, 96, "davo", 3, 2, device=0)
+    s.load_weights(S.init_weights(HEADLINE))
+    x = torch.randn(5, 2, 6, device="cuda")
+    assert torch.equal(s.allgather_poses(x), x)
+    assert s.init_comm() == 1                              # no process group: stays a world of one
+    rc = s._lib.davo_allgather_poses(s._h, None, None, 1, None, None)
+    assert rc != 0 and "bad argument" in s._lib.davo_last_error(s._h).decode()
+

@@ -367,3 +367,15 @@ def test_tf_checkpoint_reader_round_trip(tmp_path):
     with pytest.raises(ValueError, match="magic"):
         open(str(tmp_path / "junk.index"), "wb").write(b"x" * 100)
         T.read_index(str(tmp_path / "junk.index"))
+
+
+def test_comm_unique_id_binds_nccl_at_run_time():
+    """davo_comm_unique_id (include/davo_b200.h): NCCL is dlopen'ed, ids are 128 bytes and differ per call."""
+    import ctypes as C
+    from davo_b200 import _capi
+    lib = _capi.load()
+    a, b = (C.c_ubyte * 128)(), (C.c_ubyte * 128)()
+    assert lib.davo_comm_unique_id(a) == 0, lib.davo_last_error(None)
+    assert lib.davo_comm_unique_id(b) == 0
+    assert bytes(a) != bytes(b) and any(bytes(a))
+    assert lib.davo_comm_unique_id(None) != 0 and b"null argument" in lib.davo_last_error(None)

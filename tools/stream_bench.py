@@ -21,6 +21,8 @@ base = [torch.as_tensor(x).cuda() for x in S.make_inputs(64, H, W, seed=1000)]
 sysm = DAVO(version=ver)
 sysm.setup_inference(H, W, "davo", 3, B, device=local)
 sysm.load_weights(S.init_weights(ver))
+if world > 1 and os.environ.get("STREAM_GATHER", "library") == "library":
+    sysm.init_comm(rank, world)                                    # davo_allgather_poses; else torch.distributed
 poses = torch.empty((n_local, 2, 6), dtype=torch.float32, device="cuda")
 def run_stream():
     for b0 in range(0, n_local, B):
@@ -29,7 +31,7 @@ def run_stream():
         batch = tuple(t.index_select(0, sel) for t in base)      # the batch's samples, gathered on the device
         mode = "trajectory_first" if (rank == 0 and b0 == 0) else "trajectory"
         poses[b0:b0 + len(ids)] = sysm.inference(None, "pose", inputs=batch, as_torch=True, pairs=mode)["pose"]
-    return parallel.gather_poses(poses, N)
+    return parallel.gather_poses(poses, N, sysm)
 for _ in range(2):
     allp = run_stream()
 torch.cuda.synchronize()
