@@ -19,6 +19,7 @@ SYMBOLS = (
     "davo_forward_host", "davo_get_intermediate", "davo_last_launch_count",
     "davo_last_host_copy_bytes",
     "davo_profile_layers", "davo_debug_set_conv_impl", "davo_forward_pairs", "davo_forward_host_pairs",
+    "davo_forward_features",
     "davo_comm_unique_id", "davo_comm_create", "davo_comm_world", "davo_allgather_poses",
     "davo_last_error",
     "davo_destroy", "davo_build_info",
@@ -29,6 +30,12 @@ class DavoConfigC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "H", "W", "max_batch", "posenn", "cnv6_out", "in_mode", "att_src", "att_tgt_ones",
         "mask_mode", "se_act", "flow_abs", "flow_norm", "posenn_se", "micro_batch", "depth_norm", "se_pool", "se_hidden")]
+
+
+class DavoFeaturesC(C.Structure):
+    """include/davo_b200.h: davo_features (device pointers, NULL skips the output)."""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "image", "attention", "masked_image", "seg_19", "seg_color", "flow_color", "cnv6_rot", "cnv6_trans")]
 
 
 def lib_path() -> str:
@@ -67,6 +74,7 @@ def load() -> C.CDLL:
     lib.davo_last_host_copy_bytes.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
     lib.davo_profile_layers.argtypes = [vp, ip, fp, C.POINTER(ip), vp]
     lib.davo_debug_set_conv_impl.argtypes = [vp, ip]
+    lib.davo_forward_features.argtypes = [vp, ip, vp, vp, vp, vp, vp, C.POINTER(DavoFeaturesC), vp]
     lib.davo_comm_unique_id.argtypes = [vp]
     lib.davo_comm_create.argtypes = [vp, vp, ip, ip]
     lib.davo_comm_world.argtypes = [vp, C.POINTER(ip), C.POINTER(ip)]
@@ -76,7 +84,7 @@ def load() -> C.CDLL:
     lib.davo_destroy.argtypes = [vp]
     lib.davo_destroy.restype = None
     lib.davo_build_info.restype = C.c_char_p
-    for s in SYMBOLS[:16]:
+    for s in SYMBOLS[:17]:
         getattr(lib, s).restype = ip
     _LIB = lib
     return lib

@@ -27,6 +27,7 @@
 #include "conv_cm.cuh"
 #include "conv_pm.cuh"
 #include "frontend.cuh"
+#include "features.cuh"
 #include "comm.cuh"
 
 using namespace davo;
@@ -249,6 +250,9 @@ struct davo_ctx {
   // Function attributes are per device: what this context has already raised, by kernel.
   std::map<const void*, int> smem_attr;
   std::map<std::pair<const void*, int>, int> max_clusters;   // by (kernel, dynamic shared memory)
+  // mode='feature' (features.cuh)
+  float* d_wheel = nullptr;         // Middlebury colour wheel / 255
+  unsigned int* d_maxrad = nullptr; // largest flow magnitude per source frame
   // pose all-gather (comm.cuh): the handle's own communicator, if davo_comm_create made one
   davo_comm::Comm comm = nullptr;
   int comm_rank = 0, comm_world = 1;
@@ -1818,5 +1822,99 @@ extern "C" int davo_allgather_poses(davo_ctx* ctx, void* nccl_comm, const float*
   CU_OK(cudaSetDevice(ctx->device));
   const int r = n.AllGather(local, all, count, davo_comm::kNcclFloat, comm, st);
   if (r != davo_comm::kNcclSuccess) return fail(ctx, DAVO_ERR_CUDA, "ncclAllGather: %s", n.GetErrorString(r));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mode='feature' (davo.py:1553-1564): the pass, then the visualisation tensors (features.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace {
+// utils/flow_utils.py:546-593: six colour ramps of 15, 6, 4, 11, 13 and 6 steps; stored / 255 the way
+// compute_color reads it (a float64 division cast to float32, flow_utils.py:488-490)
+void middlebury_wheel(float (*wheel)[3]) {
+  const int seg[6] = {15, 6, 4, 11, 13, 6};
+  const int fixed[6] = {0, 1, 1, 2, 2, 0};       // channel held at 255
+  const int ramp[6] = {1, 0, 2, 1, 0, 2};        // channel that moves
+  const bool rising[6] = {true, false, true, false, true, false};
+  int col = 0;
+  for (int s = 0; s < 6; ++s)
+    for (int i = 0; i < seg[s]; ++i, ++col) {
+      double v[3] = {0.0, 0.0, 0.0};
+      const double step = std::floor(255.0 * i / seg[s]);
+      v[fixed[s]] = 255.0;
+      v[ramp[s]] = rising[s] ? step : 255.0 - step;
+      for (int ch = 0; ch < 3; ++ch) wheel[col][ch] = (float)(v[ch] / 255.0);
+    }
+}
+}  // namespace
+
+extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, const float* flow,
+                                     const float* seg, const float* depth, float* pose_out,
+                                     const davo_features* out, void* stream) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!out) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: null output table");
+  const int units = ctx->unit_sample ? B : 2 * B;
+  if (ctx->finalized && units > ctx->mb)
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: B=%d needs %d units, one pass holds %d", B, units, ctx->mb);
+  if ((out->flow_color) && !flow) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: flow colouring needs input_flow");
+  if ((out->seg_19 || out->seg_color) && !seg) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: label outputs need input_seglabel");
+  if (int rc = davo_forward_pairs(ctx, B, DAVO_PAIRS_ALL, img, flow, seg, depth, pose_out, stream)) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const davo_config& c = ctx->cfg;
+  if (!ctx->d_wheel) {
+    float wheel[kWheelCols][3];
+    middlebury_wheel(wheel);
+    void* p = nullptr;
+    CU_OK(cudaMalloc(&p, sizeof wheel + 2 * sizeof(unsigned int)));
+    ctx->allocs.push_back(p);
+    ctx->d_wheel = static_cast<float*>(p);
+    ctx->d_maxrad = reinterpret_cast<unsigned int*>(ctx->d_wheel + kWheelCols * 3);
+    CU_OK(cudaMemcpy(ctx->d_wheel, wheel, sizeof wheel, cudaMemcpyHostToDevice));
+  }
+  FeatureParams fp;
+  memset(&fp, 0, sizeof fp);
+  fp.B = B; fp.H = c.H; fp.W = c.W;
+  fp.unit_sample = ctx->unit_sample ? 1 : 0; fp.att_src = c.att_src; fp.att_tgt_ones = c.att_tgt_ones;
+  fp.mask_rgb = c.mask_mode != 0;
+  fp.img = img; fp.flow = flow; fp.seg = seg; fp.att_w = ctx->d_attw; fp.static_w = ctx->d_staticw;
+  fp.wheel = ctx->d_wheel; fp.maxrad = ctx->d_maxrad;
+  fp.image = out->image; fp.attention = out->attention; fp.masked_image = out->masked_image;
+  fp.seg_19 = out->seg_19; fp.seg_color = out->seg_color; fp.flow_color = out->flow_color;
+  int launches = ctx->last_launches;
+  if (fp.image || fp.attention || fp.masked_image || fp.seg_19 || fp.seg_color) {
+    const int groups = c.H * c.W / 4;
+    feature_frames_kernel<<<dim3((groups + 255) / 256, B, 3), 256, 0, st>>>(fp);
+    CU_OK(cudaGetLastError());
+    ++launches;
+  }
+  if (fp.flow_color) {
+    CU_OK(cudaMemsetAsync(ctx->d_maxrad, 0, 2 * sizeof(unsigned int), st));
+    const int blocks = std::min(ctx->num_sms * 4, (B * c.H * c.W + 255) / 256);
+    flow_maxrad_kernel<<<dim3(blocks, 2), 256, 0, st>>>(fp);
+    flow_color_kernel<<<dim3(blocks, 2), 256, 0, st>>>(fp);
+    CU_OK(cudaGetLastError());
+    launches += 2;
+  }
+  if (out->cnv6_rot || out->cnv6_trans) {
+    const Layer& L6 = ctx->layers[5];
+    ResizeParams rp;
+    rp.B = B; rp.H = c.H; rp.W = c.W;
+    rp.h = L6.Hout; rp.w = L6.Wout; rp.hp = L6.Hout_p; rp.wp = L6.Wout_p;
+    rp.C = c.cnv6_out; rp.cstride = L6.out_stride;
+    rp.unit_mul = ctx->unit_sample ? 1 : 2; rp.unit_add = ctx->unit_sample ? 0 : 1;
+    rp.src = L6.d_out;
+    const size_t total = (size_t)B * c.H * c.W * (c.cnv6_out / 4);
+    const int blocks = (int)std::min<size_t>((size_t)ctx->num_sms * 8, (total + 255) / 256);
+    float* dsts[2] = {out->cnv6_rot, out->cnv6_trans};
+    for (int br = 0; br < 2; ++br) {
+      if (!dsts[br]) continue;
+      rp.coff = (ctx->nbr == 2 && br == 1) ? c.cnv6_out : 0;      // couple nets return (cnv6, cnv6), posenn.py:66, 187, 311
+      rp.dst = dsts[br];
+      resize_bilinear_kernel<<<blocks, 256, 0, st>>>(rp);
+      CU_OK(cudaGetLastError());
+      ++launches;
+    }
+  }
+  ctx->last_launches = launches;
   return 0;
 }

@@ -129,8 +129,10 @@ class DAVO(object):
         if pairs not in _capi.PAIRS:
             raise ValueError("DAVO.inference: pairs must be one of %s" % sorted(_capi.PAIRS))
         sel = _capi.PAIRS[pairs]
-        if mode not in ('pose',):
-            raise NotImplementedError("davo_b200: inference mode %r is not built (only 'pose')" % (mode,))
+        if mode not in ('pose', 'feature'):
+            raise NotImplementedError("davo_b200: inference mode %r is not built ('pose', 'feature')" % (mode,))
+        if mode == 'feature' and sel != 0:
+            raise ValueError("DAVO.inference: mode='feature' computes every pair (pairs='all')")
         if not self._weights_loaded:
             raise RuntimeError("DAVO.inference: weights not loaded")
         depth = None
@@ -152,6 +154,8 @@ class DAVO(object):
         for name, t in (("img", img), ("flow", flow), ("seg", seg), ("depth", depth)):
             if t is not None and tuple(t.shape) != want[name]:
                 raise ValueError("DAVO.inference: %s has shape %s, expected %s" % (name, tuple(t.shape), want[name]))
+        if mode == 'feature':
+            return self._run_features(B, img, flow, seg, depth, as_torch)
         if _is_torch(img):
             return self._run_device(B, img, flow, seg, as_torch, sel, depth)
         return self._run_host(B, img, flow, seg, sel, depth)
@@ -205,6 +209,41 @@ class DAVO(object):
         if as_torch:
             return {'pose': out}
         return {'pose': out.cpu().numpy()}
+
+    def _run_features(self, B, img, flow, seg, depth, as_torch):
+        """mode='feature' (reference davo.py:1553-1564): poses plus the visualisation tensors, as the
+        same nested dict ``sess.run`` returns.  Lists are ordered [tgt, src0, src1] (davo.py:967-971,
+        1467-1474); 'flows' holds the two source flows (davo.py:989).  One C call, all on the GPU."""
+        import torch
+        if flow is None or seg is None:
+            raise ValueError("DAVO.inference: mode='feature' reads input_flow and input_seglabel")
+        dev = "cuda:%d" % self.device
+        up = lambda t, dt: None if t is None else (t if _is_torch(t) else torch.as_tensor(np.ascontiguousarray(t))).to(
+            device=dev, dtype=dt).contiguous()
+        img, flow, seg, depth = up(img, torch.uint8), up(flow, torch.float32), up(seg, torch.float32), up(depth, torch.float32)
+        H, W, c6 = self.img_height, self.img_width, self.config.cnv6_out
+        f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        u8 = lambda *shape: torch.empty(shape, dtype=torch.uint8, device=dev)
+        pose = f32(B, 2, 6)
+        image, att, masked = f32(3, B, H, W, 3), f32(3, B, H, W, 1), f32(3, B, H, W, 3)
+        seg19, segc, flowc = f32(3, B, H, W, 19), u8(3, B, H, W, 3), u8(2, B, H, W, 3)
+        rot, trans = f32(B, H, W, c6), f32(B, H, W, c6)
+        table = _capi.DavoFeaturesC(*(C.c_void_p(t.data_ptr()) for t in (image, att, masked, seg19, segc, flowc, rot, trans)))
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self._lib.davo_forward_features(self._h, B, ptr(img), ptr(flow), ptr(seg), ptr(depth), ptr(pose),
+                                                    C.byref(table), C.c_void_p(stream)), "davo_forward_features")
+        conv = (lambda t: t) if as_torch else (lambda t: t.cpu().numpy())
+        squeeze = (lambda t: t.squeeze()) if as_torch else np.squeeze        # tf.squeeze drops every unit axis (davo.py:1115)
+        return {
+            'pose': conv(pose),
+            'masks': {'image': [conv(masked[f]) for f in range(3)], 'attention': [conv(att[f]) for f in range(3)]},
+            'features': {'rot': conv(rot), 'trans': conv(trans)},
+            'images': [conv(image[f]) for f in range(3)],
+            'flows': [conv(flowc[k]) for k in range(2)],
+            'segs': [conv(segc[f]) for f in range(3)],
+            'seg_19': [squeeze(conv(seg19[f])) for f in range(3)],
+        }
 
     def _run_host(self, B, img, flow, seg, sel=0, depth=None):
         img = np.ascontiguousarray(img, dtype=np.uint8)

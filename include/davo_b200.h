@@ -106,6 +106,25 @@ int davo_forward_host_pairs(davo_ctx*, int B, int pairs, const uint8_t* img_u8, 
                             const float* seg, const float* depth, float* pose_out,
                             void* cuda_stream);
 
+/* DAVO.inference(sess, mode='feature') (reference davo.py:1553-1564): the poses plus what the
+ * reference fetches for visualisation (consumer generate_feature_map.py:183-380).  DEVICE buffers,
+ * any of them NULL to skip it; frame order of the [3]-lists is the reference's: tgt, src0, src1.
+ * The batch must fit one pass of the conv stack (2*B, or B for posenn 2-5, <= micro_batch). */
+typedef struct {
+  float*   image;         /* [3][B,H,W,3]   tgt_images: the frames in [-1,1]            (davo.py:967-971)  */
+  float*   attention;     /* [3][B,H,W,1]   masks['attention'], after the target override (:1404-1412, 1467) */
+  float*   masked_image;  /* [3][B,H,W,3]   masks['image']: input_images[f][..., :3]     (:1470-1474)       */
+  float*   seg_19;        /* [3][B,H,W,19]  one_hot(int32(seglabel), 19)                 (:1115)            */
+  uint8_t* seg_color;     /* [3][B,H,W,3]   segs: Cityscapes colouring of the labels     (:1005)            */
+  uint8_t* flow_color;    /* [2][B,H,W,3]   flows: Middlebury colouring of flow[:,0:2]   (:988-989)         */
+  float*   cnv6_rot;      /* [B,H,W,cnv6_out] features['rot']: cnv6 of the last PoseNN call (tgt->src1 for the
+                             shared nets), resize_bilinear to HxW                        (:1456-1465)       */
+  float*   cnv6_trans;    /* [B,H,W,cnv6_out] features['trans'] (the same tensor as rot for the couple nets) */
+} davo_features;
+int davo_forward_features(davo_ctx*, int B, const uint8_t* img_u8, const float* flow,
+                          const float* seg, const float* depth, float* pose_out,
+                          const davo_features* out, void* cuda_stream);
+
 /* Same call with HOST buffers (pinned for overlap; pageable works): the end-to-end
  * form of `sess.run` with fed numpy arrays (reference davo.py:1568).  The batch is
  * streamed in micro-batch chunks, the host->device copy of chunk i+1 overlapping

@@ -488,11 +488,120 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
         pose1, _ = pose_net(input_images[3], input_images[2], wts, se_attention, tf32, t1)
         pred_poses = torch.cat([pose0, pose1], dim=-2)                   # davo.py:1458
     if taps is not None:
+        taps["images"] = [t.numpy() for t in (tgt, src0, src1)]                          # davo.py:967-971
+        taps["masked_images"] = [im[..., :3].numpy() for im in input_images[:3]]        # davo.py:1470-1474
         taps["attention_maps"] = [a.numpy() for a in (a_tgt, a_s0, a_s1)]
         taps["attention_weights"] = None if att_w is None else [w.numpy() for w in att_w]
         taps["pair0"] = {k: v.numpy() for k, v in t0.items()}
         taps["pair1"] = {k: v.numpy() for k, v in t1.items()}
     return pred_poses.to(torch.float64).numpy()
+
+
+# --------------------------------------------------------------------------- #
+# mode='feature' (davo.py:1463-1494, 1553-1564)
+# --------------------------------------------------------------------------- #
+def resize_bilinear(x_nhwc: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """``tf.image.resize_bilinear(x, [out_h, out_w])`` of TF 1.13 (align_corners=False, no half-pixel
+    centres): source coordinate = index * (in / out) in float32, lower = trunc, upper = min(lower + 1,
+    in - 1), columns blended first, then rows (davo.py:1463-1464)."""
+    x = np.asarray(x_nhwc)
+    B, h, w, C = x.shape
+    fy = np.arange(out_h, dtype=np.float32) * np.float32(h / np.float32(out_h))
+    fx = np.arange(out_w, dtype=np.float32) * np.float32(w / np.float32(out_w))
+    y0, x0 = fy.astype(np.int64), fx.astype(np.int64)
+    y1, x1 = np.minimum(y0 + 1, h - 1), np.minimum(x0 + 1, w - 1)
+    ly = (fy - y0).astype(x.dtype)[None, :, None, None]
+    lx = (fx - x0).astype(x.dtype)[None, None, :, None]
+    top = x[:, y0][:, :, x0] + (x[:, y0][:, :, x1] - x[:, y0][:, :, x0]) * lx
+    bot = x[:, y1][:, :, x0] + (x[:, y1][:, :, x1] - x[:, y1][:, :, x0]) * lx
+    return top + (bot - top) * ly
+
+
+def cityscapes_colormap() -> np.ndarray:
+    """utils/seg_utils/get_dataset_colormap.py:208-234: 256 rows, the 19 train ids coloured, the rest black."""
+    cm = np.zeros((256, 3), np.uint8)
+    cm[:19] = [(128, 64, 128), (244, 35, 232), (70, 70, 70), (102, 102, 156), (190, 153, 153), (153, 153, 153),
+               (250, 170, 30), (220, 220, 0), (107, 142, 35), (152, 251, 152), (70, 130, 180), (220, 20, 60),
+               (255, 0, 0), (0, 0, 142), (0, 0, 70), (0, 60, 100), (0, 80, 100), (0, 0, 230), (119, 11, 32)]
+    return cm
+
+
+def label_to_color_image(seg_f32: np.ndarray) -> np.ndarray:
+    """get_dataset_colormap.py:383-411: gather_nd(colormap, int32(label)); an index outside the table
+    gives zeros (the GPU gather_nd rule; the table has 256 rows)."""
+    lab = np.trunc(np.asarray(seg_f32)[..., 0]).astype(np.int64)
+    ok = (lab >= 0) & (lab < 256)
+    return cityscapes_colormap()[np.where(ok, lab, 255)] * ok[..., None].astype(np.uint8)
+
+
+def middlebury_wheel() -> np.ndarray:
+    """utils/flow_utils.py:546-593 (float64 [55,3])."""
+    wheel, col = np.zeros((55, 3)), 0
+    for n, fixed, ramp, rising in ((15, 0, 1, True), (6, 1, 0, False), (4, 1, 2, True),
+                                   (11, 2, 1, False), (13, 2, 0, True), (6, 0, 2, False)):
+        steps = np.floor(255 * np.arange(n) / n)
+        wheel[col:col + n, fixed] = 255
+        wheel[col:col + n, ramp] = steps if rising else 255 - steps
+        col += n
+    return wheel
+
+
+def flow_to_uint8_image(flow_f32: np.ndarray) -> np.ndarray:
+    """``convert_to_tf_image(flow_to_image(flow))`` (davo.py:988-989, 1530-1531; utils/flow_utils.py:240-272,
+    461-500), float32 step by step as the TF ops are.  Kept quirks: the max radius is taken over the whole
+    [B,h,w] tensor; ``col1`` is assigned from ``col0`` (:491), so the wheel is not interpolated; ``k1`` is unused."""
+    f32 = np.float32
+    fl = np.asarray(flow_f32, f32)
+    u, v = fl[..., 0].copy(), fl[..., 1].copy()
+    u[np.abs(u) > 1e7] = 0
+    v[np.abs(v) > 1e7] = 0
+    rad = np.sqrt(u * u + v * v)
+    maxrad = max(f32(-1), rad.max())
+    u = u / (maxrad + f32(1e-5))
+    v = v / (maxrad + f32(1e-5))
+    rad = np.sqrt(u * u + v * v)
+    a = np.arctan2(-v, -u) / f32(np.pi)
+    fk = (a + f32(1)) / f32(2) * f32(54) + f32(1)
+    k0 = np.floor(fk)
+    f = fk - k0
+    wheel = middlebury_wheel()
+    idx = np.clip(k0.astype(np.int64) - 1, 0, 54)
+    out = np.empty(u.shape + (3,), np.uint8)
+    for ch in range(3):
+        col0 = (wheel[:, ch][idx] / 255.).astype(f32)
+        col = (f32(1) - f) * col0 + f * col0
+        col = np.where(rad <= 1, f32(1) - rad * (f32(1) - col), col * f32(0.75))
+        img = np.floor(f32(255.) * col) / f32(255.)
+        out[..., ch] = np.clip(img * f32(255.5), 0, 255).astype(np.uint8)     # convert_image_dtype(uint8)
+    return out
+
+
+def davo_features(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.ndarray,
+                  weights: Dict[str, np.ndarray], dtype=torch.float64,
+                  depth: Optional[np.ndarray] = None) -> dict:
+    """``DAVO.inference(sess, mode='feature')`` (davo.py:1553-1564): the fetched dict."""
+    taps: dict = {}
+    pose = davo_forward(version, img_u8, flow, seg, weights, dtype, taps=taps, depth=depth)
+    H, W = img_u8.shape[1], img_u8.shape[2] // 3
+    last = taps["pair1"]                                  # the call whose cnv6 is kept (davo.py:1456-1460)
+    rot = last["cnv6_rotation"]
+    trans = last.get("cnv6_translation", rot)            # couple nets return (cnv6, cnv6)
+    sg = np.asarray(seg, np.float32)
+    segs = [sg[:, 1], sg[:, 0], sg[:, 2]]                 # davo.py:1000-1004
+    seg_19 = []
+    for s_ in segs:                                       # davo.py:1115
+        lab = np.trunc(s_[..., 0]).astype(np.int64)
+        oh = (lab[..., None] == np.arange(NUM_CLASSES)).astype(np.float32)
+        seg_19.append(np.squeeze(oh))
+    return {
+        "pose": pose,
+        "masks": {"image": taps["masked_images"], "attention": taps["attention_maps"]},
+        "features": {"rot": resize_bilinear(rot, H, W), "trans": resize_bilinear(trans, H, W)},
+        "images": taps["images"],
+        "flows": [flow_to_uint8_image(np.asarray(flow)[:, k]) for k in range(2)],      # davo.py:989: [1:]
+        "segs": [label_to_color_image(s_) for s_ in segs],
+        "seg_19": seg_19,
+    }
 
 
 # --------------------------------------------------------------------------- #

@@ -9,6 +9,13 @@ from /root/reference in this container and their outputs on fixed inputs are com
                                                                   [rz,ry,rx,tx,ty,tz] -> 4x4 convention as the
                                                                   TF utils/geo_utils.py:93-119 used on the path)
 
+  utils/flow_utils.py: make_color_wheel (pure numpy), and flow_to_image + compute_color -- their source is
+                       executed UNMODIFIED over a numpy stand-in for the dozen TensorFlow elementwise ops
+                       they call (``_tf_shim``: float32 in, float32 out, one rounding per op), which pins the
+                       structure and quirks of the colouring (whole-tensor max radius, col1 := col0);
+                       the result goes through convert_image_dtype(uint8) as davo.py:989, 1530-1531 does
+  utils/seg_utils/get_dataset_colormap.py: create_cityscapes_label_colormap (pure numpy)
+
 Run:  python tests/golden/make_reference_pins.py
 """
 import importlib.util
@@ -28,6 +35,79 @@ def _load(rel, name):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+class _Shape(tuple):
+    def as_list(self):
+        return list(self)
+
+
+class _T(np.ndarray):
+    """ndarray whose .shape has as_list(), like a TF static shape."""
+    @property
+    def shape(self):
+        return _Shape(np.ndarray.shape.__get__(self))
+
+
+def _t(x, dtype=None):
+    return np.asarray(x, dtype=dtype).view(_T)
+
+
+def _tf_shim():
+    """The TensorFlow calls of flow_to_image / compute_color / label_to_color_image, on numpy."""
+    import types
+    tf = types.ModuleType("tensorflow")
+    tf.float32, tf.int32, tf.uint8 = np.float32, np.int32, np.uint8
+    tf.abs = lambda x: _t(np.abs(x))
+    tf.sqrt = lambda x: _t(np.sqrt(x))
+    tf.floor = lambda x: _t(np.floor(x))
+    tf.atan2 = lambda y, x: _t(np.arctan2(y, x))
+    tf.zeros_like = lambda x: _t(np.zeros_like(x))
+    tf.ones_like = lambda x: _t(np.ones_like(x))
+    tf.where = lambda c, a, b: _t(np.where(c, a, b))
+    tf.stack = lambda xs, axis=0: _t(np.stack(xs, axis))
+    tf.cast = lambda x, dt: _t(np.asarray(x).astype(dt))
+    tf.gather = lambda params, idx: _t(np.asarray(params)[np.asarray(idx)])
+    tf.reshape = lambda x, shape: _t(np.reshape(x, shape))
+    tf.convert_to_tensor = lambda x, name=None: _t(x)
+    tf.gather_nd = lambda params, idx: _t(np.asarray(params)[np.asarray(idx)[:, 0]])
+
+    def reduce_max(x):
+        if isinstance(x, (list, tuple)):          # TF packs [python int, float32 tensor] into a float32 tensor
+            return np.float32(max(np.float32(v) for v in x))
+        return np.float32(np.max(x))
+    tf.reduce_max = reduce_max
+    return tf
+
+
+def _load_with_shim(rel, name):
+    import types
+    saved = {k: sys.modules.get(k) for k in ("tensorflow", "png", "matplotlib", "matplotlib.colors",
+                                             "matplotlib.pyplot", "PIL", "PIL.Image")}
+    sys.modules["tensorflow"] = _tf_shim()
+    for k in list(saved)[1:]:
+        sys.modules[k] = types.ModuleType(k)
+    sys.modules["matplotlib"].colors = sys.modules["matplotlib.colors"]
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["PIL"].Image = sys.modules["PIL.Image"]
+    try:
+        return _load(rel, name)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def flow_cases():
+    rng = np.random.default_rng(5)
+    a = rng.normal(0.32, 15.38, size=(2, 6, 8, 2)).astype(np.float32)
+    b = rng.normal(0, 0.01, size=(1, 4, 4, 2)).astype(np.float32)
+    b[0, 0, 0] = (0.0, 0.0)
+    b[0, 1, 1] = (2e7, 1.0)                        # above UNKNOWN_FLOW_THRESH: zeroed
+    c = np.zeros((1, 2, 4, 2), np.float32)         # an all-zero flow (the target frame's)
+    return [a, b, c]
 
 
 def batch_cases():
@@ -80,6 +160,18 @@ def main():
             write_tum(p, t, pred)
             pins["compute_ate"].append({"t": t.tolist(), "gt": gt.tolist(), "pred": pred.tolist(),
                                         "ate": float(pe.compute_ate(g, p))})
+    fu = _load_with_shim("utils/flow_utils.py", "ref_flow_utils")
+    cmod = _load_with_shim("utils/seg_utils/get_dataset_colormap.py", "ref_colormap")
+    pins["make_color_wheel"] = np.asarray(fu.make_color_wheel(), float).tolist()
+    pins["cityscapes_colormap"] = np.asarray(cmod.create_cityscapes_label_colormap(), int).tolist()
+    pins["flow_to_image_uint8"] = []
+    for fl in flow_cases():
+        img01 = np.asarray(fu.flow_to_image(_t(fl)), np.float32)                 # range 0..1 (davo.py:988)
+        u8 = np.clip(img01 * np.float32(255.5), 0, 255).astype(np.uint8)         # convert_image_dtype (davo.py:1530)
+        pins["flow_to_image_uint8"].append({"flow": fl.tolist(), "image": u8.tolist()})
+    lab = np.array([0, 5, 18, 19, 200, 255], np.float32).reshape(1, 2, 3, 1)
+    pins["label_to_color_image"] = {"label": lab.tolist(),
+                                    "image": np.asarray(cmod.label_to_color_image(_t(lab)), int).tolist()}
     with open(os.path.join(HERE, "reference_pins.json"), "w") as f:
         json.dump(pins, f, indent=1)
     print("wrote", len(pins["complete_batch_size"]), "batch cases,", len(pins["compute_ate"]), "ATE cases")

@@ -472,3 +472,69 @@ def test_allgather_without_communicator_is_a_copy():
     rc = s._lib.davo_allgather_poses(s._h, None, None, 1, None, None)
     assert rc != 0 and "bad argument" in s._lib.davo_last_error(s._h).decode()
 
+
+
+@pytest.mark.parametrize("key", ["headline", "se_seg", "static", "couple_shared", "se_insert", "decouple_net",
+                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt"])
+def test_feature_mode_matches_oracle(key):
+    """DAVO.inference(mode='feature') (davo.py:1553-1564) through davo_forward_features: every fetched tensor
+    against the oracle.  Labels and colourings are byte-exact (flow colours: the atan2 of the two
+    implementations may differ in the last bit, which can move a pixel across a floor())."""
+    _need_gpu()
+    ver, g = G.CASES[key], G.GOLDEN
+    w = S.init_weights(ver, seed=g["weight_seed"], random_bias=True)
+    inputs = S.make_inputs(g["batch"], H, W, seed=g["input_seed"], bad_label_frac=g["bad_label_frac"])
+    depth = S.make_depth(g["batch"], H, W)
+    sysm, dev = _system(ver, g["batch"], w, inputs + (depth,))
+    got = sysm.inference(None, "feature")
+    want = O.davo_features(ver, *inputs, w, torch.float64, depth=depth)
+    assert sorted(got) == sorted(want)
+    _assert_pose(got["pose"], want["pose"])
+    _assert_pose(got["pose"], GOLD[key + "/pose"])
+    for f in range(3):
+        assert got["images"][f].shape == (g["batch"], H, W, 3)
+        assert np.abs(got["images"][f] - want["images"][f]).max() < 1e-6
+        assert got["masks"]["attention"][f].shape == (g["batch"], H, W, 1)
+        assert np.abs(got["masks"]["attention"][f] - want["masks"]["attention"][f]).max() < 5e-6, f
+        assert np.abs(got["masks"]["image"][f] - want["masks"]["image"][f]).max() < 5e-6, f
+        assert np.array_equal(got["seg_19"][f], want["seg_19"][f])
+        assert got["segs"][f].dtype == np.uint8 and np.array_equal(got["segs"][f], want["segs"][f])
+    for k in range(2):
+        d = np.abs(got["flows"][k].astype(int) - want["flows"][k].astype(int))
+        assert got["flows"][k].dtype == np.uint8 and (d != 0).mean() < 1e-3 and np.percentile(d, 99.99) <= 1, (d != 0).mean()
+    c6 = sysm.config.cnv6_out
+    for name in ("rot", "trans"):
+        assert got["features"][name].shape == (g["batch"], H, W, c6)
+        assert _rel(got["features"][name], want["features"][name]) < 1.5e-3, name
+    # same call with host arrays and with torch outputs
+    host = sysm.inference(None, "feature", inputs=inputs + (depth,))
+    assert np.array_equal(host["masks"]["attention"][1], got["masks"]["attention"][1])
+    assert np.array_equal(host["features"]["rot"], got["features"]["rot"])
+    t = sysm.inference(None, "feature", as_torch=True)
+    assert t["features"]["trans"].is_cuda and np.array_equal(t["features"]["trans"].cpu().numpy(), got["features"]["trans"])
+    # the pose mode afterwards is untouched by the extra kernels
+    assert np.array_equal(sysm.inference(None, "pose")["pose"], got["pose"])
+
+
+def test_feature_mode_limits():
+    """One pass only; trajectory selections are refused; NULL outputs are skipped."""
+    _need_gpu()
+    import ctypes as C
+    from davo_b200 import _capi
+    w = S.init_weights(HEADLINE)
+    inputs = S.make_inputs(3, H, W, seed=5)
+    sysm, dev = _system(HEADLINE, 3, w, inputs, micro_batch=4)
+    with pytest.raises(RuntimeError, match="one pass holds 4"):
+        sysm.inference(None, "feature")
+    with pytest.raises(ValueError, match="pairs='all'"):
+        sysm.inference(None, "feature", pairs="trajectory")
+    pose = torch.empty(2, 2, 6, device="cuda")
+    att = torch.full((3, 2, H, W), -7.0, device="cuda")
+    table = _capi.DavoFeaturesC(attention=C.c_void_p(att.data_ptr()))
+    rc = sysm._lib.davo_forward_features(sysm._h, 2, C.c_void_p(dev[0].data_ptr()), C.c_void_p(dev[1].data_ptr()),
+                                         C.c_void_p(dev[2].data_ptr()), None, C.c_void_p(pose.data_ptr()),
+                                         C.byref(table), None)
+    assert rc == 0, sysm._lib.davo_last_error(sysm._h)
+    torch.cuda.synchronize()
+    a = att.cpu().numpy()
+    assert np.all(a[0] == 1) and a[1:].min() >= 0 and a[1:].max() <= 1 and a[1:].std() > 0

@@ -162,6 +162,50 @@ def test_pose_vec2mat_convention_matches_the_reference_numpy_statement():
         assert np.abs(O.pose_vec2mat(v)[0] - want).max() < 2e-6
 
 
+def test_colour_helpers_match_the_reference_sources():
+    """mode='feature' colourings: the oracle against the reference's make_color_wheel, Cityscapes colormap,
+    label_to_color_image and flow_to_image (utils/flow_utils.py:240-272, 461-593;
+    utils/seg_utils/get_dataset_colormap.py:208-234, 383-411), byte for byte."""
+    pins = _pins()
+    assert np.array_equal(np.array(pins["make_color_wheel"]), O.middlebury_wheel())
+    assert np.array_equal(np.array(pins["cityscapes_colormap"]), O.cityscapes_colormap())
+    lab = pins["label_to_color_image"]
+    assert np.array_equal(O.label_to_color_image(np.array(lab["label"], np.float32)), np.array(lab["image"]))
+    for c in pins["flow_to_image_uint8"]:
+        assert np.array_equal(O.flow_to_uint8_image(np.array(c["flow"], np.float32)), np.array(c["image"], np.uint8))
+
+
+def test_resize_bilinear_tf1_rule():
+    """TF 1.x resize_bilinear (align_corners=False): source = index * in/out, no half-pixel shift."""
+    x = np.arange(2 * 3, dtype=np.float64).reshape(1, 2, 3, 1)
+    same = O.resize_bilinear(x, 2, 3)
+    assert np.array_equal(same, x)
+    up = O.resize_bilinear(x, 4, 6)[0, :, :, 0]
+    assert np.allclose(up[0], [0, 0.5, 1, 1.5, 2, 2])          # last column clamps: upper = min(lower+1, in-1)
+    assert np.allclose(up[:, 0], [0, 1.5, 3, 3])               # rows likewise
+    assert np.allclose(up[1, 1], 0.5 * (0 + 0.5 * 1) + 0.5 * (3 + 0.5 * 1))
+    rng = np.random.default_rng(0)
+    y = rng.normal(size=(2, 8, 26, 4))
+    big = O.resize_bilinear(y, 32, 104)
+    assert np.array_equal(big[:, ::4, ::4], y)                 # integer ratio: source samples are kept exactly
+
+
+def test_feature_dict_has_the_reference_layout():
+    """O.davo_features: keys and shapes of DAVO.inference(mode='feature') (davo.py:1553-1564)."""
+    from davo_b200 import synthetic as S
+    ver = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh"
+    img, flow, seg = S.make_inputs(2, 32, 64, seed=3)
+    f = O.davo_features(ver, img, flow, seg, S.init_weights(ver))
+    assert sorted(f) == ["features", "flows", "images", "masks", "pose", "seg_19", "segs"]
+    assert f["pose"].shape == (2, 2, 6) and len(f["flows"]) == 2
+    assert [m.shape for m in f["masks"]["attention"]] == [(2, 32, 64, 1)] * 3
+    assert np.all(f["masks"]["attention"][0] == 1)             # se_flow: the target map is ones (davo.py:1408-1412)
+    assert np.allclose(f["masks"]["image"][0], f["images"][0])
+    assert np.allclose(f["masks"]["image"][1], f["images"][1] * f["masks"]["attention"][1])
+    assert f["features"]["rot"].shape == (2, 32, 64, 128) and f["seg_19"][0].shape == (2, 32, 64, 19)
+    assert np.array_equal(f["seg_19"][1].argmax(-1), np.trunc(seg[:, 0, ..., 0]).astype(int))
+
+
 def test_reference_pins_are_current_when_the_reference_is_here():
     """In the build container the reference tree exists: the committed pins equal a fresh run."""
     ref = os.environ.get("DAVO_REFERENCE_DIR", "/root/reference")
