@@ -1020,7 +1020,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   fp.se_w = ctx->d_sew; fp.static_w = ctx->d_staticw;
   fp.pool_part = ctx->d_pool; fp.pool_count = ctx->d_poolcnt; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
   if (c.att_src == 1 || c.att_src >= 3) {
-    static const int se_dims[6][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}, {1, 8}};
+    static const int se_dims[7][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}, {1, 8}, {21, 19}};
     fp.se_in = se_dims[c.att_src][0]; fp.se_hid = c.se_hidden > 0 ? c.se_hidden : se_dims[c.att_src][1];
     fp.pool_2x2 = (c.att_src == 1 && c.se_pool == 1) ? 1 : 0;
     if (fp.pool_2x2) fp.se_in = 8;
@@ -1109,7 +1109,7 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (cfg->cnv6_out != 128 && cfg->cnv6_out != 64 && cfg->cnv6_out != 32)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128)", cfg->cnv6_out);
   if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
-  if (cfg->att_src < 0 || cfg->att_src > 5) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
+  if (cfg->att_src < 0 || cfg->att_src > 6) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
   if (cfg->se_pool < 0 || cfg->se_pool > 1 || cfg->se_hidden < 0 || cfg->se_hidden > 19 || (cfg->se_pool == 1 && cfg->att_src != 1))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad se_pool / se_hidden");
   if (cfg->att_src == 5 && ((cfg->H * cfg->W) % 4) != 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: se_depth needs H*W % 4 == 0");
@@ -1418,13 +1418,13 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     CU_OK(cudaMemcpy(ctx->d_wpred, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemcpy(ctx->d_bpred, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
   }
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_sew, (19 * 19 + 19 + 19 * 19 + 19) * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_sew, (21 * 19 + 19 + 19 * 19 + 19) * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_staticw, kNumClasses * 4)) return rc;
   if (c.att_src == 1 || c.att_src >= 3) {
     // se(flow|rgb, [8,19]) (attention_module.py:54-103) or se_block(seg_19, ratio=1) (:9-52)
-    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? "se_seg/" : c.att_src == 4 ? "se_rgb/" : "se_depth/");
-    const int din = c.att_src == 1 ? (c.se_pool == 1 ? 8 : 2) : c.att_src == 3 ? 19 : c.att_src == 4 ? 3 : 1;
-    const int dh = c.se_hidden > 0 ? c.se_hidden : (c.att_src == 3 ? 19 : 8);
+    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? "se_seg/" : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? "se_depth/" : "se_segflow/");
+    const int din = c.att_src == 1 ? (c.se_pool == 1 ? 8 : 2) : c.att_src == 3 ? 19 : c.att_src == 4 ? 3 : c.att_src == 5 ? 1 : 21;
+    const int dh = c.se_hidden > 0 ? c.se_hidden : ((c.att_src == 3 || c.att_src == 6) ? 19 : 8);
     const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
     const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
     const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
@@ -1466,7 +1466,7 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
   ctx->cur_seg8 = nullptr;
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward: B=%d outside 1..%d", B, ctx->cfg.max_batch);
-  if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1) && !flow))
+  if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1 || ctx->cfg.att_src == 6) && !flow))
     return fail(ctx, DAVO_ERR_ARG, "davo_forward: null input buffer");
   CU_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1507,7 +1507,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   const davo_config& c = ctx->cfg;
-  if (!img || !pose_out || (c.att_src != 0 && !seg) || ((c.in_mode == 1 || c.att_src == 1) && !flow))
+  if (!img || !pose_out || (c.att_src != 0 && !seg) || ((c.in_mode == 1 || c.att_src == 1 || c.att_src == 6) && !flow))
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: null input buffer");
   CU_OK(cudaSetDevice(ctx->device));
   const size_t hw = (size_t)c.H * c.W;
@@ -1550,7 +1550,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   // the copy stream must not run ahead of work already queued on the caller's stream
   CU_OK(cudaEventRecord(ctx->ev_start, st));
   CU_OK(cudaStreamWaitEvent(cp, ctx->ev_start, 0));
-  const bool need_flow = (c.in_mode == 1 || c.att_src == 1);
+  const bool need_flow = (c.in_mode == 1 || c.att_src == 1 || c.att_src == 6);
   const bool need_seg = c.att_src != 0;
   const bool seg_tgt = need_seg && !c.att_tgt_ones;
   size_t h2d = 0;

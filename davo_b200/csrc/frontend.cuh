@@ -15,7 +15,7 @@
 namespace davo {
 
 constexpr int kPoolSplits = 16;
-constexpr int kPoolDim = 20;     // >= the widest pooled vector (19 class frequencies)
+constexpr int kPoolDim = 24;     // >= the widest pooled vector (19 class frequencies + 2 flow means)
 constexpr int kAttFrames = 3;    // attention-weight slots per unit (see unit_frame)
 constexpr int kPackedC = 16;     // widest packed PoseNN input (see pack_kernel; FrontParams::packed_c = 8 or 16)
 constexpr int kNumClasses = 19;
@@ -52,7 +52,8 @@ struct FrontParams {
   int packed_c;          // 8: [tgt rgb, src rgb, src flow]; 16: the legacy layout of pack_kernel
   int npairs;
   int in_mode;           // 1: flows are concatenated (v1)
-  int att_src;           // 0 none, 1 se_flow, 2 static, 3 se_seg, 4 se_rgb (-> seg), 5 se_depth (-> seg): davo.py:1117-1400
+  int att_src;           // 0 none, 1 se_flow, 2 static, 3 se_seg, 4 se_rgb (-> seg), 5 se_depth (-> seg),
+                         // 6 se_segflow (-> seg): davo.py:1117-1400
   int depth_norm;        // "-norm_depth": SE depth input / 80
   int pool_2x2;          // se_flow only: mode='gp2x2' (attention_module.py:68-78): the means of the four
                          // quadrants [:h/2,:w/2], [:h/2,w/2:], [h/2:,:w/2], [h/2:,w/2:] concatenated -> 8 inputs
@@ -121,6 +122,9 @@ __device__ __forceinline__ float se_activation(float v, int act) {
 //   se_depth*_to_seg (davo.py:1214, 1223): pool = mean(depth of the frame + depth of the TARGET):
 //                                 davo.py:1109 adds a Tensor to a Python list, which TensorFlow
 //                                 broadcasts ([d_tgt, d_src0, d_src1] + d_tgt); 1 -> 8 -> 19
+//   se_SegFlow_to_seg* (davo.py:1341-1372): pool of concat(one_hot(label), SE flow) = the 19 class
+//                                 frequencies followed by the 2 flow means, 21 -> 19|8 -> 19; the
+//                                 target's flow is zeros, whose SE input is the constant se_in(0)
 // blockIdx.z = 0: the pair's source frame; 1: the target frame (variants that do not force the
 // target map to ones).
 __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   __shared__ float s_fc1[kPoolDim];
   __shared__ int s_last;
   float* part = p.pool_part + (((size_t)pl * kAttFrames + fr) * kPoolSplits + blockIdx.x) * kPoolDim;
-  if (p.att_src == 3) {
+  if (p.att_src == 3 || p.att_src == 6) {
     if (threadIdx.x < kNumClasses) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const size_t seg_off = ((size_t)b * 3 + f) * hw;
@@ -150,6 +154,32 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     }
     __syncthreads();
     if (threadIdx.x < kNumClasses) part[threadIdx.x] = (float)s_hist[threadIdx.x];
+    if (p.att_src == 6) {                       // + the flow sums of this split -> part[19], part[20]
+      float s0 = 0.f, s1 = 0.f;
+      if (f != 1) {
+        const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + (f == 2 ? 1 : 0)) * (size_t)hw * 2);
+        const int n4 = hw / 2;
+        const int per4 = (n4 + kPoolSplits - 1) / kPoolSplits;
+        const int beg4 = blockIdx.x * per4, end4 = min(beg4 + per4, n4);
+        for (int i = beg4 + threadIdx.x; i < end4; i += 256) {
+          const float4 v = __ldg(src + i);
+          s0 += se_in_x(v.x, p) + se_in_x(v.z, p);
+          s1 += se_in_y(v.y, p) + se_in_y(v.w, p);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      }
+      if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s0; red[threadIdx.x >> 5][1] = s1; }
+      __syncthreads();
+      if (threadIdx.x < 2) {
+        float a = 0.f;
+        for (int i = 0; i < 8; ++i) a += red[i][threadIdx.x];
+        part[kNumClasses + threadIdx.x] = a;
+      }
+    }
   } else {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     if (p.att_src == 5) {
@@ -254,6 +284,8 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     } else {
       a *= 1.0f / (float)hw;
     }
+    if (p.att_src == 6 && f == 1 && threadIdx.x >= kNumClasses)      // mean of a constant map: the target's zero flow
+      a = threadIdx.x == kNumClasses ? se_in_x(0.f, p) : se_in_y(0.f, p);
     if (p.att_src == 4) a = a * (1.0f / 255.0f) * 2.0f - 1.0f;
     if (p.att_src == 5 && p.depth_norm) a = a / 80.0f;
     s_pool[threadIdx.x] = a;

@@ -116,7 +116,8 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         w["pose_exp_net/%s/weights" % scope] = _xavier_uniform(rng, shape)
         w["pose_exp_net/%s/biases" % scope] = bias(shape[3])
     se_scopes = {V.ATT_SE_FLOW: ("se_flow", 2, 8), V.ATT_SE_SEG: ("se_seg", 19, 19),
-                 V.ATT_SE_RGB_SEG: ("se_rgb", 3, 8), V.ATT_SE_DEPTH_SEG: ("se_depth", 1, 8)}
+                 V.ATT_SE_RGB_SEG: ("se_rgb", 3, 8), V.ATT_SE_DEPTH_SEG: ("se_depth", 1, 8),
+                 V.ATT_SE_SEGFLOW_SEG: ("se_segflow", 21, 19)}
     if cfg.att_src in se_scopes:
         scope, din, dh = se_scopes[cfg.att_src]
         if cfg.se_pool == 1:

@@ -22,7 +22,7 @@ POSENN_COUPLE_DIL = 3            # couple_net_v0_dilation          :12-66
 POSENN_COUPLE = 4                # couple_net_v0                   :257-311
 POSENN_DECOUPLE = 5              # decouple_net_v0                 :314-378
 
-ATT_NONE, ATT_SE_FLOW, ATT_STATIC, ATT_SE_SEG, ATT_SE_RGB_SEG, ATT_SE_DEPTH_SEG = 0, 1, 2, 3, 4, 5
+ATT_NONE, ATT_SE_FLOW, ATT_STATIC, ATT_SE_SEG, ATT_SE_RGB_SEG, ATT_SE_DEPTH_SEG, ATT_SE_SEGFLOW_SEG = 0, 1, 2, 3, 4, 5, 6
 MASK_OFF, MASK_RGB, MASK_ALL, MASK_ALL_555 = 0, 1, 2, 3
 ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2
 ABS_NONE, ABS_BOTH, ABS_H, ABS_V = 0, 1, 2, 3
@@ -57,6 +57,11 @@ _BUILT_AFTER_SE_FLOW = {
     "-se_rgb_to_seg": (ATT_SE_RGB_SEG, 0),            # davo.py:1284-1292
     "-se_seg_wo_tgt": (ATT_SE_SEG, 1),                # davo.py:1304-1310
     "-se_seg": (ATT_SE_SEG, 0),                       # davo.py:1311-1316
+    # se(concat(seg_19, SE flow), "se_segflow", [8|19, 19]) -> weights gathered by label
+    "-se_SegFlow_to_seg_8_wo_tgt": (ATT_SE_SEGFLOW_SEG, 1, 8),    # davo.py:1341-1349
+    "-se_SegFlow_to_seg_8": (ATT_SE_SEGFLOW_SEG, 0, 8),           # davo.py:1350-1357
+    "-se_SegFlow_to_seg_wo_tgt": (ATT_SE_SEGFLOW_SEG, 1, 19),     # davo.py:1358-1366
+    "-se_SegFlow_to_seg": (ATT_SE_SEGFLOW_SEG, 0, 19),            # davo.py:1367-1374
 }
 
 
@@ -169,7 +174,10 @@ def parse_version(version: str) -> DavoConfig:
                 chain_hit = tok
                 break
         if chain_hit is not None:
-            cfg.att_src, cfg.att_tgt_ones = _BUILT_AFTER_SE_FLOW[chain_hit]
+            hit = _BUILT_AFTER_SE_FLOW[chain_hit]
+            cfg.att_src, cfg.att_tgt_ones = hit[0], hit[1]
+            if len(hit) > 2:
+                cfg.se_hidden = hit[2]
         elif "-no_segmask" in version:                          # davo.py:1385
             cfg.att_src = ATT_NONE
             cfg.att_tgt_ones = 1

@@ -48,7 +48,8 @@ typedef struct davo_config {
   int32_t cnv6_out;      /* "-cnv6_<n>", davo.py:1052-1053                             */
   int32_t in_mode;       /* 0 = v0 RGB only, 1 = v1 RGB+flow, davo.py:1057-1065        */
   int32_t att_src;       /* 0 none, 1 se_flow (davo.py:1175), 2 static (:1390), 3 se_seg (:1304),
-                            4 se_rgb -> seg (:1274), 5 se_depth -> seg (:1211)          */
+                            4 se_rgb -> seg (:1274), 5 se_depth -> seg (:1211),
+                            6 se_segflow -> seg (:1341-1372; se_hidden 8 for the "_8" tokens) */
   int32_t att_tgt_ones;  /* target-frame map forced to 1, davo.py:1404-1412, :1393     */
   int32_t mask_mode;     /* 0 off, 1 rgb, 2 all, 3 all(.555), davo.py:1415-1450        */
   int32_t se_act;        /* 0 relu, 1 tanh, 2 leaky_relu(0.2), davo.py:1077-1085       */

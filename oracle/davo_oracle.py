@@ -420,7 +420,7 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att.append(class_gather(pred_segs[i], w19))
         if "-se_depth_wo_tgt_to_seg" in version:
             att[0] = torch.ones_like(att[0])                             # davo.py:1218
-    elif re.search("-se_(depth|disp|SegFlow)", version):
+    elif re.search("-se_(depth|disp)", version):
         _unsupported("attention source in " + version)
     elif "-se_rgb_wo_tgt_to_seg" in version or "-se_rgb_to_seg" in version:   # davo.py:1274-1292
         att, att_w = [], []
@@ -443,6 +443,19 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att.append((onehot * exc[:, None, None, :]).sum(-1, keepdim=True))   # attention_module.py:51, davo.py:1306
         if "-se_seg_wo_tgt" in version:
             att[0] = torch.ones_like(att[0])                             # davo.py:1310
+    elif "-se_SegFlow_to_seg" in version:                                # davo.py:1341-1374 (four tokens)
+        att, att_w = [], []
+        for i in range(3):
+            lab = torch.trunc(pred_segs[i][..., 0]).to(torch.int64)      # davo.py:1115
+            onehot = torch.nn.functional.one_hot(lab.clamp(0, NUM_CLASSES - 1), NUM_CLASSES).to(dtype)
+            onehot = onehot * ((lab >= 0) & (lab < NUM_CLASSES)).to(dtype)[..., None]
+            se_input = torch.cat([onehot, se_in[i]], dim=-1)             # 19 + 2 channels
+            w19 = se_weights(se_input, wts, "pose_exp_net/se_segflow", act)   # [8|19, 19] by the weight shapes
+            att_w.append(w19)
+            att.append((onehot * w19[:, None, None, :]).sum(-1, keepdim=True))
+        if "-se_SegFlow_to_seg_8_wo_tgt" in version or (                 # first match wins: davo.py:1341, 1350, 1358
+                "-se_SegFlow_to_seg_8" not in version and "-se_SegFlow_to_seg_wo_tgt" in version):
+            att[0] = torch.ones_like(att[0])
     elif "-no_segmask" in version:                                       # davo.py:1385-1389
         att = [torch.ones_like(s) for s in pred_segs]
     elif "-segmask_" in version and "-static" in version:                # davo.py:1390-1394

@@ -320,6 +320,8 @@ def test_pair_selection_computes_what_the_trajectory_reads(host):
     ("se_insert", 128, 416, 3, 2),           # passes of 2 pairs: the excitation buffers across ragged passes
     ("se_seg", 128, 416, 5, 4),              # target map computed: all three label planes cross as bytes on the host path
     ("couple_net_v0", 128, 416, 3, 2),       # sample units, passes of 2 samples
+    ("segflow_to_seg", 128, 416, 5, 4),      # 21-wide pooled vector on all three frames; the target's constant SE flow
+    ("segflow_8_wo_tgt", 64, 208, 3, 0),     # v0 input: the flow is read by the SE only and must still cross on the host path
 ])
 def test_variant_corner_cases_device_and_host_entry(case):
     """Variants x sizes x pass sizes the other tests do not combine; device and host entry points agree
@@ -475,7 +477,7 @@ def test_allgather_without_communicator_is_a_copy():
 
 
 @pytest.mark.parametrize("key", ["headline", "se_seg", "static", "couple_shared", "se_insert", "decouple_net",
-                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt"])
+                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt", "segflow_to_seg"])
 def test_feature_mode_matches_oracle(key):
     """DAVO.inference(mode='feature') (davo.py:1553-1564) through davo_forward_features: every fetched tensor
     against the oracle.  Labels and colourings are byte-exact (flow colours: the atan2 of the two

@@ -23,10 +23,21 @@ def test_headline_variant():
     ("-segmask_all-se_seg-fc_tanh", V.ATT_SE_SEG, 0, V.MASK_ALL),              # davo.py:1311-1316
     ("-segmask_all-se_rgb_wo_tgt_to_seg", V.ATT_SE_RGB_SEG, 1, V.MASK_ALL),    # davo.py:1274-1283
     ("-segmask_rgb-se_rgb_to_seg", V.ATT_SE_RGB_SEG, 0, V.MASK_RGB),           # davo.py:1284-1292
+    ("-segmask_all-se_SegFlow_to_seg_8_wo_tgt", V.ATT_SE_SEGFLOW_SEG, 1, V.MASK_ALL),   # davo.py:1341-1349
+    ("-segmask_all-se_SegFlow_to_seg_8", V.ATT_SE_SEGFLOW_SEG, 0, V.MASK_ALL),          # davo.py:1350-1357
+    ("-segmask_rgb-se_SegFlow_to_seg_wo_tgt", V.ATT_SE_SEGFLOW_SEG, 1, V.MASK_RGB),     # davo.py:1358-1366
+    ("-segmask_all-se_SegFlow_to_seg", V.ATT_SE_SEGFLOW_SEG, 0, V.MASK_ALL),            # davo.py:1367-1374
 ])
 def test_attention_and_mask_modes(suffix, att, tgt1, mask):
     c = V.parse_version(BASE + suffix)
     assert (c.att_src, c.att_tgt_ones, c.mask_mode) == (att, tgt1, mask)
+
+
+def test_segflow_bottleneck_width_follows_the_token():
+    """se(..., layer_channels=[8,19]) for the "_8" tokens, [19,19] otherwise (davo.py:1345, 1354, 1362, 1371)."""
+    widths = {"-se_SegFlow_to_seg_8_wo_tgt": 8, "-se_SegFlow_to_seg_8": 8, "-se_SegFlow_to_seg_wo_tgt": 19, "-se_SegFlow_to_seg": 19}
+    for tok, hid in widths.items():
+        assert V.parse_version(BASE + "-segmask_all" + tok).se_hidden == hid
 
 
 def test_order_sensitive_tokens():
