@@ -332,8 +332,12 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "pcie_h2d_gbs": pcie_gbs,
                 "pcie_bound": world * 2 * B / (h2d / (pcie_gbs * 1e9)),
-                "note": "host inputs cross PCIe inside the timed region: pcie_bound = frame pairs / (h2d bytes / "
-                        "measured pinned copy rate) is the ceiling of this number on this box"},
+                "host_input_bytes_per_step": world * B * (128 * 416 * (9 + 4 * 2 * 4 + 3 * 4)),
+                "note": "host inputs (uint8 frames, float32 flow and labels, as the reference feeds them) enter the "
+                        "timed region as numpy arrays; the library copies only the planes the graph reads and, on "
+                        "the CPU inside the timed region, narrows labels to bytes and 3/4 of the flow planes to "
+                        "binary16 (the precision both entry points read the flow with), so h2d_bytes_per_step is "
+                        "what crossed PCIe; pcie_bound = frame pairs / (h2d bytes / measured pinned copy rate)"},
         "roofline": roofline, "cpu_baseline": cpu,
         "trajectory_mode": {"samples_per_s": B / (traj_ms * 1e-3), "ms_per_step": traj_ms, "frame_pairs_computed": B + 1,
                             "note": "pairs='trajectory_first' (rank 0, device-resident): the same output file as the "

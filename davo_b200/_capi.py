@@ -19,7 +19,7 @@ SYMBOLS = (
     "davo_forward_host", "davo_get_intermediate", "davo_last_launch_count",
     "davo_last_host_copy_bytes",
     "davo_profile_layers", "davo_debug_set_conv_impl", "davo_forward_pairs", "davo_forward_host_pairs",
-    "davo_forward_features",
+    "davo_forward_features", "davo_debug_flows_to_half",
     "davo_comm_unique_id", "davo_comm_create", "davo_comm_world", "davo_allgather_poses",
     "davo_last_error",
     "davo_destroy", "davo_build_info",
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     lib.davo_profile_layers.argtypes = [vp, ip, fp, C.POINTER(ip), vp]
     lib.davo_debug_set_conv_impl.argtypes = [vp, ip]
     lib.davo_forward_features.argtypes = [vp, ip, vp, vp, vp, vp, vp, C.POINTER(DavoFeaturesC), vp]
+    lib.davo_debug_flows_to_half.argtypes = [vp, vp, C.c_longlong, ip]
     lib.davo_comm_unique_id.argtypes = [vp]
     lib.davo_comm_create.argtypes = [vp, vp, ip, ip]
     lib.davo_comm_world.argtypes = [vp, C.POINTER(ip), C.POINTER(ip)]
@@ -84,7 +85,7 @@ def load() -> C.CDLL:
     lib.davo_destroy.argtypes = [vp]
     lib.davo_destroy.restype = None
     lib.davo_build_info.restype = C.c_char_p
-    for s in SYMBOLS[:17]:
+    for s in SYMBOLS[:18]:
         getattr(lib, s).restype = ip
     _LIB = lib
     return lib

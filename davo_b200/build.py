@@ -13,12 +13,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdavo_b200.so")
-SOURCES = ["davo_capi.cu"]
+SOURCES = ["davo_capi.cu", "host_convert.cpp"]
 
 
 def _deps():
     import glob
     return (glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+            glob.glob(os.path.join(CSRC, "*.cpp")) + glob.glob(os.path.join(CSRC, "*.h")) +
             [os.path.join(HERE, "..", "include", "davo_b200.h")])
 
 NVCC_FLAGS = [

@@ -5,6 +5,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 
 #include <algorithm>
 #include <cmath>
@@ -29,6 +30,7 @@
 #include "frontend.cuh"
 #include "features.cuh"
 #include "comm.cuh"
+#include "host_convert.h"
 
 using namespace davo;
 
@@ -233,6 +235,15 @@ struct davo_ctx {
   // Labels cross PCIe as bytes: converted on the CPU into pinned staging (h_seg8), copied to s_seg8.
   uint8_t *h_seg8[kStage] = {}, *s_seg8[kStage] = {};
   cudaEvent_t ev_seg8[kStage] = {};  // h_seg8[i] has been read by its copy
+  // The flow crosses PCIe as binary16 (host_convert.cpp; frontend.cuh: flow_q): h_flow16 -> s_flow16,
+  // [chunk][2 planes][H][W][2] halves.  ev_seg8[i] covers both pinned staging buffers of slot i.
+  uint16_t *h_flow16[kStage] = {}, *s_flow16[kStage] = {};
+  bool host_flow16 = true;
+  const uint16_t* cur_flow16 = nullptr;   // binary16 flow of the chunk being enqueued (NULL: float flow) ...
+  int cur_n16 = 0;                        // ... for its first cur_n16 samples; the rest of the chunk crosses as float32
+  const uint16_t* last_flow16 = nullptr;
+  int last_n16 = 0;
+  float flow16_frac = 0.75f;              // share of a chunk's samples converted on the CPU (the rest keeps the copy engine busy)
   HostPool* pool = nullptr;
   bool host_seg8 = true;
   const uint8_t* cur_seg8 = nullptr; // byte labels of the chunk being enqueued (NULL: float labels)
@@ -1017,6 +1028,8 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   fp.se_act = c.se_act; fp.flow_abs = c.flow_abs; fp.flow_norm = c.flow_norm;
   fp.img = img; fp.flow = flow; fp.seg = seg; fp.depth = ctx->cur_depth; fp.depth_norm = c.depth_norm;
   fp.seg8 = seg ? nullptr : ctx->cur_seg8;       // the host entry point passes seg = NULL with byte labels
+  fp.flow16 = reinterpret_cast<const __half*>(ctx->cur_flow16);   // host entry point: the first cur_n16 samples of the chunk
+  fp.n_flow16 = ctx->cur_flow16 ? ctx->cur_n16 : 0;
   fp.se_w = ctx->d_sew; fp.static_w = ctx->d_staticw;
   fp.pool_part = ctx->d_pool; fp.pool_count = ctx->d_poolcnt; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
   if (c.att_src == 1 || c.att_src >= 3) {
@@ -1137,6 +1150,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (mb > ctx->max_units()) mb = ctx->max_units();
   ctx->mb = mb;
   if (const char* e = getenv("DAVO_B200_HOST_SEG8")) ctx->host_seg8 = strcmp(e, "0") != 0;   // "0": labels cross PCIe as floats
+  if (const char* e = getenv("DAVO_B200_HOST_FLOW16")) ctx->host_flow16 = strcmp(e, "0") != 0;   // "0": flow crosses PCIe as float32
+  if (const char* e = getenv("DAVO_B200_HOST_FLOW16_FRAC")) ctx->flow16_frac = std::max(0.0f, std::min(1.0f, (float)atof(e)));
   if (const char* e = getenv("DAVO_B200_PDL")) ctx->pdl = strcmp(e, "0") != 0;               // "0": plain stream order
   if (const char* cr = getenv("DAVO_B200_WEIGHT_ROUNDING"))     // "nearest": plain round-to-nearest
     ctx->compensated_rounding = strcmp(cr, "nearest") != 0;
@@ -1154,6 +1169,8 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
     if (ctx->s_seg[i]) cudaFree(ctx->s_seg[i]);
     if (ctx->s_depth[i]) cudaFree(ctx->s_depth[i]);
     if (ctx->s_seg8[i]) cudaFree(ctx->s_seg8[i]);
+    if (ctx->s_flow16[i]) cudaFree(ctx->s_flow16[i]);
+    if (ctx->h_flow16[i]) cudaFreeHost(ctx->h_flow16[i]);
     if (ctx->h_seg8[i]) cudaFreeHost(ctx->h_seg8[i]);
     if (ctx->ev_seg8[i]) cudaEventDestroy(ctx->ev_seg8[i]);
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -1464,6 +1481,7 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
   if (ctx->cfg.att_src == 5 && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward: this variant reads input_depth; got NULL");
   ctx->cur_depth = depth;
   ctx->cur_seg8 = nullptr;
+  ctx->cur_flow16 = nullptr; ctx->cur_n16 = 0;
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1 || ctx->cfg.att_src == 6) && !flow))
@@ -1485,6 +1503,7 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
   ctx->last_npairs_mb = last_n;
   ctx->last_img = img; ctx->last_flow = flow; ctx->last_seg = seg; ctx->last_pose = pose_out; ctx->last_B = B;
   ctx->last_seg8 = nullptr;
+  ctx->last_flow16 = nullptr; ctx->last_n16 = 0;
   ctx->last_pairs = pairs;
   return 0;
 }
@@ -1512,6 +1531,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   CU_OK(cudaSetDevice(ctx->device));
   const size_t hw = (size_t)c.H * c.W;
   const size_t n_img = hw * 9, n_flow = hw * 8, n_seg = hw * 3;   // elements per sample
+  const bool uses_flow = (c.in_mode == 1 || c.att_src == 1 || c.att_src == 6);
   // Host inputs arrive over PCIe more slowly than the stack computes, so what matters is how soon
   // compute can start behind the copy: chunks of 16 samples (8 chunks per 128-sample batch).
   const int ups = ctx->unit_sample ? 1 : 2;                        // units of a pass per sample
@@ -1531,14 +1551,22 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
       if (ctx->host_seg8 && c.att_src != 0) {
         CU_OK(cudaMalloc((void**)&ctx->s_seg8[i], n_seg * cs));
         CU_OK(cudaHostAlloc((void**)&ctx->h_seg8[i], n_seg * cs, cudaHostAllocDefault));
-        CU_OK(cudaEventCreateWithFlags(&ctx->ev_seg8[i], cudaEventDisableTiming));
       }
+      if (ctx->host_flow16 && uses_flow) {
+        CU_OK(cudaMalloc((void**)&ctx->s_flow16[i], n_flow / 2 * sizeof(uint16_t) * cs));
+        CU_OK(cudaHostAlloc((void**)&ctx->h_flow16[i], n_flow / 2 * sizeof(uint16_t) * cs, cudaHostAllocDefault));
+      }
+      CU_OK(cudaEventCreateWithFlags(&ctx->ev_seg8[i], cudaEventDisableTiming));
       CU_OK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
       CU_OK(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
     }
     CU_OK(cudaMalloc((void**)&ctx->s_pose, (size_t)12 * 4 * c.max_batch));
-    if (ctx->host_seg8 && c.att_src != 0) {
-      int nthreads = std::max(2, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+    if ((ctx->host_seg8 && c.att_src != 0) || (ctx->host_flow16 && uses_flow)) {
+      // conversion threads: the host's hardware threads shared among the ranks of the box (torchrun sets
+      // LOCAL_WORLD_SIZE), at most 16: one thread streams ~9 GB/s and a chunk is ~30 MB of traffic
+      int ranks_here = 1;
+      if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks_here = std::max(1, atoi(e));
+      int nthreads = std::max(2, std::min(16, (int)std::thread::hardware_concurrency() / ranks_here));
       if (const char* e = getenv("DAVO_B200_HOST_THREADS")) nthreads = std::max(1, std::min(atoi(e), 32));
       ctx->pool = new HostPool(nthreads - 1);
     }
@@ -1550,7 +1578,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   // the copy stream must not run ahead of work already queued on the caller's stream
   CU_OK(cudaEventRecord(ctx->ev_start, st));
   CU_OK(cudaStreamWaitEvent(cp, ctx->ev_start, 0));
-  const bool need_flow = (c.in_mode == 1 || c.att_src == 1 || c.att_src == 6);
+  const bool need_flow = uses_flow;
   const bool need_seg = c.att_src != 0;
   const bool seg_tgt = need_seg && !c.att_tgt_ones;
   size_t h2d = 0;
@@ -1569,30 +1597,66 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
     if (chunk >= davo_ctx::kStage) CU_OK(cudaStreamWaitEvent(cp, ctx->ev_consumed[buf], 0));
     CU_OK(cudaMemcpyAsync(ctx->s_img[buf], img + n_img * s0, n_img * ns, cudaMemcpyHostToDevice, cp));
     h2d += n_img * ns;
-    if (need_flow) {
-      CU_OK(cudaMemcpy2DAsync(ctx->s_flow[buf], n_flow * 4, flow + n_flow * s0, n_flow * 4, n_flow * 2, ns,
-                              cudaMemcpyHostToDevice, cp));
-      h2d += n_flow * 2 * ns;
-    }
-    ctx->cur_seg8 = nullptr;
-    if (need_seg && ctx->host_seg8) {
-      // Labels are small integers held in floats: convert the planes the graph reads to bytes on
-      // the CPU (a few threads, while the DMA engine moves this chunk's image and flow) and send a
-      // quarter of the bytes.  The pinned buffer is reused every kStage chunks: wait for its copy.
+    // Labels are small integers held in floats, and the flow is read with 11 significant bits
+    // (frontend.cuh: flow_q): a few CPU threads convert the planes the graph reads to bytes /
+    // binary16 in pinned staging while the DMA engine moves the previous chunk, and a quarter /
+    // half of the bytes cross PCIe.  The pinned buffers are reused every kStage chunks: wait for
+    // their copies first.
+    // The CPU conversion streams ~64 GB/s on this class of host and would become the bottleneck if it
+    // took every flow plane, while the copy engine has bandwidth to spare: the first n16 samples of a
+    // chunk cross as binary16 and the rest as float32 (flow16_frac; both read through flow_q, so the
+    // split does not change a bit of the result).
+    const bool conv_seg = need_seg && ctx->host_seg8;
+    int n16 = (need_flow && ctx->host_flow16) ? std::min(ns, (int)std::lround(ctx->flow16_frac * ns)) : 0;
+    const bool conv_flow = n16 > 0;
+    const int planes[3] = {0, 2, 1};
+    const int npl = seg_tgt ? 3 : 2;
+    std::atomic<int> flow_bad{0};
+    if (conv_seg || conv_flow) {
       if (chunk >= davo_ctx::kStage) CU_OK(cudaEventSynchronize(ctx->ev_seg8[buf]));
-      const float* src = seg + n_seg * s0;
-      uint8_t* dst = ctx->h_seg8[buf];
-      const int planes[3] = {0, 2, 1};
-      const int npl = seg_tgt ? 3 : 2;
-      const size_t jobs = (size_t)ns * npl;
+      const float* lsrc = conv_seg ? seg + n_seg * s0 : nullptr;
+      uint8_t* ldst = ctx->h_seg8[buf];
+      const float* fsrc = conv_flow ? flow + n_flow * s0 : nullptr;
+      uint16_t* fdst = ctx->h_flow16[buf];
+      const size_t ljobs = conv_seg ? (size_t)ns * npl : 0, fjobs = conv_flow ? (size_t)n16 * 2 : 0;
+      const size_t fl = hw * 2;                                  // floats per flow plane
       ctx->pool->run([&](int part, int parts) {
-        // split every plane into `parts` pieces so that few-sample chunks still use all threads
-        for (size_t j = 0; j < jobs; ++j) {
-          const size_t off = ((j / npl) * 3 + planes[j % npl]) * hw;
-          const size_t beg = hw * part / parts, end = hw * (part + 1) / parts;
-          labels_to_bytes(src + off + beg, dst + off + beg, end - beg);
+        // Work units are pieces of a plane: `sub` pieces per plane so that every thread gets a few
+        // long contiguous streams (a label plane costs half a flow plane: 4 bytes read per pixel vs 8).
+        const size_t sub = (fjobs + ljobs) >= (size_t)4 * parts ? 1 : (size_t)parts;
+        const size_t units = (fjobs + ljobs) * sub;
+        for (size_t u = part; u < units; u += parts) {
+          const size_t j = u / sub, piece = u % sub;
+          if (j < fjobs) {
+            const size_t beg = (fl * piece / sub) & ~(size_t)15, end = piece + 1 == sub ? fl : ((fl * (piece + 1) / sub) & ~(size_t)15);
+            if (!davo_host::flows_to_half(fsrc + (j / 2) * n_flow + (j % 2) * fl + beg, fdst + j * fl + beg, end - beg))
+              flow_bad.store(1, std::memory_order_relaxed);
+          } else {
+            const size_t jl = j - fjobs;
+            const size_t off = ((jl / npl) * 3 + planes[jl % npl]) * hw;
+            const size_t beg = (hw * piece / sub) & ~(size_t)15, end = piece + 1 == sub ? hw : ((hw * (piece + 1) / sub) & ~(size_t)15);
+            labels_to_bytes(lsrc + off + beg, ldst + off + beg, end - beg);
+          }
         }
       });
+    }
+    ctx->cur_flow16 = nullptr;
+    ctx->cur_n16 = 0;
+    if (conv_flow && flow_bad.load()) n16 = 0;                  // a value with no finite half: the whole chunk as float32
+    if (n16 > 0) {
+      CU_OK(cudaMemcpyAsync(ctx->s_flow16[buf], ctx->h_flow16[buf], hw * 4 * sizeof(uint16_t) * n16, cudaMemcpyHostToDevice, cp));
+      h2d += hw * 4 * sizeof(uint16_t) * n16;
+      ctx->cur_flow16 = ctx->s_flow16[buf];
+      ctx->cur_n16 = n16;
+    }
+    if (need_flow && n16 < ns) {
+      CU_OK(cudaMemcpy2DAsync(ctx->s_flow[buf] + n_flow * n16, n_flow * 4, flow + n_flow * (s0 + n16), n_flow * 4, n_flow * 2,
+                              ns - n16, cudaMemcpyHostToDevice, cp));
+      h2d += n_flow * 2 * (ns - n16);
+    }
+    ctx->cur_seg8 = nullptr;
+    if (conv_seg) {
+      uint8_t* dst = ctx->h_seg8[buf];
       if (seg_tgt) {
         CU_OK(cudaMemcpyAsync(ctx->s_seg8[buf], dst, n_seg * ns, cudaMemcpyHostToDevice, cp));
         h2d += n_seg * ns;
@@ -1601,7 +1665,6 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
           CU_OK(cudaMemcpy2DAsync(ctx->s_seg8[buf] + hw * pl, n_seg, dst + hw * pl, n_seg, hw, ns, cudaMemcpyHostToDevice, cp));
         h2d += hw * 2 * ns;
       }
-      CU_OK(cudaEventRecord(ctx->ev_seg8[buf], cp));
       ctx->cur_seg8 = ctx->s_seg8[buf];
     } else if (need_seg) {
       if (seg_tgt) {
@@ -1619,6 +1682,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
       h2d += n_seg * 4 * ns;
     }
     ctx->cur_depth = ctx->s_depth[buf];
+    if (conv_seg || conv_flow) CU_OK(cudaEventRecord(ctx->ev_seg8[buf], cp));   // pinned staging of this slot has been read
     CU_OK(cudaEventRecord(ctx->ev_copied[buf], cp));
     CU_OK(cudaStreamWaitEvent(st, ctx->ev_copied[buf], 0));
     // a chunk is a batch of its own: only the first one may hold the first sample's tgt->src0
@@ -1641,6 +1705,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   ctx->last_d2h = (long long)12 * 4 * B;
   const int lastbuf = (chunk - 1) % davo_ctx::kStage;
   ctx->last_img = ctx->s_img[lastbuf]; ctx->last_flow = ctx->s_flow[lastbuf];
+  ctx->last_flow16 = ctx->cur_flow16; ctx->last_n16 = ctx->cur_n16;
   ctx->last_seg = ctx->cur_seg8 ? nullptr : ctx->s_seg[lastbuf]; ctx->last_seg8 = ctx->cur_seg8;
   ctx->last_pose = ctx->s_pose; ctx->last_B = last_ns;
   ctx->last_pairs = (pairs == DAVO_PAIRS_TRAJECTORY_FIRST && chunk > 1) ? DAVO_PAIRS_TRAJECTORY : pairs;
@@ -1713,6 +1778,7 @@ extern "C" int davo_debug_layer_timing(davo_ctx* ctx, int layer, long long* out,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int npairs = std::min(ctx->last_B * (ctx->unit_sample ? 1 : 2), ctx->mb);
   ctx->cur_seg8 = ctx->last_seg8;
+  ctx->cur_flow16 = ctx->last_flow16; ctx->cur_n16 = ctx->last_n16;
   if (int rc = launch_conv(ctx, ctx->layers[layer], npairs, st)) return rc;
   if (int rc = launch_conv(ctx, ctx->layers[layer], npairs, st)) return rc;
   CU_OK(cudaStreamSynchronize(st));
@@ -1735,6 +1801,7 @@ extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int*
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int npairs = std::min(ctx->last_B * (ctx->unit_sample ? 1 : 2), ctx->mb);
   ctx->cur_seg8 = ctx->last_seg8;
+  ctx->cur_flow16 = ctx->last_flow16; ctx->cur_n16 = ctx->last_n16;
   if (npairs_out) *npairs_out = npairs;
   cudaEvent_t e0, e1;
   CU_OK(cudaEventCreate(&e0));
@@ -1917,4 +1984,11 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
   }
   ctx->last_launches = launches;
   return 0;
+}
+
+// Test hook (no GPU needed): the CPU float32 -> binary16 conversion of the host entry point.
+extern "C" int davo_debug_flows_to_half(const float* src, uint16_t* dst, long long n, int portable) {
+  if (!src || !dst || n < 0) return DAVO_ERR_ARG;
+  const bool ok = portable ? davo_host::flows_to_half_portable(src, dst, (size_t)n) : davo_host::flows_to_half(src, dst, (size_t)n);
+  return ok ? 0 : 1;
 }

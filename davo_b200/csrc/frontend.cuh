@@ -8,6 +8,7 @@
 // Frame pair index p = 2 * sample + source (0: tgt->src0, 1: tgt->src1), the
 // row order of pred_poses (davo.py:1456-1458).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "ptx.cuh"
@@ -65,6 +66,8 @@ struct FrontParams {
   int flow_norm;
   const uint8_t* img;    // [B][H][3W][3]
   const float* flow;     // [B][4][H][W][2]
+  const __half* flow16;  // the two planes the graph reads, already binary16: [B][2][H][W][2] (host entry point) ...
+  int n_flow16;          // ... for samples b < n_flow16 of this batch; the others are read from `flow`
   const float* seg;      // [B][3][H][W][1]
   const uint8_t* seg8;   // the same labels as bytes (255 = outside 0..18), or NULL: the host entry point
                          // converts the float labels on the CPU so that a quarter of their bytes crosses PCIe
@@ -92,6 +95,34 @@ __device__ __forceinline__ void labels4_at(const FrontParams& p, size_t plane_of
     const float4 v = __ldg(reinterpret_cast<const float4*>(p.seg + plane_off + pix));
     lab[0] = (int)v.x; lab[1] = (int)v.y; lab[2] = (int)v.z; lab[3] = (int)v.w;
   }
+}
+
+// The flow input is DEFINED as rounded to IEEE binary16 (11 significant bits, what the TF32 conv
+// operands keep anyway): the host entry point can then round on the CPU and move half the bytes over
+// PCIe with bit-identical results (host_convert.cpp).  Values that do not fit a finite half
+// (|x| >= 65520, NaN) pass through unchanged; the host sends a chunk holding one as float32.
+__device__ __forceinline__ float flow_q(float x) {
+  return fabsf(x) < 65520.0f ? __half2float(__float2half_rn(x)) : x;
+}
+// pixel `pix` (x, y) of flow plane k (0: src0 -> tgt, 1: src1 -> tgt; davo.py:978-982) of sample b
+__device__ __forceinline__ float2 flow1_at(const FrontParams& p, int b, int k, int pix, int hw) {
+  if (b < p.n_flow16) {
+    const __half2 h = *reinterpret_cast<const __half2*>(p.flow16 + (((size_t)b * 2 + k) * hw + pix) * 2);
+    return __half22float2(h);
+  }
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p.flow + (((size_t)b * 4 + k) * hw + pix) * 2));
+  return make_float2(flow_q(v.x), flow_q(v.y));
+}
+// pixels pix, pix + 1 (pix even): (x0, y0, x1, y1)
+__device__ __forceinline__ float4 flow2_at(const FrontParams& p, int b, int k, int pix, int hw) {
+  if (b < p.n_flow16) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p.flow16 + (((size_t)b * 2 + k) * hw + pix) * 2));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, c.x, c.y);
+  }
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p.flow + (((size_t)b * 4 + k) * hw + pix) * 2));
+  return make_float4(flow_q(v.x), flow_q(v.y), flow_q(v.z), flow_q(v.w));
 }
 
 __device__ __forceinline__ float se_in_x(float v, const FrontParams& p) {
@@ -157,12 +188,11 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     if (p.att_src == 6) {                       // + the flow sums of this split -> part[19], part[20]
       float s0 = 0.f, s1 = 0.f;
       if (f != 1) {
-        const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + (f == 2 ? 1 : 0)) * (size_t)hw * 2);
         const int n4 = hw / 2;
         const int per4 = (n4 + kPoolSplits - 1) / kPoolSplits;
         const int beg4 = blockIdx.x * per4, end4 = min(beg4 + per4, n4);
         for (int i = beg4 + threadIdx.x; i < end4; i += 256) {
-          const float4 v = __ldg(src + i);
+          const float4 v = flow2_at(p, b, f == 2 ? 1 : 0, 2 * i, hw);
           s0 += se_in_x(v.x, p) + se_in_x(v.z, p);
           s1 += se_in_y(v.y, p) + se_in_y(v.w, p);
         }
@@ -193,13 +223,13 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
         s0 += (a.x + c.x) + (a.y + c.y) + (a.z + c.z) + (a.w + c.w);
       }
     } else if (p.att_src == 1) {
-      const float4* src = reinterpret_cast<const float4*>(p.flow + ((size_t)b * 4 + (f == 2 ? 1 : 0)) * (size_t)hw * 2);
-      const int n4 = hw / 2;                          // float4 = 2 pixels
+      const int fk = f == 2 ? 1 : 0;                  // flow plane of this frame
+      const int n4 = hw / 2;                          // one load = 2 pixels
       const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
       const int beg = blockIdx.x * per, end = min(beg + per, n4);
       if (f != 1 && !p.pool_2x2)                      // the target's flow is all zeros (davo.py:979)
         for (int i = beg + threadIdx.x; i < end; i += 256) {
-          const float4 v = __ldg(src + i);
+          const float4 v = flow2_at(p, b, fk, 2 * i, hw);
           s0 += se_in_x(v.x, p) + se_in_x(v.z, p);
           s1 += se_in_y(v.y, p) + se_in_y(v.w, p);
         }
@@ -208,7 +238,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
         float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const int hh = p.H / 2, hw2 = p.W / 2;
         for (int i = beg + threadIdx.x; i < end; i += 256) {
-          const float4 v = __ldg(src + i);
+          const float4 v = flow2_at(p, b, fk, 2 * i, hw);
           const int pix = 2 * i, h = pix / p.W, w = pix - h * p.W;       // W is even: both pixels in one row
           const int qa = (h >= hh ? 2 : 0) + (w >= hw2 ? 1 : 0), qb = (h >= hh ? 2 : 0) + (w + 1 >= hw2 ? 1 : 0);
 #pragma unroll
@@ -349,7 +379,6 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
   const float inv_w = 1.0f / (float)p.W;
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
   const size_t seg_src = ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw, seg_tgt = ((size_t)b * 3 + 1) * hw;
-  const float2* flow_src = reinterpret_cast<const float2*>(p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2);
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * kPackedC);
   const int src_col0 = (k == 0) ? 0 : 2 * p.W;
   for (int base = blockIdx.x * 256; base < hw; base += kPackBlocksPerPair * 256) {
@@ -373,7 +402,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
     const float sr = img_norm(ps[0]) * ms, sg = img_norm(ps[1]) * ms, sb = img_norm(ps[2]) * ms;
     float fx = 0.f, fy = 0.f;
     if (p.in_mode == 1) {
-      const float2 f = __ldg(flow_src + pix);
+      const float2 f = flow1_at(p, b, k, pix, hw);
       const float m = p.mask_flow ? a_src : 1.0f;
       fx = f.x * m;
       fy = f.y * m;
@@ -443,7 +472,6 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
   const size_t seg_src = ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw, seg_tgt = ((size_t)b * 3 + 1) * hw;
-  const float* flow_src = p.flow + ((size_t)b * 4 + k) * (size_t)hw * 2;
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 8);
   const int src_col0 = (k == 0) ? 0 : 2 * p.W;
   float4* st = s_stage[warp];
@@ -474,8 +502,7 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
       }
       float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f};
       if (p.in_mode == 1) {
-        const float4 f0 = __ldg(reinterpret_cast<const float4*>(flow_src + (size_t)p0 * 2));
-        const float4 f1 = __ldg(reinterpret_cast<const float4*>(flow_src + (size_t)p0 * 2 + 4));
+        const float4 f0 = flow2_at(p, b, k, p0, hw), f1 = flow2_at(p, b, k, p0 + 2, hw);
         fx[0] = f0.x; fy[0] = f0.y; fx[1] = f0.z; fy[1] = f0.w;
         fx[2] = f1.x; fy[2] = f1.y; fx[3] = f1.z; fy[3] = f1.w;
       }
@@ -526,7 +553,6 @@ __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
   __syncthreads();
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
   const size_t seg_b = (size_t)b * 3 * hw;
-  const float2* flow_b = reinterpret_cast<const float2*>(p.flow + (size_t)b * 4 * (size_t)hw * 2);
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 16);
   for (int pix = blockIdx.x * 256 + threadIdx.x; pix < hw; pix += kPackBlocksPerPair * 256) {
     const int h = pix / p.W, w = pix - h * p.W;
@@ -554,7 +580,7 @@ __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) v[3 + 5 * sidx + c] = img_norm(ps[c]) * ms;
       if (p.in_mode == 1) {
-        const float2 f = __ldg(flow_b + (size_t)sidx * hw + pix);
+        const float2 f = flow1_at(p, b, sidx, pix, hw);
         v[6 + 5 * sidx] = f.x * mf;
         v[7 + 5 * sidx] = f.y * mf;
       }

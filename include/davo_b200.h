@@ -162,6 +162,10 @@ int davo_profile_layers(davo_ctx*, int iters, float* ms_out, int* npairs_out,
  * direct convolution on CUDA cores, used only to cross-check the tensor-core
  * path on the GPU. */
 int davo_debug_set_conv_impl(davo_ctx*, int impl);
+/* Test hook, CPU only: the float32 -> IEEE binary16 conversion the host entry point applies to the
+ * flow planes before they cross PCIe (portable != 0: the scalar path instead of F16C).  Returns 0,
+ * or 1 when some value has no finite half (|x| >= 65520, NaN): such a chunk is sent as float32. */
+int davo_debug_flows_to_half(const float* src, uint16_t* dst, long long n, int portable);
 
 /* --- multi-GPU: one process and one handle per GPU, samples sharded by rank, one collective ---
  * The reference is single-process (test_kitti_pose.py:133-153); sharding its sample list by rank

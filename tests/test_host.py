@@ -379,3 +379,25 @@ def test_comm_unique_id_binds_nccl_at_run_time():
     assert lib.davo_comm_unique_id(b) == 0
     assert bytes(a) != bytes(b) and any(bytes(a))
     assert lib.davo_comm_unique_id(None) != 0 and b"null argument" in lib.davo_last_error(None)
+
+
+def test_host_flow_conversion_is_ieee_binary16_round_to_nearest_even():
+    """davo_debug_flows_to_half (the CPU side of the host entry point, csrc/host_convert.cpp): both the
+    F16C and the scalar path equal numpy's float16 cast bit for bit, subnormals and ties included, and
+    report values that have no finite half."""
+    import ctypes as C
+    from davo_b200 import _capi
+    lib = _capi.load()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(0.32, 15.38, 100003), rng.normal(0, 1e-5, 5000), rng.normal(0, 1e-7, 5000),
+                        [0.0, -0.0, 65504, 65519.9, -65519.9, 6.1e-5, 5.96e-8, 2.98e-8, 2.9802322e-08, 8.9e-8, 1e-30,
+                         2048.5, 2049.5, 1.00048828125, 1.00146484375]]).astype(np.float32)
+    want = x.astype(np.float16).view(np.uint16)
+    for portable in (0, 1):
+        out = np.zeros(x.size, np.uint16)
+        assert lib.davo_debug_flows_to_half(x.ctypes.data, out.ctypes.data, x.size, portable) == 0
+        assert np.array_equal(out, want)
+        for poison in (65520.0, -1e9, np.nan, np.inf):
+            bad = x.copy()
+            bad[777] = poison
+            assert lib.davo_debug_flows_to_half(bad.ctypes.data, out.ctypes.data, bad.size, portable) == 1
