@@ -194,10 +194,11 @@ def test_host_buffer_entry_point_matches_device_entry_point():
 
 
 @pytest.mark.parametrize("key", ["headline", "static", "no_segmask"])
-def test_host_entry_point_streams_chunks_and_trims_copies(key):
+def test_host_entry_point_streams_chunks_and_trims_copies(key, monkeypatch):
     """B=7 through davo_forward_host in 2-sample chunks (copy/compute overlap, two staging
     buffers): same bits as the device entry point; only the planes the graph reads are copied."""
     _need_gpu()
+    monkeypatch.setenv("DAVO_B200_HOST_FLOW16_FRAC", "1")     # explicit: the default depends on the host's thread count
     ver = G.CASES[key]
     w = S.init_weights(ver, random_bias=True)
     inputs = S.make_inputs(7, H, W, seed=23, bad_label_frac=0.01)
@@ -224,6 +225,7 @@ def test_flow_crosses_pcie_as_binary16_with_float32_fallback(monkeypatch):
     the host entry point's CPU conversion gives the device entry point's bits; a chunk holding a value
     with no finite half (|x| >= 65520, NaN) crosses as float32 and still gives the same bits."""
     _need_gpu()
+    monkeypatch.setenv("DAVO_B200_HOST_FLOW16_FRAC", "0.75")  # explicit: the default depends on the host's thread count
     w = S.init_weights(HEADLINE, random_bias=True)
     img, flow, seg = S.make_inputs(5, H, W, seed=31)
     flow = flow.copy()
