@@ -1568,10 +1568,12 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
       if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks_here = std::max(1, atoi(e));
       int nthreads = std::max(2, std::min(16, (int)std::thread::hardware_concurrency() / ranks_here));
       if (const char* e = getenv("DAVO_B200_HOST_THREADS")) nthreads = std::max(1, std::min(atoi(e), 32));
-      // Narrowing the flow only pays when this rank has the cores for it: with 16 threads it is +10 %
-      // on one GPU, with the 4 threads per rank of an 8-GPU box (32 host threads) it costs 35 %
-      // (profiles/r1_experiment_flow16_host_transport.log).  An explicit fraction overrides.
-      if (nthreads < 16 && !getenv("DAVO_B200_HOST_FLOW16_FRAC")) ctx->flow16_frac = 0.0f;
+      // Narrowing the flow only pays when this process has the host's cores and memory system to
+      // itself: with 16 threads it is +10 % on one GPU; with the 4 threads per rank of an 8-GPU box
+      // (32 host threads) it costs 35 % (profiles/r1_e2e_n8_flow_transport.log), and ranks that share
+      // a host share its memory bandwidth too, which the conversion doubles.  So: a single rank with
+      // >= 16 threads, unless an explicit fraction says otherwise.
+      if ((nthreads < 16 || ranks_here > 1) && !getenv("DAVO_B200_HOST_FLOW16_FRAC")) ctx->flow16_frac = 0.0f;
       ctx->pool = new HostPool(nthreads - 1);
     }
     CU_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));

@@ -104,6 +104,12 @@ __device__ __forceinline__ void labels4_at(const FrontParams& p, size_t plane_of
 __device__ __forceinline__ float flow_q(float x) {
   return fabsf(x) < 65520.0f ? __half2float(__float2half_rn(x)) : x;
 }
+// two values at once: one packed f32x2 -> f16x2 conversion; a value that overflowed to infinity (or was
+// not finite to begin with) is passed through, which is the same rule as flow_q
+__device__ __forceinline__ float2 flow_q2(float x, float y) {
+  const float2 q = __half22float2(__floats2half2_rn(x, y));
+  return make_float2(fabsf(q.x) < 65520.0f ? q.x : x, fabsf(q.y) < 65520.0f ? q.y : y);
+}
 // pixel `pix` (x, y) of flow plane k (0: src0 -> tgt, 1: src1 -> tgt; davo.py:978-982) of sample b
 __device__ __forceinline__ float2 flow1_at(const FrontParams& p, int b, int k, int pix, int hw) {
   if (b < p.n_flow16) {
@@ -111,7 +117,7 @@ __device__ __forceinline__ float2 flow1_at(const FrontParams& p, int b, int k, i
     return __half22float2(h);
   }
   const float2 v = __ldg(reinterpret_cast<const float2*>(p.flow + (((size_t)b * 4 + k) * hw + pix) * 2));
-  return make_float2(flow_q(v.x), flow_q(v.y));
+  return flow_q2(v.x, v.y);
 }
 // pixels pix, pix + 1 (pix even): (x0, y0, x1, y1)
 __device__ __forceinline__ float4 flow2_at(const FrontParams& p, int b, int k, int pix, int hw) {
@@ -122,7 +128,8 @@ __device__ __forceinline__ float4 flow2_at(const FrontParams& p, int b, int k, i
     return make_float4(a.x, a.y, c.x, c.y);
   }
   const float4 v = __ldg(reinterpret_cast<const float4*>(p.flow + (((size_t)b * 4 + k) * hw + pix) * 2));
-  return make_float4(flow_q(v.x), flow_q(v.y), flow_q(v.z), flow_q(v.w));
+  const float2 lo = flow_q2(v.x, v.y), hi = flow_q2(v.z, v.w);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 __device__ __forceinline__ float se_in_x(float v, const FrontParams& p) {
