@@ -134,7 +134,10 @@ def parse_version(version: str) -> DavoConfig:
         cfg.in_mode = 0     # pred_info stays None (davo.py:1060)
     # G5 (davo.py:1066-1073)
     if "-seglabelid" in version:
-        raise NotImplementedError("davo_b200: -seglabelid input channel is not built")
+        # The reference's inference graph cannot be built with this token: davo.py:1069-1073 zips the four
+        # pred_info entries with the THREE label maps (or replaces them by the three label maps), and
+        # davo.py:1442 (and :1428/:1434 before it) then reads pred_info[3].  Same exception, same reason.
+        raise IndexError("list index out of range (reference davo.py:1442: -seglabelid leaves pred_info with 3 entries)")
     # G6 SE activation (davo.py:1077-1085)
     if "-fc_tanh" in version:
         cfg.se_act = ACT_TANH

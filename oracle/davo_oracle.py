@@ -364,8 +364,9 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
         pass
     elif "v1" in Version:
         pred_info = pred_flows + [pred_flows[0]]
-    if "-seglabelid" in version:
-        _unsupported("-seglabelid")
+    if "-seglabelid" in version:                                         # davo.py:1066-1073
+        # zip(pred_info (4), pred_seglabels (3)) -> 3 entries; davo.py:1442 then reads pred_info[3]
+        raise IndexError("list index out of range")
     # 3.1 SE activation (davo.py:1077-1085)
     if "-fc_tanh" in version:
         act = "tanh"

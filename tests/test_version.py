@@ -102,3 +102,12 @@ def test_depth_variants_fail_loudly():
     c = V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-norm_depth-fc_tanh")     # davo.py:1211-1219
     assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 1, 1, 1)
     assert V.parse_version(BASE + "-segmask_all-se_depth_to_seg").att_tgt_ones == 0
+
+
+def test_seglabelid_fails_the_way_the_reference_graph_does():
+    """davo.py:1069-1073 leaves pred_info with three entries (zip with the three label maps) and
+    davo.py:1442 reads pred_info[3]: the reference cannot build its inference graph with -seglabelid."""
+    for ver in (BASE + "-seglabelid-segmask_all-se_flow", "v0-sharedNN-dilatedPoseNN-seglabelid", BASE + "-seglabelid-no_segmask"):
+        with pytest.raises(IndexError, match="list index out of range"):
+            V.parse_version(ver)
+
