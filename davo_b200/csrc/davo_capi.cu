@@ -1068,15 +1068,17 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
   if (int rc = launch_front(ctx, pair_mode, pair0, npairs, img, flow, seg, st, launches)) return rc;
   for (size_t li = 0; li < ctx->layers.size(); ++li) {
     Layer& L = ctx->layers[li];
-    if (li == 5 && ctx->cfg.posenn_se == 1) {      // -se_insert: excite cnv5 per branch in front of cnv6
+    const int pse = ctx->cfg.posenn_se;
+    if (li == 5 && (pse == 1 || pse == 3)) {       // -se_insert: excite cnv5 per branch in front of cnv6; -se_replace: instead of it
       Se5Params sp;
-      sp.npairs = npairs; sp.hw = L.Hin * L.Win; sp.nbr = ctx->nbr;
+      sp.npairs = npairs; sp.hw = L.Hin * L.Win; sp.nbr = ctx->nbr; sp.stack = pse == 1;
       sp.cnv5 = ctx->layers[4].d_out; sp.w = ctx->d_se5w; sp.part = ctx->d_se5part; sp.count = ctx->d_se5cnt;
       sp.scale = ctx->d_se5scale; sp.out = ctx->d_se5out;
       if (int rc = launch_k(ctx, se5_excite_kernel, dim3(kSe5Splits, npairs), dim3(256), 0, st, false, sp)) return rc;
       const long long total = (long long)npairs * sp.hw * 64;
       if (int rc = launch_k(ctx, se5_scale_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, false, sp)) return rc;
       *launches += 2;
+      if (pse == 3) continue;                      // cnv6 := se_block(cnv5): there is no cnv6 convolution (posenn.py:234-236)
     }
     int rc = ctx->conv_impl == 0 ? launch_conv(ctx, L, npairs, st) : launch_conv_direct(ctx, L, npairs, st);
     if (rc) return rc;
@@ -1114,8 +1116,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   *out = nullptr;
   if (cfg->posenn < 0 || cfg->posenn > 5)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d unknown (0..5, posenn.py:12-378)", cfg->posenn);
-  if (cfg->posenn_se != 0 && cfg->posenn_se != 1)
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built (only -se_insert)", cfg->posenn_se);
+  if (cfg->posenn_se != 0 && cfg->posenn_se != 1 && cfg->posenn_se != 3)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built (-se_insert and -se_replace are)", cfg->posenn_se);
   if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: H and W must be positive multiples of 8 (got %dx%d)", cfg->H, cfg->W);
   if (cfg->max_batch <= 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: max_batch must be positive");
@@ -1228,13 +1230,16 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   const int groups[7] = {1, 1, 1, 1, 1, c.posenn_se == 1 ? nbr : 1, nbr};
   // -se_insert: cnv6 reads two differently scaled copies of cnv5 (one per branch): a grouped layer
   const bool se5 = c.posenn_se == 1;
+  // -se_replace: cnv6 IS the excited cnv5 (256 channels per branch); cnv7 reads the scaled copies directly
+  const bool rep = c.posenn_se == 3;
+  const int c7in = rep ? 256 : c6;
   // Packed PoseNN input (frontend.cuh: pack_kernel): 8 channels per pixel when the width allows the
   // column-widened cnv1 plan (runs of 16 input pixels), else the 16-channel layout of the plain plan.
   const char* wide_env0 = getenv("DAVO_B200_WIDE");
   ctx->packed_c = (!ctx->unit_sample && (c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
-  const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? nbr * 256 : 256, nbr * c6};
-  const int cin_g[7] = {ctx->packed_c, 16, 32, 64, 128, 256, c6};
-  const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c6};
+  const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? nbr * 256 : 256, nbr * c7in};
+  const int cin_g[7] = {ctx->packed_c, 16, 32, 64, 128, 256, c7in};
+  const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c7in};
   const char* names[7] = {"cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6", "cnv7"};
   ctx->layers.resize(7);
   int H = c.H, W = c.W;
@@ -1327,7 +1332,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   float* prev = ctx->d_packed;
   for (int i = 0; i < 7; ++i) {
     Layer& L = ctx->layers[i];
-    if (i == 5 && se5) {
+    if (i == 5 && (se5 || rep)) {
       const size_t hw5 = (size_t)L.Hin * L.Win;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5part, (size_t)mb * kSe5Splits * 256 * 4)) return rc;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5cnt, (size_t)mb * 4)) return rc;
@@ -1336,6 +1341,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
       prev = ctx->d_se5out;
     }
     L.d_in = prev;
+    if (i == 5 && rep) continue;                   // no cnv6 convolution and no buffer: cnv7 reads d_se5out
     if (i < 6) {
       if (int rc = dev_alloc(ctx, (void**)&L.d_out, (size_t)mb * L.Hout_p * L.Wout_p * L.out_stride * 4)) return rc;
       prev = L.d_out;
@@ -1367,7 +1373,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   const char* brs[2] = {"rotation", "translation"};
   // variable scope of branch g under pose_exp_net/: pose/rotation/, pose/translation/ (decouple) or pose/ (couple)
   auto branch_scope = [&](int g) { return nbr == 2 ? std::string("pose/") + brs[g] + "/" : std::string("pose/"); };
-  {
+  if (!rep) {
     Layer& L = ctx->layers[5];
     const HostTensor *w[2], *b[2];
     for (int g = 0; g < nbr; ++g)
@@ -1387,11 +1393,12 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
       if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
     }
   }
-  if (se5) {
-    // reference nets/posenn.py:227: variables pose/<branch>/cnv5_se_attention/{bottleneck_fc,recover_fc}
+  if (se5 || rep) {
+    // reference nets/posenn.py:227 / :236: variables pose/<branch>/cnv5_se_attention/{bottleneck_fc,recover_fc}
+    // (-se_insert) or pose/<branch>/cnv6_se_attention/... (-se_replace)
     std::vector<float> sw;
     for (int g = 0; g < nbr; ++g) {
-      const std::string S = P + branch_scope(g) + "cnv5_se_attention/";
+      const std::string S = P + branch_scope(g) + (rep ? "cnv6_se_attention/" : "cnv5_se_attention/");
       const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
       const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
       const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
@@ -1410,9 +1417,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     Layer& L = ctx->layers[6];
     const HostTensor *w[2], *b[2];
     for (int g = 0; g < nbr; ++g)
-      if (int rc = need_conv(branch_scope(g) + "cnv7", 3, c6, 256, &w[g], &b[g])) return rc;
+      if (int rc = need_conv(branch_scope(g) + "cnv7", 3, c7in, 256, &w[g], &b[g])) return rc;
     auto getw = [&](int g, int ty, int tx, int ci, int n) {
-      return w[g]->data[(((size_t)ty * 3 + tx) * c6 + ci) * 256 + n];
+      return w[g]->data[(((size_t)ty * 3 + tx) * c7in + ci) * 256 + n];
     };
     std::vector<float> bias(nbr * 256);
     for (int n = 0; n < nbr * 256; ++n) bias[n] = b[n / 256]->data[n % 256];
@@ -1766,6 +1773,7 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
       if (s == ctx->layers[i].name) {
         const Layer& L = ctx->layers[i];
         if (L.pitched_out()) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: %s is stored with a padded pitch", L.name);
+        if (!L.d_out) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: %s is not computed by this variant", L.name);
         n = (int64_t)L.Hout * L.Wout * L.out_stride;
         src = L.d_out + (size_t)pair * n;
       }
@@ -1828,6 +1836,7 @@ extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int*
   if (int rc = timed([&] { return launch_front(ctx, ctx->unit_sample ? kUnitsAreSamples : 0, 0, npairs, ctx->last_img, ctx->last_flow, ctx->last_seg, st, &dummy); }, &ms_out[0])) return rc;
   for (int i = 0; i < 7; ++i) {
     const Layer& L = ctx->layers[i];
+    if (i == 5 && ctx->cfg.posenn_se == 3) { ms_out[1 + i] = 0.f; continue; }      // -se_replace has no cnv6 convolution
     if (int rc = timed([&] { return launch_conv(ctx, L, npairs, st); }, &ms_out[1 + i])) return rc;
   }
   if (int rc = timed([&] { return launch_head(ctx, ctx->unit_sample ? kUnitsAreSamples : 0, 0, npairs, ctx->last_pose, st, &dummy); }, &ms_out[8])) return rc;
@@ -1972,16 +1981,17 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
     const Layer& L6 = ctx->layers[5];
     ResizeParams rp;
     rp.B = B; rp.H = c.H; rp.W = c.W;
-    rp.h = L6.Hout; rp.w = L6.Wout; rp.hp = L6.Hout_p; rp.wp = L6.Wout_p;
-    rp.C = c.cnv6_out; rp.cstride = L6.out_stride;
+    const bool rep = c.posenn_se == 3;             // -se_replace: "cnv6" is the excited cnv5, 256 channels per branch
+    rp.h = rep ? L6.Hin : L6.Hout; rp.w = rep ? L6.Win : L6.Wout; rp.hp = rep ? L6.Hin : L6.Hout_p; rp.wp = rep ? L6.Win : L6.Wout_p;
+    rp.C = rep ? 256 : c.cnv6_out; rp.cstride = rep ? ctx->nbr * 256 : L6.out_stride;
     rp.unit_mul = ctx->unit_sample ? 1 : 2; rp.unit_add = ctx->unit_sample ? 0 : 1;
-    rp.src = L6.d_out;
-    const size_t total = (size_t)B * c.H * c.W * (c.cnv6_out / 4);
+    rp.src = rep ? ctx->d_se5out : L6.d_out;
+    const size_t total = (size_t)B * c.H * c.W * (rp.C / 4);
     const int blocks = (int)std::min<size_t>((size_t)ctx->num_sms * 8, (total + 255) / 256);
     float* dsts[2] = {out->cnv6_rot, out->cnv6_trans};
     for (int br = 0; br < 2; ++br) {
       if (!dsts[br]) continue;
-      rp.coff = (ctx->nbr == 2 && br == 1) ? c.cnv6_out : 0;      // couple nets return (cnv6, cnv6), posenn.py:66, 187, 311
+      rp.coff = (ctx->nbr == 2 && br == 1) ? rp.C : 0;            // couple nets return (cnv6, cnv6), posenn.py:66, 187, 311
       rp.dst = dsts[br];
       resize_bilinear_kernel<<<blocks, 256, 0, st>>>(rp);
       CU_OK(cudaGetLastError());

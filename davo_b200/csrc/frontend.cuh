@@ -658,11 +658,14 @@ constexpr int kSe5Splits = 32;
 struct Se5Params {
   int npairs, hw;               // pixels of the cnv5 map
   int nbr;                      // branches (2: rotation then translation; 1: couple nets)
+  int stack;                    // 1: -se_insert, where cnv5 is RE-ASSIGNED in the branch loop (posenn.py:227), so the
+                                //    second branch's block sees and scales the first one's output;
+                                // 0: -se_replace (posenn.py:234-236): every branch excites the original cnv5
   const float* cnv5;            // [mb][hw][256]
   const float* w;               // per branch: W1[256][32] b1[32] W2[32][256] b2[256]
   float* part;                  // [mb][kSe5Splits][256]
   unsigned int* count;          // [mb]
-  float* scale;                 // [mb][nbr][256]: exc_r, exc_r * exc_t
+  float* scale;                 // [mb][nbr][256]: exc_r, exc_r * exc_t (stack) or exc_r, exc_t
   float* out;                   // [mb][hw][nbr*256]: cnv5 * scale[0] | cnv5 * scale[1], TF32-rounded
 };
 constexpr int kSe5BranchFloats = 256 * 32 + 32 + 32 * 256 + 256;
@@ -699,7 +702,7 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
     const float* b1 = W1 + 256 * 32;
     const float* W2 = b1 + 32;                           // [32][256]
     const float* b2 = W2 + 32 * 256;
-    s_mean[c] = m * scale;                               // mean of what this branch's block sees
+    s_mean[c] = m * (p.stack ? scale : 1.0f);            // mean of what this branch's block sees
     __syncthreads();
     if (c < 32) {
       float h = b1[c];
@@ -709,7 +712,8 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
     __syncthreads();
     float e = b2[c];
     for (int j = 0; j < 32; ++j) e += s_hid[j] * W2[j * 256 + c];
-    scale *= 1.0f / (1.0f + expf(-e));
+    const float exc = 1.0f / (1.0f + expf(-e));
+    scale = p.stack ? scale * exc : exc;
     p.scale[((size_t)pl * p.nbr + br) * 256 + c] = scale;
     __syncthreads();
   }

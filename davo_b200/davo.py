@@ -222,6 +222,8 @@ class DAVO(object):
             device=dev, dtype=dt).contiguous()
         img, flow, seg, depth = up(img, torch.uint8), up(flow, torch.float32), up(seg, torch.float32), up(depth, torch.float32)
         H, W, c6 = self.img_height, self.img_width, self.config.cnv6_out
+        if self.config.posenn_se == V.PSE_REPLACE:
+            c6 = 256                                     # "cnv6" is se_block(cnv5) there (reference posenn.py:234-236)
         f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
         u8 = lambda *shape: torch.empty(shape, dtype=torch.uint8, device=dev)
         pose = f32(B, 2, 6)

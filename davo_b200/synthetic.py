@@ -81,15 +81,16 @@ def conv_specs(cfg: V.DavoConfig):
     nsrc = 1 if shared else 2                            # num_source of one evaluation
     cin = (5 if cfg.in_mode == 1 else 3) * (1 + nsrc)    # (rgb [+ flow]) x (tgt + sources)
     c6 = cfg.cnv6_out
+    rep = cfg.posenn_se == V.PSE_REPLACE                 # cnv6 := se_block(cnv5): no cnv6 variables, cnv7 reads 256 channels
     specs = [("cnv1", (7, 7, cin, 16)), ("cnv2", (5, 5, 16, 32)), ("cnv3", (3, 3, 32, 64)),
              ("cnv4", (3, 3, 64, 128)), ("cnv5", (3, 3, 128, 256))]
     if cfg.posenn in (V.POSENN_COUPLE_SHARED_DIL, V.POSENN_COUPLE_DIL, V.POSENN_COUPLE):
-        return specs + [("pose/cnv6", (3, 3, 256, c6)), ("pose/cnv7", (3, 3, c6, 256)),
-                        ("pose/pred", (1, 1, 256, 6 * nsrc))]
+        return specs + ([] if rep else [("pose/cnv6", (3, 3, 256, c6))]) + [
+            ("pose/cnv7", (3, 3, 256 if rep else c6, 256)), ("pose/pred", (1, 1, 256, 6 * nsrc))]
     for br in ("rotation", "translation"):
-        specs += [("pose/%s/cnv6" % br, (3, 3, 256, c6)),
-                  ("pose/%s/cnv7" % br, (3, 3, c6, 256)),
-                  ("pose/%s/pred" % br, (1, 1, 256, 3 * nsrc))]
+        specs += ([] if rep else [("pose/%s/cnv6" % br, (3, 3, 256, c6))]) + [
+            ("pose/%s/cnv7" % br, (3, 3, 256 if rep else c6, 256)),
+            ("pose/%s/pred" % br, (1, 1, 256, 3 * nsrc))]
     return specs
 
 
@@ -132,11 +133,11 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         # double scope is the reference's: prefix "pose_exp_net/" inside scope pose_exp_net
         w["pose_exp_net/pose_exp_net/seg_channel_weight/weight"] = \
             rng.normal(0.0, 0.05, size=(19,)).astype(np.float32)
-    if cfg.posenn_se == V.PSE_INSERT:
+    if cfg.posenn_se in (V.PSE_INSERT, V.PSE_REPLACE):
         for br in (("rotation/", "translation/") if cfg.posenn in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_DECOUPLE_DIL,
                                                                V.POSENN_DECOUPLE)
                    else ("",)):
-            sc = "pose_exp_net/pose/%scnv5_se_attention" % br
+            sc = "pose_exp_net/pose/%s%s_se_attention" % (br, "cnv5" if cfg.posenn_se == V.PSE_INSERT else "cnv6")
             for name, (fi, fo) in (("bottleneck_fc", (256, 32)), ("recover_fc", (32, 256))):
                 std = math.sqrt(1.3 * 2.0 / fi)
                 w["%s/%s/kernel" % (sc, name)] = _trunc_normal(rng, (fi, fo), std)

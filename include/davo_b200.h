@@ -55,7 +55,7 @@ typedef struct davo_config {
   int32_t se_act;        /* 0 relu, 1 tanh, 2 leaky_relu(0.2), davo.py:1077-1085       */
   int32_t flow_abs;      /* 0 none, 1 both, 2 h, 3 v, davo.py:1094-1102                */
   int32_t flow_norm;     /* "-norm_flow", davo.py:1088-1091                            */
-  int32_t posenn_se;     /* 0 none, 1 insert, 2 skipadd, 3 replace, davo.py:1010-1017  */
+  int32_t posenn_se;     /* 0 none, 1 insert, 3 replace (2 skipadd: not built), davo.py:1010-1017, posenn.py:225-236 */
   int32_t micro_batch;   /* units (frame pairs; samples for posenn 2-5) per pass of the conv stack; 0 = 256 */
   int32_t depth_norm;    /* "-norm_depth": SE depth input / 80, davo.py:1108-1111       */
   int32_t se_pool;       /* se_flow only: 0 global mean, 1 gp2x2 (four quadrant means), davo.py:1181-1192 */

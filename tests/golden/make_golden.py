@@ -38,6 +38,8 @@ CASES = {
     "plain_decouple_net": "v1-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh",
     "plain_couple_net": "v1-couplePoseNN-cnv6_64-segmask_all-static",
     "segflow_to_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_SegFlow_to_seg-norm_flow-abs_flow-fc_tanh",
+    "se_replace": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh-se_replace",
+    "couple_net_se_replace": "v1-dilatedCouplePoseNN-cnv6_64-no_segmask-se_replace",
     "segflow_8_wo_tgt": "v0-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_SegFlow_to_seg_8_wo_tgt-fc_lrelu",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)

@@ -362,6 +362,8 @@ def test_pair_selection_computes_what_the_trajectory_reads(host):
     ("se_insert", 128, 416, 3, 2),           # passes of 2 pairs: the excitation buffers across ragged passes
     ("se_seg", 128, 416, 5, 4),              # target map computed: all three label planes cross as bytes on the host path
     ("couple_net_v0", 128, 416, 3, 2),       # sample units, passes of 2 samples
+    ("se_replace", 128, 416, 3, 2),          # no cnv6 convolution: cnv7 reads the two excited copies of cnv5, ragged passes
+    ("couple_net_se_replace", 136, 424, 2, 0),   # sample units, one branch, odd-sized maps
     ("segflow_to_seg", 128, 416, 5, 4),      # 21-wide pooled vector on all three frames; the target's constant SE flow
     ("segflow_8_wo_tgt", 64, 208, 3, 0),     # v0 input: the flow is read by the SE only and must still cross on the host path
 ])
@@ -519,7 +521,7 @@ def test_allgather_without_communicator_is_a_copy():
 
 
 @pytest.mark.parametrize("key", ["headline", "se_seg", "static", "couple_shared", "se_insert", "decouple_net",
-                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt", "segflow_to_seg"])
+                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt", "segflow_to_seg", "se_replace"])
 def test_feature_mode_matches_oracle(key):
     """DAVO.inference(mode='feature') (davo.py:1553-1564) through davo_forward_features: every fetched tensor
     against the oracle.  Labels and colourings are byte-exact (flow colours: the atan2 of the two
@@ -546,7 +548,7 @@ def test_feature_mode_matches_oracle(key):
     for k in range(2):
         d = np.abs(got["flows"][k].astype(int) - want["flows"][k].astype(int))
         assert got["flows"][k].dtype == np.uint8 and (d != 0).mean() < 1e-3 and np.percentile(d, 99.99) <= 1, (d != 0).mean()
-    c6 = sysm.config.cnv6_out
+    c6 = 256 if key == "se_replace" else sysm.config.cnv6_out     # -se_replace: cnv6 is the excited cnv5
     for name in ("rot", "trans"):
         assert got["features"][name].shape == (g["batch"], H, W, c6)
         assert _rel(got["features"][name], want["features"][name]) < 1.5e-3, name
