@@ -79,7 +79,11 @@ int davo_finalize_weights(davo_ctx*);
 /* Stands in for DAVO.inference(sess, mode='pose') = one sess.run of pred_poses
  * (reference davo.py:1553-1569) on B <= max_batch samples.
  *   img_u8   device, uint8  [B, H, 3W, 3]   (src0 | tgt | src1 along width)
- *   flow     device, float  [B, 4, H, W, 2] (only [:,0:2] are read, davo.py:978-982)
+ *   flow     device, float  [B, 4, H, W, 2] (only [:,0:2] are read, davo.py:978-982).  Numerics: every
+ *            flow value is rounded to IEEE binary16 when it is read (11 significant bits, the
+ *            precision the TF32 convolution operands keep anyway; values with no finite half,
+ *            |x| >= 65520 or NaN, are used as they are), on this and on the host entry point alike,
+ *            so that the host entry point may move the flow as binary16 with identical results
  *   seg      device, float  [B, 3, H, W, 1] ([src0, tgt, src1], davo.py:1000-1004)
  *   depth    device, float  [B, 3, H, W, 1] ([src0, tgt, src1], davo.py:991-996): read by the
  *            se_depth variants only (att_src 5); NULL otherwise
@@ -130,8 +134,12 @@ int davo_forward_features(davo_ctx*, int B, const uint8_t* img_u8, const float* 
  * form of `sess.run` with fed numpy arrays (reference davo.py:1568).  The batch is
  * streamed in micro-batch chunks, the host->device copy of chunk i+1 overlapping
  * the compute of chunk i; only the planes the graph reads are copied (flow[:,0:2],
- * and seg[:,{0,2}] when the target map is ones).  Poses are copied back and the
- * stream synchronised before returning. */
+ * and seg[:,{0,2}] when the target map is ones), the labels as bytes and -- on a host with
+ * >= 16 hardware threads that this process does not share with other ranks -- three quarters of
+ * the flow as binary16, both narrowed by a small CPU thread pool inside the call
+ * (DAVO_B200_HOST_SEG8 / _FLOW16 / _FLOW16_FRAC / _THREADS override).  Results are bit-identical
+ * to the device entry point either way.  Poses are copied back and the stream synchronised
+ * before returning. */
 int davo_forward_host(davo_ctx*, int B, const uint8_t* img_u8, const float* flow,
                       const float* seg, const float* depth, float* pose_out,
                       void* cuda_stream);
