@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
       const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
       const int beg = blockIdx.x * per, end = min(beg + per, n4);
       if (f != 1 && !p.pool_2x2)                      // the target's flow is all zeros (davo.py:979)
+#pragma unroll 4                                      // four loads in flight per thread; the sums keep their order
         for (int i = beg + threadIdx.x; i < end; i += 256) {
           const float4 v = flow2_at(p, b, fk, 2 * i, hw);
           s0 += se_in_x(v.x, p) + se_in_x(v.z, p);
