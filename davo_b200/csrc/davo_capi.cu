@@ -1014,6 +1014,15 @@ __global__ void sum7_direct_kernel(const float* in, int hw, int nparts, float* o
   for (int i = 1; i < nparts; ++i) o[(size_t)i * 256] = 0.f;
 }
 
+// Blocks per frame pair of pack8_kernel (a block covers 1024 pixels per iteration; 52 cover the frame in one).
+// A full pass runs best with 13 blocks x 4 iterations (the per-block prologue is paid once per 4096 pixels:
+// front end 0.168 -> 0.161 ms per 256 pairs, tools/front_probe.py); small passes need the blocks to fill the GPU.
+int pack8_blocks(int npairs) {
+  static const int forced = [] { const char* e = getenv("DAVO_B200_PACK8_BLOCKS"); return e ? std::max(1, atoi(e)) : 0; }();
+  if (forced) return forced;
+  return npairs >= 64 ? kPack8Blocks / 4 : kPack8Blocks;
+}
+
 int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint8_t* img, const float* flow,
                  const float* seg, cudaStream_t st, int* launches) {
   const davo_config& c = ctx->cfg;
@@ -1044,7 +1053,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     ++*launches;
   }
   if (int rc = ctx->unit_sample ? launch_k(ctx, pack_sample_kernel, dim3(kPackBlocksPerPair, npairs), dim3(256), 0, st, false, fp)
-             : ctx->packed_c == 8 ? launch_k(ctx, pack8_kernel, dim3(kPack8Blocks, npairs), dim3(256), 0, st, false, fp)
+             : ctx->packed_c == 8 ? launch_k(ctx, pack8_kernel, dim3(pack8_blocks(npairs), npairs), dim3(256), 0, st, false, fp)
                                   : launch_k(ctx, pack_kernel, dim3(kPackBlocksPerPair, npairs), dim3(256), 0, st, false, fp))
     return rc;
   ++*launches;

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
 }
 
 // 8-channel packed layout (FrontParams::packed_c == 8; W % 16 == 0): [tgt r g b, src r g b (x A),
-// src flow x y (x A)], every value TF32-rounded.  grid (kPack8Blocks, npairs), 256 threads, one
+// src flow x y (x A)], every value TF32-rounded.  grid (kPack8Blocks or a quarter of it, npairs), 256 threads, one
 // thread per 4 consecutive pixels of a row: the 12 image bytes of a frame are three 32-bit
 // loads, labels and flow are float4 loads.  A thread's 8 float4 (128 B) go through a per-warp
 // XOR-swizzled staging buffer so that every store instruction of the warp writes 512
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 8);
   const int src_col0 = (k == 0) ? 0 : 2 * p.W;
   float4* st = s_stage[warp];
-  for (int base = blockIdx.x * 256; base < groups; base += kPack8Blocks * 256) {
+  for (int base = blockIdx.x * 256; base < groups; base += gridDim.x * 256) {
     const int gi = base + threadIdx.x;
     float4 q[8];
     if (gi < groups) {
