@@ -58,6 +58,8 @@ struct FrontParams {
   int depth_norm;        // "-norm_depth": SE depth input / 80
   int pool_2x2;          // se_flow only: mode='gp2x2' (attention_module.py:68-78): the means of the four
                          // quadrants [:h/2,:w/2], [:h/2,w/2:], [h/2:,:w/2], [h/2:,w/2:] concatenated -> 8 inputs
+  int spp_levels;        // se_flow only: mode='spp' (attention_module.py:79-86, 137-167): pyramid levels ...
+  int spp_n[3];          // ... and their out_pool_size; se_spp_kernel replaces se_pool_kernel
   int se_in, se_hid;     // SE dense sizes: in -> hid -> 19 (flow 2,8; seg 19,19; rgb 3,8)
   int att_tgt_ones;
   int mask_rgb, mask_flow;
@@ -334,6 +336,72 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   const float* b1 = W1 + D * Hd;               // [Hd]
   const float* W2 = b1 + Hd;                   // [Hd][19]
   const float* b2 = W2 + Hd * kNumClasses;     // [19]
+  if (threadIdx.x < Hd) {
+    float a = b1[threadIdx.x];
+    for (int i = 0; i < D; ++i) a += s_pool[i] * W1[i * Hd + threadIdx.x];
+    s_fc1[threadIdx.x] = se_activation(a, p.se_act);
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumClasses) {
+    const int c = threadIdx.x;
+    float a = b2[c];
+    for (int j = 0; j < Hd; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
+    p.att_w[((size_t)pl * kAttFrames + fr) * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
+// se(flow, "se_flow", [8,19], mode='spp', spp_size) (davo.py:1193-1210): spatial_pyramid_pool
+// (attention_module.py:137-167) as TensorFlow evaluates it.  Per level n: h_size = ceil(H/n), w_size =
+// ceil(W/n); the SE flow is zero-padded (bottom / right) to n*h_size x n*w_size, then avg_pool with a window of
+// h_size x H_SIZE -- the reference passes h_size for both sides (:158) -- at strides (h_size, w_size), 'SAME'.
+// For H <= W the window is narrower than the stride, 'SAME' pads nothing, and cell (i, j) is the mean over
+// rows [i*h_size, (i+1)*h_size) x columns [j*w_size, j*w_size + h_size) with the tf.pad zeros counted: only the
+// left part of each cell is read.  Pooled vector: levels concatenated, cells row-major, (x, y) last.
+// grid (npairs, source frames), 256 threads: a warp per cell, then the two dense layers -> att_w.
+constexpr int kSppMaxDim = 232;                          // (64 + 36 + 16) cells x 2
+__global__ void __launch_bounds__(256) se_spp_kernel(const FrontParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int pl = blockIdx.x, fr = blockIdx.y;
+  int b, k;
+  pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
+  const int hw = p.H * p.W;
+  const int f = unit_frame(p.unit_sample, k, fr);
+  const int fk = f == 2 ? 1 : 0;                        // flow plane of this frame (never the target here)
+  __shared__ float s_pool[kSppMaxDim];
+  __shared__ float s_fc1[kPoolDim];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int cell0 = 0;
+  for (int lv = 0; lv < p.spp_levels; ++lv) {
+    const int n = p.spp_n[lv];
+    const int hs = (p.H + n - 1) / n, ws = (p.W + n - 1) / n;
+    const float inv = 1.0f / (float)(hs * hs);
+    for (int cell = warp; cell < n * n; cell += 8) {
+      const int y0 = (cell / n) * hs, x0 = (cell % n) * ws;
+      float sx = 0.f, sy = 0.f;
+      for (int i = lane; i < hs * hs; i += 32) {
+        const int y = y0 + i / hs, x = x0 + i % hs;
+        if (y < p.H && x < p.W) {                       // beyond the map: tf.pad zeros
+          const float2 v = flow1_at(p, b, fk, y * p.W + x, hw);
+          sx += se_in_x(v.x, p);
+          sy += se_in_y(v.y, p);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      }
+      if (lane == 0) { s_pool[(cell0 + cell) * 2] = sx * inv; s_pool[(cell0 + cell) * 2 + 1] = sy * inv; }
+    }
+    cell0 += n * n;
+  }
+  __syncthreads();
+  const int D = cell0 * 2, Hd = p.se_hid;
+  const float* W1 = p.se_w;                    // [D][Hd]
+  const float* b1 = W1 + D * Hd;
+  const float* W2 = b1 + Hd;                   // [Hd][19]
+  const float* b2 = W2 + Hd * kNumClasses;
   if (threadIdx.x < Hd) {
     float a = b1[threadIdx.x];
     for (int i = 0; i < D; ++i) a += s_pool[i] * W1[i * Hd + threadIdx.x];

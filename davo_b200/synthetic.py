@@ -123,6 +123,8 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         scope, din, dh = se_scopes[cfg.att_src]
         if cfg.se_pool == 1:
             din *= 4                                     # gp2x2: four quadrant means concatenated
+        elif cfg.se_pool in V.SPP_SIZES:
+            din *= sum(n * n for n in V.SPP_SIZES[cfg.se_pool])   # one mean per pyramid cell
         if cfg.se_hidden:
             dh = cfg.se_hidden
         for name, (fi, fo) in (("bottleneck_fc", (din, dh)), ("recover_fc", (dh, 19))):

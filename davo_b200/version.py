@@ -27,6 +27,10 @@ MASK_OFF, MASK_RGB, MASK_ALL, MASK_ALL_555 = 0, 1, 2, 3
 ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2
 ABS_NONE, ABS_BOTH, ABS_H, ABS_V = 0, 1, 2, 3
 PSE_NONE, PSE_INSERT, PSE_SKIPADD, PSE_REPLACE = 0, 1, 2, 3
+# SE pooling of the flow sources (nets/attention_module.py:64-86): global mean, 2x2 quadrants, or the
+# spatial pyramid with out_pool_size [2,1] / [2] / [8,6,4]
+SE_POOL_GP, SE_POOL_GP2X2, SE_POOL_SPP21, SE_POOL_SPP2, SE_POOL_SPP864 = 0, 1, 2, 3, 4
+SPP_SIZES = {SE_POOL_SPP21: (2, 1), SE_POOL_SPP2: (2,), SE_POOL_SPP864: (8, 6, 4)}
 
 # Attention sources of the reference chain that this build does not implement
 # (davo.py:1117-1383), in the reference's evaluation order.
@@ -35,8 +39,7 @@ _UNBUILT_SOURCES = (
     "-se_flow_on_depthseg", "-se_mixDepthFlow", "-se_mixDispFlow",
 )
 _UNBUILT_AFTER_SE_FLOW = (
-    "-se_spp21_flow", "-se_spp2_flow",
-    "-se_spp_flow", "-se_spp864_flow", "-se_depth_wo_tgt_to_seg", "-se_depth_to_seg",
+    "-se_depth_wo_tgt_to_seg", "-se_depth_to_seg",
     "-se_depth_wo_tgt", "-se_depth", "-se_disp_wo_tgt_to_seg", "-se_disp_to_seg",
     "-se_disp_wo_tgt", "-se_disp", "-se_rgb_wo_tgt_to_seg", "-se_rgb_to_seg",
     "-se_rgb_wo_tgt", "-se_rgb", "-se_seg_wo_tgt", "-se_seg", "-se_gp2x2_seg",
@@ -79,7 +82,7 @@ class DavoConfig:
     flow_norm: int = 0
     posenn_se: int = PSE_NONE
     depth_norm: int = 0         # "-norm_depth" (davo.py:1108-1111); only read by the se_depth sources
-    se_pool: int = 0            # se_flow: 0 = global mean, 1 = gp2x2 (davo.py:1181-1192)
+    se_pool: int = 0            # se_flow: SE_POOL_* (davo.py:1175-1210)
     se_hidden: int = 0          # SE bottleneck width, 0 = default (8; se_seg 19); gp2x2_flow_nobottle: 19
     needs_depth: int = 0        # "depth"/"disp" in the version: the graph reads input_depth (davo.py:960)
     version_tag: str = "v0"
@@ -168,6 +171,13 @@ def parse_version(version: str) -> DavoConfig:
         cfg.att_tgt_ones = 1
         cfg.se_pool = 1
         cfg.se_hidden = 19 if "-se_gp2x2_flow_nobottle" in version else 8
+    elif re.search("-se_spp(21|2|864|)_flow", version):                          # davo.py:1193-1210
+        # se(flow, "se_flow", [8,19], mode='spp', spp_size): spatial_pyramid_pool of the SE flow; the variables
+        # live under pose_exp_net/se_flow, so the target map is forced to ones as for -se_flow
+        cfg.att_src = ATT_SE_FLOW
+        cfg.att_tgt_ones = 1
+        cfg.se_pool = (SE_POOL_SPP21 if "-se_spp21_flow" in version else
+                       SE_POOL_SPP2 if "-se_spp2_flow" in version else SE_POOL_SPP864)
     else:
         chain_hit = None
         for tok in _UNBUILT_AFTER_SE_FLOW:                      # reference order: first match wins

@@ -89,8 +89,31 @@ def _act(name: str):
     return torch.relu
 
 
+def spatial_pyramid_pool(x_nhwc: torch.Tensor, out_pool_size) -> torch.Tensor:
+    """nets/attention_module.py:137-167 as TensorFlow evaluates it -> [B, sum(n*n) * C].
+
+    Per level n: h_size = ceil(H/n), w_size = ceil(W/n); the map is zero-padded at the bottom / right to
+    n*h_size x n*w_size (tf.pad: the zeros count as data); then ``avg_pool`` with
+    ``ksize=[1, h_size, h_size, 1]`` -- the reference passes h_size for BOTH window sides (:158) -- and
+    strides (h_size, w_size), padding 'SAME'.  For H <= W the window is narrower than the stride, so
+    'SAME' adds no padding of its own and output cell (i, j) is the plain mean over rows
+    [i*h_size, (i+1)*h_size) and columns [j*w_size, j*w_size + h_size): only the left part of every
+    cell is looked at.  Cells are flattened row-major with the channel last (:163-165), levels concatenated.
+    """
+    B, H, W, C = x_nhwc.shape
+    if H > W:
+        _unsupported("spatial_pyramid_pool on a portrait map (SAME padding of the square window)")
+    out = []
+    for n in out_pool_size:
+        hs, ws = math.ceil(H / n), math.ceil(W / n)
+        xp = torch.nn.functional.pad(x_nhwc, (0, 0, 0, n * ws - W, 0, n * hs - H))
+        cells = [xp[:, i * hs:(i + 1) * hs, j * ws:j * ws + hs].mean(dim=(1, 2)) for i in range(n) for j in range(n)]
+        out.append(torch.stack(cells, dim=1).reshape(B, n * n * C))
+    return torch.cat(out, dim=1)
+
+
 def se_weights(x_nhwc: torch.Tensor, wts: Dict[str, torch.Tensor], scope: str,
-               activation: str, mode: str = "gp") -> torch.Tensor:
+               activation: str, mode: str = "gp", spp_size=(8, 6, 4)) -> torch.Tensor:
     """``se(input, name, layer_channels, mode='gp', activation)`` -> [B, units2].
 
     nets/attention_module.py:54-103: global average pool (:66), dense +
@@ -101,6 +124,8 @@ def se_weights(x_nhwc: torch.Tensor, wts: Dict[str, torch.Tensor], scope: str,
         h, w = x_nhwc.shape[1] // 2, x_nhwc.shape[2] // 2
         pool = torch.cat([x_nhwc[:, :h, :w].mean(dim=(1, 2)), x_nhwc[:, :h, w:].mean(dim=(1, 2)),
                           x_nhwc[:, h:, :w].mean(dim=(1, 2)), x_nhwc[:, h:, w:].mean(dim=(1, 2))], dim=-1)
+    elif mode == "spp":                                                  # :79-86
+        pool = spatial_pyramid_pool(x_nhwc, spp_size)
     else:
         pool = x_nhwc.mean(dim=(1, 2))                                   # :66
     fc1 = _act(activation)(pool @ wts[scope + "/bottleneck_fc/kernel"]
@@ -400,6 +425,14 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
         att, att_w = [], []
         for i in range(3):
             w19 = se_weights(se_in[i], wts, "pose_exp_net/se_flow", act, mode="gp2x2")
+            att_w.append(w19)
+            att.append(class_gather(pred_segs[i], w19))
+        use_se_flow = True                               # variables under pose_exp_net/se_flow (davo.py:1404)
+    elif re.search("-se_spp(21|2|864|)_flow", version):                  # davo.py:1193-1210, first match wins
+        sizes = (2, 1) if "-se_spp21_flow" in version else (2,) if "-se_spp2_flow" in version else (8, 6, 4)
+        att, att_w = [], []
+        for i in range(3):
+            w19 = se_weights(se_in[i], wts, "pose_exp_net/se_flow", act, mode="spp", spp_size=sizes)
             att_w.append(w19)
             att.append(class_gather(pred_segs[i], w19))
         use_se_flow = True                               # variables under pose_exp_net/se_flow (davo.py:1404)

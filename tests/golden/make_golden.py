@@ -40,6 +40,8 @@ CASES = {
     "segflow_to_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_SegFlow_to_seg-norm_flow-abs_flow-fc_tanh",
     "se_replace": "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh-se_replace",
     "couple_net_se_replace": "v1-dilatedCouplePoseNN-cnv6_64-no_segmask-se_replace",
+    "spp864_flow": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_spp_flow-abs_flow-fc_tanh",
+    "spp21_flow_net": "v1-dilatedPoseNN-cnv6_128-segmask_rgb-se_spp21_flow-norm_flow-fc_lrelu",
     "segflow_8_wo_tgt": "v0-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_SegFlow_to_seg_8_wo_tgt-fc_lrelu",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)

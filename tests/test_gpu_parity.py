@@ -72,7 +72,8 @@ def test_variants_match_oracle_and_golden(key):
         sample_units = sysm.config.posenn >= 2          # non-shared nets: one evaluation (unit) per sample
         for p in range(2 if sample_units else 4):
             want = GOLD[key + "/att_w"][p, 0] if sample_units else GOLD[key + "/att_w"][p // 2, p % 2]
-            np.testing.assert_allclose(sysm.get_intermediate("att_weights", p), want, rtol=3e-5, atol=1e-7)   # SE flow input is read as binary16
+            # the SE flow input is read as binary16; pyramid cells average as few as 256 pixels of it
+            np.testing.assert_allclose(sysm.get_intermediate("att_weights", p), want, rtol=1e-4 if "spp" in key else 3e-5, atol=1e-7)
     if sysm.config.att_src == 5:                                             # host-buffer entry point with depth
         assert np.array_equal(out, sysm.inference(None, "pose", inputs=inputs + (depth,))["pose"])
         with pytest.raises(ValueError):
@@ -364,6 +365,8 @@ def test_pair_selection_computes_what_the_trajectory_reads(host):
     ("couple_net_v0", 128, 416, 3, 2),       # sample units, passes of 2 samples
     ("se_replace", 128, 416, 3, 2),          # no cnv6 convolution: cnv7 reads the two excited copies of cnv5, ragged passes
     ("couple_net_se_replace", 136, 424, 2, 0),   # sample units, one branch, odd-sized maps
+    ("spp864_flow", 136, 424, 3, 4),         # pyramid cells that do not divide the map (tf.pad zeros counted), ragged passes, host entry
+    ("spp21_flow_net", 64, 208, 2, 0),       # sample units: both source frames pooled in one launch
     ("segflow_to_seg", 128, 416, 5, 4),      # 21-wide pooled vector on all three frames; the target's constant SE flow
     ("segflow_8_wo_tgt", 64, 208, 3, 0),     # v0 input: the flow is read by the SE only and must still cross on the host path
 ])

@@ -175,6 +175,25 @@ def test_colour_helpers_match_the_reference_sources():
         assert np.array_equal(O.flow_to_uint8_image(np.array(c["flow"], np.float32)), np.array(c["image"], np.uint8))
 
 
+def test_spatial_pyramid_pool_reads_the_left_square_of_every_cell():
+    """nets/attention_module.py:137-167 with its ksize=[1,h_size,h_size,1] (:158): on a landscape map the window
+    is h_size wide at a stride of w_size, zeros of tf.pad included; cells row-major, channel last."""
+    H, W = 6, 20
+    x = torch.arange(H * W * 2, dtype=torch.float64).reshape(1, H, W, 2)
+    got = O.spatial_pyramid_pool(x, (2, 1))
+    assert got.shape == (1, (4 + 1) * 2)
+    hs, ws = 3, 10                                             # level 2
+    want = [x[0, i * hs:(i + 1) * hs, j * ws:j * ws + hs].mean(dim=(0, 1)) for i in range(2) for j in range(2)]
+    want.append(x[0, :6, :6].mean(dim=(0, 1)))                 # level 1: a 6 x 6 window out of 6 x 20
+    assert torch.allclose(got[0], torch.cat(want))
+    # a map that does not divide: H = 7 at level 2 -> h_size 4, one padded zero row counted in the lower cells
+    y = torch.ones(1, 7, 20, 1, dtype=torch.float64)
+    g = O.spatial_pyramid_pool(y, (2,))[0]
+    assert torch.allclose(g, torch.tensor([1.0, 1.0, 0.75, 0.75], dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        O.spatial_pyramid_pool(torch.ones(1, 20, 6, 1), (2,))
+
+
 def test_resize_bilinear_tf1_rule():
     """TF 1.x resize_bilinear (align_corners=False): source = index * in/out, no half-pixel shift."""
     x = np.arange(2 * 3, dtype=np.float64).reshape(1, 2, 3, 1)

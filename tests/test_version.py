@@ -40,6 +40,15 @@ def test_segflow_bottleneck_width_follows_the_token():
         assert V.parse_version(BASE + "-segmask_all" + tok).se_hidden == hid
 
 
+def test_pyramid_pooling_tokens():
+    """se(flow, "se_flow", [8,19], mode='spp', spp_size=...) (davo.py:1193-1210): first match wins; the variables
+    live under pose_exp_net/se_flow, so the target map is ones as for -se_flow (davo.py:1404-1412)."""
+    for tok, pool in (("-se_spp21_flow", V.SE_POOL_SPP21), ("-se_spp2_flow", V.SE_POOL_SPP2),
+                      ("-se_spp_flow", V.SE_POOL_SPP864), ("-se_spp864_flow", V.SE_POOL_SPP864)):
+        c = V.parse_version(BASE + "-segmask_all" + tok)
+        assert (c.att_src, c.att_tgt_ones, c.se_pool) == (V.ATT_SE_FLOW, 1, pool), tok
+
+
 def test_order_sensitive_tokens():
     assert V.parse_version(BASE + "-se_flow-abs_flow_h").flow_abs == V.ABS_H      # _h before bare token
     assert V.parse_version(BASE + "-se_flow-abs_flow_v").flow_abs == V.ABS_V
@@ -88,7 +97,7 @@ def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_rgb_wo_tgt", "-se_gp2x2_seg", "-se_spp21_flow", "-se_mixSegFlow"])
+@pytest.mark.parametrize("tok", ["-se_rgb_wo_tgt", "-se_gp2x2_seg", "-se_spp21_seg", "-se_mixSegFlow"])
 def test_unbuilt_sources_fail_loudly(tok):
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
