@@ -1044,14 +1044,19 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   if (c.att_src == 1 || c.att_src >= 3) {
     static const int se_dims[7][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}, {1, 8}, {21, 19}};
     fp.se_in = se_dims[c.att_src][0]; fp.se_hid = c.se_hidden > 0 ? c.se_hidden : se_dims[c.att_src][1];
-    fp.pool_2x2 = (c.att_src == 1 && c.se_pool == 1) ? 1 : 0;
-    if (fp.pool_2x2) fp.se_in = 8;
+    fp.pool_2x2 = c.se_pool == 1 ? 1 : 0;
+    if (fp.pool_2x2 && c.att_src == 1) fp.se_in = 8;
     const int src_frames = ctx->unit_sample ? 2 : 1;
-    if (c.att_src == 1 && c.se_pool >= 2) {       // mode='spp': out_pool_size [2,1] / [2] / [8,6,4]
+    if (c.se_pool >= 2) {                         // mode='spp': out_pool_size [2,1] / [2] / [8,6,4]
       static const int sizes[3][4] = {{2, 2, 1, 0}, {1, 2, 0, 0}, {3, 8, 6, 4}};
       const int* sz = sizes[c.se_pool - 2];
       fp.spp_levels = sz[0];
       for (int i = 0; i < sz[0]; ++i) fp.spp_n[i] = sz[1 + i];
+    }
+    if (c.att_src == 3 && c.se_pool != 0) {       // cell-wise class frequencies of the label map
+      if (int rc = launch_k(ctx, se_segcells_kernel, dim3(npairs, src_frames + (c.att_tgt_ones ? 0 : 1)), dim3(256), 0, st, false, fp))
+        return rc;
+    } else if (c.att_src == 1 && c.se_pool >= 2) {
       if (int rc = launch_k(ctx, se_spp_kernel, dim3(npairs, src_frames), dim3(256), 0, st, false, fp)) return rc;
     } else if (int rc = launch_k(ctx, se_pool_kernel, dim3(kPoolSplits, npairs, src_frames + (c.att_tgt_ones ? 0 : 1)),
                                  dim3(256), 0, st, false, fp)) {
@@ -1141,10 +1146,11 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128)", cfg->cnv6_out);
   if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
   if (cfg->att_src < 0 || cfg->att_src > 6) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
-  if (cfg->se_pool < 0 || cfg->se_pool > 4 || cfg->se_hidden < 0 || cfg->se_hidden > 19 || (cfg->se_pool != 0 && cfg->att_src != 1))
+  if (cfg->se_pool < 0 || cfg->se_pool > 4 || cfg->se_hidden < 0 || cfg->se_hidden > 19 ||
+      (cfg->se_pool != 0 && cfg->att_src != 1 && cfg->att_src != 3))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad se_pool / se_hidden");
-  if (cfg->se_pool >= 2 && (cfg->H > cfg->W || !cfg->att_tgt_ones))
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: the pyramid pooling is built for H <= W and a target map of ones");
+  if (cfg->se_pool >= 2 && (cfg->H > cfg->W || (cfg->att_src == 1 && !cfg->att_tgt_ones)))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: the pyramid pooling is built for H <= W (and, on the flow, a target map of ones)");
   if (cfg->att_src == 5 && ((cfg->H * cfg->W) % 4) != 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: se_depth needs H*W % 4 == 0");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1460,13 +1466,14 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     CU_OK(cudaMemcpy(ctx->d_wpred, wp.data(), wp.size() * 4, cudaMemcpyHostToDevice));
     CU_OK(cudaMemcpy(ctx->d_bpred, bp.data(), bp.size() * 4, cudaMemcpyHostToDevice));
   }
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_sew, (kSppMaxDim * 19 + 19 + 19 * 19 + 19) * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_sew, (kSegCellsMaxDim * 19 + 19 + 19 * 19 + 19) * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_staticw, kNumClasses * 4)) return rc;
   if (c.att_src == 1 || c.att_src >= 3) {
     // se(flow|rgb, [8,19]) (attention_module.py:54-103) or se_block(seg_19, ratio=1) (:9-52)
-    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? "se_seg/" : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? "se_depth/" : "se_segflow/");
+    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? (c.se_pool >= 2 ? "se_spp_seg/" : "se_seg/") : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? "se_depth/" : "se_segflow/");
     static const int spp_dim[5] = {2, 8, 10, 8, kSppMaxDim};      // pooled vector of se_flow by se_pool: gp, gp2x2, spp [2,1], [2], [8,6,4]
-    const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 : c.att_src == 4 ? 3 : c.att_src == 5 ? 1 : 21;
+    static const int cells[5] = {1, 4, 5, 4, 116};                // pooled cells by se_pool
+    const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 * cells[c.se_pool] : c.att_src == 4 ? 3 : c.att_src == 5 ? 1 : 21;
     const int dh = c.se_hidden > 0 ? c.se_hidden : ((c.att_src == 3 || c.att_src == 6) ? 19 : 8);
     const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
     const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");

@@ -416,6 +416,78 @@ __global__ void __launch_bounds__(256) se_spp_kernel(const FrontParams p) {
   }
 }
 
+// se_block(seg_19, "se_seg", ratio=1, mode='gp2x2') (davo.py:1317-1322) and se_spp_block(seg_19, "se_spp_seg",
+// ratio=1, spp_size) (davo.py:1323-1340; attention_module.py:105-135): the one-hot label map pooled per cell --
+// the four quadrants [:h/2,:w/2] ... [h/2:,w/2:] (attention_module.py:26-35), or the pyramid cells of
+// se_spp_kernel (left h_size x h_size square of every cell, tf.pad zeros counted) -- i.e. the class
+// frequencies of each cell, 19 per cell, then dense -> 19 (activation) -> 19 (sigmoid); the map is
+// excitation[label].  grid (npairs, frames), 256 threads: a warp per cell with a shared-memory histogram.
+constexpr int kSegCellsMaxDim = (64 + 36 + 16) * kNumClasses;      // 2204
+__global__ void __launch_bounds__(256) se_segcells_kernel(const FrontParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int pl = blockIdx.x, fr = blockIdx.y;
+  int b, k;
+  pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
+  const int hw = p.H * p.W;
+  const int f = unit_frame(p.unit_sample, k, fr);
+  const size_t seg_off = ((size_t)b * 3 + f) * hw;
+  __shared__ float s_pool[kSegCellsMaxDim];
+  __shared__ int s_hist[8][kNumClasses];
+  __shared__ float s_fc1[kPoolDim];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int cell0 = 0;
+  const int levels = p.pool_2x2 ? 1 : p.spp_levels;
+  for (int lv = 0; lv < levels; ++lv) {
+    const int n = p.pool_2x2 ? 2 : p.spp_n[lv];
+    const int hs = (p.H + n - 1) / n, ws = (p.W + n - 1) / n;
+    for (int cell = warp; cell < n * n; cell += 8) {
+      int y0, x0, ch, cw;                                // cell origin and the window that is averaged
+      float inv;
+      if (p.pool_2x2) {
+        const int hh = p.H / 2, hw2 = p.W / 2;
+        y0 = (cell >> 1) ? hh : 0; x0 = (cell & 1) ? hw2 : 0;
+        ch = (cell >> 1) ? p.H - hh : hh; cw = (cell & 1) ? p.W - hw2 : hw2;
+        inv = 1.0f / (float)(ch * cw);
+      } else {
+        y0 = (cell / n) * hs; x0 = (cell % n) * ws; ch = hs; cw = hs;
+        inv = 1.0f / (float)(hs * hs);
+      }
+      if (lane < kNumClasses) s_hist[warp][lane] = 0;
+      __syncwarp();
+      for (int i = lane; i < ch * cw; i += 32) {
+        const int y = y0 + i / cw, x = x0 + i % cw;
+        if (y < p.H && x < p.W) {                       // beyond the map: tf.pad zeros (an all-zero one-hot row)
+          const int lab = label_at(p, seg_off, y * p.W + x);
+          if (lab >= 0 && lab < kNumClasses) atomicAdd(&s_hist[warp][lab], 1);
+        }
+      }
+      __syncwarp();
+      if (lane < kNumClasses) s_pool[(cell0 + cell) * kNumClasses + lane] = (float)s_hist[warp][lane] * inv;
+      __syncwarp();
+    }
+    cell0 += n * n;
+  }
+  __syncthreads();
+  const int D = cell0 * kNumClasses, Hd = p.se_hid;
+  const float* W1 = p.se_w;                    // [D][Hd]
+  const float* b1 = W1 + D * Hd;
+  const float* W2 = b1 + Hd;                   // [Hd][19]
+  const float* b2 = W2 + Hd * kNumClasses;
+  if (threadIdx.x < Hd) {
+    float a = b1[threadIdx.x];
+    for (int i = 0; i < D; ++i) a += s_pool[i] * W1[i * Hd + threadIdx.x];
+    s_fc1[threadIdx.x] = se_activation(a, p.se_act);
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumClasses) {
+    const int c = threadIdx.x;
+    float a = b2[c];
+    for (int j = 0; j < Hd; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
+    p.att_w[((size_t)pl * kAttFrames + fr) * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
 __device__ __forceinline__ float img_norm(uint8_t v) {
   return (float)v * (1.0f / 255.0f) * 2.0f - 1.0f;     // davo.py:1519-1522
 }

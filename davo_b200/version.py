@@ -65,6 +65,13 @@ _BUILT_AFTER_SE_FLOW = {
     "-se_SegFlow_to_seg_8": (ATT_SE_SEGFLOW_SEG, 0, 8),           # davo.py:1350-1357
     "-se_SegFlow_to_seg_wo_tgt": (ATT_SE_SEGFLOW_SEG, 1, 19),     # davo.py:1358-1366
     "-se_SegFlow_to_seg": (ATT_SE_SEGFLOW_SEG, 0, 19),            # davo.py:1367-1374
+    # se_block / se_spp_block on the one-hot label map with cell-wise pooling (hidden width 19 = ratio 1)
+    "-se_gp2x2_seg": (ATT_SE_SEG, 0, 0, SE_POOL_GP2X2),           # davo.py:1317-1322
+    "-se_spp21_seg": (ATT_SE_SEG, 0, 0, SE_POOL_SPP21),           # davo.py:1323-1328
+    "-se_spp_seg_21": (ATT_SE_SEG, 0, 0, SE_POOL_SPP21),
+    "-se_spp2_seg": (ATT_SE_SEG, 0, 0, SE_POOL_SPP2),             # davo.py:1329-1334
+    "-se_spp_seg": (ATT_SE_SEG, 0, 0, SE_POOL_SPP864),            # davo.py:1335-1340
+    "-se_spp864_seg": (ATT_SE_SEG, 0, 0, SE_POOL_SPP864),
 }
 
 
@@ -191,6 +198,8 @@ def parse_version(version: str) -> DavoConfig:
             cfg.att_src, cfg.att_tgt_ones = hit[0], hit[1]
             if len(hit) > 2:
                 cfg.se_hidden = hit[2]
+            if len(hit) > 3:
+                cfg.se_pool = hit[3]
         elif "-no_segmask" in version:                          # davo.py:1385
             cfg.att_src = ATT_NONE
             cfg.att_tgt_ones = 1

@@ -58,8 +58,8 @@ typedef struct davo_config {
   int32_t posenn_se;     /* 0 none, 1 insert, 3 replace (2 skipadd: not built), davo.py:1010-1017, posenn.py:225-236 */
   int32_t micro_batch;   /* units (frame pairs; samples for posenn 2-5) per pass of the conv stack; 0 = 256 */
   int32_t depth_norm;    /* "-norm_depth": SE depth input / 80, davo.py:1108-1111       */
-  int32_t se_pool;       /* se_flow only: 0 global mean, 1 gp2x2 (four quadrant means, davo.py:1181-1192),
-                            2 / 3 / 4 spatial pyramid [2,1] / [2] / [8,6,4] (davo.py:1193-1210) */
+  int32_t se_pool;       /* se_flow and se_seg: 0 global mean, 1 gp2x2 (four quadrants, davo.py:1181-1192, 1317),
+                            2 / 3 / 4 spatial pyramid [2,1] / [2] / [8,6,4] (davo.py:1193-1210, 1323-1340) */
   int32_t se_hidden;     /* width of the SE bottleneck; 0 = the source's default (8; se_seg 19)  */
 } davo_config;
 

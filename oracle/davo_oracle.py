@@ -436,7 +436,7 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att_w.append(w19)
             att.append(class_gather(pred_segs[i], w19))
         use_se_flow = True                               # variables under pose_exp_net/se_flow (davo.py:1404)
-    elif re.search("-se_(gp2x2|spp)", version):
+    elif "mixSegFlow" in version:                                        # davo.py:1375-1383: per-pixel maps, not restated
         _unsupported("attention source in " + version)
     elif "-se_depth_wo_tgt_to_seg" in version or "-se_depth_to_seg" in version:     # davo.py:1211-1227
         dp = torch.as_tensor(depth).to(dtype)
@@ -466,13 +466,25 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att[0] = torch.ones_like(att[0])                             # davo.py:1283
     elif "-se_rgb" in version:
         _unsupported("-se_rgb without _to_seg")
-    elif "-se_seg_wo_tgt" in version or "-se_seg" in version:            # davo.py:1304-1316
+    elif ("-se_seg_wo_tgt" in version or "-se_seg" in version or "-se_gp2x2_seg" in version
+          or re.search("-se_spp(21|2|864|)_seg", version) or "-se_spp_seg_21" in version):   # davo.py:1304-1340
+        # se_block / se_spp_block on the one-hot label map, ratio=1: pooled class frequencies -> 19 -> 19.
+        # Reference order: -se_seg_wo_tgt, -se_seg, -se_gp2x2_seg, -se_spp21_seg | -se_spp_seg_21, -se_spp2_seg,
+        # -se_spp_seg | -se_spp864_seg
+        if "-se_seg_wo_tgt" in version or "-se_seg" in version:
+            seg_scope, seg_mode, seg_sizes = "pose_exp_net/se_seg", "gp", None
+        elif "-se_gp2x2_seg" in version:
+            seg_scope, seg_mode, seg_sizes = "pose_exp_net/se_seg", "gp2x2", None
+        else:
+            seg_scope, seg_mode = "pose_exp_net/se_spp_seg", "spp"
+            seg_sizes = ((2, 1) if ("-se_spp21_seg" in version or "-se_spp_seg_21" in version)
+                         else (2,) if "-se_spp2_seg" in version else (8, 6, 4))
         att, att_w = [], []
         for i in range(3):
             lab = torch.trunc(pred_segs[i][..., 0]).to(torch.int64)      # davo.py:1115
             onehot = torch.nn.functional.one_hot(lab.clamp(0, NUM_CLASSES - 1), NUM_CLASSES).to(dtype)
             onehot = onehot * ((lab >= 0) & (lab < NUM_CLASSES)).to(dtype)[..., None]
-            exc = se_weights(onehot, wts, "pose_exp_net/se_seg", act)    # se_block, ratio=1: 19 -> 19 -> 19
+            exc = se_weights(onehot, wts, seg_scope, act, mode=seg_mode, spp_size=seg_sizes)   # 19 per cell -> 19 -> 19
             att_w.append(exc)
             att.append((onehot * exc[:, None, None, :]).sum(-1, keepdim=True))   # attention_module.py:51, davo.py:1306
         if "-se_seg_wo_tgt" in version:

@@ -367,6 +367,8 @@ def test_pair_selection_computes_what_the_trajectory_reads(host):
     ("couple_net_se_replace", 136, 424, 2, 0),   # sample units, one branch, odd-sized maps
     ("spp864_flow", 136, 424, 3, 4),         # pyramid cells that do not divide the map (tf.pad zeros counted), ragged passes, host entry
     ("spp21_flow_net", 64, 208, 2, 0),       # sample units: both source frames pooled in one launch
+    ("spp864_seg", 136, 424, 3, 4),          # 116 pyramid cells x 19 classes on a map they do not divide; byte labels on the host path
+    ("gp2x2_seg", 64, 208, 2, 0),
     ("segflow_to_seg", 128, 416, 5, 4),      # 21-wide pooled vector on all three frames; the target's constant SE flow
     ("segflow_8_wo_tgt", 64, 208, 3, 0),     # v0 input: the flow is read by the SE only and must still cross on the host path
 ])
@@ -524,7 +526,7 @@ def test_allgather_without_communicator_is_a_copy():
 
 
 @pytest.mark.parametrize("key", ["headline", "se_seg", "static", "couple_shared", "se_insert", "decouple_net",
-                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt", "segflow_to_seg", "se_replace"])
+                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt", "segflow_to_seg", "se_replace", "spp21_seg_couple"])
 def test_feature_mode_matches_oracle(key):
     """DAVO.inference(mode='feature') (davo.py:1553-1564) through davo_forward_features: every fetched tensor
     against the oracle.  Labels and colourings are byte-exact (flow colours: the atan2 of the two

@@ -49,6 +49,15 @@ def test_pyramid_pooling_tokens():
         assert (c.att_src, c.att_tgt_ones, c.se_pool) == (V.ATT_SE_FLOW, 1, pool), tok
 
 
+def test_label_map_pooling_tokens():
+    """se_block(seg_19, "se_seg", mode='gp2x2') and se_spp_block(seg_19, "se_spp_seg", spp_size) (davo.py:1317-1340):
+    the target frame gets its own map (no _wo_tgt form exists, nothing lives under se_flow)."""
+    for tok, pool in (("-se_gp2x2_seg", V.SE_POOL_GP2X2), ("-se_spp21_seg", V.SE_POOL_SPP21), ("-se_spp_seg_21", V.SE_POOL_SPP21),
+                      ("-se_spp2_seg", V.SE_POOL_SPP2), ("-se_spp_seg", V.SE_POOL_SPP864), ("-se_spp864_seg", V.SE_POOL_SPP864)):
+        c = V.parse_version(BASE + "-segmask_all" + tok)
+        assert (c.att_src, c.att_tgt_ones, c.se_pool) == (V.ATT_SE_SEG, 0, pool), tok
+
+
 def test_order_sensitive_tokens():
     assert V.parse_version(BASE + "-se_flow-abs_flow_h").flow_abs == V.ABS_H      # _h before bare token
     assert V.parse_version(BASE + "-se_flow-abs_flow_v").flow_abs == V.ABS_V
@@ -97,7 +106,7 @@ def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_rgb_wo_tgt", "-se_gp2x2_seg", "-se_spp21_seg", "-se_mixSegFlow"])
+@pytest.mark.parametrize("tok", ["-se_rgb_wo_tgt", "-se_depth_wo_tgt", "-se_spp21_mixSegFlow", "-se_mixSegFlow"])
 def test_unbuilt_sources_fail_loudly(tok):
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
