@@ -1470,7 +1470,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_staticw, kNumClasses * 4)) return rc;
   if (c.att_src == 1 || c.att_src >= 3) {
     // se(flow|rgb, [8,19]) (attention_module.py:54-103) or se_block(seg_19, ratio=1) (:9-52)
-    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? (c.se_pool >= 2 ? "se_spp_seg/" : "se_seg/") : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? "se_depth/" : "se_segflow/");
+    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? (c.se_pool >= 2 ? "se_spp_seg/" : "se_seg/") : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? (c.depth_norm == 2 ? "se_disp/" : "se_depth/") : "se_segflow/");
     static const int spp_dim[5] = {2, 8, 10, 8, kSppMaxDim};      // pooled vector of se_flow by se_pool: gp, gp2x2, spp [2,1], [2], [8,6,4]
     static const int cells[5] = {1, 4, 5, 4, 116};                // pooled cells by se_pool
     const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 * cells[c.se_pool] : c.att_src == 4 ? 3 : c.att_src == 5 ? 1 : 21;

@@ -55,7 +55,7 @@ struct FrontParams {
   int in_mode;           // 1: flows are concatenated (v1)
   int att_src;           // 0 none, 1 se_flow, 2 static, 3 se_seg, 4 se_rgb (-> seg), 5 se_depth (-> seg),
                          // 6 se_segflow (-> seg): davo.py:1117-1400
-  int depth_norm;        // "-norm_depth": SE depth input / 80
+  int depth_norm;        // 1: "-norm_depth", SE depth input / 80; 2: the se_disp sources, SE input = 1 / depth of the frame
   int pool_2x2;          // se_flow only: mode='gp2x2' (attention_module.py:68-78): the means of the four
                          // quadrants [:h/2,:w/2], [:h/2,w/2:], [h/2:,:w/2], [h/2:,w/2:] concatenated -> 8 inputs
   int spp_levels;        // se_flow only: mode='spp' (attention_module.py:79-86, 137-167): pyramid levels ...
@@ -227,6 +227,12 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
       const int n4 = hw / 4;
       const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
       const int beg = blockIdx.x * per, end = min(beg + per, n4);
+      if (p.depth_norm == 2)                          // se_disp*_to_seg (davo.py:1253-1270): 1. / depth, no target term
+        for (int i = beg + threadIdx.x; i < end; i += 256) {
+          const float4 a = __ldg(df + i);
+          s0 += 1.0f / a.x + 1.0f / a.y + 1.0f / a.z + 1.0f / a.w;
+        }
+      else
       for (int i = beg + threadIdx.x; i < end; i += 256) {
         const float4 a = __ldg(df + i), c = __ldg(dt + i);
         s0 += (a.x + c.x) + (a.y + c.y) + (a.z + c.z) + (a.w + c.w);
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     if (p.att_src == 6 && f == 1 && threadIdx.x >= kNumClasses)      // mean of a constant map: the target's zero flow
       a = threadIdx.x == kNumClasses ? se_in_x(0.f, p) : se_in_y(0.f, p);
     if (p.att_src == 4) a = a * (1.0f / 255.0f) * 2.0f - 1.0f;
-    if (p.att_src == 5 && p.depth_norm) a = a / 80.0f;
+    if (p.att_src == 5 && p.depth_norm == 1) a = a / 80.0f;
     s_pool[threadIdx.x] = a;
   }
   __syncthreads();

@@ -121,6 +121,8 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
                  V.ATT_SE_SEGFLOW_SEG: ("se_segflow", 21, 19)}
     if cfg.att_src in se_scopes:
         scope, din, dh = se_scopes[cfg.att_src]
+        if cfg.att_src == V.ATT_SE_DEPTH_SEG and cfg.depth_norm == 2:
+            scope = "se_disp"                            # se(1. / depth, "se_disp", ...) (davo.py:1257)
         if cfg.att_src == V.ATT_SE_SEG and cfg.se_pool in V.SPP_SIZES:
             scope = "se_spp_seg"                         # se_spp_block(seg_19, "se_spp_seg", ...) (davo.py:1326)
         if cfg.se_pool == 1:

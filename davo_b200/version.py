@@ -56,6 +56,8 @@ _UNBUILT_AFTER_SE_FLOW = (
 _BUILT_AFTER_SE_FLOW = {
     "-se_depth_wo_tgt_to_seg": (ATT_SE_DEPTH_SEG, 1), # davo.py:1211-1219
     "-se_depth_to_seg": (ATT_SE_DEPTH_SEG, 0),        # davo.py:1220-1227
+    "-se_disp_wo_tgt_to_seg": (ATT_SE_DEPTH_SEG, 1, 0, 0, 2),     # davo.py:1253-1262: se(1. / depth, "se_disp", [8,19])
+    "-se_disp_to_seg": (ATT_SE_DEPTH_SEG, 0, 0, 0, 2),            # davo.py:1263-1270
     "-se_rgb_wo_tgt_to_seg": (ATT_SE_RGB_SEG, 1),     # davo.py:1274-1283
     "-se_rgb_to_seg": (ATT_SE_RGB_SEG, 0),            # davo.py:1284-1292
     "-se_seg_wo_tgt": (ATT_SE_SEG, 1),                # davo.py:1304-1310
@@ -200,6 +202,8 @@ def parse_version(version: str) -> DavoConfig:
                 cfg.se_hidden = hit[2]
             if len(hit) > 3:
                 cfg.se_pool = hit[3]
+            if len(hit) > 4:
+                cfg.depth_norm = hit[4]                              # the disparity sources ignore -norm_depth
         elif "-no_segmask" in version:                          # davo.py:1385
             cfg.att_src = ATT_NONE
             cfg.att_tgt_ones = 1

@@ -57,7 +57,8 @@ typedef struct davo_config {
   int32_t flow_norm;     /* "-norm_flow", davo.py:1088-1091                            */
   int32_t posenn_se;     /* 0 none, 1 insert, 3 replace (2 skipadd: not built), davo.py:1010-1017, posenn.py:225-236 */
   int32_t micro_batch;   /* units (frame pairs; samples for posenn 2-5) per pass of the conv stack; 0 = 256 */
-  int32_t depth_norm;    /* "-norm_depth": SE depth input / 80, davo.py:1108-1111       */
+  int32_t depth_norm;    /* att_src 5: 0 depth_i + depth_tgt (davo.py:1109), 1 the same / 80 ("-norm_depth",
+                            :1110-1111), 2 the se_disp sources: 1 / depth_i (:1253-1270)            */
   int32_t se_pool;       /* se_flow and se_seg: 0 global mean, 1 gp2x2 (four quadrants, davo.py:1181-1192, 1317),
                             2 / 3 / 4 spatial pyramid [2,1] / [2] / [8,6,4] (davo.py:1193-1210, 1323-1340) */
   int32_t se_hidden;     /* width of the SE bottleneck; 0 = the source's default (8; se_seg 19)  */

@@ -454,7 +454,19 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att.append(class_gather(pred_segs[i], w19))
         if "-se_depth_wo_tgt_to_seg" in version:
             att[0] = torch.ones_like(att[0])                             # davo.py:1218
-    elif re.search("-se_(depth|disp)", version):
+    elif "-se_depth" in version:                                         # davo.py:1228-1245: per-pixel maps, not restated
+        _unsupported("attention source in " + version)
+    elif "-se_disp_wo_tgt_to_seg" in version or "-se_disp_to_seg" in version:   # davo.py:1246-1270
+        dp = torch.as_tensor(depth).to(dtype)
+        pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]                     # davo.py:991-996: tgt, src0, src1
+        att, att_w = [], []
+        for i in range(3):
+            w19 = se_weights(1.0 / pred_depths[i], wts, "pose_exp_net/se_disp", act)
+            att_w.append(w19)
+            att.append(class_gather(pred_segs[i], w19))
+        if "-se_disp_wo_tgt_to_seg" in version:
+            att[0] = torch.ones_like(att[0])                             # davo.py:1261
+    elif "-se_disp" in version:
         _unsupported("attention source in " + version)
     elif "-se_rgb_wo_tgt_to_seg" in version or "-se_rgb_to_seg" in version:   # davo.py:1274-1292
         att, att_w = [], []

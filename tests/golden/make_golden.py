@@ -45,6 +45,7 @@ CASES = {
     "gp2x2_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_gp2x2_seg-fc_tanh",
     "spp864_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_spp_seg-fc_tanh",
     "spp21_seg_couple": "v0-sharedNN-dilatedCouplePoseNN-cnv6_64-segmask_rgb-se_spp_seg_21-fc_lrelu",
+    "se_disp": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_disp_to_seg-norm_depth-fc_tanh",
     "segflow_8_wo_tgt": "v0-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_SegFlow_to_seg_8_wo_tgt-fc_lrelu",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)

@@ -58,6 +58,15 @@ def test_label_map_pooling_tokens():
         assert (c.att_src, c.att_tgt_ones, c.se_pool) == (V.ATT_SE_SEG, 0, pool), tok
 
 
+def test_disparity_sources():
+    """se(1. / depth, "se_disp", [8,19]) (davo.py:1246-1270): reads input_depth, ignores -norm_depth."""
+    for tok, tgt1 in (("-se_disp_wo_tgt_to_seg", 1), ("-se_disp_to_seg", 0)):
+        c = V.parse_version(BASE + "-segmask_all" + tok + "-norm_depth")
+        assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, tgt1, 2, 1)
+    with pytest.raises(NotImplementedError):
+        V.parse_version(BASE + "-segmask_all-se_disp_wo_tgt")
+
+
 def test_order_sensitive_tokens():
     assert V.parse_version(BASE + "-se_flow-abs_flow_h").flow_abs == V.ABS_H      # _h before bare token
     assert V.parse_version(BASE + "-se_flow-abs_flow_v").flow_abs == V.ABS_V
@@ -116,7 +125,7 @@ def test_depth_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt-fc_tanh")
     with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all-se_disp_wo_tgt_to_seg-fc_tanh")
+        V.parse_version(BASE + "-segmask_all-se_disp_wo_tgt-fc_tanh")            # per-pixel disparity map: not built
     c = V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-norm_depth-fc_tanh")     # davo.py:1211-1219
     assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 1, 1, 1)
     assert V.parse_version(BASE + "-segmask_all-se_depth_to_seg").att_tgt_ones == 0
