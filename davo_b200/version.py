@@ -167,6 +167,11 @@ def parse_version(version: str) -> DavoConfig:
     elif "-abs_flow" in version:
         cfg.flow_abs = ABS_BOTH
     # G10 attention source (davo.py:1117-1400), reference order
+    if "-se_flow_on_depthseg_sharedlayers" in version:
+        # davo.py:1118-1119 reads `depth_thres` before anything assigns it: the reference stops here
+        raise UnboundLocalError("local variable 'depth_thres' referenced before assignment (reference davo.py:1119)")
+    if "-se_flow_on_depthseg" in version and "-se_flow_on_depthseg_seplayers" not in version:
+        raise NameError("please select `-se_flow_on_depthseg_seplayers' or `-se_flow_on_depthseg_sharedlayers'.")   # davo.py:1155-1156
     for tok in _UNBUILT_SOURCES:
         if tok in version:
             raise NotImplementedError("davo_b200: attention source %s is not built" % tok)

@@ -138,3 +138,14 @@ def test_seglabelid_fails_the_way_the_reference_graph_does():
         with pytest.raises(IndexError, match="list index out of range"):
             V.parse_version(ver)
 
+
+def test_depthseg_tokens_fail_the_way_the_reference_does():
+    """davo.py:1117-1156: `_sharedlayers` reads depth_thres before assignment (:1119); the bare token raises the
+    reference's NameError (:1155-1156); `_seplayers` is a real source that this build does not have."""
+    with pytest.raises(UnboundLocalError, match="depth_thres"):
+        V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg_sharedlayers_15")
+    with pytest.raises(NameError, match="please select"):
+        V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg")
+    with pytest.raises(NotImplementedError, match="seplayers"):
+        V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg_seplayers_15")
+
