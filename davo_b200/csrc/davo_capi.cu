@@ -1044,6 +1044,9 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   if (c.att_src == 1 || c.att_src >= 3) {
     static const int se_dims[7][2] = {{0, 0}, {2, 8}, {0, 0}, {19, 19}, {3, 8}, {1, 8}, {21, 19}};
     fp.se_in = se_dims[c.att_src][0]; fp.se_hid = c.se_hidden > 0 ? c.se_hidden : se_dims[c.att_src][1];
+    fp.se_out = kNumClasses;
+    fp.pixel_map = c.pixel_map;
+    if (c.pixel_map) fp.se_hid = fp.se_out = fp.se_in;     // se_block(..., ratio=1): channel -> channel -> channel
     fp.pool_2x2 = c.se_pool == 1 ? 1 : 0;
     if (fp.pool_2x2 && c.att_src == 1) fp.se_in = 8;
     const int src_frames = ctx->unit_sample ? 2 : 1;
@@ -1151,6 +1154,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad se_pool / se_hidden");
   if (cfg->se_pool >= 2 && (cfg->H > cfg->W || (cfg->att_src == 1 && !cfg->att_tgt_ones)))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: the pyramid pooling is built for H <= W (and, on the flow, a target map of ones)");
+  if (cfg->pixel_map != 0 && (cfg->pixel_map != 1 || cfg->att_src < 4 || cfg->att_src > 6 || cfg->posenn > 1 || cfg->se_pool != 0))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: per-pixel maps are built for att_src 4..6, global pooling and the shared nets");
   if (cfg->att_src == 5 && ((cfg->H * cfg->W) % 4) != 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: se_depth needs H*W % 4 == 0");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1260,7 +1265,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   // Packed PoseNN input (frontend.cuh: pack_kernel): 8 channels per pixel when the width allows the
   // column-widened cnv1 plan (runs of 16 input pixels), else the 16-channel layout of the plain plan.
   const char* wide_env0 = getenv("DAVO_B200_WIDE");
-  ctx->packed_c = (!ctx->unit_sample && (c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
+  // (the per-pixel attention maps are computed by the 16-channel pack_kernel only)
+  ctx->packed_c = (!ctx->unit_sample && !c.pixel_map && (c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
   const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? nbr * 256 : 256, nbr * c7in};
   const int cin_g[7] = {ctx->packed_c, 16, 32, 64, 128, 256, c7in};
   const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c7in};
@@ -1351,7 +1357,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   // ---- workspace ----
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_pool, (size_t)mb * kAttFrames * kPoolSplits * kPoolDim * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_poolcnt, (size_t)mb * kAttFrames * 4)) return rc;
-  if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * kAttFrames * kNumClasses * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * kAttFrames * kAttStride * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_packed, (size_t)mb * c.H * c.W * ctx->packed_c * 4)) return rc;
   float* prev = ctx->d_packed;
   for (int i = 0; i < 7; ++i) {
@@ -1474,12 +1480,13 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     static const int spp_dim[5] = {2, 8, 10, 8, kSppMaxDim};      // pooled vector of se_flow by se_pool: gp, gp2x2, spp [2,1], [2], [8,6,4]
     static const int cells[5] = {1, 4, 5, 4, 116};                // pooled cells by se_pool
     const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 * cells[c.se_pool] : c.att_src == 4 ? 3 : c.att_src == 5 ? 1 : 21;
-    const int dh = c.se_hidden > 0 ? c.se_hidden : ((c.att_src == 3 || c.att_src == 6) ? 19 : 8);
+    const int dh = c.pixel_map ? din : c.se_hidden > 0 ? c.se_hidden : ((c.att_src == 3 || c.att_src == 6) ? 19 : 8);
+    const int dout = c.pixel_map ? din : 19;
     const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
     const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
     const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
     const HostTensor* b2 = find_w(ctx, S + "recover_fc/bias");
-    if (!shape_is(w1, {din, dh}) || !shape_is(b1, {dh}) || !shape_is(w2, {dh, 19}) || !shape_is(b2, {19}))
+    if (!shape_is(w1, {din, dh}) || !shape_is(b1, {dh}) || !shape_is(w2, {dh, dout}) || !shape_is(b2, {dout}))
       return fail(ctx, DAVO_ERR_WEIGHT, "missing or mis-shaped %s{bottleneck_fc,recover_fc}/{kernel,bias}", S.c_str());
     std::vector<float> se;
     se.insert(se.end(), w1->data.begin(), w1->data.end());
@@ -1774,7 +1781,7 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
   if (s == "att_weights") {
     n = kNumClasses;
     if (cap < n) return fail(ctx, DAVO_ERR_ARG, "davo_get_intermediate: buffer too small");
-    if (c.att_src == 1 || c.att_src >= 3) src = ctx->d_attw + (size_t)pair * kAttFrames * n;
+    if (c.att_src == 1 || c.att_src >= 3) src = ctx->d_attw + (size_t)pair * kAttFrames * kAttStride;
     else if (c.att_src == 2) src = ctx->d_staticw;
     else { for (int i = 0; i < n; ++i) out[i] = 1.0f; *n_out = n; return 0; }
   }
@@ -1964,6 +1971,7 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
   const int units = ctx->unit_sample ? B : 2 * B;
   if (ctx->finalized && units > ctx->mb)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: B=%d needs %d units, one pass holds %d", B, units, ctx->mb);
+  if (ctx->cfg.pixel_map) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: not built for the per-pixel attention sources");
   if ((out->flow_color) && !flow) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: flow colouring needs input_flow");
   if ((out->seg_19 || out->seg_color) && !seg) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: label outputs need input_seglabel");
   if (int rc = davo_forward_pairs(ctx, B, DAVO_PAIRS_ALL, img, flow, seg, depth, pose_out, stream)) return rc;

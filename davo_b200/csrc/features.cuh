@@ -23,7 +23,7 @@ struct FeatureParams {
   const uint8_t* img;     // [B][H][3W][3]
   const float* flow;      // [B][4][H][W][2]
   const float* seg;       // [B][3][H][W][1]
-  const float* att_w;     // [units][kAttFrames][19] of the pass that just ran (pair mode 'all')
+  const float* att_w;     // [units][kAttFrames][kAttStride] of the pass that just ran (pair mode 'all')
   const float* static_w;  // [19]
   const float* wheel;     // [55][3] Middlebury colour wheel / 255 (double division, then fp32), built by the host
   // outputs, frame order f = 0 tgt, 1 src0, 2 src1 (the order of the reference's lists); any may be NULL
@@ -50,9 +50,9 @@ __device__ __forceinline__ const float* frame_weights(const FeatureParams& p, in
   if (f == 0 && p.att_tgt_ones) return nullptr;
   if (p.att_src == 2) return p.static_w;
   // slots of a unit: frontend.cuh unit_frame
-  if (p.unit_sample) return p.att_w + ((size_t)b * kAttFrames + (f == 0 ? 2 : f - 1)) * kNumClasses;
-  if (f == 0) return p.att_w + ((size_t)(2 * b) * kAttFrames + 1) * kNumClasses;
-  return p.att_w + ((size_t)(2 * b + (f - 1)) * kAttFrames + 0) * kNumClasses;
+  if (p.unit_sample) return p.att_w + ((size_t)b * kAttFrames + (f == 0 ? 2 : f - 1)) * kAttStride;
+  if (f == 0) return p.att_w + ((size_t)(2 * b) * kAttFrames + 1) * kAttStride;
+  return p.att_w + ((size_t)(2 * b + (f - 1)) * kAttFrames + 0) * kAttStride;
 }
 
 // grid (blocks, B, 3 frames); a thread takes 4 consecutive pixels of a row

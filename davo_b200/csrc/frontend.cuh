@@ -18,6 +18,7 @@ namespace davo {
 constexpr int kPoolSplits = 16;
 constexpr int kPoolDim = 24;     // >= the widest pooled vector (19 class frequencies + 2 flow means)
 constexpr int kAttFrames = 3;    // attention-weight slots per unit (see unit_frame)
+constexpr int kAttStride = 24;   // floats per slot of att_w: 19 class weights, or the excitation of a per-pixel source (<= 21)
 constexpr int kPackedC = 16;     // widest packed PoseNN input (see pack_kernel; FrontParams::packed_c = 8 or 16)
 constexpr int kNumClasses = 19;
 constexpr int kPackBlocksPerPair = 104;
@@ -60,7 +61,11 @@ struct FrontParams {
                          // quadrants [:h/2,:w/2], [:h/2,w/2:], [h/2:,:w/2], [h/2:,w/2:] concatenated -> 8 inputs
   int spp_levels;        // se_flow only: mode='spp' (attention_module.py:79-86, 137-167): pyramid levels ...
   int spp_n[3];          // ... and their out_pool_size; se_spp_kernel replaces se_pool_kernel
-  int se_in, se_hid;     // SE dense sizes: in -> hid -> 19 (flow 2,8; seg 19,19; rgb 3,8)
+  int se_in, se_hid;     // SE dense sizes: in -> hid -> se_out (flow 2,8; seg 19,19; rgb 3,8)
+  int se_out;            // 19 class weights, or with pixel_map the excitation of the SE input itself (= se_in)
+  int pixel_map;         // 1: se_block sources whose map is reduce_sum(input * excitation) per pixel instead of a
+                         //    class weight gathered by label (davo.py:1228-1245, 1293-1303, 1375-1379); att_src
+                         //    4: r,g,b of the frame; 5: its depth term; 6: one_hot(label) and the SE flow
   int att_tgt_ones;
   int mask_rgb, mask_flow;
   int se_act;            // 0 relu, 1 tanh, 2 lrelu
@@ -78,7 +83,7 @@ struct FrontParams {
   const float* static_w; // sigmoid(seg_channel_weight)[19]
   float* pool_part;      // [mb][kAttFrames][kPoolSplits][kPoolDim]
   unsigned int* pool_count;  // [mb][kAttFrames], zero between launches
-  float* att_w;          // [mb][kAttFrames][19], slots as in unit_frame
+  float* att_w;          // [mb][kAttFrames][kAttStride], slots as in unit_frame
   float* packed;         // [mb][H][W][16]
 };
 
@@ -148,6 +153,31 @@ __device__ __forceinline__ float se_activation(float v, int act) {
   if (act == 1) return tanhf(v);
   if (act == 2) return v > 0.f ? v : 0.2f * v;
   return fmaxf(v, 0.f);
+}
+
+// The two dense layers of se() / se_block() (attention_module.py:89-101 / :37-50) on a pooled vector held in
+// shared memory: s_pool[D] -> activation(W1 . + b1)[hid] -> sigmoid(W2 . + b2)[se_out] -> att_w[pl][fr][:].  Called by
+// a whole 256-thread block after a barrier that made s_pool visible; p.se_w = W1[D][hid] b1[hid] W2[hid][out] b2[out].
+__device__ __forceinline__ void se_dense_layers(const FrontParams& p, const float* s_pool, float* s_fc1, int D,
+                                                int pl, int fr) {
+  const int Hd = p.se_hid;
+  const float* W1 = p.se_w;
+  const float* b1 = W1 + D * Hd;
+  const float* W2 = b1 + Hd;
+  const int out = p.se_out;
+  const float* b2 = W2 + Hd * out;
+  if (threadIdx.x < Hd) {
+    float a = b1[threadIdx.x];
+    for (int i = 0; i < D; ++i) a += s_pool[i] * W1[i * Hd + threadIdx.x];
+    s_fc1[threadIdx.x] = se_activation(a, p.se_act);
+  }
+  __syncthreads();
+  if (threadIdx.x < out) {
+    const int c = threadIdx.x;
+    float a = b2[c];
+    for (int j = 0; j < Hd; ++j) a += s_fc1[j] * W2[j * out + c];
+    p.att_w[((size_t)pl * kAttFrames + fr) * kAttStride + c] = 1.0f / (1.0f + expf(-a));
+  }
 }
 
 // grid (kPoolSplits, npairs, frames), 256 threads.  Global average pool of the SE input in
@@ -337,23 +367,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     s_pool[threadIdx.x] = a;
   }
   __syncthreads();
-  const int Hd = p.se_hid;
-  const float* W1 = p.se_w;                    // [D][Hd]
-  const float* b1 = W1 + D * Hd;               // [Hd]
-  const float* W2 = b1 + Hd;                   // [Hd][19]
-  const float* b2 = W2 + Hd * kNumClasses;     // [19]
-  if (threadIdx.x < Hd) {
-    float a = b1[threadIdx.x];
-    for (int i = 0; i < D; ++i) a += s_pool[i] * W1[i * Hd + threadIdx.x];
-    s_fc1[threadIdx.x] = se_activation(a, p.se_act);
-  }
-  __syncthreads();
-  if (threadIdx.x < kNumClasses) {
-    const int c = threadIdx.x;
-    float a = b2[c];
-    for (int j = 0; j < Hd; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
-    p.att_w[((size_t)pl * kAttFrames + fr) * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
-  }
+  se_dense_layers(p, s_pool, s_fc1, D, pl, fr);
 }
 
 // se(flow, "se_flow", [8,19], mode='spp', spp_size) (davo.py:1193-1210): spatial_pyramid_pool
@@ -403,23 +417,7 @@ __global__ void __launch_bounds__(256) se_spp_kernel(const FrontParams p) {
     cell0 += n * n;
   }
   __syncthreads();
-  const int D = cell0 * 2, Hd = p.se_hid;
-  const float* W1 = p.se_w;                    // [D][Hd]
-  const float* b1 = W1 + D * Hd;
-  const float* W2 = b1 + Hd;                   // [Hd][19]
-  const float* b2 = W2 + Hd * kNumClasses;
-  if (threadIdx.x < Hd) {
-    float a = b1[threadIdx.x];
-    for (int i = 0; i < D; ++i) a += s_pool[i] * W1[i * Hd + threadIdx.x];
-    s_fc1[threadIdx.x] = se_activation(a, p.se_act);
-  }
-  __syncthreads();
-  if (threadIdx.x < kNumClasses) {
-    const int c = threadIdx.x;
-    float a = b2[c];
-    for (int j = 0; j < Hd; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
-    p.att_w[((size_t)pl * kAttFrames + fr) * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
-  }
+  se_dense_layers(p, s_pool, s_fc1, cell0 * 2, pl, fr);
 }
 
 // se_block(seg_19, "se_seg", ratio=1, mode='gp2x2') (davo.py:1317-1322) and se_spp_block(seg_19, "se_spp_seg",
@@ -475,23 +473,7 @@ __global__ void __launch_bounds__(256) se_segcells_kernel(const FrontParams p) {
     cell0 += n * n;
   }
   __syncthreads();
-  const int D = cell0 * kNumClasses, Hd = p.se_hid;
-  const float* W1 = p.se_w;                    // [D][Hd]
-  const float* b1 = W1 + D * Hd;
-  const float* W2 = b1 + Hd;                   // [Hd][19]
-  const float* b2 = W2 + Hd * kNumClasses;
-  if (threadIdx.x < Hd) {
-    float a = b1[threadIdx.x];
-    for (int i = 0; i < D; ++i) a += s_pool[i] * W1[i * Hd + threadIdx.x];
-    s_fc1[threadIdx.x] = se_activation(a, p.se_act);
-  }
-  __syncthreads();
-  if (threadIdx.x < kNumClasses) {
-    const int c = threadIdx.x;
-    float a = b2[c];
-    for (int j = 0; j < Hd; ++j) a += s_fc1[j] * W2[j * kNumClasses + c];
-    p.att_w[((size_t)pl * kAttFrames + fr) * kNumClasses + c] = 1.0f / (1.0f + expf(-a));
-  }
+  se_dense_layers(p, s_pool, s_fc1, cell0 * kNumClasses, pl, fr);
 }
 
 __device__ __forceinline__ float img_norm(uint8_t v) {
@@ -516,17 +498,18 @@ __device__ __forceinline__ float4 shfl_xor4(const float4 v, int m) {
 __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
   pdl_launch_dependents();
   pdl_wait();                     // workspace buffers are shared with the kernels before this one
-  __shared__ float s_w[kNumClasses], s_wt[kNumClasses];    // class weights: source frame, target frame
+  __shared__ float s_w[kAttStride], s_wt[kAttStride];      // class weights (or excitation): source frame, target frame
   const int pl = blockIdx.y;
   int b, k;
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
-  if (threadIdx.x < kNumClasses) {
+  if (threadIdx.x < kAttStride) {
     const bool se = p.att_src == 1 || p.att_src >= 3;
-    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * kAttFrames + 0) * kNumClasses + threadIdx.x]
-                     : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
-    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * kAttFrames + 1) * kNumClasses + threadIdx.x]
-                      : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
+    const float st = threadIdx.x < kNumClasses ? p.static_w[threadIdx.x] : 0.0f;
+    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * kAttFrames + 0) * kAttStride + threadIdx.x]
+                     : p.att_src == 2 ? st : 1.0f;
+    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * kAttFrames + 1) * kAttStride + threadIdx.x]
+                      : p.att_src == 2 ? st : 1.0f;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, j = lane & 3;
@@ -540,8 +523,36 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
     const int pix = min(pix_raw, hw - 1);                       // keep every lane in the shuffles
     const int h = (int)(((float)pix + 0.5f) * inv_w);           // exact for these sizes
     const int row_off = pix + 2 * p.W * h;                      // h * 3W + w
+    const uint8_t* pt = img_b + (size_t)(row_off + p.W) * 3;    // tgt = centre frame
+    const uint8_t* ps = img_b + (size_t)(row_off + src_col0) * 3;
+    const float tr0 = img_norm(pt[0]), tg0 = img_norm(pt[1]), tb0 = img_norm(pt[2]);
+    const float sr0 = img_norm(ps[0]), sg0 = img_norm(ps[1]), sb0 = img_norm(ps[2]);
+    float2 fl = make_float2(0.f, 0.f);
+    if (p.in_mode == 1 || (p.pixel_map && p.att_src == 6)) fl = flow1_at(p, b, k, pix, hw);
     float a_src = 1.0f, a_tgt = 1.0f;
-    if (p.att_src != 0) {
+    if (p.pixel_map) {
+      // the map is reduce_sum(SE input * excitation) at the pixel (attention_module.py:51 + davo.py:1230, 1295, 1377)
+      if (p.att_src == 4) {                                      // se_block(image): r, g, b of the frame itself
+        a_src = sr0 * s_w[0] + sg0 * s_w[1] + sb0 * s_w[2];
+        if (!p.att_tgt_ones) a_tgt = tr0 * s_wt[0] + tg0 * s_wt[1] + tb0 * s_wt[2];
+      } else if (p.att_src == 5) {                               // se_block(depth term of the frame), see se_pool_kernel
+        const float dt = __ldg(p.depth + ((size_t)b * 3 + 1) * hw + pix);
+        const float ds = __ldg(p.depth + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw + pix);
+        const float xs = p.depth_norm == 2 ? 1.0f / ds : p.depth_norm == 1 ? (ds + dt) / 80.0f : ds + dt;
+        const float xt = p.depth_norm == 2 ? 1.0f / dt : p.depth_norm == 1 ? (dt + dt) / 80.0f : dt + dt;
+        a_src = xs * s_w[0];
+        if (!p.att_tgt_ones) a_tgt = xt * s_wt[0];
+      } else {                                                   // se_block(concat(one_hot(label), SE flow)): 19 + 2 channels
+        const int lab = label_at(p, seg_src, pix);
+        a_src = ((lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f) + se_in_x(fl.x, p) * s_w[kNumClasses] +
+                se_in_y(fl.y, p) * s_w[kNumClasses + 1];
+        if (!p.att_tgt_ones) {                                   // the target's flow is zeros (davo.py:979)
+          const int lt = label_at(p, seg_tgt, pix);
+          a_tgt = ((lt >= 0 && lt < kNumClasses) ? s_wt[lt] : 0.0f) + se_in_x(0.f, p) * s_wt[kNumClasses] +
+                  se_in_y(0.f, p) * s_wt[kNumClasses + 1];
+        }
+      }
+    } else if (p.att_src != 0) {
       const int lab = label_at(p, seg_src, pix);                 // tf.cast truncates toward zero
       a_src = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;  // one_hot: out of range -> 0
       if (!p.att_tgt_ones) {
@@ -550,16 +561,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
       }
     }
     const float mt = p.mask_rgb ? a_tgt : 1.0f, ms = p.mask_rgb ? a_src : 1.0f;
-    const uint8_t* pt = img_b + (size_t)(row_off + p.W) * 3;    // tgt = centre frame
-    const uint8_t* ps = img_b + (size_t)(row_off + src_col0) * 3;
-    const float tr = img_norm(pt[0]) * mt, tg = img_norm(pt[1]) * mt, tb = img_norm(pt[2]) * mt;
-    const float sr = img_norm(ps[0]) * ms, sg = img_norm(ps[1]) * ms, sb = img_norm(ps[2]) * ms;
+    const float tr = tr0 * mt, tg = tg0 * mt, tb = tb0 * mt;
+    const float sr = sr0 * ms, sg = sg0 * ms, sb = sb0 * ms;
     float fx = 0.f, fy = 0.f;
     if (p.in_mode == 1) {
-      const float2 f = flow1_at(p, b, k, pix, hw);
       const float m = p.mask_flow ? a_src : 1.0f;
-      fx = f.x * m;
-      fy = f.y * m;
+      fx = fl.x * m;
+      fy = fl.y * m;
     }
     const float trh = round_tf32(tr), tgh = round_tf32(tg), tbh = round_tf32(tb);
     const float srh = round_tf32(sr), sgh = round_tf32(sg), sbh = round_tf32(sb);
@@ -617,9 +625,9 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
   const int hw = p.H * p.W, groups = hw / 4;
   if (threadIdx.x < kNumClasses) {
     const bool se = p.att_src == 1 || p.att_src >= 3;
-    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * kAttFrames + 0) * kNumClasses + threadIdx.x]
+    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * kAttFrames + 0) * kAttStride + threadIdx.x]
                      : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
-    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * kAttFrames + 1) * kNumClasses + threadIdx.x]
+    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * kAttFrames + 1) * kAttStride + threadIdx.x]
                       : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
   }
   __syncthreads();
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
     const bool se = p.att_src == 1 || p.att_src >= 3;
     float v = 1.0f;
     if (p.att_src == 2) v = p.static_w[c];
-    else if (se && !(fr == 2 && p.att_tgt_ones)) v = p.att_w[((size_t)pl * kAttFrames + fr) * kNumClasses + c];
+    else if (se && !(fr == 2 && p.att_tgt_ones)) v = p.att_w[((size_t)pl * kAttFrames + fr) * kAttStride + c];
     s_w[fr][c] = v;
   }
   __syncthreads();

@@ -74,7 +74,7 @@ class DAVO(object):
             mask_mode=self.config.mask_mode, se_act=self.config.se_act,
             flow_abs=self.config.flow_abs, flow_norm=self.config.flow_norm,
             posenn_se=self.config.posenn_se, micro_batch=micro_batch, depth_norm=self.config.depth_norm,
-            se_pool=self.config.se_pool, se_hidden=self.config.se_hidden)
+            se_pool=self.config.se_pool, se_hidden=self.config.se_hidden, pixel_map=self.config.pixel_map)
         h = C.c_void_p()
         rc = self._lib.davo_create(C.byref(cfg), self.device, C.byref(h))
         if rc != 0:

@@ -131,7 +131,10 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
             din *= sum(n * n for n in V.SPP_SIZES[cfg.se_pool])   # one mean per pyramid cell
         if cfg.se_hidden:
             dh = cfg.se_hidden
-        for name, (fi, fo) in (("bottleneck_fc", (din, dh)), ("recover_fc", (dh, 19))):
+        dout = 19
+        if cfg.pixel_map:                                # se_block(..., ratio=1): channel -> channel -> channel
+            dh = dout = din
+        for name, (fi, fo) in (("bottleneck_fc", (din, dh)), ("recover_fc", (dh, dout))):
             std = math.sqrt(1.3 * 2.0 / fi)
             w["pose_exp_net/%s/%s/kernel" % (scope, name)] = _trunc_normal(rng, (fi, fo), std)
             w["pose_exp_net/%s/%s/bias" % (scope, name)] = bias(fo)

@@ -74,6 +74,14 @@ _BUILT_AFTER_SE_FLOW = {
     "-se_spp2_seg": (ATT_SE_SEG, 0, 0, SE_POOL_SPP2),             # davo.py:1329-1334
     "-se_spp_seg": (ATT_SE_SEG, 0, 0, SE_POOL_SPP864),            # davo.py:1335-1340
     "-se_spp864_seg": (ATT_SE_SEG, 0, 0, SE_POOL_SPP864),
+    # se_block sources whose map is reduce_sum(input * excitation) per pixel (no label gather), ratio=1
+    "-se_depth_wo_tgt": dict(att_src=ATT_SE_DEPTH_SEG, att_tgt_ones=1, pixel_map=1),    # davo.py:1228-1237
+    "-se_depth": dict(att_src=ATT_SE_DEPTH_SEG, att_tgt_ones=0, pixel_map=1),           # davo.py:1238-1245
+    "-se_disp_wo_tgt": dict(att_src=ATT_SE_DEPTH_SEG, att_tgt_ones=1, pixel_map=1, depth_norm=2),   # davo.py:1271-1281
+    "-se_disp": dict(att_src=ATT_SE_DEPTH_SEG, att_tgt_ones=0, pixel_map=1, depth_norm=2),          # davo.py:1282-1292
+    "-se_rgb_wo_tgt": dict(att_src=ATT_SE_RGB_SEG, att_tgt_ones=1, pixel_map=1),        # davo.py:1293-1298
+    "-se_rgb": dict(att_src=ATT_SE_RGB_SEG, att_tgt_ones=0, pixel_map=1),               # davo.py:1299-1303
+    "-se_mixSegFlow": dict(att_src=ATT_SE_SEGFLOW_SEG, att_tgt_ones=0, pixel_map=1),    # davo.py:1375-1379
 }
 
 
@@ -92,6 +100,7 @@ class DavoConfig:
     posenn_se: int = PSE_NONE
     depth_norm: int = 0         # "-norm_depth" (davo.py:1108-1111); only read by the se_depth sources
     se_pool: int = 0            # se_flow: SE_POOL_* (davo.py:1175-1210)
+    pixel_map: int = 0          # 1: map = reduce_sum(SE input * excitation) per pixel (-se_rgb, -se_depth, -se_disp, -se_mixSegFlow)
     se_hidden: int = 0          # SE bottleneck width, 0 = default (8; se_seg 19); gp2x2_flow_nobottle: 19
     needs_depth: int = 0        # "depth"/"disp" in the version: the graph reads input_depth (davo.py:960)
     version_tag: str = "v0"
@@ -202,6 +211,12 @@ def parse_version(version: str) -> DavoConfig:
                 break
         if chain_hit is not None:
             hit = _BUILT_AFTER_SE_FLOW[chain_hit]
+            if isinstance(hit, dict):
+                if cfg.posenn >= POSENN_DECOUPLE_DIL:
+                    raise NotImplementedError("davo_b200: attention source %s is built for the -sharedNN nets only" % chain_hit)
+                for key, val in hit.items():
+                    setattr(cfg, key, val)
+                hit = (cfg.att_src, cfg.att_tgt_ones)
             cfg.att_src, cfg.att_tgt_ones = hit[0], hit[1]
             if len(hit) > 2:
                 cfg.se_hidden = hit[2]

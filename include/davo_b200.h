@@ -62,6 +62,10 @@ typedef struct davo_config {
   int32_t se_pool;       /* se_flow and se_seg: 0 global mean, 1 gp2x2 (four quadrants, davo.py:1181-1192, 1317),
                             2 / 3 / 4 spatial pyramid [2,1] / [2] / [8,6,4] (davo.py:1193-1210, 1323-1340) */
   int32_t se_hidden;     /* width of the SE bottleneck; 0 = the source's default (8; se_seg 19)  */
+  int32_t pixel_map;     /* 1: the se_block sources whose map is reduce_sum(input * excitation) per pixel rather
+                            than a class weight gathered by label: att_src 4 -se_rgb[_wo_tgt] (davo.py:1293-1303),
+                            5 -se_depth[_wo_tgt] / -se_disp[_wo_tgt] (:1228-1245, 1271-1292), 6 -se_mixSegFlow
+                            (:1375-1379); shared nets only                                           */
 } davo_config;
 
 /* Stands in for DAVO.__init__ + DAVO.setup_inference (reference davo.py:31-33,

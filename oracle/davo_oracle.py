@@ -412,7 +412,7 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
     # 3.5 attention maps (davo.py:1114-1400)
     use_se_flow = False
     att_w = None
-    if "-se_flow_on_depthseg" in version or "-se_mix" in version:
+    if "-se_flow_on_depthseg" in version or "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:
         _unsupported("depth/mix attention")
     elif "-se_flow" in version:                                          # davo.py:1175-1180
         att, att_w = [], []
@@ -436,7 +436,7 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att_w.append(w19)
             att.append(class_gather(pred_segs[i], w19))
         use_se_flow = True                               # variables under pose_exp_net/se_flow (davo.py:1404)
-    elif "mixSegFlow" in version:                                        # davo.py:1375-1383: per-pixel maps, not restated
+    elif "-se_spp21_mixSegFlow" in version:                              # davo.py:1380-1383: not restated
         _unsupported("attention source in " + version)
     elif "-se_depth_wo_tgt_to_seg" in version or "-se_depth_to_seg" in version:     # davo.py:1211-1227
         dp = torch.as_tensor(depth).to(dtype)
@@ -454,8 +454,15 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att.append(class_gather(pred_segs[i], w19))
         if "-se_depth_wo_tgt_to_seg" in version:
             att[0] = torch.ones_like(att[0])                             # davo.py:1218
-    elif "-se_depth" in version:                                         # davo.py:1228-1245: per-pixel maps, not restated
-        _unsupported("attention source in " + version)
+    elif "-se_depth_wo_tgt" in version or "-se_depth" in version:        # davo.py:1228-1245
+        dp = torch.as_tensor(depth).to(dtype)
+        pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]
+        se_in_d = [d + pred_depths[0] for d in pred_depths]              # davo.py:1109 (list + Tensor broadcast)
+        if "-norm_depth" in version:
+            se_in_d = [d / 80.0 for d in se_in_d]
+        att = [se_block(x, wts, "pose_exp_net/se_depth", act).sum(-1, keepdim=True) for x in se_in_d]
+        if "-se_depth_wo_tgt" in version:
+            att[0] = torch.ones_like(att[0])                             # davo.py:1236
     elif "-se_disp_wo_tgt_to_seg" in version or "-se_disp_to_seg" in version:   # davo.py:1246-1270
         dp = torch.as_tensor(depth).to(dtype)
         pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]                     # davo.py:991-996: tgt, src0, src1
@@ -466,8 +473,12 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att.append(class_gather(pred_segs[i], w19))
         if "-se_disp_wo_tgt_to_seg" in version:
             att[0] = torch.ones_like(att[0])                             # davo.py:1261
-    elif "-se_disp" in version:
-        _unsupported("attention source in " + version)
+    elif "-se_disp_wo_tgt" in version or "-se_disp" in version:          # davo.py:1271-1292
+        dp = torch.as_tensor(depth).to(dtype)
+        pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]
+        att = [se_block(1.0 / d, wts, "pose_exp_net/se_disp", act).sum(-1, keepdim=True) for d in pred_depths]
+        if "-se_disp_wo_tgt" in version:
+            att[0] = torch.ones_like(att[0])                             # davo.py:1280
     elif "-se_rgb_wo_tgt_to_seg" in version or "-se_rgb_to_seg" in version:   # davo.py:1274-1292
         att, att_w = [], []
         for i in range(3):
@@ -476,8 +487,10 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att.append(class_gather(pred_segs[i], w19))
         if "-se_rgb_wo_tgt_to_seg" in version:
             att[0] = torch.ones_like(att[0])                             # davo.py:1283
-    elif "-se_rgb" in version:
-        _unsupported("-se_rgb without _to_seg")
+    elif "-se_rgb_wo_tgt" in version or "-se_rgb" in version:            # davo.py:1293-1303
+        att = [se_block(input_images[i], wts, "pose_exp_net/se_rgb", act).sum(-1, keepdim=True) for i in range(3)]
+        if "-se_rgb_wo_tgt" in version:
+            att[0] = torch.ones_like(att[0])                             # davo.py:1297
     elif ("-se_seg_wo_tgt" in version or "-se_seg" in version or "-se_gp2x2_seg" in version
           or re.search("-se_spp(21|2|864|)_seg", version) or "-se_spp_seg_21" in version):   # davo.py:1304-1340
         # se_block / se_spp_block on the one-hot label map, ratio=1: pooled class frequencies -> 19 -> 19.
@@ -514,6 +527,14 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
         if "-se_SegFlow_to_seg_8_wo_tgt" in version or (                 # first match wins: davo.py:1341, 1350, 1358
                 "-se_SegFlow_to_seg_8" not in version and "-se_SegFlow_to_seg_wo_tgt" in version):
             att[0] = torch.ones_like(att[0])
+    elif "-se_mixSegFlow" in version:                                    # davo.py:1375-1379
+        att = []
+        for i in range(3):
+            lab = torch.trunc(pred_segs[i][..., 0]).to(torch.int64)
+            onehot = torch.nn.functional.one_hot(lab.clamp(0, NUM_CLASSES - 1), NUM_CLASSES).to(dtype)
+            onehot = onehot * ((lab >= 0) & (lab < NUM_CLASSES)).to(dtype)[..., None]
+            x = torch.cat([onehot, se_in[i]], dim=-1)                    # 19 + 2 channels
+            att.append(se_block(x, wts, "pose_exp_net/se_segflow", act).sum(-1, keepdim=True))
     elif "-no_segmask" in version:                                       # davo.py:1385-1389
         att = [torch.ones_like(s) for s in pred_segs]
     elif "-segmask_" in version and "-static" in version:                # davo.py:1390-1394

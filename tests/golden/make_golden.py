@@ -46,6 +46,10 @@ CASES = {
     "spp864_seg": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_spp_seg-fc_tanh",
     "spp21_seg_couple": "v0-sharedNN-dilatedCouplePoseNN-cnv6_64-segmask_rgb-se_spp_seg_21-fc_lrelu",
     "se_disp": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_disp_to_seg-norm_depth-fc_tanh",
+    "pix_rgb": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_rgb-fc_tanh",
+    "pix_depth_wo_tgt": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_rgb-se_depth_wo_tgt-norm_depth-fc_lrelu",
+    "pix_disp": "v1-sharedNN-dilatedCouplePoseNN-cnv6_64-segmask_all-se_disp-fc_tanh",
+    "pix_mix_segflow": "v0-sharedNN-dilatedPoseNN-cnv6_128-segmask_rgb-se_mixSegFlow-abs_flow-norm_flow-fc_tanh",
     "segflow_8_wo_tgt": "v0-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_SegFlow_to_seg_8_wo_tgt-fc_lrelu",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)

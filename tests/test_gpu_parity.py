@@ -369,6 +369,8 @@ def test_pair_selection_computes_what_the_trajectory_reads(host):
     ("spp21_flow_net", 64, 208, 2, 0),       # sample units: both source frames pooled in one launch
     ("spp864_seg", 136, 424, 3, 4),          # 116 pyramid cells x 19 classes on a map they do not divide; byte labels on the host path
     ("gp2x2_seg", 64, 208, 2, 0),
+    ("pix_mix_segflow", 128, 416, 3, 2),     # per-pixel map with flow terms on a v0 input: the flow crosses for the map only
+    ("pix_rgb", 136, 424, 2, 0),             # per-pixel map of the image itself, target map computed
     ("segflow_to_seg", 128, 416, 5, 4),      # 21-wide pooled vector on all three frames; the target's constant SE flow
     ("segflow_8_wo_tgt", 64, 208, 3, 0),     # v0 input: the flow is read by the SE only and must still cross on the host path
 ])

@@ -63,8 +63,20 @@ def test_disparity_sources():
     for tok, tgt1 in (("-se_disp_wo_tgt_to_seg", 1), ("-se_disp_to_seg", 0)):
         c = V.parse_version(BASE + "-segmask_all" + tok + "-norm_depth")
         assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, tgt1, 2, 1)
-    with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all-se_disp_wo_tgt")
+
+
+def test_per_pixel_sources():
+    """se_block sources whose map is reduce_sum(input * excitation) (davo.py:1228-1245, 1271-1303, 1375-1379)."""
+    table = {"-se_rgb": (V.ATT_SE_RGB_SEG, 0, 0), "-se_rgb_wo_tgt": (V.ATT_SE_RGB_SEG, 1, 0),
+             "-se_depth": (V.ATT_SE_DEPTH_SEG, 0, 0), "-se_depth_wo_tgt": (V.ATT_SE_DEPTH_SEG, 1, 0),
+             "-se_disp": (V.ATT_SE_DEPTH_SEG, 0, 2), "-se_disp_wo_tgt": (V.ATT_SE_DEPTH_SEG, 1, 2),
+             "-se_mixSegFlow": (V.ATT_SE_SEGFLOW_SEG, 0, 0)}
+    for tok, (att, tgt1, dn) in table.items():
+        c = V.parse_version(BASE + "-segmask_all" + tok)
+        assert (c.att_src, c.att_tgt_ones, c.pixel_map, c.depth_norm) == (att, tgt1, 1, dn), tok
+    assert V.parse_version(BASE + "-segmask_all-se_rgb_to_seg").pixel_map == 0
+    with pytest.raises(NotImplementedError, match="sharedNN"):
+        V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_rgb")
 
 
 def test_order_sensitive_tokens():
@@ -115,7 +127,7 @@ def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_rgb_wo_tgt", "-se_depth_wo_tgt", "-se_spp21_mixSegFlow", "-se_mixSegFlow"])
+@pytest.mark.parametrize("tok", ["-se_mixDepthFlow", "-se_mixDispFlow", "-se_spp21_mixSegFlow", "-se_flow_on_depthseg_seplayers"])
 def test_unbuilt_sources_fail_loudly(tok):
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
@@ -123,9 +135,7 @@ def test_unbuilt_sources_fail_loudly(tok):
 
 def test_depth_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt-fc_tanh")
-    with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all-se_disp_wo_tgt-fc_tanh")            # per-pixel disparity map: not built
+        V.parse_version(BASE + "-segmask_all-se_mixDepthFlow-fc_tanh")
     c = V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-norm_depth-fc_tanh")     # davo.py:1211-1219
     assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 1, 1, 1)
     assert V.parse_version(BASE + "-segmask_all-se_depth_to_seg").att_tgt_ones == 0
