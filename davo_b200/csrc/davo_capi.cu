@@ -1046,6 +1046,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     fp.se_in = se_dims[c.att_src][0]; fp.se_hid = c.se_hidden > 0 ? c.se_hidden : se_dims[c.att_src][1];
     fp.se_out = kNumClasses;
     fp.pixel_map = c.pixel_map;
+    if (c.pixel_map == 2) fp.se_in = 3;                    // depth term, SE flow x, SE flow y
     if (c.pixel_map) fp.se_hid = fp.se_out = fp.se_in;     // se_block(..., ratio=1): channel -> channel -> channel
     fp.pool_2x2 = c.se_pool == 1 ? 1 : 0;
     if (fp.pool_2x2 && c.att_src == 1) fp.se_in = 8;
@@ -1154,7 +1155,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad se_pool / se_hidden");
   if (cfg->se_pool >= 2 && (cfg->H > cfg->W || (cfg->att_src == 1 && !cfg->att_tgt_ones)))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: the pyramid pooling is built for H <= W (and, on the flow, a target map of ones)");
-  if (cfg->pixel_map != 0 && (cfg->pixel_map != 1 || cfg->att_src < 4 || cfg->att_src > 6 || cfg->posenn > 1 || cfg->se_pool != 0))
+  if (cfg->pixel_map != 0 && (cfg->pixel_map < 1 || cfg->pixel_map > 2 || (cfg->pixel_map == 2 && cfg->att_src != 5) ||
+                              cfg->att_src < 4 || cfg->att_src > 6 || cfg->posenn > 1 || cfg->se_pool != 0))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: per-pixel maps are built for att_src 4..6, global pooling and the shared nets");
   if (cfg->att_src == 5 && ((cfg->H * cfg->W) % 4) != 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: se_depth needs H*W % 4 == 0");
   int ndev = 0;
@@ -1476,10 +1478,10 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_staticw, kNumClasses * 4)) return rc;
   if (c.att_src == 1 || c.att_src >= 3) {
     // se(flow|rgb, [8,19]) (attention_module.py:54-103) or se_block(seg_19, ratio=1) (:9-52)
-    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? (c.se_pool >= 2 ? "se_spp_seg/" : "se_seg/") : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? (c.depth_norm == 2 ? "se_disp/" : "se_depth/") : "se_segflow/");
+    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? (c.se_pool >= 2 ? "se_spp_seg/" : "se_seg/") : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? (c.pixel_map == 2 ? (c.depth_norm == 2 ? "se_dispflow/" : "se_depthflow/") : c.depth_norm == 2 ? "se_disp/" : "se_depth/") : "se_segflow/");
     static const int spp_dim[5] = {2, 8, 10, 8, kSppMaxDim};      // pooled vector of se_flow by se_pool: gp, gp2x2, spp [2,1], [2], [8,6,4]
     static const int cells[5] = {1, 4, 5, 4, 116};                // pooled cells by se_pool
-    const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 * cells[c.se_pool] : c.att_src == 4 ? 3 : c.att_src == 5 ? 1 : 21;
+    const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 * cells[c.se_pool] : c.att_src == 4 ? 3 : c.att_src == 5 ? (c.pixel_map == 2 ? 3 : 1) : 21;
     const int dh = c.pixel_map ? din : c.se_hidden > 0 ? c.se_hidden : ((c.att_src == 3 || c.att_src == 6) ? 19 : 8);
     const int dout = c.pixel_map ? din : 19;
     const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
@@ -1524,7 +1526,7 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
   ctx->cur_flow16 = nullptr; ctx->cur_n16 = 0;
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward: B=%d outside 1..%d", B, ctx->cfg.max_batch);
-  if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1 || ctx->cfg.att_src == 6) && !flow))
+  if (!img || !pose_out || (ctx->cfg.att_src != 0 && !seg) || ((ctx->cfg.in_mode == 1 || ctx->cfg.att_src == 1 || ctx->cfg.att_src == 6 || ctx->cfg.pixel_map == 2) && !flow))
     return fail(ctx, DAVO_ERR_ARG, "davo_forward: null input buffer");
   CU_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1566,12 +1568,12 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   const davo_config& c = ctx->cfg;
-  if (!img || !pose_out || (c.att_src != 0 && !seg) || ((c.in_mode == 1 || c.att_src == 1 || c.att_src == 6) && !flow))
+  if (!img || !pose_out || (c.att_src != 0 && !seg) || ((c.in_mode == 1 || c.att_src == 1 || c.att_src == 6 || c.pixel_map == 2) && !flow))
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: null input buffer");
   CU_OK(cudaSetDevice(ctx->device));
   const size_t hw = (size_t)c.H * c.W;
   const size_t n_img = hw * 9, n_flow = hw * 8, n_seg = hw * 3;   // elements per sample
-  const bool uses_flow = (c.in_mode == 1 || c.att_src == 1 || c.att_src == 6);
+  const bool uses_flow = (c.in_mode == 1 || c.att_src == 1 || c.att_src == 6 || c.pixel_map == 2);
   // Host inputs arrive over PCIe more slowly than the stack computes, so what matters is how soon
   // compute can start behind the copy: chunks of 16 samples (8 chunks per 128-sample batch).
   const int ups = ctx->unit_sample ? 1 : 2;                        // units of a pass per sample

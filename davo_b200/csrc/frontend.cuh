@@ -63,7 +63,8 @@ struct FrontParams {
   int spp_n[3];          // ... and their out_pool_size; se_spp_kernel replaces se_pool_kernel
   int se_in, se_hid;     // SE dense sizes: in -> hid -> se_out (flow 2,8; seg 19,19; rgb 3,8)
   int se_out;            // 19 class weights, or with pixel_map the excitation of the SE input itself (= se_in)
-  int pixel_map;         // 1: se_block sources whose map is reduce_sum(input * excitation) per pixel instead of a
+  int pixel_map;         // 1 (2: with att_src 5, depth term AND SE flow, -se_mixDepthFlow / -se_mixDispFlow, davo.py:1157-1174):
+                         //    se_block sources whose map is reduce_sum(input * excitation) per pixel instead of a
                          //    class weight gathered by label (davo.py:1228-1245, 1293-1303, 1375-1379); att_src
                          //    4: r,g,b of the frame; 5: its depth term; 6: one_hot(label) and the SE flow
   int att_tgt_ones;
@@ -267,6 +268,12 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
         const float4 a = __ldg(df + i), c = __ldg(dt + i);
         s0 += (a.x + c.x) + (a.y + c.y) + (a.z + c.z) + (a.w + c.w);
       }
+      if (p.pixel_map == 2 && f != 1)                 // -se_mixDepthFlow / -se_mixDispFlow: + the two SE flow means
+        for (int i = beg + threadIdx.x; i < end; i += 256) {
+          const float4 v0 = flow2_at(p, b, f == 2 ? 1 : 0, 4 * i, hw), v1 = flow2_at(p, b, f == 2 ? 1 : 0, 4 * i + 2, hw);
+          s1 += se_in_x(v0.x, p) + se_in_x(v0.z, p) + se_in_x(v1.x, p) + se_in_x(v1.z, p);
+          s2 += se_in_y(v0.y, p) + se_in_y(v0.w, p) + se_in_y(v1.y, p) + se_in_y(v1.w, p);
+        }
     } else if (p.att_src == 1) {
       const int fk = f == 2 ? 1 : 0;                  // flow plane of this frame
       const int n4 = hw / 2;                          // one load = 2 pixels
@@ -363,7 +370,9 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     if (p.att_src == 6 && f == 1 && threadIdx.x >= kNumClasses)      // mean of a constant map: the target's zero flow
       a = threadIdx.x == kNumClasses ? se_in_x(0.f, p) : se_in_y(0.f, p);
     if (p.att_src == 4) a = a * (1.0f / 255.0f) * 2.0f - 1.0f;
-    if (p.att_src == 5 && p.depth_norm == 1) a = a / 80.0f;
+    if (p.att_src == 5 && p.depth_norm == 1 && threadIdx.x == 0) a = a / 80.0f;
+    if (p.att_src == 5 && f == 1 && threadIdx.x >= 1)                // depth + flow sources: the target's zero flow
+      a = threadIdx.x == 1 ? se_in_x(0.f, p) : se_in_y(0.f, p);
     s_pool[threadIdx.x] = a;
   }
   __syncthreads();
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
     const float tr0 = img_norm(pt[0]), tg0 = img_norm(pt[1]), tb0 = img_norm(pt[2]);
     const float sr0 = img_norm(ps[0]), sg0 = img_norm(ps[1]), sb0 = img_norm(ps[2]);
     float2 fl = make_float2(0.f, 0.f);
-    if (p.in_mode == 1 || (p.pixel_map && p.att_src == 6)) fl = flow1_at(p, b, k, pix, hw);
+    if (p.in_mode == 1 || (p.pixel_map && p.att_src == 6) || p.pixel_map == 2) fl = flow1_at(p, b, k, pix, hw);
     float a_src = 1.0f, a_tgt = 1.0f;
     if (p.pixel_map) {
       // the map is reduce_sum(SE input * excitation) at the pixel (attention_module.py:51 + davo.py:1230, 1295, 1377)
@@ -542,6 +551,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
         const float xt = p.depth_norm == 2 ? 1.0f / dt : p.depth_norm == 1 ? (dt + dt) / 80.0f : dt + dt;
         a_src = xs * s_w[0];
         if (!p.att_tgt_ones) a_tgt = xt * s_wt[0];
+        if (p.pixel_map == 2) {                                  // concat(depth term, SE flow): three channels
+          a_src += se_in_x(fl.x, p) * s_w[1] + se_in_y(fl.y, p) * s_w[2];
+          if (!p.att_tgt_ones) a_tgt += se_in_x(0.f, p) * s_wt[1] + se_in_y(0.f, p) * s_wt[2];
+        }
       } else {                                                   // se_block(concat(one_hot(label), SE flow)): 19 + 2 channels
         const int lab = label_at(p, seg_src, pix);
         a_src = ((lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f) + se_in_x(fl.x, p) * s_w[kNumClasses] +

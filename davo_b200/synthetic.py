@@ -123,6 +123,8 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         scope, din, dh = se_scopes[cfg.att_src]
         if cfg.att_src == V.ATT_SE_DEPTH_SEG and cfg.depth_norm == 2:
             scope = "se_disp"                            # se(1. / depth, "se_disp", ...) (davo.py:1257)
+        if cfg.att_src == V.ATT_SE_DEPTH_SEG and cfg.pixel_map == 2:
+            scope, din = ("se_dispflow" if cfg.depth_norm == 2 else "se_depthflow"), 3     # davo.py:1161, 1171
         if cfg.att_src == V.ATT_SE_SEG and cfg.se_pool in V.SPP_SIZES:
             scope = "se_spp_seg"                         # se_spp_block(seg_19, "se_spp_seg", ...) (davo.py:1326)
         if cfg.se_pool == 1:

@@ -36,7 +36,7 @@ SPP_SIZES = {SE_POOL_SPP21: (2, 1), SE_POOL_SPP2: (2,), SE_POOL_SPP864: (8, 6, 4
 # (davo.py:1117-1383), in the reference's evaluation order.
 _UNBUILT_SOURCES = (
     "-se_flow_on_depthseg_sharedlayers", "-se_flow_on_depthseg_seplayers",
-    "-se_flow_on_depthseg", "-se_mixDepthFlow", "-se_mixDispFlow",
+    "-se_flow_on_depthseg",
 )
 _UNBUILT_AFTER_SE_FLOW = (
     "-se_depth_wo_tgt_to_seg", "-se_depth_to_seg",
@@ -184,7 +184,14 @@ def parse_version(version: str) -> DavoConfig:
     for tok in _UNBUILT_SOURCES:
         if tok in version:
             raise NotImplementedError("davo_b200: attention source %s is not built" % tok)
-    if "-se_flow" in version:                                   # davo.py:1175
+    if "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:           # davo.py:1157-1174
+        # se_block(concat(depth term, SE flow), "se_depthflow" | "se_dispflow", ratio=1): a per-pixel map of 3 channels
+        if cfg.posenn >= POSENN_DECOUPLE_DIL:
+            raise NotImplementedError("davo_b200: the depth + flow attention sources are built for the -sharedNN nets only")
+        cfg.att_src, cfg.att_tgt_ones, cfg.pixel_map = ATT_SE_DEPTH_SEG, 0, 2
+        if "-se_mixDepthFlow" not in version:
+            cfg.depth_norm = 2                                   # 1. / depth (davo.py:1167), whatever -norm_depth says
+    elif "-se_flow" in version:                                   # davo.py:1175
         cfg.att_src = ATT_SE_FLOW
         cfg.att_tgt_ones = 1                                    # davo.py:1404-1412
     elif "-se_gp2x2_flow_nobottle" in version or "-se_gp2x2_flow" in version:     # davo.py:1181-1192

@@ -65,7 +65,8 @@ typedef struct davo_config {
   int32_t pixel_map;     /* 1: the se_block sources whose map is reduce_sum(input * excitation) per pixel rather
                             than a class weight gathered by label: att_src 4 -se_rgb[_wo_tgt] (davo.py:1293-1303),
                             5 -se_depth[_wo_tgt] / -se_disp[_wo_tgt] (:1228-1245, 1271-1292), 6 -se_mixSegFlow
-                            (:1375-1379); shared nets only                                           */
+                            (:1375-1379); 2 (att_src 5 only): depth term AND SE flow, -se_mixDepthFlow /
+                            -se_mixDispFlow (:1157-1174); shared nets only                           */
 } davo_config;
 
 /* Stands in for DAVO.__init__ + DAVO.setup_inference (reference davo.py:31-33,

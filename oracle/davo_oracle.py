@@ -412,8 +412,20 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
     # 3.5 attention maps (davo.py:1114-1400)
     use_se_flow = False
     att_w = None
-    if "-se_flow_on_depthseg" in version or "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:
-        _unsupported("depth/mix attention")
+    if "-se_flow_on_depthseg" in version:
+        _unsupported("depth-split attention")
+    elif "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:  # davo.py:1157-1174
+        dp = torch.as_tensor(depth).to(dtype)
+        pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]
+        if "-se_mixDepthFlow" in version:
+            terms = [d + pred_depths[0] for d in pred_depths]            # davo.py:1109
+            if "-norm_depth" in version:
+                terms = [d / 80.0 for d in terms]
+            scope = "pose_exp_net/se_depthflow"
+        else:
+            terms = [1.0 / d for d in pred_depths]                       # davo.py:1167
+            scope = "pose_exp_net/se_dispflow"
+        att = [se_block(torch.cat([terms[i], se_in[i]], dim=-1), wts, scope, act).sum(-1, keepdim=True) for i in range(3)]
     elif "-se_flow" in version:                                          # davo.py:1175-1180
         att, att_w = [], []
         for i in range(3):

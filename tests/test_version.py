@@ -75,6 +75,10 @@ def test_per_pixel_sources():
         c = V.parse_version(BASE + "-segmask_all" + tok)
         assert (c.att_src, c.att_tgt_ones, c.pixel_map, c.depth_norm) == (att, tgt1, 1, dn), tok
     assert V.parse_version(BASE + "-segmask_all-se_rgb_to_seg").pixel_map == 0
+    c = V.parse_version(BASE + "-segmask_all-se_mixDepthFlow-norm_depth")            # davo.py:1157-1165
+    assert (c.att_src, c.att_tgt_ones, c.pixel_map, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 0, 2, 1, 1)
+    c = V.parse_version(BASE + "-segmask_all-se_mixDispFlow-norm_depth")             # davo.py:1166-1174
+    assert (c.att_src, c.att_tgt_ones, c.pixel_map, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 0, 2, 2, 1)
     with pytest.raises(NotImplementedError, match="sharedNN"):
         V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_rgb")
 
@@ -127,7 +131,7 @@ def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_mixDepthFlow", "-se_mixDispFlow", "-se_spp21_mixSegFlow", "-se_flow_on_depthseg_seplayers"])
+@pytest.mark.parametrize("tok", ["-se_spp21_mixSegFlow", "-se_flow_on_depthseg_seplayers"])
 def test_unbuilt_sources_fail_loudly(tok):
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
@@ -135,7 +139,7 @@ def test_unbuilt_sources_fail_loudly(tok):
 
 def test_depth_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all-se_mixDepthFlow-fc_tanh")
+        V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg_seplayers-fc_tanh")
     c = V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-norm_depth-fc_tanh")     # davo.py:1211-1219
     assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 1, 1, 1)
     assert V.parse_version(BASE + "-segmask_all-se_depth_to_seg").att_tgt_ones == 0
