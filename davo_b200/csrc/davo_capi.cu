@@ -261,6 +261,7 @@ struct davo_ctx {
   // Function attributes are per device: what this context has already raised, by kernel.
   std::map<const void*, int> smem_attr;
   std::map<std::pair<const void*, int>, int> max_clusters;   // by (kernel, dynamic shared memory)
+  float depth_thres = 0.f;          // -se_flow_on_depthseg_seplayers: the variable se_flow/depth_threshold
   // mode='feature' (features.cuh)
   float* d_wheel = nullptr;         // Middlebury colour wheel / 255
   unsigned int* d_maxrad = nullptr; // largest flow magnitude per source frame
@@ -1046,6 +1047,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     fp.se_in = se_dims[c.att_src][0]; fp.se_hid = c.se_hidden > 0 ? c.se_hidden : se_dims[c.att_src][1];
     fp.se_out = kNumClasses;
     fp.pixel_map = c.pixel_map;
+    fp.depth_split = c.depth_split; fp.depth_thres = ctx->depth_thres;
     if (c.pixel_map == 2) fp.se_in = 3;                    // depth term, SE flow x, SE flow y
     if (c.pixel_map) fp.se_hid = fp.se_out = fp.se_in;     // se_block(..., ratio=1): channel -> channel -> channel
     fp.pool_2x2 = c.se_pool == 1 ? 1 : 0;
@@ -1062,7 +1064,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
         return rc;
     } else if (c.att_src == 1 && c.se_pool >= 2) {
       if (int rc = launch_k(ctx, se_spp_kernel, dim3(npairs, src_frames), dim3(256), 0, st, false, fp)) return rc;
-    } else if (int rc = launch_k(ctx, se_pool_kernel, dim3(kPoolSplits, npairs, src_frames + (c.att_tgt_ones ? 0 : 1)),
+    } else if (int rc = launch_k(ctx, se_pool_kernel, dim3(kPoolSplits, npairs, c.depth_split ? 2 : src_frames + (c.att_tgt_ones ? 0 : 1)),
                                  dim3(256), 0, st, false, fp)) {
       return rc;
     }
@@ -1155,6 +1157,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad se_pool / se_hidden");
   if (cfg->se_pool >= 2 && (cfg->H > cfg->W || (cfg->att_src == 1 && !cfg->att_tgt_ones)))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: the pyramid pooling is built for H <= W (and, on the flow, a target map of ones)");
+  if (cfg->depth_split != 0 && (cfg->depth_split != 1 || cfg->att_src != 1 || cfg->se_pool != 0 || cfg->posenn > 1 || !cfg->att_tgt_ones))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: depth_split needs att_src 1 with global pooling, a target map of ones and a shared net");
   if (cfg->pixel_map != 0 && (cfg->pixel_map < 1 || cfg->pixel_map > 2 || (cfg->pixel_map == 2 && cfg->att_src != 5) ||
                               cfg->att_src < 4 || cfg->att_src > 6 || cfg->posenn > 1 || cfg->se_pool != 0))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: per-pixel maps are built for att_src 4..6, global pooling and the shared nets");
@@ -1220,7 +1224,7 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
 extern "C" int davo_set_weight(davo_ctx* ctx, const char* name, const float* host,
                                const int64_t* shape, int rank) {
   if (!ctx) return DAVO_ERR_ARG;
-  if (!name || !host || !shape || rank < 1 || rank > 4) return fail(ctx, DAVO_ERR_ARG, "davo_set_weight: bad argument");
+  if (!name || !host || (!shape && rank > 0) || rank < 0 || rank > 4) return fail(ctx, DAVO_ERR_ARG, "davo_set_weight: bad argument");   // rank 0: a scalar variable
   if (ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_set_weight: weights already finalized");
   HostTensor t;
   size_t n = 1;
@@ -1268,7 +1272,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   // column-widened cnv1 plan (runs of 16 input pixels), else the 16-channel layout of the plain plan.
   const char* wide_env0 = getenv("DAVO_B200_WIDE");
   // (the per-pixel attention maps are computed by the 16-channel pack_kernel only)
-  ctx->packed_c = (!ctx->unit_sample && !c.pixel_map && (c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
+  ctx->packed_c = (!ctx->unit_sample && !c.pixel_map && !c.depth_split && (c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
   const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? nbr * 256 : 256, nbr * c7in};
   const int cin_g[7] = {ctx->packed_c, 16, 32, 64, 128, 256, c7in};
   const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c7in};
@@ -1484,17 +1488,27 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 * cells[c.se_pool] : c.att_src == 4 ? 3 : c.att_src == 5 ? (c.pixel_map == 2 ? 3 : 1) : 21;
     const int dh = c.pixel_map ? din : c.se_hidden > 0 ? c.se_hidden : ((c.att_src == 3 || c.att_src == 6) ? 19 : 8);
     const int dout = c.pixel_map ? din : 19;
-    const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
-    const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
-    const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
-    const HostTensor* b2 = find_w(ctx, S + "recover_fc/bias");
-    if (!shape_is(w1, {din, dh}) || !shape_is(b1, {dh}) || !shape_is(w2, {dh, dout}) || !shape_is(b2, {dout}))
-      return fail(ctx, DAVO_ERR_WEIGHT, "missing or mis-shaped %s{bottleneck_fc,recover_fc}/{kernel,bias}", S.c_str());
+    // depth_split: the two SEs "se_flow_near", "se_flow_far" (davo.py:1150) one after the other, and the threshold
+    std::vector<std::string> scopes = {S};
+    if (c.depth_split) scopes = {P + "se_flow_near/", P + "se_flow_far/"};
     std::vector<float> se;
-    se.insert(se.end(), w1->data.begin(), w1->data.end());
-    se.insert(se.end(), b1->data.begin(), b1->data.end());
-    se.insert(se.end(), w2->data.begin(), w2->data.end());
-    se.insert(se.end(), b2->data.begin(), b2->data.end());
+    for (const std::string& sc : scopes) {
+      const HostTensor* w1 = find_w(ctx, sc + "bottleneck_fc/kernel");
+      const HostTensor* b1 = find_w(ctx, sc + "bottleneck_fc/bias");
+      const HostTensor* w2 = find_w(ctx, sc + "recover_fc/kernel");
+      const HostTensor* b2 = find_w(ctx, sc + "recover_fc/bias");
+      if (!shape_is(w1, {din, dh}) || !shape_is(b1, {dh}) || !shape_is(w2, {dh, dout}) || !shape_is(b2, {dout}))
+        return fail(ctx, DAVO_ERR_WEIGHT, "missing or mis-shaped %s{bottleneck_fc,recover_fc}/{kernel,bias}", sc.c_str());
+      se.insert(se.end(), w1->data.begin(), w1->data.end());
+      se.insert(se.end(), b1->data.begin(), b1->data.end());
+      se.insert(se.end(), w2->data.begin(), w2->data.end());
+      se.insert(se.end(), b2->data.begin(), b2->data.end());
+    }
+    if (c.depth_split) {
+      const HostTensor* th = find_w(ctx, P + "se_flow/depth_threshold");
+      if (!th || th->data.size() != 1) return fail(ctx, DAVO_ERR_WEIGHT, "missing scalar variable %sse_flow/depth_threshold", P.c_str());
+      ctx->depth_thres = th->data[0];
+    }
     CU_OK(cudaMemcpy(ctx->d_sew, se.data(), se.size() * 4, cudaMemcpyHostToDevice));
   } else if (c.att_src == 2) {
     // reference posenn.py:380-394 -- variable is double-scoped by davo.py:1392 inside :1114
@@ -1520,7 +1534,7 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
   if (!ctx) return DAVO_ERR_ARG;
   if (pairs < DAVO_PAIRS_ALL || pairs > DAVO_PAIRS_TRAJECTORY_FIRST)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward: pair selection %d unknown", pairs);
-  if (ctx->cfg.att_src == 5 && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward: this variant reads input_depth; got NULL");
+  if ((ctx->cfg.att_src == 5 || ctx->cfg.depth_split) && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward: this variant reads input_depth; got NULL");
   ctx->cur_depth = depth;
   ctx->cur_seg8 = nullptr;
   ctx->cur_flow16 = nullptr; ctx->cur_n16 = 0;
@@ -1564,7 +1578,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
   if (!ctx) return DAVO_ERR_ARG;
   if (pairs < DAVO_PAIRS_ALL || pairs > DAVO_PAIRS_TRAJECTORY_FIRST)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: pair selection %d unknown", pairs);
-  if (ctx->cfg.att_src == 5 && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: this variant reads input_depth; got NULL");
+  if ((ctx->cfg.att_src == 5 || ctx->cfg.depth_split) && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: this variant reads input_depth; got NULL");
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: B=%d outside 1..%d", B, ctx->cfg.max_batch);
   const davo_config& c = ctx->cfg;
@@ -1589,7 +1603,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
       CU_OK(cudaMalloc((void**)&ctx->s_seg[i], n_seg * 4 * cs));
       CU_OK(cudaMemset(ctx->s_flow[i], 0, n_flow * 4 * cs));
       CU_OK(cudaMemset(ctx->s_seg[i], 0, n_seg * 4 * cs));
-      if (c.att_src == 5) CU_OK(cudaMalloc((void**)&ctx->s_depth[i], n_seg * 4 * cs));
+      if (c.att_src == 5 || c.depth_split) CU_OK(cudaMalloc((void**)&ctx->s_depth[i], n_seg * 4 * cs));
       if (ctx->host_seg8 && c.att_src != 0) {
         CU_OK(cudaMalloc((void**)&ctx->s_seg8[i], n_seg * cs));
         CU_OK(cudaHostAlloc((void**)&ctx->h_seg8[i], n_seg * cs, cudaHostAllocDefault));
@@ -1725,7 +1739,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
         h2d += hw * 4 * 2 * ns;
       }
     }
-    if (c.att_src == 5) {       // se_depth: all three planes (the frame's and the target's are pooled)
+    if (c.att_src == 5 || c.depth_split) {       // depth sources: all three planes (the frame's and the target's are read)
       CU_OK(cudaMemcpyAsync(ctx->s_depth[buf], depth + n_seg * s0, n_seg * 4 * ns, cudaMemcpyHostToDevice, cp));
       h2d += n_seg * 4 * ns;
     }
@@ -1973,7 +1987,8 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
   const int units = ctx->unit_sample ? B : 2 * B;
   if (ctx->finalized && units > ctx->mb)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: B=%d needs %d units, one pass holds %d", B, units, ctx->mb);
-  if (ctx->cfg.pixel_map) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: not built for the per-pixel attention sources");
+  if (ctx->cfg.pixel_map || ctx->cfg.depth_split)
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: not built for the per-pixel and depth-split attention sources");
   if ((out->flow_color) && !flow) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: flow colouring needs input_flow");
   if ((out->seg_19 || out->seg_color) && !seg) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: label outputs need input_seglabel");
   if (int rc = davo_forward_pairs(ctx, B, DAVO_PAIRS_ALL, img, flow, seg, depth, pose_out, stream)) return rc;

@@ -62,6 +62,8 @@ struct FrontParams {
   int spp_levels;        // se_flow only: mode='spp' (attention_module.py:79-86, 137-167): pyramid levels ...
   int spp_n[3];          // ... and their out_pool_size; se_spp_kernel replaces se_pool_kernel
   int se_in, se_hid;     // SE dense sizes: in -> hid -> se_out (flow 2,8; seg 19,19; rgb 3,8)
+  int depth_split;       // 1: -se_flow_on_depthseg_seplayers (davo.py:1136-1154): slot 0 / 1 of a pair hold the class weights of
+  float depth_thres;     //    SE "se_flow_near" / "se_flow_far" on the SOURCE flow; a pixel reads slot 0 where depth < depth_thres
   int se_out;            // 19 class weights, or with pixel_map the excitation of the SE input itself (= se_in)
   int pixel_map;         // 1 (2: with att_src 5, depth term AND SE flow, -se_mixDepthFlow / -se_mixDispFlow, davo.py:1157-1174):
                          //    se_block sources whose map is reduce_sum(input * excitation) per pixel instead of a
@@ -162,7 +164,8 @@ __device__ __forceinline__ float se_activation(float v, int act) {
 __device__ __forceinline__ void se_dense_layers(const FrontParams& p, const float* s_pool, float* s_fc1, int D,
                                                 int pl, int fr) {
   const int Hd = p.se_hid;
-  const float* W1 = p.se_w;
+  // depth_split: slot fr uses its own weight set (near, far), stored one after the other
+  const float* W1 = p.se_w + (p.depth_split ? fr * (D * Hd + Hd + Hd * p.se_out + p.se_out) : 0);
   const float* b1 = W1 + D * Hd;
   const float* W2 = b1 + Hd;
   const int out = p.se_out;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
   const int D = p.se_in;
-  const int f = unit_frame(p.unit_sample, k, fr);
+  const int f = unit_frame(p.unit_sample, k, p.depth_split ? 0 : fr);     // depth_split: both slots pool the source flow
   __shared__ float red[8][4];
   __shared__ int s_hist[kNumClasses];
   __shared__ float s_pool[kPoolDim];
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
     const float st = threadIdx.x < kNumClasses ? p.static_w[threadIdx.x] : 0.0f;
     s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * kAttFrames + 0) * kAttStride + threadIdx.x]
                      : p.att_src == 2 ? st : 1.0f;
-    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * kAttFrames + 1) * kAttStride + threadIdx.x]
+    s_wt[threadIdx.x] = (se && (!p.att_tgt_ones || p.depth_split)) ? p.att_w[((size_t)pl * kAttFrames + 1) * kAttStride + threadIdx.x]
                       : p.att_src == 2 ? st : 1.0f;
   }
   __syncthreads();
@@ -565,6 +568,11 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
                   se_in_y(0.f, p) * s_wt[kNumClasses + 1];
         }
       }
+    } else if (p.depth_split) {
+      // near / far tables (slot 0 / slot 1) chosen by the source frame's depth (davo.py:1143-1152); target map = 1
+      const int lab = label_at(p, seg_src, pix);
+      const float ds = __ldg(p.depth + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw + pix);
+      a_src = (lab >= 0 && lab < kNumClasses) ? (ds < p.depth_thres ? s_w[lab] : s_wt[lab]) : 0.0f;
     } else if (p.att_src != 0) {
       const int lab = label_at(p, seg_src, pix);                 // tf.cast truncates toward zero
       a_src = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;  // one_hot: out of range -> 0

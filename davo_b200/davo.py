@@ -74,7 +74,8 @@ class DAVO(object):
             mask_mode=self.config.mask_mode, se_act=self.config.se_act,
             flow_abs=self.config.flow_abs, flow_norm=self.config.flow_norm,
             posenn_se=self.config.posenn_se, micro_batch=micro_batch, depth_norm=self.config.depth_norm,
-            se_pool=self.config.se_pool, se_hidden=self.config.se_hidden, pixel_map=self.config.pixel_map)
+            se_pool=self.config.se_pool, se_hidden=self.config.se_hidden, pixel_map=self.config.pixel_map,
+            depth_split=self.config.depth_split)
         h = C.c_void_p()
         rc = self._lib.davo_create(C.byref(cfg), self.device, C.byref(h))
         if rc != 0:
@@ -144,8 +145,8 @@ class DAVO(object):
             img, flow, seg, depth = inputs
         else:
             img, flow, seg = inputs
-        if self.config.att_src != V.ATT_SE_DEPTH_SEG:
-            depth = None                                  # only the se_depth sources read it
+        if self.config.att_src != V.ATT_SE_DEPTH_SEG and not self.config.depth_split:
+            depth = None                                  # only the depth sources read it
         elif depth is None:
             raise ValueError("DAVO.inference: version %r reads input_depth [B,3,H,W,1]" % (self.version,))
         B = int(img.shape[0])

@@ -140,6 +140,16 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
             std = math.sqrt(1.3 * 2.0 / fi)
             w["pose_exp_net/%s/%s/kernel" % (scope, name)] = _trunc_normal(rng, (fi, fo), std)
             w["pose_exp_net/%s/%s/bias" % (scope, name)] = bias(fo)
+    if cfg.depth_split:
+        # davo.py:1137-1140, 1150: two SEs instead of se_flow, and the threshold variable N(15 | the token's number, 0.1)
+        for name in ("bottleneck_fc", "recover_fc"):
+            for leaf in ("kernel", "bias"):
+                t = w.pop("pose_exp_net/se_flow/%s/%s" % (name, leaf))
+                w["pose_exp_net/se_flow_near/%s/%s" % (name, leaf)] = t
+                w["pose_exp_net/se_flow_far/%s/%s" % (name, leaf)] = (
+                    _trunc_normal(rng, t.shape, math.sqrt(1.3 * 2.0 / t.shape[0])) if leaf == "kernel" else bias(t.shape[0]))
+        m = __import__("re").search("-se_flow_on_depthseg_.*layers_([0-9.]+)", version)
+        w["pose_exp_net/se_flow/depth_threshold"] = np.float32(rng.normal(15.0 if m is None else float(m.group(1)), 0.1))
     if cfg.att_src == V.ATT_STATIC:
         # double scope is the reference's: prefix "pose_exp_net/" inside scope pose_exp_net
         w["pose_exp_net/pose_exp_net/seg_channel_weight/weight"] = \

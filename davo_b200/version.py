@@ -34,10 +34,7 @@ SPP_SIZES = {SE_POOL_SPP21: (2, 1), SE_POOL_SPP2: (2,), SE_POOL_SPP864: (8, 6, 4
 
 # Attention sources of the reference chain that this build does not implement
 # (davo.py:1117-1383), in the reference's evaluation order.
-_UNBUILT_SOURCES = (
-    "-se_flow_on_depthseg_sharedlayers", "-se_flow_on_depthseg_seplayers",
-    "-se_flow_on_depthseg",
-)
+_UNBUILT_SOURCES = ()
 _UNBUILT_AFTER_SE_FLOW = (
     "-se_depth_wo_tgt_to_seg", "-se_depth_to_seg",
     "-se_depth_wo_tgt", "-se_depth", "-se_disp_wo_tgt_to_seg", "-se_disp_to_seg",
@@ -100,6 +97,7 @@ class DavoConfig:
     posenn_se: int = PSE_NONE
     depth_norm: int = 0         # "-norm_depth" (davo.py:1108-1111); only read by the se_depth sources
     se_pool: int = 0            # se_flow: SE_POOL_* (davo.py:1175-1210)
+    depth_split: int = 0        # 1: -se_flow_on_depthseg_seplayers: near / far class-weight tables split by a learned depth threshold
     pixel_map: int = 0          # 1: map = reduce_sum(SE input * excitation) per pixel (-se_rgb, -se_depth, -se_disp, -se_mixSegFlow)
     se_hidden: int = 0          # SE bottleneck width, 0 = default (8; se_seg 19); gp2x2_flow_nobottle: 19
     needs_depth: int = 0        # "depth"/"disp" in the version: the graph reads input_depth (davo.py:960)
@@ -184,7 +182,13 @@ def parse_version(version: str) -> DavoConfig:
     for tok in _UNBUILT_SOURCES:
         if tok in version:
             raise NotImplementedError("davo_b200: attention source %s is not built" % tok)
-    if "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:           # davo.py:1157-1174
+    if "-se_flow_on_depthseg_seplayers" in version:                             # davo.py:1136-1154
+        # se(flow, "se_flow_near" | "se_flow_far", [8,19]) applied to the labels of the pixels nearer / farther than
+        # the variable se_flow/depth_threshold; everything lives under pose_exp_net/se_flow*, so the target map is ones
+        if cfg.posenn >= POSENN_DECOUPLE_DIL:
+            raise NotImplementedError("davo_b200: -se_flow_on_depthseg_seplayers is built for the -sharedNN nets only")
+        cfg.att_src, cfg.att_tgt_ones, cfg.depth_split = ATT_SE_FLOW, 1, 1
+    elif "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:         # davo.py:1157-1174
         # se_block(concat(depth term, SE flow), "se_depthflow" | "se_dispflow", ratio=1): a per-pixel map of 3 channels
         if cfg.posenn >= POSENN_DECOUPLE_DIL:
             raise NotImplementedError("davo_b200: the depth + flow attention sources are built for the -sharedNN nets only")

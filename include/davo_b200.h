@@ -67,6 +67,10 @@ typedef struct davo_config {
                             5 -se_depth[_wo_tgt] / -se_disp[_wo_tgt] (:1228-1245, 1271-1292), 6 -se_mixSegFlow
                             (:1375-1379); 2 (att_src 5 only): depth term AND SE flow, -se_mixDepthFlow /
                             -se_mixDispFlow (:1157-1174); shared nets only                           */
+  int32_t depth_split;   /* 1: -se_flow_on_depthseg_seplayers (davo.py:1136-1154), att_src 1 only: two SEs on the flow,
+                            "se_flow_near" / "se_flow_far"; a pixel takes its class weight from the near table where
+                            its depth is below the variable se_flow/depth_threshold, else from the far table; reads
+                            input_depth; shared nets only                                            */
 } davo_config;
 
 /* Stands in for DAVO.__init__ + DAVO.setup_inference (reference davo.py:31-33,
@@ -75,7 +79,7 @@ int davo_create(const davo_config* cfg, int device, davo_ctx** out);
 
 /* Stands in for tf.train.Saver(...).restore (reference test_kitti_pose.py:129-131),
  * one variable at a time, keyed by TF variable name.  Conv kernels are HWIO,
- * dense kernels [in, out], as TF stores them.  `host` is host memory. */
+ * dense kernels [in, out], as TF stores them; rank 0 is a scalar variable.  `host` is host memory. */
 int davo_set_weight(davo_ctx*, const char* tf_var_name, const float* host,
                     const int64_t* shape, int rank);
 

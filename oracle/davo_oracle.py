@@ -412,7 +412,18 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
     # 3.5 attention maps (davo.py:1114-1400)
     use_se_flow = False
     att_w = None
-    if "-se_flow_on_depthseg" in version:
+    if "-se_flow_on_depthseg_seplayers" in version:                      # davo.py:1136-1154
+        dp = torch.as_tensor(depth).to(dtype)
+        pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]
+        thres = wts["pose_exp_net/se_flow/depth_threshold"]
+        att = []
+        for i in range(3):
+            near = (pred_depths[i] < thres).to(dtype)                    # :1143
+            w_near = se_weights(se_in[i], wts, "pose_exp_net/se_flow_near", act)
+            w_far = se_weights(se_in[i], wts, "pose_exp_net/se_flow_far", act)
+            att.append(class_gather(pred_segs[i], w_near) * near + class_gather(pred_segs[i], w_far) * (near - 1.0) * (-1.0))
+        use_se_flow = True                               # the variables live under pose_exp_net/se_flow* (davo.py:1404)
+    elif "-se_flow_on_depthseg" in version:
         _unsupported("depth-split attention")
     elif "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:  # davo.py:1157-1174
         dp = torch.as_tensor(depth).to(dtype)

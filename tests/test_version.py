@@ -131,7 +131,7 @@ def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_spp21_mixSegFlow", "-se_flow_on_depthseg_seplayers"])
+@pytest.mark.parametrize("tok", ["-se_spp21_mixSegFlow"])
 def test_unbuilt_sources_fail_loudly(tok):
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
@@ -139,7 +139,7 @@ def test_unbuilt_sources_fail_loudly(tok):
 
 def test_depth_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg_seplayers-fc_tanh")
+        V.parse_version(BASE + "-segmask_all-se_spp21_mixSegFlow-fc_tanh")
     c = V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-norm_depth-fc_tanh")     # davo.py:1211-1219
     assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 1, 1, 1)
     assert V.parse_version(BASE + "-segmask_all-se_depth_to_seg").att_tgt_ones == 0
@@ -155,11 +155,11 @@ def test_seglabelid_fails_the_way_the_reference_graph_does():
 
 def test_depthseg_tokens_fail_the_way_the_reference_does():
     """davo.py:1117-1156: `_sharedlayers` reads depth_thres before assignment (:1119); the bare token raises the
-    reference's NameError (:1155-1156); `_seplayers` is a real source that this build does not have."""
+    reference's NameError (:1155-1156); `_seplayers` is built."""
     with pytest.raises(UnboundLocalError, match="depth_thres"):
         V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg_sharedlayers_15")
     with pytest.raises(NameError, match="please select"):
         V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg")
-    with pytest.raises(NotImplementedError, match="seplayers"):
-        V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg_seplayers_15")
+    c = V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg_seplayers_15")       # davo.py:1136-1154
+    assert (c.att_src, c.att_tgt_ones, c.depth_split, c.needs_depth) == (V.ATT_SE_FLOW, 1, 1, 1)
 
