@@ -1059,7 +1059,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
       fp.spp_levels = sz[0];
       for (int i = 0; i < sz[0]; ++i) fp.spp_n[i] = sz[1 + i];
     }
-    if (c.att_src == 3 && c.se_pool != 0) {       // cell-wise class frequencies of the label map
+    if ((c.att_src == 3 || c.att_src == 6) && c.se_pool != 0) {   // cell-wise class frequencies of the label map (+ flow means)
       if (int rc = launch_k(ctx, se_segcells_kernel, dim3(npairs, src_frames + (c.att_tgt_ones ? 0 : 1)), dim3(256), 0, st, false, fp))
         return rc;
     } else if (c.att_src == 1 && c.se_pool >= 2) {
@@ -1153,14 +1153,14 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
   if (cfg->att_src < 0 || cfg->att_src > 6) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
   if (cfg->se_pool < 0 || cfg->se_pool > 4 || cfg->se_hidden < 0 || cfg->se_hidden > 19 ||
-      (cfg->se_pool != 0 && cfg->att_src != 1 && cfg->att_src != 3))
+      (cfg->se_pool != 0 && cfg->att_src != 1 && cfg->att_src != 3 && !(cfg->att_src == 6 && cfg->pixel_map == 1 && cfg->se_pool == 2)))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad se_pool / se_hidden");
   if (cfg->se_pool >= 2 && (cfg->H > cfg->W || (cfg->att_src == 1 && !cfg->att_tgt_ones)))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: the pyramid pooling is built for H <= W (and, on the flow, a target map of ones)");
   if (cfg->depth_split != 0 && (cfg->depth_split != 1 || cfg->att_src != 1 || cfg->se_pool != 0 || cfg->posenn > 1 || !cfg->att_tgt_ones))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: depth_split needs att_src 1 with global pooling, a target map of ones and a shared net");
   if (cfg->pixel_map != 0 && (cfg->pixel_map < 1 || cfg->pixel_map > 2 || (cfg->pixel_map == 2 && cfg->att_src != 5) ||
-                              cfg->att_src < 4 || cfg->att_src > 6 || cfg->posenn > 1 || cfg->se_pool != 0))
+                              cfg->att_src < 4 || cfg->att_src > 6 || cfg->posenn > 1 || (cfg->se_pool != 0 && cfg->att_src != 6)))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: per-pixel maps are built for att_src 4..6, global pooling and the shared nets");
   if (cfg->att_src == 5 && ((cfg->H * cfg->W) % 4) != 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: se_depth needs H*W % 4 == 0");
   int ndev = 0;
@@ -1482,12 +1482,13 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_staticw, kNumClasses * 4)) return rc;
   if (c.att_src == 1 || c.att_src >= 3) {
     // se(flow|rgb, [8,19]) (attention_module.py:54-103) or se_block(seg_19, ratio=1) (:9-52)
-    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? (c.se_pool >= 2 ? "se_spp_seg/" : "se_seg/") : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? (c.pixel_map == 2 ? (c.depth_norm == 2 ? "se_dispflow/" : "se_depthflow/") : c.depth_norm == 2 ? "se_disp/" : "se_depth/") : "se_segflow/");
+    const std::string S = P + (c.att_src == 1 ? "se_flow/" : c.att_src == 3 ? (c.se_pool >= 2 ? "se_spp_seg/" : "se_seg/") : c.att_src == 4 ? "se_rgb/" : c.att_src == 5 ? (c.pixel_map == 2 ? (c.depth_norm == 2 ? "se_dispflow/" : "se_depthflow/") : c.depth_norm == 2 ? "se_disp/" : "se_depth/") : (c.se_pool >= 2 ? "se_spp_segflow/" : "se_segflow/"));
     static const int spp_dim[5] = {2, 8, 10, 8, kSppMaxDim};      // pooled vector of se_flow by se_pool: gp, gp2x2, spp [2,1], [2], [8,6,4]
     static const int cells[5] = {1, 4, 5, 4, 116};                // pooled cells by se_pool
-    const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 * cells[c.se_pool] : c.att_src == 4 ? 3 : c.att_src == 5 ? (c.pixel_map == 2 ? 3 : 1) : 21;
-    const int dh = c.pixel_map ? din : c.se_hidden > 0 ? c.se_hidden : ((c.att_src == 3 || c.att_src == 6) ? 19 : 8);
-    const int dout = c.pixel_map ? din : 19;
+    const int din = c.att_src == 1 ? spp_dim[c.se_pool] : c.att_src == 3 ? 19 * cells[c.se_pool] : c.att_src == 4 ? 3 : c.att_src == 5 ? (c.pixel_map == 2 ? 3 : 1) : 21 * cells[c.se_pool];
+    const int chan = c.att_src == 6 ? 21 : din;             // channels of the SE input (the pooled vector may be several cells of them)
+    const int dh = c.pixel_map ? chan : c.se_hidden > 0 ? c.se_hidden : ((c.att_src == 3 || c.att_src == 6) ? 19 : 8);
+    const int dout = c.pixel_map ? chan : 19;
     // depth_split: the two SEs "se_flow_near", "se_flow_far" (davo.py:1150) one after the other, and the threshold
     std::vector<std::string> scopes = {S};
     if (c.depth_split) scopes = {P + "se_flow_near/", P + "se_flow_far/"};

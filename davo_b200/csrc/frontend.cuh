@@ -454,6 +454,9 @@ __global__ void __launch_bounds__(256) se_segcells_kernel(const FrontParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int cell0 = 0;
   const int levels = p.pool_2x2 ? 1 : p.spp_levels;
+  // -se_spp21_mixSegFlow (davo.py:1380-1383): the pooled map is concat(one_hot(label), SE flow): 19 + 2 values per cell
+  const bool with_flow = p.att_src == 6;
+  const int cs = with_flow ? kNumClasses + 2 : kNumClasses;
   for (int lv = 0; lv < levels; ++lv) {
     const int n = p.pool_2x2 ? 2 : p.spp_n[lv];
     const int hs = (p.H + n - 1) / n, ws = (p.W + n - 1) / n;
@@ -471,21 +474,38 @@ __global__ void __launch_bounds__(256) se_segcells_kernel(const FrontParams p) {
       }
       if (lane < kNumClasses) s_hist[warp][lane] = 0;
       __syncwarp();
+      float sx = 0.f, sy = 0.f;
       for (int i = lane; i < ch * cw; i += 32) {
         const int y = y0 + i / cw, x = x0 + i % cw;
         if (y < p.H && x < p.W) {                       // beyond the map: tf.pad zeros (an all-zero one-hot row)
           const int lab = label_at(p, seg_off, y * p.W + x);
           if (lab >= 0 && lab < kNumClasses) atomicAdd(&s_hist[warp][lab], 1);
+          if (with_flow) {                              // the target's flow is zeros (davo.py:979): SE input se_in(0)
+            const float2 v = f == 1 ? make_float2(0.f, 0.f) : flow1_at(p, b, f == 2 ? 1 : 0, y * p.W + x, hw);
+            sx += se_in_x(v.x, p);
+            sy += se_in_y(v.y, p);
+          }
+        }
+      }
+      if (with_flow) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          sx += __shfl_xor_sync(0xffffffffu, sx, o);
+          sy += __shfl_xor_sync(0xffffffffu, sy, o);
         }
       }
       __syncwarp();
-      if (lane < kNumClasses) s_pool[(cell0 + cell) * kNumClasses + lane] = (float)s_hist[warp][lane] * inv;
+      if (lane < kNumClasses) s_pool[(cell0 + cell) * cs + lane] = (float)s_hist[warp][lane] * inv;
+      if (with_flow && lane == 0) {
+        s_pool[(cell0 + cell) * cs + kNumClasses] = sx * inv;
+        s_pool[(cell0 + cell) * cs + kNumClasses + 1] = sy * inv;
+      }
       __syncwarp();
     }
     cell0 += n * n;
   }
   __syncthreads();
-  se_dense_layers(p, s_pool, s_fc1, cell0 * kNumClasses, pl, fr);
+  se_dense_layers(p, s_pool, s_fc1, cell0 * cs, pl, fr);
 }
 
 __device__ __forceinline__ float img_norm(uint8_t v) {

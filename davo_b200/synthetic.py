@@ -136,6 +136,9 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         dout = 19
         if cfg.pixel_map:                                # se_block(..., ratio=1): channel -> channel -> channel
             dh = dout = din
+            if cfg.att_src == V.ATT_SE_SEGFLOW_SEG and cfg.se_pool in V.SPP_SIZES:   # se_spp_block(concat(seg_19, flow), "se_spp_segflow")
+                scope, dh, dout = "se_spp_segflow", 21, 21
+                din = 21 * sum(n * n for n in V.SPP_SIZES[cfg.se_pool])
         for name, (fi, fo) in (("bottleneck_fc", (din, dh)), ("recover_fc", (dh, dout))):
             std = math.sqrt(1.3 * 2.0 / fi)
             w["pose_exp_net/%s/%s/kernel" % (scope, name)] = _trunc_normal(rng, (fi, fo), std)

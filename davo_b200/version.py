@@ -79,6 +79,7 @@ _BUILT_AFTER_SE_FLOW = {
     "-se_rgb_wo_tgt": dict(att_src=ATT_SE_RGB_SEG, att_tgt_ones=1, pixel_map=1),        # davo.py:1293-1298
     "-se_rgb": dict(att_src=ATT_SE_RGB_SEG, att_tgt_ones=0, pixel_map=1),               # davo.py:1299-1303
     "-se_mixSegFlow": dict(att_src=ATT_SE_SEGFLOW_SEG, att_tgt_ones=0, pixel_map=1),    # davo.py:1375-1379
+    "-se_spp21_mixSegFlow": dict(att_src=ATT_SE_SEGFLOW_SEG, att_tgt_ones=0, pixel_map=1, se_pool=SE_POOL_SPP21),   # davo.py:1380-1383
 }
 
 
@@ -117,7 +118,9 @@ def parse_version(version: str) -> DavoConfig:
     if "-se_insert" in version:
         cfg.posenn_se = PSE_INSERT
     elif "-se_skipadd" in version:
-        cfg.posenn_se = PSE_SKIPADD
+        # cnv6 = relu(cnv5 + se_block(cnv6)) (posenn.py:229-233) only type-checks with -cnv6_256, a width the conv
+        # kernels are not instantiated for
+        raise NotImplementedError("davo_b200: -se_skipadd is not built")
     elif "-se_replace" in version:
         cfg.posenn_se = PSE_REPLACE
     # G2 PoseNN type (davo.py:1027-1049)

@@ -459,8 +459,7 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
             att_w.append(w19)
             att.append(class_gather(pred_segs[i], w19))
         use_se_flow = True                               # variables under pose_exp_net/se_flow (davo.py:1404)
-    elif "-se_spp21_mixSegFlow" in version:                              # davo.py:1380-1383: not restated
-        _unsupported("attention source in " + version)
+
     elif "-se_depth_wo_tgt_to_seg" in version or "-se_depth_to_seg" in version:     # davo.py:1211-1227
         dp = torch.as_tensor(depth).to(dtype)
         pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]                     # davo.py:991-996: tgt, src0, src1
@@ -550,14 +549,19 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
         if "-se_SegFlow_to_seg_8_wo_tgt" in version or (                 # first match wins: davo.py:1341, 1350, 1358
                 "-se_SegFlow_to_seg_8" not in version and "-se_SegFlow_to_seg_wo_tgt" in version):
             att[0] = torch.ones_like(att[0])
-    elif "-se_mixSegFlow" in version:                                    # davo.py:1375-1379
+    elif "-se_mixSegFlow" in version or "-se_spp21_mixSegFlow" in version:   # davo.py:1375-1383
+        spp21 = "-se_mixSegFlow" not in version          # first match wins (the two tokens do not contain each other)
         att = []
         for i in range(3):
             lab = torch.trunc(pred_segs[i][..., 0]).to(torch.int64)
             onehot = torch.nn.functional.one_hot(lab.clamp(0, NUM_CLASSES - 1), NUM_CLASSES).to(dtype)
             onehot = onehot * ((lab >= 0) & (lab < NUM_CLASSES)).to(dtype)[..., None]
             x = torch.cat([onehot, se_in[i]], dim=-1)                    # 19 + 2 channels
-            att.append(se_block(x, wts, "pose_exp_net/se_segflow", act).sum(-1, keepdim=True))
+            if spp21:                                                    # se_spp_block(..., "se_spp_segflow", ratio=1, spp_size=[2,1])
+                exc = se_weights(x, wts, "pose_exp_net/se_spp_segflow", act, mode="spp", spp_size=(2, 1))
+                att.append((x * exc[:, None, None, :]).sum(-1, keepdim=True))
+            else:
+                att.append(se_block(x, wts, "pose_exp_net/se_segflow", act).sum(-1, keepdim=True))
     elif "-no_segmask" in version:                                       # davo.py:1385-1389
         att = [torch.ones_like(s) for s in pred_segs]
     elif "-segmask_" in version and "-static" in version:                # davo.py:1390-1394

@@ -53,6 +53,7 @@ CASES = {
     "pix_mix_depthflow": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_mixDepthFlow-norm_depth-abs_flow-fc_tanh",
     "pix_mix_dispflow": "v0-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_mixDispFlow-norm_flow-fc_lrelu",
     "depthseg_seplayers": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow_on_depthseg_seplayers_40-abs_flow-fc_tanh",
+    "spp21_mix_segflow": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_spp21_mixSegFlow-norm_flow-fc_tanh",
     "segflow_8_wo_tgt": "v0-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_SegFlow_to_seg_8_wo_tgt-fc_lrelu",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)

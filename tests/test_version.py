@@ -127,11 +127,10 @@ def test_all_six_posenn_kinds_resolve_as_in_the_reference():
 
 def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-no_segmask-se_insert").posenn_se == V.PSE_INSERT
-    assert V.parse_version(BASE + "-se_skipadd").posenn_se == V.PSE_SKIPADD
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_spp21_mixSegFlow"])
+@pytest.mark.parametrize("tok", ["-se_skipadd", "-batch_norm"])
 def test_unbuilt_sources_fail_loudly(tok):
     with pytest.raises(NotImplementedError):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
@@ -139,7 +138,7 @@ def test_unbuilt_sources_fail_loudly(tok):
 
 def test_depth_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all-se_spp21_mixSegFlow-fc_tanh")
+        V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_depth_wo_tgt-fc_tanh")   # per-pixel source in a non-shared net
     c = V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-norm_depth-fc_tanh")     # davo.py:1211-1219
     assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 1, 1, 1)
     assert V.parse_version(BASE + "-segmask_all-se_depth_to_seg").att_tgt_ones == 0
