@@ -22,7 +22,7 @@ SYMBOLS = (
     "davo_forward_features", "davo_debug_flows_to_half",
     "davo_comm_unique_id", "davo_comm_create", "davo_comm_world", "davo_allgather_poses",
     "davo_last_error",
-    "davo_destroy", "davo_build_info",
+    "davo_destroy", "davo_build_info", "davo_config_bytes",
 )
 
 
@@ -86,6 +86,10 @@ def load() -> C.CDLL:
     lib.davo_destroy.argtypes = [vp]
     lib.davo_destroy.restype = None
     lib.davo_build_info.restype = C.c_char_p
+    lib.davo_config_bytes.restype = ip
+    if lib.davo_config_bytes() != C.sizeof(DavoConfigC):
+        raise ImportError("%s: davo_config is %d bytes in the library, %d in this binding (rebuild: python davo_b200/build.py --force)"
+                          % (path, lib.davo_config_bytes(), C.sizeof(DavoConfigC)))
     for s in SYMBOLS[:18]:
         getattr(lib, s).restype = ip
     _LIB = lib

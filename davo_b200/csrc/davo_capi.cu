@@ -1133,6 +1133,8 @@ extern "C" const char* davo_build_info(void) {
   return "davo_b200 sm_100a tcgen05/TMA, nvcc " __DATE__;
 }
 
+extern "C" int davo_config_bytes(void) { return (int)sizeof(davo_config); }
+
 extern "C" const char* davo_last_error(const davo_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_create_error.c_str();
 }

@@ -209,6 +209,7 @@ int davo_allgather_poses(davo_ctx*, void* nccl_comm, const float* local_dev, int
 const char* davo_last_error(const davo_ctx*);   /* NULL handle -> last create error */
 void davo_destroy(davo_ctx*);
 const char* davo_build_info(void);              /* arch / compiler string */
+int davo_config_bytes(void);                    /* sizeof(davo_config) in this build: a binding checks its struct against it */
 
 #ifdef __cplusplus
 }

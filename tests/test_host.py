@@ -401,3 +401,17 @@ def test_host_flow_conversion_is_ieee_binary16_round_to_nearest_even():
             bad = x.copy()
             bad[777] = poison
             assert lib.davo_debug_flows_to_half(bad.ctypes.data, out.ctypes.data, bad.size, portable) == 1
+
+
+def test_binding_struct_matches_the_header():
+    """The ctypes davo_config has the header's fields in the header's order, and the library's size."""
+    import ctypes as C, re
+    from davo_b200 import _capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "davo_b200.h")).read()
+    body = hdr[hdr.index("typedef struct davo_config {"):hdr.index("} davo_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"int32_t\s+([a-z_0-9, A-Z]+);", body)
+    names = [n.strip() for f in fields for n in f.split(",")]
+    assert names == [n for n, _ in _capi.DavoConfigC._fields_]
+    assert _capi.load().davo_config_bytes() == C.sizeof(_capi.DavoConfigC) == 4 * len(names)
