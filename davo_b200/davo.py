@@ -20,7 +20,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Dict, Optional
 
 import numpy as np
 

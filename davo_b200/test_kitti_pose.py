@@ -21,7 +21,6 @@ from __future__ import annotations
 
 import argparse
 import os
-import sys
 from glob import glob
 
 import numpy as np
