@@ -280,7 +280,7 @@ def _write_bundle(prefix, tensors, extra_entries=(), block_bytes=300):
     data = bytearray()
     entries = {b"": _pb(1, 0, _pb_varint(1)) + _pb(3, 2, _pb_varint(2) + _pb(1, 0, _pb_varint(1)))}   # header
     for name in sorted(tensors):
-        a = np.ascontiguousarray(tensors[name])
+        a = np.require(np.asarray(tensors[name]), requirements="C")      # (ascontiguousarray would make a scalar 1-d)
         raw = a.astype("<f4").tobytes() if a.dtype != np.int64 else a.astype("<i8").tobytes()
         shape = b"".join(_pb(2, 2, _pb_varint(len(_pb(1, 0, _pb_varint(d)))) + _pb(1, 0, _pb_varint(d))) for d in a.shape)
         e = _pb(1, 0, _pb_varint(1 if a.dtype != np.int64 else 9)) + _pb(2, 2, _pb_varint(len(shape)) + shape)
@@ -339,7 +339,10 @@ def test_tf_checkpoint_reader_round_trip(tmp_path):
     from davo_b200 import tf_checkpoint as T
     from davo_b200 import synthetic as S
     assert T.crc32c(b"123456789") == 0xE3069283                      # the Castagnoli check value
-    w = S.init_weights("v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh", random_bias=True)
+    # a variant with a SCALAR variable (se_flow/depth_threshold, rank 0) next to the conv and dense ones
+    w = S.init_weights("v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow_on_depthseg_seplayers_15-abs_flow-fc_tanh",
+                       random_bias=True)
+    assert np.asarray(w["pose_exp_net/se_flow/depth_threshold"]).shape == ()
     extra = {"global_step": np.array([1600000], np.int64),
              "pose_exp_net/cnv1/weights/Adam": np.zeros((7, 7, 10, 16), np.float32),
              "depth_net/cnv1/weights": np.ones((3, 3, 3, 8), np.float32)}
@@ -351,7 +354,7 @@ def test_tf_checkpoint_reader_round_trip(tmp_path):
     got = T.read_checkpoint(prefix, T.pose_variables, verify_data_crc=True)
     assert set(got) == set(w)
     for k in w:
-        assert got[k].dtype == np.float32 and got[k].shape == w[k].shape and np.array_equal(got[k], w[k])
+        assert got[k].dtype == np.float32 and got[k].shape == np.shape(w[k]) and np.array_equal(got[k], w[k])
     assert "depth_net/cnv1/weights" in T.read_checkpoint(prefix) and "global_step" not in T.read_checkpoint(prefix)
     # damage: a flipped byte in the index fails the block crc; a flipped tensor byte fails the data crc
     raw = bytearray(open(prefix + ".index", "rb").read())
