@@ -418,3 +418,24 @@ def test_binding_struct_matches_the_header():
     names = [n.strip() for f in fields for n in f.split(",")]
     assert names == [n for n, _ in _capi.DavoConfigC._fields_]
     assert _capi.load().davo_config_bytes() == C.sizeof(_capi.DavoConfigC) == 4 * len(names)
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/davo_b200.h compiles as C99 (the boundary is a C ABI, not a C++ one) and a C program that
+    links the shared library sees the config size the Python binding sees."""
+    import shutil, subprocess, ctypes as C
+    from davo_b200 import _capi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "host.c"
+    src.write_text('#include <stdio.h>\n#include "davo_b200.h"\n'
+                   'int main(void) { davo_config c; davo_features f; (void)c; (void)f;\n'
+                   '  printf("%d %d %s\\n", davo_config_bytes(), (int)sizeof(davo_config), davo_build_info()); return 0; }\n')
+    exe = tmp_path / "host"
+    lib = _capi.lib_path()
+    _capi.load()
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                    str(src), lib, "-Wl,-rpath," + os.path.dirname(lib), "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == int(out[1]) == C.sizeof(_capi.DavoConfigC)
