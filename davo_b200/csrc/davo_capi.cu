@@ -1990,8 +1990,6 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
   const int units = ctx->unit_sample ? B : 2 * B;
   if (ctx->finalized && units > ctx->mb)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: B=%d needs %d units, one pass holds %d", B, units, ctx->mb);
-  if (ctx->cfg.pixel_map || ctx->cfg.depth_split)
-    return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: not built for the per-pixel and depth-split attention sources");
   if ((out->flow_color) && !flow) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: flow colouring needs input_flow");
   if ((out->seg_19 || out->seg_color) && !seg) return fail(ctx, DAVO_ERR_ARG, "davo_forward_features: label outputs need input_seglabel");
   if (int rc = davo_forward_pairs(ctx, B, DAVO_PAIRS_ALL, img, flow, seg, depth, pose_out, stream)) return rc;
@@ -2012,6 +2010,10 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
   fp.B = B; fp.H = c.H; fp.W = c.W;
   fp.unit_sample = ctx->unit_sample ? 1 : 0; fp.att_src = c.att_src; fp.att_tgt_ones = c.att_tgt_ones;
   fp.mask_rgb = c.mask_mode != 0;
+  // what frame_attention reads: the variant's flags and the flow / depth planes of this batch
+  fp.fp.H = c.H; fp.fp.W = c.W; fp.fp.att_src = c.att_src; fp.fp.pixel_map = c.pixel_map; fp.fp.depth_norm = c.depth_norm;
+  fp.fp.depth_split = c.depth_split; fp.fp.depth_thres = ctx->depth_thres; fp.fp.flow_abs = c.flow_abs; fp.fp.flow_norm = c.flow_norm;
+  fp.fp.flow = flow; fp.fp.depth = depth;
   fp.img = img; fp.flow = flow; fp.seg = seg; fp.att_w = ctx->d_attw; fp.static_w = ctx->d_staticw;
   fp.wheel = ctx->d_wheel; fp.maxrad = ctx->d_maxrad;
   fp.image = out->image; fp.attention = out->attention; fp.masked_image = out->masked_image;

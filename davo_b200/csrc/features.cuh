@@ -18,6 +18,7 @@
 namespace davo {
 
 struct FeatureParams {
+  FrontParams fp;         // the variant's flags and the flow / depth inputs, as the pack kernels see them (frame_attention)
   int B, H, W;
   int unit_sample, att_src, att_tgt_ones, mask_rgb;
   const uint8_t* img;     // [B][H][3W][3]
@@ -57,16 +58,20 @@ __device__ __forceinline__ const float* frame_weights(const FeatureParams& p, in
 
 // grid (blocks, B, 3 frames); a thread takes 4 consecutive pixels of a row
 __global__ void __launch_bounds__(256) feature_frames_kernel(const FeatureParams p) {
-  __shared__ float s_w[kNumClasses];
+  __shared__ float s_w[kAttStride], s_wf[kAttStride];      // the frame's table, and the "far" table of a depth-split source
   __shared__ int s_ones;
   const int b = blockIdx.y, f = blockIdx.z;
   const int hw = p.H * p.W, groups = hw / 4;
   if (threadIdx.x == 0) s_ones = frame_weights(p, b, f) == nullptr;
-  if (threadIdx.x < kNumClasses) {
+  if (threadIdx.x < kAttStride) {
     const float* w = frame_weights(p, b, f);
-    s_w[threadIdx.x] = w ? w[threadIdx.x] : 1.0f;
+    const bool table = p.att_src != 2 || threadIdx.x < kNumClasses;        // static_w holds 19 values
+    s_w[threadIdx.x] = (w && table) ? w[threadIdx.x] : 1.0f;
+    s_wf[threadIdx.x] = (w && p.fp.depth_split) ? w[kAttStride + threadIdx.x] : 0.0f;   // slot 1 of the same pair
   }
   __syncthreads();
+  const bool need_depth = p.fp.depth_split || (p.fp.pixel_map && p.att_src == 5);
+  const bool need_flow = p.fp.pixel_map && (p.att_src == 6 || p.fp.pixel_map == 2);
   const bool ones = s_ones != 0;
   const int plane = f == 0 ? 1 : f == 1 ? 0 : 2;        // position in the inputs: [src0, tgt, src1]
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
@@ -84,8 +89,20 @@ __global__ void __launch_bounds__(256) feature_frames_kernel(const FeatureParams
     }
     float a[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      a[i] = ones ? 1.0f : (lab[i] >= 0 && lab[i] < kNumClasses) ? s_w[lab[i]] : 0.0f;
+    for (int i = 0; i < 4; ++i) {
+      if (ones) { a[i] = 1.0f; continue; }
+      float ds = 0.f, dt = 0.f, sfx = se_in_x(0.f, p.fp), sfy = se_in_y(0.f, p.fp);   // the target's flow is zeros
+      if (need_depth) {
+        ds = __ldg(p.fp.depth + ((size_t)b * 3 + plane) * hw + p0 + i);
+        dt = __ldg(p.fp.depth + ((size_t)b * 3 + 1) * hw + p0 + i);
+      }
+      if (need_flow && f != 0) {
+        const float2 v = flow1_at(p.fp, b, f - 1, p0 + i, hw);
+        sfx = se_in_x(v.x, p.fp);
+        sfy = se_in_y(v.y, p.fp);
+      }
+      a[i] = frame_attention(p.fp, s_w, s_wf, lab[i], r[i], g[i], bl[i], ds, dt, sfx, sfy);
+    }
     const size_t px0 = fb * hw + p0;
     if (p.attention) *reinterpret_cast<float4*>(p.attention + px0) = make_float4(a[0], a[1], a[2], a[3]);
     if (p.image) {

@@ -512,6 +512,31 @@ __device__ __forceinline__ float img_norm(uint8_t v) {
   return (float)v * (1.0f / 255.0f) * 2.0f - 1.0f;     // davo.py:1519-1522
 }
 
+// Attention value of one pixel of one frame (davo.py:1115-1400 after the pooling and the dense layers).
+//   w      the frame's slot of att_w: 19 class weights, or the excitation of a per-pixel source
+//   w_far  depth_split only: the "far" table (the frame's slot holds the "near" one)
+//   lab    the pixel's label (tf.cast(seg, int32)); r, g, b its [-1, 1] colour; d_self / d_tgt the depth of this
+//          frame and of the target at the pixel; sfx, sfy the SE flow (se_in_x / se_in_y; se_in(0) on the target)
+// Class-weight sources: w[lab], 0 outside 0..18 (tf.one_hot gives an all-zero row).  Per-pixel sources
+// (pixel_map): reduce_sum(SE input * excitation) (attention_module.py:51; davo.py:1161, 1230, 1295, 1377).
+__device__ __forceinline__ float frame_attention(const FrontParams& p, const float* w, const float* w_far, int lab,
+                                                 float r, float g, float b, float d_self, float d_tgt, float sfx,
+                                                 float sfy) {
+  const bool in = lab >= 0 && lab < kNumClasses;
+  if (p.pixel_map) {
+    if (p.att_src == 4) return r * w[0] + g * w[1] + b * w[2];            // se_block(image)
+    if (p.att_src == 5) {                                                 // se_block(depth term [, SE flow]); see se_pool_kernel
+      const float x = p.depth_norm == 2 ? 1.0f / d_self : p.depth_norm == 1 ? (d_self + d_tgt) / 80.0f : d_self + d_tgt;
+      float a = x * w[0];
+      if (p.pixel_map == 2) a += sfx * w[1] + sfy * w[2];
+      return a;
+    }
+    return (in ? w[lab] : 0.0f) + sfx * w[kNumClasses] + sfy * w[kNumClasses + 1];   // se_block(concat(one_hot, SE flow))
+  }
+  if (p.depth_split) return in ? (d_self < p.depth_thres ? w[lab] : w_far[lab]) : 0.0f;   // davo.py:1143-1152
+  return in ? w[lab] : 0.0f;
+}
+
 // grid (kPackBlocksPerPair, npairs), 256 threads, one thread per pixel.  Writes the
 // 16-channel packed pixel (davo.py:1439-1442, posenn.py:198):
 //   ch 0-2  tgt r g b        ch 3-4  tgt flow (zeros)     ch 5-7  src r g b (x A)
@@ -562,43 +587,19 @@ __global__ void __launch_bounds__(256) pack_kernel(const FrontParams p) {
     float2 fl = make_float2(0.f, 0.f);
     if (p.in_mode == 1 || (p.pixel_map && p.att_src == 6) || p.pixel_map == 2) fl = flow1_at(p, b, k, pix, hw);
     float a_src = 1.0f, a_tgt = 1.0f;
-    if (p.pixel_map) {
-      // the map is reduce_sum(SE input * excitation) at the pixel (attention_module.py:51 + davo.py:1230, 1295, 1377)
-      if (p.att_src == 4) {                                      // se_block(image): r, g, b of the frame itself
-        a_src = sr0 * s_w[0] + sg0 * s_w[1] + sb0 * s_w[2];
-        if (!p.att_tgt_ones) a_tgt = tr0 * s_wt[0] + tg0 * s_wt[1] + tb0 * s_wt[2];
-      } else if (p.att_src == 5) {                               // se_block(depth term of the frame), see se_pool_kernel
-        const float dt = __ldg(p.depth + ((size_t)b * 3 + 1) * hw + pix);
-        const float ds = __ldg(p.depth + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw + pix);
-        const float xs = p.depth_norm == 2 ? 1.0f / ds : p.depth_norm == 1 ? (ds + dt) / 80.0f : ds + dt;
-        const float xt = p.depth_norm == 2 ? 1.0f / dt : p.depth_norm == 1 ? (dt + dt) / 80.0f : dt + dt;
-        a_src = xs * s_w[0];
-        if (!p.att_tgt_ones) a_tgt = xt * s_wt[0];
-        if (p.pixel_map == 2) {                                  // concat(depth term, SE flow): three channels
-          a_src += se_in_x(fl.x, p) * s_w[1] + se_in_y(fl.y, p) * s_w[2];
-          if (!p.att_tgt_ones) a_tgt += se_in_x(0.f, p) * s_wt[1] + se_in_y(0.f, p) * s_wt[2];
-        }
-      } else {                                                   // se_block(concat(one_hot(label), SE flow)): 19 + 2 channels
-        const int lab = label_at(p, seg_src, pix);
-        a_src = ((lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f) + se_in_x(fl.x, p) * s_w[kNumClasses] +
-                se_in_y(fl.y, p) * s_w[kNumClasses + 1];
-        if (!p.att_tgt_ones) {                                   // the target's flow is zeros (davo.py:979)
-          const int lt = label_at(p, seg_tgt, pix);
-          a_tgt = ((lt >= 0 && lt < kNumClasses) ? s_wt[lt] : 0.0f) + se_in_x(0.f, p) * s_wt[kNumClasses] +
-                  se_in_y(0.f, p) * s_wt[kNumClasses + 1];
-        }
+    if (p.att_src != 0) {
+      const bool need_lab = !p.pixel_map || p.att_src == 6;
+      const bool need_depth = p.depth_split || (p.pixel_map && p.att_src == 5);
+      float ds = 0.f, dt = 0.f;
+      if (need_depth) {
+        dt = __ldg(p.depth + ((size_t)b * 3 + 1) * hw + pix);
+        ds = __ldg(p.depth + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw + pix);
       }
-    } else if (p.depth_split) {
-      // near / far tables (slot 0 / slot 1) chosen by the source frame's depth (davo.py:1143-1152); target map = 1
-      const int lab = label_at(p, seg_src, pix);
-      const float ds = __ldg(p.depth + ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw + pix);
-      a_src = (lab >= 0 && lab < kNumClasses) ? (ds < p.depth_thres ? s_w[lab] : s_wt[lab]) : 0.0f;
-    } else if (p.att_src != 0) {
-      const int lab = label_at(p, seg_src, pix);                 // tf.cast truncates toward zero
-      a_src = (lab >= 0 && lab < kNumClasses) ? s_w[lab] : 0.0f;  // one_hot: out of range -> 0
-      if (!p.att_tgt_ones) {
-        const int lt = label_at(p, seg_tgt, pix);
-        a_tgt = (lt >= 0 && lt < kNumClasses) ? s_wt[lt] : 0.0f;
+      const int ls = need_lab ? label_at(p, seg_src, pix) : -1;          // tf.cast truncates toward zero
+      a_src = frame_attention(p, s_w, s_wt, ls, sr0, sg0, sb0, ds, dt, se_in_x(fl.x, p), se_in_y(fl.y, p));
+      if (!p.att_tgt_ones) {                                             // the target's flow is zeros (davo.py:979)
+        const int lt = need_lab ? label_at(p, seg_tgt, pix) : -1;
+        a_tgt = frame_attention(p, s_wt, s_wt, lt, tr0, tg0, tb0, dt, dt, se_in_x(0.f, p), se_in_y(0.f, p));
       }
     }
     const float mt = p.mask_rgb ? a_tgt : 1.0f, ms = p.mask_rgb ? a_src : 1.0f;

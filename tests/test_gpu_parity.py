@@ -528,7 +528,8 @@ def test_allgather_without_communicator_is_a_copy():
 
 
 @pytest.mark.parametrize("key", ["headline", "se_seg", "static", "couple_shared", "se_insert", "decouple_net",
-                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt", "segflow_to_seg", "se_replace", "spp21_seg_couple"])
+                                 "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt", "segflow_to_seg", "se_replace", "spp21_seg_couple",
+                                 "pix_rgb", "pix_depth_wo_tgt", "pix_mix_segflow", "pix_mix_dispflow", "depthseg_seplayers"])
 def test_feature_mode_matches_oracle(key):
     """DAVO.inference(mode='feature') (davo.py:1553-1564) through davo_forward_features: every fetched tensor
     against the oracle.  Labels and colourings are byte-exact (flow colours: the atan2 of the two
@@ -548,8 +549,11 @@ def test_feature_mode_matches_oracle(key):
         assert got["images"][f].shape == (g["batch"], H, W, 3)
         assert np.abs(got["images"][f] - want["images"][f]).max() < 1e-6
         assert got["masks"]["attention"][f].shape == (g["batch"], H, W, 1)
-        assert np.abs(got["masks"]["attention"][f] - want["masks"]["attention"][f]).max() < 5e-6, f
-        assert np.abs(got["masks"]["image"][f] - want["masks"]["image"][f]).max() < 5e-6, f
+        scale = max(1.0, float(np.abs(want["masks"]["attention"][f]).max()))     # per-pixel sources are not bounded by 1
+        # a map with flow terms carries the binary16 rounding of the flow it is computed from: |flow| * 2^-11 per pixel
+        tol = (1e-3 if "pix_mix" in key else 5e-6) * scale
+        assert np.abs(got["masks"]["attention"][f] - want["masks"]["attention"][f]).max() < tol, f
+        assert np.abs(got["masks"]["image"][f] - want["masks"]["image"][f]).max() < tol, f
         assert np.array_equal(got["seg_19"][f], want["seg_19"][f])
         assert got["segs"][f].dtype == np.uint8 and np.array_equal(got["segs"][f], want["segs"][f])
     for k in range(2):
