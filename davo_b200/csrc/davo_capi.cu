@@ -1040,6 +1040,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
   fp.seg8 = seg ? nullptr : ctx->cur_seg8;       // the host entry point passes seg = NULL with byte labels
   fp.flow16 = reinterpret_cast<const __half*>(ctx->cur_flow16);   // host entry point: the first cur_n16 samples of the chunk
   fp.n_flow16 = ctx->cur_flow16 ? ctx->cur_n16 : 0;
+  fp.flow_f16 = c.flow_f16;
   fp.se_w = ctx->d_sew; fp.static_w = ctx->d_staticw;
   fp.pool_part = ctx->d_pool; fp.pool_count = ctx->d_poolcnt; fp.att_w = ctx->d_attw; fp.packed = ctx->d_packed;
   if (c.att_src == 1 || c.att_src >= 3) {
@@ -1189,7 +1190,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (mb > ctx->max_units()) mb = ctx->max_units();
   ctx->mb = mb;
   if (const char* e = getenv("DAVO_B200_HOST_SEG8")) ctx->host_seg8 = strcmp(e, "0") != 0;   // "0": labels cross PCIe as floats
-  if (const char* e = getenv("DAVO_B200_HOST_FLOW16")) ctx->host_flow16 = strcmp(e, "0") != 0;   // "0": flow crosses PCIe as float32
+  ctx->host_flow16 = cfg->flow_f16 != 0;        // the binary16 transport exists only where the flow is defined as binary16
+  if (const char* e = getenv("DAVO_B200_HOST_FLOW16")) ctx->host_flow16 = ctx->host_flow16 && strcmp(e, "0") != 0;   // "0": flow crosses PCIe as float32
   if (const char* e = getenv("DAVO_B200_HOST_FLOW16_FRAC")) ctx->flow16_frac = std::max(0.0f, std::min(1.0f, (float)atof(e)));
   if (const char* e = getenv("DAVO_B200_PDL")) ctx->pdl = strcmp(e, "0") != 0;               // "0": plain stream order
   if (const char* cr = getenv("DAVO_B200_WEIGHT_ROUNDING"))     // "nearest": plain round-to-nearest
@@ -2013,7 +2015,7 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
   // what frame_attention reads: the variant's flags and the flow / depth planes of this batch
   fp.fp.H = c.H; fp.fp.W = c.W; fp.fp.att_src = c.att_src; fp.fp.pixel_map = c.pixel_map; fp.fp.depth_norm = c.depth_norm;
   fp.fp.depth_split = c.depth_split; fp.fp.depth_thres = ctx->depth_thres; fp.fp.flow_abs = c.flow_abs; fp.fp.flow_norm = c.flow_norm;
-  fp.fp.flow = flow; fp.fp.depth = depth;
+  fp.fp.flow = flow; fp.fp.depth = depth; fp.fp.flow_f16 = c.flow_f16;
   fp.img = img; fp.flow = flow; fp.seg = seg; fp.att_w = ctx->d_attw; fp.static_w = ctx->d_staticw;
   fp.wheel = ctx->d_wheel; fp.maxrad = ctx->d_maxrad;
   fp.image = out->image; fp.attention = out->attention; fp.masked_image = out->masked_image;

@@ -78,6 +78,7 @@ struct FrontParams {
   const float* flow;     // [B][4][H][W][2]
   const __half* flow16;  // the two planes the graph reads, already binary16: [B][2][H][W][2] (host entry point) ...
   int n_flow16;          // ... for samples b < n_flow16 of this batch; the others are read from `flow`
+  int flow_f16;          // davo_config.flow_f16: 1 = float32 flow values are rounded to binary16 when read (flow_q)
   const float* seg;      // [B][3][H][W][1]
   const uint8_t* seg8;   // the same labels as bytes (255 = outside 0..18), or NULL: the host entry point
                          // converts the float labels on the CPU so that a quarter of their bytes crosses PCIe
@@ -107,10 +108,11 @@ __device__ __forceinline__ void labels4_at(const FrontParams& p, size_t plane_of
   }
 }
 
-// The flow input is DEFINED as rounded to IEEE binary16 (11 significant bits, what the TF32 conv
-// operands keep anyway): the host entry point can then round on the CPU and move half the bytes over
-// PCIe with bit-identical results (host_convert.cpp).  Values that do not fit a finite half
-// (|x| >= 65520, NaN) pass through unchanged; the host sends a chunk holding one as float32.
+// davo_config.flow_f16 = 1 (opt-in): the flow input is DEFINED as rounded to IEEE binary16 (11 significant
+// bits, what the TF32 conv operands keep anyway): the host entry point can then round on the CPU and move
+// half the bytes over PCIe with bit-identical results (host_convert.cpp).  Values that do not fit a finite
+// half (|x| >= 65520, NaN) pass through unchanged; the host sends a chunk holding one as float32.
+// Default (flow_f16 = 0): the float32 values are used as given, as the reference's graph does.
 __device__ __forceinline__ float flow_q(float x) {
   return fabsf(x) < 65520.0f ? __half2float(__float2half_rn(x)) : x;
 }
@@ -127,7 +129,7 @@ __device__ __forceinline__ float2 flow1_at(const FrontParams& p, int b, int k, i
     return __half22float2(h);
   }
   const float2 v = __ldg(reinterpret_cast<const float2*>(p.flow + (((size_t)b * 4 + k) * hw + pix) * 2));
-  return flow_q2(v.x, v.y);
+  return p.flow_f16 ? flow_q2(v.x, v.y) : v;
 }
 // pixels pix, pix + 1 (pix even): (x0, y0, x1, y1)
 __device__ __forceinline__ float4 flow2_at(const FrontParams& p, int b, int k, int pix, int hw) {
@@ -138,6 +140,7 @@ __device__ __forceinline__ float4 flow2_at(const FrontParams& p, int b, int k, i
     return make_float4(a.x, a.y, c.x, c.y);
   }
   const float4 v = __ldg(reinterpret_cast<const float4*>(p.flow + (((size_t)b * 4 + k) * hw + pix) * 2));
+  if (!p.flow_f16) return v;
   const float2 lo = flow_q2(v.x, v.y), hi = flow_q2(v.z, v.w);
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }

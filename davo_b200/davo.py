@@ -42,8 +42,13 @@ class DAVO(object):
     # ------------------------------------------------------------------ setup
     def setup_inference(self, img_height, img_width, mode, seq_length=3, batch_size=1,
                         input_img_uint8=None, input_pose=None, input_flow=None,
-                        input_depth=None, input_seglabel=None, device=None, micro_batch=0):
-        """Reference ``davo.py:1533-1551``; only ``mode == 'davo'`` builds anything there."""
+                        input_depth=None, input_seglabel=None, device=None, micro_batch=0, flow_f16=None):
+        """Reference ``davo.py:1533-1551``; only ``mode == 'davo'`` builds anything there.
+
+        ``flow_f16`` (extension; default False, or the environment's ``DAVO_B200_FLOW16=1``): define the optical
+        flow input as rounded to IEEE binary16 on both entry points, which lets the host entry point move it
+        over PCIe at half the bytes (include/davo_b200.h: davo_config.flow_f16).  Off, the flow is read as the
+        float32 it is given in, like the reference's graph."""
         self.img_height = img_height
         self.img_width = img_width
         self.mode = mode
@@ -74,7 +79,9 @@ class DAVO(object):
             flow_abs=self.config.flow_abs, flow_norm=self.config.flow_norm,
             posenn_se=self.config.posenn_se, micro_batch=micro_batch, depth_norm=self.config.depth_norm,
             se_pool=self.config.se_pool, se_hidden=self.config.se_hidden, pixel_map=self.config.pixel_map,
-            depth_split=self.config.depth_split)
+            depth_split=self.config.depth_split,
+            flow_f16=int(os.environ.get("DAVO_B200_FLOW16", "0") == "1") if flow_f16 is None else int(bool(flow_f16)))
+        self.flow_f16 = bool(cfg.flow_f16)
         h = C.c_void_p()
         rc = self._lib.davo_create(C.byref(cfg), self.device, C.byref(h))
         if rc != 0:

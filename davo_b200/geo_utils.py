@@ -38,24 +38,39 @@ def pose_vec2mat(vec):
     return out
 
 
-def relative_pose_list(pred_poses):
+def relative_pose_list(pred_poses, batch_size=1, reference_batch_semantics=False):
     """pred_poses [N,2,6] in sample order -> list of 4x4 relative motions.
 
-    reference test_kitti_pose.py:136-145: T(tgt->src0) of the first sample only,
-    then inv(T(tgt->src1)) of every sample.
+    Default ("intended" loop): T(tgt->src0) of the first sample only, then inv(T(tgt->src1)) of every sample.
+    That is what reference test_kitti_pose.py:136-145 produces at ``--batch_size 1`` (the setting of
+    run_inference.sh:50), and it is the trajectory: N samples -> N+2 frames.
+
+    ``reference_batch_semantics=True`` reproduces the reference's loop literally at ``batch_size`` > 1, where it
+    differs: ``if i == 0`` (:143) tests the BATCH index inside the ``for j`` loop, so every sample of the first
+    batch contributes its tgt->src0 pose in front of its inv(tgt->src1), and ``pred_poses`` is expected to hold
+    the duplicated padding samples of ``complete_batch_size`` (:96-101), which the reference composes too.
+    The file then has 1 + min(B, N_padded) + N_padded lines.
     """
     pred_poses = np.asarray(pred_poses, np.float32)
-    t_src0 = pose_vec2mat(pred_poses[:1, 0])           # first sample, tgt->src0
-    t_src1 = pose_vec2mat(pred_poses[:, 1])            # every sample, tgt->src1
-    rel = [t_src0[0]]
-    rel.extend(np.linalg.inv(t_src1))                  # one batched LAPACK call: the same bits as one call per matrix
+    t_src1 = np.linalg.inv(pose_vec2mat(pred_poses[:, 1]))     # one batched LAPACK call: the same bits as one call per matrix
+    if reference_batch_semantics and batch_size > 1:
+        nb = min(batch_size, len(pred_poses))
+        t_src0 = pose_vec2mat(pred_poses[:nb, 0])
+        rel = []
+        for j in range(nb):                                    # batch i == 0: both poses of every sample, interleaved
+            rel.append(t_src0[j])
+            rel.append(t_src1[j])
+        rel.extend(t_src1[nb:])
+        return rel
+    rel = [pose_vec2mat(pred_poses[:1, 0])[0]]                 # first sample, tgt->src0
+    rel.extend(t_src1)
     return rel
 
 
-def compose_trajectory(pred_poses):
-    """Absolute poses [N+2,4,4] fp64, chained by right multiplication
+def compose_trajectory(pred_poses, batch_size=1, reference_batch_semantics=False):
+    """Absolute poses [len(rel)+1,4,4] fp64, chained by right multiplication
     (reference test_kitti_pose.py:118-119, 147-149)."""
-    rel = relative_pose_list(pred_poses)
+    rel = relative_pose_list(pred_poses, batch_size, reference_batch_semantics)
     out = np.empty((len(rel) + 1, 4, 4), np.float64)
     out[0] = np.eye(4)
     rel64 = np.asarray(rel, np.float64)                # np.dot(float64, float32) promotes the same way

@@ -47,44 +47,72 @@ def build_parser():
                     help="compute both poses of every sample as the reference graph does; by default only "
                          "the poses the trajectory is composed from are computed (reference :143-145), "
                          "which writes the same file with half the work")
+    ap.add_argument("--reference_batch_semantics", action="store_true",
+                    help="at --batch_size > 1 write exactly the file the reference's loop writes: its `if i == 0` "
+                         "(reference :143) tests the batch index, so EVERY sample of the first batch contributes its "
+                         "tgt->src0 pose, and the duplicated samples that pad the last batch (reference :96-101) are "
+                         "composed as well.  Default: the intended trajectory (first sample's tgt->src0 only, padding "
+                         "trimmed), which is what the reference writes at its shipped --batch_size 1")
     return ap
 
 
 class SyntheticStream:
     """Samples of a synthetic N-frame sequence, generated in seeded blocks of 64."""
 
-    def __init__(self, n_frames, h, w, seed):
+    def __init__(self, n_frames, h, w, seed, depth_from="none"):
         self.n = n_frames - 2
-        self.h, self.w, self.seed = h, w, seed
+        self.h, self.w, self.seed, self.depth_from = h, w, seed, depth_from
         self._blk, self._data = None, None
 
     def sample(self, i):
         blk = i // 64
         if blk != self._blk:
             self._data = synthetic.make_inputs(64, self.h, self.w, seed=self.seed + blk)
+            if self.depth_from == "depth":
+                self._data += (synthetic.make_depth(64, self.h, self.w, seed=4321 + self.seed + blk),)
+            elif self.depth_from == "seglabel":
+                self._data += (self._data[2],)
             self._blk = blk
         return tuple(a[i % 64] for a in self._data)
+
+
+def depth_source(version):
+    """Which file the reference's CLI feeds as ``input_depth`` (reference test_kitti_pose.py:48, 59-62, 91-94).
+
+    ``read_depth = "depth" in version`` there -- but the GRAPH reads input_depth whenever "depth" OR "disp" is in
+    the version (davo.py:960).  So a "disp"-only version (``-se_disp*``) is fed the SEGLABEL file as its depth
+    (`depth = image_sequence_seglabels` when load_depth is False).  Mirrored, not repaired: "depth" ->
+    ``<id>-monodepth2_depth.npy``, "seglabel" -> ``<id>-seglabel.npy``, "none" -> the graph does not read it.
+    """
+    if "depth" in version:
+        return "depth"
+    return "seglabel" if "disp" in version else "none"
 
 
 class DumpStream:
     """The reference's on-disk dump (reference test_kitti_pose.py:33-72, doc/preprocessing.md)."""
 
-    def __init__(self, root, seq, h, w, seq_length):
+    def __init__(self, root, seq, h, w, seq_length, depth_from="none"):
         d = os.path.join(root, '%.2d' % seq)
         half = int((seq_length - 1) / 2)
         n_frames = len(glob(d + '/*.jpg')) + 2 * half
         frames = ['%.2d %.6d' % (seq, n) for n in range(n_frames)]
         self.ids = [frames[i].split(' ')[1] for i in range(n_frames)
                     if parallel.is_valid_sample(frames, i, seq_length)]
-        self.dir, self.n, self.h, self.w = d, len(self.ids), h, w
+        self.dir, self.n, self.h, self.w, self.depth_from = d, len(self.ids), h, w, depth_from
 
     def sample(self, i):
         from PIL import Image
         fid = self.ids[i]
         img = np.asarray(Image.open(os.path.join(self.dir, fid + '.jpg')).convert('RGB'), np.uint8)
         flow = np.load(os.path.join(self.dir, fid + '-flownet2.npy')).astype(np.float32)
-        seg = np.load(os.path.join(self.dir, fid + '-seglabel.npy')).astype(np.float32)
-        return img, flow, seg.reshape(3, self.h, self.w, 1)
+        seg = np.load(os.path.join(self.dir, fid + '-seglabel.npy')).astype(np.float32).reshape(3, self.h, self.w, 1)
+        if self.depth_from == "none":
+            return img, flow, seg
+        if self.depth_from == "seglabel":
+            return img, flow, seg, seg
+        depth = np.load(os.path.join(self.dir, fid + '-monodepth2_depth.npy')).astype(np.float32)
+        return img, flow, seg, depth.reshape(3, self.h, self.w, 1)
 
 
 def main(argv=None):
@@ -103,14 +131,21 @@ def main(argv=None):
         os.makedirs(FLAGS.output_dir)
     H, W, B = FLAGS.img_height, FLAGS.img_width, FLAGS.batch_size
     if FLAGS.synthetic:
-        stream = SyntheticStream(FLAGS.synthetic, H, W, FLAGS.seed)
+        stream = SyntheticStream(FLAGS.synthetic, H, W, FLAGS.seed, depth_source(FLAGS.version))
     else:
         if not FLAGS.concat_img_dir:
             raise SystemExit("test_kitti_pose: give --concat_img_dir or --synthetic N")
-        stream = DumpStream(FLAGS.concat_img_dir, FLAGS.test_seq, H, W, FLAGS.seq_length)
+        stream = DumpStream(FLAGS.concat_img_dir, FLAGS.test_seq, H, W, FLAGS.seq_length, depth_source(FLAGS.version))
     n = stream.n
+    order = list(range(n))
+    if FLAGS.reference_batch_semantics:
+        # the reference pads the SAMPLE LIST to a multiple of the batch size before anything else (:96-101) and
+        # composes the duplicates; here that list is what gets sharded
+        order = parallel.complete_batch_size(order, B)
+        n = len(order)
     # shard, then fill the last batch by repeating the last item (reference common_utils.py:8-13)
-    idx = parallel.padded_indices(n, rank, world)
+    idx = [order[k] for k in parallel.padded_indices(n, rank, world)]
+    first = parallel.padded_indices(n, rank, world)[0] if n else 0      # global position of this rank's first item
     n_local = len(idx)
     idx = parallel.complete_batch_size(list(idx), B)
 
@@ -128,14 +163,17 @@ def main(argv=None):
     poses = torch.empty((len(idx), 2, 6), dtype=torch.float32, device="cuda:%d" % local)
     for i in range(len(idx) // B):                                     # reference :133
         batch = [stream.sample(j) for j in idx[i * B:(i + 1) * B]]
-        img, flow, seg = (np.stack([s[k] for s in batch]) for k in range(3))
+        inputs = tuple(np.stack([s[k] for s in batch]) for k in range(len(batch[0])))   # (img, flow, seg[, depth])
         # reference :143-145 reads pose[s,1] of every sample and pose[0,0] of the sequence's first
-        sel = 'all' if FLAGS.all_pairs else ('trajectory_first' if (i == 0 and idx[0] == 0) else 'trajectory')
-        pred = system.inference(None, mode='pose', inputs=(img, flow, seg), pairs=sel)   # reference :135
+        if FLAGS.all_pairs or (FLAGS.reference_batch_semantics and B > 1 and first + i * B < B):
+            sel = 'all'                       # reference semantics: batch 0 contributes tgt->src0 of every sample
+        else:
+            sel = 'trajectory_first' if (i == 0 and first == 0) else 'trajectory'
+        pred = system.inference(None, mode='pose', inputs=inputs, pairs=sel)   # reference :135
         poses[i * B:(i + 1) * B] = torch.as_tensor(pred['pose'])
     all_poses = parallel.gather_poses(poses[:n_local].contiguous(), n, system).cpu().numpy()
     if rank == 0:
-        traj = geo_utils.compose_trajectory(all_poses)                 # reference :136-149
+        traj = geo_utils.compose_trajectory(all_poses, B, FLAGS.reference_batch_semantics)   # reference :136-149
         if FLAGS.output_dir:
             out = os.path.join(FLAGS.output_dir, '%.2d-pred_kitti_pose.txt' % FLAGS.test_seq)
             if os.path.isfile(out):

@@ -195,6 +195,14 @@ def parse_version(version: str) -> DavoConfig:
         # se_block(concat(depth term, SE flow), "se_depthflow" | "se_dispflow", ratio=1): a per-pixel map of 3 channels
         if cfg.posenn >= POSENN_DECOUPLE_DIL:
             raise NotImplementedError("davo_b200: the depth + flow attention sources are built for the -sharedNN nets only")
+        if not cfg.needs_depth:
+            # "Depth" / "Disp" in these two tokens are capitalised, so davo.py:960's `"depth" in version or "disp" in
+            # version` is False unless another token (-norm_depth, ...) says so; the branch then reads
+            # se_input_depths (:1161) / pred_depths (:1167), which were never assigned: the reference stops here.
+            # Found by running the reference's graph code itself (tests/golden/make_golden.py).
+            raise UnboundLocalError("local variable '%s' referenced before assignment (reference davo.py:%d: no "
+                                    "lower-case 'depth' or 'disp' in the version, so input_depth is not read)"
+                                    % (("se_input_depths", 1161) if "-se_mixDepthFlow" in version else ("pred_depths", 1167)))
         cfg.att_src, cfg.att_tgt_ones, cfg.pixel_map = ATT_SE_DEPTH_SEG, 0, 2
         if "-se_mixDepthFlow" not in version:
             cfg.depth_norm = 2                                   # 1. / depth (davo.py:1167), whatever -norm_depth says

@@ -71,6 +71,13 @@ typedef struct davo_config {
                             "se_flow_near" / "se_flow_far"; a pixel takes its class weight from the near table where
                             its depth is below the variable se_flow/depth_threshold, else from the far table; reads
                             input_depth; shared nets only                                            */
+  int32_t flow_f16;      /* 0 (default): the optical flow is read as the float32 it is given in, like the reference's
+                            graph (davo.py:978-982; the SE pooling, attention_module.py:66, averages float32 values).
+                            1: opt-in transport narrowing -- every flow value is rounded to IEEE binary16 when read (11
+                            significant bits, what a TF32 conv operand keeps; the SE pooling then averages the rounded
+                            values: class weights move by <= 1.5e-5 relative, poses by ~2e-8), on BOTH entry points, so
+                            that davo_forward_host may move the flow over PCIe as binary16 with results bit-identical
+                            to davo_forward in the same mode                                         */
 } davo_config;
 
 /* Stands in for DAVO.__init__ + DAVO.setup_inference (reference davo.py:31-33,
@@ -90,11 +97,9 @@ int davo_finalize_weights(davo_ctx*);
 /* Stands in for DAVO.inference(sess, mode='pose') = one sess.run of pred_poses
  * (reference davo.py:1553-1569) on B <= max_batch samples.
  *   img_u8   device, uint8  [B, H, 3W, 3]   (src0 | tgt | src1 along width)
- *   flow     device, float  [B, 4, H, W, 2] (only [:,0:2] are read, davo.py:978-982).  Numerics: every
- *            flow value is rounded to IEEE binary16 when it is read (11 significant bits, the
- *            precision the TF32 convolution operands keep anyway; values with no finite half,
- *            |x| >= 65520 or NaN, are used as they are), on this and on the host entry point alike,
- *            so that the host entry point may move the flow as binary16 with identical results
+ *   flow     device, float  [B, 4, H, W, 2] (only [:,0:2] are read, davo.py:978-982); read as float32
+ *            unless davo_config.flow_f16 = 1 (then rounded to binary16 when read; values with no finite
+ *            half, |x| >= 65520 or NaN, are used as they are)
  *   seg      device, float  [B, 3, H, W, 1] ([src0, tgt, src1], davo.py:1000-1004)
  *   depth    device, float  [B, 3, H, W, 1] ([src0, tgt, src1], davo.py:991-996): read by the
  *            se_depth variants only (att_src 5); NULL otherwise
@@ -145,11 +150,12 @@ int davo_forward_features(davo_ctx*, int B, const uint8_t* img_u8, const float* 
  * form of `sess.run` with fed numpy arrays (reference davo.py:1568).  The batch is
  * streamed in micro-batch chunks, the host->device copy of chunk i+1 overlapping
  * the compute of chunk i; only the planes the graph reads are copied (flow[:,0:2],
- * and seg[:,{0,2}] when the target map is ones), the labels as bytes and -- on a host with
- * >= 16 hardware threads that this process does not share with other ranks -- three quarters of
- * the flow as binary16, both narrowed by a small CPU thread pool inside the call
- * (DAVO_B200_HOST_SEG8 / _FLOW16 / _FLOW16_FRAC / _THREADS override).  Results are bit-identical
- * to the device entry point either way.  Poses are copied back and the stream synchronised
+ * and seg[:,{0,2}] when the target map is ones), the labels as bytes (lossless: the graph casts them
+ * to int32, davo.py:1115) and -- only with davo_config.flow_f16 = 1, on a host with >= 16 hardware
+ * threads that this process does not share with other ranks -- three quarters of the flow as binary16,
+ * both narrowed by a small CPU thread pool inside the call (DAVO_B200_HOST_SEG8 / _FLOW16 /
+ * _FLOW16_FRAC / _THREADS override).  Results are bit-identical to the device entry point of the
+ * same configuration either way.  Poses are copied back and the stream synchronised
  * before returning. */
 int davo_forward_host(davo_ctx*, int B, const uint8_t* img_u8, const float* flow,
                       const float* seg, const float* depth, float* pose_out,

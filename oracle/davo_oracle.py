@@ -426,6 +426,8 @@ def davo_forward(version: str, img_u8: np.ndarray, flow: np.ndarray, seg: np.nda
     elif "-se_flow_on_depthseg" in version:
         _unsupported("depth-split attention")
     elif "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:  # davo.py:1157-1174
+        if not is_read_depth:        # capital D: davo.py:960 is False unless another token holds "depth" / "disp"
+            raise UnboundLocalError("local variable 'pred_depths' referenced before assignment")   # davo.py:1161 / 1167
         dp = torch.as_tensor(depth).to(dtype)
         pred_depths = [dp[:, 1], dp[:, 0], dp[:, 2]]
         if "-se_mixDepthFlow" in version:
@@ -761,19 +763,26 @@ def pose_vec2mat(vec, dtype=np.float32):
     return out
 
 
-def compose_trajectory(pred_poses: np.ndarray) -> np.ndarray:
+def compose_trajectory(pred_poses: np.ndarray, batch_size: int = 1,
+                       reference_batch_semantics: bool = False) -> np.ndarray:
     """test_kitti_pose.py:133-149 for seq_length 3.
 
-    pred_poses [N,2,6] in sample order -> absolute poses [N+2,4,4] (fp64):
-    identity, then T(tgt->src0) of the first sample, then inv(T(tgt->src1)) of
-    every sample, chained by right-multiplication.
+    Default: pred_poses [N,2,6] in sample order -> absolute poses [N+2,4,4] (fp64): identity, then
+    T(tgt->src0) of the first sample, then inv(T(tgt->src1)) of every sample, chained by
+    right-multiplication -- the reference's output at --batch_size 1.
+
+    ``reference_batch_semantics``: the loop as written, for any batch size: ``i`` is the batch index, so every
+    sample ``j`` of batch 0 appends its tgt->src0 pose (:143-144); pred_poses must already hold the padding
+    duplicates of complete_batch_size (:96-101), which the loop composes like any other sample.
     """
     pred_poses = np.asarray(pred_poses, np.float32)
+    B = batch_size if reference_batch_semantics else 1
     rel = []
     for s in range(pred_poses.shape[0]):
+        i = s // B                                                       # :133 `for i in range(round_num)`, :136 `for j`
         v = np.insert(pred_poses[s], 1, np.zeros((1, 6), np.float32), axis=0)   # :141
         m = pose_vec2mat(v)                                              # :142
-        if s == 0:
+        if (i == 0) if reference_batch_semantics else (s == 0):
             rel.append(m[0])                                             # :143-144
         rel.append(np.linalg.inv(m[2]))                                  # :145
     prev = np.eye(4).astype(float)

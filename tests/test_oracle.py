@@ -79,18 +79,57 @@ def test_c_restatement_agrees_with_torch_restatement(key):
 
 
 @pytest.mark.parametrize("key", list(G.CASES))
-def test_oracle_reproduces_committed_golden(key):
-    ver = G.CASES[key]
-    g = G.GOLDEN
+def test_oracle_matches_the_reference_fixture(key):
+    """The oracle against tests/golden/poses.npz, which holds what the REFERENCE'S OWN graph code computed for
+    the same seeded inputs and weights (tests/golden/make_golden.py runs davo.py / nets/*.py unmodified over
+    tests/tf_shim): poses, SE class weights, per-layer statistics of the first PoseNN call, attention maps,
+    masked frames, the upsampled cnv6 of mode='feature', and the uint8 colourings byte for byte (CRC)."""
+    ver, g = G.CASES[key], G.GOLDEN
     w = S.init_weights(ver, seed=g["weight_seed"], random_bias=True)
-    img, flow, seg = S.make_inputs(1, g["height"], g["width"], seed=g["input_seed"],
-                                   bad_label_frac=g["bad_label_frac"])
-    # inputs are generated batch-major from one stream: regenerate the full batch, use sample 0
-    img, flow, seg = S.make_inputs(g["batch"], g["height"], g["width"], seed=g["input_seed"],
-                                   bad_label_frac=g["bad_label_frac"])
-    depth = S.make_depth(g["batch"], g["height"], g["width"])
-    pose = O.davo_forward(ver, img[:1], flow[:1], seg[:1], w, torch.float64, depth=depth[:1])
-    np.testing.assert_allclose(pose[0], GOLD[key + "/pose"][0], rtol=1e-9, atol=1e-13)
+    img, flow, seg, depth = G.golden_inputs()
+    taps = {}
+    pose = O.davo_forward(ver, img, flow, seg, w, torch.float64, taps=taps, depth=depth)
+    np.testing.assert_allclose(pose, GOLD[key + "/pose"], rtol=1e-9, atol=1e-13)
+    if key + "/att_w" in GOLD.files:
+        got = np.stack([a.reshape(a.shape[0], -1) for a in taps["attention_weights"][1:]], 1)
+        np.testing.assert_allclose(got, GOLD[key + "/att_w"], rtol=1e-10, atol=1e-14)
+    else:
+        assert taps["attention_weights"] is None
+    # every slim.conv2d output of the first PoseNN call (sample 0): mean, mean |x|, max
+    names = {n[len(key) + 6:] for n in GOLD.files if n.startswith(key + "/stat/")}
+    t0 = dict(taps["pair0"])
+    alias = {"pose.rotation.cnv6": "cnv6_rotation", "pose.translation.cnv6": "cnv6_translation",
+             "pose.rotation.cnv7": "cnv7_rotation", "pose.translation.cnv7": "cnv7_translation",
+             "pose.cnv6": "cnv6_rotation", "pose.cnv7": "cnv7_rotation"}
+    checked = 0
+    for n in sorted(names):
+        tap = alias.get(n, n)
+        if tap in t0:
+            np.testing.assert_allclose(G.stat3(t0[tap][0]), GOLD[key + "/stat/" + n], rtol=1e-9, atol=1e-13, err_msg=n)
+            checked += 1
+    assert checked >= 6, (checked, sorted(names), sorted(t0))       # input + cnv1..5 at least (se_replace has no cnv6 conv)
+    for i in range(3):                                   # attention maps after the target override, every 8th pixel
+        a = np.asarray(taps["attention_maps"][i], np.float64)
+        np.testing.assert_allclose(a[:, ::G.AMAP_STRIDE, ::G.AMAP_STRIDE, 0], GOLD[key + "/feat/amap%d" % i], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(a.mean(), GOLD[key + "/feat/amap%d_mean" % i], rtol=1e-10)
+
+
+@pytest.mark.parametrize("key", ["headline", "static", "couple_net_v0", "plain_decouple_net", "pix_mix_depthflow", "se_replace"])
+def test_oracle_feature_mode_matches_the_reference_fixture(key):
+    """O.davo_features against the digests of the reference's inference(mode='feature') (davo.py:1553-1564)."""
+    ver, g = G.CASES[key], G.GOLDEN
+    w = S.init_weights(ver, seed=g["weight_seed"], random_bias=True)
+    img, flow, seg, depth = G.golden_inputs()
+    f = O.davo_features(ver, img, flow, seg, w, torch.float64, depth=depth)
+    for name, a in G.feature_digest(f).items():
+        np.testing.assert_allclose(a, GOLD[key + "/feat/" + name], rtol=1e-9, atol=1e-12, err_msg=name)
+    for name, a in G.colour_digest(f).items():
+        if name.startswith("flow_px"):
+            assert np.abs(a.astype(int) - GOLD[key + "/feat/" + name].astype(int)).max() <= 1, name
+        elif name.startswith("flow_crc"):
+            continue                     # last-bit atan2 differences flip single bytes; the strided pixels are compared
+        else:
+            assert a == GOLD[key + "/feat/" + name], name
 
 
 def test_fp32_oracle_close_to_fp64_oracle():
