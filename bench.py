@@ -12,7 +12,14 @@ Prints ONE JSON line (rank 0).  ``value`` is device-resident throughput, ``e2e``
 the same metric through ``DAVO.inference`` with host numpy inputs (host<->device
 copies inside the timed region), ``roofline`` the dominant kernel (cnv6) against
 the measured tensor peak, ``cpu_baseline`` the oracle's fp32 CPU restatement of
-the reference graph timed on this box's host cores.
+the reference graph timed on this box's host cores.  Correctness travels with the
+numbers: ``parity`` compares the poses of the timed batch (device-resident and
+host-fed) with the fp32 oracle on the same inputs (tolerance 1e-4 + 1e-3 |ref|,
+BASELINE.json north_star); under N > 1 the per-step gather is the library's own
+``davo_allgather_poses`` and ``gather_check`` says whether the gathered
+[N*B,2,6] equals, bit for bit, what rank 0 computes alone from every rank's
+seeded inputs.  ``stream_4541`` is BASELINE configs[2]: the 4541-frame stream
+sharded over the N ranks (strong scaling), gathered and composed.
 """
 from __future__ import annotations
 
@@ -122,23 +129,42 @@ def live_tf32_gemm_tflops(dev, n=8192, reps=10):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def cpu_oracle_rate(batch, iters, threads=None, min_seconds=0.0):
-    """Frame pairs / s of the oracle's fp32 torch-CPU restatement on the host cores."""
+def cpu_oracle_rate(batch, iters, threads=None, min_seconds=0.0, inputs=None):
+    """Frame pairs / s of the oracle's fp32 torch-CPU restatement on the host cores; also returns the
+    poses it computed (for the given `inputs`' first `batch` samples when given)."""
     import torch
     from davo_b200 import synthetic as S
     from oracle import davo_oracle as O
     if threads:
         torch.set_num_threads(threads)
     w = S.init_weights(VERSION)
-    img, flow, seg = S.make_inputs(batch, H, W, seed=4321)
+    if inputs is None:
+        img, flow, seg = S.make_inputs(batch, H, W, seed=4321)
+    else:
+        img, flow, seg = (a[:batch] for a in inputs)
     O.davo_forward(VERSION, img[:1], flow[:1], seg[:1], w, torch.float32)     # warm
     t0 = time.perf_counter()
     done = 0
+    poses = None
     while done < iters or time.perf_counter() - t0 < min_seconds:
-        O.davo_forward(VERSION, img, flow, seg, w, torch.float32)
+        poses = O.davo_forward(VERSION, img, flow, seg, w, torch.float32)
         done += 1
     dt = time.perf_counter() - t0
-    return 2 * batch * done / dt, dt, torch.get_num_threads(), done
+    return 2 * batch * done / dt, dt, torch.get_num_threads(), done, poses
+
+
+def parity_block(ref, **got):
+    """max |gpu - oracle32| of each given pose array against the north_star tolerance 1e-4 + 1e-3 |ref|."""
+    import numpy as np
+    out = {"n_samples": int(ref.shape[0]), "against": "fp32 oracle (CPU restatement held to the reference's own graph "
+           "code by tests/golden/poses.npz)", "tolerance": "abs(gpu - ref) <= 1e-4 + 1e-3 * abs(ref)", "ok": True}
+    for name, g in got.items():
+        g = np.asarray(g, np.float64)[: ref.shape[0]]
+        err = np.abs(g - ref)
+        ok = bool(np.all(np.isfinite(g)) and np.all(err <= 1e-4 + 1e-3 * np.abs(ref)))
+        out[name] = {"max_abs": float(err.max()), "max_abs_ref": float(np.abs(ref).max()), "ok": ok}
+        out["ok"] = out["ok"] and ok
+    return out
 
 
 def run_reference(args):
@@ -155,7 +181,7 @@ def run_reference(args):
     for _ in range(max(args.warmup, 1) - 1):
         cpu_oracle_rate(batch, 1, cores)
     steps = max(1, args.steps)                   # a step = 16 samples: ~0.2 s of CPU work
-    rate, dt, thr, steps = cpu_oracle_rate(batch, steps, cores)
+    rate, dt, thr, steps, _ = cpu_oracle_rate(batch, steps, cores)
     sample = "%d steps x %d samples (%d frame pairs each) of the 128-sample batch, fp32 torch-CPU" % (
         steps, batch, 2 * batch)
     line = {
@@ -170,6 +196,67 @@ def run_reference(args):
         "note": "oracle port of the TF 1.13 graph (TF not installable); not TensorFlow itself",
     }
     print(json.dumps(line), flush=True)
+
+
+def stream_4541(system, dev, rank, world, dist, n_samples=4539, batch=128):
+    """BASELINE.json configs[2]: the 4541-frame stream (4539 samples) sharded by sample over the ranks (contiguous
+    blocks, the last padded by the reference's complete_batch_size rule), each rank's shard resident in HBM, run in
+    128-sample batches in trajectory mode (only the poses reference test_kitti_pose.py:143-145 composes), gathered
+    once by davo_allgather_poses, composed on rank 0.  STRONG scaling: the stream is fixed, the ranks divide it.
+    Returns (on rank 0) ms per stream = max over ranks of the device time, frames/s and the host composition time."""
+    import numpy as np
+    import torch
+    from davo_b200 import geo_utils, parallel
+    from davo_b200 import synthetic as S
+    idx = parallel.padded_indices(n_samples, rank, world)
+    n_local = len(idx)
+    # the shard's inputs: a seeded 64-sample block tiled over the shard, resident (2.8 MB per sample)
+    base = [torch.as_tensor(x).to(dev) for x in S.make_inputs(64, H, W, seed=1000 + rank)]
+    reps = -(-n_local // 64)
+    shard = [t.repeat((reps,) + (1,) * (t.dim() - 1))[:n_local].contiguous() for t in base]
+    del base
+    poses = torch.empty((n_local, 2, 6), dtype=torch.float32, device=dev)
+
+    def run_stream():
+        for b0 in range(0, n_local, batch):
+            b1 = min(b0 + batch, n_local)
+            mode = "trajectory_first" if (rank == 0 and b0 == 0) else "trajectory"
+            out = system.inference(None, "pose", inputs=tuple(t[b0:b1] for t in shard), as_torch=True, pairs=mode)["pose"]
+            poses[b0:b1] = out
+        return parallel.gather_poses(poses, n_samples, system)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        allp = run_stream()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps_t = 5
+    e0.record()
+    for _ in range(reps_t):
+        allp = run_stream()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps_t], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    del shard
+    if rank != 0:
+        return None
+    allp = allp.cpu().numpy()
+    t0 = time.perf_counter()
+    traj = geo_utils.compose_trajectory(allp)
+    t_host = time.perf_counter() - t0
+    ms = float(ms.item())
+    return {"workload": "configs[2]: 4541-frame stream = 4539 samples, sample-sharded x%d (%d per rank), trajectory mode, "
+                        "inputs resident in HBM, one davo_allgather_poses, host composition on rank 0" % (world, n_local),
+            "scaling": "strong", "n_gpus": world, "frames": int(traj.shape[0]), "ms_per_stream": ms,
+            "frames_per_s": 4541 / (ms * 1e-3), "frame_pairs_computed": n_samples + 1,
+            "host_composition_ms": 1e3 * t_host, "finite": bool(np.all(np.isfinite(traj))),
+            "passes_per_rank": -(-n_local // batch), "last_pass_samples": n_local - (n_local - 1) // batch * batch}
 
 
 def run_ours(args):
@@ -199,11 +286,16 @@ def run_ours(args):
     system.setup_inference(H, W, "davo", 3, B, d_img, input_flow=d_flow, input_seglabel=d_seg,
                            device=local, micro_batch=args.micro_batch)
     system.load_weights(weights)
+    # ranks that share a host: keep each rank's threads and pinned staging on the NUMA node of its GPU
+    numa_node = system.bind_host_numa() if (world > 1 and os.environ.get("DAVO_B200_NUMA_BIND", "1") != "0") else -1
+
+    if world > 1:
+        system.init_comm(rank, world)            # the handle's own NCCL communicator (davo_comm_create)
 
     def step():
         out = system.inference(None, "pose", as_torch=True)["pose"]
         if world > 1:
-            out = parallel.gather_poses(out, world * B)
+            out = parallel.gather_poses(out, world * B, system)      # davo_allgather_poses (ncclAllGather, compute stream)
         return out
 
     def sync_all():
@@ -220,12 +312,13 @@ def run_ours(args):
     sync_all()
     e0.record()
     for _ in range(args.steps):
-        step()
+        timed_out = step()
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = system.last_launch_count() * args.steps
+    timed_out = timed_out.cpu().numpy()          # [world*B,2,6] under N > 1 (gathered), [B,2,6] at N = 1
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -247,19 +340,54 @@ def run_ours(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * 2 * B * e2e_steps / float(dt.item())
     h2d, d2h = system.last_host_copy_bytes()      # counted by the library from the copies it issues
-    # what the link itself gives: one plain pinned host->device copy of the same number of bytes
+    # the same, for a caller whose loader already holds byte labels and half-precision flow (extension, labelled)
+    c_flow, c_seg = S.compact_inputs(flow, seg)
+    c_flow, c_seg = (torch.as_tensor(x).pin_memory().numpy() for x in (c_flow, c_seg))
+    for _ in range(2):
+        pose_compact = system.inference(None, "pose", inputs=(h_img, c_flow, c_seg))["pose"]
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pose_compact = system.inference(None, "pose", inputs=(h_img, c_flow, c_seg))["pose"]
+    torch.cuda.synchronize()
+    dtk = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dtk, op=dist.ReduceOp.MAX)
+    compact_value = world * 2 * B * e2e_steps / float(dtk.item())
+    compact_h2d = system.last_host_copy_bytes()[0]
+    system.inference(None, "pose", inputs=(h_img, h_flow, h_seg))     # leave the float-input state behind for what follows
+    # What the host's links give when EVERY rank copies at once: a plain pinned host->device copy of the same number
+    # of bytes, all ranks released together by a barrier, timed on each rank's device; the bound uses the slowest.
     pin = torch.empty(h2d, dtype=torch.uint8).pin_memory()
     dst = torch.empty(h2d, dtype=torch.uint8, device=dev)
     dst.copy_(pin, non_blocking=True)
-    torch.cuda.synchronize()
+    sync_all()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
     for _ in range(5):
         dst.copy_(pin, non_blocking=True)
     c1.record()
     torch.cuda.synchronize()
-    pcie_gbs = 5 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    gb = torch.tensor([5 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9], device=dev)
+    gb_min = gb.clone()
+    if world > 1:
+        dist.all_reduce(gb_min, op=dist.ReduceOp.MIN)
+        dist.all_reduce(gb, op=dist.ReduceOp.SUM)
+    pcie_gbs, pcie_gbs_sum = float(gb_min.item()), float(gb.item())
     del pin, dst
+    # the library's own copies without compute (DAVO_B200_HOST_COPY_ONLY): staging + H2D of exactly what it moves
+    os.environ["DAVO_B200_HOST_COPY_ONLY"] = "1"
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        system.inference(None, "pose", inputs=(h_img, h_flow, h_seg))
+    torch.cuda.synchronize()
+    dtc = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
+    os.environ.pop("DAVO_B200_HOST_COPY_ONLY")
+    copy_only_value = world * 2 * B * 5 / float(dtc.item())
+    stream = stream_4541(system, dev, rank, world, dist)
 
     if rank != 0:
         if world > 1:
@@ -313,31 +441,56 @@ def run_ours(args):
         "whole_step_tflops": value / world * FLOP_PER_PAIR / 1e12,
         "whole_step_frac": value / world * FLOP_PER_PAIR / 1e12 / peak_tf32,
     }
-    cpu = None
-    if world == 1 or True:
-        rate, cdt, thr, n = cpu_oracle_rate(16, 1, min_seconds=12.0)
-        cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
-               "sample": "%d x 16 samples (32 frame pairs each) of the same workload, fp32 torch-CPU oracle "
-                         "(restatement of the TF graph, not TF), %.1f s" % (n, cdt)}
+    # CPU baseline leg = the fp32 oracle on the FIRST 16 SAMPLES OF THE TIMED BATCH; its poses are the parity reference
+    rate, cdt, thr, n, ref16 = cpu_oracle_rate(16, 1, min_seconds=12.0, inputs=(img, flow, seg))
+    cpu = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
+           "sample": "%d x the first 16 samples (32 frame pairs) of the timed batch, fp32 torch-CPU oracle "
+                     "(restatement of the TF graph, not TF), %.1f s" % (n, cdt)}
+    parity = parity_block(ref16, device_resident=timed_out[:16], host_fed=pose_host[:16], host_fed_compact=pose_compact[:16])
+    gather_check = None
+    if world > 1:
+        # what every rank contributed, recomputed by rank 0 alone from that rank's seeded inputs: same kernels, same
+        # per-sample reduction order, so the gathered block must be the same BITS
+        equal, worst = True, 0.0
+        for r in range(world):
+            ri = S.make_inputs(B, H, W, seed=1234 + r)
+            alone = system.inference(None, "pose", inputs=tuple(torch.as_tensor(x).to(dev) for x in ri))["pose"]
+            blk = timed_out[r * B:(r + 1) * B]
+            equal = equal and bool(np.array_equal(alone, blk))
+            worst = max(worst, float(np.abs(alone.astype(np.float64) - blk).max()))
+        gather_check = {"via": "davo_allgather_poses (ncclAllGather on the compute stream, the handle's communicator)",
+                        "ranks": world, "shape": list(timed_out.shape), "bit_equal_to_single_gpu": equal,
+                        "max_abs_diff": worst, "ok": equal and timed_out.shape[0] == world * B}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 accumulate)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32 operands (activations and weights), fp32 accumulate; inputs read as given (uint8 frames, float32 "
+                 "flow and labels; flow_f16 off)", "data": "synthetic",
         "config": {"workload": "configs[1]: 256 frame pairs (128 samples) per GPU @128x416, headline variant",
                    "version": VERSION, "samples_per_gpu": B, "frame_pairs_per_step": world * 2 * B,
                    "micro_batch_pairs": npairs,
                    "l2": "inputs (361 MB per step) exceed the 126 MB L2; no flush needed",
                    "parallelism": "sample-sharded x%d, NCCL all-gather of poses" % world},
-        "clocks": clocks, "gpu_launches": launches,
+        "clocks": clocks, "gpu_launches": launches, "parity": parity, "gather_check": gather_check,
+        "stream_4541": stream,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "pcie_h2d_gbs": pcie_gbs,
+                "steps": e2e_steps, "pcie_h2d_gbs": pcie_gbs, "pcie_h2d_gbs_all_ranks": pcie_gbs_sum,
                 "pcie_bound": world * 2 * B / (h2d / (pcie_gbs * 1e9)),
+                "copy_only": copy_only_value, "frac_of_copy_only": e2e_value / copy_only_value,
+                "compact_inputs": {"value": compact_value, "unit": UNIT, "h2d_bytes_per_step": compact_h2d,
+                                   "note": "NOT the reference's input contract: the caller supplies uint8 labels and "
+                                           "binary16 flow planes (davo_forward_host_compact); no CPU pass, fewer bytes"},
+                "numa_node": numa_node,
                 "host_input_bytes_per_step": world * B * (128 * 416 * (9 + 4 * 2 * 4 + 3 * 4)),
                 "note": "host inputs (uint8 frames, float32 flow and labels, as the reference feeds them) enter the "
                         "timed region as numpy arrays; the library copies only the planes the graph reads and, on "
-                        "the CPU inside the timed region, narrows labels to bytes and 3/4 of the flow planes to "
-                        "binary16 (the precision both entry points read the flow with), so h2d_bytes_per_step is "
-                        "what crossed PCIe; pcie_bound = frame pairs / (h2d bytes / measured pinned copy rate)"},
+                        "the CPU inside the timed region, narrows the labels to bytes (lossless: the graph casts them "
+                        "to int32); the flow crosses as float32 (flow_f16 off), so h2d_bytes_per_step is what crossed "
+                        "PCIe.  pcie_h2d_gbs = plain pinned copies of that many bytes issued by ALL ranks at once "
+                        "(barrier-released), slowest rank; pcie_bound = frame pairs / (h2d bytes / that rate); "
+                        "copy_only = the library's own staging + copies with the kernels skipped "
+                        "(DAVO_B200_HOST_COPY_ONLY), same ranks, same buffers: the ceiling e2e can reach"},
         "roofline": roofline, "cpu_baseline": cpu,
         "trajectory_mode": {"samples_per_s": B / (traj_ms * 1e-3), "ms_per_step": traj_ms, "frame_pairs_computed": B + 1,
                             "note": "pairs='trajectory_first' (rank 0, device-resident): the same output file as the "

@@ -45,16 +45,31 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library.  Safe under torchrun: ranks serialise on a file lock, the first one compiles into a
+    temporary file and renames it into place (a rank can never dlopen a half-written .so), the others find it
+    fresh when they get the lock."""
+    import fcntl
     if not force and not is_stale():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libdavo_b200.so")
-    with open(os.path.join(CSRC, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():          # another rank built it while this one waited
+                return LIB
+            tmp = "%s.%d.tmp" % (LIB, os.getpid())
+            cmd = [find_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libdavo_b200.so")
+            os.replace(tmp, LIB)
+            with open(os.path.join(CSRC, "build.log"), "w") as f:
+                f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -13,6 +13,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cctype>
+#include <sched.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -239,6 +241,7 @@ struct davo_ctx {
   // [chunk][2 planes][H][W][2] halves.  ev_seg8[i] covers both pinned staging buffers of slot i.
   uint16_t *h_flow16[kStage] = {}, *s_flow16[kStage] = {};
   bool host_flow16 = true;
+  int numa_node = -1, numa_cpus = 0;      // davo_bind_host_numa
   const uint16_t* cur_flow16 = nullptr;   // binary16 flow of the chunk being enqueued (NULL: float flow) ...
   int cur_n16 = 0;                        // ... for its first cur_n16 samples; the rest of the chunk crosses as float32
   const uint16_t* last_flow16 = nullptr;
@@ -1136,6 +1139,41 @@ extern "C" const char* davo_build_info(void) {
 
 extern "C" int davo_config_bytes(void) { return (int)sizeof(davo_config); }
 
+// include/davo_b200.h: davo_bind_host_numa.  sysfs only; no libnuma in the image.
+extern "C" int davo_bind_host_numa(davo_ctx* ctx) {
+  if (!ctx) return -1;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->device) != cudaSuccess) return -1;
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  int node = -1;
+  if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+  if (node < 0) return -1;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  char list[1024] = {0};
+  const bool got = fgets(list, sizeof list, f) != nullptr;
+  fclose(f);
+  if (!got) return -1;
+  cpu_set_t allowed, want;
+  CPU_ZERO(&want);
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return -1;
+  int n = 0;
+  for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k < 1) continue;
+    if (k == 1) b = a;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+      if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &want); ++n; }      // never outside what the container allows
+  }
+  if (n == 0 || sched_setaffinity(0, sizeof want, &want) != 0) return -1;
+  ctx->numa_node = node; ctx->numa_cpus = n;
+  return node;
+}
+
 extern "C" const char* davo_last_error(const davo_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_create_error.c_str();
 }
@@ -1578,8 +1616,33 @@ extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const
   return davo_forward_host_pairs(ctx, B, DAVO_PAIRS_ALL, img, flow, seg, depth, pose_out, stream);
 }
 
+// flow16 / seg8 non-NULL: the caller already holds the compact forms (davo_forward_host_compact) -- the two flow
+// planes the graph reads as binary16 [B][2][H][W][2], the labels as bytes [B][3][H][W] -- and they are copied
+// straight from the caller's memory: no CPU pass at all.
+static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
+                             const float* seg, const float* depth, float* pose_out, void* stream,
+                             const uint16_t* flow16, const uint8_t* seg8);
+
 extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
                                        const float* seg, const float* depth, float* pose_out, void* stream) {
+  return forward_host_impl(ctx, B, pairs, img, flow, seg, depth, pose_out, stream, nullptr, nullptr);
+}
+
+extern "C" int davo_forward_host_compact(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const uint16_t* flow_f16,
+                                         const uint8_t* seg_u8, const float* depth, float* pose_out, void* stream) {
+  if (!ctx) return DAVO_ERR_ARG;
+  const davo_config& c = ctx->cfg;
+  const bool uses_flow = (c.in_mode == 1 || c.att_src == 1 || c.att_src == 6 || c.pixel_map == 2);
+  if ((uses_flow && !flow_f16) || (c.att_src != 0 && !seg_u8))
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward_host_compact: null input buffer");
+  // the float pointers only serve as "present" flags and are never dereferenced when the compact forms are given
+  return forward_host_impl(ctx, B, pairs, img, reinterpret_cast<const float*>(flow_f16), reinterpret_cast<const float*>(seg_u8),
+                           depth, pose_out, stream, uses_flow ? flow_f16 : nullptr, c.att_src != 0 ? seg_u8 : nullptr);
+}
+
+static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
+                             const float* seg, const float* depth, float* pose_out, void* stream,
+                             const uint16_t* flow16_in, const uint8_t* seg8_in) {
   if (!ctx) return DAVO_ERR_ARG;
   if (pairs < DAVO_PAIRS_ALL || pairs > DAVO_PAIRS_TRAJECTORY_FIRST)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: pair selection %d unknown", pairs);
@@ -1609,13 +1672,13 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
       CU_OK(cudaMemset(ctx->s_flow[i], 0, n_flow * 4 * cs));
       CU_OK(cudaMemset(ctx->s_seg[i], 0, n_seg * 4 * cs));
       if (c.att_src == 5 || c.depth_split) CU_OK(cudaMalloc((void**)&ctx->s_depth[i], n_seg * 4 * cs));
-      if (ctx->host_seg8 && c.att_src != 0) {
+      if (c.att_src != 0) {
         CU_OK(cudaMalloc((void**)&ctx->s_seg8[i], n_seg * cs));
-        CU_OK(cudaHostAlloc((void**)&ctx->h_seg8[i], n_seg * cs, cudaHostAllocDefault));
+        if (ctx->host_seg8) CU_OK(cudaHostAlloc((void**)&ctx->h_seg8[i], n_seg * cs, cudaHostAllocDefault));
       }
-      if (ctx->host_flow16 && uses_flow) {
+      if (uses_flow) {
         CU_OK(cudaMalloc((void**)&ctx->s_flow16[i], n_flow / 2 * sizeof(uint16_t) * cs));
-        CU_OK(cudaHostAlloc((void**)&ctx->h_flow16[i], n_flow / 2 * sizeof(uint16_t) * cs, cudaHostAllocDefault));
+        if (ctx->host_flow16) CU_OK(cudaHostAlloc((void**)&ctx->h_flow16[i], n_flow / 2 * sizeof(uint16_t) * cs, cudaHostAllocDefault));
       }
       CU_OK(cudaEventCreateWithFlags(&ctx->ev_seg8[i], cudaEventDisableTiming));
       CU_OK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
@@ -1673,8 +1736,8 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
     // took every flow plane, while the copy engine has bandwidth to spare: the first n16 samples of a
     // chunk cross as binary16 and the rest as float32 (flow16_frac; both read through flow_q, so the
     // split does not change a bit of the result).
-    const bool conv_seg = need_seg && ctx->host_seg8;
-    int n16 = (need_flow && ctx->host_flow16) ? std::min(ns, (int)std::lround(ctx->flow16_frac * ns)) : 0;
+    const bool conv_seg = need_seg && ctx->host_seg8 && !seg8_in;
+    int n16 = (need_flow && ctx->host_flow16 && !flow16_in) ? std::min(ns, (int)std::lround(ctx->flow16_frac * ns)) : 0;
     const bool conv_flow = n16 > 0;
     const int planes[3] = {0, 2, 1};
     const int npl = seg_tgt ? 3 : 2;
@@ -1710,8 +1773,10 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
     ctx->cur_flow16 = nullptr;
     ctx->cur_n16 = 0;
     if (conv_flow && flow_bad.load()) n16 = 0;                  // a value with no finite half: the whole chunk as float32
+    if (flow16_in && need_flow) n16 = ns;                         // the caller's binary16 planes, as they are
     if (n16 > 0) {
-      CU_OK(cudaMemcpyAsync(ctx->s_flow16[buf], ctx->h_flow16[buf], hw * 4 * sizeof(uint16_t) * n16, cudaMemcpyHostToDevice, cp));
+      CU_OK(cudaMemcpyAsync(ctx->s_flow16[buf], flow16_in ? flow16_in + hw * 4 * (size_t)s0 : ctx->h_flow16[buf],
+                            hw * 4 * sizeof(uint16_t) * n16, cudaMemcpyHostToDevice, cp));
       h2d += hw * 4 * sizeof(uint16_t) * n16;
       ctx->cur_flow16 = ctx->s_flow16[buf];
       ctx->cur_n16 = n16;
@@ -1722,8 +1787,8 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
       h2d += n_flow * 2 * (ns - n16);
     }
     ctx->cur_seg8 = nullptr;
-    if (conv_seg) {
-      uint8_t* dst = ctx->h_seg8[buf];
+    if (conv_seg || (seg8_in && need_seg)) {
+      const uint8_t* dst = seg8_in ? seg8_in + n_seg * (size_t)s0 : ctx->h_seg8[buf];
       if (seg_tgt) {
         CU_OK(cudaMemcpyAsync(ctx->s_seg8[buf], dst, n_seg * ns, cudaMemcpyHostToDevice, cp));
         h2d += n_seg * ns;
@@ -1755,7 +1820,7 @@ extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const ui
     // a chunk is a batch of its own: only the first one may hold the first sample's tgt->src0
     const int chunk_pairs = (pairs == DAVO_PAIRS_TRAJECTORY_FIRST && s0 > 0) ? DAVO_PAIRS_TRAJECTORY : pairs;
     const int np_chunk = pairs_selected(chunk_pairs, ns);
-    static const bool copy_only = getenv("DAVO_B200_HOST_COPY_ONLY") != nullptr;   // experiment: time the copies alone
+    const bool copy_only = getenv("DAVO_B200_HOST_COPY_ONLY") != nullptr;   // measurement: the copies alone (bench.py e2e.copy_only)
     for (int q0 = 0; q0 < np_chunk && !copy_only; q0 += ctx->mb)
       if (int rc = run_microbatch(ctx, chunk_pairs, q0, std::min(ctx->mb, np_chunk - q0), ctx->s_img[buf],
                                   ctx->s_flow[buf], ctx->cur_seg8 ? nullptr : ctx->s_seg[buf],

@@ -157,6 +157,9 @@ class DAVO(object):
             raise ValueError("DAVO.inference: version %r reads input_depth [B,3,H,W,1]" % (self.version,))
         B = int(img.shape[0])
         H, W = self.img_height, self.img_width
+        if (isinstance(img, np.ndarray) and mode == 'pose' and flow is not None and seg is not None
+                and getattr(flow, "dtype", None) == np.float16 and getattr(seg, "dtype", None) == np.uint8):
+            return self._run_host_compact(B, img, flow, seg, sel, depth)       # the caller holds the compact forms
         want = {"img": (B, H, 3 * W, 3), "flow": (B, 4, H, W, 2), "seg": (B, 3, H, W, 1), "depth": (B, 3, H, W, 1)}
         for name, t in (("img", img), ("flow", flow), ("seg", seg), ("depth", depth)):
             if t is not None and tuple(t.shape) != want[name]:
@@ -189,7 +192,9 @@ class DAVO(object):
         # The same buffers called again and again (the bound-inputs form of the reference's
         # sess.run loop): davo_forward only enqueues work, so the third identical call is captured
         # into a CUDA graph and later ones replay it (launch gaps: -13 % latency at B=1, -1.4 % at
-        # B=128).  DAVO_B200_GRAPH=0 switches this off; any capture failure does too.
+        # B=128).  DAVO_B200_GRAPH=0 switches this off; any capture failure does too.  Side effects to know
+        # about: torch's capture synchronises the device once (at the third identical call) and frees its
+        # cached blocks; nothing else in the process is touched.
         key = (B, sel, out.data_ptr()) + tuple(t.data_ptr() if t is not None else 0 for t in (img, flow, seg, depth))
         if torch.cuda.is_current_stream_capturing():     # the caller is building a graph of their own
             launch()
@@ -203,18 +208,22 @@ class DAVO(object):
         elif self._graph_ok and self._graph_hits == 3:
             try:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g):            # ends (and discards) the capture itself if launch() raises
                     launch()
                 g.replay()
                 self._graph = g
             except Exception:
                 self._graph_ok, self._graph = False, None
                 torch.cuda.synchronize(self.device)
+                if torch.cuda.is_current_stream_capturing():
+                    raise                            # the stream is still in an invalidated capture: do not launch into it
                 launch()
         else:
             launch()
         if as_torch:
-            return {'pose': out}
+            # ``out`` is the handle's reusable output buffer (a fixed address is what lets the call be replayed as a
+            # graph): the caller gets a tensor of its own, which the next inference() does not overwrite
+            return {'pose': out.clone()}
         return {'pose': out.cpu().numpy()}
 
     def _run_features(self, B, img, flow, seg, depth, as_torch):
@@ -264,6 +273,25 @@ class DAVO(object):
         self._check(self._lib.davo_forward_host_pairs(self._h, B, sel, ptr(img), ptr(flow), ptr(seg), ptr(depth),
                                                       ptr(out), None), "davo_forward_host")
         return {'pose': out}
+
+    def _run_host_compact(self, B, img, flow16, seg8, sel=0, depth=None):
+        """Extension (include/davo_b200.h: davo_forward_host_compact): ``flow16`` float16 [B,2,H,W,2] = the two flow
+        planes the graph reads, ``seg8`` uint8 [B,3,H,W(,1)] = the labels as bytes (255 = no class).  No CPU pass."""
+        H, W = self.img_height, self.img_width
+        if tuple(img.shape) != (B, H, 3 * W, 3) or tuple(flow16.shape) != (B, 2, H, W, 2) or seg8.size != B * 3 * H * W:
+            raise ValueError("DAVO.inference (compact inputs): img [B,H,3W,3] uint8, flow [B,2,H,W,2] float16, seg [B,3,H,W] uint8")
+        img, flow16, seg8 = np.ascontiguousarray(img), np.ascontiguousarray(flow16), np.ascontiguousarray(seg8)
+        depth = None if depth is None else np.ascontiguousarray(depth, dtype=np.float32)
+        out = np.empty((B, 2, 6), np.float32)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        self._check(self._lib.davo_forward_host_compact(self._h, B, sel, ptr(img), ptr(flow16), ptr(seg8), ptr(depth),
+                                                        ptr(out), None), "davo_forward_host_compact")
+        return {'pose': out}
+
+    def bind_host_numa(self):
+        """Bind this thread (and threads created after it) to the CPUs next to this handle's GPU
+        (``davo_bind_host_numa``); call it before allocating pinned inputs.  Returns the NUMA node or -1."""
+        return int(self._lib.davo_bind_host_numa(self._h))
 
     # ------------------------------------------------------ test / debug taps
     def get_intermediate(self, name: str, pair: int) -> np.ndarray:

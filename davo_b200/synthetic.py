@@ -49,6 +49,15 @@ def make_inputs(batch: int, height: int = 128, width: int = 416, seed: int = 123
     return img, flow, seg[..., None].copy()
 
 
+def compact_inputs(flow: np.ndarray, seg: np.ndarray):
+    """(flow16 [B,2,H,W,2] float16, seg8 [B,3,H,W] uint8): the compact forms ``DAVO.inference`` accepts as an
+    extension -- the two flow planes the graph reads (reference davo.py:978-982) in half precision and the labels as
+    ``tf.cast(seg, int32)`` (davo.py:1115) clamped to a byte, 255 standing for every label outside 0..18."""
+    lab = np.trunc(np.asarray(seg, np.float32)[..., 0])
+    seg8 = np.where((lab >= 0) & (lab <= 18), lab, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.asarray(flow)[:, 0:2].astype(np.float16)), seg8
+
+
 def make_depth(batch: int, height: int = 128, width: int = 416, seed: int = 4321) -> np.ndarray:
     """Seeded input_depth [B,3,H,W,1] (metres, 1..80, smooth over 8x8 blocks): [src0, tgt, src1]
     (reference davo.py:991-996); read only by the se_depth attention sources."""

@@ -161,6 +161,25 @@ int davo_forward_host(davo_ctx*, int B, const uint8_t* img_u8, const float* flow
                       const float* seg, const float* depth, float* pose_out,
                       void* cuda_stream);
 
+/* The same call for a caller that already holds the inputs in compact form (its own loader decoded the labels to
+ * bytes and keeps the flow in half precision): nothing is converted on the CPU, the planes go from the caller's
+ * (ideally pinned) memory straight to the device, 1.06 MB per sample instead of 1.44 MB.
+ *   flow_f16  host, IEEE binary16 [B, 2, H, W, 2]: the two planes the graph reads (flow[:,0:2], davo.py:978-982);
+ *             widened exactly, so the result equals davo_forward on the widened values in either flow_f16 mode
+ *   seg_u8    host, uint8 [B, 3, H, W]: tf.cast(seglabel, int32) (davo.py:1115) clamped to a byte, any value
+ *             outside 0..18 meaning "no class" (255 by convention)
+ * `pairs` as in davo_forward_pairs.  This is an EXTENSION of the reference's input contract (which feeds float32
+ * flow and labels, test_kitti_pose.py:104-114); bench.py reports it as a separate, labelled end-to-end number. */
+int davo_forward_host_compact(davo_ctx*, int B, int pairs, const uint8_t* img_u8, const uint16_t* flow_f16,
+                              const uint8_t* seg_u8, const float* depth, float* pose_out, void* cuda_stream);
+
+/* Binds the calling thread (and the threads it creates afterwards: the handle's conversion pool, the caller's
+ * loader threads) to the CPUs of the NUMA node the handle's GPU hangs off (/sys/bus/pci/devices/<id>/numa_node,
+ * local_cpulist), so that pinned staging allocated afterwards is first-touched next to the GPU and the conversion
+ * threads read local memory.  Opt-in (it changes the caller's CPU affinity); a host without NUMA information or
+ * with one node is left as it is.  Returns the node (>= 0), or -1 when nothing was bound. */
+int davo_bind_host_numa(davo_ctx*);
+
 /* Test / mode='feature' access to what the last davo_forward left in the
  * workspace for frame pair `pair` (= 2*sample + source index) of the LAST
  * micro-batch: "att_weights" [19], "packed" [H,W,16], "cnv1".."cnv5",

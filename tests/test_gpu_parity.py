@@ -74,7 +74,7 @@ def test_variants_match_oracle_and_golden(key):
         for p in range(2 if sample_units else 4):
             want = GOLD[key + "/att_w"][p, 0] if sample_units else GOLD[key + "/att_w"][p // 2, p % 2]
             # float32 flow (the default): fp32 pooling of 53 248 (pyramid cells: >= 256) values against the fp64 reference run
-            np.testing.assert_allclose(sysm.get_intermediate("att_weights", p), want, rtol=2e-6, atol=1e-7)
+            np.testing.assert_allclose(sysm.get_intermediate("att_weights", p), want, rtol=1e-5 if "spp" in key else 2e-6, atol=1e-7)   # spp: a 232-term fp32 dot product
     if sysm.config.att_src == 5:                                             # host-buffer entry point with depth
         assert np.array_equal(out, sysm.inference(None, "pose", inputs=inputs + (depth,))["pose"])
         with pytest.raises(ValueError):
@@ -276,6 +276,30 @@ def test_flow_crosses_pcie_as_binary16_with_float32_fallback(monkeypatch):
     assert np.array_equal(a, s3.inference(None, "pose", inputs=(img, q, seg))["pose"])      # same grid, rounded by the caller
 
 
+@pytest.mark.parametrize("key", ["headline", "se_seg", "no_segmask", "decouple_net"])
+def test_compact_host_inputs_equal_the_widened_float_inputs(key):
+    """davo_forward_host_compact (extension): binary16 flow planes + byte labels from the caller's memory, no CPU
+    pass; the same bits as the float entry points fed with the widened values, in both pair selections."""
+    _need_gpu()
+    ver = G.CASES[key]
+    w = S.init_weights(ver, random_bias=True)
+    img, flow, seg = S.make_inputs(5, H, W, seed=77, bad_label_frac=0.01)
+    seg[0, 0, :4, :4, 0] = [[-3.0, -0.5, 18.9, 19.0], [300.0, 255.0, 0.2, 7.0], [1e9, 18.0, 3.5, 0.0], [5.0, 6.0, 7.0, 8.0]]
+    flow16, seg8 = S.compact_inputs(flow, seg)
+    assert flow16.shape == (5, 2, H, W, 2) and seg8.shape == (5, 3, H, W) and seg8[0, 0, 0, :4].tolist() == [255, 0, 18, 255]
+    wide = np.zeros_like(flow)
+    wide[:, 0:2] = flow16.astype(np.float32)
+    sysm, _ = _system(ver, 5, w, (img, wide, seg), micro_batch=4)
+    for pairs in ("all", "trajectory_first"):
+        a = sysm.inference(None, "pose", pairs=pairs)["pose"].copy()
+        b = sysm.inference(None, "pose", inputs=(img, flow16, seg8), pairs=pairs)["pose"]
+        assert np.array_equal(a, b), pairs
+    hw = H * W
+    uses_flow = sysm.config.in_mode == 1 or sysm.config.att_src == 1
+    n_lab = 0 if key == "no_segmask" else (2 if sysm.config.att_tgt_ones else 3)
+    assert sysm.last_host_copy_bytes()[0] == 5 * (hw * 9 + (hw * 8 if uses_flow else 0) + hw * n_lab)
+
+
 def test_exact_flow_mode_meets_the_tight_class_weight_tolerance():
     """with the float32 flow (default) the SE class weights agree with the fp64 reference run to
     1e-6 relative; with the opt-in binary16 flow they cannot (the pooled values themselves are rounded)."""
@@ -366,6 +390,43 @@ def test_full_length_stream_is_batch_split_invariant():
     assert np.array_equal(out[4512:4539], first[:27])
     traj = geo_utils.compose_trajectory(out)
     assert traj.shape == (4541, 4, 4) and np.all(np.isfinite(traj))
+
+
+def test_full_stream_ate_against_the_committed_reference_poses(monkeypatch):
+    """North star, BASELINE configs[2]: the 4541-frame stream (4539 seeded samples, random-init weights) composed from
+    the GPU poses against the trajectory composed from tests/golden/stream_poses.npz (fp32 reference poses, made by
+    tests/golden/make_stream_golden.py): ATE <= 1e-3 m.  Plain round-to-nearest TF32 weights
+    (DAVO_B200_WEIGHT_ROUNDING=nearest) leave a systematic per-pose offset that the composition accumulates: they
+    must come out WORSE than the compensated rounding the library uses -- which is what keeps that code justified."""
+    _need_gpu()
+    from tests.golden import make_stream_golden as SG
+    gold = np.load(os.path.join(os.path.dirname(G.__file__), "stream_poses.npz"))["pose"]
+    assert gold.shape == (SG.N, 2, 6)
+    w = S.init_weights(HEADLINE)
+    systems = {}
+    for mode in ("compensated", "nearest"):
+        monkeypatch.setenv("DAVO_B200_WEIGHT_ROUNDING", mode)
+        systems[mode] = DAVO(version=HEADLINE)
+        systems[mode].setup_inference(H, W, "davo", 3, SG.CHUNK, device=0)
+        systems[mode].load_weights(w)
+    got = {m: np.zeros_like(gold) for m in systems}
+    for s in range(0, SG.N, SG.CHUNK):
+        inputs = SG.stream_chunk(s)
+        for m, sysm in systems.items():
+            got[m][s:s + len(inputs[0])] = sysm.inference(None, "pose", inputs=inputs)["pose"]
+    ref_traj = O.compose_trajectory(gold)
+    res = {}
+    for m in systems:
+        assert np.all(np.abs(got[m] - gold) <= ATOL + RTOL * np.abs(gold))          # every single pose within tolerance
+        traj = geo_utils.compose_trajectory(got[m])
+        assert traj.shape == (4541, 4, 4)
+        res[m] = (O.ate(traj, ref_traj), float(np.linalg.norm(traj[-1, :3, 3] - ref_traj[-1, :3, 3])),
+                  float(np.abs((got[m] - gold).mean((0, 1))).max()))
+    print("stream ATE / end-point error / mean pose offset:", res)
+    assert res["compensated"][0] <= 1e-3, res                   # the north-star bar
+    assert res["compensated"][1] <= 2e-3, res
+    assert res["nearest"][0] > 2 * res["compensated"][0], res   # the offset the compensation removes
+    assert res["nearest"][2] > 2 * res["compensated"][2], res
 
 
 @pytest.mark.parametrize("host", [False, True])
