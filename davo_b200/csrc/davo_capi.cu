@@ -32,6 +32,7 @@
 #include "frontend.cuh"
 #include "features.cuh"
 #include "comm.cuh"
+#include "trajectory.cuh"
 #include "host_convert.h"
 
 using namespace davo;
@@ -242,6 +243,8 @@ struct davo_ctx {
   uint16_t *h_flow16[kStage] = {}, *s_flow16[kStage] = {};
   bool host_flow16 = true;
   int numa_node = -1, numa_cpus = 0;      // davo_bind_host_numa
+  void* d_traj_scratch = nullptr;         // davo_compose_trajectory / davo_kitti_errors: relative motions, distances, segments
+  size_t traj_scratch_bytes = 0;
   const uint16_t* cur_flow16 = nullptr;   // binary16 flow of the chunk being enqueued (NULL: float flow) ...
   int cur_n16 = 0;                        // ... for its first cur_n16 samples; the rest of the chunk crosses as float32
   const uint16_t* last_flow16 = nullptr;
@@ -1201,8 +1204,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (cfg->depth_split != 0 && (cfg->depth_split != 1 || cfg->att_src != 1 || cfg->se_pool != 0 || cfg->posenn > 1 || !cfg->att_tgt_ones))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: depth_split needs att_src 1 with global pooling, a target map of ones and a shared net");
   if (cfg->pixel_map != 0 && (cfg->pixel_map < 1 || cfg->pixel_map > 2 || (cfg->pixel_map == 2 && cfg->att_src != 5) ||
-                              cfg->att_src < 4 || cfg->att_src > 6 || cfg->posenn > 1 || (cfg->se_pool != 0 && cfg->att_src != 6)))
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: per-pixel maps are built for att_src 4..6, global pooling and the shared nets");
+                              cfg->att_src < 4 || cfg->att_src > 6 || (cfg->se_pool != 0 && cfg->att_src != 6)))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: per-pixel maps are built for att_src 4..6 and global pooling");
   if (cfg->att_src == 5 && ((cfg->H * cfg->W) % 4) != 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: se_depth needs H*W % 4 == 0");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1242,6 +1245,7 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->d_traj_scratch) cudaFree(ctx->d_traj_scratch);
   for (int i = 0; i < davo_ctx::kStage; ++i) {
     if (ctx->s_img[i]) cudaFree(ctx->s_img[i]);
     if (ctx->s_flow[i]) cudaFree(ctx->s_flow[i]);
@@ -2126,6 +2130,55 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
 }
 
 // Test hook (no GPU needed): the CPU float32 -> binary16 conversion of the host entry point.
+// ---- on-device trajectory composition and KITTI evaluation (include/davo_b200.h; csrc/trajectory.cuh) ----
+static int traj_scratch(davo_ctx* ctx, size_t bytes) {
+  if (ctx->traj_scratch_bytes >= bytes) return 0;
+  if (ctx->d_traj_scratch) cudaFree(ctx->d_traj_scratch);
+  ctx->d_traj_scratch = nullptr; ctx->traj_scratch_bytes = 0;
+  CU_OK(cudaMalloc(&ctx->d_traj_scratch, bytes));
+  ctx->traj_scratch_bytes = bytes;
+  return 0;
+}
+
+extern "C" int davo_compose_trajectory(davo_ctx* ctx, const float* poses, int n, double* traj, void* stream) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!poses || !traj || n < 1) return fail(ctx, DAVO_ERR_ARG, "davo_compose_trajectory: null buffer or no samples");
+  CU_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int m = n + 1;                                   // relative motions
+  if (int rc = traj_scratch(ctx, (size_t)m * sizeof(Mat4))) return rc;
+  Mat4* rel = reinterpret_cast<Mat4*>(ctx->d_traj_scratch);
+  pose_rel_kernel<<<(m + 127) / 128, 128, 0, st>>>(poses, n, rel);
+  CU_OK(cudaGetLastError());
+  const int threads = 256, chunk = (m + threads - 1) / threads;
+  traj_scan_kernel<<<1, threads, threads * 16 * sizeof(double), st>>>(rel, m, chunk, reinterpret_cast<Mat4*>(traj));
+  CU_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int davo_kitti_errors(davo_ctx* ctx, const double* gt, const double* res, int n, davo_kitti_segment* seg,
+                                 float* stats_host, void* stream) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!gt || !res || n < 1 || !stats_host) return fail(ctx, DAVO_ERR_ARG, "davo_kitti_errors: null buffer or no frames");
+  static_assert(sizeof(davo_kitti_segment) == sizeof(KittiSeg), "segment layouts differ");
+  CU_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int n_first = (n + kKittiStep - 1) / kKittiStep, count = n_first * kKittiLengths;
+  const size_t off_seg = ((size_t)n * sizeof(float) + 255) & ~(size_t)255, off_stats = off_seg + (size_t)count * sizeof(KittiSeg);
+  if (int rc = traj_scratch(ctx, off_stats + 64)) return rc;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ctx->d_traj_scratch);
+  float* dist = reinterpret_cast<float*>(base);
+  KittiSeg* segs = seg ? reinterpret_cast<KittiSeg*>(seg) : reinterpret_cast<KittiSeg*>(base + off_seg);
+  float* stats = reinterpret_cast<float*>(base + off_stats);
+  kitti_dist_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const Mat4*>(gt), n, dist);
+  kitti_segments_kernel<<<(count + 127) / 128, 128, 0, st>>>(reinterpret_cast<const Mat4*>(gt), reinterpret_cast<const Mat4*>(res), dist, n, n_first, segs);
+  kitti_stats_kernel<<<1, 32, 0, st>>>(segs, count, stats);
+  CU_OK(cudaGetLastError());
+  CU_OK(cudaMemcpyAsync(stats_host, stats, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 extern "C" int davo_debug_flows_to_half(const float* src, uint16_t* dst, long long n, int portable) {
   if (!src || !dst || n < 0) return DAVO_ERR_ARG;
   const bool ok = portable ? davo_host::flows_to_half_portable(src, dst, (size_t)n) : davo_host::flows_to_half(src, dst, (size_t)n);

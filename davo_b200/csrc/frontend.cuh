@@ -744,20 +744,23 @@ __global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
 __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
   pdl_launch_dependents();
   pdl_wait();                     // workspace buffers are shared with the kernels before this one
-  __shared__ float s_w[3][kNumClasses];                     // class weights of slots src0, src1, tgt
+  __shared__ float s_w[3][kAttStride];                      // class weights (or excitation) of slots src0, src1, tgt
   const int pl = blockIdx.y;
   int b, k;
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
-  if (threadIdx.x < 3 * kNumClasses) {
-    const int fr = threadIdx.x / kNumClasses, c = threadIdx.x % kNumClasses;
+  if (threadIdx.x < 3 * kAttStride) {
+    const int fr = threadIdx.x / kAttStride, c = threadIdx.x % kAttStride;
     const bool se = p.att_src == 1 || p.att_src >= 3;
     float v = 1.0f;
-    if (p.att_src == 2) v = p.static_w[c];
+    if (p.att_src == 2) v = c < kNumClasses ? p.static_w[c] : 0.0f;
     else if (se && !(fr == 2 && p.att_tgt_ones)) v = p.att_w[((size_t)pl * kAttFrames + fr) * kAttStride + c];
     s_w[fr][c] = v;
   }
   __syncthreads();
+  const bool need_lab = !p.pixel_map || p.att_src == 6;
+  const bool need_depth = p.pixel_map && p.att_src == 5;
+  const bool need_seflow = (p.pixel_map && p.att_src == 6) || p.pixel_map == 2;
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
   const size_t seg_b = (size_t)b * 3 * hw;
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 16);
@@ -766,11 +769,23 @@ __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
     const uint8_t* row = img_b + ((size_t)h * 3 * p.W + w) * 3;
     float a[3] = {1.f, 1.f, 1.f};                            // A_src0, A_src1, A_tgt
     if (p.att_src != 0) {
+      const float dt = need_depth ? __ldg(p.depth + ((size_t)b * 3 + 1) * hw + pix) : 0.f;
 #pragma unroll
       for (int fr = 0; fr < 3; ++fr) {
         if (fr == 2 && p.att_tgt_ones) continue;
-        const int lab = label_at(p, seg_b + (size_t)unit_frame(1, 0, fr) * hw, pix);    // tf.cast truncates
-        a[fr] = (lab >= 0 && lab < kNumClasses) ? s_w[fr][lab] : 0.0f;                 // one_hot: out of range -> 0
+        const int plane = unit_frame(1, 0, fr);              // 0 = src0, 2 = src1, 1 = tgt: label / depth plane, image column block
+        const int lab = need_lab ? label_at(p, seg_b + (size_t)plane * hw, pix) : -1;   // tf.cast truncates
+        float r = 0.f, g = 0.f, bl = 0.f, ds = 0.f, sfx = se_in_x(0.f, p), sfy = se_in_y(0.f, p);   // the target's flow is zeros (davo.py:979)
+        if (p.pixel_map && p.att_src == 4) {
+          const uint8_t* pf = row + (size_t)plane * p.W * 3;
+          r = img_norm(pf[0]); g = img_norm(pf[1]); bl = img_norm(pf[2]);
+        }
+        if (need_depth) ds = __ldg(p.depth + ((size_t)b * 3 + plane) * hw + pix);
+        if (need_seflow && fr != 2) {
+          const float2 f = flow1_at(p, b, fr, pix, hw);      // slot 0 = src0 -> flow[:, 0], slot 1 = src1 -> flow[:, 1]
+          sfx = se_in_x(f.x, p); sfy = se_in_y(f.y, p);
+        }
+        a[fr] = frame_attention(p, s_w[fr], s_w[fr], lab, r, g, bl, ds, dt, sfx, sfy);   // one_hot: out of range -> 0
       }
     }
     float v[16];

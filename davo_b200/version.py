@@ -193,8 +193,6 @@ def parse_version(version: str) -> DavoConfig:
         cfg.att_src, cfg.att_tgt_ones, cfg.depth_split = ATT_SE_FLOW, 1, 1
     elif "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:         # davo.py:1157-1174
         # se_block(concat(depth term, SE flow), "se_depthflow" | "se_dispflow", ratio=1): a per-pixel map of 3 channels
-        if cfg.posenn >= POSENN_DECOUPLE_DIL:
-            raise NotImplementedError("davo_b200: the depth + flow attention sources are built for the -sharedNN nets only")
         if not cfg.needs_depth:
             # "Depth" / "Disp" in these two tokens are capitalised, so davo.py:960's `"depth" in version or "disp" in
             # version` is False unless another token (-norm_depth, ...) says so; the branch then reads
@@ -234,8 +232,6 @@ def parse_version(version: str) -> DavoConfig:
         if chain_hit is not None:
             hit = _BUILT_AFTER_SE_FLOW[chain_hit]
             if isinstance(hit, dict):
-                if cfg.posenn >= POSENN_DECOUPLE_DIL:
-                    raise NotImplementedError("davo_b200: attention source %s is built for the -sharedNN nets only" % chain_hit)
                 for key, val in hit.items():
                     setattr(cfg, key, val)
                 hit = (cfg.att_src, cfg.att_tgt_ones)

@@ -231,6 +231,29 @@ int davo_comm_world(const davo_ctx*, int* rank, int* world);
 int davo_allgather_poses(davo_ctx*, void* nccl_comm, const float* local_dev, int n_local,
                          float* all_dev, void* cuda_stream);
 
+/* --- on-device trajectory composition and KITTI evaluation ---
+ * davo_compose_trajectory stands in for the host loop of reference test_kitti_pose.py:136-149 at its shipped
+ * --batch_size 1: rel = [T(pose[0,0])] + [inv(T(pose[s,1])) for every sample s] with T = pose_vec2mat
+ * (utils/geo_utils.py:12-63, 93-119, fp32 like the TF graph), P_0 = I, P_{i+1} = P_i . rel_i in fp64 -- as a
+ * blocked parallel prefix product instead of a sequential chain.
+ *   poses_dev  device, float  [n_samples, 2, 6] (what davo_forward / davo_allgather_poses wrote)
+ *   traj_dev   device, double [n_samples + 2, 4, 4] absolute poses, row-major
+ * davo_kitti_errors stands in for calcSequenceErrors + saveStats of the reference's KITTI devkit
+ * (kitti_benchmark/cpp/test_odometry_all.cpp:44-125, 395-404): segment lengths 100..800 m, first frames every 10
+ * frames, distances accumulated in float in frame order as the devkit does.
+ *   gt_dev, res_dev  device, double [n_frames, 4, 4]
+ *   seg_dev          device, davo_kitti_segment [ceil(n_frames / 10) * 8] or NULL; last_frame = -1: the sequence
+ *                    is too short for that (first_frame, length)
+ *   stats_host       host, float [3]: mean t_err (per metre), mean r_err (rad per metre), number of segments --
+ *                    the two numbers of <seq>-stats.txt.  Synchronises the stream. */
+typedef struct davo_kitti_segment {
+  int32_t first_frame, last_frame;
+  float r_err, t_err, len, speed;       /* as the devkit's `errors` struct (:16-24): errors already divided by len */
+} davo_kitti_segment;
+int davo_compose_trajectory(davo_ctx*, const float* poses_dev, int n_samples, double* traj_dev, void* cuda_stream);
+int davo_kitti_errors(davo_ctx*, const double* gt_dev, const double* res_dev, int n_frames,
+                      davo_kitti_segment* seg_dev, float* stats_host, void* cuda_stream);
+
 const char* davo_last_error(const davo_ctx*);   /* NULL handle -> last create error */
 void davo_destroy(davo_ctx*);
 const char* davo_build_info(void);              /* arch / compiler string */

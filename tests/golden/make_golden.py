@@ -80,6 +80,12 @@ CASES = {
     "depthseg_seplayers": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow_on_depthseg_seplayers_40-abs_flow-fc_tanh",
     "spp21_mix_segflow": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_spp21_mixSegFlow-norm_flow-fc_tanh",
     "segflow_8_wo_tgt": "v0-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_SegFlow_to_seg_8_wo_tgt-fc_lrelu",
+    # the per-pixel (se_block) sources inside the non-shared nets: one evaluation per sample on (tgt, src0, src1)
+    "pix_rgb_net": "v1-dilatedPoseNN-cnv6_128-segmask_all-se_rgb-fc_tanh",
+    "pix_mix_segflow_net": "v1-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_mixSegFlow-abs_flow-norm_flow-fc_tanh",
+    "pix_mix_depthflow_net": "v0-cnv6_128-segmask_rgb-se_mixDepthFlow-norm_depth-norm_flow-fc_lrelu",
+    "pix_disp_wo_tgt_net": "v1-couplePoseNN-cnv6_64-segmask_all-se_disp_wo_tgt-fc_tanh",
+    "spp21_mix_segflow_net": "v1-dilatedPoseNN-cnv6_128-segmask_all-se_spp21_mixSegFlow-norm_flow-fc_tanh",
 }
 # version strings the reference itself cannot build, with the exception its graph code raises (checked by the generator)
 REFERENCE_RAISES = {

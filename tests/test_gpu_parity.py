@@ -300,21 +300,24 @@ def test_compact_host_inputs_equal_the_widened_float_inputs(key):
     assert sysm.last_host_copy_bytes()[0] == 5 * (hw * 9 + (hw * 8 if uses_flow else 0) + hw * n_lab)
 
 
-def test_exact_flow_mode_meets_the_tight_class_weight_tolerance():
+@pytest.mark.parametrize("key", ["headline", "gp2x2_flow_nobottle"])
+def test_exact_flow_mode_meets_the_tight_class_weight_tolerance(key):
     """with the float32 flow (default) the SE class weights agree with the fp64 reference run to
-    1e-6 relative; with the opt-in binary16 flow they cannot (the pooled values themselves are rounded)."""
+    ~1e-6 relative.  The opt-in binary16 flow rounds the pooled values themselves: invisible behind the saturated
+    tanh of the headline variant, visible with -norm_flow (quadrant means of normalised flow, unsaturated)."""
     _need_gpu()
-    g = G.GOLDEN
-    w = S.init_weights(HEADLINE, seed=g["weight_seed"], random_bias=True)
+    ver, g = G.CASES[key], G.GOLDEN
+    w = S.init_weights(ver, seed=g["weight_seed"], random_bias=True)
     inputs = S.make_inputs(g["batch"], H, W, seed=g["input_seed"], bad_label_frac=g["bad_label_frac"])
     err = {}
     for f16 in (False, True):
-        sysm, _ = _system(HEADLINE, g["batch"], w, inputs, flow_f16=f16)
+        sysm, _ = _system(ver, g["batch"], w, inputs, flow_f16=f16)
         sysm.inference(None, "pose")
         got = np.stack([sysm.get_intermediate("att_weights", p) for p in range(4)]).reshape(2, 2, 19)
-        err[f16] = float(np.abs(got / GOLD["headline/att_w"] - 1).max())
-    assert err[False] < 1e-6, err
-    assert err[False] < err[True] < 3e-5, err
+        err[f16] = float(np.abs(got / GOLD[key + "/att_w"] - 1).max())
+    print(key, "class-weight error, float32 / binary16 flow:", err)
+    assert err[False] < 2e-6, err
+    assert err[False] <= err[True] < 1e-4, err
 
 
 def test_linearity_of_the_head_in_pred_weights():
@@ -686,3 +689,51 @@ def test_feature_mode_limits():
     torch.cuda.synchronize()
     a = att.cpu().numpy()
     assert np.all(a[0] == 1) and a[1:].min() >= 0 and a[1:].max() <= 1 and a[1:].std() > 0
+
+
+def test_on_device_trajectory_composition_and_kitti_errors():
+    """davo_compose_trajectory (batched pose_vec2mat + blocked prefix product) against the host loop of
+    geo_utils.compose_trajectory (reference test_kitti_pose.py:136-149), and davo_kitti_errors against the oracle's
+    restatement of the reference's C++ devkit (itself held to the devkit binary in tests/test_oracle.py): the same
+    segments frame for frame, errors to float rounding."""
+    _need_gpu()
+    from davo_b200 import evaluation
+    from oracle import kitti_eval
+    from tests.test_oracle import _kitti_like_poses
+    rng = np.random.default_rng(9)
+    sysm = DAVO(version=HEADLINE)
+    sysm.setup_inference(H, W, "davo", 3, 1, device=0)
+    for n in (1, 2, 255, 256, 257, 1100, 4539):
+        base = _kitti_like_poses(n, rng)
+        host = geo_utils.compose_trajectory(base)
+        dev = evaluation.compose_trajectory_gpu(sysm, torch.as_tensor(base).cuda())
+        assert dev.is_cuda and dev.dtype == torch.float64 and tuple(dev.shape) == (n + 2, 4, 4)
+        got = dev.cpu().numpy()
+        assert np.array_equal(got[0], np.eye(4)) and np.all(got[:, 3] == [0, 0, 0, 1])
+        path = float(np.linalg.norm(np.diff(host[:, :3, 3], axis=0), axis=1).sum())
+        # fp32 sin / cos and the fp32 LAPACK inverse of the host loop vs cosf / sinf and an fp64 inverse here
+        assert np.abs(got - host)[:, :3, 3].max() <= 2e-6 * path + 1e-6, (n, np.abs(got - host).max(), path)
+        assert np.abs(got - host)[:, :3, :3].max() <= 2e-5
+    n = 1100
+    base = _kitti_like_poses(n, rng)
+    noisy = base.copy()
+    noisy[:, 1] += (rng.normal(0, 1, size=(n, 6)) * np.array([2e-4, 2e-4, 2e-4, 0.01, 0.01, 0.01])).astype(np.float32)
+    gt, res = geo_utils.compose_trajectory(base), geo_utils.compose_trajectory(noisy)
+    want = kitti_eval.sequence_errors(gt, res)
+    out = evaluation.kitti_errors_gpu(sysm, gt, res, segments=True)
+    seg = out["segments"][out["segments"]["last_frame"] >= 0]
+    assert out["num"] == len(want) == len(seg) > 200
+    assert [int(v) for v in seg["first_frame"]] == [e[0] for e in want] and [int(v) for v in seg["last_frame"]] == [e[1] for e in want]
+    np.testing.assert_allclose(seg["r_err"], [e[2] for e in want], rtol=2e-4, atol=2e-9)
+    np.testing.assert_allclose(seg["t_err"], [e[3] for e in want], rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(seg["speed"], [e[5] for e in want], rtol=1e-6)
+    t_mean, r_mean = kitti_eval.stats(want)
+    assert abs(out["t_err"] - t_mean) <= 1e-5 * t_mean and abs(out["r_err"] - r_mean) <= 2e-4 * r_mean
+    # identical trajectories score zero; a short sequence has no segments; 3x4 inputs are accepted
+    same = evaluation.kitti_errors_gpu(sysm, gt[:, :3], gt[:, :3])
+    assert same["num"] == len(want) and same["t_err"] < 1e-6 and same["r_err"] < 1e-6
+    assert evaluation.kitti_errors_gpu(sysm, gt[:50], res[:50])["num"] == 0
+    # device-resident end to end: poses -> trajectory -> errors without leaving the GPU
+    dev_res = evaluation.compose_trajectory_gpu(sysm, torch.as_tensor(noisy).cuda())
+    chained = evaluation.kitti_errors_gpu(sysm, torch.as_tensor(gt).cuda(), dev_res)
+    assert chained["num"] == len(want) and abs(chained["t_err"] - t_mean) <= 1e-3 * t_mean

@@ -312,3 +312,52 @@ def test_trajectory_file_is_read_by_the_reference_devkit(tmp_path):
              for seq in (0, 10)}
     assert stats[0][0] < 1e-5 and stats[0][1] < 1e-7           # identical files: zero translation / rotation error
     assert abs(stats[10][0] - 0.02) < 2e-3                      # 2 % scale error reads as 2 % translation error
+
+
+def _kitti_like_poses(n, rng, noise=0.0):
+    poses = np.zeros((n, 2, 6), np.float32)
+    poses[:, 1, :3] = rng.normal(0, 4e-3, size=(n, 3))                  # small rotations
+    poses[:, 1, 3:] = np.array([0.0, 0.0, -1.0]) + rng.normal(0, 0.02, size=(n, 3))     # one metre per frame
+    poses[:, 0, 3:] = [0.0, 0.0, 1.0]
+    if noise:
+        poses[:, 1] += rng.normal(0, noise, size=(n, 6)).astype(np.float32) * np.array([0.1, 0.1, 0.1, 1, 1, 1], np.float32)
+    return poses
+
+
+def test_kitti_eval_restatement_matches_the_reference_devkit(tmp_path):
+    """oracle/kitti_eval.py (calcSequenceErrors + saveStats restated) against the reference's own C++ devkit run on
+    the same files: per-segment records of errors/NN.txt and the two numbers of NN-stats.txt."""
+    import subprocess
+    from oracle import kitti_eval, ref_build
+    from davo_b200 import geo_utils
+    devkit = ref_build.build()
+    if devkit is None:
+        pytest.skip("reference devkit not built and reference tree not on this box")
+    rng = np.random.default_rng(9)
+    gt_dir, res_dir = tmp_path / "data" / "odometry" / "poses", tmp_path / "results" / "x" / "data"
+    gt_dir.mkdir(parents=True)
+    res_dir.mkdir(parents=True)
+    trajs = {}
+    for seq in range(11):
+        n = 1100 if seq < 2 else 150                                  # two long sequences (all eight lengths), nine short ones
+        base = _kitti_like_poses(n, rng)
+        noisy = base.copy()
+        noisy[:, 1] += (rng.normal(0, 1, size=(n, 6)) * np.array([2e-4, 2e-4, 2e-4, 0.01, 0.01, 0.01])).astype(np.float32)
+        gt, res = geo_utils.compose_trajectory(base), geo_utils.compose_trajectory(noisy)
+        geo_utils.write_kitti_trajectory(str(gt_dir / ("%02d.txt" % seq)), gt)
+        geo_utils.write_kitti_trajectory(str(res_dir / ("%02d.txt" % seq)), res)
+        trajs[seq] = (gt, res)
+    out = subprocess.run([devkit, "x"], cwd=str(tmp_path), capture_output=True, text=True, timeout=300).stdout
+    assert "Done." in out, out[-2000:]
+    for seq in (0, 1, 5):
+        errs = kitti_eval.sequence_errors(*trajs[seq])
+        rows = [[float(v) for v in line.split()] for line in (tmp_path / "results" / "x" / "errors" / ("%02d.txt" % seq)).read_text().splitlines()]
+        assert len(rows) == len(errs), (seq, len(rows), len(errs))
+        for row, e in zip(rows, errs):                                # "%d %f %f %f %f": first_frame r_err t_err len speed
+            assert int(row[0]) == e[0] and row[3] == e[4]
+            assert abs(row[1] - e[2]) <= 1.5e-6 and abs(row[2] - e[3]) <= 1.5e-6 and abs(row[4] - e[5]) <= 1e-4 * e[5] + 1e-6
+        if errs:
+            t_mean, r_mean = kitti_eval.stats(errs)
+            want = [float(v) for v in (tmp_path / "results" / "x" / ("%02d-stats.txt" % seq)).read_text().split()]
+            assert abs(want[0] - t_mean) <= 1.5e-6 and abs(want[1] - r_mean) <= 1.5e-6
+    assert len(kitti_eval.sequence_errors(*trajs[0])) > 200 and len(kitti_eval.sequence_errors(*trajs[5])) > 0

@@ -79,8 +79,12 @@ def test_per_pixel_sources():
     assert (c.att_src, c.att_tgt_ones, c.pixel_map, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 0, 2, 1, 1)
     c = V.parse_version(BASE + "-segmask_all-se_mixDispFlow-norm_depth")             # davo.py:1166-1174
     assert (c.att_src, c.att_tgt_ones, c.pixel_map, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 0, 2, 2, 1)
-    with pytest.raises(NotImplementedError, match="sharedNN"):
-        V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_rgb")
+    c = V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_rgb")              # the non-shared nets take them too
+    assert (c.posenn, c.att_src, c.pixel_map) == (V.POSENN_DECOUPLE_DIL, V.ATT_SE_RGB_SEG, 1)
+    with pytest.raises(UnboundLocalError):                                           # capital "Disp": input_depth is never read (davo.py:960, 1167)
+        V.parse_version(BASE + "-segmask_all-se_mixDispFlow")
+    with pytest.raises(NotImplementedError, match="sharedNN"):                       # the depth split stays shared-net only
+        V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_flow_on_depthseg_seplayers")
 
 
 def test_order_sensitive_tokens():
@@ -136,9 +140,9 @@ def test_unbuilt_sources_fail_loudly(tok):
         V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
 
 
-def test_depth_variants_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_depth_wo_tgt-fc_tanh")   # per-pixel source in a non-shared net
+def test_depth_variants():
+    c = V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_depth_wo_tgt-fc_tanh")     # per-pixel source in a non-shared net
+    assert (c.posenn, c.att_src, c.pixel_map, c.att_tgt_ones) == (V.POSENN_DECOUPLE_DIL, V.ATT_SE_DEPTH_SEG, 1, 1)
     c = V.parse_version(BASE + "-segmask_all-se_depth_wo_tgt_to_seg-norm_depth-fc_tanh")     # davo.py:1211-1219
     assert (c.att_src, c.att_tgt_ones, c.depth_norm, c.needs_depth) == (V.ATT_SE_DEPTH_SEG, 1, 1, 1)
     assert V.parse_version(BASE + "-segmask_all-se_depth_to_seg").att_tgt_ones == 0
