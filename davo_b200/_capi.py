@@ -31,7 +31,7 @@ class DavoConfigC(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "H", "W", "max_batch", "posenn", "cnv6_out", "in_mode", "att_src", "att_tgt_ones",
         "mask_mode", "se_act", "flow_abs", "flow_norm", "posenn_se", "micro_batch", "depth_norm", "se_pool", "se_hidden",
-        "pixel_map", "depth_split", "flow_f16")]
+        "pixel_map", "depth_split", "flow_f16", "batch_norm")]
 
 
 class DavoFeaturesC(C.Structure):

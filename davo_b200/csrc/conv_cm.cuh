@@ -62,6 +62,7 @@ struct ConvParams {
   int patch_bytes;                // Hp * Wp * 128 (what TMA delivers)
   int patch_stage_bytes;          // rounded up to 1024
   int p_stages, w_stages;         // ring depths
+  int raw;                        // store epilogue: 1 = plain fp32 sums, no relu, no rounding (-batch_norm: bn.cuh finishes the layer)
   float* out;           // EPI_STORE: [pairs][Hout][Wout][out_stride]
   const float* bias;    // [groups * cout_g]
   float* sum_out;       // EPI_SUM:   [pairs][groups][tiles_h*tiles_w][cout_g]
@@ -133,6 +134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   constexpr int kTmemCols = 2 * NPIX;
 
   pdl_launch_dependents();
+  const EpiAct ea = epi_act(p.raw);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // known warp-uniform to the compiler
   const int lane = threadIdx.x & 31;
   const int rank = CLUSTER ? (int)cluster_ctarank() : 0;
@@ -287,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                v[j] = __float_as_uint(round_tf32_finite(fmaxf(__uint_as_float(v[j]) + bias, 0.f)));
+                v[j] = __float_as_uint(epi_out(__uint_as_float(v[j]) + bias, ea));
               if (lane == 0) tma_store_wait_read<0>();    // the previous store has read the buffer
               __syncwarp();
 #pragma unroll
@@ -314,7 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               const int hh = hb + (j >> 3), ww = tc.w0 + (j & 7);
               if (co_ok && hh < p.Hout && ww < p.Wout)
                 obase[((size_t)hh * p.Wout + ww) * pix_stride] =
-                    round_tf32(fmaxf(__uint_as_float(v[j]) + bias, 0.f));
+                    epi_out(__uint_as_float(v[j]) + bias, ea);
             }
           }
         }

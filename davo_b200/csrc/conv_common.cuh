@@ -37,6 +37,23 @@ struct TapDesc {
 
 enum { EPI_STORE_RELU = 0, EPI_SUM_RELU = 1 };
 
+// What a store epilogue writes for the accumulator value x (+ bias): relu, rounded to TF32 (ties away, the integer
+// form of cvt.rna: add half an ulp to the magnitude, clear 13 bits) for the next layer's tensor-core read -- or,
+// ConvParams::raw (the -batch_norm variants), the plain fp32 convolution sum, which the batch-norm kernels then
+// normalise, activate and round (bn.cuh).  The mode lives in three per-thread constants, so the hot path pays
+// nothing for it: max(x, 0 | -inf), + 0x1000 | 0, & 0xFFFFE000 | 0xFFFFFFFF.
+struct EpiAct { float lo; uint32_t add, mask; };
+__device__ __forceinline__ EpiAct epi_act(int raw) {
+  EpiAct a;
+  a.lo = raw ? __uint_as_float(0xFF800000u) : 0.f;
+  a.add = raw ? 0u : 0x1000u;
+  a.mask = raw ? 0xFFFFFFFFu : 0xFFFFE000u;
+  return a;
+}
+__device__ __forceinline__ float epi_out(float x, const EpiAct& a) {
+  return __uint_as_float((__float_as_uint(fmaxf(x, a.lo)) + a.add) & a.mask);
+}
+
 // Ordering of the tensor-core reads after a TMA-fed mbarrier wait.  The wait itself orders the
 // async-proxy writes of TMA before what the waiting thread issues next; -DDAVO_MMA_FENCES=1
 // adds the explicit tcgen05.fence for A/B comparison.

@@ -72,6 +72,7 @@ struct ConvParams {
   int tile_h, tile_w;             // tile = tile_h output rows x tile_w runs (tile_h * tile_w = 128)
   int run_px;                     // G: output pixels per run (per M row)
   int b_boxes, b_box_rows;        // resident weights: one TMA box of b_box_rows rows per filter row
+  int raw;                        // store epilogue: 1 = plain fp32 sums, no relu, no rounding (-batch_norm: bn.cuh finishes the layer)
   float* out;           // EPI_STORE: [pairs][Hout][Wout][out_stride]
   const float* bias;    // [groups * BN]
   float* sum_out;       // EPI_SUM:   [pairs][groups][tiles_h*tiles_w][4][BN]
@@ -114,6 +115,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarrierBytes);
 
   pdl_launch_dependents();
+  const EpiAct ea = epi_act(p.raw);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // known warp-uniform to the compiler
   const int lane = threadIdx.x & 31;
 #ifdef DAVO_TIMING
@@ -298,10 +300,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 8; ++j) {
             const float4 b = lds_v4(bias_a + (c0 + 4 * j) * 4);
             float4 o;
-            o.x = round_tf32_finite(fmaxf(__uint_as_float(v[4 * j + 0]) + b.x, 0.f));
-            o.y = round_tf32_finite(fmaxf(__uint_as_float(v[4 * j + 1]) + b.y, 0.f));
-            o.z = round_tf32_finite(fmaxf(__uint_as_float(v[4 * j + 2]) + b.z, 0.f));
-            o.w = round_tf32_finite(fmaxf(__uint_as_float(v[4 * j + 3]) + b.w, 0.f));
+            o.x = epi_out(__uint_as_float(v[4 * j + 0]) + b.x, ea);
+            o.y = epi_out(__uint_as_float(v[4 * j + 1]) + b.y, ea);
+            o.z = epi_out(__uint_as_float(v[4 * j + 2]) + b.z, ea);
+            o.w = epi_out(__uint_as_float(v[4 * j + 3]) + b.w, ea);
             sts_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), o);
           }
           fence_proxy_async_smem();
@@ -332,10 +334,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < LPP; ++j) {
             float4 o;
-            o.x = round_tf32(fmaxf(__uint_as_float(v[4 * j + 0]) + bias[c0 + 4 * j + 0], 0.f));
-            o.y = round_tf32(fmaxf(__uint_as_float(v[4 * j + 1]) + bias[c0 + 4 * j + 1], 0.f));
-            o.z = round_tf32(fmaxf(__uint_as_float(v[4 * j + 2]) + bias[c0 + 4 * j + 2], 0.f));
-            o.w = round_tf32(fmaxf(__uint_as_float(v[4 * j + 3]) + bias[c0 + 4 * j + 3], 0.f));
+            o.x = epi_out(__uint_as_float(v[4 * j + 0]) + bias[c0 + 4 * j + 0], ea);
+            o.y = epi_out(__uint_as_float(v[4 * j + 1]) + bias[c0 + 4 * j + 1], ea);
+            o.z = epi_out(__uint_as_float(v[4 * j + 2]) + bias[c0 + 4 * j + 2], ea);
+            o.w = epi_out(__uint_as_float(v[4 * j + 3]) + bias[c0 + 4 * j + 3], ea);
             *reinterpret_cast<float4*>(stg + lane * RB + ((j ^ (lane & (LPP - 1))) << 4)) = o;
           }
           __syncwarp();

@@ -33,6 +33,7 @@
 #include "features.cuh"
 #include "comm.cuh"
 #include "trajectory.cuh"
+#include "bn.cuh"
 #include "host_convert.h"
 
 using namespace davo;
@@ -196,6 +197,7 @@ struct Layer {
   int wide_tw = 0;             //   runs per tile row (tile = 128/wide_tw rows x wide_tw runs)
   int pc2w[16];                // input tensor channel -> HWIO input channel of the weights, -1: none (cnv1: packed input)
   int smem_bytes = 0;
+  float* d_beta = nullptr;     // -batch_norm: BatchNorm/beta of this layer [out_stride] (bn.cuh)
   CUtensorMap tmA, tmB;          // activation (patch) map, weight map
   CUtensorMap tmO;               // pm store epilogue: output tiles (TMA store)
   CUtensorMap tmB64;             // cm clusters: weight map with a 64-row box (half a slab per CTA)
@@ -243,6 +245,8 @@ struct davo_ctx {
   uint16_t *h_flow16[kStage] = {}, *s_flow16[kStage] = {};
   bool host_flow16 = true;
   int numa_node = -1, numa_cpus = 0;      // davo_bind_host_numa
+  double* d_bn_part = nullptr;            // -batch_norm scratch: partial sums, means, reciprocal deviations (bn.cuh)
+  float *d_bn_mean = nullptr, *d_bn_rstd = nullptr;
   void* d_traj_scratch = nullptr;         // davo_compose_trajectory / davo_kitti_errors: relative motions, distances, segments
   size_t traj_scratch_bytes = 0;
   const uint16_t* cur_flow16 = nullptr;   // binary16 flow of the chunk being enqueued (NULL: float flow) ...
@@ -890,6 +894,7 @@ template <int BN, int EPI, bool RES>
 int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   if (int rc = ensure_smem(ctx, pm::conv_tc_kernel<BN, EPI, RES>, L.smem_bytes)) return rc;
   pm::ConvParams P = L.prm_pm;
+  P.raw = ctx->cfg.batch_norm ? 1 : 0;
   P.num_tiles = npairs * L.groups * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
@@ -902,6 +907,7 @@ int launch_pm_wide(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   auto* kern = pm::conv_tc_kernel<128, EPI_STORE_RELU, true, true>;
   if (int rc = ensure_smem(ctx, kern, L.smem_bytes)) return rc;
   pm::ConvParams P = L.prm_pm;
+  P.raw = ctx->cfg.batch_norm ? 1 : 0;
   P.num_tiles = npairs * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
@@ -918,6 +924,7 @@ template <int NPIX, int EPI, bool STAGED = false>
 int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   if (int rc = ensure_smem(ctx, cm::conv_tc_kernel<NPIX, EPI, STAGED>, L.smem_bytes)) return rc;
   cm::ConvParams P = L.prm_cm;
+  P.raw = ctx->cfg.batch_norm ? 1 : 0;
   P.num_tiles = npairs * L.groups * L.tiles_h * L.tiles_w * L.m_blocks;
   P.out = L.d_out;
   P.sum_out = ctx->d_sum7;
@@ -946,6 +953,7 @@ int launch_cm_cluster(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st
     if (getenv("DAVO_B200_VERBOSE")) fprintf(stderr, "[davo_b200] %s: %d active 2-CTA clusters\n", L.name, max_clusters);
   }
   cm::ConvParams P = L.prm_cm;
+  P.raw = ctx->cfg.batch_norm ? 1 : 0;
   P.num_pixel_tiles = npairs * L.tiles_h * L.tiles_w;
   P.num_tiles = ((P.num_pixel_tiles + 1) / 2) * L.groups * L.m_blocks;
   P.out = L.d_out;
@@ -1103,20 +1111,45 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
   for (size_t li = 0; li < ctx->layers.size(); ++li) {
     Layer& L = ctx->layers[li];
     const int pse = ctx->cfg.posenn_se;
-    if (li == 5 && (pse == 1 || pse == 3)) {       // -se_insert: excite cnv5 per branch in front of cnv6; -se_replace: instead of it
+    auto se5 = [&](int skipadd) -> int {
       Se5Params sp;
-      sp.npairs = npairs; sp.hw = L.Hin * L.Win; sp.nbr = ctx->nbr; sp.stack = pse == 1;
-      sp.cnv5 = ctx->layers[4].d_out; sp.w = ctx->d_se5w; sp.part = ctx->d_se5part; sp.count = ctx->d_se5cnt;
+      memset(&sp, 0, sizeof sp);
+      sp.npairs = npairs; sp.hw = ctx->layers[5].Hin * ctx->layers[5].Win; sp.nbr = ctx->nbr; sp.stack = pse == 1; sp.skipadd = skipadd;
+      sp.cnv5 = ctx->layers[4].d_out; sp.cnv6 = ctx->layers[5].d_out; sp.w = ctx->d_se5w; sp.part = ctx->d_se5part; sp.count = ctx->d_se5cnt;
       sp.scale = ctx->d_se5scale; sp.out = ctx->d_se5out;
       if (int rc = launch_k(ctx, se5_excite_kernel, dim3(kSe5Splits, npairs), dim3(256), 0, st, false, sp)) return rc;
       const long long total = (long long)npairs * sp.hw * 64;
       if (int rc = launch_k(ctx, se5_scale_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, false, sp)) return rc;
       *launches += 2;
+      return 0;
+    };
+    if (li == 5 && (pse == 1 || pse == 3)) {       // -se_insert: excite cnv5 per branch in front of cnv6; -se_replace: instead of it
+      if (int rc = se5(0)) return rc;
       if (pse == 3) continue;                      // cnv6 := se_block(cnv5): there is no cnv6 convolution (posenn.py:234-236)
     }
     int rc = ctx->conv_impl == 0 ? launch_conv(ctx, L, npairs, st) : launch_conv_direct(ctx, L, npairs, st);
     if (rc) return rc;
     *launches += (ctx->conv_impl == 0) ? 1 : L.groups;
+    if (li == 5 && pse == 2)                       // -se_skipadd: cnv6 := relu(cnv5 + se_block(cnv6)) (posenn.py:229-233)
+      if (int rc2 = se5(1)) return rc2;
+    if (ctx->cfg.batch_norm) {                     // the conv wrote plain sums: normalise with this call's batch statistics
+      BnParams bp;
+      memset(&bp, 0, sizeof bp);
+      bp.units = npairs; bp.pair0 = pair0; bp.pair_mode = pair_mode;
+      bp.ngroups = (!ctx->unit_sample && pair_mode == DAVO_PAIRS_ALL) ? 2 : 1;
+      bp.H = L.Hout; bp.W = L.Wout; bp.Hp = L.Hout_p; bp.Wp = L.Wout_p; bp.C = L.out_stride;
+      bp.x = L.d_out; bp.beta = L.d_beta; bp.part = ctx->d_bn_part; bp.mean = ctx->d_bn_mean; bp.rstd = ctx->d_bn_rstd;
+      bp.sum_out = ctx->d_sum7;
+      if (int rc2 = launch_k(ctx, bn_stats_kernel, dim3(kBnSplits, bp.ngroups), dim3(256), 0, st, false, bp)) return rc2;
+      if (int rc2 = launch_k(ctx, bn_finalize_kernel, dim3(bp.ngroups), dim3(256), 0, st, false, bp)) return rc2;
+      if (li + 1 == ctx->layers.size()) {
+        if (int rc2 = launch_k(ctx, bn_apply_sum_kernel, dim3(npairs), dim3(256), 0, st, false, bp)) return rc2;
+      } else {
+        const long long total = (long long)npairs * L.Hout * L.Wout * (L.out_stride / 4);
+        if (int rc2 = launch_k(ctx, bn_apply_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, false, bp)) return rc2;
+      }
+      *launches += 3;
+    }
   }
   const Layer& L7 = ctx->layers.back();
   if (ctx->conv_impl != 0) {
@@ -1187,13 +1220,17 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   *out = nullptr;
   if (cfg->posenn < 0 || cfg->posenn > 5)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d unknown (0..5, posenn.py:12-378)", cfg->posenn);
-  if (cfg->posenn_se != 0 && cfg->posenn_se != 1 && cfg->posenn_se != 3)
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d is not built (-se_insert and -se_replace are)", cfg->posenn_se);
+  if (cfg->posenn_se < 0 || cfg->posenn_se > 3)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d unknown (1 insert, 2 skipadd, 3 replace)", cfg->posenn_se);
+  if (cfg->batch_norm != 0 && (cfg->batch_norm != 1 || cfg->posenn_se != 0))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: batch_norm is 0 or 1 and is not built together with a PoseNN-internal SE block");
+  if (cfg->posenn_se == 2 && cfg->cnv6_out != 256)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: -se_skipadd adds cnv5 (256 channels) to se_block(cnv6): cnv6 width must be 256, got %d", cfg->cnv6_out);
   if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: H and W must be positive multiples of 8 (got %dx%d)", cfg->H, cfg->W);
   if (cfg->max_batch <= 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: max_batch must be positive");
-  if (cfg->cnv6_out != 128 && cfg->cnv6_out != 64 && cfg->cnv6_out != 32)
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128)", cfg->cnv6_out);
+  if (cfg->cnv6_out != 128 && cfg->cnv6_out != 64 && cfg->cnv6_out != 32 && !(cfg->cnv6_out == 256 && cfg->posenn_se == 2))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128; 256 with -se_skipadd)", cfg->cnv6_out);
   if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
   if (cfg->att_src < 0 || cfg->att_src > 6) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
   if (cfg->se_pool < 0 || cfg->se_pool > 4 || cfg->se_hidden < 0 || cfg->se_hidden > 19 ||
@@ -1313,13 +1350,16 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   const bool se5 = c.posenn_se == 1;
   // -se_replace: cnv6 IS the excited cnv5 (256 channels per branch); cnv7 reads the scaled copies directly
   const bool rep = c.posenn_se == 3;
+  // -se_skipadd: cnv6 (256 channels per branch, one N = nbr*256 GEMM) feeds an SE block and is added to cnv5; cnv7
+  // reads relu(cnv5 + se_block(cnv6)) from the same per-branch buffer -se_replace uses
+  const bool skip = c.posenn_se == 2;
   const int c7in = rep ? 256 : c6;
   // Packed PoseNN input (frontend.cuh: pack_kernel): 8 channels per pixel when the width allows the
   // column-widened cnv1 plan (runs of 16 input pixels), else the 16-channel layout of the plain plan.
   const char* wide_env0 = getenv("DAVO_B200_WIDE");
   // (the per-pixel attention maps are computed by the 16-channel pack_kernel only)
   ctx->packed_c = (!ctx->unit_sample && !c.pixel_map && !c.depth_split && (c.W % 16) == 0 && !(wide_env0 && !strcmp(wide_env0, "0"))) ? 8 : 16;
-  const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? nbr * 256 : 256, nbr * c7in};
+  const int cin_total[7] = {ctx->packed_c, 16, 32, 64, 128, se5 ? nbr * 256 : 256, nbr * c7in};   // skip: c6 == 256, so cnv7 reads nbr*256 as well
   const int cin_g[7] = {ctx->packed_c, 16, 32, 64, 128, 256, c7in};
   const int cin_w[7] = {cin1, 16, 32, 64, 128, 256, c7in};
   const char* names[7] = {"cnv1", "cnv2", "cnv3", "cnv4", "cnv5", "cnv6", "cnv7"};
@@ -1336,9 +1376,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     SamePad ph = same_pad(H, L.k, L.stride, L.dil), pw = same_pad(W, L.k, L.stride, L.dil);
     L.Hout = ph.out; L.Wout = pw.out; L.pad_t = ph.before; L.pad_l = pw.before;
     L.Hout_p = L.Hout + (L.Hout & 1 && L.Hout > 1 ? 1 : 0); L.Wout_p = L.Wout + (L.Wout & 1 ? 1 : 0);
-    if (i == 6) { L.Hout_p = L.Hout; L.Wout_p = L.Wout; }      // cnv7 is never stored
+    if (i == 6 && !c.batch_norm) { L.Hout_p = L.Hout; L.Wout_p = L.Wout; }      // cnv7 is never stored ...
     L.out_stride = cout_total[i];
-    L.epi = (i == 6) ? EPI_SUM_RELU : EPI_STORE_RELU;
+    L.epi = (i == 6 && !c.batch_norm) ? EPI_SUM_RELU : EPI_STORE_RELU;   // ... except under -batch_norm, whose statistics need the whole map
     // Orientation (measured): channels-on-M for the wide stride-1 layers whose
     // maps are tall enough for a 32-row tile; pixels-on-M for thin layers and the summed cnv7.
     const char* force = getenv("DAVO_B200_ORIENT");          // debug: "pm" or "cm" for every layer
@@ -1414,34 +1454,52 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   float* prev = ctx->d_packed;
   for (int i = 0; i < 7; ++i) {
     Layer& L = ctx->layers[i];
-    if (i == 5 && (se5 || rep)) {
+    if (i == 5 && (se5 || rep || skip)) {
       const size_t hw5 = (size_t)L.Hin * L.Win;
-      if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5part, (size_t)mb * kSe5Splits * 256 * 4)) return rc;
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5part, (size_t)mb * kSe5Splits * 256 * (skip ? nbr : 1) * 4)) return rc;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5cnt, (size_t)mb * 4)) return rc;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5scale, (size_t)mb * 2 * 256 * 4)) return rc;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5out, (size_t)mb * hw5 * nbr * 256 * 4)) return rc;
-      prev = ctx->d_se5out;
+      if (!skip) prev = ctx->d_se5out;          // skip: cnv6 still reads cnv5; cnv7 reads d_se5out (below)
     }
-    L.d_in = prev;
+    L.d_in = (i == 6 && skip) ? ctx->d_se5out : prev;
     if (i == 5 && rep) continue;                   // no cnv6 convolution and no buffer: cnv7 reads d_se5out
-    if (i < 6) {
+    if (i < 6 || c.batch_norm) {
       if (int rc = dev_alloc(ctx, (void**)&L.d_out, (size_t)mb * L.Hout_p * L.Wout_p * L.out_stride * 4)) return rc;
       prev = L.d_out;
     }
   }
   {
     const Layer& L7 = ctx->layers[6];
-    ctx->nparts7 = L7.tiles_h * L7.tiles_w * (L7.orient == 0 ? 4 : 1);
+    ctx->nparts7 = c.batch_norm ? 1 : L7.tiles_h * L7.tiles_w * (L7.orient == 0 ? 4 : 1);    // bn_apply_sum_kernel writes one row per unit
+    if (c.batch_norm) {
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_bn_part, (size_t)2 * kBnSplits * 2 * kBnMaxC * sizeof(double))) return rc;
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_bn_mean, (size_t)2 * kBnMaxC * 4)) return rc;
+      if (int rc = dev_alloc(ctx, (void**)&ctx->d_bn_rstd, (size_t)2 * kBnMaxC * 4)) return rc;
+    }
     if (int rc = dev_alloc(ctx, (void**)&ctx->d_sum7, (size_t)mb * nbr * ctx->nparts7 * 256 * 4)) return rc;
   }
 
   // ---- weights ----
+  // -batch_norm: slim creates <scope>/BatchNorm/beta instead of <scope>/biases for every conv but pred (posenn.py:206, 240).
+  // The beta vector is handed back through `b` (the callers assemble it per output channel exactly like a bias) and
+  // ends up in Layer::d_beta; the conv itself then runs with a zero bias (plan_layer_bn below).
   auto need_conv = [&](const std::string& scope, int k, int ci, int co, const HostTensor** w, const HostTensor** b) -> int {
+    const bool bn_layer = c.batch_norm && scope.size() >= 4 && scope.compare(scope.size() - 4, 4, "pred") != 0;
     *w = find_w(ctx, P + scope + "/weights");
-    *b = find_w(ctx, P + scope + "/biases");
-    if (!*w || !*b) return fail(ctx, DAVO_ERR_WEIGHT, "missing variable %s%s/{weights,biases}", P.c_str(), scope.c_str());
+    *b = find_w(ctx, P + scope + (bn_layer ? "/BatchNorm/beta" : "/biases"));
+    if (!*w || !*b) return fail(ctx, DAVO_ERR_WEIGHT, "missing variable %s%s/{weights,%s}", P.c_str(), scope.c_str(), bn_layer ? "BatchNorm/beta" : "biases");
     if (!shape_is(*w, {k, k, ci, co}) || !shape_is(*b, {co}))
       return fail(ctx, DAVO_ERR_WEIGHT, "variable %s%s has the wrong shape (want [%d,%d,%d,%d])", P.c_str(), scope.c_str(), k, k, ci, co);
+    return 0;
+  };
+  // -batch_norm: the per-channel vector the callers assembled is beta, kept for bn.cuh; the conv adds nothing
+  auto bias_or_beta = [&](Layer& L, const std::vector<float>& v, std::vector<float>* out) -> int {
+    *out = v;
+    if (!c.batch_norm) return 0;
+    if (int rc = dev_alloc(ctx, (void**)&L.d_beta, v.size() * 4)) return rc;
+    CU_OK(cudaMemcpy(L.d_beta, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+    std::fill(out->begin(), out->end(), 0.f);
     return 0;
   };
   for (int i = 0; i < 5; ++i) {
@@ -1450,7 +1508,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     if (int rc = need_conv(names[i], L.k, L.Cin_w, L.BN, &w, &b)) return rc;
     const int Ci = L.Cin_w, Co = L.BN, K = L.k;
     auto getw = [&](int, int ty, int tx, int ci, int n) { return w->data[(((size_t)ty * K + tx) * Ci + ci) * Co + n]; };
-    if (int rc = L.wide_G ? plan_layer_wide(ctx, L, getw, b->data) : plan_layer(ctx, L, getw, b->data)) return rc;
+    std::vector<float> bias;
+    if (int rc = bias_or_beta(L, b->data, &bias)) return rc;
+    if (int rc = L.wide_G ? plan_layer_wide(ctx, L, getw, bias) : plan_layer(ctx, L, getw, bias)) return rc;
   }
   const char* brs[2] = {"rotation", "translation"};
   // variable scope of branch g under pose_exp_net/: pose/rotation/, pose/translation/ (decouple) or pose/ (couple)
@@ -1460,8 +1520,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     const HostTensor *w[2], *b[2];
     for (int g = 0; g < nbr; ++g)
       if (int rc = need_conv(branch_scope(g) + "cnv6", 3, 256, c6, &w[g], &b[g])) return rc;
-    std::vector<float> bias(nbr * c6);
-    for (int n = 0; n < nbr * c6; ++n) bias[n] = b[n / c6]->data[n % c6];
+    std::vector<float> bias0(nbr * c6), bias;
+    for (int n = 0; n < nbr * c6; ++n) bias0[n] = b[n / c6]->data[n % c6];
+    if (int rc = bias_or_beta(L, bias0, &bias)) return rc;
     if (se5) {      // two groups: branch g convolves its own scaled copy of cnv5
       auto getw = [&](int g, int ty, int tx, int ci, int n) {
         return w[g]->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + n];
@@ -1475,12 +1536,12 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
       if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
     }
   }
-  if (se5 || rep) {
-    // reference nets/posenn.py:227 / :236: variables pose/<branch>/cnv5_se_attention/{bottleneck_fc,recover_fc}
-    // (-se_insert) or pose/<branch>/cnv6_se_attention/... (-se_replace)
+  if (se5 || rep || skip) {
+    // reference nets/posenn.py:227 / :232, :236: variables pose/<branch>/cnv5_se_attention/{bottleneck_fc,recover_fc}
+    // (-se_insert) or pose/<branch>/cnv6_se_attention/... (-se_skipadd, -se_replace)
     std::vector<float> sw;
     for (int g = 0; g < nbr; ++g) {
-      const std::string S = P + branch_scope(g) + (rep ? "cnv6_se_attention/" : "cnv5_se_attention/");
+      const std::string S = P + branch_scope(g) + ((rep || skip) ? "cnv6_se_attention/" : "cnv5_se_attention/");
       const HostTensor* w1 = find_w(ctx, S + "bottleneck_fc/kernel");
       const HostTensor* b1 = find_w(ctx, S + "bottleneck_fc/bias");
       const HostTensor* w2 = find_w(ctx, S + "recover_fc/kernel");
@@ -1503,8 +1564,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     auto getw = [&](int g, int ty, int tx, int ci, int n) {
       return w[g]->data[(((size_t)ty * 3 + tx) * c7in + ci) * 256 + n];
     };
-    std::vector<float> bias(nbr * 256);
-    for (int n = 0; n < nbr * 256; ++n) bias[n] = b[n / 256]->data[n % 256];
+    std::vector<float> bias0(nbr * 256), bias;
+    for (int n = 0; n < nbr * 256; ++n) bias0[n] = b[n / 256]->data[n % 256];
+    if (int rc = bias_or_beta(L, bias0, &bias)) return rc;
     if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
     if (int rc = dev_alloc(ctx, (void**)&ctx->d_c7tmp, (size_t)mb * L.Hout * L.Wout * nbr * 256 * 4)) return rc;
   }
@@ -1591,9 +1653,13 @@ extern "C" int davo_forward_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t
     return fail(ctx, DAVO_ERR_ARG, "davo_forward: null input buffer");
   CU_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ctx->cfg.batch_norm && !ctx->unit_sample && pairs != DAVO_PAIRS_ALL)
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward: -batch_norm normalises with the statistics of a whole PoseNN call: every pair must be computed (DAVO_PAIRS_ALL)");
   if (ctx->unit_sample) pairs = kUnitsAreSamples;        // both poses come out of one evaluation
   int launches = 0;
   const int total = pairs_selected(pairs, B);
+  if (ctx->cfg.batch_norm && total > ctx->mb)
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward: -batch_norm needs the whole batch in one pass (%d units > micro_batch %d)", total, ctx->mb);
   int last_n = 0;
   if (pairs == DAVO_PAIRS_TRAJECTORY || pairs == DAVO_PAIRS_TRAJECTORY_FIRST)
     CU_OK(cudaMemsetAsync(pose_out, 0, (size_t)B * 12 * sizeof(float), st));
@@ -1653,6 +1719,8 @@ static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img
   if ((ctx->cfg.att_src == 5 || ctx->cfg.depth_split) && !depth) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: this variant reads input_depth; got NULL");
   if (!ctx->finalized) return fail(ctx, DAVO_ERR_STATE, "davo_forward_host: weights not finalized");
   if (B <= 0 || B > ctx->cfg.max_batch) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: B=%d outside 1..%d", B, ctx->cfg.max_batch);
+  if (ctx->cfg.batch_norm)
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: -batch_norm needs the whole batch in one pass; the chunked host entry point does not take it (copy the batch to the device and call davo_forward)");
   const davo_config& c = ctx->cfg;
   if (!img || !pose_out || (c.att_src != 0 && !seg) || ((c.in_mode == 1 || c.att_src == 1 || c.att_src == 6 || c.pixel_map == 2) && !flow))
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: null input buffer");
@@ -2108,7 +2176,8 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
     const Layer& L6 = ctx->layers[5];
     ResizeParams rp;
     rp.B = B; rp.H = c.H; rp.W = c.W;
-    const bool rep = c.posenn_se == 3;             // -se_replace: "cnv6" is the excited cnv5, 256 channels per branch
+    const bool rep = c.posenn_se == 3 || c.posenn_se == 2;   // -se_replace: "cnv6" is the excited cnv5, 256 channels per branch;
+                                                             // -se_skipadd: relu(cnv5 + se_block(cnv6)), same buffer and geometry
     rp.h = rep ? L6.Hin : L6.Hout; rp.w = rep ? L6.Win : L6.Wout; rp.hp = rep ? L6.Hin : L6.Hout_p; rp.wp = rep ? L6.Win : L6.Wout_p;
     rp.C = rep ? 256 : c.cnv6_out; rp.cstride = rep ? ctx->nbr * 256 : L6.out_stride;
     rp.unit_mul = ctx->unit_sample ? 1 : 2; rp.unit_add = ctx->unit_sample ? 0 : 1;

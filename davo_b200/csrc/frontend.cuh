@@ -876,12 +876,16 @@ struct Se5Params {
   int stack;                    // 1: -se_insert, where cnv5 is RE-ASSIGNED in the branch loop (posenn.py:227), so the
                                 //    second branch's block sees and scales the first one's output;
                                 // 0: -se_replace (posenn.py:234-236): every branch excites the original cnv5
+  int skipadd;                  // 1: -se_skipadd (posenn.py:229-233): the block sits on cnv6 (256 channels per branch,
+                                //    `cnv6` below) and the result is relu(cnv5 + cnv6 * excitation)
   const float* cnv5;            // [mb][hw][256]
+  const float* cnv6;            // skipadd: [mb][hw][nbr*256]
   const float* w;               // per branch: W1[256][32] b1[32] W2[32][256] b2[256]
-  float* part;                  // [mb][kSe5Splits][256]
+  float* part;                  // [mb][kSe5Splits][256] (skipadd: [mb][kSe5Splits][nbr][256])
   unsigned int* count;          // [mb]
   float* scale;                 // [mb][nbr][256]: exc_r, exc_r * exc_t (stack) or exc_r, exc_t
   float* out;                   // [mb][hw][nbr*256]: cnv5 * scale[0] | cnv5 * scale[1], TF32-rounded
+                                //   (skipadd: relu(cnv5 + cnv6[br] * scale[br]))
 };
 constexpr int kSe5BranchFloats = 256 * 32 + 32 + 32 * 256 + 256;
 
@@ -892,10 +896,14 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
   const int pl = blockIdx.y, c = threadIdx.x;
   const int per = (p.hw + kSe5Splits - 1) / kSe5Splits;
   const int beg = blockIdx.x * per, end = min(beg + per, p.hw);
-  const float* src = p.cnv5 + (size_t)pl * p.hw * 256 + c;
-  float a = 0.f;
-  for (int i = beg; i < end; ++i) a += src[(size_t)i * 256];
-  p.part[((size_t)pl * kSe5Splits + blockIdx.x) * 256 + c] = a;
+  const int npool = p.skipadd ? p.nbr : 1;                   // pooled maps: cnv5, or every branch's cnv6
+  for (int q = 0; q < npool; ++q) {
+    const float* src = p.skipadd ? p.cnv6 + (size_t)pl * p.hw * (p.nbr * 256) + q * 256 + c : p.cnv5 + (size_t)pl * p.hw * 256 + c;
+    const size_t stride = p.skipadd ? (size_t)p.nbr * 256 : 256;
+    float a = 0.f;
+    for (int i = beg; i < end; ++i) a += src[(size_t)i * stride];
+    p.part[(((size_t)pl * kSe5Splits + blockIdx.x) * npool + q) * 256 + c] = a;
+  }
   __shared__ int s_last;
   __shared__ float s_mean[256], s_hid[32];
   __syncthreads();
@@ -908,16 +916,18 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  float m = 0.f;
-  for (int sp = 0; sp < kSe5Splits; ++sp) m += __ldcg(p.part + ((size_t)pl * kSe5Splits + sp) * 256 + c);
-  m *= 1.0f / (float)p.hw;
+  float m[2] = {0.f, 0.f};
+  for (int q = 0; q < npool; ++q) {
+    for (int sp = 0; sp < kSe5Splits; ++sp) m[q] += __ldcg(p.part + (((size_t)pl * kSe5Splits + sp) * npool + q) * 256 + c);
+    m[q] *= 1.0f / (float)p.hw;
+  }
   float scale = 1.0f;
   for (int br = 0; br < p.nbr; ++br) {
     const float* W1 = p.w + br * kSe5BranchFloats;       // [256][32]
     const float* b1 = W1 + 256 * 32;
     const float* W2 = b1 + 32;                           // [32][256]
     const float* b2 = W2 + 32 * 256;
-    s_mean[c] = m * (p.stack ? scale : 1.0f);            // mean of what this branch's block sees
+    s_mean[c] = p.skipadd ? m[br] : m[0] * (p.stack ? scale : 1.0f);     // mean of what this branch's block sees
     __syncthreads();
     if (c < 32) {
       float h = b1[c];
@@ -934,7 +944,8 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
   }
 }
 
-// one thread per (pixel, 4 channels): out[pixel][br*256 + c] = tf32(cnv5[pixel][c] * scale[br][c])
+// one thread per (pixel, 4 channels): out[pixel][br*256 + c] = tf32(cnv5[pixel][c] * scale[br][c]);
+// skipadd: tf32(relu(cnv5[pixel][c] + cnv6[pixel][br*256 + c] * scale[br][c]))
 __global__ void __launch_bounds__(256) se5_scale_kernel(const Se5Params p) {
   pdl_launch_dependents();
   pdl_wait();                     // workspace buffers are shared with the kernels before this one
@@ -948,8 +959,14 @@ __global__ void __launch_bounds__(256) se5_scale_kernel(const Se5Params p) {
   float4* o = reinterpret_cast<float4*>(p.out) + pix * 64 * p.nbr + c4;
   for (int br = 0; br < p.nbr; ++br) {
     const float4 sc = *reinterpret_cast<const float4*>(p.scale + ((size_t)pl * p.nbr + br) * 256 + c4 * 4);
-    o[br * 64] = make_float4(round_tf32(v.x * sc.x), round_tf32(v.y * sc.y), round_tf32(v.z * sc.z),
-                             round_tf32(v.w * sc.w));
+    if (p.skipadd) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(p.cnv6) + pix * 64 * p.nbr + br * 64 + c4);
+      o[br * 64] = make_float4(round_tf32(fmaxf(v.x + u.x * sc.x, 0.f)), round_tf32(fmaxf(v.y + u.y * sc.y, 0.f)),
+                               round_tf32(fmaxf(v.z + u.z * sc.z, 0.f)), round_tf32(fmaxf(v.w + u.w * sc.w, 0.f)));
+    } else {
+      o[br * 64] = make_float4(round_tf32(v.x * sc.x), round_tf32(v.y * sc.y), round_tf32(v.z * sc.z),
+                               round_tf32(v.w * sc.w));
+    }
   }
 }
 

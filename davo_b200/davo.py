@@ -79,7 +79,7 @@ class DAVO(object):
             flow_abs=self.config.flow_abs, flow_norm=self.config.flow_norm,
             posenn_se=self.config.posenn_se, micro_batch=micro_batch, depth_norm=self.config.depth_norm,
             se_pool=self.config.se_pool, se_hidden=self.config.se_hidden, pixel_map=self.config.pixel_map,
-            depth_split=self.config.depth_split,
+            depth_split=self.config.depth_split, batch_norm=self.config.batch_norm,
             flow_f16=int(os.environ.get("DAVO_B200_FLOW16", "0") == "1") if flow_f16 is None else int(bool(flow_f16)))
         self.flow_f16 = bool(cfg.flow_f16)
         h = C.c_void_p()
@@ -168,6 +168,13 @@ class DAVO(object):
             return self._run_features(B, img, flow, seg, depth, as_torch)
         if _is_torch(img):
             return self._run_device(B, img, flow, seg, as_torch, sel, depth)
+        if self.config.batch_norm:
+            # batch statistics need the whole batch in one pass: no chunked streaming; upload and take the device path
+            import torch
+            dev = "cuda:%d" % self.device
+            up = lambda t, dt: None if t is None else torch.as_tensor(np.ascontiguousarray(t)).to(device=dev, dtype=dt)
+            return self._run_device(B, up(img, torch.uint8), up(flow, torch.float32), up(seg, torch.float32), as_torch, sel,
+                                    up(depth, torch.float32))
         return self._run_host(B, img, flow, seg, sel, depth)
 
     def _run_device(self, B, img, flow, seg, as_torch, sel=0, depth=None):

@@ -124,7 +124,12 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
 
     for scope, shape in conv_specs(cfg):
         w["pose_exp_net/%s/weights" % scope] = _xavier_uniform(rng, shape)
-        w["pose_exp_net/%s/biases" % scope] = bias(shape[3])
+        if cfg.batch_norm and not scope.endswith("pred"):
+            # normalizer_fn=slim.batch_norm (posenn.py:206): no biases; BatchNorm/beta is the only other trainable
+            # variable (scale=False), zeros at initialisation
+            w["pose_exp_net/%s/BatchNorm/beta" % scope] = bias(shape[3])
+        else:
+            w["pose_exp_net/%s/biases" % scope] = bias(shape[3])
     se_scopes = {V.ATT_SE_FLOW: ("se_flow", 2, 8), V.ATT_SE_SEG: ("se_seg", 19, 19),
                  V.ATT_SE_RGB_SEG: ("se_rgb", 3, 8), V.ATT_SE_DEPTH_SEG: ("se_depth", 1, 8),
                  V.ATT_SE_SEGFLOW_SEG: ("se_segflow", 21, 19)}
@@ -166,7 +171,7 @@ def init_weights(version: str, seed: int = 8964, random_bias: bool = False
         # double scope is the reference's: prefix "pose_exp_net/" inside scope pose_exp_net
         w["pose_exp_net/pose_exp_net/seg_channel_weight/weight"] = \
             rng.normal(0.0, 0.05, size=(19,)).astype(np.float32)
-    if cfg.posenn_se in (V.PSE_INSERT, V.PSE_REPLACE):
+    if cfg.posenn_se in (V.PSE_INSERT, V.PSE_SKIPADD, V.PSE_REPLACE):
         for br in (("rotation/", "translation/") if cfg.posenn in (V.POSENN_DECOUPLE_SHARED_DIL, V.POSENN_DECOUPLE_DIL,
                                                                V.POSENN_DECOUPLE)
                    else ("",)):

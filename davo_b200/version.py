@@ -102,6 +102,7 @@ class DavoConfig:
     pixel_map: int = 0          # 1: map = reduce_sum(SE input * excitation) per pixel (-se_rgb, -se_depth, -se_disp, -se_mixSegFlow)
     se_hidden: int = 0          # SE bottleneck width, 0 = default (8; se_seg 19); gp2x2_flow_nobottle: 19
     needs_depth: int = 0        # "depth"/"disp" in the version: the graph reads input_depth (davo.py:960)
+    batch_norm: int = 0         # "-batch_norm": slim.batch_norm on every conv but pred, BATCH statistics at test time
     version_tag: str = "v0"
 
     def as_dict(self):
@@ -118,9 +119,7 @@ def parse_version(version: str) -> DavoConfig:
     if "-se_insert" in version:
         cfg.posenn_se = PSE_INSERT
     elif "-se_skipadd" in version:
-        # cnv6 = relu(cnv5 + se_block(cnv6)) (posenn.py:229-233) only type-checks with -cnv6_256, a width the conv
-        # kernels are not instantiated for
-        raise NotImplementedError("davo_b200: -se_skipadd is not built")
+        cfg.posenn_se = PSE_SKIPADD                                 # checked against the cnv6 width below (G3)
     elif "-se_replace" in version:
         cfg.posenn_se = PSE_REPLACE
     # G2 PoseNN type (davo.py:1027-1049)
@@ -144,6 +143,14 @@ def parse_version(version: str) -> DavoConfig:
     # G3 cnv6 width (davo.py:1052-1053)
     m = re.search("-cnv6_([0-9]+)", version)
     cfg.cnv6_out = 128 if m is None else int(m.group(1))
+    if cfg.posenn_se == PSE_SKIPADD:
+        if cfg.posenn in (POSENN_COUPLE, POSENN_DECOUPLE):
+            raise NotImplementedError("davo_b200: -se_skipadd is built for the dilated nets only (the original nets run "
+                                      "their cnv6 at stride 1 in this mode, reference posenn.py:292, 355)")
+        if cfg.cnv6_out != 256:
+            # cnv6 = relu(cnv5 + se_block(cnv6)) (posenn.py:229-233): TensorFlow refuses to add 256 and cnv6_out channels
+            raise ValueError("Dimensions must be equal, but are 256 and %d (reference posenn.py:233: cnv5 + se_cnv6 "
+                             "needs -cnv6_256)" % cfg.cnv6_out)
     # G4 input version (davo.py:1057-1065)
     m = re.search("^(v[0-9.]+)", version)
     tag = "v0" if m is None else m.group(1)
@@ -269,5 +276,9 @@ def parse_version(version: str) -> DavoConfig:
         raise NotImplementedError(
             "davo_b200: depth/disp attention inputs are not built (version %r)" % version)
     if "-batch_norm" in version:                                # davo.py:1453
-        raise NotImplementedError("davo_b200: -batch_norm is not built")
+        # slim.batch_norm with its default is_training=True (no normalizer_params, posenn.py:206): batch statistics
+        # at test time, so the poses depend on which samples share a call
+        if cfg.posenn_se != PSE_NONE:
+            raise NotImplementedError("davo_b200: -batch_norm together with a PoseNN-internal SE block is not built")
+        cfg.batch_norm = 1
     return cfg

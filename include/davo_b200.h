@@ -55,7 +55,7 @@ typedef struct davo_config {
   int32_t se_act;        /* 0 relu, 1 tanh, 2 leaky_relu(0.2), davo.py:1077-1085       */
   int32_t flow_abs;      /* 0 none, 1 both, 2 h, 3 v, davo.py:1094-1102                */
   int32_t flow_norm;     /* "-norm_flow", davo.py:1088-1091                            */
-  int32_t posenn_se;     /* 0 none, 1 insert, 3 replace (2 skipadd: not built), davo.py:1010-1017, posenn.py:225-236 */
+  int32_t posenn_se;     /* 0 none, 1 insert, 2 skipadd (needs cnv6_out 256), 3 replace, davo.py:1010-1017, posenn.py:225-236 */
   int32_t micro_batch;   /* units (frame pairs; samples for posenn 2-5) per pass of the conv stack; 0 = 256 */
   int32_t depth_norm;    /* att_src 5: 0 depth_i + depth_tgt (davo.py:1109), 1 the same / 80 ("-norm_depth",
                             :1110-1111), 2 the se_disp sources: 1 / depth_i (:1253-1270)            */
@@ -78,6 +78,14 @@ typedef struct davo_config {
                             values: class weights move by <= 1.5e-5 relative, poses by ~2e-8), on BOTH entry points, so
                             that davo_forward_host may move the flow over PCIe as binary16 with results bit-identical
                             to davo_forward in the same mode                                         */
+  int32_t batch_norm;    /* "-batch_norm" (davo.py:1453, posenn.py:206): slim.batch_norm on every conv except pred, and --
+                            because the reference passes no normalizer_params -- with slim's default is_training=True at
+                            test time: each layer is normalised with the mean / biased variance of the batch of its
+                            PoseNN call (the shared nets make two calls: all tgt->src0 pairs, all tgt->src1 pairs);
+                            variables <conv>/BatchNorm/beta instead of <conv>/biases.  The poses therefore depend on
+                            which samples share a call: the whole batch must fit one pass (2*B, or B for posenn 2-5,
+                            <= micro_batch), every pair is computed (DAVO_PAIRS_ALL) and only the device entry points
+                            take it                                                                  */
 } davo_config;
 
 /* Stands in for DAVO.__init__ + DAVO.setup_inference (reference davo.py:31-33,

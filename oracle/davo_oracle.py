@@ -78,6 +78,26 @@ def conv2d_same(x_nhwc: torch.Tensor, w_hwio: torch.Tensor, b: Optional[torch.Te
     return y.permute(0, 2, 3, 1).contiguous()
 
 
+def conv_layer(x_nhwc: torch.Tensor, wts: Dict[str, torch.Tensor], scope: str, stride: int = 1, rate: int = 1,
+               relu: bool = True, tf32: bool = False) -> torch.Tensor:
+    """One ``slim.conv2d`` of the PoseNN arg_scope (nets/posenn.py:205-209).
+
+    With ``-batch_norm`` the arg_scope sets ``normalizer_fn=slim.batch_norm`` (:206) for every conv except ``pred``
+    (:240 passes normalizer_fn=None): slim then creates NO biases but ``<scope>/BatchNorm/beta`` and, because the
+    reference passes no normalizer_params, runs batch_norm with its default ``is_training=True`` -- at test time too:
+    y = (conv - mean_batch) / sqrt(var_batch + 0.001) + beta with the biased variance over (N, H, W) of THIS call's
+    batch, then ReLU.  Which mode a layer is in is read off the variables: beta present <=> batch norm.
+    """
+    beta = wts.get(scope + "/BatchNorm/beta")
+    if beta is None:
+        return conv2d_same(x_nhwc, wts[scope + "/weights"], wts[scope + "/biases"], stride=stride, rate=rate, relu=relu, tf32=tf32)
+    y = conv2d_same(x_nhwc, wts[scope + "/weights"], None, stride=stride, rate=rate, relu=False, tf32=tf32)
+    mean = y.mean(dim=(0, 1, 2))
+    var = ((y - mean) ** 2).mean(dim=(0, 1, 2))
+    y = (y - mean) * torch.rsqrt(var + 1e-3) + beta
+    return torch.relu(y) if relu else y
+
+
 # --------------------------------------------------------------------------- #
 # Attention module
 # --------------------------------------------------------------------------- #
@@ -180,8 +200,7 @@ def decouple_sharednet_v0_dilation(tgt: torch.Tensor, src: torch.Tensor,
     P = "pose_exp_net/"
 
     def cv(x, name, stride=1, rate=1, relu=True):
-        return conv2d_same(x, wts[P + name + "/weights"], wts[P + name + "/biases"],
-                           stride=stride, rate=rate, relu=relu, tf32=tf32)
+        return conv_layer(x, wts, P + name, stride=stride, rate=rate, relu=relu, tf32=tf32)
 
     x = torch.cat([tgt, src], dim=3)                                     # :198
     c1 = cv(x, "cnv1", stride=2)                                         # :211
@@ -231,8 +250,7 @@ def couple_sharednet_v0_dilation(tgt: torch.Tensor, src: torch.Tensor,
     P = "pose_exp_net/"
 
     def cv(x, name, stride=1, rate=1, relu=True):
-        return conv2d_same(x, wts[P + name + "/weights"], wts[P + name + "/biases"],
-                           stride=stride, rate=rate, relu=relu, tf32=tf32)
+        return conv_layer(x, wts, P + name, stride=stride, rate=rate, relu=relu, tf32=tf32)
 
     x = torch.cat([tgt, src], dim=3)                                     # :142
     c1 = cv(x, "cnv1", stride=2)                                         # :153
@@ -276,8 +294,7 @@ def net_v0_dilation(tgt: torch.Tensor, src0: torch.Tensor, src1: torch.Tensor,
     P = "pose_exp_net/"
 
     def cv(x, name, stride=1, rate=1, relu=True):
-        return conv2d_same(x, wts[P + name + "/weights"], wts[P + name + "/biases"],
-                           stride=stride, rate=rate, relu=relu, tf32=tf32)
+        return conv_layer(x, wts, P + name, stride=stride, rate=rate, relu=relu, tf32=tf32)
 
     def mid(x, name, rate):          # cnv3..cnv6: dilated, or stride 2 in the original nets
         return cv(x, name, rate=rate) if dilated else cv(x, name, stride=2)

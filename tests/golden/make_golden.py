@@ -86,6 +86,13 @@ CASES = {
     "pix_mix_depthflow_net": "v0-cnv6_128-segmask_rgb-se_mixDepthFlow-norm_depth-norm_flow-fc_lrelu",
     "pix_disp_wo_tgt_net": "v1-couplePoseNN-cnv6_64-segmask_all-se_disp_wo_tgt-fc_tanh",
     "spp21_mix_segflow_net": "v1-dilatedPoseNN-cnv6_128-segmask_all-se_spp21_mixSegFlow-norm_flow-fc_tanh",
+    # -se_skipadd: cnv6 = relu(cnv5 + se_block(cnv6)) (posenn.py:229-233); only type-checks with -cnv6_256
+    "se_skipadd": "v1-sharedNN-dilatedPoseNN-cnv6_256-segmask_all-se_flow-abs_flow-fc_tanh-se_skipadd",
+    "couple_net_se_skipadd": "v1-dilatedCouplePoseNN-cnv6_256-no_segmask-se_skipadd",
+    # -batch_norm: slim.batch_norm with batch statistics at test time (posenn.py:206), BatchNorm/beta instead of biases
+    "batch_norm": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh-batch_norm",
+    "batch_norm_couple_net": "v1-dilatedCouplePoseNN-cnv6_64-no_segmask-batch_norm",
+    "batch_norm_plain_net": "v0-cnv6_128-segmask_rgb-static-batch_norm",
 }
 # version strings the reference itself cannot build, with the exception its graph code raises (checked by the generator)
 REFERENCE_RAISES = {
@@ -96,6 +103,7 @@ REFERENCE_RAISES = {
     "v1-sharedNN-dilatedPoseNN-segmask_all-se_mixDispFlow-fc_tanh": "UnboundLocalError",
     "v1-sharedNN-dilatedPoseNN-segmask_all-se_mixDepthFlow-fc_tanh": "UnboundLocalError",
     "v1-sharedNN-dilatedPoseNN-segmask_all-se_flow-seglabelid": "IndexError",
+    "v1-sharedNN-dilatedPoseNN-cnv6_128-no_segmask-se_skipadd": "ValueError",      # cnv5 (256) + se_block(cnv6) (128)
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)
 AMAP_STRIDE, FEAT_STRIDE = 8, (16, 16, 8)

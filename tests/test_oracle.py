@@ -101,6 +101,8 @@ def test_oracle_matches_the_reference_fixture(key):
     alias = {"pose.rotation.cnv6": "cnv6_rotation", "pose.translation.cnv6": "cnv6_translation",
              "pose.rotation.cnv7": "cnv7_rotation", "pose.translation.cnv7": "cnv7_translation",
              "pose.cnv6": "cnv6_rotation", "pose.cnv7": "cnv7_rotation"}
+    if "skipadd" in key:                   # the oracle taps cnv6 AFTER relu(cnv5 + se_block(cnv6)); the fixture holds the conv's own output
+        alias = {k: v for k, v in alias.items() if "cnv6" not in k}
     checked = 0
     for n in sorted(names):
         tap = alias.get(n, n)

@@ -134,10 +134,19 @@ def test_posenn_internal_se_tokens():
     assert V.parse_version(BASE + "-se_replace").posenn_se == V.PSE_REPLACE
 
 
-@pytest.mark.parametrize("tok", ["-se_skipadd", "-batch_norm"])
-def test_unbuilt_sources_fail_loudly(tok):
+def test_skipadd_and_batch_norm_tokens():
+    """-se_skipadd (posenn.py:229-233) type-checks in the reference only with -cnv6_256 (cnv5 + se_block(cnv6)): the
+    same ValueError otherwise.  -batch_norm (posenn.py:206) is a flag of the config; not built next to an SE block."""
+    c = V.parse_version("v1-sharedNN-dilatedPoseNN-cnv6_256-segmask_all-se_flow-se_skipadd")
+    assert (c.posenn_se, c.cnv6_out) == (V.PSE_SKIPADD, 256)
+    with pytest.raises(ValueError, match="Dimensions must be equal"):
+        V.parse_version(BASE + "-segmask_all-se_skipadd-fc_tanh")               # BASE has -cnv6_128
     with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-segmask_all" + tok + "-fc_tanh")
+        V.parse_version("v1-couplePoseNN-cnv6_256-no_segmask-se_skipadd")       # the original nets: not built
+    assert V.parse_version(BASE + "-segmask_all-se_flow-batch_norm").batch_norm == 1
+    assert V.parse_version(BASE + "-segmask_all-se_flow").batch_norm == 0
+    with pytest.raises(NotImplementedError):
+        V.parse_version(BASE + "-no_segmask-se_insert-batch_norm")
 
 
 def test_depth_variants():

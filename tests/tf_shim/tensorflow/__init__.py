@@ -210,7 +210,10 @@ class Tensor:
     # ---- operators ----------------------------------------------------------------------------
     def _bin(self, other, fn, rev=False):
         a, b = _pair(self, other)
-        return Tensor(fn(b, a) if rev else fn(a, b))
+        try:
+            return Tensor(fn(b, a) if rev else fn(a, b))
+        except RuntimeError as e:            # TF's shape inference refuses the op when the graph is built
+            raise ValueError("Dimensions must be equal, but are %s and %s (%s)" % (tuple(a.shape), tuple(b.shape), e))
 
     def __add__(self, o): return self._bin(o, _torch.add)
     def __radd__(self, o): return self._bin(o, _torch.add, True)

@@ -30,14 +30,20 @@ __device__ __forceinline__ void tc_commit_2cta(uint64_t* bar, uint16_t mask) {
 
 // MODE 1: cta_group::1, M=128, N=NN per CTA.  MODE 2: cta_group::2, M=256, N=NN per CTA pair.
 template <int MODE, int NN>
-__global__ void __launch_bounds__(128, 1) k(long long* out, long long iters) {
+__global__ void __launch_bounds__(128, 1) k(long long* out, long long iters, int random_data) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bar = (uint64_t*)(smem + 160 * 1024);
   uint32_t* slot = (uint32_t*)(bar + 2);
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = MODE == 2 ? cluster_ctarank() : 0;
-  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) ((float*)smem)[i] = 1.0f + (float)(i & 7) * 0.125f;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += 128) {
+    // low-entropy operands (eight distinct values) or hashed pseudo-random ones in (-1, 1), TF32-rounded like the
+    // conv stack's activations and weights: the tensor core's switching power depends on the data
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    const float r = (float)(int)(h >> 8) * (1.0f / 8388608.0f) - 1.0f;
+    ((float*)smem)[i] = random_data ? round_tf32(r) : 1.0f + (float)(i & 7) * 0.125f;
+  }
   if (threadIdx.x == 0) { mbar_init(&bar[0], 1); fence_mbar_init(); }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 0) { if (MODE == 2) tmem_alloc2(slot, 256); else tmem_alloc(slot, 256); }
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, long long iters) {
 }
 
 template <int MODE, int NN>
-void run(long long* d, double seconds, int sms) {
+void run(long long* d, double seconds, int sms, int random_data) {
   auto* kern = k<MODE, NN>;
   const int smem = 162 * 1024 + 1024;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -85,7 +91,7 @@ void run(long long* d, double seconds, int sms) {
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int pass = 0; pass < 2; ++pass) {        // pass 0 calibrates the iteration count
     cudaEventRecord(e0);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, d, iters);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, d, iters, random_data);
     cudaEventRecord(e1);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("mode %d N=%d: %s\n", MODE, NN, cudaGetErrorString(e)); return; }
@@ -94,9 +100,10 @@ void run(long long* d, double seconds, int sms) {
     long long cyc = 0;
     cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
     if (pass == 1)
-      printf("cta_group::%d M=%d N=%d on %d SMs: %.2f s, %.1f TFLOP/s, %.1f cycles per (MMA x %d SM), mean SM clock %.0f MHz\n", MODE,
+      printf("%s data, cta_group::%d M=%d N=%d on %d SMs: %.2f s, %.1f TFLOP/s, %.1f cycles per (MMA x %d SM), mean SM clock %.0f MHz\n", random_data ? "random" : "constant", MODE,
              MODE == 2 ? 256 : 128, NN, sms & ~1, ms * 1e-3, flop_per_iter * iters * issuers / (ms * 1e-3) / 1e12,
              (double)cyc / (4.0 * iters), MODE, cyc / (ms * 1e-3) / 1e6);
+
     iters = (long long)(iters * seconds / (ms * 1e-3));
   }
   fflush(stdout);
@@ -106,11 +113,12 @@ int main(int argc, char** argv) {
   const double seconds = argc > 1 ? atof(argv[1]) : 4.0;
   long long* d; cudaMalloc(&d, 16);
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
-  for (int rep = 0; rep < 2; ++rep) {
-    run<1, 256>(d, seconds, p.multiProcessorCount);
-    run<2, 256>(d, seconds, p.multiProcessorCount);
-  }
-  run<1, 128>(d, seconds, p.multiProcessorCount);
-  run<2, 128>(d, seconds, p.multiProcessorCount);
+  for (int random_data = 0; random_data < 2; ++random_data)
+    for (int rep = 0; rep < 2; ++rep) {
+      run<1, 256>(d, seconds, p.multiProcessorCount, random_data);
+      run<2, 256>(d, seconds, p.multiProcessorCount, random_data);
+    }
+  run<1, 128>(d, seconds, p.multiProcessorCount, 1);
+  run<2, 128>(d, seconds, p.multiProcessorCount, 1);
   return 0;
 }
