@@ -387,7 +387,7 @@ def run_ours(args):
         dist.all_reduce(dtc, op=dist.ReduceOp.MAX)
     os.environ.pop("DAVO_B200_HOST_COPY_ONLY")
     copy_only_value = world * 2 * B * 5 / float(dtc.item())
-    stream = stream_4541(system, dev, rank, world, dist)
+    stream = None if os.environ.get("DAVO_BENCH_SKIP_STREAM") else stream_4541(system, dev, rank, world, dist)   # skipped under ncu
 
     if rank != 0:
         if world > 1:
@@ -476,7 +476,6 @@ def run_ours(args):
         "stream_4541": stream,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "pcie_h2d_gbs": pcie_gbs, "pcie_h2d_gbs_all_ranks": pcie_gbs_sum,
-                "pcie_bound": world * 2 * B / (h2d / (pcie_gbs * 1e9)),
                 "copy_only": copy_only_value, "frac_of_copy_only": e2e_value / copy_only_value,
                 "compact_inputs": {"value": compact_value, "unit": UNIT, "h2d_bytes_per_step": compact_h2d,
                                    "note": "NOT the reference's input contract: the caller supplies uint8 labels and "
@@ -488,8 +487,8 @@ def run_ours(args):
                         "the CPU inside the timed region, narrows the labels to bytes (lossless: the graph casts them "
                         "to int32); the flow crosses as float32 (flow_f16 off), so h2d_bytes_per_step is what crossed "
                         "PCIe.  pcie_h2d_gbs = plain pinned copies of that many bytes issued by ALL ranks at once "
-                        "(barrier-released), slowest rank; pcie_bound = frame pairs / (h2d bytes / that rate); "
-                        "copy_only = the library's own staging + copies with the kernels skipped "
+                        "(barrier-released), slowest rank (context: its value depends on which NUMA node the "
+                        "probe's buffer landed on); copy_only = the library's own staging + copies with the kernels skipped "
                         "(DAVO_B200_HOST_COPY_ONLY), same ranks, same buffers: the ceiling e2e can reach"},
         "roofline": roofline, "cpu_baseline": cpu,
         "trajectory_mode": {"samples_per_s": B / (traj_ms * 1e-3), "ms_per_step": traj_ms, "frame_pairs_computed": B + 1,

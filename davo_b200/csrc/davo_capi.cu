@@ -220,6 +220,11 @@ struct davo_ctx {
   bool compensated_rounding = true; // TF32 weight rounding directions chosen so tap sums cancel
   bool pdl = true;                  // programmatic dependent launch of every kernel of a pass
   std::vector<Layer> layers;        // cnv1..cnv7
+  // Latency plans (BASELINE configs[0], batch 1): the channels-on-M layers re-planned with 128-pixel tiles (16 x 8)
+  // instead of 256.  A 256-pixel tile costs 128 cycles per MMA, a 128-pixel one 64: when the big tiling cannot fill
+  // the SMs anyway (few units), half-size tiles halve the layer's critical path at no cost.  Same buffers, own
+  // weight pack and tensor maps.  layers_small[i].npix == 0: layer i has no such plan.
+  std::vector<Layer> layers_small;
   // device buffers
   std::vector<void*> allocs;
   unsigned int* d_poolcnt = nullptr;
@@ -1109,7 +1114,14 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
                    const float* seg, float* pose_out, cudaStream_t st, int* launches) {
   if (int rc = launch_front(ctx, pair_mode, pair0, npairs, img, flow, seg, st, launches)) return rc;
   for (size_t li = 0; li < ctx->layers.size(); ++li) {
-    Layer& L = ctx->layers[li];
+    Layer* Lp = &ctx->layers[li];
+    if (li < ctx->layers_small.size() && ctx->layers_small[li].npix != 0) {
+      // the big tiling leaves SMs idle: take the half-size tiles (twice as many, half as long)
+      const Layer& B = *Lp;
+      const long tiles_big = (long)npairs * B.groups * B.tiles_h * B.tiles_w * B.m_blocks;
+      if (tiles_big < ctx->num_sms) Lp = &ctx->layers_small[li];
+    }
+    Layer& L = *Lp;
     const int pse = ctx->cfg.posenn_se;
     auto se5 = [&](int skipadd) -> int {
       Se5Params sp;
@@ -1502,6 +1514,23 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     std::fill(out->begin(), out->end(), 0.f);
     return 0;
   };
+  // plan a layer and, for the channels-on-M layers with 256-pixel tiles, its latency twin with 128-pixel tiles
+  ctx->layers_small.assign(7, Layer());
+  for (Layer& Ls : ctx->layers_small) Ls.npix = 0;
+  const char* small_env = getenv("DAVO_B200_SMALL_TILES");          // debug: "0" never uses the latency plans
+  auto plan_both = [&](int idx, auto getw, const std::vector<float>& bias) -> int {
+    Layer& L = ctx->layers[idx];
+    if (int rc = L.wide_G ? plan_layer_wide(ctx, L, getw, bias) : plan_layer(ctx, L, getw, bias)) return rc;
+    if (L.orient == 1 && L.npix == 256 && L.epi == EPI_STORE_RELU && !(small_env && !strcmp(small_env, "0"))) {
+      Layer Ls = L;
+      Ls.npix = 128;
+      Ls.tiles_h = (Ls.Hout + Ls.npix / kTileW - 1) / (Ls.npix / kTileW);
+      Ls.d_wpack = nullptr; Ls.d_bias = nullptr; Ls.d_whwio[0] = Ls.d_whwio[1] = nullptr;
+      if (int rc = plan_layer(ctx, Ls, getw, bias)) return rc;
+      ctx->layers_small[idx] = Ls;
+    }
+    return 0;
+  };
   for (int i = 0; i < 5; ++i) {
     Layer& L = ctx->layers[i];
     const HostTensor *w, *b;
@@ -1510,7 +1539,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     auto getw = [&](int, int ty, int tx, int ci, int n) { return w->data[(((size_t)ty * K + tx) * Ci + ci) * Co + n]; };
     std::vector<float> bias;
     if (int rc = bias_or_beta(L, b->data, &bias)) return rc;
-    if (int rc = L.wide_G ? plan_layer_wide(ctx, L, getw, bias) : plan_layer(ctx, L, getw, bias)) return rc;
+    if (int rc = plan_both(i, getw, bias)) return rc;
   }
   const char* brs[2] = {"rotation", "translation"};
   // variable scope of branch g under pose_exp_net/: pose/rotation/, pose/translation/ (decouple) or pose/ (couple)
@@ -1527,13 +1556,13 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
       auto getw = [&](int g, int ty, int tx, int ci, int n) {
         return w[g]->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + n];
       };
-      if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
+      if (int rc = plan_both(5, getw, bias)) return rc;
     } else {        // one N = 2*c6 GEMM: rotation | translation
       auto getw = [&](int, int ty, int tx, int ci, int n) {
         const HostTensor* t = w[n / c6];
         return t->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + (n % c6)];
       };
-      if (int rc = plan_layer(ctx, L, getw, bias)) return rc;
+      if (int rc = plan_both(5, getw, bias)) return rc;
     }
   }
   if (se5 || rep || skip) {
