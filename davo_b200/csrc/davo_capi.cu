@@ -193,6 +193,9 @@ struct Layer {
   bool cm_staged = false;      // cm: store epilogue through shared memory + TMA tile stores
   bool cm_cluster = false;     // cm: 2-CTA clusters, each weight slab fetched once and multicast
   bool b_resident = false;     // pm: all weight slabs stay in shared memory
+  int strips = -1;             // halo patches cut into one vertical strip per filter column: -1 = decided by plan_layer
+                               // (and recorded here); a latency twin takes its big plan's choice so that both accumulate
+                               // every output element in the same tap order (bit-identical results at any batch size)
   int wide_G = 0;              // pm, column-widened: output pixels per M row (0 = off)
   int wide_tw = 0;             //   runs per tile row (tile = 128/wide_tw rows x wide_tw runs)
   int pc2w[16];                // input tensor channel -> HWIO input channel of the weights, -1: none (cnv1: packed input)
@@ -508,7 +511,8 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
   // vertical strip per filter column (cnv5: dilation 8).
   const int TR = L.npix / kTileW;                 // tile rows
   const int full_hp = TR + (L.k - 1) * L.dil, full_wp = kTileW + (L.k - 1) * L.dil;
-  const bool strips = !strided && (size_t)full_hp * full_wp * kSlabBytes > 64 * 1024;
+  const bool strips = L.strips >= 0 ? L.strips != 0 : (!strided && (size_t)full_hp * full_wp * kSlabBytes > 64 * 1024);
+  L.strips = strips ? 1 : 0;
   for (int ty = 0; ty < L.k; ++ty) {
     const int dy = ty * L.dil - L.pad_t;
     const int dh = strided ? floordiv(dy, 2) : dy;

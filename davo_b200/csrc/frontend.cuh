@@ -659,7 +659,7 @@ __device__ __forceinline__ void unpack_rgb4(uint32_t t0, uint32_t t1, uint32_t t
   r[3] = img_norm((t2 >> 8) & 255u); g[3] = img_norm((t2 >> 16) & 255u); b[3] = img_norm(t2 >> 24);
 }
 
-__global__ void __launch_bounds__(256) pack8_kernel(const FrontParams p) {
+__global__ void __launch_bounds__(256, 4) pack8_kernel(const FrontParams p) {
   pdl_launch_dependents();
   pdl_wait();                     // workspace buffers are shared with the kernels before this one
   __shared__ float s_w[kNumClasses], s_wt[kNumClasses];    // class weights: source frame, target frame

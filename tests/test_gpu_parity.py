@@ -182,6 +182,24 @@ def test_ragged_micro_batches_and_batch_invariance():
     assert np.array_equal(sub, outs[0][:2])
 
 
+def test_latency_plans_give_the_bits_of_the_throughput_plans(monkeypatch):
+    """Small batches run the channels-on-M layers with 128-pixel tiles (davo_capi.cu: layers_small) so that one sample
+    fills more SMs; every output element still accumulates its taps in the same order, so a sample computed alone,
+    inside a 100-sample batch, or with the latency plans switched off carries the same bits."""
+    _need_gpu()
+    w = S.init_weights(HEADLINE, random_bias=True)
+    inputs = S.make_inputs(100, H, W, seed=61)
+    big, _ = _system(HEADLINE, 100, w, inputs)
+    ref = big.inference(None, "pose")["pose"]
+    for n in (1, 2, 5):
+        sysm, _ = _system(HEADLINE, n, w, tuple(a[:n] for a in inputs))
+        assert np.array_equal(sysm.inference(None, "pose")["pose"], ref[:n]), n
+        assert np.array_equal(sysm.inference(None, "pose", pairs="trajectory")["pose"][:, 1], ref[:n, 1]), n
+    monkeypatch.setenv("DAVO_B200_SMALL_TILES", "0")
+    off, _ = _system(HEADLINE, 1, w, tuple(a[:1] for a in inputs))
+    assert np.array_equal(off.inference(None, "pose")["pose"], ref[:1])
+
+
 def test_host_buffer_entry_point_matches_device_entry_point():
     _need_gpu()
     w = S.init_weights(HEADLINE)
@@ -512,6 +530,30 @@ def test_cli_writes_reference_format_trajectory(tmp_path):
     inputs = tuple(np.stack([stream.sample(i)[k] for i in range(6)]) for k in range(3))
     ref = O.davo_forward(HEADLINE, *inputs, S.init_weights(HEADLINE), torch.float32)
     _assert_pose(poses[:6], ref)
+
+
+def test_cli_reference_batch_semantics_and_depth_variants(tmp_path):
+    """--reference_batch_semantics at --batch_size 4 writes the file the reference's loop writes (every sample of the
+    first batch contributes tgt->src0, padding duplicates composed: reference test_kitti_pose.py:96-101, 133-145), the
+    default writes the intended N+2 lines; a depth variant runs through the CLI (synthetic depth)."""
+    _need_gpu()
+    from davo_b200 import test_kitti_pose as cli
+    args = ["--synthetic", "12", "--batch_size", "4", "--version", HEADLINE, "--output_dir", str(tmp_path), "--test_seq", "9", "--seed", "5"]
+    poses = cli.main(args + ["--all_pairs"])
+    assert poses.shape == (10, 2, 6)
+    assert len((tmp_path / "09-pred_kitti_pose.txt").read_text().strip().split("\n")) == 12
+    ref_poses = cli.main(args + ["--reference_batch_semantics"])
+    assert ref_poses.shape == (12, 2, 6)                                      # 10 samples padded to 12 (:96-101)
+    assert np.array_equal(ref_poses[:10, 1], poses[:, 1]) and np.array_equal(ref_poses[:4, 0], poses[:4, 0])
+    assert np.array_equal(ref_poses[10:, 1], np.stack([poses[9, 1]] * 2))     # the duplicates of the last sample
+    lines = (tmp_path / "09-pred_kitti_pose.txt").read_text().strip().split("\n")
+    assert len(lines) == 1 + 4 + 12
+    assert lines == O.kitti_lines(O.compose_trajectory(ref_poses, 4, True))
+    ver = G.CASES["se_depth"]
+    dposes = cli.main(["--synthetic", "8", "--batch_size", "3", "--version", ver, "--all_pairs", "--output_dir", str(tmp_path), "--seed", "9"])
+    stream = cli.SyntheticStream(8, H, W, 9, "depth")
+    inputs = tuple(np.stack([stream.sample(i)[k] for i in range(6)]) for k in range(4))
+    _assert_pose(dposes, O.davo_forward(ver, *inputs[:3], S.init_weights(ver), torch.float64, depth=inputs[3]))
 
 
 def test_cli_on_a_reference_layout_dump(tmp_path):

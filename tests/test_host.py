@@ -236,6 +236,7 @@ def _write_dump(root, seq, n_frames, h, w, seed=3):
         seg = rng.integers(0, 19, size=(3, h, w, 1)).astype(np.uint8)
         np.save(os.path.join(d, fid + "-flownet2.npy"), flow)
         np.save(os.path.join(d, fid + "-seglabel.npy"), seg)
+        np.save(os.path.join(d, fid + "-monodepth2_depth.npy"), rng.uniform(1.0, 80.0, size=(3, h, w, 1)).astype(np.float32))
         out.append((flow, seg))
     return out
 
@@ -439,3 +440,25 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
                     str(src), lib, "-Wl,-rpath," + os.path.dirname(lib), "-o", str(exe)], check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == int(out[1]) == C.sizeof(_capi.DavoConfigC)
+
+
+def test_cli_depth_source_mirrors_the_reference_cli(tmp_path):
+    """Which file feeds input_depth: reference test_kitti_pose.py:91 reads the depth file only when "depth" is in the
+    version, while the graph reads input_depth for "depth" OR "disp" (davo.py:960): a disp-only version gets the
+    SEGLABEL file as its depth (:59-62).  DumpStream / SyntheticStream return the 4-tuple DAVO.inference needs."""
+    from davo_b200 import test_kitti_pose as cli
+    assert cli.depth_source("v1-sharedNN-dilatedPoseNN-segmask_all-se_depth_wo_tgt_to_seg") == "depth"
+    assert cli.depth_source("v1-sharedNN-dilatedPoseNN-segmask_all-se_disp_to_seg-norm_depth") == "depth"
+    assert cli.depth_source("v1-sharedNN-dilatedPoseNN-segmask_all-se_disp_to_seg") == "seglabel"
+    assert cli.depth_source("v1-sharedNN-dilatedPoseNN-segmask_all-se_flow") == "none"
+    _write_dump(str(tmp_path / "dump"), 9, 5, 16, 24)
+    d = os.path.join(str(tmp_path / "dump"), "09")
+    s3 = cli.DumpStream(str(tmp_path / "dump"), 9, 16, 24, 3).sample(0)
+    s4 = cli.DumpStream(str(tmp_path / "dump"), 9, 16, 24, 3, "depth").sample(1)
+    sl = cli.DumpStream(str(tmp_path / "dump"), 9, 16, 24, 3, "seglabel").sample(1)
+    assert len(s3) == 3 and len(s4) == 4 and s4[3].shape == (3, 16, 24, 1) and s4[3].dtype == np.float32
+    assert np.array_equal(s4[3], np.load(os.path.join(d, "000002-monodepth2_depth.npy")))
+    assert np.array_equal(sl[3], sl[2])
+    syn = cli.SyntheticStream(10, 16, 24, 5, "depth").sample(3)
+    assert len(syn) == 4 and syn[3].shape == (3, 16, 24, 1) and syn[3].min() >= 1.0
+    assert len(cli.SyntheticStream(10, 16, 24, 5).sample(3)) == 3
