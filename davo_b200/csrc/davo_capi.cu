@@ -1114,18 +1114,22 @@ int launch_head(davo_ctx* ctx, int pair_mode, int pair0, int npairs, float* pose
   return 0;
 }
 
+// The plan of layer `li` for a pass of `npairs` units: the latency twin (128-pixel tiles: twice as many, half as long)
+// when the 256-pixel tiling would leave SMs idle.
+Layer& pick_layer(davo_ctx* ctx, size_t li, int npairs) {
+  Layer& B = ctx->layers[li];
+  if (li < ctx->layers_small.size() && ctx->layers_small[li].npix != 0) {
+    const long tiles_big = (long)npairs * B.groups * B.tiles_h * B.tiles_w * B.m_blocks;
+    if (tiles_big < ctx->num_sms) return ctx->layers_small[li];
+  }
+  return B;
+}
+
 int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint8_t* img, const float* flow,
                    const float* seg, float* pose_out, cudaStream_t st, int* launches) {
   if (int rc = launch_front(ctx, pair_mode, pair0, npairs, img, flow, seg, st, launches)) return rc;
   for (size_t li = 0; li < ctx->layers.size(); ++li) {
-    Layer* Lp = &ctx->layers[li];
-    if (li < ctx->layers_small.size() && ctx->layers_small[li].npix != 0) {
-      // the big tiling leaves SMs idle: take the half-size tiles (twice as many, half as long)
-      const Layer& B = *Lp;
-      const long tiles_big = (long)npairs * B.groups * B.tiles_h * B.tiles_w * B.m_blocks;
-      if (tiles_big < ctx->num_sms) Lp = &ctx->layers_small[li];
-    }
-    Layer& L = *Lp;
+    Layer& L = pick_layer(ctx, li, npairs);
     const int pse = ctx->cfg.posenn_se;
     auto se5 = [&](int skipadd) -> int {
       Se5Params sp;
@@ -2059,7 +2063,7 @@ extern "C" int davo_profile_layers(davo_ctx* ctx, int iters, float* ms_out, int*
   };
   if (int rc = timed([&] { return launch_front(ctx, ctx->unit_sample ? kUnitsAreSamples : 0, 0, npairs, ctx->last_img, ctx->last_flow, ctx->last_seg, st, &dummy); }, &ms_out[0])) return rc;
   for (int i = 0; i < 7; ++i) {
-    const Layer& L = ctx->layers[i];
+    const Layer& L = pick_layer(ctx, i, npairs);
     if (i == 5 && ctx->cfg.posenn_se == 3) { ms_out[1 + i] = 0.f; continue; }      // -se_replace has no cnv6 convolution
     if (int rc = timed([&] { return launch_conv(ctx, L, npairs, st); }, &ms_out[1 + i])) return rc;
   }

@@ -32,6 +32,10 @@ for small in ("1", "0"):
             torch.cuda.synchronize()
             out["device small_tiles=%s graph=%s pairs=%s ms" % (small, graph, pairs)] = round(e0.elapsed_time(e1) / 500, 5)
         if graph == "1":
+            sysm.inference(None, "pose", as_torch=True)
+            torch.cuda.synchronize()
+            lm, npairs = sysm.profile_layers(iters=50)
+            out["layers small_tiles=%s (each kernel alone, %d pairs) us" % (small, npairs)] = {k: round(1e3 * v, 2) for k, v in lm.items()}
             for _ in range(5):
                 sysm.inference(None, "pose", inputs=tuple(pinned))
             t0 = time.perf_counter()
