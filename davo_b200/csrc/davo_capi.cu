@@ -34,6 +34,7 @@
 #include "comm.cuh"
 #include "trajectory.cuh"
 #include "bn.cuh"
+#include "jpeg.cuh"
 #include "host_convert.h"
 
 using namespace davo;
@@ -253,6 +254,8 @@ struct davo_ctx {
   uint16_t *h_flow16[kStage] = {}, *s_flow16[kStage] = {};
   bool host_flow16 = true;
   int numa_node = -1, numa_cpus = 0;      // davo_bind_host_numa
+  nvjpegHandle_t jpeg_handle = nullptr;   // davo_decode_jpeg_batch (jpeg.cuh)
+  nvjpegJpegState_t jpeg_state = nullptr;
   double* d_bn_part = nullptr;            // -batch_norm scratch: partial sums, means, reciprocal deviations (bn.cuh)
   float *d_bn_mean = nullptr, *d_bn_rstd = nullptr;
   void* d_traj_scratch = nullptr;         // davo_compose_trajectory / davo_kitti_errors: relative motions, distances, segments
@@ -1150,8 +1153,6 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
     int rc = ctx->conv_impl == 0 ? launch_conv(ctx, L, npairs, st) : launch_conv_direct(ctx, L, npairs, st);
     if (rc) return rc;
     *launches += (ctx->conv_impl == 0) ? 1 : L.groups;
-    if (li == 5 && pse == 2)                       // -se_skipadd: cnv6 := relu(cnv5 + se_block(cnv6)) (posenn.py:229-233)
-      if (int rc2 = se5(1)) return rc2;
     if (ctx->cfg.batch_norm) {                     // the conv wrote plain sums: normalise with this call's batch statistics
       BnParams bp;
       memset(&bp, 0, sizeof bp);
@@ -1170,6 +1171,8 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
       }
       *launches += 3;
     }
+    if (li == 5 && pse == 2)                       // -se_skipadd: cnv6 := relu(cnv5 + se_block(cnv6)) (posenn.py:229-233);
+      if (int rc2 = se5(1)) return rc2;            // under -batch_norm the block sees the normalised, activated cnv6
   }
   const Layer& L7 = ctx->layers.back();
   if (ctx->conv_impl != 0) {
@@ -1242,8 +1245,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN kind %d unknown (0..5, posenn.py:12-378)", cfg->posenn);
   if (cfg->posenn_se < 0 || cfg->posenn_se > 3)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: PoseNN-internal SE mode %d unknown (1 insert, 2 skipadd, 3 replace)", cfg->posenn_se);
-  if (cfg->batch_norm != 0 && (cfg->batch_norm != 1 || cfg->posenn_se != 0))
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: batch_norm is 0 or 1 and is not built together with a PoseNN-internal SE block");
+  if (cfg->batch_norm != 0 && cfg->batch_norm != 1)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: batch_norm is 0 or 1");
   if (cfg->posenn_se == 2 && cfg->cnv6_out != 256)
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: -se_skipadd adds cnv5 (256 channels) to se_block(cnv6): cnv6 width must be 256, got %d", cfg->cnv6_out);
   if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
@@ -1303,6 +1306,8 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->d_traj_scratch) cudaFree(ctx->d_traj_scratch);
+  if (ctx->jpeg_state) davo_jpeg::api().StateDestroy(ctx->jpeg_state);
+  if (ctx->jpeg_handle) davo_jpeg::api().Destroy(ctx->jpeg_handle);
   for (int i = 0; i < davo_ctx::kStage; ++i) {
     if (ctx->s_img[i]) cudaFree(ctx->s_img[i]);
     if (ctx->s_flow[i]) cudaFree(ctx->s_flow[i]);
@@ -2281,6 +2286,38 @@ extern "C" int davo_kitti_errors(davo_ctx* ctx, const double* gt, const double* 
   kitti_stats_kernel<<<1, 32, 0, st>>>(segs, count, stats);
   CU_OK(cudaGetLastError());
   CU_OK(cudaMemcpyAsync(stats_host, stats, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- nvJPEG decode into the frame tensor (include/davo_b200.h; csrc/jpeg.cuh) ----
+extern "C" int davo_decode_jpeg_batch(davo_ctx* ctx, const uint8_t* const* jpeg, const int64_t* nbytes, int n, uint8_t* img_dev,
+                                      void* stream) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!jpeg || !nbytes || !img_dev || n < 1) return fail(ctx, DAVO_ERR_ARG, "davo_decode_jpeg_batch: null buffer or no images");
+  const davo_jpeg::Api& j = davo_jpeg::api();
+  if (!j.why.empty()) return fail(ctx, DAVO_ERR_STATE, "davo_decode_jpeg_batch: %s", j.why.c_str());
+  CU_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!ctx->jpeg_handle) {
+    if (j.CreateSimple(&ctx->jpeg_handle) != NVJPEG_STATUS_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "nvjpegCreateSimple failed");
+    if (j.StateCreate(ctx->jpeg_handle, &ctx->jpeg_state) != NVJPEG_STATUS_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "nvjpegJpegStateCreate failed");
+  }
+  const int H = ctx->cfg.H, W3 = 3 * ctx->cfg.W;
+  for (int i = 0; i < n; ++i) {
+    int comps = 0, ws[NVJPEG_MAX_COMPONENT], hs[NVJPEG_MAX_COMPONENT];
+    nvjpegChromaSubsampling_t sub;
+    if (j.GetImageInfo(ctx->jpeg_handle, jpeg[i], (size_t)nbytes[i], &comps, &sub, ws, hs) != NVJPEG_STATUS_SUCCESS)
+      return fail(ctx, DAVO_ERR_ARG, "davo_decode_jpeg_batch: image %d is not a JPEG nvJPEG can parse", i);
+    if (ws[0] != W3 || hs[0] != H)
+      return fail(ctx, DAVO_ERR_ARG, "davo_decode_jpeg_batch: image %d is %dx%d, the frame triple must be %dx%d", i, hs[0], ws[0], H, W3);
+    nvjpegImage_t out;
+    memset(&out, 0, sizeof out);
+    out.channel[0] = img_dev + (size_t)i * H * W3 * 3;
+    out.pitch[0] = (size_t)W3 * 3;
+    const nvjpegStatus_t rc = j.Decode(ctx->jpeg_handle, ctx->jpeg_state, jpeg[i], (size_t)nbytes[i], NVJPEG_OUTPUT_RGBI, &out, st);
+    if (rc != NVJPEG_STATUS_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "nvjpegDecode(image %d) -> %d", i, (int)rc);
+  }
   CU_OK(cudaStreamSynchronize(st));
   return 0;
 }

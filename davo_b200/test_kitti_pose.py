@@ -47,6 +47,11 @@ def build_parser():
                     help="compute both poses of every sample as the reference graph does; by default only "
                          "the poses the trajectory is composed from are computed (reference :143-145), "
                          "which writes the same file with half the work")
+    ap.add_argument("--jpeg_decode", choices=["host", "nvjpeg"], default="host",
+                    help="where the <id>.jpg frame triples of a dump are decoded: 'host' = PIL / libjpeg in the loader's "
+                         "worker threads (TensorFlow's decoder family: the default), 'nvjpeg' = on the GPU, straight into "
+                         "the frame tensor (pixels within a few levels of libjpeg's)")
+    ap.add_argument("--loader_workers", type=int, default=4, help="reader / decoder threads (reference: num_parallel_calls=4)")
     ap.add_argument("--reference_batch_semantics", action="store_true",
                     help="at --batch_size > 1 write exactly the file the reference's loop writes: its `if i == 0` "
                          "(reference :143) tests the batch index, so EVERY sample of the first batch contributes its "
@@ -100,6 +105,14 @@ class DumpStream:
         self.ids = [frames[i].split(' ')[1] for i in range(n_frames)
                     if parallel.is_valid_sample(frames, i, seq_length)]
         self.dir, self.n, self.h, self.w, self.depth_from = d, len(self.ids), h, w, depth_from
+
+    def file_lists(self, depth_from="none"):
+        """(names, poses, flows, depths, seglabels) as reference test_kitti_pose.py:32-72 builds them; the depth list is
+        the seglabel list unless the version says "depth" (:59-62)."""
+        b = [os.path.join(self.dir, fid) for fid in self.ids]
+        segs = [x + '-seglabel.npy' for x in b]
+        depths = [x + '-monodepth2_depth.npy' for x in b] if depth_from == "depth" else segs
+        return [x + '.jpg' for x in b], [x + '_cam.txt' for x in b], [x + '-flownet2.npy' for x in b], depths, segs
 
     def sample(self, i):
         from PIL import Image
@@ -161,9 +174,24 @@ def main(argv=None):
     if world > 1:
         system.init_comm(rank, world)                                  # the library's own NCCL communicator
     poses = torch.empty((len(idx), 2, 6), dtype=torch.float32, device="cuda:%d" % local)
+    batches = None
+    if not FLAGS.synthetic:
+        # the reference's input pipeline (test_kitti_pose.py:90-114): file lists -> DataLoader.load_test_batch_flow;
+        # worker threads read, decode and fill pinned batches ahead of the loop below
+        from .data_loader import DataLoader
+        dsrc = depth_source(FLAGS.version)
+        lists = stream.file_lists(dsrc)
+        loader = DataLoader(FLAGS.concat_img_dir, B, H, W, FLAGS.seq_length - 1, read_flow=True, read_depth=dsrc != "none",
+                            read_seglabel=True)
+        batches = loader.load_test_batch_flow(*[[l[j] for j in idx] for l in lists], system=system,
+                                              decode=FLAGS.jpeg_decode, workers=FLAGS.loader_workers)
     for i in range(len(idx) // B):                                     # reference :133
-        batch = [stream.sample(j) for j in idx[i * B:(i + 1) * B]]
-        inputs = tuple(np.stack([s[k] for s in batch]) for k in range(len(batch[0])))   # (img, flow, seg[, depth])
+        if batches is not None:
+            img, _, flow, depth, seg = batches.get_next()              # reference :104-114: inputs_batch[0..4]
+            inputs = (img, flow, seg) if depth is None else (img, flow, seg, depth)
+        else:
+            batch = [stream.sample(j) for j in idx[i * B:(i + 1) * B]]
+            inputs = tuple(np.stack([s[k] for s in batch]) for k in range(len(batch[0])))   # (img, flow, seg[, depth])
         # reference :143-145 reads pose[s,1] of every sample and pose[0,0] of the sequence's first
         if FLAGS.all_pairs or (FLAGS.reference_batch_semantics and B > 1 and first + i * B < B):
             sel = 'all'                       # reference semantics: batch 0 contributes tgt->src0 of every sample

@@ -278,7 +278,5 @@ def parse_version(version: str) -> DavoConfig:
     if "-batch_norm" in version:                                # davo.py:1453
         # slim.batch_norm with its default is_training=True (no normalizer_params, posenn.py:206): batch statistics
         # at test time, so the poses depend on which samples share a call
-        if cfg.posenn_se != PSE_NONE:
-            raise NotImplementedError("davo_b200: -batch_norm together with a PoseNN-internal SE block is not built")
         cfg.batch_norm = 1
     return cfg

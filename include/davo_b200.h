@@ -262,6 +262,17 @@ int davo_compose_trajectory(davo_ctx*, const float* poses_dev, int n_samples, do
 int davo_kitti_errors(davo_ctx*, const double* gt_dev, const double* res_dev, int n_frames,
                       davo_kitti_segment* seg_dev, float* stats_host, void* cuda_stream);
 
+/* --- real-data input path ---
+ * The reference decodes its `<seq>/<id>.jpg` frame triples on the CPU inside tf.data (data_loader.py:241-249,
+ * tf.image.decode_jpeg) and feeds uint8 [B,H,3W,3].  davo_decode_jpeg_batch decodes n JPEG byte strings (host memory)
+ * with nvJPEG straight into the device tensor davo_forward reads, on `cuda_stream`: image i lands at
+ * img_dev + i*H*3W*3, interleaved RGB.  Every image must be H x 3W.  nvJPEG is bound at run time (libnvjpeg.so.12;
+ * DAVO_B200_NVJPEG_LIB overrides).  Its pixels are within a few levels of libjpeg's, not identical: the host decode of
+ * davo_b200/data_loader.py (PIL) stays the default; this is the throughput option.  Synchronises the stream (nvJPEG's
+ * hybrid decoder does its Huffman stage on the host). */
+int davo_decode_jpeg_batch(davo_ctx*, const uint8_t* const* jpeg, const int64_t* nbytes, int n, uint8_t* img_dev,
+                           void* cuda_stream);
+
 const char* davo_last_error(const davo_ctx*);   /* NULL handle -> last create error */
 void davo_destroy(davo_ctx*);
 const char* davo_build_info(void);              /* arch / compiler string */

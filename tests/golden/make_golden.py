@@ -93,6 +93,9 @@ CASES = {
     "batch_norm": "v1-sharedNN-dilatedPoseNN-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh-batch_norm",
     "batch_norm_couple_net": "v1-dilatedCouplePoseNN-cnv6_64-no_segmask-batch_norm",
     "batch_norm_plain_net": "v0-cnv6_128-segmask_rgb-static-batch_norm",
+    "batch_norm_se_insert": "v1-sharedNN-dilatedPoseNN-cnv6_128-no_segmask-se_insert-batch_norm",
+    "batch_norm_se_skipadd": "v1-dilatedPoseNN-cnv6_256-segmask_all-se_flow-abs_flow-fc_tanh-se_skipadd-batch_norm",
+    "batch_norm_se_replace": "v1-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_seg-fc_tanh-se_replace-batch_norm",
 }
 # version strings the reference itself cannot build, with the exception its graph code raises (checked by the generator)
 REFERENCE_RAISES = {
@@ -106,6 +109,10 @@ REFERENCE_RAISES = {
     "v1-sharedNN-dilatedPoseNN-cnv6_128-no_segmask-se_skipadd": "ValueError",      # cnv5 (256) + se_block(cnv6) (128)
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)
+# other frame sizes of the headline variant (BASELINE configs[4]: 256x832; a partial widened run; a width that is not
+# a multiple of 16; a small map): (H, W, batch), inputs make_inputs(batch, H, W, seed=11, bad_label_frac=0.01),
+# weights init_weights(headline, random_bias=True) -> "size/<H>x<W>/pose"
+SIZE_CASES = [(256, 832, 2), (64, 208, 3), (128, 400, 2), (136, 424, 1)]
 AMAP_STRIDE, FEAT_STRIDE = 8, (16, 16, 8)
 
 
@@ -308,6 +315,15 @@ def cli_loop_inputs(n=10):
     return p
 
 
+def reference_size_case(h, w_, b):
+    from davo_b200 import synthetic as S
+    ver = CASES["headline"]
+    w = S.init_weights(ver, random_bias=True)
+    img, flow, seg = S.make_inputs(b, h, w_, seed=11, bad_label_frac=0.01)
+    out, _ = run_reference(ver, img, flow, seg, S.make_depth(b, h, w_), w, "float64", "pose")
+    return np.asarray(out["pose"], np.float64)
+
+
 def main(keys=None):
     out = {}
     with reference_on_path():
@@ -331,6 +347,9 @@ def main(keys=None):
                 print("reference raises %-18s for %s" % (exc, ver))
             else:
                 raise AssertionError("the reference built %r, expected %s" % (ver, exc))
+        for (h, w_, b) in SIZE_CASES:
+            out["size/%dx%d/pose" % (h, w_)] = reference_size_case(h, w_, b)
+            print("headline at %dx%d, batch %d: from the reference's code" % (h, w_, b), flush=True)
         for B in (1, 4, 5):                                            # 10 samples: 4 pads to 12, 5 divides
             out["cli_loop/B%d" % B] = reference_cli_loop(cli_loop_inputs(), B)
             print("reference CLI loop, batch %d: %d poses for 10 samples" % (B, len(out["cli_loop/B%d" % B])))

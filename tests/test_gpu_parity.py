@@ -143,7 +143,9 @@ def test_other_input_sizes(size):
     d = [torch.as_tensor(x).cuda() for x in inputs]
     sysm.setup_inference(h, w_, "davo", 3, b, d[0], input_flow=d[1], input_seglabel=d[2], device=0)
     sysm.load_weights(w)
-    _assert_pose(sysm.inference(None, "pose")["pose"], O.davo_forward(HEADLINE, *inputs, w, torch.float64))
+    out = sysm.inference(None, "pose")["pose"]
+    _assert_pose(out, O.davo_forward(HEADLINE, *inputs, w, torch.float64))
+    _assert_pose(out, GOLD["size/%dx%d/pose" % (h, w_)])                 # the reference's own graph code at this size
 
 
 def test_tensor_core_path_agrees_with_direct_fp32_conv_on_gpu():
@@ -779,3 +781,56 @@ def test_on_device_trajectory_composition_and_kitti_errors():
     dev_res = evaluation.compose_trajectory_gpu(sysm, torch.as_tensor(noisy).cuda())
     chained = evaluation.kitti_errors_gpu(sysm, torch.as_tensor(gt).cuda(), dev_res)
     assert chained["num"] == len(want) and abs(chained["t_err"] - t_mean) <= 1e-3 * t_mean
+
+
+def test_nvjpeg_decode_and_loader_feed_the_forward(tmp_path):
+    """the dump goes through davo_b200/data_loader.py (reference DataLoader.load_test_batch_flow) with
+    the host decoder (PIL / libjpeg: the default) and with nvJPEG on the GPU (davo_decode_jpeg_batch).  The two decoders
+    agree to a few levels per pixel and the poses to well inside the tolerance; the CLI runs on either."""
+    _need_gpu()
+    from PIL import Image
+    from davo_b200 import test_kitti_pose as cli
+    from davo_b200.data_loader import DataLoader
+    from tests.test_host import _write_dump
+    _write_dump(str(tmp_path / "dump"), 9, 9, H, W)                       # 7 samples
+    # smooth frames compress the way photographs do (noise does not): overwrite the random jpgs
+    rng = np.random.default_rng(5)
+    d = tmp_path / "dump" / "09"
+    for f in sorted(d.glob("*.jpg")):
+        yy, xx = np.mgrid[0:H, 0:3 * W]
+        img = np.stack([127 + 100 * np.sin(xx / 37.0 + k + rng.uniform(0, 6)) * np.cos(yy / 23.0) for k in range(3)], -1)
+        Image.fromarray(np.clip(img + rng.normal(0, 4, img.shape), 0, 255).astype(np.uint8)).save(str(f), quality=92)
+    w = S.init_weights(HEADLINE, random_bias=True)
+    sysm = DAVO(version=HEADLINE)
+    sysm.setup_inference(H, W, "davo", 3, 4, device=0)
+    sysm.load_weights(w)
+    stream = cli.DumpStream(str(tmp_path / "dump"), 9, H, W, 3)
+    lists = stream.file_lists()
+    loader = DataLoader(str(tmp_path / "dump"), 4, H, W, 2, read_flow=True, read_seglabel=True)
+    host = list(loader.load_test_batch_flow(*lists, workers=3))
+    dev = list(loader.load_test_batch_flow(*lists, system=sysm, decode="nvjpeg", workers=3))
+    assert [b[0].shape[0] for b in host] == [4, 3] == [b[0].shape[0] for b in dev]
+    for hb, db in zip(host, dev):
+        assert db[0].is_cuda and db[0].dtype == torch.uint8 and tuple(db[0].shape) == hb[0].shape
+        diff = np.abs(db[0].cpu().numpy().astype(int) - hb[0].astype(int))
+        assert diff.max() <= 6 and diff.mean() < 0.6, (diff.max(), diff.mean())        # two IDCT / upsampling implementations
+        assert np.array_equal(db[2][:, :2].cpu().numpy(), hb[2][:, :2]) and np.array_equal(db[4].cpu().numpy(), hb[4])
+        ph = sysm.inference(None, "pose", inputs=(hb[0], hb[2], hb[4]))["pose"]
+        pd = sysm.inference(None, "pose", inputs=(db[0], db[2], db[4]))["pose"]
+        _assert_pose(ph, O.davo_forward(HEADLINE, hb[0], hb[2], hb[4], w, torch.float64))
+        assert np.abs(pd - ph).max() < 2e-5, np.abs(pd - ph).max()                      # the decoders' few levels, through the net
+    np.savez(str(tmp_path / "model.npz"), **w)
+    args = ["--concat_img_dir", str(tmp_path / "dump"), "--test_seq", "9", "--batch_size", "3", "--all_pairs", "--version", HEADLINE,
+            "--ckpt_file", str(tmp_path / "model.npz")]
+    p_host = cli.main(args + ["--output_dir", str(tmp_path / "o1")])
+    p_nvj = cli.main(args + ["--output_dir", str(tmp_path / "o2"), "--jpeg_decode", "nvjpeg"])
+    assert p_host.shape == p_nvj.shape == (7, 2, 6) and np.abs(p_host - p_nvj).max() < 2e-5
+    assert np.array_equal(p_host[:4], sysm.inference(None, "pose", inputs=(host[0][0], host[0][2], host[0][4]))["pose"])
+    with pytest.raises(RuntimeError, match="frame triple must be"):
+        small = tmp_path / "small.jpg"
+        Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(str(small))
+        b = small.read_bytes()
+        import ctypes as C
+        out = torch.empty((1, H, 3 * W, 3), dtype=torch.uint8, device="cuda")
+        sysm._check(sysm._lib.davo_decode_jpeg_batch(sysm._h, (C.c_void_p * 1)(C.cast(C.c_char_p(b), C.c_void_p)), (C.c_int64 * 1)(len(b)), 1,
+                                                     C.c_void_p(out.data_ptr()), None), "davo_decode_jpeg_batch")

@@ -462,3 +462,38 @@ def test_cli_depth_source_mirrors_the_reference_cli(tmp_path):
     syn = cli.SyntheticStream(10, 16, 24, 5, "depth").sample(3)
     assert len(syn) == 4 and syn[3].shape == (3, 16, 24, 1) and syn[3].min() >= 1.0
     assert len(cli.SyntheticStream(10, 16, 24, 5).sample(3)) == 3
+
+
+def test_data_loader_mirrors_load_test_batch_flow(tmp_path):
+    """davo_b200/data_loader.py: the reference's file lists (test_kitti_pose.py:32-72) and its batch iterator
+    (data_loader.py:241-325): tuple order image, pose, flow, depth, seglabel; batches in list order, the last one
+    partial; contents equal the files; worker threads and prefetch do not reorder anything."""
+    from PIL import Image
+    from davo_b200.data_loader import DataLoader, load_kitti_image_sequence_names
+    h, w = 16, 24
+    _write_dump(str(tmp_path / "dump"), 9, 9, h, w)                       # 9 frames -> 7 samples
+    frames = ["%.2d %.6d" % (9, n) for n in range(9)]
+    names, tgt, poses, flows, depths, segs = load_kitti_image_sequence_names(str(tmp_path / "dump"), frames, 3, load_pose=True,
+                                                                          load_flow=True, load_depth=False, load_seglabel=True)
+    assert tgt == list(range(1, 8)) and names[0].endswith("09/000001.jpg") and flows[6].endswith("000007-flownet2.npy")
+    assert depths == segs                                                  # load_depth False: the seglabel files (:59-62)
+    assert load_kitti_image_sequence_names(str(tmp_path / "dump"), frames, 3, load_depth=True)[4][0].endswith("-monodepth2_depth.npy")
+    loader = DataLoader(str(tmp_path / "dump"), 3, h, w, 2, read_flow=True, read_depth=True, read_seglabel=True)
+    it = loader.load_test_batch_flow(names, poses, flows, depths, segs, workers=3, prefetch=2)
+    assert len(it) == 3
+    seen = 0
+    for img, pose, flow, depth, seg in it:
+        n = img.shape[0]
+        assert pose is None and img.dtype == np.uint8 and flow.shape == (n, 4, h, w, 2) and seg.shape == (n, 3, h, w, 1)
+        for k in range(n):
+            assert np.array_equal(img[k], np.asarray(Image.open(names[seen + k]).convert("RGB")))
+            assert np.array_equal(flow[k], np.load(flows[seen + k]))
+            assert np.array_equal(seg[k][..., 0], np.load(segs[seen + k])[..., 0].astype(np.float32))
+            assert np.array_equal(depth[k], seg[k])                        # the depth list IS the seglabel list here
+        seen += n
+    assert seen == 7
+    bad = loader.load_test_batch_flow(names[:2] + [str(tmp_path / "missing.jpg")], poses[:3], flows[:3], depths[:3], segs[:3])
+    with pytest.raises(FileNotFoundError):
+        list(bad)
+    with pytest.raises(ValueError):
+        loader.load_test_batch_flow(names, poses, flows, depths, segs, decode="nvjpeg")      # needs a DAVO handle

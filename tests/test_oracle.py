@@ -363,3 +363,13 @@ def test_kitti_eval_restatement_matches_the_reference_devkit(tmp_path):
             want = [float(v) for v in (tmp_path / "results" / "x" / ("%02d-stats.txt" % seq)).read_text().split()]
             assert abs(want[0] - t_mean) <= 1.5e-6 and abs(want[1] - r_mean) <= 1.5e-6
     assert len(kitti_eval.sequence_errors(*trajs[0])) > 200 and len(kitti_eval.sequence_errors(*trajs[5])) > 0
+
+
+@pytest.mark.parametrize("size", G.SIZE_CASES[1:])
+def test_oracle_matches_the_reference_at_other_frame_sizes(size):
+    """The headline variant at other frame sizes (partial widened runs, widths that are not multiples of 16): the oracle
+    against the poses the reference's own code computed there (tests/golden/make_golden.reference_size_case)."""
+    h, w_, b = size
+    w = S.init_weights(HEADLINE, random_bias=True)
+    inputs = S.make_inputs(b, h, w_, seed=11, bad_label_frac=0.01)
+    np.testing.assert_allclose(O.davo_forward(HEADLINE, *inputs, w, torch.float64), GOLD["size/%dx%d/pose" % (h, w_)], rtol=1e-9, atol=1e-13)

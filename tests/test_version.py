@@ -145,8 +145,8 @@ def test_skipadd_and_batch_norm_tokens():
         V.parse_version("v1-couplePoseNN-cnv6_256-no_segmask-se_skipadd")       # the original nets: not built
     assert V.parse_version(BASE + "-segmask_all-se_flow-batch_norm").batch_norm == 1
     assert V.parse_version(BASE + "-segmask_all-se_flow").batch_norm == 0
-    with pytest.raises(NotImplementedError):
-        V.parse_version(BASE + "-no_segmask-se_insert-batch_norm")
+    c = V.parse_version(BASE + "-no_segmask-se_insert-batch_norm")
+    assert (c.batch_norm, c.posenn_se) == (1, V.PSE_INSERT)
 
 
 def test_depth_variants():
