@@ -1091,7 +1091,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
         return rc;
     } else if (c.att_src == 1 && c.se_pool >= 2) {
       if (int rc = launch_k(ctx, se_spp_kernel, dim3(npairs, src_frames), dim3(256), 0, st, false, fp)) return rc;
-    } else if (int rc = launch_k(ctx, se_pool_kernel, dim3(kPoolSplits, npairs, c.depth_split ? 2 : src_frames + (c.att_tgt_ones ? 0 : 1)),
+    } else if (int rc = launch_k(ctx, se_pool_kernel, dim3(kPoolSplits, npairs, c.depth_split ? 2 * src_frames : src_frames + (c.att_tgt_ones ? 0 : 1)),
                                  dim3(256), 0, st, false, fp)) {
       return rc;
     }
@@ -1137,7 +1137,9 @@ int run_microbatch(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const ui
     auto se5 = [&](int skipadd) -> int {
       Se5Params sp;
       memset(&sp, 0, sizeof sp);
-      sp.npairs = npairs; sp.hw = ctx->layers[5].Hin * ctx->layers[5].Win; sp.nbr = ctx->nbr; sp.stack = pse == 1; sp.skipadd = skipadd;
+      // the cnv5 map with its pitch (the stride-2 nets store 4x13 as 4x14: the extra column is zeros and stays zeros)
+      sp.npairs = npairs; sp.hw = ctx->layers[5].Hin_p * ctx->layers[5].Win_p; sp.nbr = ctx->nbr; sp.stack = pse == 1; sp.skipadd = skipadd;
+      sp.inv_n = 1.0f / (float)(ctx->layers[5].Hin * ctx->layers[5].Win);
       sp.cnv5 = ctx->layers[4].d_out; sp.cnv6 = ctx->layers[5].d_out; sp.w = ctx->d_se5w; sp.part = ctx->d_se5part; sp.count = ctx->d_se5cnt;
       sp.scale = ctx->d_se5scale; sp.out = ctx->d_se5out;
       if (int rc = launch_k(ctx, se5_excite_kernel, dim3(kSe5Splits, npairs), dim3(256), 0, st, false, sp)) return rc;
@@ -1261,8 +1263,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad se_pool / se_hidden");
   if (cfg->se_pool >= 2 && (cfg->H > cfg->W || (cfg->att_src == 1 && !cfg->att_tgt_ones)))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: the pyramid pooling is built for H <= W (and, on the flow, a target map of ones)");
-  if (cfg->depth_split != 0 && (cfg->depth_split != 1 || cfg->att_src != 1 || cfg->se_pool != 0 || cfg->posenn > 1 || !cfg->att_tgt_ones))
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: depth_split needs att_src 1 with global pooling, a target map of ones and a shared net");
+  if (cfg->depth_split != 0 && (cfg->depth_split != 1 || cfg->att_src != 1 || cfg->se_pool != 0 || !cfg->att_tgt_ones))
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: depth_split needs att_src 1 with global pooling and a target map of ones");
   if (cfg->pixel_map != 0 && (cfg->pixel_map < 1 || cfg->pixel_map > 2 || (cfg->pixel_map == 2 && cfg->att_src != 5) ||
                               cfg->att_src < 4 || cfg->att_src > 6 || (cfg->se_pool != 0 && cfg->att_src != 6)))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: per-pixel maps are built for att_src 4..6 and global pooling");
@@ -1362,8 +1364,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   const Geo geo_dil[7] = {{7, 2, 1}, {5, 2, 1}, {3, 1, 2}, {3, 1, 4}, {3, 1, 8}, {3, 1, 2}, {3, 2, 1}};
   const Geo geo_v0[7] = {{7, 2, 1}, {5, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}};
   const Geo* geo = dilated ? geo_dil : geo_v0;
-  if (!dilated && c.posenn_se != 0)
-    return fail(ctx, DAVO_ERR_ARG, "PoseNN-internal SE is built for the dilated nets only");
+  if (!dilated && c.posenn_se == 2)       // there cnv6 runs at stride 1 in this mode only (posenn.py:292, 355): not built
+    return fail(ctx, DAVO_ERR_ARG, "-se_skipadd is built for the dilated nets only");
   // couple nets (posenn.py:133-187): one branch, pred 256 -> 6; decouple nets: rotation | translation
   const int nbr = (c.posenn == 1 || c.posenn == 3 || c.posenn == 4) ? 1 : 2;
   const int nsrc = ctx->unit_sample ? 2 : 1;      // poses per evaluation (num_source, posenn.py:19, 76, 140, 196)
@@ -1432,7 +1434,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
       L.tiles_w = (runs + L.wide_tw - 1) / L.wide_tw;
     }
     for (int j = 0; j < 16; ++j) { L.cmap[j] = j; L.pc2w[j] = j < L.Cin_w ? j : -1; }
-    H = L.Hout; W = L.Wout; Hq = L.Hout_p; Wq = L.Wout_p;
+    if (!(i == 5 && c.posenn_se == 3)) {             // -se_replace: there is no cnv6 (cnv6 := se_block(cnv5)): cnv7 reads cnv5's map
+      H = L.Hout; W = L.Wout; Hq = L.Hout_p; Wq = L.Wout_p;
+    }
   }
   {
     // cnv1 reads the packed input.  The reference's cnv1 sees [tgt rgb, tgt flow (zeros), src rgb,
@@ -1480,7 +1484,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   for (int i = 0; i < 7; ++i) {
     Layer& L = ctx->layers[i];
     if (i == 5 && (se5 || rep || skip)) {
-      const size_t hw5 = (size_t)L.Hin * L.Win;
+      const size_t hw5 = (size_t)L.Hin_p * L.Win_p;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5part, (size_t)mb * kSe5Splits * 256 * (skip ? nbr : 1) * 4)) return rc;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5cnt, (size_t)mb * 4)) return rc;
       if (int rc = dev_alloc(ctx, (void**)&ctx->d_se5scale, (size_t)mb * 2 * 256 * 4)) return rc;
@@ -2220,7 +2224,7 @@ extern "C" int davo_forward_features(davo_ctx* ctx, int B, const uint8_t* img, c
     rp.B = B; rp.H = c.H; rp.W = c.W;
     const bool rep = c.posenn_se == 3 || c.posenn_se == 2;   // -se_replace: "cnv6" is the excited cnv5, 256 channels per branch;
                                                              // -se_skipadd: relu(cnv5 + se_block(cnv6)), same buffer and geometry
-    rp.h = rep ? L6.Hin : L6.Hout; rp.w = rep ? L6.Win : L6.Wout; rp.hp = rep ? L6.Hin : L6.Hout_p; rp.wp = rep ? L6.Win : L6.Wout_p;
+    rp.h = rep ? L6.Hin : L6.Hout; rp.w = rep ? L6.Win : L6.Wout; rp.hp = rep ? L6.Hin_p : L6.Hout_p; rp.wp = rep ? L6.Win_p : L6.Wout_p;
     rp.C = rep ? 256 : c.cnv6_out; rp.cstride = rep ? ctx->nbr * 256 : L6.out_stride;
     rp.unit_mul = ctx->unit_sample ? 1 : 2; rp.unit_add = ctx->unit_sample ? 0 : 1;
     rp.src = rep ? ctx->d_se5out : L6.d_out;

@@ -51,6 +51,7 @@ __device__ __forceinline__ const float* frame_weights(const FeatureParams& p, in
   if (f == 0 && p.att_tgt_ones) return nullptr;
   if (p.att_src == 2) return p.static_w;
   // slots of a unit: frontend.cuh unit_frame
+  if (p.unit_sample && p.fp.depth_split) return p.att_w + ((size_t)b * kAttFrames + 2 * (f - 1)) * kAttStride;   // (near, far) of src f-1
   if (p.unit_sample) return p.att_w + ((size_t)b * kAttFrames + (f == 0 ? 2 : f - 1)) * kAttStride;
   if (f == 0) return p.att_w + ((size_t)(2 * b) * kAttFrames + 1) * kAttStride;
   return p.att_w + ((size_t)(2 * b + (f - 1)) * kAttFrames + 0) * kAttStride;

@@ -17,7 +17,7 @@ namespace davo {
 
 constexpr int kPoolSplits = 16;
 constexpr int kPoolDim = 24;     // >= the widest pooled vector (19 class frequencies + 2 flow means)
-constexpr int kAttFrames = 3;    // attention-weight slots per unit (see unit_frame)
+constexpr int kAttFrames = 4;    // attention-weight slots per unit (see unit_frame; 4: the depth-split source in a sample unit)
 constexpr int kAttStride = 24;   // floats per slot of att_w: 19 class weights, or the excitation of a per-pixel source (<= 21)
 constexpr int kPackedC = 16;     // widest packed PoseNN input (see pack_kernel; FrontParams::packed_c = 8 or 16)
 constexpr int kNumClasses = 19;
@@ -168,7 +168,8 @@ __device__ __forceinline__ void se_dense_layers(const FrontParams& p, const floa
                                                 int pl, int fr) {
   const int Hd = p.se_hid;
   // depth_split: slot fr uses its own weight set (near, far), stored one after the other
-  const float* W1 = p.se_w + (p.depth_split ? fr * (D * Hd + Hd + Hd * p.se_out + p.se_out) : 0);
+  const int wset = p.unit_sample ? (fr & 1) : fr;           // sample units: slots (0,1) / (2,3) = (near, far) of src0 / src1
+  const float* W1 = p.se_w + (p.depth_split ? wset * (D * Hd + Hd + Hd * p.se_out + p.se_out) : 0);
   const float* b1 = W1 + D * Hd;
   const float* W2 = b1 + Hd;
   const int out = p.se_out;
@@ -212,7 +213,9 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
   const int D = p.se_in;
-  const int f = unit_frame(p.unit_sample, k, p.depth_split ? 0 : fr);     // depth_split: both slots pool the source flow
+  // depth_split: a source frame has two slots (near, far), both pooling that frame's flow: slots (0, 1) of a frame pair;
+  // (0, 1) = src0 and (2, 3) = src1 of a sample unit
+  const int f = unit_frame(p.unit_sample, k, p.depth_split ? (p.unit_sample ? (fr >> 1) : 0) : fr);
   __shared__ float red[8][4];
   __shared__ int s_hist[kNumClasses];
   __shared__ float s_pool[kPoolDim];
@@ -744,22 +747,24 @@ __global__ void __launch_bounds__(256, 4) pack8_kernel(const FrontParams p) {
 __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
   pdl_launch_dependents();
   pdl_wait();                     // workspace buffers are shared with the kernels before this one
-  __shared__ float s_w[3][kAttStride];                      // class weights (or excitation) of slots src0, src1, tgt
+  // class weights (or excitation) of slots src0, src1, tgt; with the depth-split source (target map = ones) the four
+  // slots are src0 near, src0 far, src1 near, src1 far
+  __shared__ float s_w[kAttFrames][kAttStride];
   const int pl = blockIdx.y;
   int b, k;
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
-  if (threadIdx.x < 3 * kAttStride) {
-    const int fr = threadIdx.x / kAttStride, c = threadIdx.x % kAttStride;
+  for (int t = threadIdx.x; t < kAttFrames * kAttStride; t += blockDim.x) {
+    const int fr = t / kAttStride, c = t % kAttStride;
     const bool se = p.att_src == 1 || p.att_src >= 3;
     float v = 1.0f;
     if (p.att_src == 2) v = c < kNumClasses ? p.static_w[c] : 0.0f;
-    else if (se && !(fr == 2 && p.att_tgt_ones)) v = p.att_w[((size_t)pl * kAttFrames + fr) * kAttStride + c];
+    else if (se && (p.depth_split || (fr < 3 && !(fr == 2 && p.att_tgt_ones)))) v = p.att_w[((size_t)pl * kAttFrames + fr) * kAttStride + c];
     s_w[fr][c] = v;
   }
   __syncthreads();
   const bool need_lab = !p.pixel_map || p.att_src == 6;
-  const bool need_depth = p.pixel_map && p.att_src == 5;
+  const bool need_depth = p.depth_split || (p.pixel_map && p.att_src == 5);
   const bool need_seflow = (p.pixel_map && p.att_src == 6) || p.pixel_map == 2;
   const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
   const size_t seg_b = (size_t)b * 3 * hw;
@@ -785,7 +790,9 @@ __global__ void __launch_bounds__(256) pack_sample_kernel(const FrontParams p) {
           const float2 f = flow1_at(p, b, fr, pix, hw);      // slot 0 = src0 -> flow[:, 0], slot 1 = src1 -> flow[:, 1]
           sfx = se_in_x(f.x, p); sfy = se_in_y(f.y, p);
         }
-        a[fr] = frame_attention(p, s_w[fr], s_w[fr], lab, r, g, bl, ds, dt, sfx, sfy);   // one_hot: out of range -> 0
+        const float* wn = p.depth_split ? s_w[2 * fr] : s_w[fr];                       // depth_split: fr is 0 or 1 (target map = ones)
+        const float* wf = p.depth_split ? s_w[2 * fr + 1] : s_w[fr];
+        a[fr] = frame_attention(p, wn, wf, lab, r, g, bl, ds, dt, sfx, sfy);             // one_hot: out of range -> 0
       }
     }
     float v[16];
@@ -871,7 +878,8 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
 // The excitation is per channel, so the second block needs no second pass over the map.
 constexpr int kSe5Splits = 32;
 struct Se5Params {
-  int npairs, hw;               // pixels of the cnv5 map
+  int npairs, hw;               // pixels of the cnv5 map as stored (with its pitch; pad pixels are zeros)
+  float inv_n;                  // 1 / (pixels of the map proper): the divisor of the global average pool
   int nbr;                      // branches (2: rotation then translation; 1: couple nets)
   int stack;                    // 1: -se_insert, where cnv5 is RE-ASSIGNED in the branch loop (posenn.py:227), so the
                                 //    second branch's block sees and scales the first one's output;
@@ -919,7 +927,7 @@ __global__ void __launch_bounds__(256) se5_excite_kernel(const Se5Params p) {
   float m[2] = {0.f, 0.f};
   for (int q = 0; q < npool; ++q) {
     for (int sp = 0; sp < kSe5Splits; ++sp) m[q] += __ldcg(p.part + (((size_t)pl * kSe5Splits + sp) * npool + q) * 256 + c);
-    m[q] *= 1.0f / (float)p.hw;
+    m[q] *= p.inv_n;
   }
   float scale = 1.0f;
   for (int br = 0; br < p.nbr; ++br) {

@@ -195,8 +195,6 @@ def parse_version(version: str) -> DavoConfig:
     if "-se_flow_on_depthseg_seplayers" in version:                             # davo.py:1136-1154
         # se(flow, "se_flow_near" | "se_flow_far", [8,19]) applied to the labels of the pixels nearer / farther than
         # the variable se_flow/depth_threshold; everything lives under pose_exp_net/se_flow*, so the target map is ones
-        if cfg.posenn >= POSENN_DECOUPLE_DIL:
-            raise NotImplementedError("davo_b200: -se_flow_on_depthseg_seplayers is built for the -sharedNN nets only")
         cfg.att_src, cfg.att_tgt_ones, cfg.depth_split = ATT_SE_FLOW, 1, 1
     elif "-se_mixDepthFlow" in version or "-se_mixDispFlow" in version:         # davo.py:1157-1174
         # se_block(concat(depth term, SE flow), "se_depthflow" | "se_dispflow", ratio=1): a per-pixel map of 3 channels

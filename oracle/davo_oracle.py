@@ -299,8 +299,6 @@ def net_v0_dilation(tgt: torch.Tensor, src0: torch.Tensor, src1: torch.Tensor,
     def mid(x, name, rate):          # cnv3..cnv6: dilated, or stride 2 in the original nets
         return cv(x, name, rate=rate) if dilated else cv(x, name, stride=2)
 
-    if not dilated and se_attention is not False:
-        _unsupported("PoseNN-internal SE in the non-dilated nets")
     x = torch.cat([tgt, src0, src1], dim=3)
     c1 = cv(x, "cnv1", stride=2)
     c2 = cv(c1, "cnv2", stride=2)
@@ -313,9 +311,9 @@ def net_v0_dilation(tgt: torch.Tensor, src0: torch.Tensor, src1: torch.Tensor,
     for br in (("pose/rotation/", "pose/translation/") if decouple else ("pose/",)):
         if se_attention is True:             # cnv5 is re-assigned: the second branch sees the first's output
             c5 = se_block(c5, wts, P + br + "cnv5_se_attention", "relu")
-            c6 = cv(c5, br + "cnv6", rate=2)
+            c6 = mid(c5, br + "cnv6", 2)     # posenn.py:44, 103 (rate 2) / :289, 351 (stride 2)
         elif se_attention == "se_skipadd":
-            c6 = cv(c5, br + "cnv6", rate=2)
+            c6 = cv(c5, br + "cnv6", rate=2) if dilated else cv(c5, br + "cnv6", stride=1)   # posenn.py:292, 355: stride 1 there
             c6 = torch.relu(c5 + se_block(c6, wts, P + br + "cnv6_se_attention", "relu"))
         elif se_attention == "se_replace":
             c6 = se_block(c5, wts, P + br + "cnv6_se_attention", "relu")

@@ -96,6 +96,11 @@ CASES = {
     "batch_norm_se_insert": "v1-sharedNN-dilatedPoseNN-cnv6_128-no_segmask-se_insert-batch_norm",
     "batch_norm_se_skipadd": "v1-dilatedPoseNN-cnv6_256-segmask_all-se_flow-abs_flow-fc_tanh-se_skipadd-batch_norm",
     "batch_norm_se_replace": "v1-sharedNN-dilatedCouplePoseNN-cnv6_128-segmask_rgb-se_seg-fc_tanh-se_replace-batch_norm",
+    # the depth-split source in a non-shared net; PoseNN-internal SE in the two original stride-2 nets (4x13 / 2x7 maps)
+    "depthseg_seplayers_net": "v1-dilatedPoseNN-cnv6_128-segmask_all-se_flow_on_depthseg_seplayers_40-abs_flow-fc_tanh",
+    "plain_couple_se_insert": "v1-couplePoseNN-cnv6_64-no_segmask-se_insert",
+    "plain_decouple_se_replace": "v0-cnv6_128-segmask_rgb-static-se_replace",
+    "plain_decouple_se_insert": "v1-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh-se_insert",
 }
 # version strings the reference itself cannot build, with the exception its graph code raises (checked by the generator)
 REFERENCE_RAISES = {

@@ -83,8 +83,8 @@ def test_per_pixel_sources():
     assert (c.posenn, c.att_src, c.pixel_map) == (V.POSENN_DECOUPLE_DIL, V.ATT_SE_RGB_SEG, 1)
     with pytest.raises(UnboundLocalError):                                           # capital "Disp": input_depth is never read (davo.py:960, 1167)
         V.parse_version(BASE + "-segmask_all-se_mixDispFlow")
-    with pytest.raises(NotImplementedError, match="sharedNN"):                       # the depth split stays shared-net only
-        V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_flow_on_depthseg_seplayers")
+    c = V.parse_version("v1-dilatedPoseNN-cnv6_128-segmask_all-se_flow_on_depthseg_seplayers")   # the depth split in a non-shared net
+    assert (c.posenn, c.depth_split, c.att_tgt_ones) == (V.POSENN_DECOUPLE_DIL, 1, 1)
 
 
 def test_order_sensitive_tokens():
