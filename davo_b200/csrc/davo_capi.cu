@@ -717,7 +717,7 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     if (r != CUDA_SUCCESS) return fail(ctx, DAVO_ERR_CUDA, "%s: cuTensorMapEncodeTiled(weights) -> %d", L.name, (int)r);
     L.tmB64 = L.tmB;
     const char* cl_env = getenv("DAVO_B200_CLUSTER");            // debug: "0" switches the clusters off
-    L.cm_cluster = L.orient == 1 && L.epi == EPI_STORE_RELU && !(cl_env && !strcmp(cl_env, "0"));
+    L.cm_cluster = L.orient == 1 && (L.epi == EPI_STORE_RELU || getenv("DAVO_B200_CNV7_CM")) && !(cl_env && !strcmp(cl_env, "0"));
     if (L.cm_cluster) {
       const cuuint32_t box64[2] = {32, (cuuint32_t)(rows_per_slab / 2)};
       r = enc(&L.tmB64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, L.d_wpack, dims, strides, box64, es,
@@ -946,9 +946,9 @@ int launch_cm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
 }
 
 // 2-CTA clusters, weights multicast (conv_cm.cuh: CLUSTER).
-template <int NPIX, bool STAGED>
+template <int NPIX, bool STAGED, int EPI = EPI_STORE_RELU>
 int launch_cm_cluster(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
-  auto* kern = cm::conv_tc_kernel<NPIX, EPI_STORE_RELU, STAGED, true>;
+  auto* kern = cm::conv_tc_kernel<NPIX, EPI, STAGED, true>;
   if (int rc = ensure_smem(ctx, kern, L.smem_bytes)) return rc;
   int& max_clusters = ctx->max_clusters[std::make_pair(reinterpret_cast<const void*>(kern), L.smem_bytes)];
   cudaLaunchConfig_t cfg;
@@ -976,6 +976,9 @@ int launch_cm_cluster(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st
 
 int launch_conv(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
   if (L.orient == 1 && L.cm_cluster) {
+    if (L.epi == EPI_SUM_RELU)
+      return L.npix == 256 ? launch_cm_cluster<256, false, EPI_SUM_RELU>(ctx, L, npairs, st)
+                           : launch_cm_cluster<128, false, EPI_SUM_RELU>(ctx, L, npairs, st);
     if (L.cm_staged)
       return L.npix == 256 ? launch_cm_cluster<256, true>(ctx, L, npairs, st) : launch_cm_cluster<128, true>(ctx, L, npairs, st);
     return L.npix == 256 ? launch_cm_cluster<256, false>(ctx, L, npairs, st) : launch_cm_cluster<128, false>(ctx, L, npairs, st);
@@ -1413,6 +1416,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     if (force && !strcmp(force, "pm")) L.orient = 0;
     if (force && !strcmp(force, "cm")) L.orient = 1;
     if (L.orient == 0 && L.epi == EPI_SUM_RELU && L.BN != 256) L.orient = 1;
+    // cnv7 channels-on-M (experiment knob): 128-pixel tiles, 2-CTA clusters sharing the weight slabs
+    if (const char* e7 = getenv("DAVO_B200_CNV7_CM")) if (i == 6 && !strcmp(e7, "1") && L.epi == EPI_SUM_RELU) L.orient = 1;
     L.npix = (L.orient == 1 && L.Hout > 16) ? 256 : 128;
     L.m_blocks = L.orient == 1 ? (L.BN + cm::kBlockM - 1) / cm::kBlockM : 1;
     L.tiles_h = (L.Hout + L.npix / kTileW - 1) / (L.npix / kTileW);

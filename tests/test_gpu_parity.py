@@ -668,7 +668,8 @@ def test_allgather_without_communicator_is_a_copy():
 
 @pytest.mark.parametrize("key", ["headline", "se_seg", "static", "couple_shared", "se_insert", "decouple_net",
                                  "plain_couple_net", "couple_net_v0", "se_depth_norm_tgt", "segflow_to_seg", "se_replace", "spp21_seg_couple",
-                                 "pix_rgb", "pix_depth_wo_tgt", "pix_mix_segflow", "pix_mix_dispflow", "depthseg_seplayers"])
+                                 "pix_rgb", "pix_depth_wo_tgt", "pix_mix_segflow", "pix_mix_dispflow", "depthseg_seplayers",
+                                 "se_skipadd", "batch_norm", "depthseg_seplayers_net", "pix_mix_depthflow_net", "plain_decouple_se_replace"])
 def test_feature_mode_matches_oracle(key):
     """DAVO.inference(mode='feature') (davo.py:1553-1564) through davo_forward_features: every fetched tensor
     against the oracle.  Labels and colourings are byte-exact (flow colours: the atan2 of the two
@@ -697,7 +698,7 @@ def test_feature_mode_matches_oracle(key):
     for k in range(2):
         d = np.abs(got["flows"][k].astype(int) - want["flows"][k].astype(int))
         assert got["flows"][k].dtype == np.uint8 and (d != 0).mean() < 1e-3 and np.percentile(d, 99.99) <= 1, (d != 0).mean()
-    c6 = 256 if key == "se_replace" else sysm.config.cnv6_out     # -se_replace: cnv6 is the excited cnv5
+    c6 = 256 if "se_replace" in key else sysm.config.cnv6_out     # -se_replace: cnv6 is the excited cnv5
     for name in ("rot", "trans"):
         assert got["features"][name].shape == (g["batch"], H, W, c6)
         assert _rel(got["features"][name], want["features"][name]) < 1.5e-3, name
