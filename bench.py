@@ -335,7 +335,24 @@ def run_ours(args):
     for _ in range(e2e_steps):
         pose_host = system.inference(None, "pose", inputs=(h_img, h_flow, h_seg))["pose"]
     torch.cuda.synchronize()
+    dt_sync = torch.tensor([time.perf_counter() - t0], device=dev)
+    # the same loop through the asynchronous form of the same call (DAVO.inference_async): step k+1's copies are queued
+    # while step k computes, as tf.data's prefetch does for the reference's sess.run loop; every step's inputs still
+    # cross PCIe inside the region and every step's poses are read back on the host
+    sync_all()
+    t0 = time.perf_counter()
+    pending = None
+    for _ in range(e2e_steps):
+        nxt = system.inference_async((h_img, h_flow, h_seg))
+        if pending is not None:
+            pose_host = pending.result()["pose"]
+        pending = nxt
+    pose_host = pending.result()["pose"].copy()
+    torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt_sync, op=dist.ReduceOp.MAX)
+    e2e_sync_value = world * 2 * B * e2e_steps / float(dt_sync.item())
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * 2 * B * e2e_steps / float(dt.item())
@@ -347,8 +364,13 @@ def run_ours(args):
         pose_compact = system.inference(None, "pose", inputs=(h_img, c_flow, c_seg))["pose"]
     sync_all()
     t0 = time.perf_counter()
+    pending = None
     for _ in range(e2e_steps):
-        pose_compact = system.inference(None, "pose", inputs=(h_img, c_flow, c_seg))["pose"]
+        nxt = system.inference_async((h_img, c_flow, c_seg))
+        if pending is not None:
+            pose_compact = pending.result()["pose"]
+        pending = nxt
+    pose_compact = pending.result()["pose"].copy()
     torch.cuda.synchronize()
     dtk = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -379,8 +401,13 @@ def run_ours(args):
     os.environ["DAVO_B200_HOST_COPY_ONLY"] = "1"
     sync_all()
     t0 = time.perf_counter()
+    pending = None
     for _ in range(5):
-        system.inference(None, "pose", inputs=(h_img, h_flow, h_seg))
+        nxt = system.inference_async((h_img, h_flow, h_seg))
+        if pending is not None:
+            pending.result()
+        pending = nxt
+    pending.result()
     torch.cuda.synchronize()
     dtc = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -477,6 +504,10 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "pcie_h2d_gbs": pcie_gbs, "pcie_h2d_gbs_all_ranks": pcie_gbs_sum,
                 "copy_only": copy_only_value, "frac_of_copy_only": e2e_value / copy_only_value,
+                "one_call_at_a_time": e2e_sync_value,
+                "api": "DAVO.inference_async(host arrays).result(): one step in flight behind the one being read "
+                       "(davo_forward_host_pairs_async / davo_host_wait); one_call_at_a_time = the blocking "
+                       "DAVO.inference(inputs=host arrays) loop, where each step's pipeline fill and drain are exposed",
                 "compact_inputs": {"value": compact_value, "unit": UNIT, "h2d_bytes_per_step": compact_h2d,
                                    "note": "NOT the reference's input contract: the caller supplies uint8 labels and "
                                            "binary16 flow planes (davo_forward_host_compact); no CPU pass, fewer bytes"},

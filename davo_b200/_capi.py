@@ -21,6 +21,7 @@ SYMBOLS = (
     "davo_profile_layers", "davo_debug_set_conv_impl", "davo_forward_pairs", "davo_forward_host_pairs",
     "davo_forward_features", "davo_debug_flows_to_half", "davo_forward_host_compact", "davo_bind_host_numa",
     "davo_compose_trajectory", "davo_kitti_errors", "davo_decode_jpeg_batch",
+    "davo_forward_host_pairs_async", "davo_forward_host_compact_async", "davo_host_wait",
     "davo_comm_unique_id", "davo_comm_create", "davo_comm_world", "davo_allgather_poses",
     "davo_last_error",
     "davo_destroy", "davo_build_info", "davo_config_bytes",
@@ -76,6 +77,9 @@ def load() -> C.CDLL:
     lib.davo_compose_trajectory.argtypes = [vp, vp, ip, vp, vp]
     lib.davo_kitti_errors.argtypes = [vp, vp, vp, ip, vp, fp, vp]
     lib.davo_decode_jpeg_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64), ip, vp, vp]
+    lib.davo_forward_host_pairs_async.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_longlong)]
+    lib.davo_forward_host_compact_async.argtypes = [vp, ip, ip, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_longlong)]
+    lib.davo_host_wait.argtypes = [vp, C.c_longlong]
     lib.davo_get_intermediate.argtypes = [vp, C.c_char_p, ip, vp, C.c_int64, C.POINTER(C.c_int64)]
     lib.davo_last_launch_count.argtypes = [vp]
     lib.davo_last_host_copy_bytes.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
@@ -96,7 +100,7 @@ def load() -> C.CDLL:
     if lib.davo_config_bytes() != C.sizeof(DavoConfigC):
         raise ImportError("%s: davo_config is %d bytes in the library, %d in this binding (rebuild: python davo_b200/build.py --force)"
                           % (path, lib.davo_config_bytes(), C.sizeof(DavoConfigC)))
-    for s in SYMBOLS[:23]:
+    for s in SYMBOLS[:26]:
         getattr(lib, s).restype = ip
     _LIB = lib
     return lib

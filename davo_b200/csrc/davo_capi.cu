@@ -272,6 +272,9 @@ struct davo_ctx {
   int s_chunk = 0;                  // samples per staging buffer
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[kStage] = {}, ev_consumed[kStage] = {}, ev_start = nullptr;
+  static constexpr int kTickets = 8;      // asynchronous host calls whose completion can still be waited for by name
+  cudaEvent_t ev_host_done[kTickets] = {};
+  long long host_tickets = 0, host_calls = 0;
   long long last_h2d = 0, last_d2h = 0;
   // last forward
   int last_launches = 0;
@@ -1330,6 +1333,7 @@ extern "C" void davo_destroy(davo_ctx* ctx) {
   if (ctx->comm) davo_comm::api().CommDestroy(ctx->comm);
   if (ctx->s_pose) cudaFree(ctx->s_pose);
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  for (cudaEvent_t& ev : ctx->ev_host_done) if (ev) cudaEventDestroy(ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
@@ -1742,11 +1746,29 @@ extern "C" int davo_forward_host(davo_ctx* ctx, int B, const uint8_t* img, const
 // straight from the caller's memory: no CPU pass at all.
 static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
                              const float* seg, const float* depth, float* pose_out, void* stream,
-                             const uint16_t* flow16, const uint8_t* seg8);
+                             const uint16_t* flow16, const uint8_t* seg8, long long* ticket = nullptr);
 
 extern "C" int davo_forward_host_pairs(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
                                        const float* seg, const float* depth, float* pose_out, void* stream) {
   return forward_host_impl(ctx, B, pairs, img, flow, seg, depth, pose_out, stream, nullptr, nullptr);
+}
+
+// Asynchronous forms (include/davo_b200.h): everything is queued, nothing is waited for; *ticket names the call.
+extern "C" int davo_forward_host_pairs_async(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
+                                             const float* seg, const float* depth, float* pose_out, void* stream,
+                                             long long* ticket) {
+  if (!ticket) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host_pairs_async: null ticket");
+  return forward_host_impl(ctx, B, pairs, img, flow, seg, depth, pose_out, stream, nullptr, nullptr, ticket);
+}
+
+extern "C" int davo_host_wait(davo_ctx* ctx, long long ticket) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (ticket <= 0 || ticket > ctx->host_tickets) return fail(ctx, DAVO_ERR_ARG, "davo_host_wait: ticket %lld was never issued", ticket);
+  CU_OK(cudaSetDevice(ctx->device));
+  // the ring holds the last kTickets calls; an older ticket's slot now belongs to a later call on the same stream,
+  // whose completion implies the older one's
+  CU_OK(cudaEventSynchronize(ctx->ev_host_done[ticket % davo_ctx::kTickets]));
+  return 0;
 }
 
 extern "C" int davo_forward_host_compact(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const uint16_t* flow_f16,
@@ -1761,9 +1783,22 @@ extern "C" int davo_forward_host_compact(davo_ctx* ctx, int B, int pairs, const 
                            depth, pose_out, stream, uses_flow ? flow_f16 : nullptr, c.att_src != 0 ? seg_u8 : nullptr);
 }
 
+extern "C" int davo_forward_host_compact_async(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const uint16_t* flow_f16,
+                                               const uint8_t* seg_u8, const float* depth, float* pose_out, void* stream,
+                                               long long* ticket) {
+  if (!ctx) return DAVO_ERR_ARG;
+  if (!ticket) return fail(ctx, DAVO_ERR_ARG, "davo_forward_host_compact_async: null ticket");
+  const davo_config& c = ctx->cfg;
+  const bool uses_flow = (c.in_mode == 1 || c.att_src == 1 || c.att_src == 6 || c.pixel_map == 2);
+  if ((uses_flow && !flow_f16) || (c.att_src != 0 && !seg_u8))
+    return fail(ctx, DAVO_ERR_ARG, "davo_forward_host_compact_async: null input buffer");
+  return forward_host_impl(ctx, B, pairs, img, reinterpret_cast<const float*>(flow_f16), reinterpret_cast<const float*>(seg_u8),
+                           depth, pose_out, stream, uses_flow ? flow_f16 : nullptr, c.att_src != 0 ? seg_u8 : nullptr, ticket);
+}
+
 static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img, const float* flow,
                              const float* seg, const float* depth, float* pose_out, void* stream,
-                             const uint16_t* flow16_in, const uint8_t* seg8_in) {
+                             const uint16_t* flow16_in, const uint8_t* seg8_in, long long* ticket) {
   if (!ctx) return DAVO_ERR_ARG;
   if (pairs < DAVO_PAIRS_ALL || pairs > DAVO_PAIRS_TRAJECTORY_FIRST)
     return fail(ctx, DAVO_ERR_ARG, "davo_forward_host: pair selection %d unknown", pairs);
@@ -1829,8 +1864,12 @@ static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaStream_t cp = ctx->copy_stream;
   // the copy stream must not run ahead of work already queued on the caller's stream
-  CU_OK(cudaEventRecord(ctx->ev_start, st));
-  CU_OK(cudaStreamWaitEvent(cp, ctx->ev_start, 0));
+  // (staging buffers are protected by their own events below, so consecutive calls may overlap: the copies of call
+  // k+1 run under the compute of call k.  Only the first use of the copy stream is ordered behind the caller's stream.)
+  if (ctx->host_calls++ == 0) {
+    CU_OK(cudaEventRecord(ctx->ev_start, st));
+    CU_OK(cudaStreamWaitEvent(cp, ctx->ev_start, 0));
+  }
   const bool need_flow = uses_flow;
   const bool need_seg = c.att_src != 0;
   const bool seg_tgt = need_seg && !c.att_tgt_ones;
@@ -1847,7 +1886,7 @@ static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img
     ns = std::min(cs, B - s0);
     last_ns = ns;
     const int buf = chunk % davo_ctx::kStage;
-    if (chunk >= davo_ctx::kStage) CU_OK(cudaStreamWaitEvent(cp, ctx->ev_consumed[buf], 0));
+    CU_OK(cudaStreamWaitEvent(cp, ctx->ev_consumed[buf], 0));       // whoever read this staging slot last (this call or the one before) is done
     CU_OK(cudaMemcpyAsync(ctx->s_img[buf], img + n_img * s0, n_img * ns, cudaMemcpyHostToDevice, cp));
     h2d += n_img * ns;
     // Labels are small integers held in floats, and the flow is read with 11 significant bits
@@ -1866,7 +1905,7 @@ static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img
     const int npl = seg_tgt ? 3 : 2;
     std::atomic<int> flow_bad{0};
     if (conv_seg || conv_flow) {
-      if (chunk >= davo_ctx::kStage) CU_OK(cudaEventSynchronize(ctx->ev_seg8[buf]));
+      CU_OK(cudaEventSynchronize(ctx->ev_seg8[buf]));              // the pinned staging of this slot has been copied out (no-op before its first use)
       const float* lsrc = conv_seg ? seg + n_seg * s0 : nullptr;
       uint8_t* ldst = ctx->h_seg8[buf];
       const float* fsrc = conv_flow ? flow + n_flow * s0 : nullptr;
@@ -1953,7 +1992,15 @@ static int forward_host_impl(davo_ctx* ctx, int B, int pairs, const uint8_t* img
     last_n = np_chunk;
   }
   CU_OK(cudaMemcpyAsync(pose_out, ctx->s_pose, (size_t)12 * 4 * B, cudaMemcpyDeviceToHost, st));
-  CU_OK(cudaStreamSynchronize(st));
+  if (ticket) {
+    const long long t = ++ctx->host_tickets;
+    cudaEvent_t& ev = ctx->ev_host_done[t % davo_ctx::kTickets];
+    if (!ev) CU_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU_OK(cudaEventRecord(ev, st));
+    *ticket = t;
+  } else {
+    CU_OK(cudaStreamSynchronize(st));
+  }
   ctx->last_launches = launches;
   ctx->last_npairs_mb = last_n;
   ctx->last_h2d = (long long)h2d;

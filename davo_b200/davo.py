@@ -295,6 +295,59 @@ class DAVO(object):
                                                         ptr(out), None), "davo_forward_host_compact")
         return {'pose': out}
 
+    # ------------------------------------------------------------ asynchronous host calls
+    class _Pending(object):
+        """A queued host-input inference; ``result()`` waits for it and returns ``{'pose': ndarray [B,2,6]}``."""
+
+        def __init__(self, system, ticket, out, keep):
+            self._system, self._ticket, self._out, self._keep = system, ticket, out, keep
+
+        def result(self):
+            if self._ticket is not None:
+                s = self._system
+                s._check(s._lib.davo_host_wait(s._h, self._ticket), "davo_host_wait")
+                self._ticket, self._keep = None, None
+            return {'pose': self._out}
+
+    def inference_async(self, inputs, pairs='all'):
+        """``inference(sess, 'pose', inputs=<host arrays>)`` without waiting: the copies and launches are queued and the
+        call returns, so the NEXT call's host->device copies run under this one's compute (what ``tf.data``'s prefetch
+        gives the reference's ``sess.run`` loop).  ``inputs`` as in ``inference`` (float32 arrays, or the compact
+        ``float16`` / ``uint8`` forms); they must not be modified before ``.result()``.  Returns a handle whose
+        ``.result()`` gives the same dict as ``inference``.  Up to 8 calls may be in flight."""
+        import torch
+        if self.config.batch_norm:
+            raise NotImplementedError("DAVO.inference_async: -batch_norm takes the device path (one pass per batch)")
+        sel = _capi.PAIRS[pairs]
+        depth = None
+        if len(inputs) == 4:
+            img, flow, seg, depth = inputs
+        else:
+            img, flow, seg = inputs
+        if self.config.att_src != V.ATT_SE_DEPTH_SEG and not self.config.depth_split:
+            depth = None
+        B = int(img.shape[0])
+        ring = getattr(self, "_async_out", None)
+        if ring is None or ring[0].shape[0] < B:
+            ring = self._async_out = [torch.empty((max(B, self.batch_size), 2, 6), dtype=torch.float32).pin_memory() for _ in range(8)]
+            self._async_n = 0
+        out = ring[self._async_n % 8][:B].numpy()
+        self._async_n += 1
+        compact = getattr(flow, "dtype", None) == np.float16 and getattr(seg, "dtype", None) == np.uint8
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if compact:
+            flow, seg = np.ascontiguousarray(flow), np.ascontiguousarray(seg)
+        else:
+            flow = None if flow is None else np.ascontiguousarray(flow, dtype=np.float32)
+            seg = None if seg is None else np.ascontiguousarray(seg, dtype=np.float32)
+        depth = None if depth is None else np.ascontiguousarray(depth, dtype=np.float32)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        ticket = C.c_longlong(0)
+        fn = self._lib.davo_forward_host_compact_async if compact else self._lib.davo_forward_host_pairs_async
+        self._check(fn(self._h, B, sel, ptr(img), ptr(flow), ptr(seg), ptr(depth), ptr(out), None, C.byref(ticket)),
+                    "davo_forward_host_async")
+        return DAVO._Pending(self, ticket.value, out, (img, flow, seg, depth))
+
     def bind_host_numa(self):
         """Bind this thread (and threads created after it) to the CPUs next to this handle's GPU
         (``davo_bind_host_numa``); call it before allocating pinned inputs.  Returns the NUMA node or -1."""

@@ -181,6 +181,20 @@ int davo_forward_host(davo_ctx*, int B, const uint8_t* img_u8, const float* flow
 int davo_forward_host_compact(davo_ctx*, int B, int pairs, const uint8_t* img_u8, const uint16_t* flow_f16,
                               const uint8_t* seg_u8, const float* depth, float* pose_out, void* cuda_stream);
 
+/* Asynchronous forms of the two host entry points: the call returns as soon as its copies and launches are queued
+ * (chunk by chunk, as above), so the copies of the NEXT batch run under the compute of this one -- the reference gets
+ * the same overlap from tf.data's prefetch in front of sess.run.  `pose_out` must be page-locked and stay valid until
+ * davo_host_wait(ctx, *ticket) returns; calls complete in issue order; the input buffers may be reused as soon as the
+ * call returns only if they are not written before davo_host_wait (the DMA engine reads them in place).  At most 8
+ * tickets are remembered: waiting for an older one waits for a later call, which implies it. */
+int davo_forward_host_pairs_async(davo_ctx*, int B, int pairs, const uint8_t* img_u8, const float* flow,
+                                  const float* seg, const float* depth, float* pose_out, void* cuda_stream,
+                                  long long* ticket);
+int davo_forward_host_compact_async(davo_ctx*, int B, int pairs, const uint8_t* img_u8, const uint16_t* flow_f16,
+                                    const uint8_t* seg_u8, const float* depth, float* pose_out, void* cuda_stream,
+                                    long long* ticket);
+int davo_host_wait(davo_ctx*, long long ticket);
+
 /* Binds the calling thread (and the threads it creates afterwards: the handle's conversion pool, the caller's
  * loader threads) to the CPUs of the NUMA node the handle's GPU hangs off (/sys/bus/pci/devices/<id>/numa_node,
  * local_cpulist), so that pinned staging allocated afterwards is first-touched next to the GPU and the conversion

@@ -835,3 +835,33 @@ def test_nvjpeg_decode_and_loader_feed_the_forward(tmp_path):
         out = torch.empty((1, H, 3 * W, 3), dtype=torch.uint8, device="cuda")
         sysm._check(sysm._lib.davo_decode_jpeg_batch(sysm._h, (C.c_void_p * 1)(C.cast(C.c_char_p(b), C.c_void_p)), (C.c_int64 * 1)(len(b)), 1,
                                                      C.c_void_p(out.data_ptr()), None), "davo_decode_jpeg_batch")
+
+
+def test_asynchronous_host_calls_overlap_and_keep_the_bits():
+    """davo_forward_host_pairs_async / _compact_async + davo_host_wait: several batches queued back to back (the copies
+    of batch k+1 under the compute of batch k) give, batch by batch, the bits of the synchronous calls; results are
+    delivered in order and a handle can be waited for more than once."""
+    _need_gpu()
+    w = S.init_weights(HEADLINE, random_bias=True)
+    batches = [S.make_inputs(20, H, W, seed=200 + i, bad_label_frac=0.01) for i in range(5)]
+    sysm = DAVO(version=HEADLINE)
+    sysm.setup_inference(H, W, "davo", 3, 20, device=0)
+    sysm.load_weights(w)
+    want = [sysm.inference(None, "pose", inputs=b)["pose"].copy() for b in batches]
+    pending = [sysm.inference_async(b) for b in batches]                   # five calls in flight
+    got = [p.result()["pose"].copy() for p in pending]
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    assert np.array_equal(pending[0].result()["pose"], got[0])
+    # trajectory selection and the compact forms, interleaved with synchronous calls
+    c = [(b[0],) + S.compact_inputs(b[1], b[2]) for b in batches[:3]]
+    wide = []
+    for b, cb in zip(batches[:3], c):
+        f = np.zeros_like(b[1])
+        f[:, :2] = cb[1].astype(np.float32)
+        wide.append(sysm.inference(None, "pose", inputs=(b[0], f, b[2]), pairs="trajectory")["pose"].copy())
+    pend = [sysm.inference_async(cb, pairs="trajectory") for cb in c]
+    mid = sysm.inference(None, "pose", inputs=batches[4])["pose"]            # a synchronous call behind queued ones
+    assert np.array_equal(mid, want[4])
+    for a, p in zip(wide, pend):
+        assert np.array_equal(a, p.result()["pose"])
