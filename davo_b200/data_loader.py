@@ -52,8 +52,9 @@ def load_kitti_image_sequence_names(dataset_dir, frames, seq_length, load_pose=F
 class _Batches:
     """Iterator over batches; ``get_next()`` is the reference's name for ``__next__`` (test_kitti_pose.py:104)."""
 
-    def __init__(self, loader, lists, system, decode, workers, prefetch):
+    def __init__(self, loader, lists, system, decode, workers, prefetch, hold=1):
         self.loader, self.lists, self.system, self.decode = loader, lists, system, decode
+        self._hold, self._held = max(1, hold), []          # batches the consumer may still be reading (asynchronous inference)
         self.n = len(lists[0])
         self.B = loader.batch_size
         self.n_batches = -(-self.n // self.B)
@@ -62,7 +63,7 @@ class _Batches:
         self._stop = threading.Event()
         self._pool = ThreadPoolExecutor(max_workers=max(1, workers))
         self._err = None
-        self._buffers(prefetch + 2)
+        self._buffers(prefetch + 1 + self._hold)
         self._thread = threading.Thread(target=self._produce, daemon=True)
         self._thread.start()
         self._served = 0
@@ -136,9 +137,8 @@ class _Batches:
         return self.n_batches
 
     def __next__(self):
-        if getattr(self, "_last", None) is not None:
-            self._free.put(self._last)                       # the previous batch has been consumed
-            self._last = None
+        while len(self._held) >= self._hold:
+            self._free.put(self._held.pop(0))                # that batch has been consumed: its pinned arrays may be refilled
         item = self._q.get()
         if item is None:
             self._pool.shutdown(wait=False)
@@ -146,7 +146,7 @@ class _Batches:
                 raise self._err
             raise StopIteration
         n, buf, jpegs = item
-        self._last = buf
+        self._held.append(buf)
         self._served += 1
         depth = buf["depth"][:n] if "depth" in buf else None
         if self.decode == "host":
@@ -197,18 +197,20 @@ class DataLoader(object):
 
     def load_test_batch_flow(self, image_sequence_names, image_sequence_poses, image_sequence_flows,
                              image_sequence_depths, image_sequence_seglabels, system=None, decode="host", workers=4,
-                             prefetch=8):
+                             prefetch=8, hold=1):
         """Reference ``data_loader.py:241-325``: an iterator over ``(image uint8 [B,H,3W,3], pose (None: never read by
         the graph), flow [B,4,H,W,2], depth [B,3,H,W,1] | None, seglabel [B,3,H,W,1])``.  ``workers`` = the reference's
         ``num_parallel_calls=4``; ``prefetch`` batches are kept ready (the reference: ``prefetch(batch_size * 8)``).
-        ``decode='nvjpeg'`` needs ``system`` (a ``DAVO`` after ``setup_inference``) and yields CUDA tensors."""
+        ``decode='nvjpeg'`` needs ``system`` (a ``DAVO`` after ``setup_inference``) and yields CUDA tensors.  The arrays of
+        a batch stay valid until ``hold`` further batches have been asked for (``hold=3`` for a consumer that keeps two
+        ``inference_async`` calls in flight)."""
         if decode not in ("host", "nvjpeg"):
             raise ValueError("decode must be 'host' or 'nvjpeg'")
         if decode == "nvjpeg" and system is None:
             raise ValueError("decode='nvjpeg' decodes on the GPU of a DAVO handle: pass system=")
         lists = (list(image_sequence_names), list(image_sequence_poses), list(image_sequence_flows),
                  list(image_sequence_depths), list(image_sequence_seglabels))
-        return _Batches(self, lists, system, decode, workers, prefetch)
+        return _Batches(self, lists, system, decode, workers, prefetch, hold)
 
     def batch_unpack_image_sequence(self, image_seq, img_height, img_width, num_source):
         """Reference ``data_loader.py:537-557`` on a numpy / torch array ``[B,H,3W,C]``: (tgt, src stack on channels).

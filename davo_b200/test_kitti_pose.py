@@ -174,7 +174,7 @@ def main(argv=None):
     if world > 1:
         system.init_comm(rank, world)                                  # the library's own NCCL communicator
     poses = torch.empty((len(idx), 2, 6), dtype=torch.float32, device="cuda:%d" % local)
-    batches = None
+    batches, in_flight = None, []
     if not FLAGS.synthetic:
         # the reference's input pipeline (test_kitti_pose.py:90-114): file lists -> DataLoader.load_test_batch_flow;
         # worker threads read, decode and fill pinned batches ahead of the loop below
@@ -184,7 +184,7 @@ def main(argv=None):
         loader = DataLoader(FLAGS.concat_img_dir, B, H, W, FLAGS.seq_length - 1, read_flow=True, read_depth=dsrc != "none",
                             read_seglabel=True)
         batches = loader.load_test_batch_flow(*[[l[j] for j in idx] for l in lists], system=system,
-                                              decode=FLAGS.jpeg_decode, workers=FLAGS.loader_workers)
+                                              decode=FLAGS.jpeg_decode, workers=FLAGS.loader_workers, hold=3)
     for i in range(len(idx) // B):                                     # reference :133
         if batches is not None:
             img, _, flow, depth, seg = batches.get_next()              # reference :104-114: inputs_batch[0..4]
@@ -197,8 +197,18 @@ def main(argv=None):
             sel = 'all'                       # reference semantics: batch 0 contributes tgt->src0 of every sample
         else:
             sel = 'trajectory_first' if (i == 0 and first == 0) else 'trajectory'
-        pred = system.inference(None, mode='pose', inputs=inputs, pairs=sel)   # reference :135
-        poses[i * B:(i + 1) * B] = torch.as_tensor(pred['pose'])
+        if isinstance(inputs[0], np.ndarray) and not system.config.batch_norm:
+            # host arrays: queue this batch and collect the one before last, so that its copies run under the previous
+            # batch's compute (reference :135 is a blocking sess.run behind tf.data's prefetch: the same overlap)
+            in_flight.append((i, system.inference_async(inputs, pairs=sel)))
+            while len(in_flight) > 2:
+                j, h = in_flight.pop(0)
+                poses[j * B:(j + 1) * B] = torch.as_tensor(h.result()['pose'])
+        else:
+            pred = system.inference(None, mode='pose', inputs=inputs, pairs=sel)   # reference :135
+            poses[i * B:(i + 1) * B] = torch.as_tensor(pred['pose'])
+    for j, h in in_flight:
+        poses[j * B:(j + 1) * B] = torch.as_tensor(h.result()['pose'])
     all_poses = parallel.gather_poses(poses[:n_local].contiguous(), n, system).cpu().numpy()
     if rank == 0:
         traj = geo_utils.compose_trajectory(all_poses, B, FLAGS.reference_batch_semantics)   # reference :136-149
