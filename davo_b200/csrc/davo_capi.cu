@@ -194,6 +194,7 @@ struct Layer {
   bool cm_staged = false;      // cm: store epilogue through shared memory + TMA tile stores
   bool cm_cluster = false;     // cm: 2-CTA clusters, each weight slab fetched once and multicast
   bool b_resident = false;     // pm: all weight slabs stay in shared memory
+  bool cin_shared = false;     // grouped layer whose groups all read the same input channels (cin_group_off = 0)
   int strips = -1;             // halo patches cut into one vertical strip per filter column: -1 = decided by plan_layer
                                // (and recorded here); a latency twin takes its big plan's choice so that both accumulate
                                // every output element in the same tap order (bit-identical results at any batch size)
@@ -637,7 +638,7 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     memset(&P, 0, sizeof P);
     P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.groups = L.groups;
     P.Hout = L.Hout; P.Wout = L.Wout; P.out_stride = L.out_stride;
-    P.cin_group_off = L.Cin_g;
+    P.cin_group_off = L.cin_shared ? 0 : L.Cin_g;
     P.n_patches = np; P.n_taps = nt; P.patch_w = Wp;
     P.patch_bytes = patch_bytes; P.patch_stage_bytes = patch_stage;
     P.bias = L.d_bias;
@@ -665,7 +666,7 @@ int plan_layer(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>& bia
     memset(&P, 0, sizeof P);
     P.tiles_w = L.tiles_w; P.tiles_h = L.tiles_h; P.groups = L.groups; P.m_blocks = MB;
     P.Hout = L.Hout; P.Wout = L.Wout; P.out_stride = L.out_stride; P.cout_g = L.BN;
-    P.cin_group_off = L.Cin_g;
+    P.cin_group_off = L.cin_shared ? 0 : L.Cin_g;
     P.n_patches = np; P.n_taps = nt; P.patch_w = Wp;
     P.patch_bytes = patch_bytes; P.patch_stage_bytes = patch_stage;
     P.bias = L.d_bias;
@@ -1018,7 +1019,7 @@ int launch_conv_direct(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t s
     DirectConvParams p;
     memset(&p, 0, sizeof p);
     p.npairs = npairs; p.Hin = L.Hin; p.Win = L.Win; p.Cin_total = L.Cin_total;
-    p.cin_off = g * L.Cin_g; p.Cin = L.Cin_w;
+    p.cin_off = L.cin_shared ? 0 : g * L.Cin_g; p.Cin = L.Cin_w;
     p.Hout = L.Hout; p.Wout = L.Wout; p.Cout = L.BN;
     p.kh = p.kw = L.k; p.stride = L.stride; p.dil = L.dil; p.pad_t = L.pad_t; p.pad_l = L.pad_l;
     p.relu = 1;
@@ -1370,16 +1371,20 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   const bool dilated = c.posenn <= 3;
   const Geo geo_dil[7] = {{7, 2, 1}, {5, 2, 1}, {3, 1, 2}, {3, 1, 4}, {3, 1, 8}, {3, 1, 2}, {3, 2, 1}};
   const Geo geo_v0[7] = {{7, 2, 1}, {5, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}};
-  const Geo* geo = dilated ? geo_dil : geo_v0;
-  if (!dilated && c.posenn_se == 2)       // there cnv6 runs at stride 1 in this mode only (posenn.py:292, 355): not built
-    return fail(ctx, DAVO_ERR_ARG, "-se_skipadd is built for the dilated nets only");
+  // -se_skipadd in the original nets: there, and only there, cnv6 runs at stride 1 (posenn.py:292, 355), so that
+  // cnv5 + se_block(cnv6) add maps of one size
+  const Geo geo_v0_skip[7] = {{7, 2, 1}, {5, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 1, 1}, {3, 2, 1}};
+  const Geo* geo = dilated ? geo_dil : (c.posenn_se == 2 ? geo_v0_skip : geo_v0);
+  // skipadd on a map too short for the channels-on-M plan: the branches' 256-wide cnv6 run as groups of one
+  // pixels-on-M layer that all read the SAME input (a fused N = 512 accumulator does not exist there)
+  const bool skip_grouped = c.posenn_se == 2 && !dilated;
   // couple nets (posenn.py:133-187): one branch, pred 256 -> 6; decouple nets: rotation | translation
   const int nbr = (c.posenn == 1 || c.posenn == 3 || c.posenn == 4) ? 1 : 2;
   const int nsrc = ctx->unit_sample ? 2 : 1;      // poses per evaluation (num_source, posenn.py:19, 76, 140, 196)
   ctx->nbr = nbr;
   const int cout_total[7] = {16, 32, 64, 128, 256, nbr * c6, nbr * 256};
-  const int bn[7] = {16, 32, 64, 128, 256, (c.posenn_se == 1 ? 1 : nbr) * c6, 256};
-  const int groups[7] = {1, 1, 1, 1, 1, c.posenn_se == 1 ? nbr : 1, nbr};
+  const int bn[7] = {16, 32, 64, 128, 256, ((c.posenn_se == 1 || skip_grouped) ? 1 : nbr) * c6, 256};
+  const int groups[7] = {1, 1, 1, 1, 1, (c.posenn_se == 1 || skip_grouped) ? nbr : 1, nbr};
   // -se_insert: cnv6 reads two differently scaled copies of cnv5 (one per branch): a grouped layer
   const bool se5 = c.posenn_se == 1;
   // -se_replace: cnv6 IS the excited cnv5 (256 channels per branch); cnv7 reads the scaled copies directly
@@ -1407,6 +1412,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     L.Cin_total = cin_total[i]; L.Cin_g = cin_g[i]; L.groups = groups[i];
     L.Cin_w = cin_w[i];
     L.BN = bn[i];
+    L.cin_shared = i == 5 && skip_grouped;
     SamePad ph = same_pad(H, L.k, L.stride, L.dil), pw = same_pad(W, L.k, L.stride, L.dil);
     L.Hout = ph.out; L.Wout = pw.out; L.pad_t = ph.before; L.pad_l = pw.before;
     L.Hout_p = L.Hout + (L.Hout & 1 && L.Hout > 1 ? 1 : 0); L.Wout_p = L.Wout + (L.Wout & 1 ? 1 : 0);
@@ -1578,7 +1584,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     std::vector<float> bias0(nbr * c6), bias;
     for (int n = 0; n < nbr * c6; ++n) bias0[n] = b[n / c6]->data[n % c6];
     if (int rc = bias_or_beta(L, bias0, &bias)) return rc;
-    if (se5) {      // two groups: branch g convolves its own scaled copy of cnv5
+    if (se5 || skip_grouped) {      // two groups: branch g convolves its own scaled copy of cnv5 (skip_grouped: the same cnv5)
       auto getw = [&](int g, int ty, int tx, int ci, int n) {
         return w[g]->data[(((size_t)ty * 3 + tx) * 256 + ci) * c6 + n];
       };

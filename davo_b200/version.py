@@ -144,9 +144,6 @@ def parse_version(version: str) -> DavoConfig:
     m = re.search("-cnv6_([0-9]+)", version)
     cfg.cnv6_out = 128 if m is None else int(m.group(1))
     if cfg.posenn_se == PSE_SKIPADD:
-        if cfg.posenn in (POSENN_COUPLE, POSENN_DECOUPLE):
-            raise NotImplementedError("davo_b200: -se_skipadd is built for the dilated nets only (the original nets run "
-                                      "their cnv6 at stride 1 in this mode, reference posenn.py:292, 355)")
         if cfg.cnv6_out != 256:
             # cnv6 = relu(cnv5 + se_block(cnv6)) (posenn.py:229-233): TensorFlow refuses to add 256 and cnv6_out channels
             raise ValueError("Dimensions must be equal, but are 256 and %d (reference posenn.py:233: cnv5 + se_cnv6 "

@@ -101,6 +101,8 @@ CASES = {
     "plain_couple_se_insert": "v1-couplePoseNN-cnv6_64-no_segmask-se_insert",
     "plain_decouple_se_replace": "v0-cnv6_128-segmask_rgb-static-se_replace",
     "plain_decouple_se_insert": "v1-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh-se_insert",
+    "plain_decouple_se_skipadd": "v1-cnv6_256-segmask_all-se_flow-abs_flow-fc_tanh-se_skipadd",     # cnv6 at stride 1 (posenn.py:355)
+    "plain_couple_se_skipadd": "v0-couplePoseNN-cnv6_256-segmask_rgb-static-se_skipadd",
 }
 # version strings the reference itself cannot build, with the exception its graph code raises (checked by the generator)
 REFERENCE_RAISES = {

@@ -141,8 +141,7 @@ def test_skipadd_and_batch_norm_tokens():
     assert (c.posenn_se, c.cnv6_out) == (V.PSE_SKIPADD, 256)
     with pytest.raises(ValueError, match="Dimensions must be equal"):
         V.parse_version(BASE + "-segmask_all-se_skipadd-fc_tanh")               # BASE has -cnv6_128
-    with pytest.raises(NotImplementedError):
-        V.parse_version("v1-couplePoseNN-cnv6_256-no_segmask-se_skipadd")       # the original nets: not built
+    assert V.parse_version("v1-couplePoseNN-cnv6_256-no_segmask-se_skipadd").posenn_se == V.PSE_SKIPADD   # cnv6 at stride 1 there
     assert V.parse_version(BASE + "-segmask_all-se_flow-batch_norm").batch_norm == 1
     assert V.parse_version(BASE + "-segmask_all-se_flow").batch_norm == 0
     c = V.parse_version(BASE + "-no_segmask-se_insert-batch_norm")
