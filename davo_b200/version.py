@@ -266,10 +266,9 @@ def parse_version(version: str) -> DavoConfig:
             cfg.mask_mode = MASK_OFF
     else:
         cfg.mask_mode = MASK_RGB if "-segmask" in version else MASK_OFF
-    if cfg.needs_depth and cfg.att_src != ATT_SE_DEPTH_SEG and cfg.att_src != ATT_SE_FLOW:
-        # depth/disp is only read by sources of the chain; the ones built are the se_depth*_to_seg pair
-        raise NotImplementedError(
-            "davo_b200: depth/disp attention inputs are not built (version %r)" % version)
+    # (a version that says "depth" / "disp" but selects a source that never touches the depth -- e.g. -se_seg-norm_depth --
+    # makes the reference slice input_depth and then ignore it (davo.py:991-996, 1108-1111): needs_depth stays set, the
+    # kernels simply do not read it)
     if "-batch_norm" in version:                                # davo.py:1453
         # slim.batch_norm with its default is_training=True (no normalizer_params, posenn.py:206): batch statistics
         # at test time, so the poses depend on which samples share a call

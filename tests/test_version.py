@@ -174,3 +174,15 @@ def test_depthseg_tokens_fail_the_way_the_reference_does():
     c = V.parse_version(BASE + "-segmask_all-se_flow_on_depthseg_seplayers_15")       # davo.py:1136-1154
     assert (c.att_src, c.att_tgt_ones, c.depth_split, c.needs_depth) == (V.ATT_SE_FLOW, 1, 1, 1)
 
+
+
+def test_depth_token_next_to_a_source_that_ignores_depth():
+    """davo.py:960, 991-996, 1108-1111: "depth" in the version makes the graph slice input_depth; a source that never
+    uses it (-se_seg, -se_flow, static ...) is unaffected -- the same config as without the token."""
+    a = V.parse_version(BASE + "-segmask_all-se_seg-norm_depth-fc_tanh")
+    b = V.parse_version(BASE + "-segmask_all-se_seg-fc_tanh")
+    assert a.needs_depth == 1 and b.needs_depth == 0
+    da, db = a.as_dict(), b.as_dict()
+    for k in ("needs_depth", "depth_norm"):
+        da.pop(k), db.pop(k)
+    assert da == db
