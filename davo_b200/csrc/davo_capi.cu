@@ -257,6 +257,7 @@ struct davo_ctx {
   int numa_node = -1, numa_cpus = 0;      // davo_bind_host_numa
   nvjpegHandle_t jpeg_handle = nullptr;   // davo_decode_jpeg_batch (jpeg.cuh)
   nvjpegJpegState_t jpeg_state = nullptr;
+  int* d_pipe = nullptr;                  // front_pipeline_kernel: work counter, exit counter, launch counter, [mb] ready flags
   double* d_bn_part = nullptr;            // -batch_norm scratch: partial sums, means, reciprocal deviations (bn.cuh)
   float *d_bn_mean = nullptr, *d_bn_rstd = nullptr;
   void* d_traj_scratch = nullptr;         // davo_compose_trajectory / davo_kitti_errors: relative motions, distances, segments
@@ -1087,6 +1088,20 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     fp.pool_2x2 = c.se_pool == 1 ? 1 : 0;
     if (fp.pool_2x2 && c.att_src == 1) fp.se_in = 8;
     const int src_frames = ctx->unit_sample ? 2 : 1;
+    // One launch for pool + pack (frontend.cuh: front_pipeline_kernel): se_flow with global pooling, one pooled frame per
+    // pair, 8-channel packed layout -- the headline and most ablations.  DAVO_B200_FRONT_PIPE=0 keeps the two kernels.
+    static const bool pipe_off = [] { const char* e = getenv("DAVO_B200_FRONT_PIPE"); return e && !strcmp(e, "0"); }();
+    if (!pipe_off && c.att_src == 1 && c.se_pool == 0 && !c.depth_split && !c.pixel_map && c.att_tgt_ones && !ctx->unit_sample &&
+        ctx->packed_c == 8 && ctx->d_pipe) {
+      FrontPipe q;
+      q.next = ctx->d_pipe; q.done = ctx->d_pipe + 1; q.launches = reinterpret_cast<unsigned int*>(ctx->d_pipe + 2);
+      q.ready = reinterpret_cast<unsigned int*>(ctx->d_pipe + 4);
+      const int work = (npairs + kPipeLook) * (kPoolSplits + kPipePack);
+      const int grid = std::min(work, ctx->num_sms * 4);
+      if (int rc = launch_k(ctx, front_pipeline_kernel, dim3(grid), dim3(256), 0, st, false, fp, q)) return rc;
+      ++*launches;
+      return 0;
+    }
     if (c.se_pool >= 2) {                         // mode='spp': out_pool_size [2,1] / [2] / [8,6,4]
       static const int sizes[3][4] = {{2, 2, 1, 0}, {1, 2, 0, 0}, {3, 8, 6, 4}};
       const int* sz = sizes[c.se_pool - 2];
@@ -1495,6 +1510,8 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_poolcnt, (size_t)mb * kAttFrames * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_attw, (size_t)mb * kAttFrames * kAttStride * 4)) return rc;
   if (int rc = dev_alloc(ctx, (void**)&ctx->d_packed, (size_t)mb * c.H * c.W * ctx->packed_c * 4)) return rc;
+  if (int rc = dev_alloc(ctx, (void**)&ctx->d_pipe, (size_t)(4 + mb) * 4)) return rc;
+  CU_OK(cudaMemset(ctx->d_pipe, 0, (size_t)(4 + mb) * 4));
   float* prev = ctx->d_packed;
   for (int i = 0; i < 7; ++i) {
     Layer& L = ctx->layers[i];

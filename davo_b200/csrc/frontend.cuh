@@ -205,10 +205,9 @@ __device__ __forceinline__ void se_dense_layers(const FrontParams& p, const floa
 //                                 target's flow is zeros, whose SE input is the constant se_in(0)
 // blockIdx.z = 0: the pair's source frame; 1: the target frame (variants that do not force the
 // target map to ones).
-__global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
-  pdl_launch_dependents();
-  pdl_wait();                     // workspace buffers are shared with the kernels before this one
-  const int pl = blockIdx.y, fr = blockIdx.z;
+// The body of se_pool_kernel for block (split bx, unit pl, slot fr); returns true in the one block that finished the
+// (unit, slot) and wrote its class weights.  Also called by front_pipeline_kernel.
+__device__ __forceinline__ bool se_pool_body(const FrontParams& p, const int bx, const int pl, const int fr) {
   int b, k;
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W;
@@ -221,13 +220,13 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   __shared__ float s_pool[kPoolDim];
   __shared__ float s_fc1[kPoolDim];
   __shared__ int s_last;
-  float* part = p.pool_part + (((size_t)pl * kAttFrames + fr) * kPoolSplits + blockIdx.x) * kPoolDim;
+  float* part = p.pool_part + (((size_t)pl * kAttFrames + fr) * kPoolSplits + bx) * kPoolDim;
   if (p.att_src == 3 || p.att_src == 6) {
     if (threadIdx.x < kNumClasses) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const size_t seg_off = ((size_t)b * 3 + f) * hw;
     const int per = (hw + kPoolSplits - 1) / kPoolSplits;
-    const int beg = blockIdx.x * per, end = min(beg + per, hw);
+    const int beg = bx * per, end = min(beg + per, hw);
     for (int i = beg + threadIdx.x; i < end; i += 256) {
       const int lab = label_at(p, seg_off, i);                   // tf.cast truncates toward zero
       if (lab >= 0 && lab < kNumClasses) atomicAdd(&s_hist[lab], 1);   // integer counts: exact, order-free
@@ -239,7 +238,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
       if (f != 1) {
         const int n4 = hw / 2;
         const int per4 = (n4 + kPoolSplits - 1) / kPoolSplits;
-        const int beg4 = blockIdx.x * per4, end4 = min(beg4 + per4, n4);
+        const int beg4 = bx * per4, end4 = min(beg4 + per4, n4);
         for (int i = beg4 + threadIdx.x; i < end4; i += 256) {
           const float4 v = flow2_at(p, b, f == 2 ? 1 : 0, 2 * i, hw);
           s0 += se_in_x(v.x, p) + se_in_x(v.z, p);
@@ -266,7 +265,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
       const float4* dt = reinterpret_cast<const float4*>(p.depth + ((size_t)b * 3 + 1) * hw);
       const int n4 = hw / 4;
       const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
-      const int beg = blockIdx.x * per, end = min(beg + per, n4);
+      const int beg = bx * per, end = min(beg + per, n4);
       if (p.depth_norm == 2)                          // se_disp*_to_seg (davo.py:1253-1270): 1. / depth, no target term
         for (int i = beg + threadIdx.x; i < end; i += 256) {
           const float4 a = __ldg(df + i);
@@ -287,7 +286,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
       const int fk = f == 2 ? 1 : 0;                  // flow plane of this frame
       const int n4 = hw / 2;                          // one load = 2 pixels
       const int per = (n4 + kPoolSplits - 1) / kPoolSplits;
-      const int beg = blockIdx.x * per, end = min(beg + per, n4);
+      const int beg = bx * per, end = min(beg + per, n4);
       if (f != 1 && !p.pool_2x2)                      // the target's flow is all zeros (davo.py:979)
 #pragma unroll 4                                      // four loads in flight per thread; the sums keep their order
         for (int i = beg + threadIdx.x; i < end; i += 256) {
@@ -329,7 +328,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
       const uint8_t* img_b = p.img + (size_t)b * p.H * 3 * p.W * 3;
       const int col0 = f * p.W;
       const int per = (hw + kPoolSplits - 1) / kPoolSplits;
-      const int beg = blockIdx.x * per, end = min(beg + per, hw);
+      const int beg = bx * per, end = min(beg + per, hw);
       unsigned int u0 = 0, u1 = 0, u2 = 0;
       for (int i = beg + threadIdx.x; i < end; i += 256) {
         const int h = i / p.W, w = i - h * p.W;
@@ -363,7 +362,7 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
     if (s_last) p.pool_count[pl * kAttFrames + fr] = 0;       // ready for the next launch
   }
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last) return false;
   __threadfence();
   if (threadIdx.x < D) {
     const float* pp = p.pool_part + ((size_t)pl * kAttFrames + fr) * kPoolSplits * kPoolDim + threadIdx.x;
@@ -386,6 +385,13 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
   }
   __syncthreads();
   se_dense_layers(p, s_pool, s_fc1, D, pl, fr);
+  return true;
+}
+
+__global__ void __launch_bounds__(256) se_pool_kernel(const FrontParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
+  se_pool_body(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // se(flow, "se_flow", [8,19], mode='spp', spp_size) (davo.py:1193-1210): spatial_pyramid_pool
@@ -662,20 +668,18 @@ __device__ __forceinline__ void unpack_rgb4(uint32_t t0, uint32_t t1, uint32_t t
   r[3] = img_norm((t2 >> 8) & 255u); g[3] = img_norm((t2 >> 16) & 255u); b[3] = img_norm(t2 >> 24);
 }
 
-__global__ void __launch_bounds__(256, 4) pack8_kernel(const FrontParams p) {
-  pdl_launch_dependents();
-  pdl_wait();                     // workspace buffers are shared with the kernels before this one
+// The body of pack8_kernel for block bx of nbx of unit pl.  Also called by front_pipeline_kernel.
+__device__ __forceinline__ void pack8_body(const FrontParams& p, const int bx, const int nbx, const int pl) {
   __shared__ float s_w[kNumClasses], s_wt[kNumClasses];    // class weights: source frame, target frame
   __shared__ float4 s_stage[8][256];
-  const int pl = blockIdx.y;
   int b, k;
   pair_of_slot(p.pair_mode, p.pair0 + pl, &b, &k);
   const int hw = p.H * p.W, groups = hw / 4;
   if (threadIdx.x < kNumClasses) {
     const bool se = p.att_src == 1 || p.att_src >= 3;
-    s_w[threadIdx.x] = se ? p.att_w[((size_t)pl * kAttFrames + 0) * kAttStride + threadIdx.x]
+    s_w[threadIdx.x] = se ? __ldcg(p.att_w + ((size_t)pl * kAttFrames + 0) * kAttStride + threadIdx.x)
                      : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
-    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? p.att_w[((size_t)pl * kAttFrames + 1) * kAttStride + threadIdx.x]
+    s_wt[threadIdx.x] = (se && !p.att_tgt_ones) ? __ldcg(p.att_w + ((size_t)pl * kAttFrames + 1) * kAttStride + threadIdx.x)
                       : p.att_src == 2 ? p.static_w[threadIdx.x] : 1.0f;
   }
   __syncthreads();
@@ -685,7 +689,7 @@ __global__ void __launch_bounds__(256, 4) pack8_kernel(const FrontParams p) {
   float4* out = reinterpret_cast<float4*>(p.packed + (size_t)pl * hw * 8);
   const int src_col0 = (k == 0) ? 0 : 2 * p.W;
   float4* st = s_stage[warp];
-  for (int base = blockIdx.x * 256; base < groups; base += gridDim.x * 256) {
+  for (int base = bx * 256; base < groups; base += nbx * 256) {
     const int gi = base + threadIdx.x;
     float4 q[8];
     if (gi < groups) {
@@ -737,6 +741,75 @@ __global__ void __launch_bounds__(256, 4) pack8_kernel(const FrontParams p) {
       if (f4_0 + i < (size_t)hw * 2) out[f4_0 + i] = v;
     }
     __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) pack8_kernel(const FrontParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
+  pack8_body(p, blockIdx.x, gridDim.x, blockIdx.y);
+}
+
+// ---- the whole front end of a pass in ONE launch (se_flow with global pooling, 8-channel packed layout) ----
+// Persistent blocks take work items from a global counter, in order.  Step t of the schedule holds the 16 pooling
+// items of frame pair t and the kPipePack packing items of frame pair t - kPipeLook: a pair is packed a few steps after it
+// was pooled, so the second read of its flow planes comes out of L2 instead of HBM, and the latency-bound pooling runs
+// next to the streaming pack instead of in front of it.  A packing item waits for its pair's class weights (a flag the
+// pooling block that finished the pair sets); every item it can wait for has a smaller index and was therefore already
+// taken by a running block that never waits: no deadlock.  The arithmetic of every item is the separate kernels', so
+// the results are the same bits.
+constexpr int kPipePack = 13;        // packing items per pair (as pack8_kernel's grid on full passes)
+constexpr int kPipeLook = 4;         // pairs pooled ahead of the pair being packed (1.7 MB of flow: L2-resident)
+struct FrontPipe {
+  int* next;                         // work counter, zero between launches
+  int* done;                         // blocks that have left, zero between launches
+  unsigned int* launches;            // completed launches: kept on the DEVICE so that a replayed CUDA graph (whose kernel
+                                     // arguments are frozen) still sees a new number every time
+  unsigned int* ready;               // [mb] number of the launch in which the pair's class weights were written
+};
+
+__global__ void __launch_bounds__(256, 4) front_pipeline_kernel(const FrontParams p, const FrontPipe q) {
+  pdl_launch_dependents();
+  pdl_wait();                     // workspace buffers are shared with the kernels before this one
+  __shared__ int s_item;
+  // this launch's number: the counter moves only when the LAST block of a launch leaves, i.e. after every block of that
+  // launch (this one included) has read it
+  const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(q.launches) + 1u;
+  constexpr int kStep = kPoolSplits + kPipePack;
+  const int total = (p.npairs + kPipeLook) * kStep;
+  for (;;) {
+    __syncthreads();                                     // everyone is done with the previous item (and with s_item)
+    if (threadIdx.x == 0) s_item = atomicAdd(q.next, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= total) break;
+    const int t = item / kStep, j = item - t * kStep;
+    if (j < kPoolSplits) {
+      if (t < p.npairs) {
+        const bool finished = se_pool_body(p, j, t, 0);
+        if (finished) {                                  // block-uniform
+          __syncthreads();                               // the class weights of every thread are written ...
+          if (threadIdx.x == 0) { __threadfence(); atomicExch(&q.ready[t], epoch); }   // ... and visible before the flag
+        }
+      }
+    } else {
+      const int pl = t - kPipeLook;
+      if (pl >= 0) {
+        if (threadIdx.x == 0) {
+          while (atomicAdd(&q.ready[pl], 0u) != epoch) __nanosleep(100);
+          __threadfence();
+        }
+        __syncthreads();
+        pack8_body(p, j - kPoolSplits, kPipePack, pl);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(q.done, 1) == (int)gridDim.x - 1) {      // the last block leaves the counters ready for the next launch
+      *q.next = 0; *q.done = 0; *q.launches = epoch;
+      __threadfence();
+    }
   }
 }
 

@@ -212,7 +212,7 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     assert np.array_equal(a, b)
     c = sysm.inference(None, "pose", as_torch=True)["pose"]
     assert c.is_cuda and np.array_equal(c.cpu().numpy(), a)
-    assert sysm.last_launch_count() == 10                                    # pool, pack, 7 convs, head
+    assert sysm.last_launch_count() == 9                                     # front end (pool + pack in one launch), 7 convs, head
 
 
 @pytest.mark.parametrize("key", ["headline", "static", "no_segmask"])
