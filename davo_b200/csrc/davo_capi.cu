@@ -1088,10 +1088,11 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     fp.pool_2x2 = c.se_pool == 1 ? 1 : 0;
     if (fp.pool_2x2 && c.att_src == 1) fp.se_in = 8;
     const int src_frames = ctx->unit_sample ? 2 : 1;
-    // One launch for pool + pack (frontend.cuh: front_pipeline_kernel): se_flow with global pooling, one pooled frame per
-    // pair, 8-channel packed layout -- the headline and most ablations.  DAVO_B200_FRONT_PIPE=0 keeps the two kernels.
-    static const bool pipe_off = [] { const char* e = getenv("DAVO_B200_FRONT_PIPE"); return e && !strcmp(e, "0"); }();
-    if (!pipe_off && c.att_src == 1 && c.se_pool == 0 && !c.depth_split && !c.pixel_map && c.att_tgt_ones && !ctx->unit_sample &&
+    // Experiment, off by default (DAVO_B200_FRONT_PIPE=1): pool + pack in ONE launch (frontend.cuh: front_pipeline_kernel)
+    // for se_flow with global pooling and the 8-channel layout.  Same bits, but measured slower than the two kernels
+    // (0.237 vs 0.186 ms per 256 pairs, 21 vs 10 us for one sample: profiles/r2_experiment_front_pipeline.log).
+    static const bool pipe_on = [] { const char* e = getenv("DAVO_B200_FRONT_PIPE"); return e && !strcmp(e, "1"); }();
+    if (pipe_on && c.att_src == 1 && c.se_pool == 0 && !c.depth_split && !c.pixel_map && c.att_tgt_ones && !ctx->unit_sample &&
         ctx->packed_c == 8 && ctx->d_pipe) {
       FrontPipe q;
       q.next = ctx->d_pipe; q.done = ctx->d_pipe + 1; q.launches = reinterpret_cast<unsigned int*>(ctx->d_pipe + 2);

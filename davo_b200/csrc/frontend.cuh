@@ -796,7 +796,11 @@ __global__ void __launch_bounds__(256, 4) front_pipeline_kernel(const FrontParam
       const int pl = t - kPipeLook;
       if (pl >= 0) {
         if (threadIdx.x == 0) {
-          while (atomicAdd(&q.ready[pl], 0u) != epoch) __nanosleep(100);
+          const long long t0 = clock64();                   // bounded like every other wait: a protocol bug traps, never hangs
+          while (atomicAdd(&q.ready[pl], 0u) != epoch) {
+            __nanosleep(100);
+            if (clock64() - t0 > 4000000000LL) __trap();
+          }
           __threadfence();
         }
         __syncthreads();

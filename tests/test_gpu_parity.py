@@ -212,7 +212,7 @@ def test_host_buffer_entry_point_matches_device_entry_point():
     assert np.array_equal(a, b)
     c = sysm.inference(None, "pose", as_torch=True)["pose"]
     assert c.is_cuda and np.array_equal(c.cpu().numpy(), a)
-    assert sysm.last_launch_count() == 9                                     # front end (pool + pack in one launch), 7 convs, head
+    assert sysm.last_launch_count() == 10                                    # pool, pack, 7 convs, head
 
 
 @pytest.mark.parametrize("key", ["headline", "static", "no_segmask"])
@@ -865,3 +865,35 @@ def test_asynchronous_host_calls_overlap_and_keep_the_bits():
     assert np.array_equal(mid, want[4])
     for a, p in zip(wide, pend):
         assert np.array_equal(a, p.result()["pose"])
+
+
+def test_front_pipeline_experiment_gives_the_same_bits(monkeypatch):
+    """DAVO_B200_FRONT_PIPE=1 (off by default: measured slower): pool and pack of a pass in one launch of persistent
+    blocks with per-pair ready flags -- the same bits as the two kernels, also when replayed as a CUDA graph."""
+    _need_gpu()
+    w = S.init_weights(HEADLINE, random_bias=True)
+    inputs = S.make_inputs(9, H, W, seed=71, bad_label_frac=0.01)
+    ref_sys, _ = _system(HEADLINE, 9, w, inputs)
+    ref = ref_sys.inference(None, "pose")["pose"]
+    assert ref_sys.last_launch_count() == 10
+    monkeypatch.setenv("DAVO_B200_FRONT_PIPE", "1")
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r)
+        from davo_b200 import synthetic as S
+        from davo_b200.davo import DAVO
+        ver = %r
+        inputs = [torch.as_tensor(x).cuda() for x in S.make_inputs(9, 128, 416, seed=71, bad_label_frac=0.01)]
+        s = DAVO(version=ver); s.setup_inference(128, 416, "davo", 3, 9, inputs[0], input_flow=inputs[1], input_seglabel=inputs[2], device=0)
+        s.load_weights(S.init_weights(ver, random_bias=True))
+        outs = [s.inference(None, "pose")["pose"] for _ in range(6)]          # the later calls replay a captured graph
+        assert s.last_launch_count() == 9 and all(np.array_equal(outs[0], o) for o in outs)
+        np.save(sys.argv[1], outs[-1])
+    """ % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), HEADLINE))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:                              # the knob is read once per process
+        r = subprocess.run([sys.executable, "-c", code, os.path.join(d, "p.npy")], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, DAVO_B200_FRONT_PIPE="1"))
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert np.array_equal(np.load(os.path.join(d, "p.npy")), ref)
