@@ -1,6 +1,7 @@
 """ctypes driver of the plain-C restatement ``oracle/posenn_ref.c``.
 
-TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``); PARITY UNPINNED.
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``); pinned through the torch restatement it must agree with
+(tests/test_oracle.py), which is held to the fixtures made by the reference's own code.
 ``build()`` compiles it with gcc into ``oracle/_build/`` (git-ignored).
 """
 from __future__ import annotations

@@ -1,7 +1,8 @@
 """CPU restatement of DAVO's pose-estimation forward graph (torch-CPU, fp64 or fp32).
 
-TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.  PARITY UNPINNED (the
-reference holds no golden vectors for this path; TF 1.13 is not installable).
+TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.  PINNED on the reference's own graph code: tests/test_oracle.py
+holds every function here to tests/golden/poses.npz, which tests/golden/make_golden.py produces by running the
+reference's unmodified davo.py / nets/*.py over tests/tf_shim (TF 1.13 itself is not installable here).
 
 Every function cites the reference file:line it follows (paths relative to the
 reference checkout).  Activations are NHWC at the interface (as in TF) and NCHW

@@ -1,7 +1,7 @@
 /*
  * posenn_ref.c -- plain-C, double-precision restatement of DAVO's pose forward
  * path for ONE sample (frame triple).  TEST INFRASTRUCTURE ONLY (see
- * oracle/__init__.py); PARITY UNPINNED (the reference holds no golden vectors).
+ * oracle/__init__.py); pinned through oracle/davo_oracle.py, which tests hold to fixtures made by the reference's own graph code.
  *
  * It is written independently of oracle/davo_oracle.py (scalar loops, no
  * library convolution) so that the two restatements check each other on the
