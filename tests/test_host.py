@@ -492,6 +492,16 @@ def test_data_loader_mirrors_load_test_batch_flow(tmp_path):
             assert np.array_equal(depth[k], seg[k])                        # the depth list IS the seglabel list here
         seen += n
     assert seen == 7
+    # hold=3: a batch's arrays stay untouched while two later batches are fetched (a consumer with two asynchronous
+    # inferences in flight); with hold=1 they may be refilled as soon as the next batch is asked for
+    one = DataLoader(str(tmp_path / "dump"), 1, h, w, 2, read_flow=True, read_seglabel=True)
+    it = one.load_test_batch_flow(names, poses, flows, depths, segs, workers=2, prefetch=1, hold=3)
+    first = it.get_next()
+    snap = first[2].copy()
+    for _ in range(2):
+        it.get_next()
+    assert np.array_equal(first[2], snap) and np.array_equal(snap[0], np.load(flows[0]))
+    it.close()
     bad = loader.load_test_batch_flow(names[:2] + [str(tmp_path / "missing.jpg")], poses[:3], flows[:3], depths[:3], segs[:3])
     with pytest.raises(FileNotFoundError):
         list(bad)
