@@ -19,7 +19,7 @@ SYMBOLS = (
     "davo_forward_host", "davo_get_intermediate", "davo_last_launch_count",
     "davo_last_host_copy_bytes",
     "davo_profile_layers", "davo_debug_set_conv_impl", "davo_forward_pairs", "davo_forward_host_pairs",
-    "davo_forward_features", "davo_debug_flows_to_half", "davo_forward_host_compact", "davo_bind_host_numa",
+    "davo_forward_features", "davo_debug_flows_to_half", "davo_debug_labels_to_bytes", "davo_forward_host_compact", "davo_bind_host_numa",
     "davo_compose_trajectory", "davo_kitti_errors", "davo_decode_jpeg_batch",
     "davo_forward_host_pairs_async", "davo_forward_host_compact_async", "davo_host_wait",
     "davo_comm_unique_id", "davo_comm_create", "davo_comm_world", "davo_allgather_poses",
@@ -87,6 +87,7 @@ def load() -> C.CDLL:
     lib.davo_debug_set_conv_impl.argtypes = [vp, ip]
     lib.davo_forward_features.argtypes = [vp, ip, vp, vp, vp, vp, vp, C.POINTER(DavoFeaturesC), vp]
     lib.davo_debug_flows_to_half.argtypes = [vp, vp, C.c_longlong, ip]
+    lib.davo_debug_labels_to_bytes.argtypes = [vp, vp, C.c_longlong, ip]
     lib.davo_comm_unique_id.argtypes = [vp]
     lib.davo_comm_create.argtypes = [vp, vp, ip, ip]
     lib.davo_comm_world.argtypes = [vp, C.POINTER(ip), C.POINTER(ip)]
@@ -100,7 +101,7 @@ def load() -> C.CDLL:
     if lib.davo_config_bytes() != C.sizeof(DavoConfigC):
         raise ImportError("%s: davo_config is %d bytes in the library, %d in this binding (rebuild: python davo_b200/build.py --force)"
                           % (path, lib.davo_config_bytes(), C.sizeof(DavoConfigC)))
-    for s in SYMBOLS[:26]:
+    for s in SYMBOLS[:27]:
         getattr(lib, s).restype = ip
     _LIB = lib
     return lib

@@ -82,4 +82,67 @@ bool flows_to_half(const float* src, uint16_t* dst, size_t n) {
 
 bool flows_to_half_portable(const float* src, uint16_t* dst, size_t n) { return to_half_scalar(src, dst, n); }
 
+// ---- segmentation labels: float32 -> one byte -------------------------------------------------------------------
+static void labels_scalar(const float* src, uint8_t* dst, size_t n) {
+  for (size_t i = 0; i < n; ++i) {
+    const float v = src[i];
+    dst[i] = (v > -1.0f && v < 19.0f) ? (uint8_t)(int)v : (v != v ? (uint8_t)0 : (uint8_t)255);
+  }
+}
+
+#ifdef DAVO_X86
+// 16 labels per step: in range -> the truncated integer, NaN -> 0, everything else -> 255
+static void labels_sse2(const float* src, uint8_t* dst, size_t n) {
+  const __m128 lo = _mm_set1_ps(-1.0f), hi = _mm_set1_ps(19.0f);
+  const __m128i inval = _mm_set1_epi32(255);
+  size_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    __m128i r[4];
+    for (int k = 0; k < 4; ++k) {
+      const __m128 v = _mm_loadu_ps(src + i + 4 * k);
+      const __m128i ok = _mm_castps_si128(_mm_and_ps(_mm_cmpgt_ps(v, lo), _mm_cmplt_ps(v, hi)));
+      const __m128i nan = _mm_castps_si128(_mm_cmpunord_ps(v, v));
+      const __m128i iv = _mm_cvttps_epi32(v);
+      r[k] = _mm_or_si128(_mm_and_si128(ok, iv), _mm_andnot_si128(ok, _mm_andnot_si128(nan, inval)));
+    }
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i),
+                     _mm_packus_epi16(_mm_packs_epi32(r[0], r[1]), _mm_packs_epi32(r[2], r[3])));
+  }
+  labels_scalar(src + i, dst + i, n - i);
+}
+
+// the same on 32 labels per step; the 256-bit packs work per 128-bit lane, so one dword permute puts the bytes in order
+__attribute__((target("avx2"))) static void labels_avx2(const float* src, uint8_t* dst, size_t n) {
+  const __m256 lo = _mm256_set1_ps(-1.0f), hi = _mm256_set1_ps(19.0f);
+  const __m256i inval = _mm256_set1_epi32(255);
+  const __m256i order = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+  size_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    __m256i r[4];
+    for (int k = 0; k < 4; ++k) {
+      const __m256 v = _mm256_loadu_ps(src + i + 8 * k);
+      const __m256i ok = _mm256_castps_si256(_mm256_and_ps(_mm256_cmp_ps(v, lo, _CMP_GT_OQ), _mm256_cmp_ps(v, hi, _CMP_LT_OQ)));
+      const __m256i nan = _mm256_castps_si256(_mm256_cmp_ps(v, v, _CMP_UNORD_Q));
+      const __m256i iv = _mm256_cvttps_epi32(v);
+      r[k] = _mm256_or_si256(_mm256_and_si256(ok, iv), _mm256_andnot_si256(ok, _mm256_andnot_si256(nan, inval)));
+    }
+    const __m256i b = _mm256_packus_epi16(_mm256_packs_epi32(r[0], r[1]), _mm256_packs_epi32(r[2], r[3]));
+    _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_permutevar8x32_epi32(b, order));
+  }
+  labels_sse2(src + i, dst + i, n - i);
+}
+#endif
+
+void labels_to_bytes(const float* src, uint8_t* dst, size_t n) {
+#ifdef DAVO_X86
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) return labels_avx2(src, dst, n);
+  return labels_sse2(src, dst, n);
+#else
+  labels_scalar(src, dst, n);
+#endif
+}
+
+void labels_to_bytes_portable(const float* src, uint8_t* dst, size_t n) { labels_scalar(src, dst, n); }
+
 }  // namespace davo_host

@@ -407,6 +407,26 @@ def test_host_flow_conversion_is_ieee_binary16_round_to_nearest_even():
             assert lib.davo_debug_flows_to_half(bad.ctypes.data, out.ctypes.data, bad.size, portable) == 1
 
 
+def test_host_label_conversion_truncates_and_marks_invalid_labels():
+    """davo_debug_labels_to_bytes (csrc/host_convert.cpp): the vector and the scalar path agree with
+    tf.cast(label, int32) followed by one_hot(depth=19)'s treatment of out-of-range indices, at every tail length."""
+    from davo_b200 import _capi
+    lib = _capi.load()
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.integers(0, 19, 4099).astype(np.float32), rng.uniform(-3, 22, 4000).astype(np.float32),
+                        np.float32([-0.0, -0.5, -0.999, -1.0, 18.0, 18.999, 19.0, 255.0, 256.0, 1e9, -1e9, 3e38, -3e38,
+                                    np.inf, -np.inf, np.nan])])
+    with np.errstate(invalid="ignore"):
+        t = np.trunc(x)
+    want = np.where(np.isnan(x), 0, np.where((t >= 0) & (t <= 18), t, 255)).astype(np.uint8)
+    for portable in (0, 1):
+        for n in (x.size, 31, 32, 33, 47, 48, 15, 1, 0):
+            src = np.ascontiguousarray(x[x.size - n:])
+            out = np.full(n + 8, 0xAB, np.uint8)
+            assert lib.davo_debug_labels_to_bytes(src.ctypes.data, out.ctypes.data, n, portable) == 0
+            assert np.array_equal(out[:n], want[x.size - n:]) and np.all(out[n:] == 0xAB)
+
+
 def test_binding_struct_matches_the_header():
     """The ctypes davo_config has the header's fields in the header's order, and the library's size."""
     import ctypes as C, re

@@ -7,8 +7,8 @@ sys.path.insert(0, ROOT)
 from davo_b200 import build as B
 LIB = os.path.join(ROOT, "tools", "experiments", "libdavo_b200_timing.so")
 if "--build" in sys.argv or not os.path.exists(LIB):
-    cmd = [B.find_nvcc()] + [f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DDAVO_TIMING",
-           os.path.join(B.CSRC, "davo_capi.cu"), "-o", LIB]
+    cmd = [B.find_nvcc()] + [f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DDAVO_TIMING"] + \
+          [os.path.join(B.CSRC, s) for s in B.SOURCES] + ["-o", LIB]
     subprocess.run(cmd, check=True)
     if "--build" in sys.argv:
         sys.exit(0)
