@@ -467,6 +467,10 @@ def run_ours(args):
         "front_end_frac_hbm": FRONT_BYTES_PER_PAIR * npairs / (layer_ms["front"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
         "whole_step_tflops": value / world * FLOP_PER_PAIR / 1e12,
         "whole_step_frac": value / world * FLOP_PER_PAIR / 1e12 / peak_tf32,
+        # the timed region is a long step under the power cap: beside the burst denominator above, the same number
+        # against MEASURED_PEAKS' sustained bf16 figure / 2 (what a long tensor-bound run on this pool's B200s keeps up)
+        "whole_step_frac_of_sustained": value / world * FLOP_PER_PAIR / 1e12 / (peaks["bf16_tflops_sustained"] / 2.0)
+        if peaks.get("bf16_tflops_sustained") else None,
     }
     # CPU baseline leg = the fp32 oracle on the FIRST 16 SAMPLES OF THE TIMED BATCH; its poses are the parity reference
     rate, cdt, thr, n, ref16 = cpu_oracle_rate(16, 1, min_seconds=12.0, inputs=(img, flow, seg))
