@@ -307,6 +307,7 @@ class DAVO(object):
                 s = self._system
                 s._check(s._lib.davo_host_wait(s._h, self._ticket), "davo_host_wait")
                 self._ticket, self._keep = None, None
+                self._out = np.array(self._out)      # the caller's own copy: the pinned ring slot is reused 8 calls later
             return {'pose': self._out}
 
     def inference_async(self, inputs, pairs='all'):
