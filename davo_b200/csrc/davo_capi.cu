@@ -1251,8 +1251,8 @@ extern "C" int davo_create(const davo_config* cfg, int device, davo_ctx** out) {
   if (cfg->H <= 0 || cfg->W <= 0 || (cfg->H % 8) || (cfg->W % 8))
     return fail(nullptr, DAVO_ERR_ARG, "davo_create: H and W must be positive multiples of 8 (got %dx%d)", cfg->H, cfg->W);
   if (cfg->max_batch <= 0) return fail(nullptr, DAVO_ERR_ARG, "davo_create: max_batch must be positive");
-  if (cfg->cnv6_out != 128 && cfg->cnv6_out != 64 && cfg->cnv6_out != 32 && !(cfg->cnv6_out == 256 && cfg->posenn_se == 2))
-    return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64 or 128; 256 with -se_skipadd)", cfg->cnv6_out);
+  if (cfg->cnv6_out != 256 && cfg->cnv6_out != 128 && cfg->cnv6_out != 64 && cfg->cnv6_out != 32)
+    return fail(nullptr, DAVO_ERR_ARG, "davo_create: cnv6 width %d unsupported (32, 64, 128 or 256)", cfg->cnv6_out);
   if (cfg->in_mode != 0 && cfg->in_mode != 1) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad in_mode");
   if (cfg->att_src < 0 || cfg->att_src > 6) return fail(nullptr, DAVO_ERR_ARG, "davo_create: bad att_src");
   if (cfg->se_pool < 0 || cfg->se_pool > 4 || cfg->se_hidden < 0 || cfg->se_hidden > 19 ||
@@ -1365,11 +1365,13 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
   // cnv5 + se_block(cnv6) add maps of one size
   const Geo geo_v0_skip[7] = {{7, 2, 1}, {5, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 2, 1}, {3, 1, 1}, {3, 2, 1}};
   const Geo* geo = dilated ? geo_dil : (c.posenn_se == 2 ? geo_v0_skip : geo_v0);
-  // skipadd on a map too short for the channels-on-M plan: the branches' 256-wide cnv6 run as groups of one
-  // pixels-on-M layer that all read the SAME input (a fused N = 512 accumulator does not exist there)
-  const bool skip_grouped = c.posenn_se == 2 && !dilated;
   // couple nets (posenn.py:133-187): one branch, pred 256 -> 6; decouple nets: rotation | translation
   const int nbr = (c.posenn == 1 || c.posenn == 3 || c.posenn == 4) ? 1 : 2;
+  // two 256-wide cnv6 branches (-cnv6_256, which -se_skipadd requires) on a map too short for the channels-on-M plan
+  // (the stride-2 nets; a dilated net on a frame under 128 rows): the branches run as groups of one pixels-on-M layer
+  // that all read the SAME input -- a fused N = 512 accumulator does not exist there
+  const int h_cnv3_in = same_pad(same_pad(c.H, 7, 2, 1).out, 5, 2, 1).out;
+  const bool skip_grouped = c.cnv6_out == 256 && nbr == 2 && c.posenn_se != 1 && c.posenn_se != 3 && !(dilated && h_cnv3_in >= 32);
   const int nsrc = ctx->unit_sample ? 2 : 1;      // poses per evaluation (num_source, posenn.py:19, 76, 140, 196)
   ctx->nbr = nbr;
   const int cout_total[7] = {16, 32, 64, 128, 256, nbr * c6, nbr * 256};

@@ -143,11 +143,6 @@ def parse_version(version: str) -> DavoConfig:
     # G3 cnv6 width (davo.py:1052-1053)
     m = re.search("-cnv6_([0-9]+)", version)
     cfg.cnv6_out = 128 if m is None else int(m.group(1))
-    if cfg.posenn_se == PSE_SKIPADD:
-        if cfg.cnv6_out != 256:
-            # cnv6 = relu(cnv5 + se_block(cnv6)) (posenn.py:229-233): TensorFlow refuses to add 256 and cnv6_out channels
-            raise ValueError("Dimensions must be equal, but are 256 and %d (reference posenn.py:233: cnv5 + se_cnv6 "
-                             "needs -cnv6_256)" % cfg.cnv6_out)
     # G4 input version (davo.py:1057-1065)
     m = re.search("^(v[0-9.]+)", version)
     tag = "v0" if m is None else m.group(1)
@@ -159,11 +154,7 @@ def parse_version(version: str) -> DavoConfig:
     else:
         cfg.in_mode = 0     # pred_info stays None (davo.py:1060)
     # G5 (davo.py:1066-1073)
-    if "-seglabelid" in version:
-        # The reference's inference graph cannot be built with this token: davo.py:1069-1073 zips the four
-        # pred_info entries with the THREE label maps (or replaces them by the three label maps), and
-        # davo.py:1442 (and :1428/:1434 before it) then reads pred_info[3].  Same exception, same reason.
-        raise IndexError("list index out of range (reference davo.py:1442: -seglabelid leaves pred_info with 3 entries)")
+    # (-seglabelid: the token is harmless here; the graph fails where the masking reads pred_info, see G12 below)
     # G6 SE activation (davo.py:1077-1085)
     if "-fc_tanh" in version:
         cfg.se_act = ACT_TANH
@@ -254,6 +245,13 @@ def parse_version(version: str) -> DavoConfig:
             cfg.att_src = ATT_STATIC
             cfg.att_tgt_ones = 0
     # G12 masking (davo.py:1415-1450)
+    if "-seglabelid" in version:
+        # The reference's inference graph cannot be built with this token: davo.py:1069-1073 zips the four
+        # pred_info entries with the THREE label maps (or replaces them by the three label maps), and
+        # davo.py:1442 (and :1428/:1434 before it) then reads pred_info[3].  Same exception, same reason -- and raised
+        # here, after the attention-source chain, because a version with two faults stops at the reference's first one
+        # (tests/golden/fuzz_versions.py).
+        raise IndexError("list index out of range (reference davo.py:1442: -seglabelid leaves pred_info with 3 entries)")
     if cfg.in_mode == 1:
         if "-segmask_" in version:
             if "-segmask_all" in version and ".555" in tag:
@@ -273,4 +271,9 @@ def parse_version(version: str) -> DavoConfig:
         # slim.batch_norm with its default is_training=True (no normalizer_params, posenn.py:206): batch statistics
         # at test time, so the poses depend on which samples share a call
         cfg.batch_norm = 1
+    if cfg.posenn_se == PSE_SKIPADD and cfg.cnv6_out != 256:
+        # cnv6 = relu(cnv5 + se_block(cnv6)) (posenn.py:229-233): TensorFlow refuses to add 256 and cnv6_out channels.
+        # The PoseNN is built after everything above (davo.py:1456), so this is the last fault the reference reports.
+        raise ValueError("Dimensions must be equal, but are 256 and %d (reference posenn.py:233: cnv5 + se_cnv6 "
+                         "needs -cnv6_256)" % cfg.cnv6_out)
     return cfg

@@ -103,6 +103,11 @@ CASES = {
     "plain_decouple_se_insert": "v1-cnv6_128-segmask_all-se_flow-abs_flow-fc_tanh-se_insert",
     "plain_decouple_se_skipadd": "v1-cnv6_256-segmask_all-se_flow-abs_flow-fc_tanh-se_skipadd",     # cnv6 at stride 1 (posenn.py:355)
     "plain_couple_se_skipadd": "v0-couplePoseNN-cnv6_256-segmask_rgb-static-se_skipadd",
+    # -cnv6_256 on its own (the regex at davo.py:1052 takes any width): a 512-wide fused cnv6 in the dilated shared net,
+    # two groups on one input in the stride-2 net, one 256-wide branch in a couple net (found missing by tools/fuzz_gpu.py)
+    "cnv6_256": "v1-sharedNN-dilatedPoseNN-cnv6_256-segmask_all-se_flow-abs_flow-fc_tanh",
+    "cnv6_256_plain_net": "v0-cnv6_256-segmask_rgb-static",
+    "cnv6_256_couple_se_insert": "v1-dilatedCouplePoseNN-cnv6_256-no_segmask-se_insert",
 }
 # version strings the reference itself cannot build, with the exception its graph code raises (checked by the generator)
 REFERENCE_RAISES = {
@@ -114,6 +119,12 @@ REFERENCE_RAISES = {
     "v1-sharedNN-dilatedPoseNN-segmask_all-se_mixDepthFlow-fc_tanh": "UnboundLocalError",
     "v1-sharedNN-dilatedPoseNN-segmask_all-se_flow-seglabelid": "IndexError",
     "v1-sharedNN-dilatedPoseNN-cnv6_128-no_segmask-se_skipadd": "ValueError",      # cnv5 (256) + se_block(cnv6) (128)
+    # two faults in one string: the reference stops at the first one in ITS evaluation order -- PoseNN type, then the
+    # attention-source chain, then the masking (where -seglabelid fails), then the PoseNN build (found by fuzz_versions.py)
+    "v1-cnv6_128-segmask-se_depth_wo_tgt_to_seg-seglabelid-se_skipadd-fc_tanh": "IndexError",
+    "v1-cnv6_128-segmask-se_mixDispFlow-seglabelid-norm_flow": "UnboundLocalError",
+    "v1-dilatedPoseNN-cnv6_64-segmask-se_mixDepthFlow-se_skipadd-norm_flow-fc_tanh": "UnboundLocalError",
+    "v1-sharedNN-couplePoseNN-cnv6_128-seglabelid-se_skipadd": "NameError",
 }
 GOLDEN = dict(batch=2, height=128, width=416, input_seed=1234, weight_seed=8964, bad_label_frac=0.01)
 # other frame sizes of the headline variant (BASELINE configs[4]: 256x832; a partial widened run; a width that is not

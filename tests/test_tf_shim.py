@@ -217,6 +217,20 @@ def test_reference_rejects_the_version_strings_the_parser_rejects():
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference checkout not on this box")
+def test_random_version_strings_agree_with_the_reference():
+    """tests/golden/fuzz_versions.py, a short run: random strings of the version grammar give the same poses (or the
+    same exception type) from the reference's graph code and from version.parse_version + the oracle.  Longer runs
+    (thousands of strings) are recorded in DESIGN section 2."""
+    sys.path.insert(0, os.path.dirname(G.__file__))
+    try:
+        import fuzz_versions
+    finally:
+        sys.path.pop(0)
+    bad, summary = fuzz_versions.run(40, seed=3, verbose=False)
+    assert not bad, (summary, bad)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not on this box")
 def test_reference_pose_vec2mat_and_composition_loop_over_the_shim():
     """utils/geo_utils.py:93-119 (TF) executed over the shim == the host geo_utils used for the trajectory."""
     from davo_b200 import geo_utils

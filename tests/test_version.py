@@ -2,6 +2,7 @@
 import pytest
 
 from davo_b200 import version as V
+from tests.golden import make_golden as G
 
 BASE = "v1-decay100k-sharedNN-dilatedPoseNN-cnv6_128"
 
@@ -162,6 +163,16 @@ def test_seglabelid_fails_the_way_the_reference_graph_does():
     for ver in (BASE + "-seglabelid-segmask_all-se_flow", "v0-sharedNN-dilatedPoseNN-seglabelid", BASE + "-seglabelid-no_segmask"):
         with pytest.raises(IndexError, match="list index out of range"):
             V.parse_version(ver)
+
+
+def test_a_version_with_two_faults_stops_at_the_reference_s_first_one():
+    """Evaluation order of the reference: PoseNN type (davo.py:1027-1049), attention-source chain (:1117-1400), masking
+    (:1415-1450, where -seglabelid fails), PoseNN build (posenn.py:233).  Each string is also run through the reference's
+    own code where the checkout exists (make_golden.REFERENCE_RAISES, tests/test_tf_shim.py)."""
+    for ver, exc in G.REFERENCE_RAISES.items():
+        with pytest.raises(Exception) as e:
+            V.parse_version(ver)
+        assert type(e.value).__name__ == exc, (ver, e.value)
 
 
 def test_depthseg_tokens_fail_the_way_the_reference_does():
