@@ -1407,7 +1407,7 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
     L.cin_shared = i == 5 && skip_grouped;
     SamePad ph = same_pad(H, L.k, L.stride, L.dil), pw = same_pad(W, L.k, L.stride, L.dil);
     L.Hout = ph.out; L.Wout = pw.out; L.pad_t = ph.before; L.pad_l = pw.before;
-    L.Hout_p = L.Hout + (L.Hout & 1 && L.Hout > 1 ? 1 : 0); L.Wout_p = L.Wout + (L.Wout & 1 ? 1 : 0);
+    L.Hout_p = L.Hout + (L.Hout & 1); L.Wout_p = L.Wout + (L.Wout & 1);      // even pitches: the stride-2 consumer views rows and columns in pairs (a 1-row map too)
     if (i == 6 && !c.batch_norm) { L.Hout_p = L.Hout; L.Wout_p = L.Wout; }      // cnv7 is never stored ...
     L.out_stride = cout_total[i];
     L.epi = (i == 6 && !c.batch_norm) ? EPI_SUM_RELU : EPI_STORE_RELU;   // ... except under -batch_norm, whose statistics need the whole map

@@ -9,7 +9,7 @@ source, masking, activation, normalisations, PoseNN-internal SE, -batch_norm, -s
 on the same seeded 64x208 inputs.  Both must either raise the same exception type or agree on the poses to 1e-9
 relative.  The hand-picked committed cases of make_golden.py were picked by hand; this looks where nobody picked.
 
-    python tests/golden/fuzz_versions.py [n=200] [seed=0]
+    python tests/golden/fuzz_versions.py [n=200] [seed=0] [--sizes]
 
 Needs the reference checkout (here only).  Divergences are printed and the exit status is their count; a clean run of
 the seeds recorded in DESIGN.md section 2 is part of the pinning evidence.
@@ -66,8 +66,9 @@ def ours(ver, img, flow, seg, depth):
     return O.davo_forward(ver, img, flow, seg, w, torch.float64, depth=depth), w
 
 
-def run(n, seed, verbose=True):
-    """-> (list of (version, what differs), summary line)"""
+def run(n, seed, verbose=True, sizes=False):
+    """-> (list of (version, what differs), summary line).  sizes: a random frame size (multiples of 8, H <= W) and
+    batch per string instead of 64x208 x 2."""
     from davo_b200 import synthetic as S
     rng = np.random.default_rng(seed)
     H, W, B = 64, 208, 2
@@ -81,6 +82,12 @@ def run(n, seed, verbose=True):
             if ver in seen:
                 continue
             seen.add(ver)
+            if sizes:
+                H = int(rng.integers(4, 26)) * 8
+                W = max(H, int(rng.integers(8, 60)) * 8)
+                B = int(rng.integers(1, 4))
+                img, flow, seg = S.make_inputs(B, H, W, seed=int(rng.integers(1 << 30)), bad_label_frac=0.01)
+                depth = S.make_depth(B, H, W)
             try:
                 mine, w = ours(ver, img, flow, seg, depth)
                 mine_exc = None
@@ -98,14 +105,14 @@ def run(n, seed, verbose=True):
                 same = mine_exc == ref_exc
                 raised[ref_exc] = raised.get(ref_exc, 0) + 1
                 if not same:
-                    bad.append((ver, "ours raises %s, the reference %s" % (mine_exc, ref_exc)))
+                    bad.append((ver, "%dx%d x%d: ours raises %s, the reference %s" % (H, W, B, mine_exc, ref_exc)))
                     if verbose:
                         print("DIVERGENCE", bad[-1], flush=True)
                 continue
             built += 1
             err = np.abs(mine - ref).max() / max(np.abs(ref).max(), 1e-30)
             if not (mine.shape == ref.shape and err < 1e-9):
-                bad.append((ver, "poses differ: max rel %.3e" % err))
+                bad.append((ver, "%dx%d x%d: poses differ: max rel %.3e" % (H, W, B, err)))
                 if verbose:
                     print("DIVERGENCE", bad[-1], flush=True)
     summary = ("seed %d: %d version strings in %.0f s: %d built and agree, both raise %s, %d divergences"
@@ -115,6 +122,9 @@ def run(n, seed, verbose=True):
 
 
 if __name__ == "__main__":
-    bad_, summary_ = run(int(sys.argv[1]) if len(sys.argv) > 1 else 200, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    sizes_ = "--sizes" in sys.argv
+    if sizes_:
+        sys.argv.remove("--sizes")
+    bad_, summary_ = run(int(sys.argv[1]) if len(sys.argv) > 1 else 200, int(sys.argv[2]) if len(sys.argv) > 2 else 0, sizes=sizes_)
     print(summary_)
     sys.exit(min(len(bad_), 100))

@@ -126,6 +126,61 @@ def fuzz_gpu(n, seed, batch=2, log=None, strings=None):
     return worst, failures
 
 
+def fuzz_gpu_sizes(n, seed, log=None):
+    """Random (version string, frame size, batch, pass size, pair selection): device entry point against the fp64 oracle,
+    host entry point and pair selections against the device entry point bit for bit.  Sizes are multiples of 8 (the
+    library's rule); the pyramid-pooled sources want H <= W, which every draw respects.  -> (worst / bar, failures)"""
+    from davo_b200 import _capi
+    rng = np.random.default_rng(seed)
+    worst, failures = 0.0, 0
+    vers = _fuzz_strings(n, seed + 1000)
+    for ver in vers:
+        h = int(rng.integers(4, 30)) * 8                                  # 32 .. 232
+        w_ = max(h, int(rng.integers(8, 90)) * 8)                         # 64 .. 712
+        b = int(rng.integers(1, 5))
+        mbs = 0 if "-batch_norm" in ver else int(rng.choice([0, 1, 2, 3, 5]))     # batch statistics: the whole batch is one pass
+        inputs = S.make_inputs(b, h, w_, seed=int(rng.integers(1 << 30)), bad_label_frac=0.01)
+        depth = S.make_depth(b, h, w_)
+        w = S.init_weights(ver, seed=seed, random_bias=True)
+        tag = "%-100s %3dx%-3d B%d mb%d" % (ver, h, w_, b, mbs)
+        try:
+            sysm = DAVO(version=ver)
+            dev = tuple(torch.as_tensor(x).cuda() for x in inputs + (depth,))
+            sysm.setup_inference(h, w_, "davo", 3, b, dev[0], input_flow=dev[1], input_seglabel=dev[2], input_depth=dev[3],
+                                 device=0, micro_batch=mbs)
+            sysm.load_weights(w)
+            out = sysm.inference(None, "pose")["pose"]
+        except Exception as e:  # noqa: BLE001
+            failures += 1
+            if log is None:
+                raise
+            log("%s REFUSED/RAISED %s: %s" % (tag, type(e).__name__, str(e)[:160]))
+            continue
+        ref = O.davo_forward(ver, *inputs, w, torch.float64, depth=depth)
+        err, mag = float(np.abs(out - ref).max()), float(np.abs(ref).max())
+        # (-batch_norm on a random small frame normalises by the statistics of a handful of values -- a 1x1 map times the
+        # batch -- which amplifies the TF32 operand rounding: the north-star bound alone there)
+        ok = (out.shape == ref.shape and bool(np.all(np.isfinite(out))) and bool(np.all(np.abs(out - ref) <= ATOL + RTOL * np.abs(ref)))
+              and (err <= TIGHT_ATOL + 4.9e-4 * mag or sysm.config.batch_norm))
+        why = "" if ok else " pose"
+        if ok and not sysm.config.batch_norm:
+            host = sysm.inference(None, "pose", inputs=inputs + (depth,))["pose"]
+            traj = sysm.inference(None, "pose", pairs="trajectory")["pose"]
+            first = sysm.inference(None, "pose", pairs="trajectory_first")["pose"]
+            if not np.array_equal(out, host):
+                ok, why = False, " host!=device"
+            elif not (np.array_equal(traj[:, 1], out[:, 1]) and np.array_equal(first[:, 1], out[:, 1]) and np.array_equal(first[0, 0], out[0, 0])):
+                ok, why = False, " pair selection"
+        if log is not None:
+            log("%s err %.3e max|ref| %.3e%s" % (tag, err, mag, "" if ok else "   <-- FAILS" + why))
+        else:
+            assert ok, (tag, err, mag, why)
+        worst = max(worst, err / (TIGHT_ATOL + 4.9e-4 * mag))
+        failures += 0 if ok else 1
+        del sysm
+    return worst, failures
+
+
 def test_random_version_strings_match_the_oracle():
     """Combinations nobody picked by hand (net type x cnv6 width x attention source x masking x PoseNN-internal SE x
     -batch_norm ...): 32 random buildable strings.  tools/fuzz_gpu.py runs more (profiles/r2_fuzz_gpu.log)."""
@@ -135,6 +190,15 @@ def test_random_version_strings_match_the_oracle():
     # operand rounding of error, inside the north-star bound
     fuzz_gpu(0, seed=21, strings=["v1-couplePoseNN-segmask_all-static-se_spp21_mixSegFlow-abs_flow",
                                   "v1-cnv6_128-segmask_all-se_depth_wo_tgt-se_replace-fc_tanh-norm_flow-abs_flow"])
+
+
+def test_random_frame_sizes_batches_and_pair_selections():
+    """24 random (version string, frame size 32..232 x 64..712, batch 1..4, pass size, pair selection) draws: device entry
+    point against the fp64 oracle; host entry point and the trajectory pair selections bit-equal to it.  Found by the
+    longer run (profiles/r2_fuzz_gpu_sizes.log): the stride-2 nets refused frames under 64 rows (a 1-row map had an odd
+    pitch)."""
+    _need_gpu()
+    fuzz_gpu_sizes(24, seed=41)
 
 
 def test_every_layer_matches_oracle_per_pixel(monkeypatch):
