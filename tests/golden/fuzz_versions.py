@@ -9,7 +9,7 @@ source, masking, activation, normalisations, PoseNN-internal SE, -batch_norm, -s
 on the same seeded 64x208 inputs.  Both must either raise the same exception type or agree on the poses to 1e-9
 relative.  The hand-picked committed cases of make_golden.py were picked by hand; this looks where nobody picked.
 
-    python tests/golden/fuzz_versions.py [n=200] [seed=0] [--sizes]
+    python tests/golden/fuzz_versions.py [n=200] [seed=0] [--sizes] [--feature]
 
 Needs the reference checkout (here only).  Divergences are printed and the exit status is their count; a clean run of
 the seeds recorded in DESIGN.md section 2 is part of the pinning evidence.
@@ -66,9 +66,10 @@ def ours(ver, img, flow, seg, depth):
     return O.davo_forward(ver, img, flow, seg, w, torch.float64, depth=depth), w
 
 
-def run(n, seed, verbose=True, sizes=False):
+def run(n, seed, verbose=True, sizes=False, feature=False):
     """-> (list of (version, what differs), summary line).  sizes: a random frame size (multiples of 8, H <= W) and
-    batch per string instead of 64x208 x 2."""
+    batch per string instead of 64x208 x 2.  feature: inference(mode='feature') -- attention maps, masked frames, the
+    upsampled cnv6 -- instead of the poses alone."""
     from davo_b200 import synthetic as S
     rng = np.random.default_rng(seed)
     H, W, B = 64, 208, 2
@@ -94,8 +95,19 @@ def run(n, seed, verbose=True, sizes=False):
             except Exception as e:  # noqa: BLE001
                 mine, w, mine_exc = None, {}, type(e).__name__
             try:
-                out, _ = G.run_reference(ver, img, flow, seg, depth, w, "float64", "pose")
+                out, _ = G.run_reference(ver, img, flow, seg, depth, w, "float64", "feature" if feature else "pose")
                 ref, ref_exc = np.asarray(out["pose"], np.float64), None
+                if feature and mine_exc is None:
+                    import torch
+                    from oracle import davo_oracle as O
+                    want, got = G.feature_digest(out), G.feature_digest(O.davo_features(ver, img, flow, seg, w, torch.float64, depth=depth))
+                    for name in want:
+                        a, b = np.asarray(got[name], np.float64), np.asarray(want[name], np.float64)
+                        if a.shape != b.shape or not np.allclose(a, b, rtol=1e-9, atol=1e-12):
+                            bad.append((ver, "%dx%d x%d: feature %s differs" % (H, W, B, name)))
+                            if verbose:
+                                print("DIVERGENCE", bad[-1], flush=True)
+                            break
             except AssertionError as e:
                 # the reference BUILT its graph; with no weight set to feed (ours raised) only the variable check fails
                 ref, ref_exc = None, ("builds" if "variable surface mismatch" in str(e) else "AssertionError")
@@ -122,9 +134,9 @@ def run(n, seed, verbose=True, sizes=False):
 
 
 if __name__ == "__main__":
-    sizes_ = "--sizes" in sys.argv
-    if sizes_:
-        sys.argv.remove("--sizes")
-    bad_, summary_ = run(int(sys.argv[1]) if len(sys.argv) > 1 else 200, int(sys.argv[2]) if len(sys.argv) > 2 else 0, sizes=sizes_)
+    sizes_, feature_ = "--sizes" in sys.argv, "--feature" in sys.argv
+    sys.argv = [a for a in sys.argv if a not in ("--sizes", "--feature")]
+    bad_, summary_ = run(int(sys.argv[1]) if len(sys.argv) > 1 else 200, int(sys.argv[2]) if len(sys.argv) > 2 else 0, sizes=sizes_,
+                         feature=feature_)
     print(summary_)
     sys.exit(min(len(bad_), 100))

@@ -799,16 +799,24 @@ def test_feature_mode_matches_oracle(key):
     w = S.init_weights(ver, seed=g["weight_seed"], random_bias=True)
     inputs = S.make_inputs(g["batch"], H, W, seed=g["input_seed"], bad_label_frac=g["bad_label_frac"])
     depth = S.make_depth(g["batch"], H, W)
-    sysm, dev = _system(ver, g["batch"], w, inputs + (depth,))
+    _check_feature_mode(ver, w, inputs, depth, gold_pose=GOLD[key + "/pose"])
+
+
+def _check_feature_mode(ver, w, inputs, depth, gold_pose=None):
+    B = inputs[0].shape[0]
+    sysm, dev = _system(ver, B, w, inputs + (depth,))
     got = sysm.inference(None, "feature")
     want = O.davo_features(ver, *inputs, w, torch.float64, depth=depth)
     assert sorted(got) == sorted(want)
-    _assert_pose(got["pose"], want["pose"])
-    _assert_pose(got["pose"], GOLD[key + "/pose"])
+    mag = float(np.abs(want["pose"]).max())
+    assert np.all(np.abs(got["pose"] - want["pose"]) <= ATOL + RTOL * np.abs(want["pose"]))
+    assert np.abs(got["pose"] - want["pose"]).max() <= TIGHT_ATOL + 4.9e-4 * mag or sysm.config.batch_norm
+    if gold_pose is not None:
+        _assert_pose(got["pose"], gold_pose)
     for f in range(3):
-        assert got["images"][f].shape == (g["batch"], H, W, 3)
+        assert got["images"][f].shape == (B, H, W, 3)
         assert np.abs(got["images"][f] - want["images"][f]).max() < 1e-6
-        assert got["masks"]["attention"][f].shape == (g["batch"], H, W, 1)
+        assert got["masks"]["attention"][f].shape == (B, H, W, 1)
         scale = max(1.0, float(np.abs(want["masks"]["attention"][f]).max()))     # per-pixel sources are not bounded by 1
         tol = 5e-6 * scale                             # float32 flow: no binary16 rounding in the maps with flow terms
         assert np.abs(got["masks"]["attention"][f] - want["masks"]["attention"][f]).max() < tol, f
@@ -818,10 +826,10 @@ def test_feature_mode_matches_oracle(key):
     for k in range(2):
         d = np.abs(got["flows"][k].astype(int) - want["flows"][k].astype(int))
         assert got["flows"][k].dtype == np.uint8 and (d != 0).mean() < 1e-3 and np.percentile(d, 99.99) <= 1, (d != 0).mean()
-    c6 = 256 if "se_replace" in key else sysm.config.cnv6_out     # -se_replace: cnv6 is the excited cnv5
+    c6 = 256 if sysm.config.posenn_se == 3 else sysm.config.cnv6_out     # -se_replace: cnv6 is the excited cnv5
     for name in ("rot", "trans"):
-        assert got["features"][name].shape == (g["batch"], H, W, c6)
-        assert _rel(got["features"][name], want["features"][name]) < 1.5e-3, name
+        assert got["features"][name].shape == (B, H, W, c6)
+        assert _rel(got["features"][name], want["features"][name]) < (1e-2 if sysm.config.batch_norm else 1.5e-3), name
     # same call with host arrays and with torch outputs
     host = sysm.inference(None, "feature", inputs=inputs + (depth,))
     assert np.array_equal(host["masks"]["attention"][1], got["masks"]["attention"][1])
@@ -830,6 +838,31 @@ def test_feature_mode_matches_oracle(key):
     assert t["features"]["trans"].is_cuda and np.array_equal(t["features"]["trans"].cpu().numpy(), got["features"]["trans"])
     # the pose mode afterwards is untouched by the extra kernels
     assert np.array_equal(sysm.inference(None, "pose")["pose"], got["pose"])
+
+
+def fuzz_gpu_features(n, seed, log=None):
+    """mode='feature' of n random buildable version strings against the oracle -> failures"""
+    inputs = S.make_inputs(2, H, W, seed=2000 + seed, bad_label_frac=0.01)
+    depth = S.make_depth(2, H, W)
+    failures = 0
+    for ver in _fuzz_strings(n, seed):
+        w = S.init_weights(ver, seed=seed, random_bias=True)
+        try:
+            _check_feature_mode(ver, w, inputs, depth)
+            msg = "ok"
+        except Exception as e:  # noqa: BLE001
+            if log is None:
+                raise
+            failures += 1
+            msg = "FAILS %s: %s" % (type(e).__name__, str(e)[:200].replace("\n", " "))
+        if log is not None:
+            log("%-110s %s" % (ver, msg))
+    return failures
+
+
+def test_feature_mode_of_random_version_strings():
+    _need_gpu()
+    fuzz_gpu_features(10, seed=51)
 
 
 def test_feature_mode_limits():
