@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) feature_frames_kernel(const FeatureParams
     int lab[4] = {-1, -1, -1, -1};
     if (seg_p) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(seg_p + p0));
-      lab[0] = (int)v.x; lab[1] = (int)v.y; lab[2] = (int)v.z; lab[3] = (int)v.w;   // tf.cast truncates
+      lab[0] = label_of(v.x); lab[1] = label_of(v.y); lab[2] = label_of(v.z); lab[3] = label_of(v.w);   // tf.cast truncates
     }
     float a[4];
 #pragma unroll

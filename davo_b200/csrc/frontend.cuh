@@ -93,9 +93,12 @@ struct FrontParams {
 
 // Label of pixel `pix` of plane `plane` (element offset of the plane = plane index * H*W) as the
 // reference's tf.cast(seg, int32) (davo.py:1115: truncation toward zero); bytes are already ints.
+// (a NaN has no class: on the CPU tf.cast gives INT_MIN for it, which one_hot turns into a zero row; CUDA's conversion
+// would give 0, i.e. class "road")
+__device__ __forceinline__ int label_of(float v) { return v == v ? (int)v : -1; }
 __device__ __forceinline__ int label_at(const FrontParams& p, size_t plane_off, int pix) {
   if (p.seg8) return p.seg8[plane_off + pix];
-  return (int)__ldg(p.seg + plane_off + pix);
+  return label_of(__ldg(p.seg + plane_off + pix));
 }
 // four consecutive labels (pix % 4 == 0)
 __device__ __forceinline__ void labels4_at(const FrontParams& p, size_t plane_off, int pix, int (&lab)[4]) {
@@ -104,7 +107,7 @@ __device__ __forceinline__ void labels4_at(const FrontParams& p, size_t plane_of
     lab[0] = w & 255u; lab[1] = (w >> 8) & 255u; lab[2] = (w >> 16) & 255u; lab[3] = w >> 24;
   } else {
     const float4 v = __ldg(reinterpret_cast<const float4*>(p.seg + plane_off + pix));
-    lab[0] = (int)v.x; lab[1] = (int)v.y; lab[2] = (int)v.z; lab[3] = (int)v.w;
+    lab[0] = label_of(v.x); lab[1] = label_of(v.y); lab[2] = label_of(v.z); lab[3] = label_of(v.w);
   }
 }
 

@@ -86,12 +86,12 @@ bool flows_to_half_portable(const float* src, uint16_t* dst, size_t n) { return 
 static void labels_scalar(const float* src, uint8_t* dst, size_t n) {
   for (size_t i = 0; i < n; ++i) {
     const float v = src[i];
-    dst[i] = (v > -1.0f && v < 19.0f) ? (uint8_t)(int)v : (v != v ? (uint8_t)0 : (uint8_t)255);
+    dst[i] = (v > -1.0f && v < 19.0f) ? (uint8_t)(int)v : (uint8_t)255;      // NaN fails both comparisons: no class
   }
 }
 
 #ifdef DAVO_X86
-// 16 labels per step: in range -> the truncated integer, NaN -> 0, everything else -> 255
+// 16 labels per step: in range -> the truncated integer, everything else (NaN included) -> 255
 static void labels_sse2(const float* src, uint8_t* dst, size_t n) {
   const __m128 lo = _mm_set1_ps(-1.0f), hi = _mm_set1_ps(19.0f);
   const __m128i inval = _mm_set1_epi32(255);
@@ -100,10 +100,9 @@ static void labels_sse2(const float* src, uint8_t* dst, size_t n) {
     __m128i r[4];
     for (int k = 0; k < 4; ++k) {
       const __m128 v = _mm_loadu_ps(src + i + 4 * k);
-      const __m128i ok = _mm_castps_si128(_mm_and_ps(_mm_cmpgt_ps(v, lo), _mm_cmplt_ps(v, hi)));
-      const __m128i nan = _mm_castps_si128(_mm_cmpunord_ps(v, v));
+      const __m128i ok = _mm_castps_si128(_mm_and_ps(_mm_cmpgt_ps(v, lo), _mm_cmplt_ps(v, hi)));   // false for NaN
       const __m128i iv = _mm_cvttps_epi32(v);
-      r[k] = _mm_or_si128(_mm_and_si128(ok, iv), _mm_andnot_si128(ok, _mm_andnot_si128(nan, inval)));
+      r[k] = _mm_or_si128(_mm_and_si128(ok, iv), _mm_andnot_si128(ok, inval));
     }
     _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i),
                      _mm_packus_epi16(_mm_packs_epi32(r[0], r[1]), _mm_packs_epi32(r[2], r[3])));
@@ -121,10 +120,9 @@ __attribute__((target("avx2"))) static void labels_avx2(const float* src, uint8_
     __m256i r[4];
     for (int k = 0; k < 4; ++k) {
       const __m256 v = _mm256_loadu_ps(src + i + 8 * k);
-      const __m256i ok = _mm256_castps_si256(_mm256_and_ps(_mm256_cmp_ps(v, lo, _CMP_GT_OQ), _mm256_cmp_ps(v, hi, _CMP_LT_OQ)));
-      const __m256i nan = _mm256_castps_si256(_mm256_cmp_ps(v, v, _CMP_UNORD_Q));
+      const __m256i ok = _mm256_castps_si256(_mm256_and_ps(_mm256_cmp_ps(v, lo, _CMP_GT_OQ), _mm256_cmp_ps(v, hi, _CMP_LT_OQ)));   // false for NaN
       const __m256i iv = _mm256_cvttps_epi32(v);
-      r[k] = _mm256_or_si256(_mm256_and_si256(ok, iv), _mm256_andnot_si256(ok, _mm256_andnot_si256(nan, inval)));
+      r[k] = _mm256_or_si256(_mm256_and_si256(ok, iv), _mm256_andnot_si256(ok, inval));
     }
     const __m256i b = _mm256_packus_epi16(_mm256_packs_epi32(r[0], r[1]), _mm256_packs_epi32(r[2], r[3]));
     _mm256_storeu_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_permutevar8x32_epi32(b, order));

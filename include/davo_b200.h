@@ -233,7 +233,7 @@ int davo_debug_set_conv_impl(davo_ctx*, int impl);
  * or 1 when some value has no finite half (|x| >= 65520, NaN): such a chunk is sent as float32. */
 int davo_debug_flows_to_half(const float* src, uint16_t* dst, long long n, int portable);
 /* Test hook, CPU only: the float32 label -> byte conversion of the host entry point (tf.cast(label, int32),
- * reference davo.py:1115, then "outside 0..18 -> 255 = an all-zero one_hot row", NaN -> 0 like the device
+ * reference davo.py:1115, then "outside 0..18 -> 255 = an all-zero one_hot row", NaN included like the device
  * conversion); portable != 0: the scalar path instead of AVX2 / SSE2. */
 int davo_debug_labels_to_bytes(const float* src, uint8_t* dst, long long n, int portable);
 

@@ -126,6 +126,35 @@ def fuzz_gpu(n, seed, batch=2, log=None, strings=None):
     return worst, failures
 
 
+def odd_labels(seg, seed=0):
+    """3 % of the labels replaced by values a label file never holds: fractions, -0.x (truncates to class 0), the edges of
+    the range, huge values, infinities and NaN (tf.cast on the CPU gives INT_MIN: no class)."""
+    rng = np.random.default_rng(seed)
+    seg = seg.copy()
+    odd = np.float32([np.nan, -0.5, -0.999, -1.0, 18.999, 19.0, 7.3, 255.0, 1e9, -1e9, np.inf, -np.inf, 3e38])
+    m = rng.random(seg.shape) < 0.03
+    seg[m] = odd[rng.integers(0, len(odd), size=int(m.sum()))]
+    return seg
+
+
+@pytest.mark.parametrize("key", ["headline", "se_seg", "static", "pix_mix_segflow", "decouple_net"])
+def test_unusual_label_values_follow_tf_cast(key):
+    """Labels are floats in the reference's input: the cast (davo.py:1115) truncates toward zero and everything outside
+    0..18 -- NaN included -- is an all-zero one_hot row.  Device entry point (float labels), host entry point (narrowed to
+    bytes on the CPU) and the class-frequency pooling of -se_seg against the oracle, which tests/test_tf_shim.py holds to
+    the reference's code on the same kind of labels."""
+    _need_gpu()
+    ver = G.CASES[key]
+    w = S.init_weights(ver, random_bias=True)
+    img, flow, seg = S.make_inputs(2, H, W, seed=3)
+    seg = odd_labels(seg)
+    assert np.isnan(seg).any() and (seg == -0.5).any()
+    sysm, _ = _system(ver, 2, w, (img, flow, seg))
+    out = sysm.inference(None, "pose")["pose"]
+    _assert_pose(out, O.davo_forward(ver, img, flow, seg, w, torch.float64))
+    assert np.array_equal(out, sysm.inference(None, "pose", inputs=(img, flow, seg))["pose"])
+
+
 def fuzz_gpu_sizes(n, seed, log=None):
     """Random (version string, frame size, batch, pass size, pair selection): device entry point against the fp64 oracle,
     host entry point and pair selections against the device entry point bit for bit.  Sizes are multiples of 8 (the

@@ -217,6 +217,25 @@ def test_reference_rejects_the_version_strings_the_parser_rejects():
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="reference checkout not on this box")
+@pytest.mark.parametrize("key", ["headline", "se_seg", "pix_mix_segflow"])
+def test_unusual_label_values_through_the_reference_graph(key):
+    """Fractions, negative fractions, range edges, huge values, infinities and NaN as labels: the oracle equals the
+    reference's graph code (tf.cast truncates; one_hot drops what is outside 0..18, NaN -> INT_MIN included)."""
+    from davo_b200 import synthetic as S
+    from oracle import davo_oracle as O
+    from tests.test_gpu_parity import odd_labels
+    ver = G.CASES[key]
+    w = S.init_weights(ver, random_bias=True)
+    img, flow, seg = S.make_inputs(2, 64, 208, seed=3)
+    seg = odd_labels(seg)
+    depth = S.make_depth(2, 64, 208)
+    with G.reference_on_path():
+        ref, _ = G.run_reference(ver, img, flow, seg, depth, w, "float64", "pose")
+    mine = O.davo_forward(ver, img, flow, seg, w, torch.float64, depth=depth)
+    np.testing.assert_allclose(mine, np.asarray(ref["pose"], np.float64), rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not on this box")
 def test_random_version_strings_agree_with_the_reference():
     """tests/golden/fuzz_versions.py, a short run: random strings of the version grammar give the same poses (or the
     same exception type) from the reference's graph code and from version.parse_version + the oracle.  Longer runs

@@ -436,7 +436,13 @@ def gather(params, indices, name=None):
 def gather_nd(params, indices, name=None):
     p, i = _raw(params), _raw(indices).long()
     assert i.shape[-1] == 1, "shim gather_nd: only index depth 1 is used by the reference"
-    return Tensor(p[i[..., 0]])
+    # out-of-range -> 0, as in gather above.  The one caller is label_to_color_image (get_dataset_colormap.py:410): a
+    # colouring that Session.run prunes in mode='pose' and that the CPU kernel would refuse in mode='feature' for a
+    # label outside 0..255; eager execution builds it always and must survive it.
+    i0 = i[..., 0]
+    ok = (i0 >= 0) & (i0 < p.shape[0])
+    out = p[i0.clamp(0, p.shape[0] - 1)]
+    return Tensor(_torch.where(ok.reshape(ok.shape + (1,) * (out.dim() - ok.dim())), out, _torch.zeros_like(out)))
 
 
 def one_hot(indices, depth, dtype=float32, name=None):  # noqa: F811
