@@ -168,15 +168,16 @@ def fuzz_gpu_sizes(n, seed, log=None):
         w_ = max(h, int(rng.integers(8, 90)) * 8)                         # 64 .. 712
         b = int(rng.integers(1, 5))
         mbs = 0 if "-batch_norm" in ver else int(rng.choice([0, 1, 2, 3, 5]))     # batch statistics: the whole batch is one pass
+        f16 = bool(rng.random() < 0.25)                                   # the opt-in binary16 flow definition
         inputs = S.make_inputs(b, h, w_, seed=int(rng.integers(1 << 30)), bad_label_frac=0.01)
         depth = S.make_depth(b, h, w_)
         w = S.init_weights(ver, seed=seed, random_bias=True)
-        tag = "%-100s %3dx%-3d B%d mb%d" % (ver, h, w_, b, mbs)
+        tag = "%-100s %3dx%-3d B%d mb%d%s" % (ver, h, w_, b, mbs, " f16" if f16 else "")
         try:
             sysm = DAVO(version=ver)
             dev = tuple(torch.as_tensor(x).cuda() for x in inputs + (depth,))
             sysm.setup_inference(h, w_, "davo", 3, b, dev[0], input_flow=dev[1], input_seglabel=dev[2], input_depth=dev[3],
-                                 device=0, micro_batch=mbs)
+                                 device=0, micro_batch=mbs, flow_f16=f16)
             sysm.load_weights(w)
             out = sysm.inference(None, "pose")["pose"]
         except Exception as e:  # noqa: BLE001
@@ -185,7 +186,8 @@ def fuzz_gpu_sizes(n, seed, log=None):
                 raise
             log("%s REFUSED/RAISED %s: %s" % (tag, type(e).__name__, str(e)[:160]))
             continue
-        ref = O.davo_forward(ver, *inputs, w, torch.float64, depth=depth)
+        ref_in = inputs if not f16 else (inputs[0], inputs[1].astype(np.float16).astype(np.float32), inputs[2])
+        ref = O.davo_forward(ver, *ref_in, w, torch.float64, depth=depth)
         err, mag = float(np.abs(out - ref).max()), float(np.abs(ref).max())
         # (-batch_norm on a random small frame normalises by the statistics of a handful of values -- a 1x1 map times the
         # batch -- which amplifies the TF32 operand rounding: the north-star bound alone there)
@@ -196,8 +198,16 @@ def fuzz_gpu_sizes(n, seed, log=None):
             host = sysm.inference(None, "pose", inputs=inputs + (depth,))["pose"]
             traj = sysm.inference(None, "pose", pairs="trajectory")["pose"]
             first = sysm.inference(None, "pose", pairs="trajectory_first")["pose"]
+            # the compact forms (the caller's binary16 flow planes and byte labels) against the float host call on the widened values
+            flow16, seg8 = S.compact_inputs(inputs[1], inputs[2])
+            wide = np.zeros_like(inputs[1])
+            wide[:, 0:2] = flow16.astype(np.float32)
+            host_wide = sysm.inference(None, "pose", inputs=(inputs[0], wide, inputs[2], depth))["pose"].copy()
+            host_compact = sysm.inference(None, "pose", inputs=(inputs[0], flow16, seg8, depth))["pose"]
             if not np.array_equal(out, host):
                 ok, why = False, " host!=device"
+            elif not np.array_equal(host_wide, host_compact):
+                ok, why = False, " compact!=widened"
             elif not (np.array_equal(traj[:, 1], out[:, 1]) and np.array_equal(first[:, 1], out[:, 1]) and np.array_equal(first[0, 0], out[0, 0])):
                 ok, why = False, " pair selection"
         if log is not None:
