@@ -48,6 +48,7 @@
 // round-robin.
 #pragma once
 #include "conv_common.cuh"
+#include "frontend.cuh"
 
 namespace davo {
 namespace pm {
@@ -56,6 +57,28 @@ constexpr int kTileM = 128;
 constexpr int kTileH = 16;
 constexpr int kEpiStageBytes = 4 * 2 * 4096;        // 4 epilogue warps x 2 buffers x (32 pixels x 128 B)
 constexpr int kBiasSmemBytes = 2048;                // up to 512 bias floats
+constexpr int kFusedWarps = 8;                      // FUSED: warps 7..14 build the patches from the raw inputs
+constexpr int kFusedThreads = kFusedWarps * 32;
+
+// FUSED (cnv1 on the 8-channel packed input): what the front end would have written to memory is built in shared
+// memory instead.  The patches of a tile come in two halves, one per row parity; for a half the producers
+//   A. copy the raw inputs of its rows -- Hp rows x raw_px pixels: flow (float2), the target's and the source's image
+//      bytes, the labels as bytes -- into a staging area with coalesced loads (a warp reads whole row segments), then
+//   B. build the half's patches one after the other, in the order the MMA warp consumes them: a thread takes a slab
+//      (4 pixels x 8 channels), reads its 4 pixels from the staging area, applies pack8_quad (frontend.cuh: the same
+//      function pack8_kernel stores through, so the operand bits are the same) and writes the 128 B where TMA would
+//      have put them (16-B chunks XOR-swizzled by row & 7), fences them for the async proxy and arrives on the patch's
+//      barrier (one arrival per slab).
+// The staging area is single: step A of the next half waits for step B of this one, and runs while the MMA warp works
+// through the patches waiting in the ring.
+struct FusedGeo {
+  int raw_px;          // pixels per staged row (multiple of 4)
+  int flow_pitch;      // float4 per staged flow row: raw_px / 2 + 1
+  int x_lo;            // first staged pixel relative to the tile's first input column (2 * G * w0)
+  int half_patches;    // patches per row parity; patches [0, half) share one parity and dh, [half, 2 half) the other
+  int off_tgt, off_src, off_lab_s, off_lab_t;      // byte offsets in the staging area (flow first, at 0)
+  int raw_off;         // staging area: bytes from the 1024-aligned start of dynamic shared memory
+};
 
 struct ConvParams {
   int num_tiles;        // pairs * groups * tiles_h * tiles_w
@@ -76,6 +99,8 @@ struct ConvParams {
   float* out;           // EPI_STORE: [pairs][Hout][Wout][out_stride]
   const float* bias;    // [groups * BN]
   float* sum_out;       // EPI_SUM:   [pairs][groups][tiles_h*tiles_w][4][BN]
+  FusedGeo fg;          // FUSED only
+  FrontParams front;    // FUSED only: the inputs and variant switches of the attention front end
   PatchDesc patches[kMaxPatches];
   TapDesc taps[kMaxTaps];
 };
@@ -87,8 +112,8 @@ struct ConvCfg {
   static constexpr int kTmemCols = 2 * kAccStride;                 // power of two for BN in {16..256}
 };
 
-template <int BN, int EPI, bool B_RESIDENT, bool WIDE = false>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN, int EPI, bool B_RESIDENT, bool WIDE = false, bool FUSED = false>
+__global__ void __launch_bounds__(kConvThreads + (FUSED ? kFusedThreads : 0), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BN>;
@@ -98,6 +123,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                              ~uintptr_t(1023));
   const int PS = p.p_stages;
   static_assert(!WIDE || (B_RESIDENT && EPI == EPI_STORE_RELU && BN >= 32), "WIDE: resident weights, store epilogue");
+  static_assert(!FUSED || WIDE, "the fused front end feeds the column-widened cnv1 plan");
   const int BS = B_RESIDENT ? p.n_taps * p.groups : p.b_stages;   // resident: every slab has a home
   const int b_bytes = WIDE ? p.b_boxes * p.b_box_rows * kSlabBytes : BS * Cfg::kBBytes;
   const int TH = WIDE ? p.tile_h : kTileH, TW = WIDE ? p.tile_w : kTileW;
@@ -128,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     if constexpr (EPI == EPI_STORE_RELU) tma_prefetch_desc(&tmO);
     for (int i = 0; i < kMaxStages; ++i) {
-      mbar_init(&p_full[i], 1);
+      mbar_init(&p_full[i], FUSED ? (uint32_t)(p.patch_bytes / kSlabBytes) : 1u);   // FUSED: one arrival per slab
       mbar_init(&p_empty[i], 1);
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
@@ -140,7 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
-  for (int i = threadIdx.x; i < p.groups * BN; i += kConvThreads) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.groups * BN; i += blockDim.x) bias_s[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -149,9 +175,177 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const int tiles_per_pair = tiles_per_img * p.groups;
 
-  if (warp == 0) {
+  if (FUSED && warp >= 7) {
+    // ------------------------------------- patch producers: fused front end --
+    const FrontParams& f = p.front;
+    const FusedGeo& fg = p.fg;
+    const int ptid = (int)threadIdx.x - kConvThreads;
+    uint8_t* raw = smem + fg.raw_off;
+    float* wtab = bias_s + 256;                                   // class weights: [0, 32) source frame, [32, 64) target
+    const int spp = p.patch_bytes / kSlabBytes;                   // slabs per patch: Hp x tile_w
+    const int Hp = spp / p.tile_w;
+    const int NF = fg.raw_px / 2, NT = fg.raw_px * 3 / 4, NL = fg.raw_px / 4;     // float4 / u32 / u32 per staged row
+    const int NFP = fg.flow_pitch;                                // float4 per staged flow row (NF + 1: rows start in different banks)
+    const bool lab_s = f.att_src != 0, lab_t = lab_s && !f.att_tgt_ones, use_flow = f.in_mode == 1;
+    const int hw = f.H * f.W;
+    // This thread's slabs of a half: the same positions in every tile (kFusedItems of them at most; step B below)
+    constexpr int kFusedItems = 4;
+    int it_pos[kFusedItems], it_xr[kFusedItems];                  // within | patch-in-half << 16 (-1: none); staged column per half
+#pragma unroll
+    for (int t = 0; t < kFusedItems; ++t) {
+      const int i = ptid + t * kFusedThreads;
+      it_pos[t] = -1; it_xr[t] = 0;
+      if (i < fg.half_patches * spp) {
+        const int qp = i / spp, within = i - qp * spp, j = within % p.tile_w;
+        it_pos[t] = within | (qp << 16);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const PatchDesc d = p.patches[half * fg.half_patches + qp];
+          it_xr[t] |= (2 * p.run_px * (j + d.dw) + (d.c >> 5) * 4 - fg.x_lo) << (16 * half);
+        }
+      }
+    }
+    int ring_stage0 = 0;                                          // ring stage and use count of the current half's first patch
+    uint32_t ring_use0 = 0;
+    pdl_wait();                     // the class weights come from the SE kernel before this one
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int n = tile / tiles_per_pair;
+      const int r = tile - n * tiles_per_pair;
+      const int h0 = (r / p.tiles_w) * TH, w0 = (r % p.tiles_w) * TW;
+      const int X0 = 2 * p.run_px * w0 + fg.x_lo;                 // first staged input column
+      int b, k;
+      pair_of_slot(f.pair_mode, f.pair0 + n, &b, &k);
+      const uint8_t* img_b = f.img + (size_t)b * f.H * 3 * f.W * 3;
+      const size_t seg_src = ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw, seg_tgt = ((size_t)b * 3 + 1) * hw;
+      const int src_col0 = (k == 0) ? 0 : 2 * f.W;
+      for (int half = 0; half < 2; ++half) {
+        const PatchDesc dfirst = p.patches[half * fg.half_patches];
+        const int y0 = 2 * (h0 + dfirst.dh) + dfirst.par;         // input row of staged row 0; staged row rr is y0 + 2 rr
+        // ---- A: the raw inputs of this half's rows ----
+        if (half == 0 && ptid < 2 * kNumClasses) {
+          const bool se = f.att_src == 1 || f.att_src >= 3;
+          const int fr = ptid / kNumClasses, c = ptid - fr * kNumClasses;
+          wtab[fr * 32 + c] = (se && (fr == 0 || !f.att_tgt_ones)) ? __ldcg(f.att_w + ((size_t)n * kAttFrames + fr) * kAttStride + c)
+                            : f.att_src == 2 ? f.static_w[c] : 1.0f;
+        }
+        // (loads go out in batches before the first one is stored: a thread's loads are independent, and a half is only a
+        // few loads per thread, so the staging costs about three memory round trips)
+        // The flow and the image bytes go global -> shared asynchronously (cp.async: no registers in between, every copy of
+        // the half in flight at once); the labels, which are narrowed to bytes on the way, follow through registers
+        // while those copies are under way.  One memory round trip per half.  A thread keeps its column and walks down
+        // the rows, so the loops hold no division.
+        const uint32_t raw_u = smem_u32(raw);
+        const bool flow_plain = use_flow && !f.flow_f16 && b >= f.n_flow16;       // float32 flow used as it is
+        if (flow_plain) {
+          const int RF = kFusedThreads / NF, r0 = ptid / NF, e = ptid - r0 * NF, x = X0 + 2 * e;      // two pixels of flow
+          if (r0 < RF && x >= 0 && x < f.W) {
+            const float* fsrc = f.flow + (((size_t)b * 4 + k) * hw + x) * 2;
+            for (int rr = r0; rr < Hp; rr += RF) {
+              const int y = y0 + 2 * rr;
+              if (y >= 0 && y < f.H) cp_async_16(raw_u + (rr * NFP + e) * 16, fsrc + (size_t)y * f.W * 2);
+            }
+          }
+        }
+        {
+          const int RI = kFusedThreads / (2 * NT), r0 = ptid / (2 * NT), e = ptid - r0 * 2 * NT;
+          const int fr = e >= NT, wd = e - fr * NT;                        // one 32-bit word of the target's / the source's image bytes
+          const int x = X0 + (wd / 3) * 4;                                 // the quad the word belongs to
+          if (r0 < RI && x >= 0 && x < f.W) {
+            const uint8_t* isrc = img_b + ((size_t)(fr ? src_col0 : f.W) + X0) * 3 + wd * 4;
+            const uint32_t dst0 = raw_u + (fr ? fg.off_src : fg.off_tgt) + wd * 4;
+            for (int rr = r0; rr < Hp; rr += RI) {
+              const int y = y0 + 2 * rr;
+              if (y >= 0 && y < f.H) cp_async_4(dst0 + rr * NT * 4, isrc + (size_t)y * 3 * f.W * 3);
+            }
+          }
+        }
+        if (use_flow && !flow_plain) {                     // binary16 flow (opt-in) / half planes from the host: through flow2_at
+          constexpr int U = 6;
+          for (int i0 = ptid; i0 < Hp * NF; i0 += kFusedThreads * U) {
+            float4 v[U];
+            int dst[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int idx = i0 + u * kFusedThreads, rr = idx / NF, e = idx - rr * NF;
+              const int y = y0 + 2 * rr, x = X0 + 2 * e;
+              dst[u] = (idx < Hp * NF && y >= 0 && y < f.H && x >= 0 && x < f.W) ? rr * NFP + e : -1;
+              if (dst[u] >= 0) v[u] = flow2_at(f, b, k, y * f.W + x, hw);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (dst[u] >= 0) *reinterpret_cast<float4*>(raw + (size_t)dst[u] * 16) = v[u];
+          }
+        }
+        if (lab_s) {                               // four labels: 16 B of floats, or 4 B where the host entry point sent bytes
+          const int per_row = lab_t ? 2 * NL : NL, RL = kFusedThreads / per_row, r0 = ptid / per_row, e = ptid - r0 * per_row;
+          const int fr = e >= NL, qd = e - fr * NL, x = X0 + 4 * qd;
+          if (r0 < RL && x >= 0 && x < f.W) {
+            const size_t plane = (fr ? seg_tgt : seg_src) + x;
+            const uint32_t dst0 = raw_u + (fr ? fg.off_lab_t : fg.off_lab_s) + qd * 16;
+            for (int rr = r0; rr < Hp; rr += RL) {
+              const int y = y0 + 2 * rr;
+              if (y < 0 || y >= f.H) continue;
+              if (f.seg8) cp_async_4(dst0 + rr * NL * 16, f.seg8 + plane + (size_t)y * f.W);
+              else cp_async_16(dst0 + rr * NL * 16, f.seg + plane + (size_t)y * f.W);
+            }
+          }
+        }
+        cp_async_wait_all();
+        asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");       // staged (producers only)
+        // ---- B: the patches of this half, in ring order ----
+#pragma unroll
+        for (int t = 0; t < kFusedItems; ++t) {
+          if (it_pos[t] < 0) continue;
+          const int qp = it_pos[t] >> 16, within = it_pos[t] & 0xFFFF;
+          const int rr = within / p.tile_w;
+          const int xr = (it_xr[t] >> (16 * half)) & 0xFFFF;                        // staged column of the slab's first pixel
+          const int y = y0 + 2 * rr, x = X0 + xr;
+          float4 q[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) q[c] = make_float4(0.f, 0.f, 0.f, 0.f);              // 'SAME' padding
+          if (y >= 0 && y < f.H && x >= 0 && x < f.W) {
+            const int qd = xr >> 2;
+            const uint32_t* tw = reinterpret_cast<const uint32_t*>(raw + fg.off_tgt + ((size_t)rr * NT + 3 * qd) * 4);
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(raw + fg.off_src + ((size_t)rr * NT + 3 * qd) * 4);
+            int ls[4] = {-1, -1, -1, -1}, lt[4] = {-1, -1, -1, -1};
+            auto staged_labels = [&](int off, int (&lab)[4]) {          // as labels4_at reads them from memory
+              const uint8_t* src = raw + off + ((size_t)rr * NL + qd) * 16;
+              if (f.seg8) {
+                const uint32_t w4 = *reinterpret_cast<const uint32_t*>(src);
+                lab[0] = w4 & 255u; lab[1] = (w4 >> 8) & 255u; lab[2] = (w4 >> 16) & 255u; lab[3] = w4 >> 24;
+              } else {
+                const float4 v = *reinterpret_cast<const float4*>(src);
+                lab[0] = label_of(v.x); lab[1] = label_of(v.y); lab[2] = label_of(v.z); lab[3] = label_of(v.w);
+              }
+            };
+            if (lab_s) staged_labels(fg.off_lab_s, ls);
+            if (lab_t) staged_labels(fg.off_lab_t, lt);
+            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+            if (use_flow) {
+              f0 = *reinterpret_cast<const float4*>(raw + ((size_t)rr * NFP + 2 * qd) * 16);
+              f1 = *reinterpret_cast<const float4*>(raw + ((size_t)rr * NFP + 2 * qd + 1) * 16);
+            }
+            pack8_quad(f, wtab, wtab + 32, tw[0], tw[1], tw[2], sw[0], sw[1], sw[2], ls, lt, f0, f1, q);
+          }
+          int stage = ring_stage0 + qp;                                // the patch's place in the ring's life
+          uint32_t use = ring_use0;
+          while (stage >= PS) { stage -= PS; ++use; }
+          mbar_wait(&p_empty[stage], (use & 1u) ^ 1u);
+          const uint32_t row = smem_u32(smem_p + stage * p.patch_stage_bytes) + (uint32_t)within * kSlabBytes;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) sts_v4(row + ((c ^ (within & 7)) << 4), q[c]);
+          fence_proxy_async_smem();
+          mbar_arrive(&p_full[stage]);
+        }
+        ring_stage0 += fg.half_patches;
+        while (ring_stage0 >= PS) { ring_stage0 -= PS; ++ring_use0; }
+        asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");       // everyone has read the staging area
+      }
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------- patch (A) producer --
-    if (lane == 0) {
+    if (lane == 0 && !FUSED) {
       pdl_wait();                 // the activations this layer reads are the previous kernel's output
       int ps = 0;
       uint32_t pphase = 0;

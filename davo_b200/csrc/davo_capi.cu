@@ -174,6 +174,7 @@ struct Layer {
                                // every output element in the same tap order (bit-identical results at any batch size)
   int wide_G = 0;              // pm, column-widened: output pixels per M row (0 = off)
   int wide_tw = 0;             //   runs per tile row (tile = 128/wide_tw rows x wide_tw runs)
+  bool fused_front = false;    // cnv1, widened, 8-channel input: planned with the staging area of the fused front end (conv_pm.cuh: FUSED)
   int pc2w[16];                // input tensor channel -> HWIO input channel of the weights, -1: none (cnv1: packed input)
   int smem_bytes = 0;
   float* d_beta = nullptr;     // -batch_norm: BatchNorm/beta of this layer [out_stride] (bn.cuh)
@@ -196,6 +197,8 @@ struct davo_ctx {
   int mb = 0;                       // frame pairs per micro-batch
   int packed_c = 16;                // channels per pixel of the packed PoseNN input (8 or 16)
   int conv_impl = 0;                // 0 tcgen05 (product), 1 direct fp32 (debug cross-check)
+  bool fuse_front = false;          // cnv1 builds its operand from the raw inputs: pack8_kernel is not launched (conv_pm.cuh: FUSED)
+  FrontParams fp_cur;               // the front-end parameters of the pass being launched (the fused cnv1 takes them)
   bool compensated_rounding = true; // TF32 weight rounding directions chosen so tap sums cancel
   bool pdl = true;                  // programmatic dependent launch of every kernel of a pass
   std::vector<Layer> layers;        // cnv1..cnv7
@@ -847,10 +850,46 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
   const int fixed = 1024 /*alignment*/ + kBarrierBytes + pm::kBiasSmemBytes + pm::kEpiStageBytes;
   const int resident_bytes = L.k * box_rows * kSlabBytes;
   L.b_resident = true;
-  P.p_stages = std::min(kMaxStages, (kSmemBudget - fixed - resident_bytes) / patch_stage);
+  int raw_bytes = 0;
+  if (L.fused_front) {
+    // the staging area of the fused front end (conv_pm.cuh: FusedGeo): Hp rows x raw_px pixels of flow, target and
+    // source bytes and labels.  Needs the patch list in two halves, one per row parity, each with one dh.
+    pm::FusedGeo& g = P.fg;
+    bool ok = S == 4 && np % 2 == 0 && np >= 2;
+    g.half_patches = np / 2;
+    for (int i = 0; ok && i < np; ++i) {
+      const PatchDesc& a = pdesc[(i / g.half_patches) * g.half_patches];
+      ok = pdesc[i].par == a.par && pdesc[i].dh == a.dh;
+    }
+    ok = ok && pdesc[0].par != pdesc[g.half_patches].par;
+    int x_lo = 1 << 20, x_hi = -(1 << 20);
+    for (int i = 0; i < np; ++i)
+      for (int j = 0; j < TWc; ++j) {
+        const int x = 2 * G * (j + pdesc[i].dw) + (pdesc[i].c >> 5) * S;
+        x_lo = std::min(x_lo, x); x_hi = std::max(x_hi, x + S);
+      }
+    g.x_lo = x_lo; g.raw_px = x_hi - x_lo;
+    ok = ok && (g.raw_px % 4) == 0 && (x_lo % 4) == 0 && g.raw_px <= 160 && g.half_patches * Hp * Wp <= 4 * pm::kFusedThreads;     // conv_pm.cuh: kFusedItems slabs per thread
+    const int NF = g.raw_px / 2, NT = g.raw_px * 3 / 4, NL = g.raw_px / 4;
+    g.flow_pitch = NF + 1;
+    g.off_tgt = Hp * g.flow_pitch * 16;
+    g.off_src = g.off_tgt + Hp * NT * 4;
+    g.off_lab_s = g.off_src + Hp * NT * 4;
+    g.off_lab_s = (g.off_lab_s + 15) & ~15;                 // labels are staged as they come: 16 B of floats per quad (4 B of bytes from the host entry point)
+    g.off_lab_t = g.off_lab_s + Hp * NL * 16;
+    raw_bytes = g.off_lab_t + (ctx->cfg.att_tgt_ones ? 0 : Hp * NL * 16);
+    if (!ok || (kSmemBudget - fixed - resident_bytes - raw_bytes) / patch_stage < 3) {
+      L.fused_front = false;                     // the plain widened plan (pack8_kernel feeds it)
+      raw_bytes = 0;
+      memset(&g, 0, sizeof g);
+    }
+  }
+  P.p_stages = std::min(kMaxStages, (kSmemBudget - fixed - resident_bytes - raw_bytes) / patch_stage);
   P.b_stages = 0;
   if (P.p_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: widened plan does not fit shared memory", L.name);
-  L.smem_bytes = fixed + resident_bytes + P.p_stages * patch_stage;
+  L.smem_bytes = fixed + resident_bytes + P.p_stages * patch_stage + raw_bytes;
+  if (L.fused_front)      // behind the ring, the resident weights, the epilogue staging, the barriers and the bias table
+    P.fg.raw_off = P.p_stages * patch_stage + resident_bytes + pm::kEpiStageBytes + kBarrierBytes + pm::kBiasSmemBytes;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   {
@@ -876,8 +915,9 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
   }
   if (int rc = encode_output_map(ctx, L, NW, L.Wout / G, TWc)) return rc;
   if (getenv("DAVO_B200_VERBOSE"))
-    fprintf(stderr, "[davo_b200] %s: pixels-on-M widened x%d (N=%d, %d-pixel slabs), tile %dx%d runs, patch %dx%d (%d B) x%d, %d taps, weights resident %d B, ring P%d, smem %d\n",
-            L.name, G, NW, S, THr, TWc, Hp, Wp, patch_bytes, np, nt, resident_bytes, P.p_stages, L.smem_bytes);
+    fprintf(stderr, "[davo_b200] %s: pixels-on-M widened x%d (N=%d, %d-pixel slabs), tile %dx%d runs, patch %dx%d (%d B) x%d, %d taps, weights resident %d B, ring P%d, smem %d%s\n",
+            L.name, G, NW, S, THr, TWc, Hp, Wp, patch_bytes, np, nt, resident_bytes, P.p_stages, L.smem_bytes,
+            L.fused_front ? (", fused front end: staging " + std::to_string(raw_bytes) + " B, " + std::to_string(P.fg.raw_px) + " pixels per row from " + std::to_string(P.fg.x_lo)).c_str() : "");
   return 0;
 }
 
@@ -895,13 +935,19 @@ int launch_pm_t(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
 }
 
 int launch_pm_wide(davo_ctx* ctx, const Layer& L, int npairs, cudaStream_t st) {
-  auto* kern = pm::conv_tc_kernel<128, EPI_STORE_RELU, true, true>;
-  if (int rc = ensure_smem(ctx, kern, L.smem_bytes)) return rc;
   pm::ConvParams P = L.prm_pm;
   P.raw = ctx->cfg.batch_norm ? 1 : 0;
   P.num_tiles = npairs * L.tiles_h * L.tiles_w;
   P.out = L.d_out;
   const int grid = P.num_tiles < ctx->num_sms ? P.num_tiles : ctx->num_sms;
+  if (L.fused_front && ctx->fuse_front && ctx->conv_impl == 0) {      // cnv1 with the front end inside (no packed input in memory)
+    auto* kern = pm::conv_tc_kernel<128, EPI_STORE_RELU, true, true, true>;
+    if (int rc = ensure_smem(ctx, kern, L.smem_bytes)) return rc;
+    P.front = ctx->fp_cur;
+    return launch_k(ctx, kern, dim3(grid), dim3(kConvThreads + pm::kFusedThreads), L.smem_bytes, st, false, L.tmA, L.tmB, L.tmO, P);
+  }
+  auto* kern = pm::conv_tc_kernel<128, EPI_STORE_RELU, true, true>;
+  if (int rc = ensure_smem(ctx, kern, L.smem_bytes)) return rc;
   return launch_k(ctx, kern, dim3(grid), dim3(kConvThreads), L.smem_bytes, st, false, L.tmA, L.tmB, L.tmO, P);
 }
 
@@ -1066,7 +1112,7 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     // for se_flow with global pooling and the 8-channel layout.  Same bits, but measured slower than the two kernels
     // (0.237 vs 0.186 ms per 256 pairs, 21 vs 10 us for one sample: profiles/r2_experiment_front_pipeline.log).
     static const bool pipe_on = [] { const char* e = getenv("DAVO_B200_FRONT_PIPE"); return e && !strcmp(e, "1"); }();
-    if (pipe_on && c.att_src == 1 && c.se_pool == 0 && !c.depth_split && !c.pixel_map && c.att_tgt_ones && !ctx->unit_sample &&
+    if (pipe_on && !ctx->fuse_front && c.att_src == 1 && c.se_pool == 0 && !c.depth_split && !c.pixel_map && c.att_tgt_ones && !ctx->unit_sample &&
         ctx->packed_c == 8 && ctx->d_pipe) {
       FrontPipe q;
       q.next = ctx->d_pipe; q.done = ctx->d_pipe + 1; q.launches = reinterpret_cast<unsigned int*>(ctx->d_pipe + 2);
@@ -1094,6 +1140,8 @@ int launch_front(davo_ctx* ctx, int pair_mode, int pair0, int npairs, const uint
     }
     ++*launches;
   }
+  ctx->fp_cur = fp;
+  if (ctx->fuse_front && ctx->conv_impl == 0 && ctx->layers[0].fused_front) return 0;     // cnv1 builds its own operand
   if (int rc = ctx->unit_sample ? launch_k(ctx, pack_sample_kernel, dim3(kPackBlocksPerPair, npairs), dim3(256), 0, st, false, fp)
              : ctx->packed_c == 8 ? launch_k(ctx, pack8_kernel, dim3(pack8_blocks(npairs), npairs), dim3(256), 0, st, false, fp)
                                   : launch_k(ctx, pack_kernel, dim3(kPackBlocksPerPair, npairs), dim3(256), 0, st, false, fp))
@@ -1437,6 +1485,9 @@ extern "C" int davo_finalize_weights(davo_ctx* ctx) {
         if (best < 0 || tiles < best) { best = tiles; L.wide_tw = tw; }
       }
       L.wide_G = G;
+      // Experiment (DAVO_B200_FUSED_FRONT=1): cnv1 builds its operand from the raw inputs (conv_pm.cuh: FUSED)
+      if (const char* ef = getenv("DAVO_B200_FUSED_FRONT"))
+        if (!strcmp(ef, "1") && i == 0 && ctx->packed_c == 8 && L.Cin_total == 8) { L.fused_front = true; ctx->fuse_front = true; }
       L.tiles_h = (L.Hout + 128 / L.wide_tw - 1) / (128 / L.wide_tw);
       L.tiles_w = (runs + L.wide_tw - 1) / L.wide_tw;
     }
@@ -2041,7 +2092,14 @@ extern "C" int davo_get_intermediate(davo_ctx* ctx, const char* name, int pair, 
     else if (c.att_src == 2) src = ctx->d_staticw;
     else { for (int i = 0; i < n; ++i) out[i] = 1.0f; *n_out = n; return 0; }
   }
-  else if (s == "packed") { n = (int64_t)c.H * c.W * ctx->packed_c; src = ctx->d_packed + (size_t)pair * n; }
+  else if (s == "packed") {
+    n = (int64_t)c.H * c.W * ctx->packed_c; src = ctx->d_packed + (size_t)pair * n;
+    if (ctx->fuse_front && ctx->conv_impl == 0 && ctx->layers[0].fused_front) {
+      // the fused cnv1 never wrote it: pack8_kernel, the same arithmetic (frontend.cuh: pack8_quad), on the last pass's inputs
+      if (int rc = launch_k(ctx, pack8_kernel, dim3(pack8_blocks(ctx->fp_cur.npairs), ctx->fp_cur.npairs), dim3(256), 0, (cudaStream_t)0, false, ctx->fp_cur)) return rc;
+      CU_OK(cudaDeviceSynchronize());
+    }
+  }
   else if (s == "cnv7_sum") {
     // reduce the deterministic partials on the host
     const int np = ctx->nparts7;

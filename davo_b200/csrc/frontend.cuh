@@ -671,6 +671,43 @@ __device__ __forceinline__ void unpack_rgb4(uint32_t t0, uint32_t t1, uint32_t t
   r[3] = img_norm((t2 >> 8) & 255u); g[3] = img_norm((t2 >> 16) & 255u); b[3] = img_norm(t2 >> 24);
 }
 
+// One 128-B slab of the 8-channel packed layout: 4 consecutive pixels x [tgt r g b, src r g b (x A), src flow x y (x A)],
+// every value TF32-rounded.  t0..t2 / s0..s2: the 12 image bytes of the target / source frame; ls / lt: labels as
+// tf.cast gives them (anything outside 0..18: no class); f0, f1: the flow of pixels (0, 1) and (2, 3).  s_w / s_wt: the
+// class weights of the source / target frame.  Shared by pack8_kernel and the fused front end of cnv1 (conv_pm.cuh), so
+// that both produce the same bits.
+__device__ __forceinline__ void pack8_quad(const FrontParams& p, const float* s_w, const float* s_wt, uint32_t t0, uint32_t t1,
+                                           uint32_t t2, uint32_t s0, uint32_t s1, uint32_t s2, const int (&ls)[4], const int (&lt)[4],
+                                           const float4 f0, const float4 f1, float4 (&q)[8]) {
+  float tr[4], tg[4], tb[4], sr[4], sg[4], sb[4], a_src[4] = {1.f, 1.f, 1.f, 1.f}, a_tgt[4] = {1.f, 1.f, 1.f, 1.f};
+  unpack_rgb4(t0, t1, t2, tr, tg, tb);
+  unpack_rgb4(s0, s1, s2, sr, sg, sb);
+  if (p.att_src != 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      a_src[i] = (ls[i] >= 0 && ls[i] < kNumClasses) ? s_w[ls[i]] : 0.0f;   // one_hot: out of range -> 0
+    if (!p.att_tgt_ones) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        a_tgt[i] = (lt[i] >= 0 && lt[i] < kNumClasses) ? s_wt[lt[i]] : 0.0f;
+    }
+  }
+  float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.in_mode == 1) {
+    fx[0] = f0.x; fy[0] = f0.y; fx[1] = f0.z; fy[1] = f0.w;
+    fx[2] = f1.x; fy[2] = f1.y; fx[3] = f1.z; fy[3] = f1.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float mt = p.mask_rgb ? a_tgt[i] : 1.0f, ms = p.mask_rgb ? a_src[i] : 1.0f;
+    const float mf = p.mask_flow ? a_src[i] : 1.0f;
+    q[2 * i + 0] = make_float4(round_tf32(tr[i] * mt), round_tf32(tg[i] * mt), round_tf32(tb[i] * mt),
+                               round_tf32(sr[i] * ms));
+    q[2 * i + 1] = make_float4(round_tf32(sg[i] * ms), round_tf32(sb[i] * ms), round_tf32(fx[i] * mf),
+                               round_tf32(fy[i] * mf));
+  }
+}
+
 // The body of pack8_kernel for block bx of nbx of unit pl.  Also called by front_pipeline_kernel.
 __device__ __forceinline__ void pack8_body(const FrontParams& p, const int bx, const int nbx, const int pl) {
   __shared__ float s_w[kNumClasses], s_wt[kNumClasses];    // class weights: source frame, target frame
@@ -700,38 +737,14 @@ __device__ __forceinline__ void pack8_body(const FrontParams& p, const int bx, c
       const size_t row = (size_t)h * 3 * p.W;
       const uint32_t* pt = reinterpret_cast<const uint32_t*>(img_b + (row + p.W + w) * 3);
       const uint32_t* ps = reinterpret_cast<const uint32_t*>(img_b + (row + src_col0 + w) * 3);
-      float tr[4], tg[4], tb[4], sr[4], sg[4], sb[4], a_src[4] = {1.f, 1.f, 1.f, 1.f}, a_tgt[4] = {1.f, 1.f, 1.f, 1.f};
-      unpack_rgb4(__ldg(pt), __ldg(pt + 1), __ldg(pt + 2), tr, tg, tb);
-      unpack_rgb4(__ldg(ps), __ldg(ps + 1), __ldg(ps + 2), sr, sg, sb);
+      int lsv[4] = {-1, -1, -1, -1}, ltv[4] = {-1, -1, -1, -1};
       if (p.att_src != 0) {
-        int lsv[4];
         labels4_at(p, seg_src, p0, lsv);                            // tf.cast truncates toward zero
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          a_src[i] = (lsv[i] >= 0 && lsv[i] < kNumClasses) ? s_w[lsv[i]] : 0.0f;   // one_hot: out of range -> 0
-        if (!p.att_tgt_ones) {
-          int ltv[4];
-          labels4_at(p, seg_tgt, p0, ltv);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            a_tgt[i] = (ltv[i] >= 0 && ltv[i] < kNumClasses) ? s_wt[ltv[i]] : 0.0f;
-        }
+        if (!p.att_tgt_ones) labels4_at(p, seg_tgt, p0, ltv);
       }
-      float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.in_mode == 1) {
-        const float4 f0 = flow2_at(p, b, k, p0, hw), f1 = flow2_at(p, b, k, p0 + 2, hw);
-        fx[0] = f0.x; fy[0] = f0.y; fx[1] = f0.z; fy[1] = f0.w;
-        fx[2] = f1.x; fy[2] = f1.y; fx[3] = f1.z; fy[3] = f1.w;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float mt = p.mask_rgb ? a_tgt[i] : 1.0f, ms = p.mask_rgb ? a_src[i] : 1.0f;
-        const float mf = p.mask_flow ? a_src[i] : 1.0f;
-        q[2 * i + 0] = make_float4(round_tf32(tr[i] * mt), round_tf32(tg[i] * mt), round_tf32(tb[i] * mt),
-                                   round_tf32(sr[i] * ms));
-        q[2 * i + 1] = make_float4(round_tf32(sg[i] * ms), round_tf32(sb[i] * ms), round_tf32(fx[i] * mf),
-                                   round_tf32(fy[i] * mf));
-      }
+      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+      if (p.in_mode == 1) { f0 = flow2_at(p, b, k, p0, hw); f1 = flow2_at(p, b, k, p0 + 2, hw); }
+      pack8_quad(p, s_w, s_wt, __ldg(pt), __ldg(pt + 1), __ldg(pt + 2), __ldg(ps), __ldg(ps + 1), __ldg(ps + 2), lsv, ltv, f0, f1, q);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) st[8 * lane + (j ^ (lane & 7))] = q[j];

@@ -155,6 +155,36 @@ def test_unusual_label_values_follow_tf_cast(key):
     assert np.array_equal(out, sysm.inference(None, "pose", inputs=(img, flow, seg))["pose"])
 
 
+@pytest.mark.parametrize("key", ["headline", "se_seg", "v0_lrelu", "static"])
+def test_fused_front_end_gives_the_same_bits(key, monkeypatch):
+    """DAVO_B200_FUSED_FRONT=1 (experiment, off by default; conv_pm.cuh: FUSED): cnv1 builds its operand from the raw
+    inputs in shared memory instead of reading what pack8_kernel wrote -- one launch fewer, no packed input in memory,
+    the same arithmetic (frontend.cuh: pack8_quad) and therefore the same bits, through both entry points."""
+    _need_gpu()
+    ver = G.CASES[key]
+    w = S.init_weights(ver, random_bias=True)
+    got = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("DAVO_B200_FUSED_FRONT", fused)
+        for (b, h, w_) in ((3, 128, 416), (2, 64, 208), (1, 136, 432)):
+            inputs = S.make_inputs(b, h, w_, seed=9, bad_label_frac=0.02)
+            sysm = DAVO(version=ver)
+            dev = tuple(torch.as_tensor(x).cuda() for x in inputs)
+            sysm.setup_inference(h, w_, "davo", 3, b, dev[0], input_flow=dev[1], input_seglabel=dev[2], device=0)
+            sysm.load_weights(w)
+            got[fused, h, "dev"] = sysm.inference(None, "pose")["pose"].copy()
+            got[fused, h, "first"] = sysm.inference(None, "pose", pairs="trajectory_first")["pose"].copy()
+            got[fused, h, "host"] = sysm.inference(None, "pose", inputs=inputs)["pose"].copy()
+            if h == 128:
+                got[fused, h, "launches"] = sysm.last_launch_count()
+                got[fused, h, "cnv1"] = sysm.get_intermediate("cnv1", 1)
+                got[fused, h, "packed"] = sysm.get_intermediate("packed", 1)          # fused: pack8_kernel runs on demand
+            del sysm
+    for k in [k for k in got if k[0] == "0" and k[2] != "launches"]:
+        assert np.array_equal(got[k], got[("1",) + k[1:]]), k
+    assert got["1", 128, "launches"] == got["0", 128, "launches"] - 1
+
+
 def fuzz_gpu_sizes(n, seed, log=None):
     """Random (version string, frame size, batch, pass size, pair selection): device entry point against the fp64 oracle,
     host entry point and pair selections against the device entry point bit for bit.  Sizes are multiples of 8 (the
