@@ -57,8 +57,12 @@ constexpr int kTileM = 128;
 constexpr int kTileH = 16;
 constexpr int kEpiStageBytes = 4 * 2 * 4096;        // 4 epilogue warps x 2 buffers x (32 pixels x 128 B)
 constexpr int kBiasSmemBytes = 2048;                // up to 512 bias floats
-constexpr int kFusedWarps = 8;                      // FUSED: warps 7..14 build the patches from the raw inputs
+#ifndef DAVO_FUSED_WARPS
+#define DAVO_FUSED_WARPS 8
+#endif
+constexpr int kFusedWarps = DAVO_FUSED_WARPS;       // FUSED: warps 7.. build the patches from the raw inputs
 constexpr int kFusedThreads = kFusedWarps * 32;
+constexpr int kFusedItems = kFusedWarps >= 16 ? 2 : kFusedWarps >= 12 ? 3 : 4;      // slabs of a half a producer thread builds at most
 
 // FUSED (cnv1 on the 8-channel packed input): what the front end would have written to memory is built in shared
 // memory instead.  The patches of a tile come in two halves, one per row parity; for a half the producers
@@ -77,7 +81,8 @@ struct FusedGeo {
   int x_lo;            // first staged pixel relative to the tile's first input column (2 * G * w0)
   int half_patches;    // patches per row parity; patches [0, half) share one parity and dh, [half, 2 half) the other
   int off_tgt, off_src, off_lab_s, off_lab_t;      // byte offsets in the staging area (flow first, at 0)
-  int raw_off;         // staging area: bytes from the 1024-aligned start of dynamic shared memory
+  int raw_off;         // first staging area: bytes from the 1024-aligned start of dynamic shared memory
+  int raw_bytes;       // size of one staging area; the second follows the first
 };
 
 struct ConvParams {
@@ -130,7 +135,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem_p = smem;
   uint8_t* smem_b = smem + PS * p.patch_stage_bytes;
   uint8_t* epi_stage = smem_b + b_bytes;                           // 1024-B aligned (TMA store, 128-B swizzle)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageBytes);
+  constexpr int kEpiBytes = FUSED ? kEpiStageBytes / 2 : kEpiStageBytes;      // FUSED: one staging buffer per epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + kEpiBytes);
   uint64_t* p_full = bars;                        // [kMaxStages] TMA -> MMA
   uint64_t* p_empty = bars + kMaxStages;          // [kMaxStages] MMA -> TMA
   uint64_t* b_full = bars + 2 * kMaxStages;       // [kMaxStages] (resident: [0] only)
@@ -180,8 +186,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const FrontParams& f = p.front;
     const FusedGeo& fg = p.fg;
     const int ptid = (int)threadIdx.x - kConvThreads;
-    uint8_t* raw = smem + fg.raw_off;
-    float* wtab = bias_s + 256;                                   // class weights: [0, 32) source frame, [32, 64) target
+    uint8_t* raw0 = smem + fg.raw_off;                            // two staging areas, fg.raw_bytes apart: step c uses area c & 1
+    float* wtab0 = bias_s + 256;                                  // class weights, two sets (by tile parity) of [32 source | 32 target]
     const int spp = p.patch_bytes / kSlabBytes;                   // slabs per patch: Hp x tile_w
     const int Hp = spp / p.tile_w;
     const int NF = fg.raw_px / 2, NT = fg.raw_px * 3 / 4, NL = fg.raw_px / 4;     // float4 / u32 / u32 per staged row
@@ -189,7 +195,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool lab_s = f.att_src != 0, lab_t = lab_s && !f.att_tgt_ones, use_flow = f.in_mode == 1;
     const int hw = f.H * f.W;
     // This thread's slabs of a half: the same positions in every tile (kFusedItems of them at most; step B below)
-    constexpr int kFusedItems = 4;
     int it_pos[kFusedItems], it_xr[kFusedItems];                  // within | patch-in-half << 16 (-1: none); staged column per half
 #pragma unroll
     for (int t = 0; t < kFusedItems; ++t) {
@@ -205,143 +210,196 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    int ring_stage0 = 0;                                          // ring stage and use count of the current half's first patch
-    uint32_t ring_use0 = 0;
-    pdl_wait();                     // the class weights come from the SE kernel before this one
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int n = tile / tiles_per_pair;
-      const int r = tile - n * tiles_per_pair;
-      const int h0 = (r / p.tiles_w) * TH, w0 = (r % p.tiles_w) * TW;
-      const int X0 = 2 * p.run_px * w0 + fg.x_lo;                 // first staged input column
-      int b, k;
-      pair_of_slot(f.pair_mode, f.pair0 + n, &b, &k);
+    // A step is one half of one tile: step c = half (c & 1) of this CTA's tile number (c >> 1).
+    struct Step { int ok, n, b, k, y0, X0; };
+    auto step_of = [&](int c) {
+      Step s;
+      const int tile = (int)blockIdx.x + (c >> 1) * (int)gridDim.x;
+      s.ok = tile < p.num_tiles;
+      s.n = s.b = s.k = s.y0 = s.X0 = 0;
+      if (s.ok) {
+        s.n = tile / tiles_per_pair;
+        const int r = tile - s.n * tiles_per_pair;
+        const PatchDesc d = p.patches[(c & 1) * fg.half_patches];
+        s.y0 = 2 * ((r / p.tiles_w) * TH + d.dh) + d.par;         // input row of staged row 0; staged row rr is y0 + 2 rr
+        s.X0 = 2 * p.run_px * ((r % p.tiles_w) * TW) + fg.x_lo;    // first staged input column
+        pair_of_slot(f.pair_mode, f.pair0 + s.n, &s.b, &s.k);
+      }
+      return s;
+    };
+    // float labels travel through registers (they are narrowed to bytes on the way): loaded by stage_issue, stored by
+    // stage_finish after the patches of the step before have been built
+    constexpr int kLabRegs = 3;
+    float4 lab_v[kLabRegs];
+    uint32_t lab_mask = 0;
+    auto narrow4 = [](const float4 v) {
+      const int l4[4] = {label_of(v.x), label_of(v.y), label_of(v.z), label_of(v.w)};
+      uint32_t w4 = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w4 |= (uint32_t)((l4[i] >= 0 && l4[i] < kNumClasses) ? l4[i] : 255) << (8 * i);
+      return w4;
+    };
+    // ---- A: the raw inputs of a step, on their way into its staging area ----
+    // The flow and the image bytes (and byte labels) go global -> shared asynchronously (cp.async: no registers in between,
+    // every copy of the half in flight at once).  A thread keeps its column and walks down the rows: no division in the loops.
+    auto stage_issue = [&](const Step& s, int c) {
+      uint8_t* raw = raw0 + (c & 1) * fg.raw_bytes;
+      const uint32_t raw_u = smem_u32(raw);
+      const int b = s.b, k = s.k, y0 = s.y0, X0 = s.X0;
       const uint8_t* img_b = f.img + (size_t)b * f.H * 3 * f.W * 3;
       const size_t seg_src = ((size_t)b * 3 + (k == 0 ? 0 : 2)) * hw, seg_tgt = ((size_t)b * 3 + 1) * hw;
       const int src_col0 = (k == 0) ? 0 : 2 * f.W;
-      for (int half = 0; half < 2; ++half) {
-        const PatchDesc dfirst = p.patches[half * fg.half_patches];
-        const int y0 = 2 * (h0 + dfirst.dh) + dfirst.par;         // input row of staged row 0; staged row rr is y0 + 2 rr
-        // ---- A: the raw inputs of this half's rows ----
-        if (half == 0 && ptid < 2 * kNumClasses) {
-          const bool se = f.att_src == 1 || f.att_src >= 3;
-          const int fr = ptid / kNumClasses, c = ptid - fr * kNumClasses;
-          wtab[fr * 32 + c] = (se && (fr == 0 || !f.att_tgt_ones)) ? __ldcg(f.att_w + ((size_t)n * kAttFrames + fr) * kAttStride + c)
-                            : f.att_src == 2 ? f.static_w[c] : 1.0f;
-        }
-        // (loads go out in batches before the first one is stored: a thread's loads are independent, and a half is only a
-        // few loads per thread, so the staging costs about three memory round trips)
-        // The flow and the image bytes go global -> shared asynchronously (cp.async: no registers in between, every copy of
-        // the half in flight at once); the labels, which are narrowed to bytes on the way, follow through registers
-        // while those copies are under way.  One memory round trip per half.  A thread keeps its column and walks down
-        // the rows, so the loops hold no division.
-        const uint32_t raw_u = smem_u32(raw);
-        const bool flow_plain = use_flow && !f.flow_f16 && b >= f.n_flow16;       // float32 flow used as it is
-        if (flow_plain) {
-          const int RF = kFusedThreads / NF, r0 = ptid / NF, e = ptid - r0 * NF, x = X0 + 2 * e;      // two pixels of flow
-          if (r0 < RF && x >= 0 && x < f.W) {
-            const float* fsrc = f.flow + (((size_t)b * 4 + k) * hw + x) * 2;
-            for (int rr = r0; rr < Hp; rr += RF) {
-              const int y = y0 + 2 * rr;
-              if (y >= 0 && y < f.H) cp_async_16(raw_u + (rr * NFP + e) * 16, fsrc + (size_t)y * f.W * 2);
-            }
+      if ((c & 1) == 0 && ptid < 2 * kNumClasses) {               // the tile's class weights
+        const bool se = f.att_src == 1 || f.att_src >= 3;
+        const int fr = ptid / kNumClasses, cl = ptid - fr * kNumClasses;
+        wtab0[((c >> 1) & 1) * 64 + fr * 32 + cl] =
+            (se && (fr == 0 || !f.att_tgt_ones)) ? __ldcg(f.att_w + ((size_t)s.n * kAttFrames + fr) * kAttStride + cl)
+            : f.att_src == 2 ? f.static_w[cl] : 1.0f;
+      }
+      const bool flow_plain = use_flow && !f.flow_f16 && b >= f.n_flow16;       // float32 flow used as it is
+      if (flow_plain) {
+        const int RF = kFusedThreads / NF, r0 = ptid / NF, e = ptid - r0 * NF, x = X0 + 2 * e;      // two pixels of flow
+        if (r0 < RF && x >= 0 && x < f.W) {
+          const float* fsrc = f.flow + (((size_t)b * 4 + k) * hw + x) * 2;
+          for (int rr = r0; rr < Hp; rr += RF) {
+            const int y = y0 + 2 * rr;
+            if (y >= 0 && y < f.H) cp_async_16(raw_u + (rr * NFP + e) * 16, fsrc + (size_t)y * f.W * 2);
           }
         }
-        {
-          const int RI = kFusedThreads / (2 * NT), r0 = ptid / (2 * NT), e = ptid - r0 * 2 * NT;
-          const int fr = e >= NT, wd = e - fr * NT;                        // one 32-bit word of the target's / the source's image bytes
-          const int x = X0 + (wd / 3) * 4;                                 // the quad the word belongs to
-          if (r0 < RI && x >= 0 && x < f.W) {
-            const uint8_t* isrc = img_b + ((size_t)(fr ? src_col0 : f.W) + X0) * 3 + wd * 4;
-            const uint32_t dst0 = raw_u + (fr ? fg.off_src : fg.off_tgt) + wd * 4;
-            for (int rr = r0; rr < Hp; rr += RI) {
-              const int y = y0 + 2 * rr;
-              if (y >= 0 && y < f.H) cp_async_4(dst0 + rr * NT * 4, isrc + (size_t)y * 3 * f.W * 3);
-            }
+      }
+      {
+        const int RI = kFusedThreads / (2 * NT), r0 = ptid / (2 * NT), e = ptid - r0 * 2 * NT;
+        const int fr = e >= NT, wd = e - fr * NT;                        // one 32-bit word of the target's / the source's image bytes
+        const int x = X0 + (wd / 3) * 4;                                 // the quad the word belongs to
+        if (r0 < RI && x >= 0 && x < f.W) {
+          // (16-byte copies of the aligned middle of a row were tried: slower than word copies, 0.371 against 0.348 ms)
+          const uint8_t* isrc = img_b + ((size_t)(fr ? src_col0 : f.W) + X0) * 3 + wd * 4;
+          const uint32_t dst0 = raw_u + (fr ? fg.off_src : fg.off_tgt) + wd * 4;
+          for (int rr = r0; rr < Hp; rr += RI) {
+            const int y = y0 + 2 * rr;
+            if (y >= 0 && y < f.H) cp_async_4(dst0 + rr * NT * 4, isrc + (size_t)y * 3 * f.W * 3);
           }
         }
-        if (use_flow && !flow_plain) {                     // binary16 flow (opt-in) / half planes from the host: through flow2_at
-          constexpr int U = 6;
-          for (int i0 = ptid; i0 < Hp * NF; i0 += kFusedThreads * U) {
-            float4 v[U];
-            int dst[U];
+      }
+      if (use_flow && !flow_plain) {                     // binary16 flow (opt-in) / half planes from the host: through flow2_at
+        constexpr int U = 6;
+        for (int i0 = ptid; i0 < Hp * NF; i0 += kFusedThreads * U) {
+          float4 v[U];
+          int dst[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int idx = i0 + u * kFusedThreads, rr = idx / NF, e = idx - rr * NF;
-              const int y = y0 + 2 * rr, x = X0 + 2 * e;
-              dst[u] = (idx < Hp * NF && y >= 0 && y < f.H && x >= 0 && x < f.W) ? rr * NFP + e : -1;
-              if (dst[u] >= 0) v[u] = flow2_at(f, b, k, y * f.W + x, hw);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-              if (dst[u] >= 0) *reinterpret_cast<float4*>(raw + (size_t)dst[u] * 16) = v[u];
+          for (int u = 0; u < U; ++u) {
+            const int idx = i0 + u * kFusedThreads, rr = idx / NF, e = idx - rr * NF;
+            const int y = y0 + 2 * rr, x = X0 + 2 * e;
+            dst[u] = (idx < Hp * NF && y >= 0 && y < f.H && x >= 0 && x < f.W) ? rr * NFP + e : -1;
+            if (dst[u] >= 0) v[u] = flow2_at(f, b, k, y * f.W + x, hw);
           }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (dst[u] >= 0) *reinterpret_cast<float4*>(raw + (size_t)dst[u] * 16) = v[u];
         }
-        if (lab_s) {                               // four labels: 16 B of floats, or 4 B where the host entry point sent bytes
-          const int per_row = lab_t ? 2 * NL : NL, RL = kFusedThreads / per_row, r0 = ptid / per_row, e = ptid - r0 * per_row;
-          const int fr = e >= NL, qd = e - fr * NL, x = X0 + 4 * qd;
-          if (r0 < RL && x >= 0 && x < f.W) {
-            const size_t plane = (fr ? seg_tgt : seg_src) + x;
-            const uint32_t dst0 = raw_u + (fr ? fg.off_lab_t : fg.off_lab_s) + qd * 16;
+      }
+      lab_mask = 0;
+      if (lab_s) {                                                       // four labels -> four bytes (255: no class)
+        const int per_row = lab_t ? 2 * NL : NL, RL = kFusedThreads / per_row, r0 = ptid / per_row, e = ptid - r0 * per_row;
+        const int fr = e >= NL, qd = e - fr * NL, x = X0 + 4 * qd;
+        if (r0 < RL && x >= 0 && x < f.W) {
+          const size_t plane = (fr ? seg_tgt : seg_src) + x;
+          const int dst0 = (fr ? fg.off_lab_t : fg.off_lab_s) + qd * 4;
+          if (f.seg8) {
             for (int rr = r0; rr < Hp; rr += RL) {
               const int y = y0 + 2 * rr;
-              if (y < 0 || y >= f.H) continue;
-              if (f.seg8) cp_async_4(dst0 + rr * NL * 16, f.seg8 + plane + (size_t)y * f.W);
-              else cp_async_16(dst0 + rr * NL * 16, f.seg + plane + (size_t)y * f.W);
+              if (y >= 0 && y < f.H) cp_async_4(raw_u + dst0 + rr * NL * 4, f.seg8 + plane + (size_t)y * f.W);
             }
-          }
-        }
-        cp_async_wait_all();
-        asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");       // staged (producers only)
-        // ---- B: the patches of this half, in ring order ----
+          } else {
 #pragma unroll
-        for (int t = 0; t < kFusedItems; ++t) {
-          if (it_pos[t] < 0) continue;
-          const int qp = it_pos[t] >> 16, within = it_pos[t] & 0xFFFF;
-          const int rr = within / p.tile_w;
-          const int xr = (it_xr[t] >> (16 * half)) & 0xFFFF;                        // staged column of the slab's first pixel
-          const int y = y0 + 2 * rr, x = X0 + xr;
-          float4 q[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) q[c] = make_float4(0.f, 0.f, 0.f, 0.f);              // 'SAME' padding
-          if (y >= 0 && y < f.H && x >= 0 && x < f.W) {
-            const int qd = xr >> 2;
-            const uint32_t* tw = reinterpret_cast<const uint32_t*>(raw + fg.off_tgt + ((size_t)rr * NT + 3 * qd) * 4);
-            const uint32_t* sw = reinterpret_cast<const uint32_t*>(raw + fg.off_src + ((size_t)rr * NT + 3 * qd) * 4);
-            int ls[4] = {-1, -1, -1, -1}, lt[4] = {-1, -1, -1, -1};
-            auto staged_labels = [&](int off, int (&lab)[4]) {          // as labels4_at reads them from memory
-              const uint8_t* src = raw + off + ((size_t)rr * NL + qd) * 16;
-              if (f.seg8) {
-                const uint32_t w4 = *reinterpret_cast<const uint32_t*>(src);
-                lab[0] = w4 & 255u; lab[1] = (w4 >> 8) & 255u; lab[2] = (w4 >> 16) & 255u; lab[3] = w4 >> 24;
-              } else {
-                const float4 v = *reinterpret_cast<const float4*>(src);
-                lab[0] = label_of(v.x); lab[1] = label_of(v.y); lab[2] = label_of(v.z); lab[3] = label_of(v.w);
+            for (int u = 0; u < kLabRegs; ++u) {                         // the loads only: their values are first used in stage_finish
+              const int rr = r0 + u * RL, y = y0 + 2 * rr;
+              if (rr < Hp && y >= 0 && y < f.H) {
+                lab_v[u] = __ldg(reinterpret_cast<const float4*>(f.seg + plane + (size_t)y * f.W));
+                lab_mask |= 1u << u;
               }
-            };
-            if (lab_s) staged_labels(fg.off_lab_s, ls);
-            if (lab_t) staged_labels(fg.off_lab_t, lt);
-            float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-            if (use_flow) {
-              f0 = *reinterpret_cast<const float4*>(raw + ((size_t)rr * NFP + 2 * qd) * 16);
-              f1 = *reinterpret_cast<const float4*>(raw + ((size_t)rr * NFP + 2 * qd + 1) * 16);
             }
-            pack8_quad(f, wtab, wtab + 32, tw[0], tw[1], tw[2], sw[0], sw[1], sw[2], ls, lt, f0, f1, q);
+            for (int rr = r0 + kLabRegs * RL; rr < Hp; rr += RL) {        // more rows than registers (target labels too): on the spot
+              const int y = y0 + 2 * rr;
+              if (y >= 0 && y < f.H)
+                *reinterpret_cast<uint32_t*>(raw + dst0 + rr * NL * 4) = narrow4(__ldg(reinterpret_cast<const float4*>(f.seg + plane + (size_t)y * f.W)));
+            }
           }
-          int stage = ring_stage0 + qp;                                // the patch's place in the ring's life
-          uint32_t use = ring_use0;
-          while (stage >= PS) { stage -= PS; ++use; }
-          mbar_wait(&p_empty[stage], (use & 1u) ^ 1u);
-          const uint32_t row = smem_u32(smem_p + stage * p.patch_stage_bytes) + (uint32_t)within * kSlabBytes;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) sts_v4(row + ((c ^ (within & 7)) << 4), q[c]);
-          fence_proxy_async_smem();
-          mbar_arrive(&p_full[stage]);
         }
-        ring_stage0 += fg.half_patches;
-        while (ring_stage0 >= PS) { ring_stage0 -= PS; ++ring_use0; }
-        asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");       // everyone has read the staging area
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto stage_finish = [&](int c) {                                     // the labels that waited in registers, narrowed to bytes
+      if (lab_mask == 0) return;
+      uint8_t* raw = raw0 + (c & 1) * fg.raw_bytes;
+      const int per_row = lab_t ? 2 * NL : NL, RL = kFusedThreads / per_row, r0 = ptid / per_row, e = ptid - r0 * per_row;
+      const int fr = e >= NL, qd = e - fr * NL;
+#pragma unroll
+      for (int u = 0; u < kLabRegs; ++u)
+        if (lab_mask & (1u << u))
+          *reinterpret_cast<uint32_t*>(raw + (fr ? fg.off_lab_t : fg.off_lab_s) + ((r0 + u * RL) * NL + qd) * 4) = narrow4(lab_v[u]);
+    };
+    int ring_stage0 = 0;                                          // ring stage and use count of the current half's first patch
+    uint32_t ring_use0 = 0;
+    pdl_wait();                     // the class weights come from the SE kernel before this one
+    Step cur = step_of(0);
+    if (cur.ok) { stage_issue(cur, 0); stage_finish(0); }
+    for (int c = 0; cur.ok; ++c) {
+      // The copies of the NEXT step start now, into the other staging area, and fly while this step's patches are built
+      const Step nxt = step_of(c + 1);
+      if (nxt.ok) stage_issue(nxt, c + 1);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");          // all but the newest group: this step's copies have landed
+      asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");       // ... for every producer thread
+      // ---- B: the patches of this half, in ring order ----
+      const uint8_t* raw = raw0 + (c & 1) * fg.raw_bytes;
+      const float* wtab = wtab0 + ((c >> 1) & 1) * 64;
+      const int half = c & 1, y0 = cur.y0, X0 = cur.X0;
+#pragma unroll
+      for (int t = 0; t < kFusedItems; ++t) {
+        if (it_pos[t] < 0) continue;
+        const int qp = it_pos[t] >> 16, within = it_pos[t] & 0xFFFF;
+        const int rr = within / p.tile_w;
+        const int xr = (it_xr[t] >> (16 * half)) & 0xFFFF;                        // staged column of the slab's first pixel
+        const int y = y0 + 2 * rr, x = X0 + xr;
+        float4 q[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) q[cc] = make_float4(0.f, 0.f, 0.f, 0.f);            // 'SAME' padding
+        if (y >= 0 && y < f.H && x >= 0 && x < f.W) {
+          const int qd = xr >> 2;
+          const uint32_t* tw = reinterpret_cast<const uint32_t*>(raw + fg.off_tgt + ((size_t)rr * NT + 3 * qd) * 4);
+          const uint32_t* sw = reinterpret_cast<const uint32_t*>(raw + fg.off_src + ((size_t)rr * NT + 3 * qd) * 4);
+          int ls[4] = {-1, -1, -1, -1}, lt[4] = {-1, -1, -1, -1};
+          if (lab_s) {
+            const uint32_t w4 = *reinterpret_cast<const uint32_t*>(raw + fg.off_lab_s + ((size_t)rr * NL + qd) * 4);
+            ls[0] = w4 & 255u; ls[1] = (w4 >> 8) & 255u; ls[2] = (w4 >> 16) & 255u; ls[3] = w4 >> 24;
+          }
+          if (lab_t) {
+            const uint32_t w4 = *reinterpret_cast<const uint32_t*>(raw + fg.off_lab_t + ((size_t)rr * NL + qd) * 4);
+            lt[0] = w4 & 255u; lt[1] = (w4 >> 8) & 255u; lt[2] = (w4 >> 16) & 255u; lt[3] = w4 >> 24;
+          }
+          float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+          if (use_flow) {
+            f0 = *reinterpret_cast<const float4*>(raw + ((size_t)rr * NFP + 2 * qd) * 16);
+            f1 = *reinterpret_cast<const float4*>(raw + ((size_t)rr * NFP + 2 * qd + 1) * 16);
+          }
+          pack8_quad(f, wtab, wtab + 32, tw[0], tw[1], tw[2], sw[0], sw[1], sw[2], ls, lt, f0, f1, q);
+        }
+        int stage = ring_stage0 + qp;                                // the patch's place in the ring's life
+        uint32_t use = ring_use0;
+        while (stage >= PS) { stage -= PS; ++use; }
+        mbar_wait(&p_empty[stage], (use & 1u) ^ 1u);
+        const uint32_t row = smem_u32(smem_p + stage * p.patch_stage_bytes) + (uint32_t)within * kSlabBytes;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) sts_v4(row + ((cc ^ (within & 7)) << 4), q[cc]);
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[stage]);
+      }
+      ring_stage0 += fg.half_patches;
+      while (ring_stage0 >= PS) { ring_stage0 -= PS; ++ring_use0; }
+      if (nxt.ok) stage_finish(c + 1);
+      asm volatile("bar.sync 1, %0;" ::"n"(kFusedThreads) : "memory");       // this step's staging area has been read by everyone
+      cur = nxt;
     }
   } else if (warp == 0) {
     // ------------------------------------------------- patch (A) producer --
@@ -479,7 +537,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // map's 128-B swizzle) -> one TMA store of the box {32 floats, tile_w, 32/tile_w rows}.
         // TMA clips what lies outside the image.  Two buffers per warp: the store of step i
         // drains while step i+1 is computed.
-        const uint32_t stg0 = smem_u32(epi_stage) + q * 8192;
+        const uint32_t stg0 = smem_u32(epi_stage) + q * (FUSED ? 4096 : 8192);
         const uint32_t bias_a = smem_u32(bias_s) + g * BN * 4;
         const int c_w = (r % p.tiles_w) * TW;
         const int c_h = (r / p.tiles_w) * TH + q * (32 / TW);
@@ -487,8 +545,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           TWAIT(3, { tmem_ld_32x32(t0 + c0, v); tmem_ld_wait(); });
-          const uint32_t stg = stg0 + ((epi_step & 1) << 12);
-          if (lane == 0) tma_store_wait_read<1>();      // the store that last read this buffer is done
+          const uint32_t stg = stg0 + (FUSED ? 0u : ((epi_step & 1) << 12));
+          if (lane == 0) tma_store_wait_read<FUSED ? 0 : 1>();      // the store that last read this buffer is done
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -503,7 +561,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tmO, reinterpret_cast<const void*>(epi_stage + q * 8192 + ((epi_step & 1) << 12)),
+            tma_store_4d(&tmO, reinterpret_cast<const void*>(epi_stage + q * (FUSED ? 4096 : 8192) + (FUSED ? 0 : ((epi_step & 1) << 12))),
                          (WIDE ? 0 : g * BN) + c0, c_w, c_h, n);
             tma_store_commit();
           }

@@ -869,15 +869,15 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
         x_lo = std::min(x_lo, x); x_hi = std::max(x_hi, x + S);
       }
     g.x_lo = x_lo; g.raw_px = x_hi - x_lo;
-    ok = ok && (g.raw_px % 4) == 0 && (x_lo % 4) == 0 && g.raw_px <= 160 && g.half_patches * Hp * Wp <= 4 * pm::kFusedThreads;     // conv_pm.cuh: kFusedItems slabs per thread
+    ok = ok && (g.raw_px % 4) == 0 && (x_lo % 4) == 0 && g.raw_px <= 160 && g.half_patches * Hp * Wp <= pm::kFusedItems * pm::kFusedThreads;
     const int NF = g.raw_px / 2, NT = g.raw_px * 3 / 4, NL = g.raw_px / 4;
     g.flow_pitch = NF + 1;
     g.off_tgt = Hp * g.flow_pitch * 16;
     g.off_src = g.off_tgt + Hp * NT * 4;
     g.off_lab_s = g.off_src + Hp * NT * 4;
-    g.off_lab_s = (g.off_lab_s + 15) & ~15;                 // labels are staged as they come: 16 B of floats per quad (4 B of bytes from the host entry point)
-    g.off_lab_t = g.off_lab_s + Hp * NL * 16;
-    raw_bytes = g.off_lab_t + (ctx->cfg.att_tgt_ones ? 0 : Hp * NL * 16);
+    g.off_lab_t = g.off_lab_s + Hp * NL * 4;                 // labels are staged as bytes
+    g.raw_bytes = (g.off_lab_t + (ctx->cfg.att_tgt_ones ? 0 : Hp * NL * 4) + 15) & ~15;
+    raw_bytes = 2 * g.raw_bytes - pm::kEpiStageBytes / 2;    // two staging areas; the fused kernel's epilogue gives back half of its buffers
     if (!ok || (kSmemBudget - fixed - resident_bytes - raw_bytes) / patch_stage < 3) {
       L.fused_front = false;                     // the plain widened plan (pack8_kernel feeds it)
       raw_bytes = 0;
@@ -889,7 +889,7 @@ int plan_layer_wide(davo_ctx* ctx, Layer& L, GetW getw, const std::vector<float>
   if (P.p_stages < 2) return fail(ctx, DAVO_ERR_ARG, "%s: widened plan does not fit shared memory", L.name);
   L.smem_bytes = fixed + resident_bytes + P.p_stages * patch_stage + raw_bytes;
   if (L.fused_front)      // behind the ring, the resident weights, the epilogue staging, the barriers and the bias table
-    P.fg.raw_off = P.p_stages * patch_stage + resident_bytes + pm::kEpiStageBytes + kBarrierBytes + pm::kBiasSmemBytes;
+    P.fg.raw_off = P.p_stages * patch_stage + resident_bytes + pm::kEpiStageBytes / 2 + kBarrierBytes + pm::kBiasSmemBytes;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(ctx, DAVO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   {

@@ -182,7 +182,9 @@ def test_fused_front_end_gives_the_same_bits(key, monkeypatch):
             del sysm
     for k in [k for k in got if k[0] == "0" and k[2] != "launches"]:
         assert np.array_equal(got[k], got[("1",) + k[1:]]), k
-    assert got["1", 128, "launches"] == got["0", 128, "launches"] - 1
+    # one launch fewer -- except where the planner declines (variants that also stage the target's labels: the two staging
+    # areas no longer fit beside a three-stage ring, and the plain plan runs)
+    assert got["1", 128, "launches"] == got["0", 128, "launches"] - (0 if key == "se_seg" else 1)
 
 
 def fuzz_gpu_sizes(n, seed, log=None):
