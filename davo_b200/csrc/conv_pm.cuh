@@ -67,14 +67,16 @@ constexpr int kFusedItems = kFusedWarps >= 16 ? 2 : kFusedWarps >= 12 ? 3 : 4;  
 // FUSED (cnv1 on the 8-channel packed input): what the front end would have written to memory is built in shared
 // memory instead.  The patches of a tile come in two halves, one per row parity; for a half the producers
 //   A. copy the raw inputs of its rows -- Hp rows x raw_px pixels: flow (float2), the target's and the source's image
-//      bytes, the labels as bytes -- into a staging area with coalesced loads (a warp reads whole row segments), then
+//      bytes, the labels as bytes -- into a staging area with coalesced copies (a warp reads whole row segments), then
 //   B. build the half's patches one after the other, in the order the MMA warp consumes them: a thread takes a slab
 //      (4 pixels x 8 channels), reads its 4 pixels from the staging area, applies pack8_quad (frontend.cuh: the same
 //      function pack8_kernel stores through, so the operand bits are the same) and writes the 128 B where TMA would
 //      have put them (16-B chunks XOR-swizzled by row & 7), fences them for the async proxy and arrives on the patch's
 //      barrier (one arrival per slab).
-// The staging area is single: step A of the next half waits for step B of this one, and runs while the MMA warp works
-// through the patches waiting in the ring.
+// There are two staging areas: the copies of step c + 1 (cp.async, plus the float labels held in registers) are issued
+// before the patches of step c are built and have that whole step to land.  To make room the fused kernel keeps one
+// epilogue buffer per warp instead of two and a ring of three patches.  Experiment, off by default: same bits as
+// pack8_kernel + cnv1, even in time (profiles/r2_experiment_fused_front_v2.log).
 struct FusedGeo {
   int raw_px;          // pixels per staged row (multiple of 4)
   int flow_pitch;      // float4 per staged flow row: raw_px / 2 + 1
