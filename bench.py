@@ -6,7 +6,9 @@
 A step is one pass of the hot path (attention front end -> dilated PoseNN -> 6-DoF
 head) over one batch of synthetic 128x416 samples: 128 samples = 256 frame pairs
 per GPU (BASELINE.json configs[1]).  Under torchrun every rank runs its own batch
-(weak scaling) and the poses are all-gathered once per step over NCCL.
+(weak scaling) and the poses are all-gathered once per step over NCCL; started
+plainly with ``--gpus N`` > 1, bench.py re-launches itself under
+``torch.distributed.run`` with N ranks on 127.0.0.1.
 
 Prints ONE JSON line (rank 0).  ``value`` is device-resident throughput, ``e2e``
 the same metric through ``DAVO.inference`` with host numpy inputs (host<->device
@@ -544,6 +546,17 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="samples per GPU per step (2 frame pairs each)")
     ap.add_argument("--micro-batch", type=int, default=0, help="frame pairs per pass of the conv stack")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # started as plain `python bench.py --gpus N`: become the N-rank launch the contract describes
+        # (torch.distributed.run, one rank per GPU, rendezvous on 127.0.0.1)
+        import socket
+        import subprocess
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args)
     else:

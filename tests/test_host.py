@@ -527,3 +527,22 @@ def test_data_loader_mirrors_load_test_batch_flow(tmp_path):
         list(bad)
     with pytest.raises(ValueError):
         loader.load_test_batch_flow(names, poses, flows, depths, segs, decode="nvjpeg")      # needs a DAVO handle
+
+
+def test_bench_reference_arm_prints_one_contract_line_also_when_started_plainly_with_gpus_2():
+    """`python bench.py --impl reference --gpus 2` (no torchrun around it): bench.py becomes the 2-rank launch itself
+    (127.0.0.1 rendezvous), rank 0 alone times the CPU port and prints ONE JSON line with the contract's keys; the other
+    rank exits 0 without work."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("WORLD_SIZE", "RANK", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["warmup"] == 1
+    for key in ("metric", "value", "unit", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
