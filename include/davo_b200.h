@@ -45,7 +45,7 @@ typedef struct davo_config {
                             0 decouple_sharednet_v0_dilation (:189, headline), 1 couple_sharednet_v0_dilation (:133),
                             2 decouple_net_v0_dilation (:69), 3 couple_net_v0_dilation (:12),
                             4 couple_net_v0 (:257), 5 decouple_net_v0 (:314); 2-5 evaluate a whole sample at once */
-  int32_t cnv6_out;      /* "-cnv6_<n>", davo.py:1052-1053                             */
+  int32_t cnv6_out;      /* "-cnv6_<n>", davo.py:1052-1053: 32, 64, 128 or 256         */
   int32_t in_mode;       /* 0 = v0 RGB only, 1 = v1 RGB+flow, davo.py:1057-1065        */
   int32_t att_src;       /* 0 none, 1 se_flow (davo.py:1175), 2 static (:1390), 3 se_seg (:1304),
                             4 se_rgb -> seg (:1274), 5 se_depth -> seg (:1211),
