@@ -701,9 +701,11 @@ __device__ __forceinline__ void pack8_quad(const FrontParams& p, const float* s_
   for (int i = 0; i < 4; ++i) {
     const float mt = p.mask_rgb ? a_tgt[i] : 1.0f, ms = p.mask_rgb ? a_src[i] : 1.0f;
     const float mf = p.mask_flow ? a_src[i] : 1.0f;
-    q[2 * i + 0] = make_float4(round_tf32(tr[i] * mt), round_tf32(tg[i] * mt), round_tf32(tb[i] * mt),
-                               round_tf32(sr[i] * ms));
-    q[2 * i + 1] = make_float4(round_tf32(sg[i] * ms), round_tf32(sb[i] * ms), round_tf32(fx[i] * mf),
+    // image values are finite (bytes times class weights): the two-instruction form of the rounding, bit-equal to
+    // cvt.rna.tf32 on every finite float32 (tools/experiments/tf32_round.cu: all 2^32 patterns); the flow keeps cvt.rna
+    q[2 * i + 0] = make_float4(round_tf32_finite(tr[i] * mt), round_tf32_finite(tg[i] * mt), round_tf32_finite(tb[i] * mt),
+                               round_tf32_finite(sr[i] * ms));
+    q[2 * i + 1] = make_float4(round_tf32_finite(sg[i] * ms), round_tf32_finite(sb[i] * ms), round_tf32(fx[i] * mf),
                                round_tf32(fy[i] * mf));
   }
 }
